@@ -1,0 +1,110 @@
+/* b200mosaic.h -- C ABI of libb200mosaic.so (hand-written sm_100a CUDA; no torch / C++ types cross this line).
+ *
+ * The reference (PROcessorI/Real-Time-Video-Mosaic) has no FFI: its boundary for the stitching hot path is the
+ * Python class `VideMosaic` (/root/reference/main.py:15-112, 676-977) whose methods call OpenCV.  Each entry
+ * point below replaces one of those calls (cited per function); the Python mirror of the class
+ * (`real-time-video-mosaic_b200/mosaic.py`, ctypes) binds exactly these symbols.  See INTEGRATION.md.
+ *
+ * Conventions: all functions return bm_status (0 = OK, >0 = soft outcome of the reference's control flow,
+ * <0 = error; bm_last_error() gives the text).  No exceptions cross the ABI.  Pointers named d_* are DEVICE
+ * pointers in the current CUDA primary context (e.g. torch tensors' data_ptr()); h_* are HOST pointers.
+ * `stream` is a cudaStream_t passed as void* (NULL = default stream).  Images are row-major, tightly packed
+ * unless a stride is given; colour order is OpenCV's BGR.
+ */
+#ifndef B200MOSAIC_H
+#define B200MOSAIC_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    BM_OK = 0,
+    BM_SKIP_FEW_MATCHES = 1,   /* main.py:722-724  (<4 matches: frame skipped, state not advanced)        */
+    BM_SKIP_NO_H = 2,          /* main.py:729-731  (findHomography returned None)                          */
+    BM_REJECTED_IDENTITY = 3,  /* main.py:734-737  (validate_homography failed -> identity substituted)    */
+    BM_ERR_CUDA = -1,
+    BM_ERR_ARG = -2,
+    BM_ERR_UNSUPPORTED = -3
+} bm_status;
+
+enum { BM_DET_SIFT = 0, BM_DET_ORB = 1 };
+
+/* reasons reported by validate_homography (main.py:761-801), for the Python shim's prints */
+enum { BM_VAL_OK = 0, BM_VAL_NAN = 1, BM_VAL_TRANSLATION = 2, BM_VAL_SCALE = 3, BM_VAL_PERSPECTIVE = 4 };
+
+typedef struct bm_mosaic_s* bm_handle;
+
+typedef struct {
+    int frame_h, frame_w;      /* first_image.shape[:2]                       main.py:17          */
+    int canvas_h, canvas_w;    /* int(oht*H), int(owt*W) or an explicit size  main.py:80-81       */
+    int detector;              /* BM_DET_SIFT | BM_DET_ORB                    main.py:32-37       */
+    int nfeatures;             /* 700                                         main.py:33,36       */
+    int device;                /* CUDA device ordinal                                             */
+    int row_tile_y0;           /* canvas row-tile sharding (config 5): this handle owns canvas    */
+    int row_tile_y1;           /*   rows [y0,y1); 0,0 = whole canvas                              */
+} bm_config;
+
+typedef struct {
+    int status;                /* bm_status of the frame                                          */
+    int n_kp_cur, n_kp_prev;
+    int n_matches;
+    int ransac_iters;
+    int n_inliers;
+    int validate_reason;       /* BM_VAL_*                                                        */
+    int any_overlap;           /* np.any(overlap) of main.py:885                                  */
+    int win[4];                /* x0,y0,x1,y1 of the warped frame's bounding window on the canvas */
+    double validate_value;     /* translation px or scale, for the reference's warning text       */
+    double H_rel[9];           /* raw RANSAC result (before validation), main.py:727              */
+    double H[9];               /* absolute homography used for the warp,  main.py:746             */
+} bm_frame_info;
+
+const char* bm_last_error(void);
+int bm_version(void);
+
+/* ---- whole-path handle: VideMosaic.__init__ / process_frame / output_img ------------------------------ */
+bm_status bm_create(const bm_config* cfg, bm_handle* out);                       /* main.py:17-102 (minus YOLO)  */
+bm_status bm_destroy(bm_handle h);
+/* frame 0: features + paste at rows [Hc-H,Hc), cols [Wc/2-W/2,+W); H_old = translation.   main.py:78-94,104-112 */
+bm_status bm_first_frame(bm_handle h, const uint8_t* h_bgr, size_t stride_bytes);
+/* one process_frame (main.py:710-759): H2D, gray, detect, match, RANSAC, validate, smooth, compose, warp, blend */
+bm_status bm_process_frame(bm_handle h, const uint8_t* h_bgr, size_t stride_bytes, bm_frame_info* info);
+/* output_img (uint8, Hc x Wc x 3): lazy D2H of the device canvas                     main.py:1632,1649 */
+bm_status bm_get_canvas(bm_handle h, uint8_t* h_bgr_out);
+bm_status bm_get_state(bm_handle h, double H_old[9], int* history_len, double* history /* <=5*9 */);
+bm_status bm_set_stabilization(bm_handle h, int enabled, int history_size, double translation_threshold,
+                               double scale_threshold);                          /* main.py:97-101 */
+/* pinned staging memory a decoder can write into directly (cv2.VideoCapture stays on the host)           */
+bm_status bm_alloc_pinned(size_t bytes, void** out);
+bm_status bm_free_pinned(void* p);
+/* VideMosaic.warp(frame, H) on the handle's canvas (main.py:861-927): warpPerspective + blend, device canvas. */
+bm_status bm_warp_frame(bm_handle h, const uint8_t* h_bgr, size_t stride_bytes, const double H[9], bm_frame_info* info);
+/* same with the frame already resident on the device as packed BGRX (uchar4); used by the kernel-only bench leg */
+bm_status bm_warp_frame_device(bm_handle h, const uint8_t* d_bgrx, const double H[9], bm_frame_info* info);
+/* timing helpers: last warp/blend chain duration measured with CUDA events on the handle's stream (ms) */
+bm_status bm_sync(bm_handle h);
+void* bm_stream(bm_handle h);
+/* device pointer of the handle's current BGRX frame buffer after an upload (for the kernel-only bench leg) */
+bm_status bm_upload_frame(bm_handle h, const uint8_t* h_bgr, size_t stride_bytes, const uint8_t** d_bgrx_out);
+
+/* ---- stage entry points (parity tests call these with device buffers) --------------------------------- */
+/* cv2.cvtColor(BGR2GRAY)  main.py:111,717 ; also emits the BGRX copy the warp kernel samples (either may be NULL) */
+bm_status bm_ingest_bgr(const uint8_t* d_bgr, int h, int w, uint8_t* d_gray, uint8_t* d_bgrx, void* stream);
+/* cv2.warpPerspective(frame, H, (Wc,Hc), INTER_LINEAR)  main.py:871 ; d_dst is Hc x Wc x 3, fully written */
+bm_status bm_warp_perspective_bgr(const uint8_t* d_src_bgr, int sh, int sw, const double H[9],
+                                  uint8_t* d_dst_bgr, int dh, int dw, void* stream);
+/* cv2.distanceTransform(mask, DIST_L2, 3)  main.py:888-889 ; mask u8 (0 = zero pixel), out float32 */
+bm_status bm_distance_transform(const uint8_t* d_mask, int h, int w, float* d_out, void* stream);
+/* cv2.GaussianBlur(w, (31,31), 0) on float32  main.py:897-898 */
+bm_status bm_gaussian_blur31(const float* d_in, int h, int w, float* d_out, void* stream);
+/* the blend of VideMosaic.warp  main.py:878-927 : canvas (Hc x Wc x 3 u8, in/out) <- warped (Hc x Wc x 3 u8).
+ * win = optional x0,y0,x1,y1 bounding window of the non-zero part of `warped` (NULL = whole canvas).      */
+bm_status bm_blend_step_bgr(uint8_t* d_canvas_bgr, const uint8_t* d_warped_bgr, int dh, int dw,
+                            const int* win, int* any_overlap_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MOSAIC_H */

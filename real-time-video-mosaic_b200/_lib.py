@@ -1,0 +1,97 @@
+"""ctypes binding of libb200mosaic.so (the C ABI in include/b200mosaic.h).  No CPU fallback: if the library is
+missing or CUDA is unavailable every call raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "lib" / "libb200mosaic.so"
+
+BM_OK, BM_SKIP_FEW_MATCHES, BM_SKIP_NO_H, BM_REJECTED_IDENTITY = 0, 1, 2, 3
+BM_DET_SIFT, BM_DET_ORB = 0, 1
+BM_VAL_OK, BM_VAL_NAN, BM_VAL_TRANSLATION, BM_VAL_SCALE, BM_VAL_PERSPECTIVE = range(5)
+
+
+class BmConfig(C.Structure):
+    _fields_ = [("frame_h", C.c_int), ("frame_w", C.c_int), ("canvas_h", C.c_int), ("canvas_w", C.c_int),
+                ("detector", C.c_int), ("nfeatures", C.c_int), ("device", C.c_int),
+                ("row_tile_y0", C.c_int), ("row_tile_y1", C.c_int)]
+
+
+class BmFrameInfo(C.Structure):
+    _fields_ = [("status", C.c_int), ("n_kp_cur", C.c_int), ("n_kp_prev", C.c_int), ("n_matches", C.c_int),
+                ("ransac_iters", C.c_int), ("n_inliers", C.c_int), ("validate_reason", C.c_int),
+                ("any_overlap", C.c_int), ("win", C.c_int * 4), ("validate_value", C.c_double),
+                ("H_rel", C.c_double * 9), ("H", C.c_double * 9)]
+
+
+class B200MosaicError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def _sig(lib, name, restype, *argtypes):
+    f = getattr(lib, name)
+    f.restype = restype
+    f.argtypes = list(argtypes)
+    return f
+
+
+def load():
+    """Load the shared library (building it first if it is absent and nvcc is available)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        from . import build as _build
+        _build.build()
+    lib = C.CDLL(str(LIB_PATH))
+    vp, i, sz, dp = C.c_void_p, C.c_int, C.c_size_t, C.POINTER(C.c_double)
+    ip = C.POINTER(C.c_int)
+    _sig(lib, "bm_last_error", C.c_char_p)
+    _sig(lib, "bm_version", i)
+    _sig(lib, "bm_create", i, C.POINTER(BmConfig), C.POINTER(vp))
+    _sig(lib, "bm_destroy", i, vp)
+    _sig(lib, "bm_first_frame", i, vp, vp, sz)
+    _sig(lib, "bm_process_frame", i, vp, vp, sz, C.POINTER(BmFrameInfo))
+    _sig(lib, "bm_get_canvas", i, vp, vp)
+    _sig(lib, "bm_get_state", i, vp, dp, ip, dp)
+    _sig(lib, "bm_set_stabilization", i, vp, i, i, C.c_double, C.c_double)
+    _sig(lib, "bm_alloc_pinned", i, sz, C.POINTER(vp))
+    _sig(lib, "bm_free_pinned", i, vp)
+    _sig(lib, "bm_warp_frame", i, vp, vp, sz, dp, C.POINTER(BmFrameInfo))
+    _sig(lib, "bm_warp_frame_device", i, vp, vp, dp, C.POINTER(BmFrameInfo))
+    _sig(lib, "bm_sync", i, vp)
+    _sig(lib, "bm_stream", vp, vp)
+    _sig(lib, "bm_upload_frame", i, vp, vp, sz, C.POINTER(vp))
+    _sig(lib, "bm_ingest_bgr", i, vp, i, i, vp, vp, vp)
+    _sig(lib, "bm_warp_perspective_bgr", i, vp, i, i, dp, vp, i, i, vp)
+    _sig(lib, "bm_distance_transform", i, vp, i, i, vp, vp)
+    _sig(lib, "bm_gaussian_blur31", i, vp, i, i, vp, vp)
+    _sig(lib, "bm_blend_step_bgr", i, vp, vp, i, i, ip, ip, vp)
+    for name, args in _OPTIONAL.items():
+        if hasattr(lib, name):
+            _sig(lib, name, i, *args(vp, i, sz, dp, ip))
+    _lib = lib
+    return lib
+
+
+# symbols added by later build stages (declared in include/b200mosaic.h); bound when present
+_OPTIONAL = {}
+
+
+def check(status: int, what: str = "") -> int:
+    if status < 0:
+        msg = load().bm_last_error().decode("utf-8", "replace")
+        raise B200MosaicError(f"{what or 'libb200mosaic'} failed ({status}): {msg}")
+    return status
+
+
+def dbl9(H):
+    import numpy as np
+    a = np.ascontiguousarray(np.asarray(H, dtype=np.float64).reshape(9))
+    return a, a.ctypes.data_as(C.POINTER(C.c_double))

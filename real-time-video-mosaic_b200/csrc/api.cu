@@ -1,0 +1,399 @@
+// api.cu -- C ABI of libb200mosaic.so (see include/b200mosaic.h) and the per-mosaic device state.
+// Host-side control flow mirrors VideMosaic (/root/reference/main.py:17-112, 710-859); all pixel / feature work is
+// CUDA.  There is deliberately no CPU fallback: every entry point fails with BM_ERR_CUDA if the device is missing.
+#include "../../include/b200mosaic.h"
+#include "common.cuh"
+#include "ingest.cuh"
+#include "warp_blend.cuh"
+#include "pipeline.cuh"
+#include <stdarg.h>
+#include <string.h>
+#include <math.h>
+#include <new>
+
+static thread_local char g_err[512] = "";
+void bm_set_error(const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+extern "C" const char* bm_last_error(void) { return g_err; }
+extern "C" int bm_version(void) { return 100; }
+
+#define BM_TRY(expr) do { bm_status _s = (expr); if (_s < 0) return _s; } while (0)
+
+// ------------------------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------------------------
+static void free_blend(BmBlendBufs& b) {
+    cudaFree(b.canvas); cudaFree(b.g_old); cudaFree(b.gblk_old); cudaFree(b.wbuf); cudaFree(b.g_new); cudaFree(b.gblk_new);
+    cudaFree(b.rbuf); cudaFree(b.hbuf); cudaFree(b.flags); cudaFree(b.plan);
+    memset(&b, 0, sizeof(b));
+}
+
+static bm_status alloc_blend(BmBlendBufs& b, int canvas_h, int canvas_w, size_t scratch_px) {
+    memset(&b, 0, sizeof(b));
+    b.canvas_h = canvas_h; b.canvas_w = canvas_w;
+    const size_t n = (size_t)canvas_h * canvas_w;
+    const size_t nblk = (size_t)bm_div_up(canvas_h, BM_BLK_ROWS) * canvas_w;
+    if (scratch_px > n || scratch_px == 0) scratch_px = n;
+    b.scratch_px = scratch_px;
+    BM_CUDA_OK(cudaMalloc(&b.canvas, n * sizeof(uchar4)));
+    BM_CUDA_OK(cudaMalloc(&b.g_old, n * sizeof(uint16_t)));
+    BM_CUDA_OK(cudaMalloc(&b.gblk_old, nblk * sizeof(uint16_t)));
+    BM_CUDA_OK(cudaMalloc(&b.wbuf, scratch_px * sizeof(uchar4)));
+    BM_CUDA_OK(cudaMalloc(&b.g_new, scratch_px * sizeof(uint16_t)));
+    BM_CUDA_OK(cudaMalloc(&b.gblk_new, (scratch_px / BM_BLK_ROWS + (size_t)canvas_w + 64) * sizeof(uint16_t)));
+    BM_CUDA_OK(cudaMalloc(&b.rbuf, scratch_px * sizeof(float2)));
+    BM_CUDA_OK(cudaMalloc(&b.hbuf, scratch_px * sizeof(float2)));
+    BM_CUDA_OK(cudaMalloc(&b.flags, 16 * sizeof(int)));
+    BM_CUDA_OK(cudaMalloc(&b.plan, sizeof(BmFramePlan)));
+    BM_CUDA_OK(cudaMemset(b.canvas, 0, n * sizeof(uchar4)));
+    BM_CUDA_OK(cudaMemset(b.flags, 0, 16 * sizeof(int)));
+    return BM_OK;
+}
+
+struct bm_mosaic_s {
+    bm_config cfg;
+    cudaStream_t stream = nullptr;
+    BmBlendBufs blend;
+    // frame staging: double-buffered pinned host + device buffers
+    uint8_t* h_stage[2] = {nullptr, nullptr};
+    uint8_t* d_bgr[2] = {nullptr, nullptr};
+    uchar4* d_bgrx[2] = {nullptr, nullptr};
+    uint8_t* d_gray[2] = {nullptr, nullptr};
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
+    int cur = 0;
+    // canvas export
+    uint8_t* d_canvas_bgr = nullptr;
+    // stitcher state (main.py:92-102)
+    double H_old[9];
+    double history[5][9];
+    int history_len = 0;
+    int stabilization_enabled = 1, history_size = 5;
+    double translation_threshold = 50.0, scale_threshold = 0.3;
+    int w_offset = 0, h_offset = 0;
+    BmPipeline* pipe = nullptr;       // detector / matcher / RANSAC state (pipeline.cu)
+};
+
+static size_t frame_bytes(const bm_config& c) { return (size_t)c.frame_h * c.frame_w * 3; }
+
+extern "C" bm_status bm_create(const bm_config* cfg, bm_handle* out) {
+    if (!cfg || !out || cfg->frame_h <= 0 || cfg->frame_w <= 0 || cfg->canvas_h < cfg->frame_h || cfg->canvas_w < cfg->frame_w) {
+        bm_set_error("bm_create: bad config"); return BM_ERR_ARG;
+    }
+    if (cfg->detector != BM_DET_SIFT && cfg->detector != BM_DET_ORB) { bm_set_error("bm_create: detector must be sift|orb"); return BM_ERR_ARG; }
+    int ndev = 0;
+    BM_CUDA_OK(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) { bm_set_error("bm_create: no CUDA device %d", cfg->device); return BM_ERR_CUDA; }
+    BM_CUDA_OK(cudaSetDevice(cfg->device));
+    bm_mosaic_s* m = new (std::nothrow) bm_mosaic_s();
+    if (!m) return BM_ERR_ARG;
+    m->cfg = *cfg;
+    if (m->cfg.nfeatures <= 0) m->cfg.nfeatures = 700;
+    BM_CUDA_OK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    // scratch: the window of a frame is at most the canvas; typical is frame-sized.  Size for the whole canvas when
+    // it is small (<= 64 Mpx), otherwise for 4x the frame area plus margins (config 5: 32768^2 canvas, 4K frames).
+    const size_t canvas_px = (size_t)cfg->canvas_h * cfg->canvas_w;
+    size_t scratch = canvas_px;
+    if (canvas_px > ((size_t)64 << 20)) scratch = (size_t)4 * (cfg->frame_h + 64) * (cfg->frame_w + 64);
+    bm_status st = alloc_blend(m->blend, cfg->canvas_h, cfg->canvas_w, scratch);
+    if (st != BM_OK) { delete m; return st; }
+    const size_t fb = frame_bytes(*cfg), fpx = (size_t)cfg->frame_h * cfg->frame_w;
+    for (int i = 0; i < 2; ++i) {
+        BM_CUDA_OK(cudaHostAlloc(&m->h_stage[i], fb, cudaHostAllocDefault));
+        BM_CUDA_OK(cudaMalloc(&m->d_bgr[i], fb + 16));
+        BM_CUDA_OK(cudaMalloc(&m->d_bgrx[i], fpx * sizeof(uchar4)));
+        BM_CUDA_OK(cudaMalloc(&m->d_gray[i], fpx + 16));
+        BM_CUDA_OK(cudaEventCreateWithFlags(&m->ev_h2d[i], cudaEventDisableTiming));
+    }
+    BM_CUDA_OK(cudaMalloc(&m->d_canvas_bgr, canvas_px * 3 + 16));
+    for (int i = 0; i < 9; ++i) m->H_old[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    st = bm_pipeline_create(&m->pipe, m->cfg, m->stream);
+    if (st != BM_OK) { delete m; return st; }
+    *out = m;
+    return BM_OK;
+}
+
+extern "C" bm_status bm_destroy(bm_handle m) {
+    if (!m) return BM_OK;
+    cudaSetDevice(m->cfg.device);
+    cudaStreamSynchronize(m->stream);
+    bm_pipeline_destroy(m->pipe);
+    free_blend(m->blend);
+    for (int i = 0; i < 2; ++i) {
+        cudaFreeHost(m->h_stage[i]); cudaFree(m->d_bgr[i]); cudaFree(m->d_bgrx[i]); cudaFree(m->d_gray[i]);
+        if (m->ev_h2d[i]) cudaEventDestroy(m->ev_h2d[i]);
+    }
+    cudaFree(m->d_canvas_bgr);
+    cudaStreamDestroy(m->stream);
+    delete m;
+    return BM_OK;
+}
+
+// host frame -> device (BGR packed, BGRX, gray).  Pinned sources are copied directly; pageable ones are staged.
+static bm_status upload(bm_mosaic_s* m, const uint8_t* h_bgr, size_t stride, int slot) {
+    const int fh = m->cfg.frame_h, fw = m->cfg.frame_w;
+    const size_t rowb = (size_t)fw * 3, fb = rowb * fh;
+    if (stride == 0) stride = rowb;
+    const uint8_t* src = h_bgr;
+    cudaPointerAttributes attr;
+    bool pinned = false;
+    if (stride == rowb && cudaPointerGetAttributes(&attr, h_bgr) == cudaSuccess) pinned = (attr.type == cudaMemoryTypeHost);
+    else cudaGetLastError();
+    if (!pinned) {
+        // the staging slot may still be in flight from two frames ago
+        BM_CUDA_OK(cudaEventSynchronize(m->ev_h2d[slot]));
+        if (stride == rowb) memcpy(m->h_stage[slot], h_bgr, fb);
+        else for (int y = 0; y < fh; ++y) memcpy(m->h_stage[slot] + (size_t)y * rowb, h_bgr + (size_t)y * stride, rowb);
+        src = m->h_stage[slot];
+    }
+    BM_CUDA_OK(cudaMemcpyAsync(m->d_bgr[slot], src, fb, cudaMemcpyHostToDevice, m->stream));
+    BM_CUDA_OK(cudaEventRecord(m->ev_h2d[slot], m->stream));
+    BM_CUDA_OK(bm_launch_ingest(m->d_bgr[slot], fh, fw, m->d_gray[slot], m->d_bgrx[slot], m->stream));
+    return BM_OK;
+}
+
+extern "C" bm_status bm_first_frame(bm_handle m, const uint8_t* h_bgr, size_t stride) {
+    if (!m || !h_bgr) { bm_set_error("bm_first_frame: null"); return BM_ERR_ARG; }
+    BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+    const int fh = m->cfg.frame_h, fw = m->cfg.frame_w, ch = m->cfg.canvas_h, cw = m->cfg.canvas_w;
+    m->cur = 0;
+    BM_TRY(upload(m, h_bgr, stride, 0));
+    // main.py:86-87 (the reference's names are swapped: w_offset is the ROW offset)
+    m->w_offset = (int)((double)ch / 1 - (double)fh / 1);
+    m->h_offset = (int)((double)cw / 2 - (double)fw / 2);
+    BM_CUDA_OK(cudaMemsetAsync(m->blend.canvas, 0, (size_t)ch * cw * sizeof(uchar4), m->stream));
+    BM_CUDA_OK(bm_launch_paste(m->blend.canvas, cw, m->d_bgrx[0], fw, fh, m->h_offset, m->w_offset, m->stream));   // main.py:89-90
+    BM_CUDA_OK(bm_launch_full_rowscan(m->blend, m->stream));
+    for (int i = 0; i < 9; ++i) m->H_old[i] = (i % 4 == 0) ? 1.0 : 0.0;      // main.py:92-94
+    m->H_old[2] = m->h_offset; m->H_old[5] = m->w_offset;
+    m->history_len = 0;
+    BM_TRY(bm_pipeline_first_frame(m->pipe, m->d_gray[0]));                  // main.py:104-112
+    BM_CUDA_OK(cudaStreamSynchronize(m->stream));
+    return BM_OK;
+}
+
+static void fill_info_plan(bm_frame_info* info, const BmFramePlan& p) {
+    if (!info) return;
+    info->win[0] = p.win.x0; info->win[1] = p.win.y0; info->win[2] = p.win.x1; info->win[3] = p.win.y1;
+}
+
+static bm_status warp_device(bm_mosaic_s* m, const uchar4* d_bgrx, const double H[9], bm_frame_info* info, bool want_flag) {
+    BmFramePlan plan;
+    bm_make_plan(H, m->cfg.frame_w, m->cfg.frame_h, m->cfg.canvas_w, m->cfg.canvas_h, &plan);
+    const size_t need = (size_t)bm_win_w(plan.reg) * bm_win_h(plan.reg);
+    if (plan.valid && need > m->blend.scratch_px) { bm_set_error("warp window %zu px exceeds scratch %zu px", need, m->blend.scratch_px); return BM_ERR_UNSUPPORTED; }
+    BM_CUDA_OK(bm_launch_warp_blend(m->blend, d_bgrx, plan, m->stream));
+    fill_info_plan(info, plan);
+    if (info && want_flag) {
+        int f = 0;
+        if (plan.valid) BM_CUDA_OK(cudaMemcpyAsync(&f, m->blend.flags, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+        BM_CUDA_OK(cudaStreamSynchronize(m->stream));
+        info->any_overlap = f;
+    }
+    return BM_OK;
+}
+
+extern "C" bm_status bm_warp_frame(bm_handle m, const uint8_t* h_bgr, size_t stride, const double H[9], bm_frame_info* info) {
+    if (!m || !h_bgr || !H) { bm_set_error("bm_warp_frame: null"); return BM_ERR_ARG; }
+    BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+    m->cur ^= 1;
+    BM_TRY(upload(m, h_bgr, stride, m->cur));
+    if (info) { memset(info, 0, sizeof(*info)); memcpy(info->H, H, 9 * sizeof(double)); }
+    return warp_device(m, m->d_bgrx[m->cur], H, info, true);
+}
+
+extern "C" bm_status bm_warp_frame_device(bm_handle m, const uint8_t* d_bgrx, const double H[9], bm_frame_info* info) {
+    if (!m || !d_bgrx || !H) { bm_set_error("bm_warp_frame_device: null"); return BM_ERR_ARG; }
+    BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+    return warp_device(m, reinterpret_cast<const uchar4*>(d_bgrx), H, info, false);
+}
+
+extern "C" bm_status bm_upload_frame(bm_handle m, const uint8_t* h_bgr, size_t stride, const uint8_t** d_out) {
+    if (!m || !h_bgr) return BM_ERR_ARG;
+    BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+    m->cur ^= 1;
+    BM_TRY(upload(m, h_bgr, stride, m->cur));
+    if (d_out) *d_out = reinterpret_cast<const uint8_t*>(m->d_bgrx[m->cur]);
+    return BM_OK;
+}
+
+extern "C" bm_status bm_sync(bm_handle m) {
+    if (!m) return BM_ERR_ARG;
+    BM_CUDA_OK(cudaStreamSynchronize(m->stream));
+    return BM_OK;
+}
+extern "C" void* bm_stream(bm_handle m) { return m ? (void*)m->stream : nullptr; }
+
+extern "C" bm_status bm_get_canvas(bm_handle m, uint8_t* h_out) {
+    if (!m || !h_out) return BM_ERR_ARG;
+    BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+    const size_t n = (size_t)m->cfg.canvas_h * m->cfg.canvas_w;
+    BM_CUDA_OK(bm_launch_unpack_canvas(m->blend.canvas, m->d_canvas_bgr, (int)n, m->stream));
+    BM_CUDA_OK(cudaMemcpyAsync(h_out, m->d_canvas_bgr, n * 3, cudaMemcpyDeviceToHost, m->stream));
+    BM_CUDA_OK(cudaStreamSynchronize(m->stream));
+    return BM_OK;
+}
+
+extern "C" bm_status bm_get_state(bm_handle m, double H_old[9], int* history_len, double* history) {
+    if (!m) return BM_ERR_ARG;
+    if (H_old) memcpy(H_old, m->H_old, sizeof(m->H_old));
+    if (history_len) *history_len = m->history_len;
+    if (history) memcpy(history, m->history, sizeof(double) * 9 * m->history_len);
+    return BM_OK;
+}
+
+extern "C" bm_status bm_set_stabilization(bm_handle m, int enabled, int history_size, double tt, double st) {
+    if (!m || history_size < 1 || history_size > 5) return BM_ERR_ARG;
+    m->stabilization_enabled = enabled; m->history_size = history_size; m->translation_threshold = tt; m->scale_threshold = st;
+    return BM_OK;
+}
+
+extern "C" bm_status bm_alloc_pinned(size_t bytes, void** out) {
+    if (!out) return BM_ERR_ARG;
+    BM_CUDA_OK(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return BM_OK;
+}
+extern "C" bm_status bm_free_pinned(void* p) { BM_CUDA_OK(cudaFreeHost(p)); return BM_OK; }
+
+// ------------------------------------------------------------------------------------------------------------------
+// host control flow of process_frame: validate (main.py:761-801), smooth (:803-834), compose (:746)
+// ------------------------------------------------------------------------------------------------------------------
+static int validate_h(const bm_mosaic_s* m, const double* H, double* value) {
+    for (int i = 0; i < 9; ++i) if (isnan(H[i]) || isinf(H[i])) return BM_VAL_NAN;
+    const double tr = sqrt(H[2] * H[2] + H[5] * H[5]);
+    const double sc = sqrt(H[0] * H[4] - H[1] * H[3]);          // NaN for det < 0: both comparisons false (quirk A.11)
+    if (tr > m->translation_threshold) { if (value) *value = tr; return BM_VAL_TRANSLATION; }
+    if (fabs(sc - 1.0) > m->scale_threshold) { if (value) *value = sc; return BM_VAL_SCALE; }
+    if (fabs(H[6]) > 0.001 || fabs(H[7]) > 0.001) return BM_VAL_PERSPECTIVE;
+    return BM_VAL_OK;
+}
+
+static void smooth_h(bm_mosaic_s* m, const double* H, double* out) {
+    if (!m->stabilization_enabled) { memcpy(out, H, 72); return; }
+    if (m->history_len == m->history_size) { memmove(m->history[0], m->history[1], sizeof(double) * 9 * (m->history_size - 1)); m->history_len--; }
+    memcpy(m->history[m->history_len++], H, 72);
+    const int n = m->history_len;
+    if (n < 2) { memcpy(out, H, 72); return; }
+    double w[5], sum = 0.0;
+    for (int i = 0; i < n; ++i) {                                // np.linspace(0.5, 1.0, n): start + i*step, last = stop
+        const double step = (1.0 - 0.5) / (n - 1);
+        w[i] = (i == n - 1) ? 1.0 : 0.5 + i * step;
+        sum += w[i];
+    }
+    for (int k = 0; k < 9; ++k) out[k] = 0.0;
+    for (int i = 0; i < n; ++i) { const double wi = w[i] / sum; for (int k = 0; k < 9; ++k) out[k] += wi * m->history[i][k]; }
+}
+
+static void matmul3(const double* A, const double* B, double* C) {
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) {
+        double s = 0.0;
+        for (int k = 0; k < 3; ++k) s += A[3 * r + k] * B[3 * k + c];
+        C[3 * r + c] = s;
+    }
+}
+
+extern "C" bm_status bm_process_frame(bm_handle m, const uint8_t* h_bgr, size_t stride, bm_frame_info* info_out) {
+    if (!m || !h_bgr) { bm_set_error("bm_process_frame: null"); return BM_ERR_ARG; }
+    BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+    bm_frame_info info; memset(&info, 0, sizeof(info));
+    m->cur ^= 1;
+    const int slot = m->cur;
+    BM_TRY(upload(m, h_bgr, stride, slot));
+    // detect + match + RANSAC on the device; one small D2H read of (n_matches, H_rel) -- the reference's control
+    // flow (skip / reject prints) needs them on the host at this point anyway.
+    double H_rel[9]; int have_h = 0;
+    bm_status st = bm_pipeline_estimate(m->pipe, m->d_gray[slot], &info, H_rel, &have_h);
+    if (st < 0) { m->cur ^= 1; return st; }
+    if (info.n_matches < 4) { info.status = BM_SKIP_FEW_MATCHES; m->cur ^= 1; if (info_out) *info_out = info; return BM_SKIP_FEW_MATCHES; }
+    if (!have_h) { info.status = BM_SKIP_NO_H; m->cur ^= 1; if (info_out) *info_out = info; return BM_SKIP_NO_H; }
+    memcpy(info.H_rel, H_rel, 72);
+    double Hv[9]; memcpy(Hv, H_rel, 72);
+    info.validate_reason = validate_h(m, H_rel, &info.validate_value);
+    bm_status ret = BM_OK;
+    if (info.validate_reason != BM_VAL_OK) { for (int i = 0; i < 9; ++i) Hv[i] = (i % 4 == 0) ? 1.0 : 0.0; ret = BM_REJECTED_IDENTITY; }
+    double Hs[9], Habs[9];
+    smooth_h(m, Hv, Hs);
+    matmul3(m->H_old, Hs, Habs);
+    memcpy(info.H, Habs, 72);
+    BM_TRY(warp_device(m, m->d_bgrx[slot], Habs, &info, false));
+    memcpy(m->H_old, Habs, 72);
+    bm_pipeline_advance(m->pipe);                                     // kp_prev/des_prev <- cur (main.py:756-759)
+    info.status = ret;
+    if (info_out) *info_out = info;
+    return ret;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// stage entry points
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" bm_status bm_ingest_bgr(const uint8_t* d_bgr, int h, int w, uint8_t* d_gray, uint8_t* d_bgrx, void* stream) {
+    if (!d_bgr || h <= 0 || w <= 0) return BM_ERR_ARG;
+    BM_CUDA_OK(bm_launch_ingest(d_bgr, h, w, d_gray, reinterpret_cast<uchar4*>(d_bgrx), (cudaStream_t)stream));
+    return BM_OK;
+}
+
+extern "C" bm_status bm_warp_perspective_bgr(const uint8_t* d_src, int sh, int sw, const double H[9], uint8_t* d_dst, int dh, int dw, void* stream) {
+    if (!d_src || !d_dst || !H) return BM_ERR_ARG;
+    BmFramePlan plan;
+    bm_make_plan(H, sw, sh, dw, dh, &plan);
+    BM_CUDA_OK(bm_launch_warp_full_bgr(d_src, sh, sw, plan, d_dst, (cudaStream_t)stream));
+    return BM_OK;
+}
+
+extern "C" bm_status bm_distance_transform(const uint8_t* d_mask, int h, int w, float* d_out, void* stream) {
+    if (!d_mask || !d_out || h <= 0 || w <= 0) return BM_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    uint16_t *g = nullptr, *gb = nullptr;
+    BM_CUDA_OK(cudaMalloc(&g, (size_t)h * w * 2));
+    BM_CUDA_OK(cudaMalloc(&gb, (size_t)bm_div_up(h, BM_BLK_ROWS) * w * 2));
+    cudaError_t e = bm_launch_dt_mask(d_mask, h, w, d_out, g, gb, s);
+    cudaStreamSynchronize(s);
+    cudaFree(g); cudaFree(gb);
+    BM_CUDA_OK(e);
+    return BM_OK;
+}
+
+extern "C" bm_status bm_gaussian_blur31(const float* d_in, int h, int w, float* d_out, void* stream) {
+    if (!d_in || !d_out || h < 16 || w < 16) return BM_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    float* tmp = nullptr;
+    BM_CUDA_OK(cudaMalloc(&tmp, (size_t)h * w * 4));
+    cudaError_t e = bm_launch_blur31(d_in, h, w, tmp, d_out, s);
+    cudaStreamSynchronize(s);
+    cudaFree(tmp);
+    BM_CUDA_OK(e);
+    return BM_OK;
+}
+
+extern "C" bm_status bm_blend_step_bgr(uint8_t* d_canvas, const uint8_t* d_warped, int dh, int dw, const int* win, int* any_overlap, void* stream) {
+    if (!d_canvas || !d_warped || dh < 32 || dw < 32) return BM_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    BmBlendBufs b;
+    bm_status st = alloc_blend(b, dh, dw, 0);
+    if (st != BM_OK) { free_blend(b); return st; }
+    BmFramePlan plan; memset(&plan, 0, sizeof(plan));
+    plan.canvas_w = dw; plan.canvas_h = dh; plan.valid = 1; plan.block_w = 64;
+    BmWin w = {0, 0, dw, dh};
+    if (win) {   // grow by one pixel so that the window keeps a ring of zero pixels (see k_dt_weights)
+        w.x0 = win[0] - 1 < 0 ? 0 : win[0] - 1; w.y0 = win[1] - 1 < 0 ? 0 : win[1] - 1;
+        w.x1 = win[2] + 1 > dw ? dw : win[2] + 1; w.y1 = win[3] + 1 > dh ? dh : win[3] + 1;
+    }
+    plan.win = w;
+    plan.reg.x0 = w.x0 - BM_BLUR_R < 0 ? 0 : w.x0 - BM_BLUR_R; plan.reg.y0 = w.y0 - BM_BLUR_R < 0 ? 0 : w.y0 - BM_BLUR_R;
+    plan.reg.x1 = w.x1 + BM_BLUR_R > dw ? dw : w.x1 + BM_BLUR_R; plan.reg.y1 = w.y1 + BM_BLUR_R > dh ? dh : w.y1 + BM_BLUR_R;
+    cudaError_t e = cudaSuccess;
+    if (w.x1 > w.x0 && w.y1 > w.y0) {
+        e = bm_launch_pack_canvas(d_canvas, b.canvas, dh * dw, s);
+        if (e == cudaSuccess) e = bm_launch_full_rowscan(b, s);
+        if (e == cudaSuccess) e = bm_launch_extract_wbuf(d_warped, plan, b, s);
+        if (e == cudaSuccess) e = bm_launch_blend_from_wbuf(b, plan, s);
+        if (e == cudaSuccess) e = bm_launch_unpack_canvas(b.canvas, d_canvas, dh * dw, s);
+        int f = 0;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&f, b.flags, sizeof(int), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (any_overlap) *any_overlap = f;
+    }
+    free_blend(b);
+    BM_CUDA_OK(e);
+    return BM_OK;
+}

@@ -1,0 +1,42 @@
+// Shared declarations for the b200mosaic CUDA sources (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define BM_CHAMFER_A 62587          // cvRound(0.955f  * 65536), OpenCV distanceTransform DIST_L2 3x3
+#define BM_CHAMFER_B 89738          // cvRound(1.3693f * 65536)
+#define BM_DT_INIT 536870911        // INT_MAX >> 2 (OpenCV's INIT / DIST_MAX)
+#define BM_G_INF 0xFFFF             // "no zero pixel in this row"
+#define BM_BLK_ROWS 16              // rows per block of the pruning table
+#define BM_BLUR_R 15                // 31-tap Gaussian radius
+
+struct BmWin { int x0, y0, x1, y1; };   // half-open pixel rectangle in canvas coordinates
+static inline __host__ __device__ int bm_win_w(const BmWin& w) { return w.x1 - w.x0; }
+static inline __host__ __device__ int bm_win_h(const BmWin& w) { return w.y1 - w.y0; }
+
+// Per-frame parameters every kernel of the warp/blend chain reads from device memory, so that the chain can be
+// enqueued without a host round trip (the host mirrors them only to size the grids).
+struct BmFramePlan {
+    double M[9];        // inverse homography (canvas -> frame), cofactor form
+    BmWin win;          // W: clipped bounding box of the warped frame (+ zero ring)
+    BmWin reg;          // R: W dilated by the blur radius, clipped
+    int src_w, src_h;
+    int canvas_w, canvas_h;
+    int block_w;        // OpenCV's warpPerspective evaluation block width (64 for canvases >= 64 px wide)
+    int valid;          // 0 -> nothing to do this frame
+};
+
+extern "C" const char* bm_last_error(void);
+void bm_set_error(const char* fmt, ...);
+
+#define BM_CUDA_OK(expr)                                                                   \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            bm_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return BM_ERR_CUDA;                                                            \
+        }                                                                                  \
+    } while (0)
+
+static inline int bm_div_up(int a, int b) { return (a + b - 1) / b; }

@@ -1,0 +1,14 @@
+// pipeline.cuh -- per-frame feature pipeline (detect -> match -> RANSAC) behind bm_process_frame.
+#pragma once
+#include "../../include/b200mosaic.h"
+#include "common.cuh"
+
+struct BmPipeline;
+bm_status bm_pipeline_create(BmPipeline** out, const bm_config& cfg, cudaStream_t stream);
+void bm_pipeline_destroy(BmPipeline* p);
+// features of frame 0 become "prev" (main.py:104-112)
+bm_status bm_pipeline_first_frame(BmPipeline* p, const uint8_t* d_gray);
+// features of the current frame, matches against prev, RANSAC homography cur->prev (main.py:717-727)
+bm_status bm_pipeline_estimate(BmPipeline* p, const uint8_t* d_gray, bm_frame_info* info, double H_rel[9], int* have_h);
+// cur -> prev (main.py:756-759)
+void bm_pipeline_advance(BmPipeline* p);

@@ -1,0 +1,234 @@
+"""VideMosaic -- host-side mirror of the reference class (`/root/reference/main.py:15-112, 676-977`) over the C ABI.
+
+Same constructor, methods, attributes, prints and soft-failure behaviour as the reference for the stitching path;
+all pixel / feature arithmetic runs in libb200mosaic.so (hand-written sm_100a CUDA).  Out-of-scope methods of the
+reference class (`detect_objects`, ... -- YOLO, main.py:114-674) are delegated untouched to the reference class when
+one is registered with `VideMosaic.reference_class = main.VideMosaic` (see INTEGRATION.md / run.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class _KeyPoint:
+    """cv2.KeyPoint look-alike (attributes the reference reads: .pt; plus the rest of the cv2 fields)."""
+    __slots__ = ("pt", "size", "angle", "response", "octave", "class_id")
+
+    def __init__(self, x, y, size=0.0, angle=-1.0, response=0.0, octave=0, class_id=-1):
+        self.pt = (float(x), float(y))
+        self.size, self.angle, self.response, self.octave, self.class_id = size, angle, response, octave, class_id
+
+
+class DMatch:
+    """cv2.DMatch look-alike (queryIdx, trainIdx, distance; imgIdx = 0)."""
+    __slots__ = ("queryIdx", "trainIdx", "distance", "imgIdx")
+
+    def __init__(self, q, t, d):
+        self.queryIdx, self.trainIdx, self.distance, self.imgIdx = int(q), int(t), float(d), 0
+
+    def __repr__(self):
+        return f"DMatch(q={self.queryIdx}, t={self.trainIdx}, d={self.distance:g})"
+
+
+class VideMosaic:
+    reference_class = None      # set to the reference's own class to delegate detect_objects & co.
+
+    def __init__(self, first_image, output_height_times=2, output_width_times=1.2, detector_type="sift",
+                 show_intermediate=True, output_dir=None, visualize=True, *, canvas_size=None, device=0,
+                 nfeatures=700):
+        """Same positional/keyword arguments as main.py:17.  Extra keyword-only arguments: `canvas_size=(Hc,Wc)`
+        (explicit canvas, e.g. 32768x32768 of config 5, not expressible through the float multipliers), `device`."""
+        self.detector_type = detector_type
+        self.show_intermediate = show_intermediate
+        self.output_dir = output_dir
+        self.visualize = visualize
+        if detector_type not in ("sift", "orb"):
+            # the reference leaves self.detector undefined and fails later with AttributeError (main.py:32-37)
+            raise AttributeError("'VideMosaic' object has no attribute 'detector'")
+        first_image = self._check_frame(first_image)
+        fh, fw, fc = first_image.shape
+        if canvas_size is None:
+            ch, cw = int(output_height_times * fh), int(output_width_times * fw)      # main.py:80-81
+        else:
+            ch, cw = int(canvas_size[0]), int(canvas_size[1])
+        self._lib = _lib.load()
+        cfg = _lib.BmConfig(frame_h=fh, frame_w=fw, canvas_h=ch, canvas_w=cw,
+                            detector=_lib.BM_DET_SIFT if detector_type == "sift" else _lib.BM_DET_ORB,
+                            nfeatures=nfeatures, device=device, row_tile_y0=0, row_tile_y1=0)
+        self._h = C.c_void_p()
+        _lib.check(self._lib.bm_create(C.byref(cfg), C.byref(self._h)), "bm_create")
+        self._shape = (ch, cw, fc)
+        self._frame_shape = (fh, fw, fc)
+        self._canvas_cache = None
+        self.frame_prev = first_image
+        _lib.check(self._lib.bm_first_frame(self._h, first_image.ctypes.data_as(C.c_void_p), 0), "bm_first_frame")
+        self.w_offset = int(ch / 1 - fh / 1)                      # main.py:86 (row offset, names swapped upstream)
+        self.h_offset = int(cw / 2 - fw / 2)                      # main.py:87
+        self.H_old = np.eye(3)
+        self.H_old[0, 2] = self.h_offset
+        self.H_old[1, 2] = self.w_offset
+        self.H = None
+        self.stabilization_enabled = True                          # main.py:97-102
+        self.homography_history = []
+        self.history_size = 5
+        self.translation_threshold = 50
+        self.scale_threshold = 0.3
+        self.last_valid_H = np.eye(3)
+        self.last_info = None
+        self._ref_delegate = None
+
+    # ------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _check_frame(frame):
+        if not isinstance(frame, np.ndarray) or frame.ndim != 3 or frame.shape[2] != 3 or frame.dtype != np.uint8:
+            raise TypeError("frame must be an (H, W, 3) uint8 BGR ndarray (what cv2.VideoCapture.read returns)")
+        return np.ascontiguousarray(frame)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None and self._h.value:
+                self._lib.bm_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    close = __del__
+
+    # ---- output_img: lazy device->host copy, cached until the next frame -----------------------
+    @property
+    def output_img(self):
+        if self._canvas_cache is None:
+            out = np.empty(self._shape, dtype=np.uint8)
+            _lib.check(self._lib.bm_get_canvas(self._h, out.ctypes.data_as(C.c_void_p)), "bm_get_canvas")
+            self._canvas_cache = out
+        return self._canvas_cache
+
+    # ---- main.py:710-759 -------------------------------------------------------------------------------------
+    def process_frame(self, frame_cur, frame_count=0):
+        frame_cur = self._check_frame(frame_cur)
+        if frame_cur.shape != self._frame_shape:
+            raise ValueError(f"frame shape {frame_cur.shape} != first frame shape {self._frame_shape}")
+        self.frame_cur = frame_cur
+        self._sync_knobs()
+        info = _lib.BmFrameInfo()
+        st = _lib.check(self._lib.bm_process_frame(self._h, frame_cur.ctypes.data_as(C.c_void_p), 0, C.byref(info)),
+                        "bm_process_frame")
+        self.last_info = info
+        if st == _lib.BM_SKIP_FEW_MATCHES:
+            print(f"Предупреждение: Недостаточно совпадений ({info.n_matches}), пропуск кадра")          # :723
+            return
+        if st == _lib.BM_SKIP_NO_H:
+            print("Предупреждение: Не удалось вычислить гомографию, пропуск кадра")                      # :730
+            return
+        H_rel = np.array(info.H_rel, dtype=np.float64).reshape(3, 3)
+        if st == _lib.BM_REJECTED_IDENTITY:
+            self._print_validate(info.validate_reason, info.validate_value)
+            print("Предупреждение: Невалидная гомография (тряска/размытие), использую последнюю валидную")  # :735
+            H_used = np.eye(3)
+        else:
+            self.last_valid_H = H_rel.copy()
+            H_used = H_rel
+        self.homography_history.append(H_used.copy())
+        if len(self.homography_history) > self.history_size:
+            self.homography_history.pop(0)
+        self.H = np.array(info.H, dtype=np.float64).reshape(3, 3)
+        self.H_old = self.H
+        self.frame_prev = frame_cur
+        self._canvas_cache = None
+
+    def _sync_knobs(self):
+        _lib.check(self._lib.bm_set_stabilization(self._h, int(bool(self.stabilization_enabled)), int(self.history_size),
+                                                  float(self.translation_threshold), float(self.scale_threshold)))
+
+    @staticmethod
+    def _print_validate(reason, value):
+        if reason == _lib.BM_VAL_TRANSLATION:
+            print(f"Предупреждение: Обнаружено большое смещение ({value:.1f}px), возможна тряска")        # :788
+        elif reason == _lib.BM_VAL_SCALE:
+            print(f"Предупреждение: Обнаружено большое изменение масштаба ({value:.2f}), возможна тряска")  # :793
+        elif reason == _lib.BM_VAL_PERSPECTIVE:
+            print("Предупреждение: Обнаружены сильные перспективные искажения")                           # :798
+
+    # ---- main.py:761-801 (NumPy mirror for direct callers; the frame loop uses the native copy) -------------
+    def validate_homography(self, H):
+        if H is None:
+            return False
+        if np.any(np.isnan(H)) or np.any(np.isinf(H)):
+            return False
+        translation = np.sqrt(H[0, 2] ** 2 + H[1, 2] ** 2)
+        with np.errstate(invalid="ignore"):
+            scale = np.sqrt(np.linalg.det(H[:2, :2]))
+        if translation > self.translation_threshold:
+            self._print_validate(_lib.BM_VAL_TRANSLATION, translation)
+            return False
+        if abs(scale - 1.0) > self.scale_threshold:
+            self._print_validate(_lib.BM_VAL_SCALE, scale)
+            return False
+        if abs(H[2, 0]) > 0.001 or abs(H[2, 1]) > 0.001:
+            self._print_validate(_lib.BM_VAL_PERSPECTIVE, 0.0)
+            return False
+        return True
+
+    # ---- main.py:803-834 ---------------------------------------------------------------------------------------
+    def smooth_homography(self, H):
+        if not self.stabilization_enabled:
+            return H
+        self.homography_history.append(H.copy())
+        if len(self.homography_history) > self.history_size:
+            self.homography_history.pop(0)
+        if len(self.homography_history) < 2:
+            return H
+        weights = np.linspace(0.5, 1.0, len(self.homography_history))
+        weights = weights / np.sum(weights)
+        out = np.zeros_like(H)
+        for w, h in zip(weights, self.homography_history):
+            out += w * h
+        return out
+
+    # ---- main.py:861-936 ---------------------------------------------------------------------------------------
+    def warp(self, frame_cur, H):
+        frame_cur = self._check_frame(frame_cur)
+        _a, hp = _lib.dbl9(H)
+        info = _lib.BmFrameInfo()
+        _lib.check(self._lib.bm_warp_frame(self._h, frame_cur.ctypes.data_as(C.c_void_p), 0, hp, C.byref(info)),
+                   "bm_warp_frame")
+        self.last_info = info
+        self._canvas_cache = None
+        if self.visualize:                                         # display tail, main.py:929-934 (host, optional)
+            import cv2
+            tmp = self.draw_border(np.copy(self.output_img), self.get_transformed_corners(frame_cur, np.asarray(H)),
+                                   color=(0, 0, 255))
+            cv2.namedWindow('output', cv2.WINDOW_NORMAL)
+            cv2.imshow('output', tmp / 255.)
+        return self.output_img
+
+    @staticmethod
+    def get_transformed_corners(frame_cur, H):                     # main.py:938-962 (4 points, host)
+        h, w = frame_cur.shape[:2]
+        pts = np.array([[0, 0, 1], [w, 0, 1], [w, h, 1], [0, h, 1]], dtype=np.float64).T
+        q = np.asarray(H, dtype=np.float64) @ pts
+        q = (q[:2] / q[2]).T.astype(np.float32)
+        return np.array(q[None], dtype=np.int32)
+
+    def draw_border(self, image, corners, color=(0, 0, 0)):       # main.py:964-977 (display only)
+        import cv2
+        for i in range(corners.shape[1] - 1, -1, -1):
+            cv2.line(image, tuple(int(v) for v in corners[0, i, :]), tuple(int(v) for v in corners[0, i - 1, :]),
+                     thickness=5, color=color)
+        return image
+
+    # ---- out-of-scope methods stay on the reference's path -----------------------------------------------------
+    def __getattr__(self, name):
+        # only called for attributes that are not found normally
+        if name.startswith("_") or VideMosaic.reference_class is None:
+            raise AttributeError(f"'VideMosaic' object has no attribute '{name}'")
+        d = self.__dict__.get("_ref_delegate")
+        if d is None:
+            d = VideMosaic.reference_class(np.ascontiguousarray(self.frame_prev[:64, :64]), detector_type="orb",
+                                           show_intermediate=False, output_dir=self.output_dir, visualize=False)
+            self.__dict__["_ref_delegate"] = d
+        return getattr(d, name)
