@@ -1,0 +1,217 @@
+"""Restatement of cv2.findHomography(p_cur, p_prev, cv2.RANSAC, 2.0) as the reference calls it (main.py:856-857)
+(TEST INFRASTRUCTURE, see oracle/__init__.py).  OpenCV 4.x calib3d: RANSACPointSetRegistrator::run +
+HomographyEstimatorCallback + LMSolver refinement, from the published sources as pinned in SURVEY.md A.7; checked
+against live cv2 4.13 in tests/test_oracle_ransac_cpu.py."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+FLT_EPSILON = 1.1920929e-07
+DBL_EPSILON = 2.220446049250313e-16
+
+
+class CvRNG:
+    """cv::RNG multiply-with-carry generator, seeded with (uint64)-1 as RANSACPointSetRegistrator does."""
+
+    def __init__(self, state=0xFFFFFFFFFFFFFFFF):
+        self.state = state
+
+    def next(self):
+        self.state = ((self.state & 0xFFFFFFFF) * 4164903690 + (self.state >> 32)) & 0xFFFFFFFFFFFFFFFF
+        return self.state & 0xFFFFFFFF
+
+    def uniform(self, a, b):
+        return a if a == b else int(self.next() % (b - a) + a)
+
+
+def _collinear(p):
+    i = len(p) - 1
+    for j in range(i):
+        dx1 = float(p[j][0]) - float(p[i][0]); dy1 = float(p[j][1]) - float(p[i][1])
+        for k in range(j):
+            dx2 = float(p[k][0]) - float(p[i][0]); dy2 = float(p[k][1]) - float(p[i][1])
+            if abs(dx2 * dy1 - dy2 * dx1) <= FLT_EPSILON * (abs(dx1) + abs(dy1) + abs(dx2) + abs(dy2)):
+                return True
+    return False
+
+
+def _det3(p, t):
+    a = np.array([[p[t[0]][0], p[t[0]][1], 1.0], [p[t[1]][0], p[t[1]][1], 1.0], [p[t[2]][0], p[t[2]][1], 1.0]], dtype=np.float64)
+    return (a[0, 0] * (a[1, 1] * a[2, 2] - a[1, 2] * a[2, 1]) - a[0, 1] * (a[1, 0] * a[2, 2] - a[1, 2] * a[2, 0])
+            + a[0, 2] * (a[1, 0] * a[2, 1] - a[1, 1] * a[2, 0]))
+
+
+def check_subset(s1, s2):
+    if _collinear(s1) or _collinear(s2):
+        return False
+    neg = 0
+    for t in ((0, 1, 2), (1, 2, 3), (0, 2, 3), (0, 1, 3)):
+        neg += (_det3(s1, t) * _det3(s2, t)) < 0
+    return neg in (0, 4)
+
+
+def get_subset(rng, src, dst, max_attempts=10000):
+    n = len(src)
+    for _ in range(max_attempts):
+        idx = []
+        for i in range(4):
+            v = rng.uniform(0, n)
+            while v in idx:
+                v = rng.uniform(0, n)
+            idx.append(v)
+        if check_subset(src[idx], dst[idx]):
+            return idx
+    return None
+
+
+def run_kernel(M, m):
+    """HomographyEstimatorCallback::runKernel: normalised DLT, smallest eigenvector of LtL.  M -> m.  Returns 3x3 or None."""
+    M = M.astype(np.float64); m = m.astype(np.float64)
+    n = len(M)
+    cM = M.sum(0) / n; cm = m.sum(0) / n
+    sM = np.abs(M - cM).sum(0); sm = np.abs(m - cm).sum(0)
+    if (np.abs(np.concatenate([sM, sm])) < DBL_EPSILON).any():
+        return None
+    sM = n / sM; sm = n / sm
+    invHnorm = np.array([[1.0 / sm[0], 0, cm[0]], [0, 1.0 / sm[1], cm[1]], [0, 0, 1]])
+    Hnorm2 = np.array([[sM[0], 0, -cM[0] * sM[0]], [0, sM[1], -cM[1] * sM[1]], [0, 0, 1]])
+    x = (m[:, 0] - cm[0]) * sm[0]; y = (m[:, 1] - cm[1]) * sm[1]
+    X = (M[:, 0] - cM[0]) * sM[0]; Y = (M[:, 1] - cM[1]) * sM[1]
+    one = np.ones(n); zero = np.zeros(n)
+    Lx = np.stack([X, Y, one, zero, zero, zero, -x * X, -x * Y, -x], 1)
+    Ly = np.stack([zero, zero, zero, X, Y, one, -y * X, -y * Y, -y], 1)
+    LtL = Lx.T @ Lx + Ly.T @ Ly
+    w, V = np.linalg.eigh(LtL)
+    H0 = V[:, 0].reshape(3, 3)
+    H = invHnorm @ H0 @ Hnorm2
+    return H / H[2, 2]
+
+
+def reproj_err_f32(H, M, m):
+    Hf = H.astype(np.float32).ravel()
+    Mx, My = M[:, 0].astype(np.float32), M[:, 1].astype(np.float32)
+    ww = np.float32(1.0) / (Hf[6] * Mx + Hf[7] * My + np.float32(1.0))
+    dx = (Hf[0] * Mx + Hf[1] * My + Hf[2]) * ww - m[:, 0].astype(np.float32)
+    dy = (Hf[3] * Mx + Hf[4] * My + Hf[5]) * ww - m[:, 1].astype(np.float32)
+    return dx * dx + dy * dy
+
+
+def update_num_iters(p, ep, model_points, max_iters):
+    p = min(max(p, 0.0), 1.0); ep = min(max(ep, 0.0), 1.0)
+    num = max(1.0 - p, 2.2250738585072014e-308)
+    denom = 1.0 - (1.0 - ep) ** model_points
+    if denom < 2.2250738585072014e-308:
+        return 0
+    num = math.log(num); denom = math.log(denom)
+    if denom >= 0 or -num >= max_iters * (-denom):
+        return max_iters
+    return int(np.rint(num / denom))
+
+
+def lm_refine(H, M, m, max_iters=10):
+    """LMSolver (calib3d levmarq.cpp) on the 8 free parameters with HomographyRefineCallback residuals."""
+    M = M.astype(np.float64); m = m.astype(np.float64)
+
+    def compute(h, want_j):
+        ww = 1.0 / (h[6] * M[:, 0] + h[7] * M[:, 1] + 1.0)
+        xi = (h[0] * M[:, 0] + h[1] * M[:, 1] + h[2]) * ww
+        yi = (h[3] * M[:, 0] + h[4] * M[:, 1] + h[5]) * ww
+        r = np.empty(2 * len(M)); r[0::2] = xi - m[:, 0]; r[1::2] = yi - m[:, 1]
+        if not want_j:
+            return r, None
+        J = np.zeros((2 * len(M), 8))
+        J[0::2, 0] = M[:, 0] * ww; J[0::2, 1] = M[:, 1] * ww; J[0::2, 2] = ww
+        J[0::2, 6] = -M[:, 0] * ww * xi; J[0::2, 7] = -M[:, 1] * ww * xi
+        J[1::2, 3] = M[:, 0] * ww; J[1::2, 4] = M[:, 1] * ww; J[1::2, 5] = ww
+        J[1::2, 6] = -M[:, 0] * ww * yi; J[1::2, 7] = -M[:, 1] * ww * yi
+        return r, J
+
+    x = H.ravel()[:8].copy()
+    r, J = compute(x, True)
+    S = float(r @ r)
+    A = J.T @ J; v = J.T @ r
+    D = np.diag(A).copy()
+    Rlo, Rhi = 0.25, 0.75
+    lam, lc = 1.0, 0.75
+    it = 0
+    while True:
+        Ap = A + np.diag(lam * D)
+        d = np.linalg.solve(Ap, v)
+        xd = x - d
+        rd, _ = compute(xd, False)
+        Sd = float(rd @ rd)
+        temp = -(A @ d) + 2.0 * v
+        dS = float(d @ temp)
+        R = (S - Sd) / (dS if abs(dS) > DBL_EPSILON else 1.0)
+        if R > Rhi:
+            lam *= 0.5
+            if lam < lc:
+                lam = 0.0
+        elif R < Rlo:
+            t = float(d @ v)
+            nu = (Sd - S) / (t if abs(t) > DBL_EPSILON else 1.0) + 2.0
+            nu = min(max(nu, 2.0), 10.0)
+            if lam == 0.0:
+                Ai = np.linalg.inv(A)
+                maxval = max(DBL_EPSILON, float(np.abs(np.diag(Ai)).max()))
+                lam = lc = 1.0 / maxval
+                nu *= 0.5
+            lam *= nu
+        if Sd < S:
+            S = Sd
+            x = xd
+            r, J = compute(x, True)
+            A = J.T @ J; v = J.T @ r
+        it += 1
+        if not (it < max_iters and np.abs(d).max() >= FLT_EPSILON and np.abs(r).max() >= FLT_EPSILON):
+            break
+    out = np.ones(9); out[:8] = x
+    return out.reshape(3, 3)
+
+
+def find_homography_ransac(src, dst, thresh=2.0, max_iters=2000, confidence=0.995, return_trace=False):
+    """src, dst: (n,2) float32 (cur -> prev).  Returns H (3x3 float64) or None; with return_trace also the RANSAC
+    trace (accepted subsets in order, inlier counts, iterations run, inlier mask of the winning hypothesis)."""
+    src = np.asarray(src, dtype=np.float32).reshape(-1, 2); dst = np.asarray(dst, dtype=np.float32).reshape(-1, 2)
+    n = len(src)
+    trace = {"subsets": [], "good": [], "iters": 0}
+    if n < 4:
+        return (None, trace) if return_trace else None
+    if n == 4:
+        H = run_kernel(src, dst)
+        return (H, trace) if return_trace else H
+    rng = CvRNG()
+    niters = max(max_iters, 1)
+    best_good, best_H, best_mask = 0, None, None
+    it = 0
+    t2 = thresh * thresh
+    while it < niters:
+        idx = get_subset(rng, src, dst)
+        if idx is None:
+            if it == 0:
+                return (None, trace) if return_trace else None
+            break
+        Hs = run_kernel(src[idx], dst[idx])
+        trace["subsets"].append(idx)
+        if Hs is not None:
+            mask = reproj_err_f32(Hs, src, dst) <= np.float32(t2)
+            good = int(mask.sum())
+            trace["good"].append(good)
+            if good > max(best_good, 3):
+                best_good, best_H, best_mask = good, Hs, mask
+                niters = update_num_iters(confidence, (n - good) / n, 4, niters)
+        else:
+            trace["good"].append(-1)
+        it += 1
+    trace["iters"] = it
+    if best_good <= 0:
+        return (None, trace) if return_trace else None
+    trace["mask"] = best_mask
+    s1, d1 = src[best_mask], dst[best_mask]
+    H = run_kernel(s1, d1)
+    if H is None:
+        H = best_H
+    H = lm_refine(H, s1, d1)
+    return (H, trace) if return_trace else H
