@@ -104,6 +104,29 @@ bm_status bm_gaussian_blur31(const float* d_in, int h, int w, float* d_out, void
 bm_status bm_blend_step_bgr(uint8_t* d_canvas_bgr, const uint8_t* d_warped_bgr, int dh, int dw,
                             const int* win, int* any_overlap_out, void* stream);
 
+/* ---- feature / matching / RANSAC stage entry points (small host arrays; parity tests + the Python mirror) ---------- */
+/* cv2.ORB_create(n).detectAndCompute(gray, None)  main.py:36,112,718.  h_kp rows: x, y, size, angle, response, octave
+ * (float32 x 6); h_desc: n x 32 uint8.  Order: level-major, row-major inside a level (cv2's order is nth_element's). */
+bm_status bm_orb_detect_and_compute(const uint8_t* d_gray, int h, int w, int nfeatures, float* h_kp, uint8_t* h_desc,
+                                    int cap, int* n_out);
+/* cv2.SIFT_create(n).detectAndCompute(gray, None)  main.py:33,112,718.  h_desc: n x 128 float32 (integer valued). */
+bm_status bm_sift_detect_and_compute(const uint8_t* d_gray, int h, int w, int nfeatures, float* h_kp, float* h_desc,
+                                     int cap, int* n_out);
+/* BFMatcher(NORM_HAMMING, crossCheck=True).match + sorted(key=distance)  main.py:694-698 */
+bm_status bm_match_hamming_crosscheck(const uint8_t* h_des_q, int nq, const uint8_t* h_des_t, int nt,
+                                      int* h_q, int* h_t, float* h_dist, int* m_out);
+/* BFMatcher().knnMatch(k=2) + ratio test (double compare) + sorted(key=distance)  main.py:687-698 */
+bm_status bm_match_l2_knn2_ratio(const float* h_des_q, int nq, const float* h_des_t, int nt, double ratio,
+                                 int* h_q, int* h_t, float* h_dist, int* m_out);
+/* cv2.findHomography(src, dst, cv2.RANSAC, thresh) (maxIters, confidence explicit)  main.py:856-857.
+ * h_src/h_dst: n x 2 float32.  *ok = 0 means the reference would get None. */
+bm_status bm_ransac_homography(const float* h_src, const float* h_dst, int n, double thresh, int max_iters,
+                               double confidence, double H[9], int* ok, int* iters, int* n_inliers);
+/* features / matches of the handle's last frame: which = 0 -> prev, 1 -> cur.  h_desc: uint8 n x 32 (ORB) or n x 128 (SIFT) */
+bm_status bm_get_keypoints(bm_handle h, int which, float* h_kp, uint8_t* h_desc, int cap, int* n_out);
+bm_status bm_get_matches(bm_handle h, int* h_q, int* h_t, float* h_dist, int cap, int* m_out);
+int bm_keypoint_capacity(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,15 +73,17 @@ def load():
     _sig(lib, "bm_distance_transform", i, vp, i, i, vp, vp)
     _sig(lib, "bm_gaussian_blur31", i, vp, i, i, vp, vp)
     _sig(lib, "bm_blend_step_bgr", i, vp, vp, i, i, ip, ip, vp)
-    for name, args in _OPTIONAL.items():
-        if hasattr(lib, name):
-            _sig(lib, name, i, *args(vp, i, sz, dp, ip))
+    fp = C.POINTER(C.c_float)
+    _sig(lib, "bm_orb_detect_and_compute", i, vp, i, i, i, vp, vp, i, ip)
+    _sig(lib, "bm_sift_detect_and_compute", i, vp, i, i, i, vp, vp, i, ip)
+    _sig(lib, "bm_match_hamming_crosscheck", i, vp, i, vp, i, vp, vp, vp, ip)
+    _sig(lib, "bm_match_l2_knn2_ratio", i, vp, i, vp, i, C.c_double, vp, vp, vp, ip)
+    _sig(lib, "bm_ransac_homography", i, vp, vp, i, C.c_double, i, C.c_double, dp, ip, ip, ip)
+    _sig(lib, "bm_get_keypoints", i, vp, i, vp, vp, i, ip)
+    _sig(lib, "bm_get_matches", i, vp, vp, vp, vp, i, ip)
+    _sig(lib, "bm_keypoint_capacity", i)
     _lib = lib
     return lib
-
-
-# symbols added by later build stages (declared in include/b200mosaic.h); bound when present
-_OPTIONAL = {}
 
 
 def check(status: int, what: str = "") -> int:

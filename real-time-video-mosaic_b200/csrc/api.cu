@@ -323,6 +323,35 @@ extern "C" bm_status bm_process_frame(bm_handle m, const uint8_t* h_bgr, size_t 
     return ret;
 }
 
+// features / matches of the last frame
+#include "orb.cuh"
+#include "match.cuh"
+bm_status bm_download_keypoints(const BmKeypoints& k, int desc_bytes, float* h_kp, uint8_t* h_desc, int cap, int* n_out, cudaStream_t s);
+
+extern "C" bm_status bm_get_keypoints(bm_handle m, int which, float* h_kp, uint8_t* h_desc, int cap, int* n_out) {
+    if (!m) return BM_ERR_ARG;
+    BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+    return bm_download_keypoints(*bm_pipeline_keypoints(m->pipe, which), m->cfg.detector == BM_DET_ORB ? 32 : 128, h_kp, h_desc, cap, n_out, m->stream);
+}
+
+extern "C" bm_status bm_get_matches(bm_handle m, int* h_q, int* h_t, float* h_dist, int cap, int* m_out) {
+    if (!m) return BM_ERR_ARG;
+    BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+    BmMatches* mm = bm_pipeline_matches(m->pipe);
+    int M = 0;
+    BM_CUDA_OK(cudaMemcpyAsync(&M, mm->count, 4, cudaMemcpyDeviceToHost, m->stream));
+    BM_CUDA_OK(cudaStreamSynchronize(m->stream));
+    if (M > cap) { bm_set_error("match buffer too small"); return BM_ERR_ARG; }
+    if (M > 0) {
+        BM_CUDA_OK(cudaMemcpyAsync(h_q, mm->q, M * 4, cudaMemcpyDeviceToHost, m->stream));
+        BM_CUDA_OK(cudaMemcpyAsync(h_t, mm->t, M * 4, cudaMemcpyDeviceToHost, m->stream));
+        BM_CUDA_OK(cudaMemcpyAsync(h_dist, mm->dist, M * 4, cudaMemcpyDeviceToHost, m->stream));
+        BM_CUDA_OK(cudaStreamSynchronize(m->stream));
+    }
+    if (m_out) *m_out = M;
+    return BM_OK;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // stage entry points
 // ------------------------------------------------------------------------------------------------------------------

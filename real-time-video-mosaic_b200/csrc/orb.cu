@@ -1,0 +1,448 @@
+// orb.cu -- cv2.ORB_create(700).detectAndCompute on the device, bit-exact (reference call sites: main.py:36,112,718).
+// Spec: SURVEY.md A.2-A.4 (OpenCV 4.x ORB_Impl, FAST-9/16, INTER_LINEAR_EXACT), restated and pinned in oracle/orb.py.
+//
+// B200 design: all 8 pyramid levels live in one buffer and every stage is ONE launch over all levels
+// (except the resize chain, which is inherently sequential level to level):
+//   resize chain (8.8 fixed point)            -> pyr
+//   FAST-9 score map (bitmask arc test)       -> score (u8)
+//   3x3 NMS + border filter                   -> candidate list via per-warp ballot/popc compaction + 256-bin histograms
+//   retainBest(2q) by FAST score              -> exact threshold from the histogram (scores are integers <= 254)
+//   Harris on survivors                       -> second compaction
+//   retainBest(q) by Harris (ties kept)       -> O(n^2) rank count per level, deterministic (y,x) ordering
+//   IC angle (warp per keypoint)              -> fastAtan2 in non-contracted float32
+//   fused patch blur + rBRIEF                 -> the 7x7 sigma-2 Gaussian is evaluated only on the 37x37 patch around
+//                                                each keypoint (in shared memory) instead of blurring every level
+#include "orb.cuh"
+#include "orb_pattern.cuh"
+#include <math.h>
+#include <string.h>
+#include <new>
+
+#define FAST_THR 20
+#define ORB_EDGE 31
+
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_resize_exact(const uint8_t* __restrict__ src, int sw, int sh, uint8_t* __restrict__ dst, int dw, int dh) {
+    const int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (dx >= dw || dy >= dh) return;
+    const double scx = (double)sw / (double)dw, scy = (double)sh / (double)dh;
+    double fx = __dadd_rn(__dmul_rn((double)dx + 0.5, scx), -0.5);
+    double fy = __dadd_rn(__dmul_rn((double)dy + 0.5, scy), -0.5);
+    int sx = (int)floor(fx), sy = (int)floor(fy);
+    double ax = fx - (double)sx, ay = fy - (double)sy;
+    if (sx < 0) { sx = 0; ax = 0.0; }
+    if (sx >= sw - 1) { sx = sw - 1; ax = 0.0; }
+    if (sy < 0) { sy = 0; ay = 0.0; }
+    if (sy >= sh - 1) { sy = sh - 1; ay = 0.0; }
+    const int a8 = __double2int_rn(ax * 256.0), b8 = __double2int_rn(ay * 256.0);
+    const int sx1 = min(sx + 1, sw - 1), sy1 = min(sy + 1, sh - 1);
+    const uint8_t* r0 = src + (size_t)sy * sw;
+    const uint8_t* r1 = src + (size_t)sy1 * sw;
+    const unsigned h0 = r0[sx] * (256 - a8) + r0[sx1] * a8;
+    const unsigned h1 = r1[sx] * (256 - a8) + r1[sx1] * a8;
+    dst[(size_t)dy * dw + dx] = (uint8_t)((h0 * (unsigned)(256 - b8) + h1 * (unsigned)b8 + 32768u) >> 16);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool has9(unsigned m) {
+    m |= m << 16;
+    unsigned r = m & (m >> 1);
+    r &= r >> 2;
+    r &= r >> 4;
+    r &= m >> 8;
+    return (r & 0xffffu) != 0;
+}
+
+// level / tile decode shared by the per-pixel kernels: blockIdx.y = level, blockIdx.x = tile of a 32x8 grid
+__device__ __forceinline__ bool tile_xy(const BmOrbLevel& L, int& x, int& y) {
+    const int tiles_x = (L.w + 31) >> 5;
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    x = tx * 32 + threadIdx.x;
+    y = ty * 8 + threadIdx.y;
+    return ty * 8 < L.h;
+}
+
+__global__ void __launch_bounds__(256) k_fast_score(BmOrbLevels lv, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ score) {
+    const BmOrbLevel L = lv.l[blockIdx.y];
+    int x, y;
+    if (!tile_xy(L, x, y)) return;
+    if (x >= L.w || y >= L.h) return;
+    const uint8_t* img = pyr + L.off;
+    int s = 0;
+    if (x >= 3 && y >= 3 && x < L.w - 3 && y < L.h - 3) {
+        const uint8_t* p = img + (size_t)y * L.w + x;
+        const int w = L.w;
+        const int c = p[0];
+        int d[16];
+        d[0] = c - p[3 * w];          d[1] = c - p[3 * w + 1];   d[2] = c - p[2 * w + 2];   d[3] = c - p[w + 3];
+        d[4] = c - p[3];              d[5] = c - p[-w + 3];      d[6] = c - p[-2 * w + 2];  d[7] = c - p[-3 * w + 1];
+        d[8] = c - p[-3 * w];         d[9] = c - p[-3 * w - 1];  d[10] = c - p[-2 * w - 2]; d[11] = c - p[-w - 3];
+        d[12] = c - p[-3];            d[13] = c - p[w - 3];      d[14] = c - p[2 * w - 2];  d[15] = c - p[3 * w - 1];
+        unsigned P = 0, N = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { P |= (unsigned)(d[i] > FAST_THR) << i; N |= (unsigned)(d[i] < -FAST_THR) << i; }
+        if (has9(P) || has9(N)) {
+            // cornerScore<16>: max over the 16 arcs of min(d) and of min(-d), minus 1
+            int best = FAST_THR;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                int mn = d[i], mx = d[i];
+#pragma unroll
+                for (int k = 1; k < 9; ++k) { const int v = d[(i + k) & 15]; mn = min(mn, v); mx = max(mx, v); }
+                best = max(best, max(mn, -mx));
+            }
+            s = best - 1;
+        }
+    }
+    score[L.off + (size_t)y * L.w + x] = (uint8_t)s;
+}
+
+// NMS + border filter + histogram + per-warp compaction (ballot / popc)
+__global__ void __launch_bounds__(256) k_fast_nms(BmOrbLevels lv, const uint8_t* __restrict__ score, uint2* __restrict__ cand,
+                                                  int* __restrict__ ctr, int* __restrict__ hist) {
+    const int level = blockIdx.y;
+    const BmOrbLevel L = lv.l[level];
+    int x, y;
+    if (!tile_xy(L, x, y)) return;
+    bool keep = false;
+    int s = 0;
+    if (x >= ORB_EDGE && y >= ORB_EDGE && x < L.w - ORB_EDGE && y < L.h - ORB_EDGE) {
+        const uint8_t* p = score + L.off + (size_t)y * L.w + x;
+        const int w = L.w;
+        s = p[0];
+        keep = s > 0 && s > p[-1] && s > p[1] && s > p[-w - 1] && s > p[-w] && s > p[-w + 1] && s > p[w - 1] && s > p[w] && s > p[w + 1];
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (bal) {
+        const int lane = threadIdx.x & 31;
+        const int leader = __ffs(bal) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&ctr[level], __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (keep) {
+            const int idx = base + __popc(bal & ((1u << lane) - 1u));
+            if (idx < L.cand_cap) cand[L.cand_off + idx] = make_uint2((unsigned)x | ((unsigned)y << 16), (unsigned)s);
+            atomicAdd(&hist[level * 256 + s], 1);
+        }
+    }
+}
+
+// retainBest(2*quota) threshold on the integer FAST scores: thr = the n-th largest score (ties are all kept)
+__global__ void k_fast_threshold(BmOrbLevels lv, int* __restrict__ ctr, const int* __restrict__ hist) {
+    const int level = threadIdx.x;
+    if (level >= BM_ORB_LEVELS) return;
+    const BmOrbLevel L = lv.l[level];
+    int n1 = ctr[level];
+    if (n1 > L.cand_cap) { n1 = L.cand_cap; ctr[32] = 1; }
+    ctr[level] = n1;
+    const int n = 2 * L.quota;
+    int thr = 0;
+    if (n <= 0) thr = 256;
+    else if (n1 > n) {
+        int cum = 0;
+        for (int s = 255; s >= 0; --s) { cum += hist[level * 256 + s]; if (cum >= n) { thr = s; break; } }
+    }
+    ctr[16 + level] = thr;
+}
+
+// HarrisResponses (blockSize 7, k = 0.04) on the FAST survivors; second compaction
+__global__ void __launch_bounds__(256) k_harris(BmOrbLevels lv, const uint8_t* __restrict__ pyr, const uint2* __restrict__ cand,
+                                                uint2* __restrict__ cand2, int* __restrict__ ctr) {
+    const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+    int level = 0;
+#pragma unroll
+    for (int l = 1; l < BM_ORB_LEVELS; ++l) if (gi >= lv.l[l].cand_off) level = l;
+    const BmOrbLevel L = lv.l[level];
+    const int li = gi - L.cand_off;
+    bool ok = gi < lv.total_cand && li < ctr[level];
+    uint2 cd = make_uint2(0, 0);
+    if (ok) { cd = cand[gi]; ok = (int)cd.y >= ctr[16 + level]; }
+    float resp = 0.f;
+    if (ok) {
+        const int x0 = cd.x & 0xffff, y0 = cd.x >> 16, w = L.w;
+        const uint8_t* p0 = pyr + L.off + (size_t)(y0 - 3) * w + (x0 - 3);
+        int a = 0, b = 0, c = 0;
+        for (int dy = 0; dy < 7; ++dy) {
+            const uint8_t* p = p0 + dy * w;
+#pragma unroll
+            for (int dx = 0; dx < 7; ++dx, ++p) {
+                const int Ix = (p[1] - p[-1]) * 2 + (p[-w + 1] - p[-w - 1]) + (p[w + 1] - p[w - 1]);
+                const int Iy = (p[w] - p[-w]) * 2 + (p[w - 1] - p[-w - 1]) + (p[w + 1] - p[-w + 1]);
+                a += Ix * Ix; b += Iy * Iy; c += Ix * Iy;
+            }
+        }
+        const float fa = (float)a, fb = (float)b, fc = (float)c;
+        const float scale = __fdiv_rn(1.0f, __fmul_rn(28.0f, 255.0f));
+        const float s4 = __fmul_rn(__fmul_rn(__fmul_rn(scale, scale), scale), scale);
+        const float sum = __fadd_rn(fa, fb);
+        const float t = __fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), __fmul_rn(__fmul_rn(0.04f, sum), sum));
+        resp = __fmul_rn(t, s4);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    if (bal) {
+        const int lane = threadIdx.x & 31, leader = __ffs(bal) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&ctr[8 + level], __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (ok) cand2[L.cand_off + base + __popc(bal & ((1u << lane) - 1u))] = make_uint2(cd.x, __float_as_uint(resp));
+    }
+}
+
+// retainBest(quota) on Harris responses: keep i iff fewer than quota candidates have a strictly larger response
+__global__ void __launch_bounds__(1024) k_harris_select(BmOrbLevels lv, const uint2* __restrict__ cand2, int* __restrict__ ctr,
+                                                        uint8_t* __restrict__ keep) {
+    const int level = blockIdx.x;
+    const BmOrbLevel L = lv.l[level];
+    const int n2 = ctr[8 + level];
+    __shared__ int kept;
+    if (threadIdx.x == 0) kept = 0;
+    __syncthreads();
+    const uint2* c = cand2 + L.cand_off;
+    int mine = 0;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+        const float r = __uint_as_float(c[i].y);
+        int greater = 0;
+        if (n2 > L.quota)
+            for (int j = 0; j < n2; ++j) greater += (__uint_as_float(c[j].y) > r) ? 1 : 0;
+        const bool k = greater < L.quota;
+        keep[L.cand_off + i] = k ? 1 : 0;
+        mine += k ? 1 : 0;
+    }
+    if (mine) atomicAdd(&kept, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) ctr[24 + level] = kept;
+}
+
+// final keypoint list: level-major, (y,x) order inside a level
+__global__ void __launch_bounds__(1024) k_orb_emit(BmOrbLevels lv, const uint2* __restrict__ cand2, int* ctr,
+                                                   const uint8_t* __restrict__ keep, BmKeypoints out) {
+    const int level = blockIdx.x;
+    const BmOrbLevel L = lv.l[level];
+    const int n2 = ctr[8 + level];
+    int base = 0;
+    for (int l = 0; l < level; ++l) base += ctr[24 + l];
+    const uint2* c = cand2 + L.cand_off;
+    const uint8_t* kf = keep + L.cand_off;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+        if (!kf[i]) continue;
+        const unsigned key = ((c[i].x >> 16) << 16) | (c[i].x & 0xffff);     // (y << 16) | x
+        int rank = 0;
+        for (int j = 0; j < n2; ++j) rank += (kf[j] && c[j].x < key) ? 1 : 0;  // cand.x is already (y<<16)|x
+        const int o = base + rank;
+        if (o < BM_KP_CAP) {
+            const int x = c[i].x & 0xffff, y = c[i].x >> 16;
+            out.pt[o] = make_float2(__fmul_rn((float)x, L.scale), __fmul_rn((float)y, L.scale));
+            out.size[o] = __fmul_rn(31.0f, L.scale);
+            out.response[o] = __uint_as_float(c[i].y);
+            out.octave[o] = level;
+            out.lxy[o] = make_int2(x, y);
+        }
+    }
+    if (level == BM_ORB_LEVELS - 1 && threadIdx.x == 0) {
+        int tot = base + ctr[24 + level];
+        if (tot > BM_KP_CAP) { tot = BM_KP_CAP; ctr[32] = 1; }
+        *out.count = tot;
+    }
+}
+
+// cv::fastAtan2 scalar path, float32, no FMA
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    const float k = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = __fmul_rn(0.9997878412794807f, k), p3 = __fmul_rn(-0.3258083974640975f, k);
+    const float p5 = __fmul_rn(0.1555786518463281f, k), p7 = __fmul_rn(-0.04432655554792128f, k);
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float eps = 2.220446049250313e-16f;
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.0f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0.f) a = __fsub_rn(180.0f, a);
+    if (y < 0.f) a = __fsub_rn(360.0f, a);
+    return a;
+}
+
+__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+
+// IC_Angle: one warp per keypoint, lane = column u in [-15, 15]
+__global__ void __launch_bounds__(256) k_ic_angle(BmOrbLevels lv, const uint8_t* __restrict__ pyr, BmKeypoints kp) {
+    const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (k >= *kp.count) return;
+    const BmOrbLevel L = lv.l[kp.octave[k]];
+    const int2 c = kp.lxy[k];
+    const uint8_t* center = pyr + L.off + (size_t)c.y * L.w + c.x;
+    int m10 = 0, m01 = 0;
+    const int u = lane - 15;
+    if (lane < 31) {
+        m10 = u * center[u];
+        const int au = abs(u);
+        for (int v = 1; v <= 15; ++v) {
+            if (au <= c_umax[v]) {
+                const int p = center[u + v * L.w], m = center[u - v * L.w];
+                m01 += v * (p - m);
+                m10 += u * (p + m);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o); m01 += __shfl_xor_sync(0xffffffffu, m01, o); }
+    if (lane == 0) kp.angle[k] = fast_atan2_deg((float)m01, (float)m10);
+}
+
+// fused 7x7 sigma-2 Gaussian (float separable, rounded to u8 as ORB does on the level) over the 37x37 patch + rBRIEF-256
+#define PR 18                        // blurred patch radius (pattern points are within 13*sqrt(2) of the centre)
+#define RR (PR + 3)                  // raw patch radius
+__global__ void __launch_bounds__(256) k_orb_describe(BmOrbLevels lv, const uint8_t* __restrict__ pyr, BmKeypoints kp) {
+    const int k = blockIdx.x;
+    if (k >= *kp.count) return;
+    __shared__ uint8_t raw[2 * RR + 1][2 * RR + 2];
+    __shared__ float rowf[2 * RR + 1][2 * PR + 1];
+    __shared__ uint8_t blr[2 * PR + 1][2 * PR + 2];
+    const int level = kp.octave[k];
+    const BmOrbLevel L = lv.l[level];
+    const float2 pt = kp.pt[k];
+    // computeOrbDescriptors re-derives the level coordinates from the scaled point
+    const int cx = __float2int_rn(__fmul_rn(pt.x, L.inv_scale)), cy = __float2int_rn(__fmul_rn(pt.y, L.inv_scale));
+    const uint8_t* img = pyr + L.off;
+    const int t = threadIdx.x;
+    for (int i = t; i < (2 * RR + 1) * (2 * RR + 1); i += 256) {
+        const int ry = i / (2 * RR + 1), rx = i % (2 * RR + 1);
+        int yy = cy - RR + ry, xx = cx - RR + rx;
+        yy = yy < 0 ? -yy : (yy >= L.h ? 2 * (L.h - 1) - yy : yy);     // reflect-101 (only reachable for foreign keypoints)
+        xx = xx < 0 ? -xx : (xx >= L.w ? 2 * (L.w - 1) - xx : xx);
+        raw[ry][rx] = img[(size_t)yy * L.w + xx];
+    }
+    __syncthreads();
+    // cv::getGaussianKernel(7, 2, CV_32F)
+    const float g0 = 0.07015932351350784f, g1 = 0.13107487559318542f, g2 = 0.19071282446384430f, g3 = 0.21610593795776367f;
+    for (int i = t; i < (2 * RR + 1) * (2 * PR + 1); i += 256) {
+        const int ry = i / (2 * PR + 1), bx = i % (2 * PR + 1);
+        const uint8_t* r = &raw[ry][bx];
+        float a = __fmul_rn(g0, (float)r[0]);
+        a = __fadd_rn(a, __fmul_rn(g1, (float)r[1])); a = __fadd_rn(a, __fmul_rn(g2, (float)r[2]));
+        a = __fadd_rn(a, __fmul_rn(g3, (float)r[3])); a = __fadd_rn(a, __fmul_rn(g2, (float)r[4]));
+        a = __fadd_rn(a, __fmul_rn(g1, (float)r[5])); a = __fadd_rn(a, __fmul_rn(g0, (float)r[6]));
+        rowf[ry][bx] = a;
+    }
+    __syncthreads();
+    for (int i = t; i < (2 * PR + 1) * (2 * PR + 1); i += 256) {
+        const int by = i / (2 * PR + 1), bx = i % (2 * PR + 1);
+        float a = __fmul_rn(g0, rowf[by][bx]);
+        a = __fadd_rn(a, __fmul_rn(g1, rowf[by + 1][bx])); a = __fadd_rn(a, __fmul_rn(g2, rowf[by + 2][bx]));
+        a = __fadd_rn(a, __fmul_rn(g3, rowf[by + 3][bx])); a = __fadd_rn(a, __fmul_rn(g2, rowf[by + 4][bx]));
+        a = __fadd_rn(a, __fmul_rn(g1, rowf[by + 5][bx])); a = __fadd_rn(a, __fmul_rn(g0, rowf[by + 6][bx]));
+        int v = __float2int_rn(a);
+        blr[by][bx] = (uint8_t)max(0, min(255, v));
+    }
+    __syncthreads();
+    const float th = __fmul_rn(kp.angle[k], (float)(3.14159265358979323846 / 180.0));
+    const float ca = (float)cos((double)th), sa = (float)sin((double)th);
+    const signed char* pp = c_orb_pattern + 4 * t;
+    const float x0 = (float)pp[0], y0 = (float)pp[1], x1 = (float)pp[2], y1 = (float)pp[3];
+    const int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, ca), __fmul_rn(y0, sa)));
+    const int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, sa), __fmul_rn(y0, ca)));
+    const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, ca), __fmul_rn(y1, sa)));
+    const int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, sa), __fmul_rn(y1, ca)));
+    const int v0 = blr[PR + iy0][PR + ix0], v1 = blr[PR + iy1][PR + ix1];
+    const unsigned bits = __ballot_sync(0xffffffffu, v0 < v1);
+    if ((t & 31) == 0) reinterpret_cast<unsigned*>(kp.desc + (size_t)k * 32)[t >> 5] = bits;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------------------------------
+static int cv_round_f(float v) { return (int)nearbyintf(v); }
+
+static void make_levels(BmOrbLevels* lv, int w, int h, int nfeatures) {
+    memset(lv, 0, sizeof(*lv));
+    const double sf = (double)1.2f;
+    // nfeaturesPerLevel (orb.cpp computeKeyPoints)
+    const float factor = (float)(1.0 / sf);
+    float nd = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)BM_ORB_LEVELS));
+    int sum = 0, off = 0, coff = 0;
+    for (int l = 0; l < BM_ORB_LEVELS; ++l) {
+        BmOrbLevel& L = lv->l[l];
+        L.scale = (float)pow(sf, (double)l);
+        L.inv_scale = 1.f / L.scale;
+        L.w = cv_round_f(w * L.inv_scale);
+        L.h = cv_round_f(h * L.inv_scale);
+        if (l < BM_ORB_LEVELS - 1) { L.quota = cv_round_f(nd); sum += L.quota; nd *= factor; }
+        else L.quota = nfeatures - sum > 0 ? nfeatures - sum : 0;
+        L.off = off;
+        off += (L.w * L.h + 255) & ~255;
+        L.cand_off = coff;
+        L.cand_cap = ((L.w * L.h / 4 + 1024) + 255) & ~255;
+        coff += L.cand_cap;
+    }
+    lv->total_px = off;
+    lv->total_cand = coff;
+}
+
+int bm_kp_alloc(BmKeypoints* k, int desc_bytes) {
+    memset(k, 0, sizeof(*k));
+    if (cudaMalloc(&k->pt, BM_KP_CAP * sizeof(float2)) != cudaSuccess) return -1;
+    if (cudaMalloc(&k->size, BM_KP_CAP * sizeof(float)) != cudaSuccess) return -1;
+    if (cudaMalloc(&k->angle, BM_KP_CAP * sizeof(float)) != cudaSuccess) return -1;
+    if (cudaMalloc(&k->response, BM_KP_CAP * sizeof(float)) != cudaSuccess) return -1;
+    if (cudaMalloc(&k->octave, BM_KP_CAP * sizeof(int)) != cudaSuccess) return -1;
+    if (cudaMalloc(&k->lxy, BM_KP_CAP * sizeof(int2)) != cudaSuccess) return -1;
+    if (cudaMalloc(&k->desc, (size_t)BM_KP_CAP * desc_bytes) != cudaSuccess) return -1;
+    if (cudaMalloc(&k->count, sizeof(int)) != cudaSuccess) return -1;
+    cudaMemset(k->count, 0, sizeof(int));
+    return 0;
+}
+void bm_kp_free(BmKeypoints* k) {
+    cudaFree(k->pt); cudaFree(k->size); cudaFree(k->angle); cudaFree(k->response); cudaFree(k->octave); cudaFree(k->lxy);
+    cudaFree(k->desc); cudaFree(k->count);
+    memset(k, 0, sizeof(*k));
+}
+
+int bm_orb_create(BmOrb** out, int h, int w, int nfeatures, cudaStream_t s) {
+    BmOrb* o = new (std::nothrow) BmOrb();
+    if (!o) return -1;
+    memset(o, 0, sizeof(*o));
+    o->w = w; o->h = h; o->nfeatures = nfeatures; o->stream = s;
+    make_levels(&o->lv, w, h, nfeatures);
+    bool ok = cudaMalloc(&o->pyr, o->lv.total_px + 64) == cudaSuccess && cudaMalloc(&o->score, o->lv.total_px + 64) == cudaSuccess &&
+              cudaMalloc(&o->cand, (size_t)o->lv.total_cand * sizeof(uint2)) == cudaSuccess &&
+              cudaMalloc(&o->cand2, (size_t)o->lv.total_cand * sizeof(uint2)) == cudaSuccess &&
+              cudaMalloc(&o->keep, o->lv.total_cand) == cudaSuccess && cudaMalloc(&o->ctr, 64 * sizeof(int)) == cudaSuccess &&
+              cudaMalloc(&o->hist, BM_ORB_LEVELS * 256 * sizeof(int)) == cudaSuccess;
+    if (!ok) { bm_orb_destroy(o); return -1; }
+    *out = o;
+    return 0;
+}
+void bm_orb_destroy(BmOrb* o) {
+    if (!o) return;
+    cudaFree(o->pyr); cudaFree(o->score); cudaFree(o->cand); cudaFree(o->cand2); cudaFree(o->keep); cudaFree(o->ctr); cudaFree(o->hist);
+    delete o;
+}
+
+cudaError_t bm_orb_detect(BmOrb* o, const uint8_t* d_gray, BmKeypoints* out) {
+    cudaStream_t s = o->stream;
+    const BmOrbLevels& lv = o->lv;
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(o->ctr, 0, 64 * sizeof(int), s)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(o->hist, 0, BM_ORB_LEVELS * 256 * sizeof(int), s)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(o->pyr, d_gray, (size_t)o->w * o->h, cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return e;
+    const dim3 blk(32, 8);
+    for (int l = 1; l < BM_ORB_LEVELS; ++l) {
+        const BmOrbLevel &P = lv.l[l - 1], &L = lv.l[l];
+        k_resize_exact<<<dim3((L.w + 31) / 32, (L.h + 7) / 8), blk, 0, s>>>(o->pyr + P.off, P.w, P.h, o->pyr + L.off, L.w, L.h);
+    }
+    const int tiles0 = ((lv.l[0].w + 31) / 32) * ((lv.l[0].h + 7) / 8);
+    k_fast_score<<<dim3(tiles0, BM_ORB_LEVELS), blk, 0, s>>>(lv, o->pyr, o->score);
+    k_fast_nms<<<dim3(tiles0, BM_ORB_LEVELS), blk, 0, s>>>(lv, o->score, o->cand, o->ctr, o->hist);
+    k_fast_threshold<<<1, 32, 0, s>>>(lv, o->ctr, o->hist);
+    k_harris<<<(lv.total_cand + 255) / 256, 256, 0, s>>>(lv, o->pyr, o->cand, o->cand2, o->ctr);
+    k_harris_select<<<BM_ORB_LEVELS, 1024, 0, s>>>(lv, o->cand2, o->ctr, o->keep);
+    k_orb_emit<<<BM_ORB_LEVELS, 1024, 0, s>>>(lv, o->cand2, o->ctr, o->keep, *out);
+    k_ic_angle<<<(BM_KP_CAP * 32) / 256, 256, 0, s>>>(lv, o->pyr, *out);
+    k_orb_describe<<<BM_KP_CAP, 256, 0, s>>>(lv, o->pyr, *out);
+    return cudaGetLastError();
+}

@@ -1,0 +1,47 @@
+// orb.cuh -- ORB (FAST-9 + Harris + IC angle + rBRIEF-256) detector object.
+#pragma once
+#include "common.cuh"
+
+#define BM_ORB_LEVELS 8
+#define BM_KP_CAP 8192          // final keypoints per frame (700 + ties); exceeding it is reported as an error
+
+struct BmOrbLevel {
+    int w, h;           // level size
+    int off;            // pixel offset of the level in pyr / blur / score
+    int cand_off;       // offset of the level's segment in the candidate arrays
+    int cand_cap;
+    int quota;          // features to keep on this level (cv2: nfeaturesPerLevel)
+    float scale;        // layerScale (float32 pow(1.2f, l))
+    float inv_scale;    // 1.f / scale
+};
+struct BmOrbLevels { BmOrbLevel l[BM_ORB_LEVELS]; int total_px; int total_cand; };
+
+// final keypoints, SoA on the device; order: level-major, (y,x) row-major inside a level
+struct BmKeypoints {
+    float2* pt;         // image coordinates (level coords * scale)
+    float* size;
+    float* angle;       // degrees
+    float* response;
+    int* octave;
+    int2* lxy;          // level coordinates (ORB) / unused (SIFT)
+    uint8_t* desc;      // ORB: 32 B per keypoint; SIFT: 128 floats per keypoint (512 B)
+    int* count;         // device scalar
+};
+
+struct BmOrb {
+    int w, h, nfeatures;
+    BmOrbLevels lv;
+    uint8_t *pyr, *blur, *score;
+    uint2 *cand, *cand2;
+    int* ctr;           // device counters: [0..7] cnt1, [8..15] cnt2, [16..23] thr, [24..31] kept, [32] overflow flag
+    int* hist;          // [8][256]
+    uint8_t* keep;      // keep flags for cand2
+    cudaStream_t stream;
+};
+
+int bm_orb_create(BmOrb** out, int h, int w, int nfeatures, cudaStream_t s);
+void bm_orb_destroy(BmOrb* o);
+int bm_kp_alloc(BmKeypoints* k, int desc_bytes);
+void bm_kp_free(BmKeypoints* k);
+// gray (device, tightly packed h*w) -> keypoints + descriptors into `out`
+cudaError_t bm_orb_detect(BmOrb* o, const uint8_t* d_gray, BmKeypoints* out);

@@ -1,20 +1,93 @@
-// pipeline.cu -- detect / match / RANSAC orchestration (placeholder until the detector kernels land).
+// pipeline.cu -- per-frame feature pipeline: detectAndCompute -> match -> findHomography (main.py:717-727) on the device,
+// one small D2H read (counts + RANSAC result) per frame for the reference's host-side control flow.
 #include "pipeline.cuh"
+#include "orb.cuh"
+#include "sift.cuh"
+#include "match.cuh"
+#include "ransac.cuh"
 #include <new>
+#include <string.h>
 
-struct BmPipeline { bm_config cfg; cudaStream_t stream; };
+struct BmHostReadback {      // pinned
+    BmRansacResult r;
+    int n_cur, n_prev, n_matches, overflow;
+};
+
+struct BmPipeline {
+    bm_config cfg;
+    cudaStream_t stream;
+    BmOrb* orb = nullptr;
+    BmSift* sift = nullptr;
+    BmKeypoints kp[2];
+    int prev = 0;
+    BmMatches m;
+    uint8_t* d_mask = nullptr;
+    BmRansacResult* d_res = nullptr;
+    BmHostReadback* h_rb = nullptr;
+    bool have_prev = false;
+};
 
 bm_status bm_pipeline_create(BmPipeline** out, const bm_config& cfg, cudaStream_t stream) {
     BmPipeline* p = new (std::nothrow) BmPipeline();
     if (!p) return BM_ERR_ARG;
     p->cfg = cfg; p->stream = stream;
+    memset(p->kp, 0, sizeof(p->kp)); memset(&p->m, 0, sizeof(p->m));
+    const int desc_bytes = cfg.detector == BM_DET_ORB ? 32 : 128;
+    bool ok = bm_kp_alloc(&p->kp[0], desc_bytes) == 0 && bm_kp_alloc(&p->kp[1], desc_bytes) == 0 && bm_matches_alloc(&p->m) == 0 &&
+              cudaMalloc(&p->d_mask, BM_KP_CAP) == cudaSuccess && cudaMalloc(&p->d_res, sizeof(BmRansacResult)) == cudaSuccess &&
+              cudaHostAlloc(&p->h_rb, sizeof(BmHostReadback), cudaHostAllocDefault) == cudaSuccess;
+    if (ok) {
+        if (cfg.detector == BM_DET_ORB) ok = bm_orb_create(&p->orb, cfg.frame_h, cfg.frame_w, cfg.nfeatures, stream) == 0;
+        else ok = bm_sift_create(&p->sift, cfg.frame_h, cfg.frame_w, cfg.nfeatures, stream) == 0;
+    }
+    if (!ok) { bm_set_error("bm_pipeline_create: allocation failed: %s", cudaGetErrorString(cudaGetLastError())); bm_pipeline_destroy(p); return BM_ERR_CUDA; }
     *out = p;
     return BM_OK;
 }
-void bm_pipeline_destroy(BmPipeline* p) { delete p; }
-bm_status bm_pipeline_first_frame(BmPipeline*, const uint8_t*) { return BM_OK; }
-bm_status bm_pipeline_estimate(BmPipeline*, const uint8_t*, bm_frame_info*, double*, int*) {
-    bm_set_error("feature pipeline not built yet");
-    return BM_ERR_UNSUPPORTED;
+
+void bm_pipeline_destroy(BmPipeline* p) {
+    if (!p) return;
+    bm_orb_destroy(p->orb); bm_sift_destroy(p->sift);
+    bm_kp_free(&p->kp[0]); bm_kp_free(&p->kp[1]); bm_matches_free(&p->m);
+    cudaFree(p->d_mask); cudaFree(p->d_res); cudaFreeHost(p->h_rb);
+    delete p;
 }
-void bm_pipeline_advance(BmPipeline*) {}
+
+static cudaError_t detect(BmPipeline* p, const uint8_t* d_gray, BmKeypoints* out) {
+    if (p->orb) return bm_orb_detect(p->orb, d_gray, out);
+    return bm_sift_detect(p->sift, d_gray, out);
+}
+
+bm_status bm_pipeline_first_frame(BmPipeline* p, const uint8_t* d_gray) {
+    p->prev = 0;
+    BM_CUDA_OK(detect(p, d_gray, &p->kp[0]));
+    p->have_prev = true;
+    return BM_OK;
+}
+
+bm_status bm_pipeline_estimate(BmPipeline* p, const uint8_t* d_gray, bm_frame_info* info, double H_rel[9], int* have_h) {
+    if (!p->have_prev) { bm_set_error("process_frame before first frame"); return BM_ERR_ARG; }
+    cudaStream_t s = p->stream;
+    BmKeypoints& cur = p->kp[p->prev ^ 1];
+    BmKeypoints& prev = p->kp[p->prev];
+    BM_CUDA_OK(detect(p, d_gray, &cur));
+    if (p->orb) BM_CUDA_OK(bm_match_hamming(cur, prev, p->m, s));
+    else BM_CUDA_OK(bm_match_l2_ratio(cur, prev, p->m, 0.7, s));                         // main.py:691
+    BM_CUDA_OK(bm_launch_ransac(p->m.src, p->m.dst, p->m.count, 2.0, 2000, 0.995, p->d_mask, p->d_res, s));   // main.py:857
+    BmHostReadback* rb = p->h_rb;
+    BM_CUDA_OK(cudaMemcpyAsync(&rb->r, p->d_res, sizeof(BmRansacResult), cudaMemcpyDeviceToHost, s));
+    BM_CUDA_OK(cudaMemcpyAsync(&rb->n_cur, cur.count, sizeof(int), cudaMemcpyDeviceToHost, s));
+    BM_CUDA_OK(cudaMemcpyAsync(&rb->n_prev, prev.count, sizeof(int), cudaMemcpyDeviceToHost, s));
+    BM_CUDA_OK(cudaMemcpyAsync(&rb->n_matches, p->m.count, sizeof(int), cudaMemcpyDeviceToHost, s));
+    BM_CUDA_OK(cudaStreamSynchronize(s));
+    info->n_kp_cur = rb->n_cur; info->n_kp_prev = rb->n_prev; info->n_matches = rb->n_matches;
+    info->ransac_iters = rb->r.iters; info->n_inliers = rb->r.n_inliers;
+    *have_h = rb->r.ok;
+    if (rb->r.ok) memcpy(H_rel, rb->r.H, 72);
+    return BM_OK;
+}
+
+void bm_pipeline_advance(BmPipeline* p) { p->prev ^= 1; }
+
+BmKeypoints* bm_pipeline_keypoints(BmPipeline* p, int which) { return &p->kp[which ? (p->prev ^ 1) : p->prev]; }
+BmMatches* bm_pipeline_matches(BmPipeline* p) { return &p->m; }

@@ -12,3 +12,6 @@ bm_status bm_pipeline_first_frame(BmPipeline* p, const uint8_t* d_gray);
 bm_status bm_pipeline_estimate(BmPipeline* p, const uint8_t* d_gray, bm_frame_info* info, double H_rel[9], int* have_h);
 // cur -> prev (main.py:756-759)
 void bm_pipeline_advance(BmPipeline* p);
+struct BmKeypoints; struct BmMatches;
+BmKeypoints* bm_pipeline_keypoints(BmPipeline* p, int which /*0 prev, 1 cur*/);
+BmMatches* bm_pipeline_matches(BmPipeline* p);

@@ -1,0 +1,9 @@
+// sift.cuh -- SIFT (cv2.SIFT_create(700)) detector object.
+#pragma once
+#include "common.cuh"
+#include "orb.cuh"     // BmKeypoints
+
+struct BmSift;
+int bm_sift_create(BmSift** out, int h, int w, int nfeatures, cudaStream_t s);
+void bm_sift_destroy(BmSift* o);
+cudaError_t bm_sift_detect(BmSift* o, const uint8_t* d_gray, BmKeypoints* out);

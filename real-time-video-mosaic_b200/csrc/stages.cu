@@ -1,0 +1,124 @@
+// stages.cu -- feature / matching / RANSAC stage entry points of the C ABI (small host arrays in, host arrays out).
+#include "../../include/b200mosaic.h"
+#include "common.cuh"
+#include "orb.cuh"
+#include "sift.cuh"
+#include "match.cuh"
+#include "ransac.cuh"
+#include <vector>
+#include <string.h>
+#include <math.h>
+
+extern "C" int bm_keypoint_capacity(void) { return BM_KP_CAP; }
+
+// device keypoints -> host rows (x, y, size, angle, response, octave) + descriptors
+bm_status bm_download_keypoints(const BmKeypoints& k, int desc_bytes, float* h_kp, uint8_t* h_desc, int cap, int* n_out, cudaStream_t s) {
+    int n = 0;
+    BM_CUDA_OK(cudaMemcpyAsync(&n, k.count, sizeof(int), cudaMemcpyDeviceToHost, s));
+    BM_CUDA_OK(cudaStreamSynchronize(s));
+    if (n > cap) { bm_set_error("keypoint buffer too small: %d > %d", n, cap); return BM_ERR_ARG; }
+    if (n_out) *n_out = n;
+    if (n == 0) return BM_OK;
+    std::vector<float2> pt(n); std::vector<float> sz(n), an(n), rs(n); std::vector<int> oc(n);
+    BM_CUDA_OK(cudaMemcpyAsync(pt.data(), k.pt, n * sizeof(float2), cudaMemcpyDeviceToHost, s));
+    BM_CUDA_OK(cudaMemcpyAsync(sz.data(), k.size, n * 4, cudaMemcpyDeviceToHost, s));
+    BM_CUDA_OK(cudaMemcpyAsync(an.data(), k.angle, n * 4, cudaMemcpyDeviceToHost, s));
+    BM_CUDA_OK(cudaMemcpyAsync(rs.data(), k.response, n * 4, cudaMemcpyDeviceToHost, s));
+    BM_CUDA_OK(cudaMemcpyAsync(oc.data(), k.octave, n * 4, cudaMemcpyDeviceToHost, s));
+    if (h_desc) BM_CUDA_OK(cudaMemcpyAsync(h_desc, k.desc, (size_t)n * desc_bytes, cudaMemcpyDeviceToHost, s));
+    BM_CUDA_OK(cudaStreamSynchronize(s));
+    if (h_kp) for (int i = 0; i < n; ++i) {
+        float* r = h_kp + 6 * (size_t)i;
+        r[0] = pt[i].x; r[1] = pt[i].y; r[2] = sz[i]; r[3] = an[i]; r[4] = rs[i]; r[5] = (float)oc[i];
+    }
+    return BM_OK;
+}
+
+extern "C" bm_status bm_orb_detect_and_compute(const uint8_t* d_gray, int h, int w, int nfeatures, float* h_kp, uint8_t* h_desc, int cap, int* n_out) {
+    if (!d_gray || h < 64 || w < 64) { bm_set_error("bm_orb_detect_and_compute: bad args"); return BM_ERR_ARG; }
+    BmOrb* o = nullptr; BmKeypoints k;
+    if (bm_orb_create(&o, h, w, nfeatures, nullptr) != 0 || bm_kp_alloc(&k, 32) != 0) { bm_set_error("orb alloc: %s", cudaGetErrorString(cudaGetLastError())); return BM_ERR_CUDA; }
+    cudaError_t e = bm_orb_detect(o, d_gray, &k);
+    bm_status st = BM_OK;
+    if (e != cudaSuccess) { bm_set_error("orb detect: %s", cudaGetErrorString(e)); st = BM_ERR_CUDA; }
+    if (st == BM_OK) st = bm_download_keypoints(k, 32, h_kp, h_desc, cap, n_out, nullptr);
+    if (st == BM_OK) {
+        int ov = 0;
+        cudaMemcpy(&ov, o->ctr + 32, 4, cudaMemcpyDeviceToHost);
+        if (ov) { bm_set_error("ORB candidate / keypoint capacity exceeded"); st = BM_ERR_UNSUPPORTED; }
+    }
+    bm_kp_free(&k); bm_orb_destroy(o);
+    return st;
+}
+
+extern "C" bm_status bm_sift_detect_and_compute(const uint8_t* d_gray, int h, int w, int nfeatures, float* h_kp, float* h_desc, int cap, int* n_out) {
+    if (!d_gray || h < 32 || w < 32) { bm_set_error("bm_sift_detect_and_compute: bad args"); return BM_ERR_ARG; }
+    BmSift* o = nullptr; BmKeypoints k;
+    if (bm_sift_create(&o, h, w, nfeatures, nullptr) != 0) return BM_ERR_UNSUPPORTED;
+    if (bm_kp_alloc(&k, 128) != 0) { bm_sift_destroy(o); return BM_ERR_CUDA; }
+    cudaError_t e = bm_sift_detect(o, d_gray, &k);
+    bm_status st = BM_OK;
+    if (e != cudaSuccess) { bm_set_error("sift detect: %s", cudaGetErrorString(e)); st = BM_ERR_CUDA; }
+    std::vector<uint8_t> d8((size_t)cap * 128);
+    int n = 0;
+    if (st == BM_OK) st = bm_download_keypoints(k, 128, h_kp, d8.data(), cap, &n, nullptr);
+    if (st == BM_OK) { if (h_desc) for (size_t i = 0; i < (size_t)n * 128; ++i) h_desc[i] = (float)d8[i]; if (n_out) *n_out = n; }
+    bm_kp_free(&k); bm_sift_destroy(o);
+    return st;
+}
+
+static bm_status run_match(int mode, const uint8_t* h_q, int nq, const uint8_t* h_t, int nt, int desc_bytes, double ratio,
+                           int* oq, int* ot, float* od, int* m_out) {
+    if (nq < 0 || nt < 0 || nq > BM_KP_CAP || nt > BM_KP_CAP) { bm_set_error("match: too many descriptors"); return BM_ERR_ARG; }
+    BmKeypoints a, b; BmMatches m;
+    if (bm_kp_alloc(&a, desc_bytes) != 0 || bm_kp_alloc(&b, desc_bytes) != 0 || bm_matches_alloc(&m) != 0) return BM_ERR_CUDA;
+    cudaMemcpy(a.desc, h_q, (size_t)nq * desc_bytes, cudaMemcpyHostToDevice);
+    cudaMemcpy(b.desc, h_t, (size_t)nt * desc_bytes, cudaMemcpyHostToDevice);
+    cudaMemcpy(a.count, &nq, 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(b.count, &nt, 4, cudaMemcpyHostToDevice);
+    cudaMemset(a.pt, 0, BM_KP_CAP * sizeof(float2)); cudaMemset(b.pt, 0, BM_KP_CAP * sizeof(float2));
+    cudaError_t e = mode == 0 ? bm_match_hamming(a, b, m, nullptr) : bm_match_l2_ratio(a, b, m, ratio, nullptr);
+    int M = 0;
+    if (e == cudaSuccess) e = cudaMemcpy(&M, m.count, 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && M > 0) {
+        cudaMemcpy(oq, m.q, M * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(ot, m.t, M * 4, cudaMemcpyDeviceToHost);
+        e = cudaMemcpy(od, m.dist, M * 4, cudaMemcpyDeviceToHost);
+    }
+    if (m_out) *m_out = M;
+    bm_kp_free(&a); bm_kp_free(&b); bm_matches_free(&m);
+    BM_CUDA_OK(e);
+    return BM_OK;
+}
+
+extern "C" bm_status bm_match_hamming_crosscheck(const uint8_t* q, int nq, const uint8_t* t, int nt, int* oq, int* ot, float* od, int* m_out) {
+    return run_match(0, q, nq, t, nt, 32, 0.0, oq, ot, od, m_out);
+}
+
+extern "C" bm_status bm_match_l2_knn2_ratio(const float* q, int nq, const float* t, int nt, double ratio, int* oq, int* ot, float* od, int* m_out) {
+    std::vector<uint8_t> q8((size_t)nq * 128), t8((size_t)nt * 128);
+    for (size_t i = 0; i < q8.size(); ++i) { const float v = q[i]; if (v < 0.f || v > 255.f || v != floorf(v)) { bm_set_error("L2 matcher expects SIFT descriptors (integers 0..255)"); return BM_ERR_ARG; } q8[i] = (uint8_t)v; }
+    for (size_t i = 0; i < t8.size(); ++i) { const float v = t[i]; if (v < 0.f || v > 255.f || v != floorf(v)) { bm_set_error("L2 matcher expects SIFT descriptors (integers 0..255)"); return BM_ERR_ARG; } t8[i] = (uint8_t)v; }
+    return run_match(1, q8.data(), nq, t8.data(), nt, 128, ratio, oq, ot, od, m_out);
+}
+
+extern "C" bm_status bm_ransac_homography(const float* h_src, const float* h_dst, int n, double thresh, int max_iters, double confidence,
+                                          double H[9], int* ok, int* iters, int* n_inliers) {
+    if (n < 0 || n > BM_KP_CAP || !h_src || !h_dst || !H) { bm_set_error("bm_ransac_homography: bad args"); return BM_ERR_ARG; }
+    float2 *ds = nullptr, *dd = nullptr; int* dc = nullptr; uint8_t* dm = nullptr; BmRansacResult* dr = nullptr;
+    BM_CUDA_OK(cudaMalloc(&ds, (n + 1) * sizeof(float2))); BM_CUDA_OK(cudaMalloc(&dd, (n + 1) * sizeof(float2)));
+    BM_CUDA_OK(cudaMalloc(&dc, 4)); BM_CUDA_OK(cudaMalloc(&dm, n + 1)); BM_CUDA_OK(cudaMalloc(&dr, sizeof(BmRansacResult)));
+    cudaMemcpy(ds, h_src, n * sizeof(float2), cudaMemcpyHostToDevice);
+    cudaMemcpy(dd, h_dst, n * sizeof(float2), cudaMemcpyHostToDevice);
+    cudaMemcpy(dc, &n, 4, cudaMemcpyHostToDevice);
+    cudaError_t e = bm_launch_ransac(ds, dd, dc, thresh, max_iters, confidence, dm, dr, nullptr);
+    BmRansacResult r; memset(&r, 0, sizeof(r));
+    if (e == cudaSuccess) e = cudaMemcpy(&r, dr, sizeof(r), cudaMemcpyDeviceToHost);
+    cudaFree(ds); cudaFree(dd); cudaFree(dc); cudaFree(dm); cudaFree(dr);
+    BM_CUDA_OK(e);
+    memcpy(H, r.H, 72);
+    if (ok) *ok = r.ok;
+    if (iters) *iters = r.iters;
+    if (n_inliers) *n_inliers = r.n_inliers;
+    return BM_OK;
+}

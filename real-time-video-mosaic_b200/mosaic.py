@@ -140,6 +140,54 @@ class VideMosaic:
         self.frame_prev = frame_cur
         self._canvas_cache = None
 
+    # ---- features / matches of the last frame (lazy small D2H), cv2-like objects --------------------------------
+    def _fetch_kp(self, which):
+        cap = self._lib.bm_keypoint_capacity()
+        dbytes = 32 if self.detector_type == "orb" else 128
+        kp = np.empty((cap, 6), np.float32); des = np.empty((cap, dbytes), np.uint8); n = C.c_int(0)
+        _lib.check(self._lib.bm_get_keypoints(self._h, which, kp.ctypes.data_as(C.c_void_p), des.ctypes.data_as(C.c_void_p),
+                                              cap, C.byref(n)), "bm_get_keypoints")
+        kps = [_KeyPoint(r[0], r[1], float(r[2]), float(r[3]), float(r[4]), int(r[5])) for r in kp[:n.value]]
+        d = des[:n.value].copy()
+        return kps, (d if self.detector_type == "orb" else d.astype(np.float32))
+
+    @property
+    def kp_prev(self):
+        return self._fetch_kp(0)[0]
+
+    @property
+    def des_prev(self):
+        return self._fetch_kp(0)[1]
+
+    @property
+    def matches(self):
+        cap = self._lib.bm_keypoint_capacity()
+        q = np.empty(cap, np.int32); t = np.empty(cap, np.int32); d = np.empty(cap, np.float32); m = C.c_int(0)
+        _lib.check(self._lib.bm_get_matches(self._h, q.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p),
+                                            d.ctypes.data_as(C.c_void_p), cap, C.byref(m)), "bm_get_matches")
+        return [DMatch(q[i], t[i], d[i]) for i in range(m.value)]
+
+    # ---- main.py:676-708 ---------------------------------------------------------------------------------------
+    def match(self, des_cur, des_prev):
+        from . import ops
+        if self.detector_type == "sift":
+            m = ops.match_l2_ratio(np.asarray(des_cur), np.asarray(des_prev), 0.7)
+        else:
+            m = ops.match_hamming_crosscheck(np.asarray(des_cur), np.asarray(des_prev))
+        return [DMatch(r[0], r[1], r[2]) for r in m]
+
+    # ---- main.py:836-859 ---------------------------------------------------------------------------------------
+    @staticmethod
+    def findHomography(image_1_kp, image_2_kp, matches):
+        from . import ops
+        p1 = np.zeros((len(matches), 2), dtype=np.float32)
+        p2 = np.zeros((len(matches), 2), dtype=np.float32)
+        for i, m in enumerate(matches):
+            p1[i] = image_1_kp[m.queryIdx].pt
+            p2[i] = image_2_kp[m.trainIdx].pt
+        H, _, _ = ops.ransac_homography(p1, p2, 2.0)
+        return H
+
     def _sync_knobs(self):
         _lib.check(self._lib.bm_set_stabilization(self._h, int(bool(self.stabilization_enabled)), int(self.history_size),
                                                   float(self.translation_threshold), float(self.scale_threshold)))

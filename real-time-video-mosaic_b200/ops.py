@@ -70,3 +70,67 @@ def blend_step(canvas: torch.Tensor, warped: torch.Tensor, win=None):
         wp = (C.c_int * 4)(*[int(v) for v in win])
     _lib.check(lib.bm_blend_step_bgr(_ptr(out), _ptr(warped), dh, dw, wp, C.byref(flag), _stream()), "bm_blend_step_bgr")
     return out, bool(flag.value)
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def orb_detect_and_compute(gray: torch.Tensor, nfeatures: int = 700):
+    """cv2.ORB_create(nfeatures).detectAndCompute(gray, None) (main.py:36,112,718).  gray (H,W) uint8 cuda.
+    Returns (kp float32 (n,6): x,y,size,angle,response,octave; des uint8 (n,32)), level-major / row-major order."""
+    lib = _lib.load()
+    h, w = gray.shape
+    cap = lib.bm_keypoint_capacity()
+    kp = np.empty((cap, 6), np.float32); des = np.empty((cap, 32), np.uint8); n = C.c_int(0)
+    torch.cuda.synchronize()
+    _lib.check(lib.bm_orb_detect_and_compute(_ptr(gray), h, w, nfeatures, _np_ptr(kp), _np_ptr(des), cap, C.byref(n)),
+               "bm_orb_detect_and_compute")
+    return kp[:n.value].copy(), des[:n.value].copy()
+
+
+def sift_detect_and_compute(gray: torch.Tensor, nfeatures: int = 700):
+    """cv2.SIFT_create(nfeatures).detectAndCompute(gray, None) (main.py:33,112,718). des float32 (n,128)."""
+    lib = _lib.load()
+    h, w = gray.shape
+    cap = lib.bm_keypoint_capacity()
+    kp = np.empty((cap, 6), np.float32); des = np.empty((cap, 128), np.float32); n = C.c_int(0)
+    torch.cuda.synchronize()
+    _lib.check(lib.bm_sift_detect_and_compute(_ptr(gray), h, w, nfeatures, _np_ptr(kp), _np_ptr(des), cap, C.byref(n)),
+               "bm_sift_detect_and_compute")
+    return kp[:n.value].copy(), des[:n.value].copy()
+
+
+def match_hamming_crosscheck(des_q: np.ndarray, des_t: np.ndarray):
+    """BFMatcher(NORM_HAMMING, crossCheck=True).match + sorted(key=distance) (main.py:694-698). -> (m,3) float64."""
+    lib = _lib.load()
+    q = np.ascontiguousarray(des_q, np.uint8); t = np.ascontiguousarray(des_t, np.uint8)
+    cap = max(len(q), 1)
+    oq = np.empty(cap, np.int32); ot = np.empty(cap, np.int32); od = np.empty(cap, np.float32); m = C.c_int(0)
+    _lib.check(lib.bm_match_hamming_crosscheck(_np_ptr(q), len(q), _np_ptr(t), len(t), _np_ptr(oq), _np_ptr(ot), _np_ptr(od),
+                                               C.byref(m)), "bm_match_hamming_crosscheck")
+    k = m.value
+    return np.stack([oq[:k], ot[:k], od[:k]], axis=1).astype(np.float64)
+
+
+def match_l2_ratio(des_q: np.ndarray, des_t: np.ndarray, ratio: float = 0.7):
+    """BFMatcher().knnMatch(k=2) + Lowe ratio + sorted(key=distance) (main.py:687-698). -> (m,3) float64."""
+    lib = _lib.load()
+    q = np.ascontiguousarray(des_q, np.float32); t = np.ascontiguousarray(des_t, np.float32)
+    cap = max(len(q), 1)
+    oq = np.empty(cap, np.int32); ot = np.empty(cap, np.int32); od = np.empty(cap, np.float32); m = C.c_int(0)
+    _lib.check(lib.bm_match_l2_knn2_ratio(_np_ptr(q), len(q), _np_ptr(t), len(t), float(ratio), _np_ptr(oq), _np_ptr(ot),
+                                          _np_ptr(od), C.byref(m)), "bm_match_l2_knn2_ratio")
+    k = m.value
+    return np.stack([oq[:k], ot[:k], od[:k]], axis=1).astype(np.float64)
+
+
+def ransac_homography(src: np.ndarray, dst: np.ndarray, thresh: float = 2.0, max_iters: int = 2000, confidence: float = 0.995):
+    """cv2.findHomography(src, dst, cv2.RANSAC, thresh) (main.py:856-857).  Returns (H or None, iters, n_inliers)."""
+    lib = _lib.load()
+    s = np.ascontiguousarray(np.asarray(src, np.float32).reshape(-1, 2)); d = np.ascontiguousarray(np.asarray(dst, np.float32).reshape(-1, 2))
+    H = np.zeros(9, np.float64); ok = C.c_int(0); it = C.c_int(0); ni = C.c_int(0)
+    _lib.check(lib.bm_ransac_homography(_np_ptr(s), _np_ptr(d), len(s), float(thresh), int(max_iters), float(confidence),
+                                        H.ctypes.data_as(C.POINTER(C.c_double)), C.byref(ok), C.byref(it), C.byref(ni)),
+               "bm_ransac_homography")
+    return (H.reshape(3, 3) if ok.value else None), it.value, ni.value

@@ -1,0 +1,153 @@
+"""GPU parity for the feature half of the path: ORB detectAndCompute (bit-exact as a set), Hamming / L2 matchers
+(bit-exact incl. order), RANSAC homography (< 0.5 px, in practice ~1e-6 px) -- all through the C ABI, against live cv2 /
+the oracle restatements / the reference-generated goldens."""
+import numpy as np
+import cv2
+import pytest
+import torch
+
+from oracle import orb as oorb, matching as omt, ransac as ors
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import b200mosaic.ops as o
+    return o
+
+
+@pytest.fixture(scope="module")
+def frames(golden_dir):
+    return np.load(golden_dir / "clip01_frames.npz")["frames"]
+
+
+def _synthetic_gray(w, h, seed):
+    from b200mosaic.synth import DroneSweep
+    return cv2.cvtColor(DroneSweep(w, h, seed=seed, ground_size=2048).next(), cv2.COLOR_BGR2GRAY)
+
+
+def _orb_compare(ops, gray):
+    kp, des = ops.orb_detect_and_compute(torch.from_numpy(gray).cuda())
+    kc, dc = oorb.cv_detect_and_compute(gray)
+    a, ad = oorb.canon(kp.astype(np.float64), des)
+    b, bd = oorb.canon(kc, dc)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert np.array_equal(a[:, [0, 1, 2, 5]], b[:, [0, 1, 2, 5]])          # pt, size, octave
+    assert np.array_equal(a[:, 4], b[:, 4]), np.abs(a[:, 4] - b[:, 4]).max()   # Harris response bit-equal
+    assert np.array_equal(a[:, 3], b[:, 3]), np.abs(a[:, 3] - b[:, 3]).max()   # IC angle bit-equal
+    assert np.array_equal(ad, bd), np.mean((ad == bd).all(axis=1))
+    # our own order is deterministic: level-major, then (y, x)
+    assert np.array_equal(kp, a.astype(np.float32))
+
+
+@pytest.mark.parametrize("i", [0, 2, 4])
+def test_orb_bit_exact_on_clip_frames(ops, frames, i):
+    _orb_compare(ops, cv2.cvtColor(frames[i], cv2.COLOR_BGR2GRAY))
+
+
+@pytest.mark.parametrize("size", [(640, 360), (854, 480), (1280, 720), (1920, 1080)])
+def test_orb_bit_exact_on_synthetic(ops, size):
+    _orb_compare(ops, _synthetic_gray(size[0], size[1], 21))
+
+
+def test_orb_featureless_image(ops):
+    g = np.full((240, 320), 90, np.uint8)
+    kp, des = ops.orb_detect_and_compute(torch.from_numpy(g).cuda())
+    assert len(kp) == 0 and des.shape == (0, 32)
+
+
+def test_hamming_crosscheck_exact(ops, golden_dir):
+    g = np.load(golden_dir / "clip01_orb.npz")
+    got = ops.match_hamming_crosscheck(g["des1"], g["des0"])
+    assert np.array_equal(got, g["matches1"])
+    # tie rules: duplicated rows on both sides
+    rng = np.random.default_rng(0)
+    q = rng.integers(0, 256, (300, 32), dtype=np.uint8); t = rng.integers(0, 256, (257, 32), dtype=np.uint8)
+    q[10] = q[11]; t[5] = t[6]; q[20] = t[5]; t[100:110] = q[50:60]
+    assert np.array_equal(ops.match_hamming_crosscheck(q, t), omt.match_hamming_crosscheck(q, t))
+    bf = cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=True)
+    cvm = sorted(bf.match(q, t), key=lambda m: m.distance)
+    assert np.array_equal(ops.match_hamming_crosscheck(q, t), np.array([[m.queryIdx, m.trainIdx, m.distance] for m in cvm]))
+
+
+def test_l2_ratio_exact(ops, golden_dir):
+    s = np.load(golden_dir / "clip01_sift.npz")
+    got = ops.match_l2_ratio(s["des1"], s["des0"])
+    assert np.array_equal(got, s["matches1"])
+    assert np.array_equal(ops.match_l2_ratio(s["des0"], s["des1"]), omt.match_l2_ratio(s["des0"], s["des1"]))
+
+
+def _reproj(Ha, Hb, w, h):
+    ys, xs = np.mgrid[0:h:16, 0:w:16]
+    p = np.stack([xs.ravel(), ys.ravel(), np.ones(xs.size)])
+    a = Ha @ p; b = Hb @ p
+    return np.abs(a[:2] / a[2] - b[:2] / b[2]).max()
+
+
+@pytest.mark.parametrize("det", ["orb", "sift"])
+def test_ransac_on_golden_matches(ops, golden_dir, det):
+    g = np.load(golden_dir / f"clip01_{det}.npz")
+    mm = g["matches1"]
+    src = g["kp1"][mm[:, 0].astype(int), :2].astype(np.float32)
+    dst = g["kp0"][mm[:, 1].astype(int), :2].astype(np.float32)
+    Hc, mask = cv2.findHomography(src.reshape(-1, 1, 2), dst.reshape(-1, 1, 2), cv2.RANSAC, 2.0)
+    Ho, tr = ors.find_homography_ransac(src, dst, return_trace=True)
+    H, iters, ninl = ops.ransac_homography(src, dst)
+    assert H is not None
+    assert iters == tr["iters"]                       # same seeded hypothesis sequence and stopping rule
+    assert _reproj(H, Hc, 427, 240) < 1e-3            # budget 0.5 px
+    assert _reproj(H, Ho, 427, 240) < 1e-3
+
+
+@pytest.mark.parametrize("frac", [0.0, 0.3, 0.6, 0.85])
+def test_ransac_with_outliers(ops, frac):
+    rng = np.random.default_rng(3)
+    n = 400
+    src = (rng.random((n, 2)) * [1920, 1080]).astype(np.float32)
+    Ht = np.array([[1.02, 0.03, 5], [-0.02, 0.98, -7], [1e-5, 2e-5, 1]])
+    p = np.c_[src, np.ones(n)] @ Ht.T
+    dst = (p[:, :2] / p[:, 2:] + rng.normal(0, 0.5, (n, 2))).astype(np.float32)
+    k = int(n * frac)
+    dst[:k] = (rng.random((k, 2)) * [1920, 1080]).astype(np.float32)
+    Hc, _ = cv2.findHomography(src.reshape(-1, 1, 2), dst.reshape(-1, 1, 2), cv2.RANSAC, 2.0)
+    Ho, tr = ors.find_homography_ransac(src, dst, return_trace=True)
+    H, iters, ninl = ops.ransac_homography(src, dst)
+    assert H is not None and Hc is not None
+    assert iters == tr["iters"], (iters, tr["iters"])
+    assert _reproj(H, Hc, 1920, 1080) < 0.5
+
+
+def test_ransac_degenerate_inputs(ops):
+    src = np.array([[0, 0], [100, 0], [100, 100], [0, 100]], np.float32)
+    dst = src * 1.5 + 7
+    H, _, _ = ops.ransac_homography(src, dst)
+    Hc, _ = cv2.findHomography(src.reshape(-1, 1, 2), dst.reshape(-1, 1, 2), cv2.RANSAC, 2.0)
+    assert _reproj(H, Hc, 100, 100) < 1e-6
+    H, _, _ = ops.ransac_homography(src[:3], dst[:3])
+    assert H is None
+    # all points collinear: the reference gets None
+    line = np.stack([np.arange(20.0), 2 * np.arange(20.0)], 1).astype(np.float32)
+    Hc, _ = cv2.findHomography(line.reshape(-1, 1, 2), (line + 3).reshape(-1, 1, 2), cv2.RANSAC, 2.0)
+    H, _, _ = ops.ransac_homography(line, line + 3)
+    assert (H is None) == (Hc is None)
+
+
+def test_orb_process_frame_end_to_end(frames, golden_dir, capsys):
+    """Drop-in run on the reference's own clip frames: same statuses and match counts; homographies within the 0.5 px
+    budget of the unmodified reference's (keypoint ORDER differs from cv2's nth_element order, so RANSAC samples differ)."""
+    import b200mosaic
+    g = np.load(golden_dir / "clip01_orb.npz")
+    vm = b200mosaic.VideMosaic(frames[0], detector_type="orb", show_intermediate=False, visualize=False)
+    assert np.array_equal(vm.output_img, g["canvas0"])
+    kp0, des0 = oorb.canon(np.array([[k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave] for k in vm.kp_prev]), vm.des_prev)
+    kr, dr = oorb.canon(g["kp0"], g["des0"])
+    assert np.array_equal(kp0, kr) and np.array_equal(des0, dr)
+    for t in range(1, len(frames)):
+        vm.process_frame(frames[t], t)
+        assert vm.last_info.status == 0
+        assert abs(vm.last_info.n_matches - int(g["n_matches"][t - 1])) <= 3
+        assert _reproj(vm.H, g["H"][t - 1], 427, 240) < 0.5
+    d = np.abs(vm.output_img.astype(np.int16) - g["canvas_final"].astype(np.int16))
+    assert np.mean(d > 8) < 0.02            # same mosaic up to the sub-pixel pose difference
+    assert capsys.readouterr().out == ""    # no warnings were printed on this clip (as in the reference run)
