@@ -71,6 +71,8 @@ bm_status bm_destroy(bm_handle h);
 bm_status bm_first_frame(bm_handle h, const uint8_t* h_bgr, size_t stride_bytes);
 /* one process_frame (main.py:710-759): H2D, gray, detect, match, RANSAC, validate, smooth, compose, warp, blend */
 bm_status bm_process_frame(bm_handle h, const uint8_t* h_bgr, size_t stride_bytes, bm_frame_info* info);
+/* same, with the frame already resident in device memory as packed BGR (kernel-only timing leg of bench.py) */
+bm_status bm_process_frame_device(bm_handle h, const uint8_t* d_bgr, bm_frame_info* info);
 /* output_img (uint8, Hc x Wc x 3): lazy D2H of the device canvas                     main.py:1632,1649 */
 bm_status bm_get_canvas(bm_handle h, uint8_t* h_bgr_out);
 bm_status bm_get_state(bm_handle h, double H_old[9], int* history_len, double* history /* <=5*9 */);
@@ -85,6 +87,12 @@ bm_status bm_warp_frame(bm_handle h, const uint8_t* h_bgr, size_t stride_bytes, 
 bm_status bm_warp_frame_device(bm_handle h, const uint8_t* d_bgrx, const double H[9], bm_frame_info* info);
 /* timing helpers: last warp/blend chain duration measured with CUDA events on the handle's stream (ms) */
 bm_status bm_sync(bm_handle h);
+/* CUDA-event timing of the warp/blend chain on the handle's stream: enable, then read the accumulated milliseconds,
+ * algorithmic bytes (3N + 6A per frame) and frame count since the last reset */
+bm_status bm_timing_enable(bm_handle h, int on);
+bm_status bm_timing_read(bm_handle h, double* warp_blend_ms, double* algorithmic_bytes, int* frames, int reset);
+/* number of kernels this library has launched in the calling process (all handles) */
+long long bm_kernel_launches(void);
 void* bm_stream(bm_handle h);
 /* device pointer of the handle's current BGRX frame buffer after an upload (for the kernel-only bench leg) */
 bm_status bm_upload_frame(bm_handle h, const uint8_t* h_bgr, size_t stride_bytes, const uint8_t** d_bgrx_out);
@@ -126,6 +134,8 @@ bm_status bm_ransac_homography(const float* h_src, const float* h_dst, int n, do
 bm_status bm_get_keypoints(bm_handle h, int which, float* h_kp, uint8_t* h_desc, int cap, int* n_out);
 bm_status bm_get_matches(bm_handle h, int* h_q, int* h_t, float* h_dist, int cap, int* m_out);
 int bm_keypoint_capacity(void);
+/* debug / parity: level `level` of the ORB pyramid (INTER_LINEAR_EXACT chain) and its FAST score map (either may be NULL) */
+bm_status bm_orb_debug_level(const uint8_t* d_gray, int h, int w, int level, uint8_t* h_img, uint8_t* h_score, int* lw, int* lh);
 
 #ifdef __cplusplus
 }

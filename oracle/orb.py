@@ -177,18 +177,26 @@ def ic_angles(img, xs, ys):
     return fast_atan2(m01.astype(np.float32), m10.astype(np.float32))
 
 
+def _fma32(a, b, c):
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+
+
 def blur7(img):
-    """ORB's GaussianBlur(7x7, sigma 2, REFLECT_101) of a level: float separable filter rounded to uint8."""
+    """ORB's GaussianBlur(7x7, sigma 2, REFLECT_101) of a level.  Because ORB blurs a sub-matrix of its pyramid image,
+    OpenCV skips the u8 fixed-point Gaussian and runs the generic float sepFilter2D, whose AVX2 kernels accumulate
+    rows as s = k0*x0; s = fma(k_t, x_t, s) (left to right) and columns in the symmetric form
+    s = k3*x3; s = fma(k_{3+t}, x_{3+t} + x_{3-t}, s); the float result is rounded (half-even) to uint8.
+    (probed: identical to cv2.sepFilter2D(u8, float kernel) on every pixel, and to cv2.ORB's descriptors.)"""
     x = np.arange(7, dtype=np.float64) - 3
     k = np.exp(-(x * x) / 8.0); k = (k / k.sum()).astype(np.float32)
     h, w = img.shape
     f = np.pad(img.astype(np.float32), 3, mode="reflect")
-    row = np.zeros((h + 6, w), np.float32)
-    for t in range(7):
-        row = row + k[t] * f[:, t:t + w]
-    out = np.zeros((h, w), np.float32)
-    for t in range(7):
-        out = out + k[t] * row[t:t + h, :]
+    row = (k[0] * f[:, 0:w]).astype(np.float32)
+    for t in range(1, 7):
+        row = _fma32(np.full_like(row, k[t]), f[:, t:t + w], row)
+    out = (k[3] * row[3:3 + h, :]).astype(np.float32)
+    for t in range(1, 4):
+        out = _fma32(np.full_like(out, k[3 + t]), row[3 + t:3 + t + h, :] + row[3 - t:3 - t + h, :], out)
     return np.clip(np.rint(out), 0, 255).astype(np.uint8)
 
 

@@ -66,6 +66,10 @@ def load():
     _sig(lib, "bm_warp_frame", i, vp, vp, sz, dp, C.POINTER(BmFrameInfo))
     _sig(lib, "bm_warp_frame_device", i, vp, vp, dp, C.POINTER(BmFrameInfo))
     _sig(lib, "bm_sync", i, vp)
+    _sig(lib, "bm_process_frame_device", i, vp, vp, C.POINTER(BmFrameInfo))
+    _sig(lib, "bm_timing_enable", i, vp, i)
+    _sig(lib, "bm_timing_read", i, vp, dp, dp, ip, i)
+    _sig(lib, "bm_kernel_launches", C.c_longlong)
     _sig(lib, "bm_stream", vp, vp)
     _sig(lib, "bm_upload_frame", i, vp, vp, sz, C.POINTER(vp))
     _sig(lib, "bm_ingest_bgr", i, vp, i, i, vp, vp, vp)
@@ -82,6 +86,7 @@ def load():
     _sig(lib, "bm_get_keypoints", i, vp, i, vp, vp, i, ip)
     _sig(lib, "bm_get_matches", i, vp, vp, vp, vp, i, ip)
     _sig(lib, "bm_keypoint_capacity", i)
+    _sig(lib, "bm_orb_debug_level", i, vp, i, i, i, vp, vp, ip, ip)
     _lib = lib
     return lib
 

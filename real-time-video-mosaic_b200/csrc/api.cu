@@ -17,6 +17,8 @@ void bm_set_error(const char* fmt, ...) {
 }
 extern "C" const char* bm_last_error(void) { return g_err; }
 extern "C" int bm_version(void) { return 100; }
+long long g_bm_launches = 0;
+extern "C" long long bm_kernel_launches(void) { return g_bm_launches; }
 
 #define BM_TRY(expr) do { bm_status _s = (expr); if (_s < 0) return _s; } while (0)
 
@@ -72,6 +74,12 @@ struct bm_mosaic_s {
     double translation_threshold = 50.0, scale_threshold = 0.3;
     int w_offset = 0, h_offset = 0;
     BmPipeline* pipe = nullptr;       // detector / matcher / RANSAC state (pipeline.cu)
+    // optional CUDA-event timing of the warp/blend chain
+    int timing = 0;
+    static const int kEvRing = 64;
+    cudaEvent_t ev0[kEvRing], ev1[kEvRing];
+    int ev_pending = 0;
+    double t_ms = 0.0, t_bytes = 0.0; int t_frames = 0;
 };
 
 static size_t frame_bytes(const bm_config& c) { return (size_t)c.frame_h * c.frame_w * 3; }
@@ -107,6 +115,7 @@ extern "C" bm_status bm_create(const bm_config* cfg, bm_handle* out) {
     }
     BM_CUDA_OK(cudaMalloc(&m->d_canvas_bgr, canvas_px * 3 + 16));
     for (int i = 0; i < 9; ++i) m->H_old[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    for (int i = 0; i < bm_mosaic_s::kEvRing; ++i) { BM_CUDA_OK(cudaEventCreate(&m->ev0[i])); BM_CUDA_OK(cudaEventCreate(&m->ev1[i])); }
     st = bm_pipeline_create(&m->pipe, m->cfg, m->stream);
     if (st != BM_OK) { delete m; return st; }
     *out = m;
@@ -124,6 +133,7 @@ extern "C" bm_status bm_destroy(bm_handle m) {
         if (m->ev_h2d[i]) cudaEventDestroy(m->ev_h2d[i]);
     }
     cudaFree(m->d_canvas_bgr);
+    for (int i = 0; i < bm_mosaic_s::kEvRing; ++i) { cudaEventDestroy(m->ev0[i]); cudaEventDestroy(m->ev1[i]); }
     cudaStreamDestroy(m->stream);
     delete m;
     return BM_OK;
@@ -177,12 +187,42 @@ static void fill_info_plan(bm_frame_info* info, const BmFramePlan& p) {
     info->win[0] = p.win.x0; info->win[1] = p.win.y0; info->win[2] = p.win.x1; info->win[3] = p.win.y1;
 }
 
+static bm_status timing_drain(bm_mosaic_s* m) {
+    for (int i = 0; i < m->ev_pending; ++i) {
+        float ms = 0.f;
+        BM_CUDA_OK(cudaEventSynchronize(m->ev1[i]));
+        BM_CUDA_OK(cudaEventElapsedTime(&ms, m->ev0[i], m->ev1[i]));
+        m->t_ms += ms;
+    }
+    m->ev_pending = 0;
+    return BM_OK;
+}
+
+extern "C" bm_status bm_timing_enable(bm_handle m, int on) { if (!m) return BM_ERR_ARG; m->timing = on; return BM_OK; }
+extern "C" bm_status bm_timing_read(bm_handle m, double* ms, double* bytes, int* frames, int reset) {
+    if (!m) return BM_ERR_ARG;
+    BM_TRY(timing_drain(m));
+    if (ms) *ms = m->t_ms;
+    if (bytes) *bytes = m->t_bytes;
+    if (frames) *frames = m->t_frames;
+    if (reset) { m->t_ms = 0; m->t_bytes = 0; m->t_frames = 0; }
+    return BM_OK;
+}
+
 static bm_status warp_device(bm_mosaic_s* m, const uchar4* d_bgrx, const double H[9], bm_frame_info* info, bool want_flag) {
     BmFramePlan plan;
     bm_make_plan(H, m->cfg.frame_w, m->cfg.frame_h, m->cfg.canvas_w, m->cfg.canvas_h, &plan);
     const size_t need = (size_t)bm_win_w(plan.reg) * bm_win_h(plan.reg);
     if (plan.valid && need > m->blend.scratch_px) { bm_set_error("warp window %zu px exceeds scratch %zu px", need, m->blend.scratch_px); return BM_ERR_UNSUPPORTED; }
+    if (m->timing && m->ev_pending == bm_mosaic_s::kEvRing) BM_TRY(timing_drain(m));
+    if (m->timing) BM_CUDA_OK(cudaEventRecord(m->ev0[m->ev_pending], m->stream));
     BM_CUDA_OK(bm_launch_warp_blend(m->blend, d_bgrx, plan, m->stream));
+    if (m->timing) {
+        BM_CUDA_OK(cudaEventRecord(m->ev1[m->ev_pending], m->stream));
+        m->ev_pending++;
+        const double N = (double)m->cfg.frame_w * m->cfg.frame_h, A = plan.valid ? (double)bm_win_w(plan.win) * bm_win_h(plan.win) : 0.0;
+        m->t_bytes += 3.0 * N + 6.0 * A; m->t_frames++;
+    }
     fill_info_plan(info, plan);
     if (info && want_flag) {
         int f = 0;
@@ -292,13 +332,8 @@ static void matmul3(const double* A, const double* B, double* C) {
     }
 }
 
-extern "C" bm_status bm_process_frame(bm_handle m, const uint8_t* h_bgr, size_t stride, bm_frame_info* info_out) {
-    if (!m || !h_bgr) { bm_set_error("bm_process_frame: null"); return BM_ERR_ARG; }
-    BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+static bm_status process_uploaded(bm_mosaic_s* m, int slot, bm_frame_info* info_out) {
     bm_frame_info info; memset(&info, 0, sizeof(info));
-    m->cur ^= 1;
-    const int slot = m->cur;
-    BM_TRY(upload(m, h_bgr, stride, slot));
     // detect + match + RANSAC on the device; one small D2H read of (n_matches, H_rel) -- the reference's control
     // flow (skip / reject prints) needs them on the host at this point anyway.
     double H_rel[9]; int have_h = 0;
@@ -321,6 +356,24 @@ extern "C" bm_status bm_process_frame(bm_handle m, const uint8_t* h_bgr, size_t 
     info.status = ret;
     if (info_out) *info_out = info;
     return ret;
+}
+
+extern "C" bm_status bm_process_frame(bm_handle m, const uint8_t* h_bgr, size_t stride, bm_frame_info* info_out) {
+    if (!m || !h_bgr) { bm_set_error("bm_process_frame: null"); return BM_ERR_ARG; }
+    BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+    m->cur ^= 1;
+    const int slot = m->cur;
+    BM_TRY(upload(m, h_bgr, stride, slot));
+    return process_uploaded(m, slot, info_out);
+}
+
+extern "C" bm_status bm_process_frame_device(bm_handle m, const uint8_t* d_bgr, bm_frame_info* info_out) {
+    if (!m || !d_bgr) { bm_set_error("bm_process_frame_device: null"); return BM_ERR_ARG; }
+    BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+    m->cur ^= 1;
+    const int slot = m->cur;
+    BM_CUDA_OK(bm_launch_ingest(d_bgr, m->cfg.frame_h, m->cfg.frame_w, m->d_gray[slot], m->d_bgrx[slot], m->stream));
+    return process_uploaded(m, slot, info_out);
 }
 
 // features / matches of the last frame

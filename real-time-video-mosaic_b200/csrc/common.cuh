@@ -39,4 +39,7 @@ void bm_set_error(const char* fmt, ...);
         }                                                                                  \
     } while (0)
 
+extern long long g_bm_launches;          // kernels launched by this library (bench.py reports it)
+#define BM_COUNT_LAUNCHES(n) (g_bm_launches += (n))
+
 static inline int bm_div_up(int a, int b) { return (a + b - 1) / b; }

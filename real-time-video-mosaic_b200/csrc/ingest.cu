@@ -44,7 +44,7 @@ cudaError_t bm_launch_ingest(const uint8_t* d_bgr, int h, int w, uint8_t* d_gray
     const size_t n = (size_t)h * w;
     const bool vec = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_bgr) & 3) == 0) &&
                      ((reinterpret_cast<uintptr_t>(d_gray) & 3) == 0) && ((reinterpret_cast<uintptr_t>(d_bgrx) & 15) == 0);
-    if (vec) k_ingest4<<<(unsigned)((n / 4 + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint32_t*>(d_bgr), (int)(n / 4), d_gray, d_bgrx);
-    else k_ingest1<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_bgr, (int)n, d_gray, d_bgrx);
+    if (vec) BM_COUNT_LAUNCHES(1), k_ingest4<<<(unsigned)((n / 4 + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint32_t*>(d_bgr), (int)(n / 4), d_gray, d_bgrx);
+    else BM_COUNT_LAUNCHES(1), k_ingest1<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_bgr, (int)n, d_gray, d_bgrx);
     return cudaGetLastError();
 }

@@ -151,15 +151,15 @@ __global__ void __launch_bounds__(1024) k_select_sort(int mode, double ratio, co
 
 cudaError_t bm_match_hamming(const BmKeypoints& cur, const BmKeypoints& prev, BmMatches& m, cudaStream_t s) {
     const int blocks = (BM_KP_CAP * 32) / 256;
-    k_hamming_nn<<<blocks, 256, 0, s>>>(cur.desc, cur.count, prev.desc, prev.count, m.nn_q2t, m.d_q2t);
-    k_hamming_nn<<<blocks, 256, 0, s>>>(prev.desc, prev.count, cur.desc, cur.count, m.nn_t2q, m.d_t2q);
-    k_select_sort<<<1, 1024, 0, s>>>(0, 0.0, cur.count, prev.count, m, cur.pt, prev.pt);
+    BM_COUNT_LAUNCHES(1), k_hamming_nn<<<blocks, 256, 0, s>>>(cur.desc, cur.count, prev.desc, prev.count, m.nn_q2t, m.d_q2t);
+    BM_COUNT_LAUNCHES(1), k_hamming_nn<<<blocks, 256, 0, s>>>(prev.desc, prev.count, cur.desc, cur.count, m.nn_t2q, m.d_t2q);
+    BM_COUNT_LAUNCHES(1), k_select_sort<<<1, 1024, 0, s>>>(0, 0.0, cur.count, prev.count, m, cur.pt, prev.pt);
     return cudaGetLastError();
 }
 
 cudaError_t bm_match_l2_ratio(const BmKeypoints& cur, const BmKeypoints& prev, BmMatches& m, double ratio, cudaStream_t s) {
     const int blocks = (BM_KP_CAP * 32) / 256;
-    k_l2_knn2<<<blocks, 256, 0, s>>>(cur.desc, cur.count, prev.desc, prev.count, m.nn_q2t, m.d_q2t, m.nn2_q2t, m.d2_q2t);
-    k_select_sort<<<1, 1024, 0, s>>>(1, ratio, cur.count, prev.count, m, cur.pt, prev.pt);
+    BM_COUNT_LAUNCHES(1), k_l2_knn2<<<blocks, 256, 0, s>>>(cur.desc, cur.count, prev.desc, prev.count, m.nn_q2t, m.d_q2t, m.nn2_q2t, m.d2_q2t);
+    BM_COUNT_LAUNCHES(1), k_select_sort<<<1, 1024, 0, s>>>(1, ratio, cur.count, prev.count, m, cur.pt, prev.pt);
     return cudaGetLastError();
 }

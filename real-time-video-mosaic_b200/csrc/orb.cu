@@ -82,15 +82,23 @@ __global__ void __launch_bounds__(256) k_fast_score(BmOrbLevels lv, const uint8_
 #pragma unroll
         for (int i = 0; i < 16; ++i) { P |= (unsigned)(d[i] > FAST_THR) << i; N |= (unsigned)(d[i] < -FAST_THR) << i; }
         if (has9(P) || has9(N)) {
-            // cornerScore<16>: max over the 16 arcs of min(d) and of min(-d), minus 1
-            int best = FAST_THR;
+            // cornerScore<16>: max over the 16 arcs of min(d) and of min(-d), minus 1 (window minima / maxima by doubling)
+            int lo2[16], hi2[16], lo4[16], hi4[16], lo8[16], hi8[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { lo2[i] = min(d[i], d[(i + 1) & 15]); hi2[i] = max(d[i], d[(i + 1) & 15]); }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { lo4[i] = min(lo2[i], lo2[(i + 2) & 15]); hi4[i] = max(hi2[i], hi2[(i + 2) & 15]); }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { lo8[i] = min(lo4[i], lo4[(i + 4) & 15]); hi8[i] = max(hi4[i], hi4[(i + 4) & 15]); }
+            int amax = -100000, bmin = 100000;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-                int mn = d[i], mx = d[i];
-#pragma unroll
-                for (int k = 1; k < 9; ++k) { const int v = d[(i + k) & 15]; mn = min(mn, v); mx = max(mx, v); }
-                best = max(best, max(mn, -mx));
+                amax = max(amax, min(lo8[i], d[(i + 8) & 15]));
+                bmin = min(bmin, max(hi8[i], d[(i + 8) & 15]));
             }
+            int best = FAST_THR;
+            if (amax > best) best = amax;
+            if (0 - bmin > best) best = 0 - bmin;
             s = best - 1;
         }
     }
@@ -323,19 +331,20 @@ __global__ void __launch_bounds__(256) k_orb_describe(BmOrbLevels lv, const uint
     for (int i = t; i < (2 * RR + 1) * (2 * PR + 1); i += 256) {
         const int ry = i / (2 * PR + 1), bx = i % (2 * PR + 1);
         const uint8_t* r = &raw[ry][bx];
+        // OpenCV's float row filter: first tap a product, the rest FMAs, left to right
         float a = __fmul_rn(g0, (float)r[0]);
-        a = __fadd_rn(a, __fmul_rn(g1, (float)r[1])); a = __fadd_rn(a, __fmul_rn(g2, (float)r[2]));
-        a = __fadd_rn(a, __fmul_rn(g3, (float)r[3])); a = __fadd_rn(a, __fmul_rn(g2, (float)r[4]));
-        a = __fadd_rn(a, __fmul_rn(g1, (float)r[5])); a = __fadd_rn(a, __fmul_rn(g0, (float)r[6]));
+        a = __fmaf_rn(g1, (float)r[1], a); a = __fmaf_rn(g2, (float)r[2], a); a = __fmaf_rn(g3, (float)r[3], a);
+        a = __fmaf_rn(g2, (float)r[4], a); a = __fmaf_rn(g1, (float)r[5], a); a = __fmaf_rn(g0, (float)r[6], a);
         rowf[ry][bx] = a;
     }
     __syncthreads();
     for (int i = t; i < (2 * PR + 1) * (2 * PR + 1); i += 256) {
         const int by = i / (2 * PR + 1), bx = i % (2 * PR + 1);
-        float a = __fmul_rn(g0, rowf[by][bx]);
-        a = __fadd_rn(a, __fmul_rn(g1, rowf[by + 1][bx])); a = __fadd_rn(a, __fmul_rn(g2, rowf[by + 2][bx]));
-        a = __fadd_rn(a, __fmul_rn(g3, rowf[by + 3][bx])); a = __fadd_rn(a, __fmul_rn(g2, rowf[by + 4][bx]));
-        a = __fadd_rn(a, __fmul_rn(g1, rowf[by + 5][bx])); a = __fadd_rn(a, __fmul_rn(g0, rowf[by + 6][bx]));
+        // OpenCV's float column filter: symmetric form with FMAs
+        float a = __fmul_rn(g3, rowf[by + 3][bx]);
+        a = __fmaf_rn(g2, __fadd_rn(rowf[by + 4][bx], rowf[by + 2][bx]), a);
+        a = __fmaf_rn(g1, __fadd_rn(rowf[by + 5][bx], rowf[by + 1][bx]), a);
+        a = __fmaf_rn(g0, __fadd_rn(rowf[by + 6][bx], rowf[by][bx]), a);
         int v = __float2int_rn(a);
         blr[by][bx] = (uint8_t)max(0, min(255, v));
     }
@@ -433,16 +442,16 @@ cudaError_t bm_orb_detect(BmOrb* o, const uint8_t* d_gray, BmKeypoints* out) {
     const dim3 blk(32, 8);
     for (int l = 1; l < BM_ORB_LEVELS; ++l) {
         const BmOrbLevel &P = lv.l[l - 1], &L = lv.l[l];
-        k_resize_exact<<<dim3((L.w + 31) / 32, (L.h + 7) / 8), blk, 0, s>>>(o->pyr + P.off, P.w, P.h, o->pyr + L.off, L.w, L.h);
+        BM_COUNT_LAUNCHES(1), k_resize_exact<<<dim3((L.w + 31) / 32, (L.h + 7) / 8), blk, 0, s>>>(o->pyr + P.off, P.w, P.h, o->pyr + L.off, L.w, L.h);
     }
     const int tiles0 = ((lv.l[0].w + 31) / 32) * ((lv.l[0].h + 7) / 8);
-    k_fast_score<<<dim3(tiles0, BM_ORB_LEVELS), blk, 0, s>>>(lv, o->pyr, o->score);
-    k_fast_nms<<<dim3(tiles0, BM_ORB_LEVELS), blk, 0, s>>>(lv, o->score, o->cand, o->ctr, o->hist);
-    k_fast_threshold<<<1, 32, 0, s>>>(lv, o->ctr, o->hist);
-    k_harris<<<(lv.total_cand + 255) / 256, 256, 0, s>>>(lv, o->pyr, o->cand, o->cand2, o->ctr);
-    k_harris_select<<<BM_ORB_LEVELS, 1024, 0, s>>>(lv, o->cand2, o->ctr, o->keep);
-    k_orb_emit<<<BM_ORB_LEVELS, 1024, 0, s>>>(lv, o->cand2, o->ctr, o->keep, *out);
-    k_ic_angle<<<(BM_KP_CAP * 32) / 256, 256, 0, s>>>(lv, o->pyr, *out);
-    k_orb_describe<<<BM_KP_CAP, 256, 0, s>>>(lv, o->pyr, *out);
+    BM_COUNT_LAUNCHES(1), k_fast_score<<<dim3(tiles0, BM_ORB_LEVELS), blk, 0, s>>>(lv, o->pyr, o->score);
+    BM_COUNT_LAUNCHES(1), k_fast_nms<<<dim3(tiles0, BM_ORB_LEVELS), blk, 0, s>>>(lv, o->score, o->cand, o->ctr, o->hist);
+    BM_COUNT_LAUNCHES(1), k_fast_threshold<<<1, 32, 0, s>>>(lv, o->ctr, o->hist);
+    BM_COUNT_LAUNCHES(1), k_harris<<<(lv.total_cand + 255) / 256, 256, 0, s>>>(lv, o->pyr, o->cand, o->cand2, o->ctr);
+    BM_COUNT_LAUNCHES(1), k_harris_select<<<BM_ORB_LEVELS, 1024, 0, s>>>(lv, o->cand2, o->ctr, o->keep);
+    BM_COUNT_LAUNCHES(1), k_orb_emit<<<BM_ORB_LEVELS, 1024, 0, s>>>(lv, o->cand2, o->ctr, o->keep, *out);
+    BM_COUNT_LAUNCHES(1), k_ic_angle<<<(BM_KP_CAP * 32) / 256, 256, 0, s>>>(lv, o->pyr, *out);
+    BM_COUNT_LAUNCHES(1), k_orb_describe<<<BM_KP_CAP, 256, 0, s>>>(lv, o->pyr, *out);
     return cudaGetLastError();
 }

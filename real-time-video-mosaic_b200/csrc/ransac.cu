@@ -477,6 +477,6 @@ cudaError_t bm_launch_ransac(const float2* d_src, const float2* d_dst, const int
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    k_ransac_homography<<<1, RS_THREADS, smem, s>>>(d_src, d_dst, d_count, thresh, max_iters, confidence, d_mask, d_out);
+    BM_COUNT_LAUNCHES(1), k_ransac_homography<<<1, RS_THREADS, smem, s>>>(d_src, d_dst, d_count, thresh, max_iters, confidence, d_mask, d_out);
     return cudaGetLastError();
 }

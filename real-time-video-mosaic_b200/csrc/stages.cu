@@ -122,3 +122,19 @@ extern "C" bm_status bm_ransac_homography(const float* h_src, const float* h_dst
     if (n_inliers) *n_inliers = r.n_inliers;
     return BM_OK;
 }
+
+extern "C" bm_status bm_orb_debug_level(const uint8_t* d_gray, int h, int w, int level, uint8_t* h_img, uint8_t* h_score, int* lw, int* lh) {
+    if (!d_gray || level < 0 || level >= BM_ORB_LEVELS) return BM_ERR_ARG;
+    BmOrb* o = nullptr; BmKeypoints k;
+    if (bm_orb_create(&o, h, w, 700, nullptr) != 0 || bm_kp_alloc(&k, 32) != 0) return BM_ERR_CUDA;
+    cudaError_t e = bm_orb_detect(o, d_gray, &k);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    const BmOrbLevel& L = o->lv.l[level];
+    if (lw) *lw = L.w;
+    if (lh) *lh = L.h;
+    if (e == cudaSuccess && h_img) e = cudaMemcpy(h_img, o->pyr + L.off, (size_t)L.w * L.h, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && h_score) e = cudaMemcpy(h_score, o->score + L.off, (size_t)L.w * L.h, cudaMemcpyDeviceToHost);
+    bm_kp_free(&k); bm_orb_destroy(o);
+    BM_CUDA_OK(e);
+    return BM_OK;
+}

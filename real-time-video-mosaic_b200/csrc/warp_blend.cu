@@ -498,9 +498,9 @@ static inline dim3 grid2(int w, int h, dim3 b) { return dim3((w + b.x - 1) / b.x
 
 cudaError_t bm_launch_full_rowscan(const BmBlendBufs& b, cudaStream_t s) {
     const int rows = b.canvas_h;
-    k_rowscan<<<bm_div_up(rows * 32, 256), 256, 0, s>>>(b.canvas, b.canvas_w, 0, b.canvas_w, 0, rows, b.g_old, 0, b.flags, 0);
+    BM_COUNT_LAUNCHES(1), k_rowscan<<<bm_div_up(rows * 32, 256), 256, 0, s>>>(b.canvas, b.canvas_w, 0, b.canvas_w, 0, rows, b.g_old, 0, b.flags, 0);
     const int nb = bm_div_up(rows, BM_BLK_ROWS);
-    k_blockmin<<<dim3(bm_div_up(b.canvas_w, 256), nb), 256, 0, s>>>(b.g_old, b.canvas_w, rows, 0, nb, b.gblk_old, b.flags, 0);
+    BM_COUNT_LAUNCHES(1), k_blockmin<<<dim3(bm_div_up(b.canvas_w, 256), nb), 256, 0, s>>>(b.g_old, b.canvas_w, rows, 0, nb, b.gblk_old, b.flags, 0);
     return cudaGetLastError();
 }
 
@@ -510,16 +510,16 @@ cudaError_t bm_launch_blend_from_wbuf(const BmBlendBufs& b, const BmFramePlan& p
     const int rw = bm_win_w(plan.reg), rh = bm_win_h(plan.reg);
     const dim3 blk(32, 8);
     // mask_new row structure over W (only needed when there is overlap: kernels exit early on flags[0]==0)
-    k_rowscan<<<bm_div_up(wh * 32, 256), 256, 0, s>>>(b.wbuf, ww, 0, ww, 0, wh, b.g_new, 0, b.flags, 1);
+    BM_COUNT_LAUNCHES(1), k_rowscan<<<bm_div_up(wh * 32, 256), 256, 0, s>>>(b.wbuf, ww, 0, ww, 0, wh, b.g_new, 0, b.flags, 1);
     const int nbw = bm_div_up(wh, BM_BLK_ROWS);
-    k_blockmin<<<dim3(bm_div_up(ww, 256), nbw), 256, 0, s>>>(b.g_new, ww, wh, 0, nbw, b.gblk_new, b.flags, 1);
-    k_dt_weights<<<grid2(rw, rh, blk), blk, 0, s>>>(b.plan, b.g_old, b.gblk_old, b.g_new, b.gblk_new, b.rbuf, b.flags);
-    k_blur_rows<<<grid2(ww, rh, blk), blk, 0, s>>>(b.plan, b.rbuf, b.hbuf, b.flags);
-    k_blur_cols_blend<<<grid2(ww, wh, blk), blk, 0, s>>>(b.plan, b.hbuf, b.wbuf, b.canvas, b.flags);
+    BM_COUNT_LAUNCHES(1), k_blockmin<<<dim3(bm_div_up(ww, 256), nbw), 256, 0, s>>>(b.g_new, ww, wh, 0, nbw, b.gblk_new, b.flags, 1);
+    BM_COUNT_LAUNCHES(1), k_dt_weights<<<grid2(rw, rh, blk), blk, 0, s>>>(b.plan, b.g_old, b.gblk_old, b.g_new, b.gblk_new, b.rbuf, b.flags);
+    BM_COUNT_LAUNCHES(1), k_blur_rows<<<grid2(ww, rh, blk), blk, 0, s>>>(b.plan, b.rbuf, b.hbuf, b.flags);
+    BM_COUNT_LAUNCHES(1), k_blur_cols_blend<<<grid2(ww, wh, blk), blk, 0, s>>>(b.plan, b.hbuf, b.wbuf, b.canvas, b.flags);
     // refresh the persistent row structure for the rows the frame touched
-    k_rowscan<<<bm_div_up(wh * 32, 256), 256, 0, s>>>(b.canvas, b.canvas_w, 0, b.canvas_w, plan.win.y0, wh, b.g_old, plan.win.y0, b.flags, 0);
+    BM_COUNT_LAUNCHES(1), k_rowscan<<<bm_div_up(wh * 32, 256), 256, 0, s>>>(b.canvas, b.canvas_w, 0, b.canvas_w, plan.win.y0, wh, b.g_old, plan.win.y0, b.flags, 0);
     const int Y0 = plan.win.y0 / BM_BLK_ROWS, Y1 = bm_div_up(plan.win.y1, BM_BLK_ROWS);
-    k_blockmin<<<dim3(bm_div_up(b.canvas_w, 256), Y1 - Y0), 256, 0, s>>>(b.g_old, b.canvas_w, b.canvas_h, Y0, Y1, b.gblk_old, b.flags, 0);
+    BM_COUNT_LAUNCHES(1), k_blockmin<<<dim3(bm_div_up(b.canvas_w, 256), Y1 - Y0), 256, 0, s>>>(b.g_old, b.canvas_w, b.canvas_h, Y0, Y1, b.gblk_old, b.flags, 0);
     return cudaGetLastError();
 }
 
@@ -530,7 +530,7 @@ cudaError_t bm_launch_warp_blend(const BmBlendBufs& b, const uchar4* d_src, cons
     e = cudaMemsetAsync(b.flags, 0, 4 * sizeof(int), s);
     if (e != cudaSuccess) return e;
     const dim3 blk(32, 8);
-    k_warp_window<<<grid2(bm_win_w(plan.win), bm_win_h(plan.win), blk), blk, 0, s>>>(d_src, b.plan, b.canvas, b.wbuf, b.flags);
+    BM_COUNT_LAUNCHES(1), k_warp_window<<<grid2(bm_win_w(plan.win), bm_win_h(plan.win), blk), blk, 0, s>>>(d_src, b.plan, b.canvas, b.wbuf, b.flags);
     return bm_launch_blend_from_wbuf(b, plan, s);
 }
 
@@ -539,16 +539,16 @@ cudaError_t bm_launch_warp_full_bgr(const uint8_t* d_src, int sh, int sw, const 
     if (e != cudaSuccess) return e;
     if (!plan.valid) return cudaSuccess;
     const dim3 blk(32, 8);
-    k_warp_full_bgr<<<grid2(bm_win_w(plan.win), bm_win_h(plan.win), blk), blk, 0, s>>>(d_src, plan, d_dst);
+    BM_COUNT_LAUNCHES(1), k_warp_full_bgr<<<grid2(bm_win_w(plan.win), bm_win_h(plan.win), blk), blk, 0, s>>>(d_src, plan, d_dst);
     return cudaGetLastError();
 }
 
 cudaError_t bm_launch_pack_canvas(const uint8_t* d_bgr, uchar4* d_canvas, int n, cudaStream_t s) {
-    k_pack_canvas<<<bm_div_up(n, 256), 256, 0, s>>>(d_bgr, d_canvas, n);
+    BM_COUNT_LAUNCHES(1), k_pack_canvas<<<bm_div_up(n, 256), 256, 0, s>>>(d_bgr, d_canvas, n);
     return cudaGetLastError();
 }
 cudaError_t bm_launch_unpack_canvas(const uchar4* d_canvas, uint8_t* d_bgr, int n, cudaStream_t s) {
-    k_unpack_canvas<<<bm_div_up(bm_div_up(n, 4), 256), 256, 0, s>>>(d_canvas, d_bgr, n);
+    BM_COUNT_LAUNCHES(1), k_unpack_canvas<<<bm_div_up(bm_div_up(n, 4), 256), 256, 0, s>>>(d_canvas, d_bgr, n);
     return cudaGetLastError();
 }
 cudaError_t bm_launch_extract_wbuf(const uint8_t* d_warped, const BmFramePlan& plan, const BmBlendBufs& b, cudaStream_t s) {
@@ -557,25 +557,25 @@ cudaError_t bm_launch_extract_wbuf(const uint8_t* d_warped, const BmFramePlan& p
     e = cudaMemsetAsync(b.flags, 0, 4 * sizeof(int), s);
     if (e != cudaSuccess) return e;
     const dim3 blk(32, 8);
-    k_extract_wbuf<<<grid2(bm_win_w(plan.win), bm_win_h(plan.win), blk), blk, 0, s>>>(d_warped, plan, b.canvas, b.wbuf, b.flags);
+    BM_COUNT_LAUNCHES(1), k_extract_wbuf<<<grid2(bm_win_w(plan.win), bm_win_h(plan.win), blk), blk, 0, s>>>(d_warped, plan, b.canvas, b.wbuf, b.flags);
     return cudaGetLastError();
 }
 cudaError_t bm_launch_paste(uchar4* canvas, int canvas_w, const uchar4* src, int sw, int sh, int ox, int oy, cudaStream_t s) {
     const dim3 blk(32, 8);
-    k_paste<<<grid2(sw, sh, blk), blk, 0, s>>>(canvas, canvas_w, src, sw, sh, ox, oy);
+    BM_COUNT_LAUNCHES(1), k_paste<<<grid2(sw, sh, blk), blk, 0, s>>>(canvas, canvas_w, src, sw, sh, ox, oy);
     return cudaGetLastError();
 }
 cudaError_t bm_launch_dt_mask(const uint8_t* d_mask, int h, int w, float* d_out, uint16_t* g, uint16_t* gblk, cudaStream_t s) {
-    k_rowscan_u8<<<bm_div_up(h * 32, 256), 256, 0, s>>>(d_mask, w, h, g);
+    BM_COUNT_LAUNCHES(1), k_rowscan_u8<<<bm_div_up(h * 32, 256), 256, 0, s>>>(d_mask, w, h, g);
     const int nb = bm_div_up(h, BM_BLK_ROWS);
-    k_blockmin<<<dim3(bm_div_up(w, 256), nb), 256, 0, s>>>(g, w, h, 0, nb, gblk, nullptr, 0);
+    BM_COUNT_LAUNCHES(1), k_blockmin<<<dim3(bm_div_up(w, 256), nb), 256, 0, s>>>(g, w, h, 0, nb, gblk, nullptr, 0);
     const dim3 blk(32, 8);
-    k_dt_from_g<<<grid2(w, h, blk), blk, 0, s>>>(g, gblk, w, h, d_out);
+    BM_COUNT_LAUNCHES(1), k_dt_from_g<<<grid2(w, h, blk), blk, 0, s>>>(g, gblk, w, h, d_out);
     return cudaGetLastError();
 }
 cudaError_t bm_launch_blur31(const float* d_in, int h, int w, float* d_tmp, float* d_out, cudaStream_t s) {
     const dim3 blk(32, 8);
-    k_blur31_rows_plain<<<grid2(w, h, blk), blk, 0, s>>>(d_in, h, w, d_tmp);
-    k_blur31_cols_plain<<<grid2(w, h, blk), blk, 0, s>>>(d_tmp, h, w, d_out);
+    BM_COUNT_LAUNCHES(1), k_blur31_rows_plain<<<grid2(w, h, blk), blk, 0, s>>>(d_in, h, w, d_tmp);
+    BM_COUNT_LAUNCHES(1), k_blur31_cols_plain<<<grid2(w, h, blk), blk, 0, s>>>(d_tmp, h, w, d_out);
     return cudaGetLastError();
 }

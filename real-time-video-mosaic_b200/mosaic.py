@@ -140,6 +140,34 @@ class VideMosaic:
         self.frame_prev = frame_cur
         self._canvas_cache = None
 
+    # ---- device-resident / raw-pointer variants used by bench.py ------------------------------------------------
+    def process_frame_ptr(self, host_ptr):
+        """process_frame on a raw host pointer (e.g. pinned memory): no NumPy checks, no prints.  Returns the status."""
+        info = _lib.BmFrameInfo()
+        st = _lib.check(self._lib.bm_process_frame(self._h, C.c_void_p(host_ptr), 0, C.byref(info)), "bm_process_frame")
+        self.last_info = info
+        self._canvas_cache = None
+        return st
+
+    def process_frame_device(self, dev_ptr):
+        """process_frame on a frame already in device memory (packed BGR).  Returns the status."""
+        info = _lib.BmFrameInfo()
+        st = _lib.check(self._lib.bm_process_frame_device(self._h, C.c_void_p(dev_ptr), C.byref(info)), "bm_process_frame_device")
+        self.last_info = info
+        self._canvas_cache = None
+        return st
+
+    def timing(self, enable=None, reset=False):
+        """CUDA-event timing of the warp/blend chain: returns (ms, algorithmic bytes = 3N + 6A per frame, frames)."""
+        if enable is not None:
+            _lib.check(self._lib.bm_timing_enable(self._h, int(enable)))
+        ms = C.c_double(0); by = C.c_double(0); fr = C.c_int(0)
+        _lib.check(self._lib.bm_timing_read(self._h, C.byref(ms), C.byref(by), C.byref(fr), int(reset)))
+        return ms.value, by.value, fr.value
+
+    def sync(self):
+        _lib.check(self._lib.bm_sync(self._h))
+
     # ---- features / matches of the last frame (lazy small D2H), cv2-like objects --------------------------------
     def _fetch_kp(self, which):
         cap = self._lib.bm_keypoint_capacity()

@@ -134,3 +134,14 @@ def ransac_homography(src: np.ndarray, dst: np.ndarray, thresh: float = 2.0, max
                                         H.ctypes.data_as(C.POINTER(C.c_double)), C.byref(ok), C.byref(it), C.byref(ni)),
                "bm_ransac_homography")
     return (H.reshape(3, 3) if ok.value else None), it.value, ni.value
+
+
+def orb_debug_level(gray: torch.Tensor, level: int):
+    """(level image, FAST score map) of the device ORB pyramid -- parity probe for the INTER_LINEAR_EXACT chain / FAST."""
+    lib = _lib.load()
+    h, w = gray.shape
+    img = np.empty(h * w, np.uint8); sc = np.empty(h * w, np.uint8); lw = C.c_int(0); lh = C.c_int(0)
+    torch.cuda.synchronize()
+    _lib.check(lib.bm_orb_debug_level(_ptr(gray), h, w, level, _np_ptr(img), _np_ptr(sc), C.byref(lw), C.byref(lh)), "bm_orb_debug_level")
+    n = lw.value * lh.value
+    return img[:n].reshape(lh.value, lw.value).copy(), sc[:n].reshape(lh.value, lw.value).copy()

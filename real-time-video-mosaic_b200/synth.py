@@ -38,7 +38,7 @@ class DroneSweep:
     relative homography cur->prev (what findHomography estimates, main.py:727) is exactly D_t."""
 
     def __init__(self, width=1920, height=1080, seed=1234, ground=None, ground_size=4096, max_step=12.0,
-                 noise_sigma=2.0, start=None):
+                 noise_sigma=2.0, start=None, max_travel=None):
         self.w, self.h = width, height
         self.rng = np.random.default_rng(seed)
         self.ground = make_ground(ground_size, seed) if ground is None else ground
@@ -49,6 +49,8 @@ class DroneSweep:
         self.max_step = max_step
         self.noise_sigma = noise_sigma
         self.t = 0
+        self.max_travel = max_travel      # reverse the along-track direction after this many px (keeps the mosaic on the canvas)
+        self._y0 = sy
         self.dir = np.array([0.0, -1.0])      # fly "up" the ground: the canvas grows upward like the reference's layout
         self._noise = None
         if noise_sigma > 0:
@@ -61,7 +63,11 @@ class DroneSweep:
         gs = self.ground.shape[0]
         # serpentine: reverse the along-track direction near the ground borders, drift sideways slowly
         cy = self.C[1, 2]
-        if cy < 96 and self.dir[1] < 0:
+        if self.max_travel is not None and self.dir[1] < 0 and (self._y0 - cy) > self.max_travel:
+            self.dir = np.array([0.0, 1.0])
+        elif self.max_travel is not None and self.dir[1] > 0 and cy > self._y0 - 8:
+            self.dir = np.array([0.0, -1.0])
+        elif cy < 96 and self.dir[1] < 0:
             self.dir = np.array([0.0, 1.0])
         elif cy > gs - self.h - 96 and self.dir[1] > 0:
             self.dir = np.array([0.0, -1.0])
