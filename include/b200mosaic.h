@@ -136,6 +136,8 @@ bm_status bm_get_matches(bm_handle h, int* h_q, int* h_t, float* h_dist, int cap
 int bm_keypoint_capacity(void);
 /* debug / parity: level `level` of the ORB pyramid (INTER_LINEAR_EXACT chain) and its FAST score map (either may be NULL) */
 bm_status bm_orb_debug_level(const uint8_t* d_gray, int h, int w, int level, uint8_t* h_img, uint8_t* h_score, int* lw, int* lh);
+/* debug / parity: one Gaussian (dog=0, level 0..5) or DoG (dog=1, level 0..4) image of the SIFT pyramid; returns the number of octaves in *noct */
+bm_status bm_sift_debug_level(const uint8_t* d_gray, int h, int w, int octave, int level, int dog, float* h_out, int* lw, int* lh, int* noct);
 
 #ifdef __cplusplus
 }

@@ -1,6 +1,640 @@
-// sift.cu -- placeholder until the SIFT kernels land (build order: ORB path first).
+// sift.cu -- cv2.SIFT_create(700).detectAndCompute on the device (reference call sites: main.py:33,112,718).
+// Spec: OpenCV 4.x features2d/sift (nOctaveLayers 3, contrastThreshold 0.04, edgeThreshold 10, sigma 1.6, CV_32F
+// descriptors, first octave -1), pinned in SURVEY.md A.5 and oracle/sift.py.
+//
+// B200 design:
+//  * whole Gaussian + DoG pyramid resident in HBM (~0.5 GB at 1080p); each Gaussian level is produced by ONE fused kernel:
+//    shared-memory tile (+halo, reflect-101), separable row pass then column pass in OpenCV's float accumulation order
+//    (rows: FMA left to right; columns: symmetric FMA form), and the DoG level is written in the same pass
+//    (out - in), so the DoG pyramid costs no extra reads.
+//  * extrema: one thread per DoG pixel of layers 1..3 (short-circuited 26-neighbour test), sub-pixel refinement inline
+//    (rare), survivors appended with per-warp ballot/popc compaction; duplicates (two start pixels converging to the
+//    same cell) are removed with an atomic claim bitmap instead of cv2's sort.
+//  * orientation histograms: one warp per candidate; descriptors: one CTA per keypoint, trilinear scatter into a
+//    shared 6x6x10 histogram with 64-bit fixed-point atomics (deterministic, order independent).
+//  * retainBest(700): 3-pass radix select on the float response bits (ties kept), final order = cv2's
+//    KeyPoint_LessThan order (x, y, size desc, angle, response desc, octave desc) by rank counting.
 #include "sift.cuh"
-struct BmSift { int dummy; };
-int bm_sift_create(BmSift** out, int, int, int, cudaStream_t) { *out = nullptr; bm_set_error("SIFT detector not built yet"); return -1; }
-void bm_sift_destroy(BmSift*) {}
-cudaError_t bm_sift_detect(BmSift*, const uint8_t*, BmKeypoints*) { return cudaErrorNotSupported; }
+#include <float.h>
+#include <math.h>
+#include <string.h>
+#include <new>
+#include <vector>
+
+#define SIFT_MAX_OCT 12
+#define SIFT_LAYERS 3
+#define SIFT_BORDER 5
+#define SIFT_CAND_CAP (1 << 17)
+#define SIFT_KP_CAP (1 << 17)
+
+struct SiftOct { int w, h; long long g[6]; long long d[5]; long long claim; };   // float offsets; claim: bit offset / 32
+struct SiftLayout { int noct; SiftOct o[SIFT_MAX_OCT]; };
+
+struct SiftCand {            // refined extremum (adjustLocalExtrema output)
+    int o, layer, r, c;
+    float ptx, pty, size, response;
+    int octave_packed;
+};
+
+struct BmSift {
+    int w, h, nfeatures;
+    SiftLayout lay;
+    float* pyr;              // all Gaussian + DoG levels
+    float* up;               // 2x upsampled gray (float)
+    unsigned* claim;         // one bit per (octave, layer, pixel)
+    size_t claim_words;
+    SiftCand* cand; int* ctr;            // ctr[0] = #cand, ctr[1] = #kp (pre-select), ctr[2] = overflow, ctr[3] = #selected
+    float2* kpt; float* ksize; float* kangle; float* kresp; int* koct;     // pre-select keypoint list (SIFT_KP_CAP)
+    int* sel;                // indices of the selected keypoints
+    unsigned* hist;          // radix-select scratch
+    float* kernels_dev;      // 6 kernels x 32 taps
+    cudaStream_t stream;
+};
+
+__constant__ float c_sift_k[6][32];     // [0] = base blur (sigma 1.249), [1..5] = level blurs; taps 0..K-1
+static const int h_sift_ksize[6] = {11, 11, 13, 17, 21, 27};
+
+// ------------------------------------------------------------------------------------------------------------------
+// 2x bilinear upsample of the gray image to float (cv2.resize INTER_LINEAR: weights .25/.75, edge replicate; exact)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sift_upsample(const uint8_t* __restrict__ gray, int w, int h, float* __restrict__ up) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int W = 2 * w, H = 2 * h;
+    if (x >= W || y >= H) return;
+    // fx = x/2 - 0.25: even x -> (.25, .75) on (k-1, k); odd x -> (.75, .25) on (k, k+1)
+    const int kx = x >> 1, ky = y >> 1;
+    int x0, x1, y0, y1; float ax, ay;      // weight of the SECOND tap
+    if (x & 1) { x0 = kx; x1 = min(kx + 1, w - 1); ax = 0.25f; } else { x0 = max(kx - 1, 0); x1 = kx; ax = 0.75f; }
+    if (y & 1) { y0 = ky; y1 = min(ky + 1, h - 1); ay = 0.25f; } else { y0 = max(ky - 1, 0); y1 = ky; ay = 0.75f; }
+    const float r0 = (float)gray[(size_t)y0 * w + x0] * (1.f - ax) + (float)gray[(size_t)y0 * w + x1] * ax;
+    const float r1 = (float)gray[(size_t)y1 * w + x0] * (1.f - ax) + (float)gray[(size_t)y1 * w + x1] * ax;
+    up[(size_t)y * W + x] = r0 * (1.f - ay) + r1 * ay;
+}
+
+__device__ __forceinline__ int refl101(int i, int n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+    if (i < 0) i = 0;                      // degenerate tiny images
+    return i;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// fused separable Gaussian (radius R) + DoG.  Tile 32x32 outputs, 256 threads.
+// ------------------------------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(256) k_sift_blur(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ dog,
+                                                   int w, int h, int kidx) {
+    constexpr int T = 32, S = T + 2 * R, K = 2 * R + 1;
+    __shared__ float tile[S][S + 1];
+    __shared__ float rowf[S][T + 1];
+    const int bx = blockIdx.x * T, by = blockIdx.y * T;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    for (int i = tid; i < S * S; i += 256) {
+        const int ty = i / S, tx = i % S;
+        const int gx = refl101(bx + tx - R, w), gy = refl101(by + ty - R, h);
+        tile[ty][tx] = in[(size_t)gy * w + gx];
+    }
+    __syncthreads();
+    const float* kk = c_sift_k[kidx];
+    for (int i = tid; i < S * T; i += 256) {          // row pass: first tap a product, then FMAs left to right
+        const int ty = i / T, tx = i % T;
+        float a = __fmul_rn(kk[0], tile[ty][tx]);
+#pragma unroll
+        for (int t = 1; t < K; ++t) a = __fmaf_rn(kk[t], tile[ty][tx + t], a);
+        rowf[ty][tx] = a;
+    }
+    __syncthreads();
+    for (int i = tid; i < T * T; i += 256) {          // column pass: symmetric FMA form
+        const int ty = i / T, tx = i % T;
+        const int gx = bx + tx, gy = by + ty;
+        if (gx >= w || gy >= h) continue;
+        float a = __fmul_rn(kk[R], rowf[ty + R][tx]);
+#pragma unroll
+        for (int t = 1; t <= R; ++t) a = __fmaf_rn(kk[R + t], __fadd_rn(rowf[ty + R + t][tx], rowf[ty + R - t][tx]), a);
+        out[(size_t)gy * w + gx] = a;
+        if (dog) dog[(size_t)gy * w + gx] = __fsub_rn(a, tile[ty + R][tx + R]);
+    }
+}
+
+// next octave base = level 3 decimated by 2 (INTER_NEAREST: dst(x,y) = src(2x,2y))
+__global__ void __launch_bounds__(256) k_sift_decimate(const float* __restrict__ src, int sw, float* __restrict__ dst, int dw, int dh) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    dst[(size_t)y * dw + x] = src[(size_t)(2 * y) * sw + 2 * x];
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// scale-space extrema + adjustLocalExtrema
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool solve3_cramer(const float a[3][3], const float b[3], float x[3]) {
+    // Matx33f::solve(DECOMP_LU) fast path: explicit determinant / Cramer in float
+    float d = a[0][0] * (a[1][1] * a[2][2] - a[1][2] * a[2][1]) - a[0][1] * (a[1][0] * a[2][2] - a[1][2] * a[2][0]) +
+              a[0][2] * (a[1][0] * a[2][1] - a[1][1] * a[2][0]);
+    if (d == 0.f) { x[0] = x[1] = x[2] = 0.f; return false; }
+    d = 1.f / d;
+    x[0] = d * (b[0] * (a[1][1] * a[2][2] - a[1][2] * a[2][1]) - a[0][1] * (b[1] * a[2][2] - a[1][2] * b[2]) + a[0][2] * (b[1] * a[2][1] - a[1][1] * b[2]));
+    x[1] = d * (a[0][0] * (b[1] * a[2][2] - a[1][2] * b[2]) - b[0] * (a[1][0] * a[2][2] - a[1][2] * a[2][0]) + a[0][2] * (a[1][0] * b[2] - b[1] * a[2][0]));
+    x[2] = d * (a[0][0] * (a[1][1] * b[2] - b[1] * a[2][1]) - a[0][1] * (a[1][0] * b[2] - b[1] * a[2][0]) + b[0] * (a[1][0] * a[2][1] - a[1][1] * a[2][0]));
+    return true;
+}
+
+__device__ bool adjust_local_extrema(const float* __restrict__ pyr, const SiftOct& O, int o, int& layer, int& r, int& c, SiftCand& out) {
+    const float img_scale = 1.f / 255.f, deriv_scale = img_scale * 0.5f, second_deriv_scale = img_scale, cross_deriv_scale = img_scale * 0.25f;
+    const int w = O.w, h = O.h;
+    float xi = 0, xr = 0, xc = 0;
+    int i = 0;
+    for (; i < 5; ++i) {
+        const float* img = pyr + O.d[layer]; const float* prv = pyr + O.d[layer - 1]; const float* nxt = pyr + O.d[layer + 1];
+        const size_t p = (size_t)r * w + c;
+        const float dD[3] = {(img[p + 1] - img[p - 1]) * deriv_scale, (img[p + w] - img[p - w]) * deriv_scale, (nxt[p] - prv[p]) * deriv_scale};
+        const float v2 = img[p] * 2.f;
+        const float dxx = (img[p + 1] + img[p - 1] - v2) * second_deriv_scale;
+        const float dyy = (img[p + w] + img[p - w] - v2) * second_deriv_scale;
+        const float dss = (nxt[p] + prv[p] - v2) * second_deriv_scale;
+        const float dxy = (img[p + w + 1] - img[p + w - 1] - img[p - w + 1] + img[p - w - 1]) * cross_deriv_scale;
+        const float dxs = (nxt[p + 1] - nxt[p - 1] - prv[p + 1] + prv[p - 1]) * cross_deriv_scale;
+        const float dys = (nxt[p + w] - nxt[p - w] - prv[p + w] + prv[p - w]) * cross_deriv_scale;
+        const float Hm[3][3] = {{dxx, dxy, dxs}, {dxy, dyy, dys}, {dxs, dys, dss}};
+        float X[3];
+        solve3_cramer(Hm, dD, X);
+        xi = -X[2]; xr = -X[1]; xc = -X[0];
+        if (fabsf(xi) < 0.5f && fabsf(xr) < 0.5f && fabsf(xc) < 0.5f) break;
+        if (fabsf(xi) > (float)(INT_MAX / 3) || fabsf(xr) > (float)(INT_MAX / 3) || fabsf(xc) > (float)(INT_MAX / 3)) return false;
+        c += __float2int_rn(xc); r += __float2int_rn(xr); layer += __float2int_rn(xi);
+        if (layer < 1 || layer > SIFT_LAYERS || c < SIFT_BORDER || c >= w - SIFT_BORDER || r < SIFT_BORDER || r >= h - SIFT_BORDER) return false;
+    }
+    if (i >= 5) return false;
+    {
+        const float* img = pyr + O.d[layer]; const float* prv = pyr + O.d[layer - 1]; const float* nxt = pyr + O.d[layer + 1];
+        const size_t p = (size_t)r * w + c;
+        const float d0 = (img[p + 1] - img[p - 1]) * deriv_scale, d1 = (img[p + w] - img[p - w]) * deriv_scale, d2 = (nxt[p] - prv[p]) * deriv_scale;
+        const float t = d0 * xc + d1 * xr + d2 * xi;
+        const float contr = img[p] * img_scale + t * 0.5f;
+        if (fabsf(contr) * SIFT_LAYERS < 0.04f) return false;
+        const float v2 = img[p] * 2.f;
+        const float dxx = (img[p + 1] + img[p - 1] - v2) * second_deriv_scale;
+        const float dyy = (img[p + w] + img[p - w] - v2) * second_deriv_scale;
+        const float dxy = (img[p + w + 1] - img[p + w - 1] - img[p - w + 1] + img[p - w - 1]) * cross_deriv_scale;
+        const float tr = dxx + dyy, det = dxx * dyy - dxy * dxy;
+        if (det <= 0 || tr * tr * 10.f >= 11.f * 11.f * det) return false;
+        out.o = o; out.layer = layer; out.r = r; out.c = c;
+        out.ptx = (c + xc) * (float)(1 << o);
+        out.pty = (r + xr) * (float)(1 << o);
+        out.octave_packed = o + (layer << 8) + (__double2int_rn(((double)xi + 0.5) * 255.0) << 16);
+        out.size = 1.6f * powf(2.f, (layer + xi) / (float)SIFT_LAYERS) * (float)(1 << o) * 2.f;
+        out.response = fabsf(contr);
+    }
+    return true;
+}
+
+// one thread per pixel of DoG layers 1..3 of octave `o` (blockIdx.z = layer-1)
+__global__ void __launch_bounds__(256) k_sift_extrema(SiftLayout lay, int o, const float* __restrict__ pyr, unsigned* __restrict__ claim,
+                                                      SiftCand* __restrict__ cand, int* __restrict__ ctr) {
+    const SiftOct O = lay.o[o];
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y * blockDim.y + threadIdx.y;
+    int layer = blockIdx.z + 1;
+    const int w = O.w, h = O.h;
+    bool found = false;
+    SiftCand cd;
+    if (c >= SIFT_BORDER && c < w - SIFT_BORDER && r >= SIFT_BORDER && r < h - SIFT_BORDER) {
+        const float* cur = pyr + O.d[layer];
+        const size_t p = (size_t)r * w + c;
+        const float v = cur[p];
+        if (fabsf(v) > 1.0f) {                 // threshold = cvFloor(0.5*0.04/3*255) = 1
+            const float* prv = pyr + O.d[layer - 1]; const float* nxt = pyr + O.d[layer + 1];
+            bool ext;
+            if (v > 0) {
+                ext = v >= cur[p - 1] && v >= cur[p + 1] && v >= cur[p - w - 1] && v >= cur[p - w] && v >= cur[p - w + 1] &&
+                      v >= cur[p + w - 1] && v >= cur[p + w] && v >= cur[p + w + 1];
+                if (ext) ext = v >= nxt[p] && v >= nxt[p - 1] && v >= nxt[p + 1] && v >= nxt[p - w - 1] && v >= nxt[p - w] && v >= nxt[p - w + 1] &&
+                               v >= nxt[p + w - 1] && v >= nxt[p + w] && v >= nxt[p + w + 1];
+                if (ext) ext = v >= prv[p] && v >= prv[p - 1] && v >= prv[p + 1] && v >= prv[p - w - 1] && v >= prv[p - w] && v >= prv[p - w + 1] &&
+                               v >= prv[p + w - 1] && v >= prv[p + w] && v >= prv[p + w + 1];
+            } else {
+                ext = v <= cur[p - 1] && v <= cur[p + 1] && v <= cur[p - w - 1] && v <= cur[p - w] && v <= cur[p - w + 1] &&
+                      v <= cur[p + w - 1] && v <= cur[p + w] && v <= cur[p + w + 1];
+                if (ext) ext = v <= nxt[p] && v <= nxt[p - 1] && v <= nxt[p + 1] && v <= nxt[p - w - 1] && v <= nxt[p - w] && v <= nxt[p - w + 1] &&
+                               v <= nxt[p + w - 1] && v <= nxt[p + w] && v <= nxt[p + w + 1];
+                if (ext) ext = v <= prv[p] && v <= prv[p - 1] && v <= prv[p + 1] && v <= prv[p - w - 1] && v <= prv[p - w] && v <= prv[p - w + 1] &&
+                               v <= prv[p + w - 1] && v <= prv[p + w] && v <= prv[p + w + 1];
+            }
+            if (ext) {
+                int r1 = r, c1 = c;
+                if (adjust_local_extrema(pyr, O, o, layer, r1, c1, cd)) {
+                    // duplicate removal: the first start pixel that reaches a cell claims it
+                    const long long bit = O.claim + ((long long)(layer - 1) * h + r1) * w + c1;
+                    const unsigned m = 1u << (bit & 31);
+                    const unsigned old = atomicOr(&claim[bit >> 5], m);
+                    found = (old & m) == 0;
+                }
+            }
+        }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, found);
+    if (bal) {
+        const int lane = threadIdx.x & 31, leader = __ffs(bal) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&ctr[0], __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (found) {
+            const int idx = base + __popc(bal & ((1u << lane) - 1u));
+            if (idx < SIFT_CAND_CAP) cand[idx] = cd; else ctr[2] = 1;
+        }
+    }
+}
+
+// hal::fastAtan2 (vector path: FMA Horner), degrees
+__device__ __forceinline__ float sift_atan2_deg(float y, float x) {
+    const float k = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = 0.9997878412794807f * k, p3 = -0.3258083974640975f * k, p5 = 0.1555786518463281f * k, p7 = -0.04432655554792128f * k;
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float c = __fdiv_rn(fminf(ax, ay), __fadd_rn(fmaxf(ax, ay), 2.220446049250313e-16f));
+    const float c2 = __fmul_rn(c, c);
+    float a = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmaf_rn(c2, p7, p5), c2, p3), c2, p1), c);
+    if (ay > ax) a = 90.f - a;
+    if (x < 0.f) a = 180.f - a;
+    if (y < 0.f) a = 360.f - a;
+    return a;
+}
+
+// calcOrientationHist + peak extraction: one warp per refined candidate
+__global__ void __launch_bounds__(256) k_sift_orient(SiftLayout lay, const float* __restrict__ pyr, const SiftCand* __restrict__ cand,
+                                                     int* __restrict__ ctr, float2* __restrict__ kpt, float* __restrict__ ksize,
+                                                     float* __restrict__ kangle, float* __restrict__ kresp, int* __restrict__ koct) {
+    __shared__ unsigned long long sh_hist[8][36];
+    __shared__ float sh_f[8][40];
+    const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ci = blockIdx.x * 8 + wi;
+    int ncand = ctr[0]; if (ncand > SIFT_CAND_CAP) ncand = SIFT_CAND_CAP;
+    if (ci >= ncand) return;
+    const SiftCand cd = cand[ci];
+    const SiftOct O = lay.o[cd.o];
+    const float* img = pyr + O.g[cd.layer];
+    const int w = O.w, h = O.h;
+    const float scl_octv = cd.size * 0.5f / (float)(1 << cd.o);
+    const int radius = __float2int_rn(4.5f * scl_octv);
+    const float sigma = 1.5f * scl_octv;
+    const float expf_scale = -1.f / (2.f * sigma * sigma);
+    for (int i = lane; i < 36; i += 32) sh_hist[wi][i] = 0ull;
+    __syncwarp();
+    const int side = 2 * radius + 1, len = side * side;
+    for (int k = lane; k < len; k += 32) {
+        const int i = k / side - radius, j = k % side - radius;
+        const int y = cd.r + i, x = cd.c + j;
+        if (y <= 0 || y >= h - 1 || x <= 0 || x >= w - 1) continue;
+        const float dx = img[(size_t)y * w + x + 1] - img[(size_t)y * w + x - 1];
+        const float dy = img[(size_t)(y - 1) * w + x] - img[(size_t)(y + 1) * w + x];
+        const float wgt = expf((float)(i * i + j * j) * expf_scale);
+        const float ori = sift_atan2_deg(dy, dx);
+        const float mag = sqrtf(dx * dx + dy * dy);
+        int bin = __float2int_rn((36.f / 360.f) * ori);
+        if (bin >= 36) bin -= 36;
+        if (bin < 0) bin += 36;
+        // deterministic accumulation: 2^-24 fixed point, integer atomics
+        atomicAdd(&sh_hist[wi][bin], (unsigned long long)__float2ll_rn(wgt * mag * 16777216.f));
+    }
+    __syncwarp();
+    for (int i = lane; i < 36; i += 32) sh_f[wi][i + 2] = (float)((double)sh_hist[wi][i] * (1.0 / 16777216.0));
+    __syncwarp();
+    if (lane == 0) { sh_f[wi][0] = sh_f[wi][36]; sh_f[wi][1] = sh_f[wi][37]; sh_f[wi][38] = sh_f[wi][2]; sh_f[wi][39] = sh_f[wi][3]; }
+    __syncwarp();
+    float hv[2];
+    float mx = 0.f;
+    for (int q = 0; q < 2; ++q) {
+        const int i = lane + 32 * q;
+        hv[q] = 0.f;
+        if (i < 36) {
+            const float* t = &sh_f[wi][i + 2];
+            hv[q] = (t[-2] + t[2]) * (1.f / 16.f) + (t[-1] + t[1]) * (4.f / 16.f) + t[0] * (6.f / 16.f);
+            mx = fmaxf(mx, hv[q]);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    __syncwarp();
+    for (int q = 0; q < 2; ++q) { const int i = lane + 32 * q; if (i < 36) sh_f[wi][i] = hv[q]; }     // smoothed hist in [0,36)
+    __syncwarp();
+    const float mag_thr = mx * 0.8f;
+    for (int q = 0; q < 2; ++q) {
+        const int j = lane + 32 * q;
+        bool peak = false; float angle = 0.f;
+        if (j < 36) {
+            const int l = j > 0 ? j - 1 : 35, r2 = j < 35 ? j + 1 : 0;
+            const float hj = sh_f[wi][j], hl = sh_f[wi][l], hr = sh_f[wi][r2];
+            if (hj > hl && hj > hr && hj >= mag_thr) {
+                float bin = j + 0.5f * (hl - hr) / (hl - 2 * hj + hr);
+                bin = bin < 0 ? 36 + bin : (bin >= 36 ? bin - 36 : bin);
+                angle = 360.f - (360.f / 36.f) * bin;
+                if (fabsf(angle - 360.f) < FLT_EPSILON) angle = 0.f;
+                peak = true;
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, peak);
+        if (bal) {
+            const int leader = __ffs(bal) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&ctr[1], __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (peak) {
+                const int idx = base + __popc(bal & ((1u << lane) - 1u));
+                if (idx < SIFT_KP_CAP) {
+                    kpt[idx] = make_float2(cd.ptx, cd.pty); ksize[idx] = cd.size; kangle[idx] = angle; kresp[idx] = cd.response; koct[idx] = cd.octave_packed;
+                } else ctr[2] = 1;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// retainBest(nfeatures) (ties kept) via radix select on the response bits, then cv2's KeyPoint_LessThan order
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_sift_select(int nfeatures, int* __restrict__ ctr, const float* __restrict__ kresp, int* __restrict__ sel) {
+    __shared__ unsigned hist[2048];
+    __shared__ unsigned s_prefix, s_mask, s_remaining;
+    __shared__ int s_count;
+    int n = ctr[1]; if (n > SIFT_KP_CAP) n = SIFT_KP_CAP;
+    const int tid = threadIdx.x;
+    unsigned thr_bits = 0;      // keep response bits >= thr_bits
+    if (n > nfeatures) {
+        if (tid == 0) { s_prefix = 0; s_mask = 0; s_remaining = (unsigned)nfeatures; }
+        __syncthreads();
+        const int shifts[3] = {21, 10, 0}; const int bitsn[3] = {11, 11, 10};
+        for (int pass = 0; pass < 3; ++pass) {
+            for (int i = tid; i < 2048; i += blockDim.x) hist[i] = 0;
+            __syncthreads();
+            const unsigned prefix = s_prefix, mask = s_mask;
+            for (int i = tid; i < n; i += blockDim.x) {
+                const unsigned b = __float_as_uint(kresp[i]);
+                if ((b & mask) == prefix) atomicAdd(&hist[(b >> shifts[pass]) & ((1u << bitsn[pass]) - 1u)], 1u);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                unsigned rem = s_remaining, cum = 0; int bin = (1 << bitsn[pass]) - 1;
+                for (; bin >= 0; --bin) { if (cum + hist[bin] >= rem) break; cum += hist[bin]; }
+                if (bin < 0) bin = 0;
+                s_remaining = rem - cum;
+                s_prefix = prefix | ((unsigned)bin << shifts[pass]);
+                s_mask = mask | (((1u << bitsn[pass]) - 1u) << shifts[pass]);
+            }
+            __syncthreads();
+        }
+        thr_bits = s_prefix;     // exact bits of the nfeatures-th largest response
+    }
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) {
+        if (__float_as_uint(kresp[i]) >= thr_bits) { const int p = atomicAdd(&s_count, 1); if (p < BM_KP_CAP) sel[p] = i; }
+    }
+    __syncthreads();
+    if (tid == 0) { int m = s_count; if (m > BM_KP_CAP) { m = BM_KP_CAP; ctr[2] = 1; } ctr[3] = m; }
+}
+
+__device__ __forceinline__ bool kp_less(float ax, float ay, float as, float aa, float ar, int ao, int ai,
+                                        float bx, float by, float bs, float ba, float br, int bo, int bi) {
+    if (ax != bx) return ax < bx;
+    if (ay != by) return ay < by;
+    if (as != bs) return as > bs;
+    if (aa != ba) return aa < ba;
+    if (ar != br) return ar > br;
+    if (ao != bo) return ao > bo;
+    return ai < bi;
+}
+
+// order the selected keypoints (cv2's KeyPoint_LessThan), rescale to the input image (first octave -1), emit
+__global__ void __launch_bounds__(1024) k_sift_emit(const int* __restrict__ ctr, const int* __restrict__ sel, const float2* __restrict__ kpt,
+                                                    const float* __restrict__ ksize, const float* __restrict__ kangle, const float* __restrict__ kresp,
+                                                    const int* __restrict__ koct, BmKeypoints out) {
+    const int m = ctr[3];
+    for (int a = threadIdx.x; a < m; a += blockDim.x) {
+        const int i = sel[a];
+        const float2 pi = kpt[i]; const float si = ksize[i], ai = kangle[i], ri = kresp[i]; const int oi = koct[i];
+        int rank = 0;
+        for (int b = 0; b < m; ++b) {
+            const int j = sel[b];
+            const float2 pj = kpt[j];
+            rank += kp_less(pj.x, pj.y, ksize[j], kangle[j], kresp[j], koct[j], j, pi.x, pi.y, si, ai, ri, oi, i) ? 1 : 0;
+        }
+        // firstOctave = -1: octave byte -1, pt and size halved
+        const int oc = (oi & ~255) | ((oi - 1) & 255);
+        out.pt[rank] = make_float2(pi.x * 0.5f, pi.y * 0.5f);
+        out.size[rank] = si * 0.5f;
+        out.angle[rank] = ai;
+        out.response[rank] = ri;
+        out.octave[rank] = oc;
+        out.lxy[rank] = make_int2(0, 0);
+    }
+    if (threadIdx.x == 0) *out.count = m;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// calcSIFTDescriptor: one CTA per keypoint
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sift_describe(SiftLayout lay, const float* __restrict__ pyr, BmKeypoints kp) {
+    const int k = blockIdx.x;
+    if (k >= *kp.count) return;
+    __shared__ unsigned long long hist[6 * 6 * 10];
+    __shared__ float raw[128];
+    __shared__ float red[8];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 360; i += 256) hist[i] = 0ull;
+    const int packed = kp.octave[k];
+    int octave = packed & 255; const int layer = (packed >> 8) & 255;
+    octave = octave < 128 ? octave : (-128 | octave);
+    const float scale = octave >= 0 ? 1.f / (float)(1 << octave) : (float)(1 << -octave);
+    const float size = kp.size[k] * scale;
+    const float2 p0 = kp.pt[k];
+    const float ptfx = p0.x * scale, ptfy = p0.y * scale;
+    const SiftOct O = lay.o[octave + 1];
+    const float* img = pyr + O.g[layer];
+    const int cols = O.w, rows = O.h;
+    float ori = 360.f - kp.angle[k];
+    if (fabsf(ori - 360.f) < FLT_EPSILON) ori = 0.f;
+    const float scl = size * 0.5f;
+    const int ptx = __float2int_rn(ptfx), pty = __float2int_rn(ptfy);
+    float cos_t = cosf(ori * (float)(3.14159265358979323846 / 180.0)), sin_t = sinf(ori * (float)(3.14159265358979323846 / 180.0));
+    const float bins_per_rad = 8.f / 360.f, exp_scale = -1.f / (4.f * 4.f * 0.5f), hist_width = 3.f * scl;
+    int radius = __float2int_rn(hist_width * 1.4142135623730951f * 5.f * 0.5f);
+    radius = min(radius, (int)sqrt((double)cols * cols + (double)rows * rows));
+    cos_t /= hist_width; sin_t /= hist_width;
+    __syncthreads();
+    const int side = 2 * radius + 1, len = side * side;
+    for (int q = tid; q < len; q += 256) {
+        const int i = q / side - radius, j = q % side - radius;
+        const float c_rot = j * cos_t - i * sin_t, r_rot = j * sin_t + i * cos_t;
+        float rbin = r_rot + 2.f - 0.5f, cbin = c_rot + 2.f - 0.5f;
+        const int r = pty + i, c = ptx + j;
+        if (!(rbin > -1 && rbin < 4 && cbin > -1 && cbin < 4 && r > 0 && r < rows - 1 && c > 0 && c < cols - 1)) continue;
+        const float dx = img[(size_t)r * cols + c + 1] - img[(size_t)r * cols + c - 1];
+        const float dy = img[(size_t)(r - 1) * cols + c] - img[(size_t)(r + 1) * cols + c];
+        const float wgt = expf((c_rot * c_rot + r_rot * r_rot) * exp_scale);
+        const float o_deg = sift_atan2_deg(dy, dx);
+        const float mag = sqrtf(dx * dx + dy * dy) * wgt;
+        float obin = (o_deg - ori) * bins_per_rad;
+        const int r0 = (int)floorf(rbin), c0 = (int)floorf(cbin); int o0 = (int)floorf(obin);
+        rbin -= r0; cbin -= c0; obin -= o0;
+        if (o0 < 0) o0 += 8;
+        if (o0 >= 8) o0 -= 8;
+        const float v_r1 = mag * rbin, v_r0 = mag - v_r1;
+        const float v_rc11 = v_r1 * cbin, v_rc10 = v_r1 - v_rc11, v_rc01 = v_r0 * cbin, v_rc00 = v_r0 - v_rc01;
+        const float v111 = v_rc11 * obin, v110 = v_rc11 - v111, v101 = v_rc10 * obin, v100 = v_rc10 - v101;
+        const float v011 = v_rc01 * obin, v010 = v_rc01 - v011, v001 = v_rc00 * obin, v000 = v_rc00 - v001;
+        const int idx = ((r0 + 1) * 6 + c0 + 1) * 10 + o0;
+        const float FX = 16777216.f;
+#define HADD(off, v) atomicAdd(&hist[idx + (off)], (unsigned long long)__float2ll_rn((v) * FX))
+        HADD(0, v000); HADD(1, v001); HADD(10, v010); HADD(11, v011); HADD(60, v100); HADD(61, v101); HADD(70, v110); HADD(71, v111);
+#undef HADD
+    }
+    __syncthreads();
+    // fold the circular orientation bins, gather the 4x4x8 core
+    if (tid < 128) {
+        const int i = tid >> 5, j = (tid >> 3) & 3, o = tid & 7;
+        const int idx = ((i + 1) * 6 + (j + 1)) * 10;
+        long long v = (long long)hist[idx + o];
+        if (o == 0) v += (long long)hist[idx + 8];
+        if (o == 1) v += (long long)hist[idx + 9];
+        raw[tid] = (float)((double)v * (1.0 / 16777216.0));
+    }
+    __syncthreads();
+    // norm -> clip at 0.2*norm -> renormalise to 512 -> saturate_cast<uchar>
+    float v = tid < 128 ? raw[tid] : 0.f;
+    float s = v * v;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((tid & 31) == 0) red[tid >> 5] = s;
+    __syncthreads();
+    const float nrm2 = red[0] + red[1] + red[2] + red[3];
+    const float thr = sqrtf(nrm2) * 0.2f;
+    __syncthreads();
+    v = fminf(v, thr);
+    s = tid < 128 ? v * v : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((tid & 31) == 0) red[tid >> 5] = s;
+    __syncthreads();
+    const float n2 = 512.f / fmaxf(sqrtf(red[0] + red[1] + red[2] + red[3]), FLT_EPSILON);
+    if (tid < 128) {
+        const int q = __float2int_rn(v * n2);
+        kp.desc[(size_t)k * 128 + tid] = (uint8_t)max(0, min(255, q));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------------------------------
+static void gaussian_kernel(int ksize, double sigma, float* out) {
+    // cv::getGaussianKernel(ksize, sigma, CV_32F): exp and normalisation in double, cast to float
+    std::vector<double> k(ksize);
+    double sum = 0;
+    for (int i = 0; i < ksize; ++i) { const double x = i - (ksize - 1) * 0.5; k[i] = exp(-0.5 * x * x / (sigma * sigma)); sum += k[i]; }
+    for (int i = 0; i < ksize; ++i) out[i] = (float)(k[i] / sum);
+}
+
+int bm_sift_create(BmSift** out, int h, int w, int nfeatures, cudaStream_t s) {
+    BmSift* o = new (std::nothrow) BmSift();
+    if (!o) return -1;
+    memset(o, 0, sizeof(*o));
+    o->w = w; o->h = h; o->nfeatures = nfeatures; o->stream = s;
+    const int bw = 2 * w, bh = 2 * h;
+    int noct = (int)nearbyint(log((double)(bw < bh ? bw : bh)) / log(2.0) - 2.0) + 1;
+    if (noct < 1) noct = 1;
+    if (noct > SIFT_MAX_OCT) noct = SIFT_MAX_OCT;
+    o->lay.noct = noct;
+    long long off = 0, cbits = 0;
+    int ow = bw, oh = bh;
+    for (int i = 0; i < noct; ++i) {
+        SiftOct& O = o->lay.o[i];
+        O.w = ow; O.h = oh;
+        const long long n = ((long long)ow * oh + 63) & ~63LL;
+        for (int l = 0; l < 6; ++l) { O.g[l] = off; off += n; }
+        for (int l = 0; l < 5; ++l) { O.d[l] = off; off += n; }
+        O.claim = cbits; cbits += 3LL * ow * oh;
+        ow /= 2; oh /= 2;
+        if (ow < 1 || oh < 1) { o->lay.noct = i + 1; break; }
+    }
+    o->claim_words = (size_t)((cbits + 31) / 32 + 1);
+    float hk[6][32]; memset(hk, 0, sizeof(hk));
+    {
+        // createInitialImage: sig_diff = sqrtf(max(sigma^2 - (2*0.5)^2, 0.01f)); buildGaussianPyramid: incremental sigmas
+        const float sig_diff = sqrtf(fmaxf(1.6f * 1.6f - 0.5f * 0.5f * 4.f, 0.01f));
+        gaussian_kernel(h_sift_ksize[0], (double)sig_diff, hk[0]);
+        const double k = pow(2.0, 1.0 / 3.0);
+        for (int i = 1; i <= 5; ++i) {
+            const double sig_prev = pow(k, (double)(i - 1)) * 1.6, sig_total = sig_prev * k;
+            const double sg = sqrt(sig_total * sig_total - sig_prev * sig_prev);
+            int ks = (int)nearbyint(sg * 8 + 1) | 1;
+            if (ks != h_sift_ksize[i]) { bm_set_error("unexpected SIFT kernel size %d at level %d", ks, i); delete o; return -1; }
+            gaussian_kernel(ks, sg, hk[i]);
+        }
+    }
+    bool ok = cudaMalloc(&o->pyr, (size_t)off * sizeof(float)) == cudaSuccess && cudaMalloc(&o->up, (size_t)bw * bh * sizeof(float)) == cudaSuccess &&
+              cudaMalloc(&o->claim, o->claim_words * 4) == cudaSuccess && cudaMalloc(&o->cand, SIFT_CAND_CAP * sizeof(SiftCand)) == cudaSuccess &&
+              cudaMalloc(&o->ctr, 16 * sizeof(int)) == cudaSuccess && cudaMalloc(&o->kpt, SIFT_KP_CAP * sizeof(float2)) == cudaSuccess &&
+              cudaMalloc(&o->ksize, SIFT_KP_CAP * 4) == cudaSuccess && cudaMalloc(&o->kangle, SIFT_KP_CAP * 4) == cudaSuccess &&
+              cudaMalloc(&o->kresp, SIFT_KP_CAP * 4) == cudaSuccess && cudaMalloc(&o->koct, SIFT_KP_CAP * 4) == cudaSuccess &&
+              cudaMalloc(&o->sel, BM_KP_CAP * 4) == cudaSuccess;
+    if (ok) ok = cudaMemcpyToSymbol(c_sift_k, hk, sizeof(hk)) == cudaSuccess;
+    if (!ok) { bm_set_error("bm_sift_create: %s", cudaGetErrorString(cudaGetLastError())); bm_sift_destroy(o); return -1; }
+    *out = o;
+    return 0;
+}
+
+void bm_sift_destroy(BmSift* o) {
+    if (!o) return;
+    cudaFree(o->pyr); cudaFree(o->up); cudaFree(o->claim); cudaFree(o->cand); cudaFree(o->ctr); cudaFree(o->kpt); cudaFree(o->ksize);
+    cudaFree(o->kangle); cudaFree(o->kresp); cudaFree(o->koct); cudaFree(o->sel);
+    delete o;
+}
+
+template <int R>
+static void launch_blur(const float* in, float* out, float* dog, int w, int h, int kidx, cudaStream_t s) {
+    BM_COUNT_LAUNCHES(1), k_sift_blur<R><<<dim3((w + 31) / 32, (h + 31) / 32), dim3(32, 8), 0, s>>>(in, out, dog, w, h, kidx);
+}
+
+static void blur_level(int level, const float* in, float* out, float* dog, int w, int h, cudaStream_t s) {
+    switch (level) {
+        case 0: launch_blur<5>(in, out, dog, w, h, 0, s); break;
+        case 1: launch_blur<5>(in, out, dog, w, h, 1, s); break;
+        case 2: launch_blur<6>(in, out, dog, w, h, 2, s); break;
+        case 3: launch_blur<8>(in, out, dog, w, h, 3, s); break;
+        case 4: launch_blur<10>(in, out, dog, w, h, 4, s); break;
+        default: launch_blur<13>(in, out, dog, w, h, 5, s); break;
+    }
+}
+
+const float* bm_sift_level_ptr(BmSift* o, int octave, int level, int dog, int* w, int* h) {
+    const SiftOct& O = o->lay.o[octave];
+    if (w) *w = O.w;
+    if (h) *h = O.h;
+    return o->pyr + (dog ? O.d[level] : O.g[level]);
+}
+int bm_sift_num_octaves(BmSift* o) { return o->lay.noct; }
+
+cudaError_t bm_sift_detect(BmSift* o, const uint8_t* d_gray, BmKeypoints* out) {
+    cudaStream_t s = o->stream;
+    const SiftLayout& L = o->lay;
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(o->ctr, 0, 16 * sizeof(int), s)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(o->claim, 0, o->claim_words * 4, s)) != cudaSuccess) return e;
+    const dim3 blk(32, 8);
+    const int bw = 2 * o->w, bh = 2 * o->h;
+    BM_COUNT_LAUNCHES(1), k_sift_upsample<<<dim3((bw + 31) / 32, (bh + 7) / 8), blk, 0, s>>>(d_gray, o->w, o->h, o->up);
+    for (int oc = 0; oc < L.noct; ++oc) {
+        const SiftOct& O = L.o[oc];
+        if (oc == 0) blur_level(0, o->up, o->pyr + O.g[0], nullptr, O.w, O.h, s);
+        else {
+            const SiftOct& P = L.o[oc - 1];
+            BM_COUNT_LAUNCHES(1), k_sift_decimate<<<dim3((O.w + 31) / 32, (O.h + 7) / 8), blk, 0, s>>>(o->pyr + P.g[3], P.w, o->pyr + O.g[0], O.w, O.h);
+        }
+        for (int l = 1; l < 6; ++l) blur_level(l, o->pyr + O.g[l - 1], o->pyr + O.g[l], o->pyr + O.d[l - 1], O.w, O.h, s);
+    }
+    for (int oc = 0; oc < L.noct; ++oc) {
+        const SiftOct& O = L.o[oc];
+        if (O.w <= 2 * SIFT_BORDER || O.h <= 2 * SIFT_BORDER) continue;
+        BM_COUNT_LAUNCHES(1), k_sift_extrema<<<dim3((O.w + 31) / 32, (O.h + 7) / 8, 3), blk, 0, s>>>(L, oc, o->pyr, o->claim, o->cand, o->ctr);
+    }
+    BM_COUNT_LAUNCHES(1), k_sift_orient<<<SIFT_CAND_CAP / 8, 256, 0, s>>>(L, o->pyr, o->cand, o->ctr, o->kpt, o->ksize, o->kangle, o->kresp, o->koct);
+    BM_COUNT_LAUNCHES(1), k_sift_select<<<1, 1024, 0, s>>>(o->nfeatures, o->ctr, o->kresp, o->sel);
+    BM_COUNT_LAUNCHES(1), k_sift_emit<<<1, 1024, 0, s>>>(o->ctr, o->sel, o->kpt, o->ksize, o->kangle, o->kresp, o->koct, *out);
+    BM_COUNT_LAUNCHES(1), k_sift_describe<<<BM_KP_CAP, 256, 0, s>>>(L, o->pyr, *out);
+    return cudaGetLastError();
+}

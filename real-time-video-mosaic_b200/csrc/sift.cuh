@@ -7,3 +7,5 @@ struct BmSift;
 int bm_sift_create(BmSift** out, int h, int w, int nfeatures, cudaStream_t s);
 void bm_sift_destroy(BmSift* o);
 cudaError_t bm_sift_detect(BmSift* o, const uint8_t* d_gray, BmKeypoints* out);
+const float* bm_sift_level_ptr(BmSift* o, int octave, int level, int dog, int* w, int* h);
+int bm_sift_num_octaves(BmSift* o);

@@ -138,3 +138,27 @@ extern "C" bm_status bm_orb_debug_level(const uint8_t* d_gray, int h, int w, int
     BM_CUDA_OK(e);
     return BM_OK;
 }
+
+extern "C" bm_status bm_sift_debug_level(const uint8_t* d_gray, int h, int w, int octave, int level, int dog, float* h_out, int* lw, int* lh, int* noct) {
+    if (!d_gray) return BM_ERR_ARG;
+    BmSift* o = nullptr; BmKeypoints k;
+    if (bm_sift_create(&o, h, w, 700, nullptr) != 0) return BM_ERR_CUDA;
+    if (bm_kp_alloc(&k, 128) != 0) { bm_sift_destroy(o); return BM_ERR_CUDA; }
+    if (noct) *noct = bm_sift_num_octaves(o);
+    bm_status st = BM_OK;
+    if (octave < 0 || octave >= bm_sift_num_octaves(o) || level < 0 || level > (dog ? 4 : 5)) st = BM_ERR_ARG;
+    cudaError_t e = cudaSuccess;
+    if (st == BM_OK) {
+        e = bm_sift_detect(o, d_gray, &k);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        int ww = 0, hh = 0;
+        const float* p = bm_sift_level_ptr(o, octave, level, dog, &ww, &hh);
+        if (lw) *lw = ww;
+        if (lh) *lh = hh;
+        if (e == cudaSuccess && h_out) e = cudaMemcpy(h_out, p, (size_t)ww * hh * sizeof(float), cudaMemcpyDeviceToHost);
+    }
+    bm_kp_free(&k); bm_sift_destroy(o);
+    if (st != BM_OK) return st;
+    BM_CUDA_OK(e);
+    return BM_OK;
+}

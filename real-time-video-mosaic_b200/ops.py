@@ -145,3 +145,14 @@ def orb_debug_level(gray: torch.Tensor, level: int):
     _lib.check(lib.bm_orb_debug_level(_ptr(gray), h, w, level, _np_ptr(img), _np_ptr(sc), C.byref(lw), C.byref(lh)), "bm_orb_debug_level")
     n = lw.value * lh.value
     return img[:n].reshape(lh.value, lw.value).copy(), sc[:n].reshape(lh.value, lw.value).copy()
+
+
+def sift_debug_level(gray: torch.Tensor, octave: int, level: int, dog: bool = False):
+    """One Gaussian / DoG image of the device SIFT pyramid (float32) and the octave count -- parity probe."""
+    lib = _lib.load()
+    h, w = gray.shape
+    buf = np.empty(4 * h * w, np.float32); lw = C.c_int(0); lh = C.c_int(0); no = C.c_int(0)
+    torch.cuda.synchronize()
+    _lib.check(lib.bm_sift_debug_level(_ptr(gray), h, w, octave, level, int(dog), _np_ptr(buf), C.byref(lw), C.byref(lh), C.byref(no)),
+               "bm_sift_debug_level")
+    return buf[:lw.value * lh.value].reshape(lh.value, lw.value).copy(), no.value
