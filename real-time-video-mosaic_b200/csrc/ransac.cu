@@ -145,7 +145,9 @@ __device__ void block_sum(RsShared& sh, const double* v) {
 __device__ int jacobi9(RsShared& sh) {
     const int n = 9;
     for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) sh.V[i][j] = (i == j) ? 1.0 : 0.0;
+    sh.n_in = 0;
     for (int sweep = 0; sweep < 60; ++sweep) {
+        sh.n_in = sweep;
         double off = 0, diag = 0;
         for (int i = 0; i < n; ++i) { diag += sh.A[i][i] * sh.A[i][i]; for (int j = i + 1; j < n; ++j) off += sh.A[i][j] * sh.A[i][j]; }
         if (off <= 1e-32 * diag || off == 0.0) break;
@@ -244,10 +246,14 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_ransac_homography(const float
         return;
     }
     __shared__ unsigned long long rng;
+    __shared__ long long cyc[8];
+    if (tid < 8) cyc[tid] = 0;
+    const long long t_start = clock64();
     if (tid == 0) { rng = 0xFFFFFFFFFFFFFFFFULL; sh.niters = max_iters > 1 ? max_iters : 1; sh.iter = 0; sh.best_good = 0; sh.stop = 0; }
     __syncthreads();
     while (true) {
         // ---- one thread: next batch of accepted subsets, in cv::RNG order (getSubset, 10000 attempts each) ----
+        long long t0 = clock64();
         if (tid == 0) {
             int B = sh.niters - sh.iter; if (B > RS_BATCH) B = RS_BATCH;
             sh.batch = B; sh.fail_at = -1;
@@ -275,6 +281,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_ransac_homography(const float
             rng = st;
         }
         __syncthreads();
+        if (tid == 0) { const long long t1 = clock64(); cyc[0] += t1 - t0; t0 = t1; }
         const int B = sh.batch, fail_at = sh.fail_at;
         const int nb = fail_at >= 0 ? fail_at : B;
         // ---- warp b: hypothesis b: 4-point solve by lane 0, inlier count by all lanes ----
@@ -303,6 +310,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_ransac_homography(const float
         __syncthreads();
         // ---- one thread: sequential winner selection / adaptive iteration cap ----
         if (tid == 0) {
+            { const long long t1 = clock64(); cyc[1] += t1 - t0; t0 = t1; }
             for (int b = 0; b < nb; ++b) {
                 if (sh.iter >= sh.niters) break;
                 if (sh.valid[b]) {
@@ -317,11 +325,13 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_ransac_homography(const float
                 sh.iter++;
             }
             if (sh.iter >= sh.niters || fail_at >= 0) sh.stop = 1;
+            cyc[2] += clock64() - t0;
         }
         __syncthreads();
         if (sh.stop) break;
     }
     if (sh.best_good <= 0) { if (tid == 0) { out->iters = sh.iter; } return; }
+    long long tp = clock64();
     // ---- inlier mask of the winning hypothesis ----
     {
         float Hf[8];
@@ -372,9 +382,11 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_ransac_homography(const float
         }
         block_sum<45>(sh, acc);
         if (tid == 0) {
+            { const long long t1 = clock64(); cyc[3] += t1 - tp; tp = t1; }
             int k = 0;
             for (int a = 0; a < 9; ++a) for (int b = a; b < 9; ++b) { sh.A[a][b] = sh.sums[k]; sh.A[b][a] = sh.sums[k]; ++k; }
             const int e = jacobi9(sh);
+            { const long long t1 = clock64(); cyc[4] += t1 - tp; tp = t1; }
             double h0[9];
             for (int i = 0; i < 9; ++i) h0[i] = sh.V[i][e];
             const double inv[9] = {1.0 / smx, 0, cmx, 0, 1.0 / smy, cmy, 0, 0, 1};
@@ -464,7 +476,9 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_ransac_homography(const float
     if (tid == 0) {
         for (int i = 0; i < 8; ++i) out->H[i] = sh.lmx[i];
         out->H[8] = 1.0;
-        out->ok = 1; out->iters = sh.iter; out->n_inliers = sh.best_good; out->lm_iters = it;
+        out->ok = 1; out->iters = sh.iter; out->n_inliers = sh.best_good; out->lm_iters = it; out->jacobi_sweeps = sh.n_in;
+        cyc[5] = clock64() - tp; cyc[6] = clock64() - t_start;
+        for (int i = 0; i < 8; ++i) out->cyc[i] = cyc[i];
     }
 }
 

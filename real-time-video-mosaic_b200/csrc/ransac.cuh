@@ -9,7 +9,8 @@ struct BmRansacResult {      // written by the kernel, read back by the host (on
     int iters;               // RANSAC iterations executed
     int n_inliers;           // inliers of the winning hypothesis
     int lm_iters;
-    int pad;
+    int jacobi_sweeps;
+    long long cyc[8];        // SM cycles per phase: 0 subsets, 1 hypotheses, 2 selection, 3 mask+refit sums, 4 jacobi, 5 LM, 6 total
 };
 
 // src/dst: device float2[n] (n read from *d_count); thresh = ransacReprojThreshold; scratch: >= n bytes

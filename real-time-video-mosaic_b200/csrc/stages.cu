@@ -102,8 +102,35 @@ extern "C" bm_status bm_match_l2_knn2_ratio(const float* q, int nq, const float*
     return run_match(1, q8.data(), nq, t8.data(), nt, 128, ratio, oq, ot, od, m_out);
 }
 
+static bm_status ransac_host(const float* h_src, const float* h_dst, int n, double thresh, int max_iters, double confidence, BmRansacResult* res);
+
+extern "C" bm_status bm_ransac_profile(const float* h_src, const float* h_dst, int n, double thresh, int max_iters, double confidence,
+                                       double H[9], long long cycles[8], int* lm_iters, int* jacobi_sweeps) {
+    BmRansacResult r;
+    bm_status st = ransac_host(h_src, h_dst, n, thresh, max_iters, confidence, &r);
+    if (st != BM_OK) return st;
+    if (H) memcpy(H, r.H, 72);
+    if (cycles) memcpy(cycles, r.cyc, sizeof(r.cyc));
+    if (lm_iters) *lm_iters = r.lm_iters;
+    if (jacobi_sweeps) *jacobi_sweeps = r.jacobi_sweeps;
+    return BM_OK;
+}
+
 extern "C" bm_status bm_ransac_homography(const float* h_src, const float* h_dst, int n, double thresh, int max_iters, double confidence,
                                           double H[9], int* ok, int* iters, int* n_inliers) {
+    if (!H) return BM_ERR_ARG;
+    BmRansacResult r;
+    bm_status st = ransac_host(h_src, h_dst, n, thresh, max_iters, confidence, &r);
+    if (st != BM_OK) return st;
+    memcpy(H, r.H, 72);
+    if (ok) *ok = r.ok;
+    if (iters) *iters = r.iters;
+    if (n_inliers) *n_inliers = r.n_inliers;
+    return BM_OK;
+}
+
+static bm_status ransac_host(const float* h_src, const float* h_dst, int n, double thresh, int max_iters, double confidence, BmRansacResult* res) {
+    double Hd[9]; double* H = Hd; int* ok = nullptr; int* iters = nullptr; int* n_inliers = nullptr;
     if (n < 0 || n > BM_KP_CAP || !h_src || !h_dst || !H) { bm_set_error("bm_ransac_homography: bad args"); return BM_ERR_ARG; }
     float2 *ds = nullptr, *dd = nullptr; int* dc = nullptr; uint8_t* dm = nullptr; BmRansacResult* dr = nullptr;
     BM_CUDA_OK(cudaMalloc(&ds, (n + 1) * sizeof(float2))); BM_CUDA_OK(cudaMalloc(&dd, (n + 1) * sizeof(float2)));
@@ -116,10 +143,8 @@ extern "C" bm_status bm_ransac_homography(const float* h_src, const float* h_dst
     if (e == cudaSuccess) e = cudaMemcpy(&r, dr, sizeof(r), cudaMemcpyDeviceToHost);
     cudaFree(ds); cudaFree(dd); cudaFree(dc); cudaFree(dm); cudaFree(dr);
     BM_CUDA_OK(e);
-    memcpy(H, r.H, 72);
-    if (ok) *ok = r.ok;
-    if (iters) *iters = r.iters;
-    if (n_inliers) *n_inliers = r.n_inliers;
+    (void)H; (void)ok; (void)iters; (void)n_inliers;
+    *res = r;
     return BM_OK;
 }
 

@@ -277,40 +277,50 @@ __device__ __forceinline__ int ch_cost(int u, int v) {
     return min(BM_CHAMFER_A * mx + (BM_CHAMFER_B - BM_CHAMFER_A) * mn, BM_DT_INIT);
 }
 
+// one direction of the pruned vertical search.  DIR = -1: blocks above, +1: blocks below.  Blocks are visited outward;
+// the 16-row block minima are fetched four at a time (independent loads) so the dependent chain on `best` is short.
+template <int DIR>
+__device__ __forceinline__ int col_search_dir(const uint16_t* __restrict__ g, const uint16_t* __restrict__ gblk, int n, int nrows,
+                                              int nb, int x, int y, int yb, int best) {
+    for (int k = 1;; k += 4) {
+        int gm[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int Y = yb + DIR * (k + j);
+            gm[j] = (Y >= 0 && Y < nb) ? (int)__ldg(&gblk[(size_t)Y * n + x]) : BM_G_INF;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int Y = yb + DIR * (k + j);
+            if (Y < 0 || Y >= nb) return best;
+            const int v = DIR < 0 ? y - (Y * BM_BLK_ROWS + BM_BLK_ROWS - 1) : Y * BM_BLK_ROWS - y;   // nearest row of the block
+            if (v > 8578 || BM_CHAMFER_A * v >= best) return best;
+            if (ch_cost(gm[j], v) < best) {
+                const int r0 = Y * BM_BLK_ROWS, r1 = min(nrows, r0 + BM_BLK_ROWS);
+                int gr[BM_BLK_ROWS];
+#pragma unroll
+                for (int r = 0; r < BM_BLK_ROWS; ++r) gr[r] = (r0 + r < r1) ? (int)__ldg(&g[(size_t)(r0 + r) * n + x]) : BM_G_INF;
+#pragma unroll
+                for (int r = 0; r < BM_BLK_ROWS; ++r) best = min(best, ch_cost(gr[r], abs(r0 + r - y)));
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ int col_search(const uint16_t* __restrict__ g, const uint16_t* __restrict__ gblk, int n, int nrows, int x, int y) {
     const int yb = y / BM_BLK_ROWS;
     const int nb = (nrows + BM_BLK_ROWS - 1) / BM_BLK_ROWS;
     int best = BM_DT_INIT;
     {
         const int r0 = yb * BM_BLK_ROWS, r1 = min(nrows, r0 + BM_BLK_ROWS);
-        for (int r = r0; r < r1; ++r) best = min(best, ch_cost(g[(size_t)r * n + x], abs(r - y)));
+        int gr[BM_BLK_ROWS];
+#pragma unroll
+        for (int r = 0; r < BM_BLK_ROWS; ++r) gr[r] = (r0 + r < r1) ? (int)__ldg(&g[(size_t)(r0 + r) * n + x]) : BM_G_INF;
+#pragma unroll
+        for (int r = 0; r < BM_BLK_ROWS; ++r) best = min(best, ch_cost(gr[r], abs(r0 + r - y)));
     }
-    for (int k = 1;; ++k) {
-        bool any = false;
-        const int Yu = yb - k, Yd = yb + k;
-        if (Yu >= 0) {
-            const int vu = y - (Yu * BM_BLK_ROWS + BM_BLK_ROWS - 1);       // nearest row of that block
-            if (vu <= 8578 && BM_CHAMFER_A * vu < best) {
-                any = true;
-                if (ch_cost(gblk[(size_t)Yu * n + x], vu) < best) {
-                    const int r0 = Yu * BM_BLK_ROWS;
-#pragma unroll 4
-                    for (int r = r0; r < r0 + BM_BLK_ROWS; ++r) best = min(best, ch_cost(g[(size_t)r * n + x], y - r));
-                }
-            }
-        }
-        if (Yd < nb) {
-            const int vd = Yd * BM_BLK_ROWS - y;
-            if (vd <= 8578 && BM_CHAMFER_A * vd < best) {
-                any = true;
-                if (ch_cost(gblk[(size_t)Yd * n + x], vd) < best) {
-                    const int r0 = Yd * BM_BLK_ROWS, r1 = min(nrows, r0 + BM_BLK_ROWS);
-                    for (int r = r0; r < r1; ++r) best = min(best, ch_cost(g[(size_t)r * n + x], r - y));
-                }
-            }
-        }
-        if (!any) break;
-    }
+    best = col_search_dir<-1>(g, gblk, n, nrows, nb, x, y, yb, best);
+    best = col_search_dir<+1>(g, gblk, n, nrows, nb, x, y, yb, best);
     return best;
 }
 
