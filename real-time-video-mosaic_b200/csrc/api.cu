@@ -460,6 +460,7 @@ extern "C" bm_status bm_blend_step_bgr(uint8_t* d_canvas, const uint8_t* d_warpe
         w.x0 = win[0] - 1 < 0 ? 0 : win[0] - 1; w.y0 = win[1] - 1 < 0 ? 0 : win[1] - 1;
         w.x1 = win[2] + 1 > dw ? dw : win[2] + 1; w.y1 = win[3] + 1 > dh ? dh : win[3] + 1;
     }
+    w.y0 = (w.y0 / BM_BLK_ROWS) * BM_BLK_ROWS;
     plan.win = w;
     plan.reg.x0 = w.x0 - BM_BLUR_R < 0 ? 0 : w.x0 - BM_BLUR_R; plan.reg.y0 = w.y0 - BM_BLUR_R < 0 ? 0 : w.y0 - BM_BLUR_R;
     plan.reg.x1 = w.x1 + BM_BLUR_R > dw ? dw : w.x1 + BM_BLUR_R; plan.reg.y1 = w.y1 + BM_BLUR_R > dh ? dh : w.y1 + BM_BLUR_R;

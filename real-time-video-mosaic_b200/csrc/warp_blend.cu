@@ -89,6 +89,7 @@ void bm_make_plan(const double H[9], int src_w, int src_h, int canvas_w, int can
         w.x1 = (int)fmax(0.0, fmin((double)canvas_w, fx1));
         w.y1 = (int)fmax(0.0, fmin((double)canvas_h, fy1));
     }
+    w.y0 = (w.y0 / BM_BLK_ROWS) * BM_BLK_ROWS;      // window rows start on the 16-row block grid (k_dt_weights shares one grid for both masks)
     p->win = w;
     p->reg.x0 = clampi(w.x0 - BM_BLUR_R, 0, canvas_w); p->reg.x1 = clampi(w.x1 + BM_BLUR_R, 0, canvas_w);
     p->reg.y0 = clampi(w.y0 - BM_BLUR_R, 0, canvas_h); p->reg.y1 = clampi(w.y1 + BM_BLUR_R, 0, canvas_h);
@@ -270,62 +271,82 @@ __global__ void __launch_bounds__(256) k_blockmin(const uint16_t* __restrict__ g
 // ------------------------------------------------------------------------------------------------------------------
 // exact chamfer distance from the row structure (SURVEY A.9 decomposition)
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int ch_cost(int u, int v) {
-    if (u == BM_G_INF) return BM_DT_INIT;
-    const int mx = max(u, v), mn = min(u, v);
-    if (mx > 8578) return BM_DT_INIT;                       // a*mx would exceed DIST_MAX (and int32 later)
-    return min(BM_CHAMFER_A * mx + (BM_CHAMFER_B - BM_CHAMFER_A) * mn, BM_DT_INIT);
+// ---- block-parallel exact search: one thread owns a 16-row run of one column -------------------------------------
+// N(u,v) = a*max(u,v) + (b-a)*min(u,v) = max(a*u + (b-a)*v, (b-a)*u + a*v) because a >= b-a.
+#define BM_U_CAP 16000     // a*16000 > DIST_MAX: "no zero reachable"; keeps every product inside int32
+__device__ __forceinline__ int ncost(int u, int v) {
+    return max(BM_CHAMFER_A * u + (BM_CHAMFER_B - BM_CHAMFER_A) * v, (BM_CHAMFER_B - BM_CHAMFER_A) * u + BM_CHAMFER_A * v);
 }
 
-// one direction of the pruned vertical search.  DIR = -1: blocks above, +1: blocks below.  Blocks are visited outward;
-// the 16-row block minima are fetched four at a time (independent loads) so the dependent chain on `best` is short.
-template <int DIR>
-__device__ __forceinline__ int col_search_dir(const uint16_t* __restrict__ g, const uint16_t* __restrict__ gblk, int n, int nrows,
-                                              int nb, int x, int y, int yb, int best) {
-    for (int k = 1;; k += 4) {
-        int gm[4];
+// visit one 16-row block of candidate rows for the 16 pixels of the thread.  voff: v(i, r) = voff + SI*i + SR*r
+template <int SI, int SR>
+__device__ __forceinline__ void scan_block16(const uint16_t* __restrict__ g, int n, int nrows, int x, int r0, int voff, int vmin_base,
+                                             int bmax, int (&best)[BM_BLK_ROWS]) {
+    int gr[BM_BLK_ROWS];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int Y = yb + DIR * (k + j);
-            gm[j] = (Y >= 0 && Y < nb) ? (int)__ldg(&gblk[(size_t)Y * n + x]) : BM_G_INF;
+    for (int r = 0; r < BM_BLK_ROWS; ++r) gr[r] = (r0 + r < nrows) ? min((int)__ldg(&g[(size_t)(r0 + r) * n + x]), BM_U_CAP) : BM_U_CAP;
+#pragma unroll
+    for (int r = 0; r < BM_BLK_ROWS; ++r) {
+        const int u = gr[r];
+        // smallest vertical distance from this row to any of the 16 pixels
+        const int vmin = vmin_base + (SR < 0 ? (BM_BLK_ROWS - 1 - r) : r);
+        if (ncost(u, vmin) < bmax) {
+#pragma unroll
+            for (int i = 0; i < BM_BLK_ROWS; ++i) best[i] = min(best[i], ncost(u, voff + SI * i + SR * r));
         }
+    }
+}
+
+__device__ __forceinline__ void search16(const uint16_t* __restrict__ g, const uint16_t* __restrict__ gblk, int n, int nrows, int x, int Yb,
+                                         int (&best)[BM_BLK_ROWS]) {
+    const int nb = (nrows + BM_BLK_ROWS - 1) / BM_BLK_ROWS;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int Y = yb + DIR * (k + j);
-            if (Y < 0 || Y >= nb) return best;
-            const int v = DIR < 0 ? y - (Y * BM_BLK_ROWS + BM_BLK_ROWS - 1) : Y * BM_BLK_ROWS - y;   // nearest row of the block
-            if (v > 8578 || BM_CHAMFER_A * v >= best) return best;
-            if (ch_cost(gm[j], v) < best) {
-                const int r0 = Y * BM_BLK_ROWS, r1 = min(nrows, r0 + BM_BLK_ROWS);
-                int gr[BM_BLK_ROWS];
+    for (int i = 0; i < BM_BLK_ROWS; ++i) best[i] = BM_DT_INIT;
+    {   // own block: v = |r - i|
+        int gr[BM_BLK_ROWS];
+        const int r0 = Yb * BM_BLK_ROWS;
 #pragma unroll
-                for (int r = 0; r < BM_BLK_ROWS; ++r) gr[r] = (r0 + r < r1) ? (int)__ldg(&g[(size_t)(r0 + r) * n + x]) : BM_G_INF;
+        for (int r = 0; r < BM_BLK_ROWS; ++r) gr[r] = (r0 + r < nrows) ? min((int)__ldg(&g[(size_t)(r0 + r) * n + x]), BM_U_CAP) : BM_U_CAP;
 #pragma unroll
-                for (int r = 0; r < BM_BLK_ROWS; ++r) best = min(best, ch_cost(gr[r], abs(r0 + r - y)));
+        for (int i = 0; i < BM_BLK_ROWS; ++i) best[i] = min(best[i], BM_CHAMFER_A * gr[i]);
+        int bmax = 0;
+#pragma unroll
+        for (int i = 0; i < BM_BLK_ROWS; ++i) bmax = max(bmax, best[i]);
+#pragma unroll
+        for (int r = 0; r < BM_BLK_ROWS; ++r) {
+            const int u = gr[r];
+            if (BM_CHAMFER_A * u < bmax) {
+#pragma unroll
+                for (int i = 0; i < BM_BLK_ROWS; ++i) best[i] = min(best[i], ncost(u, i > r ? i - r : r - i));
             }
         }
     }
-}
-
-__device__ __forceinline__ int col_search(const uint16_t* __restrict__ g, const uint16_t* __restrict__ gblk, int n, int nrows, int x, int y) {
-    const int yb = y / BM_BLK_ROWS;
-    const int nb = (nrows + BM_BLK_ROWS - 1) / BM_BLK_ROWS;
-    int best = BM_DT_INIT;
-    {
-        const int r0 = yb * BM_BLK_ROWS, r1 = min(nrows, r0 + BM_BLK_ROWS);
-        int gr[BM_BLK_ROWS];
+    // blocks above: rows r0..r0+15 with r0 = (Yb-k)*16; v(i,r) = 16k + i - r, nearest pair (i=0, r=15): 16k - 15
+    for (int k = 1; Yb - k >= 0; ++k) {
+        const int vnear = BM_BLK_ROWS * k - (BM_BLK_ROWS - 1);
+        int bmax = 0;
 #pragma unroll
-        for (int r = 0; r < BM_BLK_ROWS; ++r) gr[r] = (r0 + r < r1) ? (int)__ldg(&g[(size_t)(r0 + r) * n + x]) : BM_G_INF;
-#pragma unroll
-        for (int r = 0; r < BM_BLK_ROWS; ++r) best = min(best, ch_cost(gr[r], abs(r0 + r - y)));
+        for (int i = 0; i < BM_BLK_ROWS; ++i) bmax = max(bmax, best[i]);
+        if (vnear > 8578 || BM_CHAMFER_A * vnear >= bmax) break;
+        const int gm = min((int)__ldg(&gblk[(size_t)(Yb - k) * n + x]), BM_U_CAP);
+        if (ncost(gm, vnear) < bmax) scan_block16<1, -1>(g, n, nrows, x, (Yb - k) * BM_BLK_ROWS, BM_BLK_ROWS * k, vnear, bmax, best);
     }
-    best = col_search_dir<-1>(g, gblk, n, nrows, nb, x, y, yb, best);
-    best = col_search_dir<+1>(g, gblk, n, nrows, nb, x, y, yb, best);
-    return best;
+    // blocks below: v(i,r) = 16k + r - i, nearest pair (i=15, r=0)
+    for (int k = 1; Yb + k < nb; ++k) {
+        const int vnear = BM_BLK_ROWS * k - (BM_BLK_ROWS - 1);
+        int bmax = 0;
+#pragma unroll
+        for (int i = 0; i < BM_BLK_ROWS; ++i) bmax = max(bmax, best[i]);
+        if (vnear > 8578 || BM_CHAMFER_A * vnear >= bmax) break;
+        const int gm = min((int)__ldg(&gblk[(size_t)(Yb + k) * n + x]), BM_U_CAP);
+        if (ncost(gm, vnear) < bmax) scan_block16<-1, 1>(g, n, nrows, x, (Yb + k) * BM_BLK_ROWS, BM_BLK_ROWS * k, vnear, bmax, best);
+    }
 }
 
-// K3: over R, dn and do -> (dn/s, do/s) in float32 exactly as NumPy does it (main.py:892-894)
-__global__ void __launch_bounds__(256) k_dt_weights(const BmFramePlan* __restrict__ planp, const uint16_t* __restrict__ g_old,
+// K3: over R, dn and do -> (dn/s, do/s) in float32 exactly as NumPy does it (main.py:892-894).
+// thread = (column x, 16-row block Yb on the canvas block grid); plan.win.y0 is a multiple of 16 so the window-local
+// block grid of g_new coincides with the canvas grid.
+__global__ void __launch_bounds__(128) k_dt_weights(const BmFramePlan* __restrict__ planp, const uint16_t* __restrict__ g_old,
                                                     const uint16_t* __restrict__ gblk_old, const uint16_t* __restrict__ g_new,
                                                     const uint16_t* __restrict__ gblk_new, float2* __restrict__ rbuf,
                                                     const int* __restrict__ flags) {
@@ -333,19 +354,29 @@ __global__ void __launch_bounds__(256) k_dt_weights(const BmFramePlan* __restric
     __shared__ BmFramePlan plan;
     if (threadIdx.x == 0 && threadIdx.y == 0) plan = *planp;
     __syncthreads();
-    const int rw = bm_win_w(plan.reg), rh = bm_win_h(plan.reg);
-    const int lx = blockIdx.x * blockDim.x + threadIdx.x, ly = blockIdx.y * blockDim.y + threadIdx.y;
-    if (lx >= rw || ly >= rh) return;
-    const int x = plan.reg.x0 + lx, y = plan.reg.y0 + ly;
-    const int d_old = col_search(g_old, gblk_old, plan.canvas_w, plan.canvas_h, x, y);
-    int d_new = 0;
-    if (x >= plan.win.x0 && x < plan.win.x1 && y >= plan.win.y0 && y < plan.win.y1)
-        d_new = col_search(g_new, gblk_new, bm_win_w(plan.win), bm_win_h(plan.win), x - plan.win.x0, y - plan.win.y0);
+    const int rw = bm_win_w(plan.reg);
+    const int lx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int Yb = plan.reg.y0 / BM_BLK_ROWS + blockIdx.y * blockDim.y + threadIdx.y;
+    if (lx >= rw || Yb * BM_BLK_ROWS >= plan.reg.y1) return;
+    const int x = plan.reg.x0 + lx;
+    int bo[BM_BLK_ROWS], bn[BM_BLK_ROWS];
+    search16(g_old, gblk_old, plan.canvas_w, plan.canvas_h, x, Yb, bo);
+    const int xl = x - plan.win.x0, Ybl = Yb - plan.win.y0 / BM_BLK_ROWS;
+    const int ww = bm_win_w(plan.win), wh = bm_win_h(plan.win);
+    const bool in_win = xl >= 0 && xl < ww && Ybl >= 0 && Ybl * BM_BLK_ROWS < wh;
+    if (in_win) search16(g_new, gblk_new, ww, wh, xl, Ybl, bn);
     const float scale = 1.0f / 65536.0f;
-    const float dn = __fmul_rn(__int2float_rn(d_new), scale);
-    const float dold = __fmul_rn(__int2float_rn(d_old), scale);
-    const float s = __fadd_rn(__fadd_rn(dn, dold), 1e-6f);
-    rbuf[(size_t)ly * rw + lx] = make_float2(__fdiv_rn(dn, s), __fdiv_rn(dold, s));
+#pragma unroll
+    for (int i = 0; i < BM_BLK_ROWS; ++i) {
+        const int y = Yb * BM_BLK_ROWS + i;
+        if (y < plan.reg.y0 || y >= plan.reg.y1) continue;
+        const int d_new = (in_win && y < plan.win.y1) ? min(bn[i], BM_DT_INIT) : 0;
+        const int d_old = min(bo[i], BM_DT_INIT);
+        const float dn = __fmul_rn(__int2float_rn(d_new), scale);
+        const float dold = __fmul_rn(__int2float_rn(d_old), scale);
+        const float s = __fadd_rn(__fadd_rn(dn, dold), 1e-6f);
+        rbuf[(size_t)(y - plan.reg.y0) * rw + lx] = make_float2(__fdiv_rn(dn, s), __fdiv_rn(dold, s));
+    }
 }
 
 __device__ __forceinline__ int reflect101(int i, int n) {
@@ -477,10 +508,16 @@ __global__ void k_paste(uchar4* __restrict__ canvas, int canvas_w, const uchar4*
     v.w = (v.x | v.y | v.z) ? 255 : 0;
     canvas[(size_t)(oy + y) * canvas_w + ox + x] = v;
 }
-__global__ void k_dt_from_g(const uint16_t* __restrict__ g, const uint16_t* __restrict__ gblk, int n, int nrows, float* __restrict__ out) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= n || y >= nrows) return;
-    out[(size_t)y * n + x] = __fmul_rn(__int2float_rn(col_search(g, gblk, n, nrows, x, y)), 1.0f / 65536.0f);
+__global__ void __launch_bounds__(128) k_dt_from_g(const uint16_t* __restrict__ g, const uint16_t* __restrict__ gblk, int n, int nrows, float* __restrict__ out) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, Yb = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= n || Yb * BM_BLK_ROWS >= nrows) return;
+    int best[BM_BLK_ROWS];
+    search16(g, gblk, n, nrows, x, Yb, best);
+#pragma unroll
+    for (int i = 0; i < BM_BLK_ROWS; ++i) {
+        const int y = Yb * BM_BLK_ROWS + i;
+        if (y < nrows) out[(size_t)y * n + x] = __fmul_rn(__int2float_rn(min(best[i], BM_DT_INIT)), 1.0f / 65536.0f);
+    }
 }
 __global__ void k_blur31_rows_plain(const float* __restrict__ in, int h, int w, float* __restrict__ out) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -523,7 +560,11 @@ cudaError_t bm_launch_blend_from_wbuf(const BmBlendBufs& b, const BmFramePlan& p
     BM_COUNT_LAUNCHES(1), k_rowscan<<<bm_div_up(wh * 32, 256), 256, 0, s>>>(b.wbuf, ww, 0, ww, 0, wh, b.g_new, 0, b.flags, 1);
     const int nbw = bm_div_up(wh, BM_BLK_ROWS);
     BM_COUNT_LAUNCHES(1), k_blockmin<<<dim3(bm_div_up(ww, 256), nbw), 256, 0, s>>>(b.g_new, ww, wh, 0, nbw, b.gblk_new, b.flags, 1);
-    BM_COUNT_LAUNCHES(1), k_dt_weights<<<grid2(rw, rh, blk), blk, 0, s>>>(b.plan, b.g_old, b.gblk_old, b.g_new, b.gblk_new, b.rbuf, b.flags);
+    {
+        const int nyb = (plan.reg.y1 - 1) / BM_BLK_ROWS - plan.reg.y0 / BM_BLK_ROWS + 1;
+        const dim3 b2(32, 4);
+        BM_COUNT_LAUNCHES(1), k_dt_weights<<<dim3(bm_div_up(rw, 32), bm_div_up(nyb, 4)), b2, 0, s>>>(b.plan, b.g_old, b.gblk_old, b.g_new, b.gblk_new, b.rbuf, b.flags);
+    }
     BM_COUNT_LAUNCHES(1), k_blur_rows<<<grid2(ww, rh, blk), blk, 0, s>>>(b.plan, b.rbuf, b.hbuf, b.flags);
     BM_COUNT_LAUNCHES(1), k_blur_cols_blend<<<grid2(ww, wh, blk), blk, 0, s>>>(b.plan, b.hbuf, b.wbuf, b.canvas, b.flags);
     // refresh the persistent row structure for the rows the frame touched
@@ -580,7 +621,7 @@ cudaError_t bm_launch_dt_mask(const uint8_t* d_mask, int h, int w, float* d_out,
     const int nb = bm_div_up(h, BM_BLK_ROWS);
     BM_COUNT_LAUNCHES(1), k_blockmin<<<dim3(bm_div_up(w, 256), nb), 256, 0, s>>>(g, w, h, 0, nb, gblk, nullptr, 0);
     const dim3 blk(32, 8);
-    BM_COUNT_LAUNCHES(1), k_dt_from_g<<<grid2(w, h, blk), blk, 0, s>>>(g, gblk, w, h, d_out);
+    BM_COUNT_LAUNCHES(1), k_dt_from_g<<<dim3(bm_div_up(w, 32), bm_div_up(bm_div_up(h, BM_BLK_ROWS), 4)), dim3(32, 4), 0, s>>>(g, gblk, w, h, d_out);
     return cudaGetLastError();
 }
 cudaError_t bm_launch_blur31(const float* d_in, int h, int w, float* d_tmp, float* d_out, cudaStream_t s) {
