@@ -73,6 +73,20 @@ bm_status bm_first_frame(bm_handle h, const uint8_t* h_bgr, size_t stride_bytes)
 bm_status bm_process_frame(bm_handle h, const uint8_t* h_bgr, size_t stride_bytes, bm_frame_info* info);
 /* same, with the frame already resident in device memory as packed BGR (kernel-only timing leg of bench.py) */
 bm_status bm_process_frame_device(bm_handle h, const uint8_t* d_bgr, bm_frame_info* info);
+/* split form for many concurrent handles (config 4: 64 streams): _begin enqueues H2D + detect + match + RANSAC + the small
+ * D2H on the handle's stream and returns without waiting; _end waits for that read-back, runs the host control flow and
+ * enqueues the warp/blend chain.  Calling _begin on every handle and then _end on every handle overlaps the streams. */
+bm_status bm_process_frame_begin(bm_handle h, const uint8_t* h_bgr, size_t stride_bytes);
+bm_status bm_process_frame_begin_device(bm_handle h, const uint8_t* d_bgr);
+bm_status bm_process_frame_end(bm_handle h, bm_frame_info* info);
+/* offline pair-sharded mode (config 3 at N GPUs): features of this frame, matches and RANSAC against the previous frame of
+ * this handle, NO validation / warp; the frame always becomes the new "previous".  info->H_rel, n_matches, status
+ * (BM_OK | BM_SKIP_FEW_MATCHES | BM_SKIP_NO_H) are filled. */
+bm_status bm_estimate_frame(bm_handle h, const uint8_t* h_bgr, size_t stride_bytes, bm_frame_info* info);
+/* canvas row-tile mode (config 5): empty the canvas (the caller then warps frame 0 with its own homography) */
+bm_status bm_clear_canvas(bm_handle h);
+/* canvas as packed BGR into a DEVICE buffer (e.g. a torch tensor that NCCL then gathers) */
+bm_status bm_get_canvas_device(bm_handle h, uint8_t* d_bgr_out);
 /* output_img (uint8, Hc x Wc x 3): lazy D2H of the device canvas                     main.py:1632,1649 */
 bm_status bm_get_canvas(bm_handle h, uint8_t* h_bgr_out);
 bm_status bm_get_state(bm_handle h, double H_old[9], int* history_len, double* history /* <=5*9 */);

@@ -67,6 +67,12 @@ def load():
     _sig(lib, "bm_warp_frame_device", i, vp, vp, dp, C.POINTER(BmFrameInfo))
     _sig(lib, "bm_sync", i, vp)
     _sig(lib, "bm_process_frame_device", i, vp, vp, C.POINTER(BmFrameInfo))
+    _sig(lib, "bm_process_frame_begin", i, vp, vp, sz)
+    _sig(lib, "bm_process_frame_begin_device", i, vp, vp)
+    _sig(lib, "bm_process_frame_end", i, vp, C.POINTER(BmFrameInfo))
+    _sig(lib, "bm_estimate_frame", i, vp, vp, sz, C.POINTER(BmFrameInfo))
+    _sig(lib, "bm_clear_canvas", i, vp)
+    _sig(lib, "bm_get_canvas_device", i, vp, vp)
     _sig(lib, "bm_timing_enable", i, vp, i)
     _sig(lib, "bm_timing_read", i, vp, dp, dp, ip, i)
     _sig(lib, "bm_kernel_launches", C.c_longlong)

@@ -332,12 +332,11 @@ static void matmul3(const double* A, const double* B, double* C) {
     }
 }
 
-static bm_status process_uploaded(bm_mosaic_s* m, int slot, bm_frame_info* info_out) {
+static bm_status finish_frame(bm_mosaic_s* m, int slot, bm_frame_info* info_out) {
     bm_frame_info info; memset(&info, 0, sizeof(info));
-    // detect + match + RANSAC on the device; one small D2H read of (n_matches, H_rel) -- the reference's control
-    // flow (skip / reject prints) needs them on the host at this point anyway.
+    // one small D2H read of (n_matches, H_rel): the reference's control flow (skip / reject prints) needs them on the host
     double H_rel[9]; int have_h = 0;
-    bm_status st = bm_pipeline_estimate(m->pipe, m->d_gray[slot], &info, H_rel, &have_h);
+    bm_status st = bm_pipeline_estimate_end(m->pipe, &info, H_rel, &have_h);
     if (st < 0) { m->cur ^= 1; return st; }
     if (info.n_matches < 4) { info.status = BM_SKIP_FEW_MATCHES; m->cur ^= 1; if (info_out) *info_out = info; return BM_SKIP_FEW_MATCHES; }
     if (!have_h) { info.status = BM_SKIP_NO_H; m->cur ^= 1; if (info_out) *info_out = info; return BM_SKIP_NO_H; }
@@ -358,22 +357,78 @@ static bm_status process_uploaded(bm_mosaic_s* m, int slot, bm_frame_info* info_
     return ret;
 }
 
-extern "C" bm_status bm_process_frame(bm_handle m, const uint8_t* h_bgr, size_t stride, bm_frame_info* info_out) {
-    if (!m || !h_bgr) { bm_set_error("bm_process_frame: null"); return BM_ERR_ARG; }
+extern "C" bm_status bm_process_frame_begin(bm_handle m, const uint8_t* h_bgr, size_t stride) {
+    if (!m || !h_bgr) { bm_set_error("bm_process_frame_begin: null"); return BM_ERR_ARG; }
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
     m->cur ^= 1;
-    const int slot = m->cur;
-    BM_TRY(upload(m, h_bgr, stride, slot));
-    return process_uploaded(m, slot, info_out);
+    BM_TRY(upload(m, h_bgr, stride, m->cur));
+    bm_status st = bm_pipeline_estimate_begin(m->pipe, m->d_gray[m->cur]);
+    if (st < 0) m->cur ^= 1;
+    return st;
+}
+
+extern "C" bm_status bm_process_frame_begin_device(bm_handle m, const uint8_t* d_bgr) {
+    if (!m || !d_bgr) { bm_set_error("bm_process_frame_begin_device: null"); return BM_ERR_ARG; }
+    BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+    m->cur ^= 1;
+    BM_CUDA_OK(bm_launch_ingest(d_bgr, m->cfg.frame_h, m->cfg.frame_w, m->d_gray[m->cur], m->d_bgrx[m->cur], m->stream));
+    bm_status st = bm_pipeline_estimate_begin(m->pipe, m->d_gray[m->cur]);
+    if (st < 0) m->cur ^= 1;
+    return st;
+}
+
+extern "C" bm_status bm_process_frame_end(bm_handle m, bm_frame_info* info_out) {
+    if (!m) return BM_ERR_ARG;
+    BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+    return finish_frame(m, m->cur, info_out);
+}
+
+extern "C" bm_status bm_process_frame(bm_handle m, const uint8_t* h_bgr, size_t stride, bm_frame_info* info_out) {
+    bm_status st = bm_process_frame_begin(m, h_bgr, stride);
+    if (st < 0) return st;
+    return bm_process_frame_end(m, info_out);
 }
 
 extern "C" bm_status bm_process_frame_device(bm_handle m, const uint8_t* d_bgr, bm_frame_info* info_out) {
-    if (!m || !d_bgr) { bm_set_error("bm_process_frame_device: null"); return BM_ERR_ARG; }
+    bm_status st = bm_process_frame_begin_device(m, d_bgr);
+    if (st < 0) return st;
+    return bm_process_frame_end(m, info_out);
+}
+
+extern "C" bm_status bm_estimate_frame(bm_handle m, const uint8_t* h_bgr, size_t stride, bm_frame_info* info_out) {
+    if (!m || !h_bgr) { bm_set_error("bm_estimate_frame: null"); return BM_ERR_ARG; }
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
     m->cur ^= 1;
-    const int slot = m->cur;
-    BM_CUDA_OK(bm_launch_ingest(d_bgr, m->cfg.frame_h, m->cfg.frame_w, m->d_gray[slot], m->d_bgrx[slot], m->stream));
-    return process_uploaded(m, slot, info_out);
+    BM_TRY(upload(m, h_bgr, stride, m->cur));
+    bm_frame_info info; memset(&info, 0, sizeof(info));
+    double H_rel[9]; int have_h = 0;
+    bm_status st = bm_pipeline_estimate(m->pipe, m->d_gray[m->cur], &info, H_rel, &have_h);
+    if (st < 0) { m->cur ^= 1; return st; }
+    bm_pipeline_advance(m->pipe);                  // pair (t-1, t): the frame always becomes "previous"
+    bm_status ret = BM_OK;
+    if (info.n_matches < 4) ret = BM_SKIP_FEW_MATCHES;
+    else if (!have_h) ret = BM_SKIP_NO_H;
+    else memcpy(info.H_rel, H_rel, 72);
+    info.status = ret;
+    if (info_out) *info_out = info;
+    return ret;
+}
+
+extern "C" bm_status bm_clear_canvas(bm_handle m) {
+    if (!m) return BM_ERR_ARG;
+    BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+    BM_CUDA_OK(cudaMemsetAsync(m->blend.canvas, 0, (size_t)m->cfg.canvas_h * m->cfg.canvas_w * sizeof(uchar4), m->stream));
+    BM_CUDA_OK(bm_launch_full_rowscan(m->blend, m->stream));
+    BM_CUDA_OK(cudaStreamSynchronize(m->stream));
+    return BM_OK;
+}
+
+extern "C" bm_status bm_get_canvas_device(bm_handle m, uint8_t* d_out) {
+    if (!m || !d_out) return BM_ERR_ARG;
+    BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+    BM_CUDA_OK(bm_launch_unpack_canvas(m->blend.canvas, d_out, (int)((size_t)m->cfg.canvas_h * m->cfg.canvas_w), m->stream));
+    BM_CUDA_OK(cudaStreamSynchronize(m->stream));
+    return BM_OK;
 }
 
 // features / matches of the last frame

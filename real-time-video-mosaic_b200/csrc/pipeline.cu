@@ -65,7 +65,7 @@ bm_status bm_pipeline_first_frame(BmPipeline* p, const uint8_t* d_gray) {
     return BM_OK;
 }
 
-bm_status bm_pipeline_estimate(BmPipeline* p, const uint8_t* d_gray, bm_frame_info* info, double H_rel[9], int* have_h) {
+bm_status bm_pipeline_estimate_begin(BmPipeline* p, const uint8_t* d_gray) {
     if (!p->have_prev) { bm_set_error("process_frame before first frame"); return BM_ERR_ARG; }
     cudaStream_t s = p->stream;
     BmKeypoints& cur = p->kp[p->prev ^ 1];
@@ -79,12 +79,23 @@ bm_status bm_pipeline_estimate(BmPipeline* p, const uint8_t* d_gray, bm_frame_in
     BM_CUDA_OK(cudaMemcpyAsync(&rb->n_cur, cur.count, sizeof(int), cudaMemcpyDeviceToHost, s));
     BM_CUDA_OK(cudaMemcpyAsync(&rb->n_prev, prev.count, sizeof(int), cudaMemcpyDeviceToHost, s));
     BM_CUDA_OK(cudaMemcpyAsync(&rb->n_matches, p->m.count, sizeof(int), cudaMemcpyDeviceToHost, s));
-    BM_CUDA_OK(cudaStreamSynchronize(s));
+    return BM_OK;
+}
+
+bm_status bm_pipeline_estimate_end(BmPipeline* p, bm_frame_info* info, double H_rel[9], int* have_h) {
+    BM_CUDA_OK(cudaStreamSynchronize(p->stream));
+    BmHostReadback* rb = p->h_rb;
     info->n_kp_cur = rb->n_cur; info->n_kp_prev = rb->n_prev; info->n_matches = rb->n_matches;
     info->ransac_iters = rb->r.iters; info->n_inliers = rb->r.n_inliers;
-    *have_h = rb->r.ok;
-    if (rb->r.ok) memcpy(H_rel, rb->r.H, 72);
+    *have_h = rb->r.ok == 1;
+    if (*have_h) memcpy(H_rel, rb->r.H, 72);
     return BM_OK;
+}
+
+bm_status bm_pipeline_estimate(BmPipeline* p, const uint8_t* d_gray, bm_frame_info* info, double H_rel[9], int* have_h) {
+    bm_status st = bm_pipeline_estimate_begin(p, d_gray);
+    if (st != BM_OK) return st;
+    return bm_pipeline_estimate_end(p, info, H_rel, have_h);
 }
 
 void bm_pipeline_advance(BmPipeline* p) { p->prev ^= 1; }

@@ -10,6 +10,9 @@ void bm_pipeline_destroy(BmPipeline* p);
 bm_status bm_pipeline_first_frame(BmPipeline* p, const uint8_t* d_gray);
 // features of the current frame, matches against prev, RANSAC homography cur->prev (main.py:717-727)
 bm_status bm_pipeline_estimate(BmPipeline* p, const uint8_t* d_gray, bm_frame_info* info, double H_rel[9], int* have_h);
+// split form of bm_pipeline_estimate: enqueue (no wait) / wait + read back
+bm_status bm_pipeline_estimate_begin(BmPipeline* p, const uint8_t* d_gray);
+bm_status bm_pipeline_estimate_end(BmPipeline* p, bm_frame_info* info, double H_rel[9], int* have_h);
 // cur -> prev (main.py:756-759)
 void bm_pipeline_advance(BmPipeline* p);
 struct BmKeypoints; struct BmMatches;

@@ -195,34 +195,45 @@ __global__ void __launch_bounds__(256) k_warp_full_bgr(const uint8_t* __restrict
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_rowscan(const uchar4* __restrict__ img, int stride, int col0, int n, int row0, int nrows,
                                                  uint16_t* __restrict__ g, int g_row0, const int* __restrict__ flags, int need_flag) {
+    // one CTA per row; warp w owns the contiguous chunk [w*chunk, (w+1)*chunk).  Phase A: first / last zero of every chunk;
+    // phase B: forward (nearest zero at or before x) and backward (at or after x) ballot scans inside the chunk with the
+    // carries of the neighbouring chunks.  3 passes over n/8 pixels per warp instead of 2 passes over n.
     if (need_flag && flags[0] == 0) return;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= nrows) return;
-    const uchar4* row = img + (size_t)(row0 + warp) * stride + col0;
-    uint16_t* grow = g + (size_t)(g_row0 + warp) * n;
-    const int NOZ = -(1 << 28);
-    int carry = NOZ;
-    for (int c = 0; c < n; c += 32) {                      // left-to-right: nearest zero at or before x
+    __shared__ int s_first[8], s_last[8];
+    const int r = blockIdx.x;
+    if (r >= nrows) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uchar4* row = img + (size_t)(row0 + r) * stride + col0;
+    uint16_t* grow = g + (size_t)(g_row0 + r) * n;
+    const int chunk = (((n + 7) / 8) + 31) & ~31;
+    const int c0 = warp * chunk, c1 = min(n, c0 + chunk);
+    const int NOZ = -(1 << 28), FAR = 1 << 28;
+    int first = FAR, last = NOZ;
+    for (int c = c0; c < c1; c += 32) {
         const int x = c + lane;
-        const bool z = (x < n) && (row[x].w == 0);
-        const unsigned b = __ballot_sync(0xffffffffu, z);
+        const unsigned b = __ballot_sync(0xffffffffu, (x < c1) && (row[x].w == 0));
+        if (b) { if (first == FAR) first = c + __ffs(b) - 1; last = c + 31 - __clz(b); }
+    }
+    if (lane == 0) { s_first[warp] = first; s_last[warp] = last; }
+    __syncthreads();
+    int carry = NOZ;
+    for (int w = 0; w < warp; ++w) carry = max(carry, s_last[w]);
+    for (int c = c0; c < c1; c += 32) {
+        const int x = c + lane;
+        const unsigned b = __ballot_sync(0xffffffffu, (x < c1) && (row[x].w == 0));
         const unsigned m = b & (0xffffffffu >> (31 - lane));
         const int lastz = m ? (c + 31 - __clz(m)) : carry;
-        if (x < n) grow[x] = (uint16_t)min(x - lastz, (int)BM_G_INF);
+        if (x < c1) grow[x] = (uint16_t)min(x - lastz, (int)BM_G_INF);
         if (b) carry = c + 31 - __clz(b);
     }
-    carry = 1 << 28;
-    for (int c = ((n - 1) / 32) * 32; c >= 0; c -= 32) {   // right-to-left: nearest zero at or after x
+    carry = FAR;
+    for (int w = 7; w > warp; --w) carry = min(carry, s_first[w]);
+    for (int c = c0 + ((max(c1 - c0, 1) - 1) / 32) * 32; c >= c0; c -= 32) {
         const int x = c + lane;
-        const bool z = (x < n) && (row[x].w == 0);
-        const unsigned b = __ballot_sync(0xffffffffu, z);
+        const unsigned b = __ballot_sync(0xffffffffu, (x < c1) && (row[x].w == 0));
         const unsigned m = b & (0xffffffffu << lane);
         const int nextz = m ? (c + __ffs(m) - 1) : carry;
-        if (x < n) {
-            const int r = min(nextz - x, (int)BM_G_INF);
-            const int l = grow[x];
-            grow[x] = (uint16_t)min(l, r);
-        }
+        if (x < c1) grow[x] = (uint16_t)min((int)grow[x], min(nextz - x, (int)BM_G_INF));
         if (b) carry = c + __ffs(b) - 1;
     }
 }
@@ -385,77 +396,97 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i;
 }
 
-// K4: horizontal 31-tap pass (FMA, taps left to right) for W columns x R rows
-__global__ void __launch_bounds__(256) k_blur_rows(const BmFramePlan* __restrict__ planp, const float2* __restrict__ rbuf,
-                                                   float2* __restrict__ hbuf, const int* __restrict__ flags) {
-    if (flags[0] == 0) return;
+// K4: GaussianBlur(31) of both weight planes + blend + canvas update, one kernel.  CTA = 32x32 output pixels of W.
+//  stage 0: (dn/s, do/s) tile with a 15 px halo (reflect-101 at the canvas border) -> shared memory
+//  stage 1: row pass, 8 consecutive outputs per thread from a 38-value register window (cv2 order: tap 0 product, then
+//           FMAs left to right)
+//  stage 2: column pass, 4 consecutive outputs per thread from a 34-value register window (cv2's symmetric FMA form),
+//           then the blend of main.py:905-927 and the canvas write.
+#define FB_T 32
+#define FB_S (FB_T + 2 * BM_BLUR_R)      // 62
+__global__ void __launch_bounds__(256) k_blur_blend(const BmFramePlan* __restrict__ planp, const float2* __restrict__ rbuf,
+                                                    const uchar4* __restrict__ wbuf, uchar4* __restrict__ canvas,
+                                                    const int* __restrict__ flags) {
     __shared__ BmFramePlan plan;
-    if (threadIdx.x == 0 && threadIdx.y == 0) plan = *planp;
-    __syncthreads();
-    const int ww = bm_win_w(plan.win), rw = bm_win_w(plan.reg), rh = bm_win_h(plan.reg);
-    const int lx = blockIdx.x * blockDim.x + threadIdx.x, ly = blockIdx.y * blockDim.y + threadIdx.y;
-    if (lx >= ww || ly >= rh) return;
-    const int x = plan.win.x0 + lx;
-    const float2* row = rbuf + (size_t)ly * rw;
-    float ax = 0.f, ay = 0.f;
-#pragma unroll
-    for (int k = 0; k < 31; ++k) {
-        const int xx = reflect101(x + k - BM_BLUR_R, plan.canvas_w) - plan.reg.x0;
-        const float2 v = row[xx];
-        const float c = c_gk[k < 16 ? k : 30 - k];
-        if (k == 0) { ax = __fmul_rn(v.x, c); ay = __fmul_rn(v.y, c); }
-        else { ax = __fmaf_rn(v.x, c, ax); ay = __fmaf_rn(v.y, c, ay); }
-    }
-    hbuf[(size_t)ly * ww + lx] = make_float2(ax, ay);
-}
-
-// K5: vertical 31-tap pass (symmetric FMA form) + blend + canvas update
-__global__ void __launch_bounds__(256) k_blur_cols_blend(const BmFramePlan* __restrict__ planp, const float2* __restrict__ hbuf,
-                                                         const uchar4* __restrict__ wbuf, uchar4* __restrict__ canvas,
-                                                         const int* __restrict__ flags) {
-    __shared__ BmFramePlan plan;
-    if (threadIdx.x == 0 && threadIdx.y == 0) plan = *planp;
+    __shared__ float2 tile[FB_S][FB_S + 1];
+    __shared__ float2 hrow[FB_S][FB_T + 1];
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    if (tid == 0) plan = *planp;
     __syncthreads();
     const int ww = bm_win_w(plan.win), wh = bm_win_h(plan.win);
-    const int lx = blockIdx.x * blockDim.x + threadIdx.x, ly = blockIdx.y * blockDim.y + threadIdx.y;
-    if (lx >= ww || ly >= wh) return;
-    const int x = plan.win.x0 + lx, y = plan.win.y0 + ly;
-    const uchar4 w = wbuf[(size_t)ly * ww + lx];
-    uchar4* cp = canvas + (size_t)y * plan.canvas_w + x;
-    if (flags[0] == 0) {                                   // main.py:925-927: channel-wise overwrite
-        if (!w.w) return;
-        uchar4 c = *cp;
-        if (w.x) c.x = w.x;
-        if (w.y) c.y = w.y;
-        if (w.z) c.z = w.z;
-        c.w = 255;
-        *cp = c;
+    const int bx = plan.win.x0 + blockIdx.x * FB_T, by = plan.win.y0 + blockIdx.y * FB_T;     // canvas coords of the tile origin
+    if (flags[0] == 0) {                                   // main.py:925-927: channel-wise overwrite, no weights needed
+        for (int i = tid; i < FB_T * FB_T; i += 256) {
+            const int x = bx + (i & 31), y = by + (i >> 5);
+            if (x >= plan.win.x1 || y >= plan.win.y1) continue;
+            const uchar4 w = wbuf[(size_t)(y - plan.win.y0) * ww + (x - plan.win.x0)];
+            if (!w.w) continue;
+            uchar4* cp = canvas + (size_t)y * plan.canvas_w + x;
+            uchar4 c = *cp;
+            if (w.x) c.x = w.x;
+            if (w.y) c.y = w.y;
+            if (w.z) c.z = w.z;
+            c.w = 255;
+            *cp = c;
+        }
         return;
     }
-    if (!w.w) return;                                      // canvas keeps its value where mask_new == 0
-    uchar4 c = *cp;
-    if (!c.w) { *cp = w; return; }                         // non-overlap new: pixel copy (main.py:922-924)
-    // overlap: weights = Blur31(dn/s), Blur31(do/s) at this pixel
-    float wn, wo;
-    {
-        const float2 v0 = hbuf[(size_t)(y - plan.reg.y0) * ww + lx];
-        wn = __fmul_rn(v0.x, c_gk[15]); wo = __fmul_rn(v0.y, c_gk[15]);
+    const int rw = bm_win_w(plan.reg);
+    for (int i = tid; i < FB_S * FB_S; i += 256) {
+        const int ty = i / FB_S, tx = i % FB_S;
+        const int gx = reflect101(bx + tx - BM_BLUR_R, plan.canvas_w), gy = reflect101(by + ty - BM_BLUR_R, plan.canvas_h);
+        float2 v = make_float2(0.f, 0.f);
+        // pixels of the tile that lie beyond the window (only for partial edge tiles) are never used by valid outputs
+        if (gx >= plan.reg.x0 && gx < plan.reg.x1 && gy >= plan.reg.y0 && gy < plan.reg.y1)
+            v = rbuf[(size_t)(gy - plan.reg.y0) * rw + (gx - plan.reg.x0)];
+        tile[ty][tx] = v;
+    }
+    __syncthreads();
+    if (tid < FB_S * 4) {                                  // 62 rows x 4 segments of 8 outputs
+        const int r = tid >> 2, c0 = (tid & 3) * 8;
+        float ax[8], ay[8];
 #pragma unroll
-        for (int t = 1; t <= BM_BLUR_R; ++t) {
-            const int ya = reflect101(y + t, plan.canvas_h) - plan.reg.y0;
-            const int yb = reflect101(y - t, plan.canvas_h) - plan.reg.y0;
-            const float2 a = hbuf[(size_t)ya * ww + lx], b = hbuf[(size_t)yb * ww + lx];
-            wn = __fmaf_rn(__fadd_rn(a.x, b.x), c_gk[15 - t], wn);
-            wo = __fmaf_rn(__fadd_rn(a.y, b.y), c_gk[15 - t], wo);
+        for (int t = 0; t < 38; ++t) {
+            const float2 v = tile[r][c0 + t];
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+                const int k = t - o;
+                if (k == 0) { ax[o] = __fmul_rn(v.x, c_gk[0]); ay[o] = __fmul_rn(v.y, c_gk[0]); }
+                else if (k > 0 && k < 31) { const float g = c_gk[k < 16 ? k : 30 - k]; ax[o] = __fmaf_rn(v.x, g, ax[o]); ay[o] = __fmaf_rn(v.y, g, ay[o]); }
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < 8; ++o) hrow[r][c0 + o] = make_float2(ax[o], ay[o]);
+    }
+    __syncthreads();
+    {
+        const int c = tid & 31, r0 = (tid >> 5) * 4;       // 32 columns x 8 groups of 4 rows
+        float2 h[34];
+#pragma unroll
+        for (int t = 0; t < 34; ++t) h[t] = hrow[r0 + t][c];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            const int x = bx + c, y = by + r0 + o;
+            if (x >= plan.win.x1 || y >= plan.win.y1) continue;
+            const uchar4 w = wbuf[(size_t)(y - plan.win.y0) * ww + (x - plan.win.x0)];
+            if (!w.w) continue;                            // canvas keeps its value where mask_new == 0
+            uchar4* cp = canvas + (size_t)y * plan.canvas_w + x;
+            const uchar4 cv = *cp;
+            if (!cv.w) { *cp = w; continue; }              // non-overlap new: pixel copy (main.py:922-924)
+            float wn = __fmul_rn(h[o + 15].x, c_gk[15]), wo = __fmul_rn(h[o + 15].y, c_gk[15]);
+#pragma unroll
+            for (int t = 1; t <= BM_BLUR_R; ++t) {
+                wn = __fmaf_rn(__fadd_rn(h[o + 15 + t].x, h[o + 15 - t].x), c_gk[15 - t], wn);
+                wo = __fmaf_rn(__fadd_rn(h[o + 15 + t].y, h[o + 15 - t].y), c_gk[15 - t], wo);
+            }
+            uchar4 ov;
+            ov.x = (unsigned char)__float2int_rz(__fadd_rn(__fmul_rn((float)cv.x, wo), __fmul_rn((float)w.x, wn)));
+            ov.y = (unsigned char)__float2int_rz(__fadd_rn(__fmul_rn((float)cv.y, wo), __fmul_rn((float)w.y, wn)));
+            ov.z = (unsigned char)__float2int_rz(__fadd_rn(__fmul_rn((float)cv.z, wo), __fmul_rn((float)w.z, wn)));
+            ov.w = (ov.x | ov.y | ov.z) ? 255 : 0;
+            *cp = ov;
         }
     }
-    uchar4 o;
-    // float32(canvas)*w_old + float32(warped)*w_new, then astype(uint8) = truncation (main.py:905-910)
-    o.x = (unsigned char)__float2int_rz(__fadd_rn(__fmul_rn((float)c.x, wo), __fmul_rn((float)w.x, wn)));
-    o.y = (unsigned char)__float2int_rz(__fadd_rn(__fmul_rn((float)c.y, wo), __fmul_rn((float)w.y, wn)));
-    o.z = (unsigned char)__float2int_rz(__fadd_rn(__fmul_rn((float)c.z, wo), __fmul_rn((float)w.z, wn)));
-    o.w = (o.x | o.y | o.z) ? 255 : 0;
-    *cp = o;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -545,7 +576,7 @@ static inline dim3 grid2(int w, int h, dim3 b) { return dim3((w + b.x - 1) / b.x
 
 cudaError_t bm_launch_full_rowscan(const BmBlendBufs& b, cudaStream_t s) {
     const int rows = b.canvas_h;
-    BM_COUNT_LAUNCHES(1), k_rowscan<<<bm_div_up(rows * 32, 256), 256, 0, s>>>(b.canvas, b.canvas_w, 0, b.canvas_w, 0, rows, b.g_old, 0, b.flags, 0);
+    BM_COUNT_LAUNCHES(1), k_rowscan<<<rows, 256, 0, s>>>(b.canvas, b.canvas_w, 0, b.canvas_w, 0, rows, b.g_old, 0, b.flags, 0);
     const int nb = bm_div_up(rows, BM_BLK_ROWS);
     BM_COUNT_LAUNCHES(1), k_blockmin<<<dim3(bm_div_up(b.canvas_w, 256), nb), 256, 0, s>>>(b.g_old, b.canvas_w, rows, 0, nb, b.gblk_old, b.flags, 0);
     return cudaGetLastError();
@@ -557,7 +588,7 @@ cudaError_t bm_launch_blend_from_wbuf(const BmBlendBufs& b, const BmFramePlan& p
     const int rw = bm_win_w(plan.reg), rh = bm_win_h(plan.reg);
     const dim3 blk(32, 8);
     // mask_new row structure over W (only needed when there is overlap: kernels exit early on flags[0]==0)
-    BM_COUNT_LAUNCHES(1), k_rowscan<<<bm_div_up(wh * 32, 256), 256, 0, s>>>(b.wbuf, ww, 0, ww, 0, wh, b.g_new, 0, b.flags, 1);
+    BM_COUNT_LAUNCHES(1), k_rowscan<<<wh, 256, 0, s>>>(b.wbuf, ww, 0, ww, 0, wh, b.g_new, 0, b.flags, 1);
     const int nbw = bm_div_up(wh, BM_BLK_ROWS);
     BM_COUNT_LAUNCHES(1), k_blockmin<<<dim3(bm_div_up(ww, 256), nbw), 256, 0, s>>>(b.g_new, ww, wh, 0, nbw, b.gblk_new, b.flags, 1);
     {
@@ -565,10 +596,9 @@ cudaError_t bm_launch_blend_from_wbuf(const BmBlendBufs& b, const BmFramePlan& p
         const dim3 b2(32, 4);
         BM_COUNT_LAUNCHES(1), k_dt_weights<<<dim3(bm_div_up(rw, 32), bm_div_up(nyb, 4)), b2, 0, s>>>(b.plan, b.g_old, b.gblk_old, b.g_new, b.gblk_new, b.rbuf, b.flags);
     }
-    BM_COUNT_LAUNCHES(1), k_blur_rows<<<grid2(ww, rh, blk), blk, 0, s>>>(b.plan, b.rbuf, b.hbuf, b.flags);
-    BM_COUNT_LAUNCHES(1), k_blur_cols_blend<<<grid2(ww, wh, blk), blk, 0, s>>>(b.plan, b.hbuf, b.wbuf, b.canvas, b.flags);
+    BM_COUNT_LAUNCHES(1), k_blur_blend<<<dim3(bm_div_up(ww, FB_T), bm_div_up(wh, FB_T)), blk, 0, s>>>(b.plan, b.rbuf, b.wbuf, b.canvas, b.flags);
     // refresh the persistent row structure for the rows the frame touched
-    BM_COUNT_LAUNCHES(1), k_rowscan<<<bm_div_up(wh * 32, 256), 256, 0, s>>>(b.canvas, b.canvas_w, 0, b.canvas_w, plan.win.y0, wh, b.g_old, plan.win.y0, b.flags, 0);
+    BM_COUNT_LAUNCHES(1), k_rowscan<<<wh, 256, 0, s>>>(b.canvas, b.canvas_w, 0, b.canvas_w, plan.win.y0, wh, b.g_old, plan.win.y0, b.flags, 0);
     const int Y0 = plan.win.y0 / BM_BLK_ROWS, Y1 = bm_div_up(plan.win.y1, BM_BLK_ROWS);
     BM_COUNT_LAUNCHES(1), k_blockmin<<<dim3(bm_div_up(b.canvas_w, 256), Y1 - Y0), 256, 0, s>>>(b.g_old, b.canvas_w, b.canvas_h, Y0, Y1, b.gblk_old, b.flags, 0);
     return cudaGetLastError();

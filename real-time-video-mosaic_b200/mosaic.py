@@ -157,6 +157,39 @@ class VideMosaic:
         self._canvas_cache = None
         return st
 
+    def begin_frame_ptr(self, host_ptr):
+        """enqueue half of process_frame (H2D + detect + match + RANSAC), no wait -- see bm_process_frame_begin"""
+        _lib.check(self._lib.bm_process_frame_begin(self._h, C.c_void_p(host_ptr), 0), "bm_process_frame_begin")
+
+    def begin_frame_device(self, dev_ptr):
+        _lib.check(self._lib.bm_process_frame_begin_device(self._h, C.c_void_p(dev_ptr)), "bm_process_frame_begin_device")
+
+    def end_frame(self):
+        """second half: wait for the read-back, host control flow, enqueue warp/blend.  Returns the status."""
+        info = _lib.BmFrameInfo()
+        st = _lib.check(self._lib.bm_process_frame_end(self._h, C.byref(info)), "bm_process_frame_end")
+        self.last_info = info
+        self._canvas_cache = None
+        return st
+
+    def estimate_frame(self, frame):
+        """offline pair mode: features + matches + RANSAC against the previous frame, no validation / warp; the frame
+        becomes the new previous.  Returns (status, H_rel or None, n_matches)."""
+        frame = self._check_frame(frame)
+        info = _lib.BmFrameInfo()
+        st = _lib.check(self._lib.bm_estimate_frame(self._h, frame.ctypes.data_as(C.c_void_p), 0, C.byref(info)), "bm_estimate_frame")
+        self.last_info = info
+        H = np.array(info.H_rel, dtype=np.float64).reshape(3, 3) if st == _lib.BM_OK else None
+        return st, H, info.n_matches
+
+    def clear_canvas(self):
+        _lib.check(self._lib.bm_clear_canvas(self._h), "bm_clear_canvas")
+        self._canvas_cache = None
+
+    def canvas_to_device(self, dev_ptr):
+        """packed BGR canvas into a device buffer (torch tensor .data_ptr()) -- for NCCL gathers of canvas tiles"""
+        _lib.check(self._lib.bm_get_canvas_device(self._h, C.c_void_p(dev_ptr)), "bm_get_canvas_device")
+
     def timing(self, enable=None, reset=False):
         """CUDA-event timing of the warp/blend chain: returns (ms, algorithmic bytes = 3N + 6A per frame, frames)."""
         if enable is not None:

@@ -1,0 +1,96 @@
+"""GPU tests of the sharded modes on one device: the split begin/end form used for concurrent streams, the
+offline per-pair estimation + prefix composition, and canvas row tiles."""
+import numpy as np
+import cv2
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sweep_frames():
+    from b200mosaic.synth import DroneSweep
+    sw = DroneSweep(640, 360, seed=7, ground_size=2048, max_step=9.0)
+    return sw.frames(7), sw
+
+
+def test_interleaved_streams_equal_sequential(sweep_frames):
+    import b200mosaic
+    frames, _ = sweep_frames
+    from b200mosaic.synth import DroneSweep
+    frames_b = DroneSweep(640, 360, seed=8, ground_size=2048, max_step=9.0).frames(7)
+    seq = []
+    for fr in (frames, frames_b):
+        vm = b200mosaic.VideMosaic(fr[0], detector_type="orb", show_intermediate=False, visualize=False)
+        for t in range(1, 7):
+            vm.process_frame(fr[t], t)
+        seq.append((vm.output_img.copy(), vm.H.copy()))
+    a = b200mosaic.VideMosaic(frames[0], detector_type="orb", show_intermediate=False, visualize=False)
+    b = b200mosaic.VideMosaic(frames_b[0], detector_type="orb", show_intermediate=False, visualize=False)
+    pin_a = torch.from_numpy(np.stack(frames)).pin_memory(); pin_b = torch.from_numpy(np.stack(frames_b)).pin_memory()
+    fb = frames[0].nbytes
+    for t in range(1, 7):
+        a.begin_frame_ptr(pin_a.data_ptr() + t * fb)
+        b.begin_frame_ptr(pin_b.data_ptr() + t * fb)
+        assert a.end_frame() == 0 and b.end_frame() == 0
+    assert np.array_equal(a.output_img, seq[0][0]) and np.array_equal(b.output_img, seq[1][0])
+    assert np.array_equal(np.array(a.last_info.H).reshape(3, 3), seq[0][1])
+
+
+def test_offline_pairs_and_prefix_composition(sweep_frames):
+    import b200mosaic
+    from b200mosaic import sharding as sh
+    frames, _ = sweep_frames
+    vm = b200mosaic.VideMosaic(frames[0], detector_type="orb", show_intermediate=False, visualize=False)
+    H0 = vm.H_old.copy()
+    want_rel, want_abs = [], []
+    for t in range(1, 7):
+        vm.process_frame(frames[t], t)
+        want_rel.append(np.array(vm.last_info.H_rel).reshape(3, 3)); want_abs.append(vm.H.copy())
+    # two "ranks" on one device: pairs [1,4) and [4,7)
+    rows = []
+    for r in range(2):
+        s, e = sh.shard_pairs(len(frames), r, 2)
+        st, Hs = sh.estimate_pairs(frames, s, e, detector_type="orb")
+        rows.append(sh.pack_pairs(st, Hs))
+    rel = sh.unpack_pairs(np.concatenate(rows))
+    for a, b in zip(rel, want_rel):
+        assert np.array_equal(a, b)                       # same kernels, same inputs -> bit-identical H_rel
+    got = sh.compose_chain(H0, rel)
+    for a, b in zip(got, want_abs):
+        assert np.abs(a - b).max() < 1e-9
+
+
+def test_canvas_row_tiles_match_untiled(sweep_frames):
+    """two row tiles on one device; the sweep stays inside the lower tile, so every tile must equal the same rows of the
+    untiled canvas bit for bit; assembled with the same gather helper the NCCL path uses."""
+    import b200mosaic
+    from b200mosaic import sharding as sh
+    frames, sw = sweep_frames
+    fh, fw = frames[0].shape[:2]
+    Hc, Wc = 3 * fh + 24, int(1.2 * fw)                 # frame 0 sits at the bottom; 6 steps of <= 9 px stay in the lower tile
+    full = b200mosaic.VideMosaic(frames[0], detector_type="orb", show_intermediate=False, visualize=False, canvas_size=(Hc, Wc))
+    H = full.H_old.copy()
+    Hs = [H.copy()]
+    for t in range(1, 7):
+        H = H @ sw.D_true[t - 1]
+        Hs.append(H.copy())
+        full.warp(frames[t], H)
+    want = full.output_img
+    tiles = []
+    for r in range(2):
+        y0, y1 = sh.tile_rows(Hc, r, 2)
+        vm = b200mosaic.VideMosaic(frames[0], detector_type="orb", show_intermediate=False, visualize=False, canvas_size=(y1 - y0, Wc))
+        vm.clear_canvas()
+        for t in range(0, 7):
+            if sh.touches_tile(Hs[t], fw, fh, y0, y1):
+                vm.warp(frames[t], sh.tile_homography(Hs[t], y0))
+        dev = torch.empty((y1 - y0, Wc, 3), dtype=torch.uint8, device="cuda")
+        vm.canvas_to_device(dev.data_ptr())
+        tiles.append(dev)
+    got = torch.cat(tiles, dim=0).cpu().numpy()
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
+    y0, y1 = sh.tile_rows(Hc, 0, 2)
+    assert got[:y1].max() == 0                            # the upper tile was never touched
