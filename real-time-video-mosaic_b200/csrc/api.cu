@@ -26,8 +26,8 @@ extern "C" long long bm_kernel_launches(void) { return g_bm_launches; }
 // handle
 // ------------------------------------------------------------------------------------------------------------------
 static void free_blend(BmBlendBufs& b) {
-    cudaFree(b.canvas); cudaFree(b.g_old); cudaFree(b.gblk_old); cudaFree(b.wbuf); cudaFree(b.g_new); cudaFree(b.gblk_new);
-    cudaFree(b.rbuf); cudaFree(b.hbuf); cudaFree(b.flags); cudaFree(b.plan);
+    cudaFree(b.canvas); cudaFree(b.wbuf); cudaFree(b.wn); cudaFree(b.wo); cudaFree(b.flags);
+    bm_dt_free_plane(&b.dt.p[0]); bm_dt_free_plane(&b.dt.p[1]);
     memset(&b, 0, sizeof(b));
 }
 
@@ -35,19 +35,16 @@ static bm_status alloc_blend(BmBlendBufs& b, int canvas_h, int canvas_w, size_t 
     memset(&b, 0, sizeof(b));
     b.canvas_h = canvas_h; b.canvas_w = canvas_w;
     const size_t n = (size_t)canvas_h * canvas_w;
-    const size_t nblk = (size_t)bm_div_up(canvas_h, BM_BLK_ROWS) * canvas_w;
     if (scratch_px > n || scratch_px == 0) scratch_px = n;
     b.scratch_px = scratch_px;
+    const size_t pad = (size_t)8 * canvas_h + 64;          // row strides of the scratch planes are padded to 8 / 4 columns
     BM_CUDA_OK(cudaMalloc(&b.canvas, n * sizeof(uchar4)));
-    BM_CUDA_OK(cudaMalloc(&b.g_old, n * sizeof(uint16_t)));
-    BM_CUDA_OK(cudaMalloc(&b.gblk_old, nblk * sizeof(uint16_t)));
-    BM_CUDA_OK(cudaMalloc(&b.wbuf, scratch_px * sizeof(uchar4)));
-    BM_CUDA_OK(cudaMalloc(&b.g_new, scratch_px * sizeof(uint16_t)));
-    BM_CUDA_OK(cudaMalloc(&b.gblk_new, (scratch_px / BM_BLK_ROWS + (size_t)canvas_w + 64) * sizeof(uint16_t)));
-    BM_CUDA_OK(cudaMalloc(&b.rbuf, scratch_px * sizeof(float2)));
-    BM_CUDA_OK(cudaMalloc(&b.hbuf, scratch_px * sizeof(float2)));
+    BM_CUDA_OK(bm_dt_alloc_plane(&b.dt.p[0], canvas_w, canvas_h, n));
+    BM_CUDA_OK(bm_dt_alloc_plane(&b.dt.p[1], canvas_w, canvas_h, scratch_px));
+    BM_CUDA_OK(cudaMalloc(&b.wbuf, (scratch_px + pad) * sizeof(uchar4)));
+    BM_CUDA_OK(cudaMalloc(&b.wn, (scratch_px + pad) * sizeof(float)));
+    BM_CUDA_OK(cudaMalloc(&b.wo, (scratch_px + pad) * sizeof(float)));
     BM_CUDA_OK(cudaMalloc(&b.flags, 16 * sizeof(int)));
-    BM_CUDA_OK(cudaMalloc(&b.plan, sizeof(BmFramePlan)));
     BM_CUDA_OK(cudaMemset(b.canvas, 0, n * sizeof(uchar4)));
     BM_CUDA_OK(cudaMemset(b.flags, 0, 16 * sizeof(int)));
     return BM_OK;
@@ -480,12 +477,12 @@ extern "C" bm_status bm_warp_perspective_bgr(const uint8_t* d_src, int sh, int s
 extern "C" bm_status bm_distance_transform(const uint8_t* d_mask, int h, int w, float* d_out, void* stream) {
     if (!d_mask || !d_out || h <= 0 || w <= 0) return BM_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
-    uint16_t *g = nullptr, *gb = nullptr;
-    BM_CUDA_OK(cudaMalloc(&g, (size_t)h * w * 2));
-    BM_CUDA_OK(cudaMalloc(&gb, (size_t)bm_div_up(h, BM_BLK_ROWS) * w * 2));
-    cudaError_t e = bm_launch_dt_mask(d_mask, h, w, d_out, g, gb, s);
+    BmDtPlane p;
+    cudaError_t e = bm_dt_alloc_plane(&p, w, h, (size_t)w * h);
+    if (e == cudaSuccess) e = bm_launch_rowscan_u8(d_mask, w, p, s);
+    if (e == cudaSuccess) e = bm_launch_dt_map(p, d_out, s);
     cudaStreamSynchronize(s);
-    cudaFree(g); cudaFree(gb);
+    bm_dt_free_plane(&p);
     BM_CUDA_OK(e);
     return BM_OK;
 }
@@ -515,12 +512,10 @@ extern "C" bm_status bm_blend_step_bgr(uint8_t* d_canvas, const uint8_t* d_warpe
         w.x0 = win[0] - 1 < 0 ? 0 : win[0] - 1; w.y0 = win[1] - 1 < 0 ? 0 : win[1] - 1;
         w.x1 = win[2] + 1 > dw ? dw : win[2] + 1; w.y1 = win[3] + 1 > dh ? dh : win[3] + 1;
     }
-    w.y0 = (w.y0 / BM_BLK_ROWS) * BM_BLK_ROWS;
     plan.win = w;
-    plan.reg.x0 = w.x0 - BM_BLUR_R < 0 ? 0 : w.x0 - BM_BLUR_R; plan.reg.y0 = w.y0 - BM_BLUR_R < 0 ? 0 : w.y0 - BM_BLUR_R;
-    plan.reg.x1 = w.x1 + BM_BLUR_R > dw ? dw : w.x1 + BM_BLUR_R; plan.reg.y1 = w.y1 + BM_BLUR_R > dh ? dh : w.y1 + BM_BLUR_R;
+    bm_finish_plan(&plan);
     cudaError_t e = cudaSuccess;
-    if (w.x1 > w.x0 && w.y1 > w.y0) {
+    if (plan.valid) {
         e = bm_launch_pack_canvas(d_canvas, b.canvas, dh * dw, s);
         if (e == cudaSuccess) e = bm_launch_full_rowscan(b, s);
         if (e == cudaSuccess) e = bm_launch_extract_wbuf(d_warped, plan, b, s);

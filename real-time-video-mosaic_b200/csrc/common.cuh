@@ -6,9 +6,9 @@
 
 #define BM_CHAMFER_A 62587          // cvRound(0.955f  * 65536), OpenCV distanceTransform DIST_L2 3x3
 #define BM_CHAMFER_B 89738          // cvRound(1.3693f * 65536)
-#define BM_DT_INIT 536870911        // INT_MAX >> 2 (OpenCV's INIT / DIST_MAX)
+#define BM_DT_INIT 4294877557u      // OpenCV 4.x distanceTransform_3x3: DIST_MAX = UINT_MAX - DIAG_DIST (saturation value)
 #define BM_G_INF 0xFFFF             // "no zero pixel in this row"
-#define BM_BLK_ROWS 16              // rows per block of the pruning table
+#define BM_BLK_ROWS 16              // rows per block of the distance-transform sweep tables
 #define BM_BLUR_R 15                // 31-tap Gaussian radius
 
 struct BmWin { int x0, y0, x1, y1; };   // half-open pixel rectangle in canvas coordinates
@@ -25,7 +25,11 @@ struct BmFramePlan {
     int canvas_w, canvas_h;
     int block_w;        // OpenCV's warpPerspective evaluation block width (64 for canvases >= 64 px wide)
     int valid;          // 0 -> nothing to do this frame
+    int ws;             // row stride of the window scratch (warped frame, g_new): win width padded to 8
+    int rx0, rws;       // weight planes over R: column origin (reg.x0 rounded down to 4) and row stride
 };
+// win -> aligned win (x0 to 8 columns, y0 to 16 rows), reg, strides.  Host side (warp_blend.cu).
+void bm_finish_plan(BmFramePlan* p);
 
 extern "C" const char* bm_last_error(void);
 void bm_set_error(const char* fmt, ...);

@@ -1,0 +1,410 @@
+// dt.cu -- cv2.distanceTransform(mask, DIST_L2, 3) (reference: /root/reference/main.py:888-889), exact, O(1) per pixel.
+//
+// OpenCV's 3x3 chamfer transform is the shortest-path distance on the 8-connected pixel grid with integer 16.16 step
+// costs a (axial) and b (diagonal), a <= b <= 2a.  A shortest path to a zero pixel can always be ordered as
+//        k vertical steps, then j steps along ONE diagonal direction, then a horizontal run,
+// and steps commute, so with  s(x,y) = a * g(x,y)  (g = horizontal distance to the nearest zero pixel of row y):
+//        E1(x,y) = min(s(x,y), E1(x-1,y-1) + b)        E2(x,y) = min(s(x,y), E2(x+1,y-1) + b)
+//        V (x,y) = min(min(E1,E2)(x,y), V(x,y-1) + a)                                   ("downward" sweep)
+// plus the mirrored upward sweep; D = min(V_down, V_up).  Every recurrence is a one-directional linear-cost min-scan
+// along a line (diagonal or column): cutting the lines into blocks of 16 rows, a block's result is
+//        min(block-local scan, carry of the previous block + 16 * step)
+// and the carries form a scalar chain PER LINE (no coupling between lines).  That gives five fully parallel phases:
+//   1. k_dt_local       block-local E1/E2 (down and up) at the block boundary rows              -> LE
+//   2. k_dt_diag_chain  one thread per diagonal line walks the blocks                           -> CE
+//   3. k_dt_vert_local  E1/E2 with their carries, min, block-local V at the boundary rows       -> CV (local)
+//   4. k_dt_vert_chain  one thread per column walks the blocks                                  -> CV (in place)
+//   5. k_dt_weights / k_dt_map   both sweeps of a block with all carries -> D (-> blend weights)
+// For the canvas plane phase 1 is persistent: only blocks whose rows changed are recomputed (after each blend).
+// All arithmetic is integer and order-free (min / +), so the result equals OpenCV's two-pass raster scan bit for bit.
+// A warp sweeps a tile of 128 columns x 16 rows, 4 consecutive columns per lane (8-byte loads of g), exchanging only
+// the two edge columns per row with its neighbours by shuffle; 16 columns on each side are halo.
+#include "dt.cuh"
+#include "rowscan.cuh"
+
+#define A_ ((unsigned)BM_CHAMFER_A)
+#define B_ ((unsigned)BM_CHAMFER_B)
+typedef unsigned int u32;
+#define DT_CHAIN_BATCH 32
+#define FULL 0xffffffffu
+
+// ------------------------------------------------------------------------------------------------------------------
+// row scans
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_rowscan_bgrx(const uchar4* __restrict__ img, int img_stride, int img_col0, int img_row0,
+                                                      uint16_t* __restrict__ g, int gs, int n, int row0, const int* __restrict__ flags,
+                                                      int need_flag) {
+    if (need_flag && flags[0] == 0) return;
+    const int r = blockIdx.x, tid = threadIdx.x;
+    const uchar4* row = img + (size_t)(img_row0 + r) * img_stride + img_col0;
+    const int nch = (n + BM_ROWSCAN_CHUNK - 1) / BM_ROWSCAN_CHUNK;
+    const bool vec = (reinterpret_cast<uintptr_t>(row) & 15) == 0;
+    BmZeroBits zb; zb.clear();
+    for (int c = 0; c < nch; ++c) {
+        const int base = c * BM_ROWSCAN_CHUNK + 8 * tid;
+        unsigned b = 0;
+        if (vec && base + 7 < n) {
+            const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(row + base)), v1 = __ldg(reinterpret_cast<const uint4*>(row + base) + 1);
+            b = ((v0.x >> 24) == 0) | (((v0.y >> 24) == 0) << 1) | (((v0.z >> 24) == 0) << 2) | (((v0.w >> 24) == 0) << 3) |
+                (((v1.x >> 24) == 0) << 4) | (((v1.y >> 24) == 0) << 5) | (((v1.z >> 24) == 0) << 6) | (((v1.w >> 24) == 0) << 7);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if (base + i < n && row[base + i].w == 0) b |= 1u << i;
+        }
+        zb.set(c, b);
+    }
+    bm_rowscan_block(zb, nch, n, g + (size_t)(row0 + r) * gs);
+}
+
+__global__ void __launch_bounds__(256) k_rowscan_mask(const uint8_t* __restrict__ mask, int stride, uint16_t* __restrict__ g, int gs, int n) {
+    const int r = blockIdx.x, tid = threadIdx.x;
+    const uint8_t* row = mask + (size_t)r * stride;
+    const int nch = (n + BM_ROWSCAN_CHUNK - 1) / BM_ROWSCAN_CHUNK;
+    BmZeroBits zb; zb.clear();
+    for (int c = 0; c < nch; ++c) {
+        const int base = c * BM_ROWSCAN_CHUNK + 8 * tid;
+        unsigned b = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (base + i < n && row[base + i] == 0) b |= 1u << i;
+        zb.set(c, b);
+    }
+    bm_rowscan_block(zb, nch, n, g + (size_t)r * gs);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// warp-tile sweep primitives
+// ------------------------------------------------------------------------------------------------------------------
+struct DtRows { uint2 g[BM_BLK_ROWS]; unsigned colmask; };
+
+// the 16 rows of block k for the lane's 4 columns [cx, cx+4) (cx is a multiple of 4, may lie outside the plane)
+__device__ __forceinline__ void dt_load_rows(const BmDtPlane& p, int k, int cx, DtRows& R) {
+    R.colmask = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if (cx + i >= 0 && cx + i < p.W) R.colmask |= 1u << i;
+    const bool ld = cx >= 0 && cx < p.W;
+    const uint16_t* base = p.g + (size_t)(k * BM_BLK_ROWS) * p.gs + cx;
+#pragma unroll
+    for (int r = 0; r < BM_BLK_ROWS; ++r) {
+        R.g[r] = make_uint2(0xffffffffu, 0xffffffffu);
+        if (ld && k * BM_BLK_ROWS + r < p.H) R.g[r] = __ldg(reinterpret_cast<const uint2*>(base + (size_t)r * p.gs));
+    }
+}
+
+// seeds a * g in cv2's unsigned 16.16 arithmetic: g <= 65534 keeps a * g < DIST_MAX; g == 0xFFFF means "no zero in this row"
+__device__ __forceinline__ u32 dt_seed1(u32 g, bool colok) { return (colok && g != BM_G_INF) ? A_ * g : BM_DT_INF; }
+__device__ __forceinline__ void dt_seeds(const DtRows& R, int r, u32 (&s)[4]) {
+    const uint2 v = R.g[r];
+    s[0] = dt_seed1(v.x & 0xffffu, R.colmask & 1u);
+    s[1] = dt_seed1(v.x >> 16, R.colmask & 2u);
+    s[2] = dt_seed1(v.y & 0xffffu, R.colmask & 4u);
+    s[3] = dt_seed1(v.y >> 16, R.colmask & 8u);
+}
+
+// one row step of both diagonal scans: E1 flows to the right (from column x-1 of the previous row), E2 to the left
+// (every value is <= DIST_MAX = UINT_MAX - b, so "+ b" cannot wrap; "+ a" neither since a < b)
+__device__ __forceinline__ void dt_step(u32 (&E1)[4], u32 (&E2)[4], const u32 (&s)[4], int lane) {
+    u32 l = __shfl_up_sync(FULL, E1[3], 1), r = __shfl_down_sync(FULL, E2[0], 1);
+    if (lane == 0) l = BM_DT_INF;
+    if (lane == 31) r = BM_DT_INF;
+    E1[3] = min(s[3], E1[2] + B_); E1[2] = min(s[2], E1[1] + B_); E1[1] = min(s[1], E1[0] + B_); E1[0] = min(s[0], l + B_);
+    E2[0] = min(s[0], E2[1] + B_); E2[1] = min(s[1], E2[2] + B_); E2[2] = min(s[2], E2[3] + B_); E2[3] = min(s[3], r + B_);
+}
+
+__device__ __forceinline__ void dt_fill(u32 (&v)[4], u32 x) { v[0] = v[1] = v[2] = v[3] = x; }
+
+// 4 carry values of table row `k` at columns [cx, cx+4); BM_DT_INF outside the plane / block range
+__device__ __forceinline__ void dt_carry4(const u32* __restrict__ tab, const BmDtPlane& p, int k, int cx, u32 (&o)[4]) {
+    dt_fill(o, BM_DT_INF);
+    if (k < 0 || k >= p.nb || cx < 0 || cx >= p.W) return;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(tab + (size_t)k * p.ts + cx));
+    o[0] = v.x;
+    if (cx + 1 < p.W) o[1] = v.y;
+    if (cx + 2 < p.W) o[2] = v.z;
+    if (cx + 3 < p.W) o[3] = v.w;
+}
+
+__device__ __forceinline__ void dt_store4(u32* __restrict__ tab, const BmDtPlane& p, int k, int cx, const u32 (&v)[4]) {
+    *reinterpret_cast<uint4*>(tab + (size_t)k * p.ts + cx) = make_uint4(v[0], v[1], v[2], v[3]);
+}
+
+// lanes whose 4 columns are exact after 16 row steps (the outer 16 columns of the 128 miss contributions)
+__device__ __forceinline__ bool dt_lane_valid(int lane) { return lane >= 4 && lane < 28; }
+
+// one sweep direction over the 16 rows of a block (UP: rows 15..0).  row(r, V) is called after each row step.
+template <bool UP, bool WITH_V, class RowFn>
+__device__ __forceinline__ void dt_sweep(const DtRows& R, u32 (&E1)[4], u32 (&E2)[4], u32 (&V)[4], int lane, RowFn row) {
+#pragma unroll
+    for (int i = 0; i < BM_BLK_ROWS; ++i) {
+        const int r = UP ? BM_BLK_ROWS - 1 - i : i;
+        u32 s[4];
+        dt_seeds(R, r, s);
+        dt_step(E1, E2, s, lane);
+        if (WITH_V) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) V[c] = min(min(E1[c], E2[c]), V[c] + A_);
+        }
+        row(r, V);
+    }
+}
+struct DtNoRow { __device__ __forceinline__ void operator()(int, const u32 (&)[4]) const {} };
+
+// ------------------------------------------------------------------------------------------------------------------
+// phase 1: block-local diagonal sweeps.  CTA = 2 tiles x {down, up}: one warp per (tile, direction)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_dt_local(BmDtPlane p, int kb0, const int* __restrict__ flags, int need_flag) {
+    if (need_flag && flags[0] == 0) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * 2 + (warp >> 1), k = kb0 + blockIdx.y;
+    const bool up = warp & 1;
+    if (tile * BM_DT_TILE_VALID >= p.W) return;
+    const int cx = tile * BM_DT_TILE_VALID - 16 + 4 * lane;
+    DtRows R;
+    dt_load_rows(p, k, cx, R);
+    u32 E1[4], E2[4], V[4];
+    dt_fill(E1, BM_DT_INF); dt_fill(E2, BM_DT_INF); dt_fill(V, BM_DT_INF);
+    if (up) dt_sweep<true, false>(R, E1, E2, V, lane, DtNoRow());
+    else dt_sweep<false, false>(R, E1, E2, V, lane, DtNoRow());
+    if (dt_lane_valid(lane) && cx < p.W) {
+        dt_store4(p.LE + (up ? 2 : 0) * p.tsz, p, k, cx, E1);
+        dt_store4(p.LE + (up ? 3 : 1) * p.tsz, p, k, cx, E2);
+    }
+}
+
+__device__ __forceinline__ u32 dt_add_sat(u32 c, u32 d) { return c > BM_DT_INF - d ? BM_DT_INF : c + d; }
+
+// ------------------------------------------------------------------------------------------------------------------
+// phase 2: diagonal carries.  type 0: down, from x-16; 1: down, from x+16; 2: up, from x-16; 3: up, from x+16
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_dt_diag_chain(BmDtPair pp, const int* __restrict__ flags, int need_flag) {
+    if (need_flag && flags[0] == 0) return;
+    const BmDtPlane& p = pp.p[blockIdx.z];
+    const int type = blockIdx.y;
+    const int nlines = p.W + 16 * (p.nb - 1);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nlines) return;
+    const bool right = (type & 1) == 0, down = type < 2;
+    const int x0 = right ? t - 16 * (p.nb - 1) : t, dx = right ? 16 : -16;
+    const u32* __restrict__ L = p.LE + (size_t)type * p.tsz;
+    u32* __restrict__ C = p.CE + (size_t)type * p.tsz;
+    u32 c = BM_DT_INF;
+    // the loads do not depend on the chain: issue DT_CHAIN_BATCH of them at once, then walk
+    for (int j0 = 0; j0 < p.nb; j0 += DT_CHAIN_BATCH) {
+        u32 v[DT_CHAIN_BATCH];
+#pragma unroll
+        for (int u = 0; u < DT_CHAIN_BATCH; ++u) {
+            const int j = j0 + u, x = x0 + dx * j, k = down ? j : p.nb - 1 - j;
+            v[u] = (j < p.nb && x >= 0 && x < p.W) ? __ldg(L + (size_t)k * p.ts + x) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < DT_CHAIN_BATCH; ++u) {
+            const int j = j0 + u, x = x0 + dx * j, k = down ? j : p.nb - 1 - j;
+            if (j < p.nb && x >= 0 && x < p.W) { c = min(v[u], dt_add_sat(c, 16u * B_)); C[(size_t)k * p.ts + x] = c; }
+            else c = BM_DT_INF;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// phase 3: diagonal sweeps with carries -> block-local vertical sweep
+// ------------------------------------------------------------------------------------------------------------------
+struct DtRange { int xa[2], xb[2]; };
+
+__global__ void __launch_bounds__(128) k_dt_vert_local(BmDtPair pp, DtRange rg, const int* __restrict__ flags, int need_flag) {
+    if (need_flag && flags[0] == 0) return;
+    const int pl = blockIdx.z;
+    const BmDtPlane& p = pp.p[pl];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * 2 + (warp >> 1), k = blockIdx.y;
+    const bool up = warp & 1;
+    const int xa = rg.xa[pl], xb = rg.xb[pl];
+    if (k >= p.nb || xa + tile * BM_DT_TILE_VALID >= xb) return;
+    const int cx = xa + tile * BM_DT_TILE_VALID - 16 + 4 * lane;
+    DtRows R;
+    dt_load_rows(p, k, cx, R);
+    u32 E1[4], E2[4], V[4];
+    dt_carry4(p.CE + (up ? 2 : 0) * p.tsz, p, up ? k + 1 : k - 1, cx, E1);
+    dt_carry4(p.CE + (up ? 3 : 1) * p.tsz, p, up ? k + 1 : k - 1, cx, E2);
+    dt_fill(V, BM_DT_INF);
+    if (up) dt_sweep<true, true>(R, E1, E2, V, lane, DtNoRow());
+    else dt_sweep<false, true>(R, E1, E2, V, lane, DtNoRow());
+    if (dt_lane_valid(lane) && cx < xb && cx < p.W) dt_store4(p.CV + (up ? 1 : 0) * p.tsz, p, k, cx, V);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// phase 4: vertical carries, in place.  type 0: down, 1: up
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_dt_vert_chain(BmDtPair pp, DtRange rg, const int* __restrict__ flags, int need_flag) {
+    if (need_flag && flags[0] == 0) return;
+    const int pl = blockIdx.z;
+    const BmDtPlane& p = pp.p[pl];
+    const int x = rg.xa[pl] + blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= rg.xb[pl] || x >= p.W) return;
+    const bool down = blockIdx.y == 0;
+    u32* __restrict__ C = p.CV + (size_t)blockIdx.y * p.tsz;
+    u32 c = BM_DT_INF;
+    for (int j0 = 0; j0 < p.nb; j0 += DT_CHAIN_BATCH) {
+        u32 v[DT_CHAIN_BATCH];
+#pragma unroll
+        for (int u = 0; u < DT_CHAIN_BATCH; ++u) {
+            const int j = j0 + u, k = down ? j : p.nb - 1 - j;
+            v[u] = j < p.nb ? C[(size_t)k * p.ts + x] : BM_DT_INF;
+        }
+#pragma unroll
+        for (int u = 0; u < DT_CHAIN_BATCH; ++u) {
+            const int j = j0 + u, k = down ? j : p.nb - 1 - j;
+            if (j < p.nb) { c = min(v[u], dt_add_sat(c, 16u * A_)); C[(size_t)k * p.ts + x] = c; }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// phase 5: sweeps of one block with all carries.  One warp per (plane, direction) writes its 16 x 128 values to shared
+// memory; the CTA then combines them.
+// ------------------------------------------------------------------------------------------------------------------
+#define DT_TW 128
+__device__ __forceinline__ void dt_sweep_to_smem(const BmDtPlane& p, int k, int cx, bool up, int lane, u32 (*T)[DT_TW]) {
+    DtRows R;
+    dt_load_rows(p, k, cx, R);
+    u32 E1[4], E2[4], V[4];
+    dt_carry4(p.CE + (up ? 2 : 0) * p.tsz, p, up ? k + 1 : k - 1, cx, E1);
+    dt_carry4(p.CE + (up ? 3 : 1) * p.tsz, p, up ? k + 1 : k - 1, cx, E2);
+    dt_carry4(p.CV + (up ? 1 : 0) * p.tsz, p, up ? k + 1 : k - 1, cx, V);
+    auto put = [&](int r, const u32 (&v)[4]) { *reinterpret_cast<uint4*>(&T[r][4 * lane]) = make_uint4(v[0], v[1], v[2], v[3]); };
+    if (up) dt_sweep<true, true>(R, E1, E2, V, lane, put);
+    else dt_sweep<false, true>(R, E1, E2, V, lane, put);
+}
+
+__global__ void __launch_bounds__(64) k_dt_map(BmDtPlane p, float* __restrict__ out) {
+    __shared__ __align__(16) u32 T[2][BM_BLK_ROWS][DT_TW];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x, k = blockIdx.y;
+    const int tx0 = tile * BM_DT_TILE_VALID - 16;
+    dt_sweep_to_smem(p, k, tx0 + 4 * lane, warp == 1, lane, T[warp]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < BM_BLK_ROWS * BM_DT_TILE_VALID; i += 64) {
+        const int r = i / BM_DT_TILE_VALID, c = 16 + i - r * BM_DT_TILE_VALID;
+        const int x = tx0 + c, y = k * BM_BLK_ROWS + r;
+        if (x < p.W && y < p.H) out[(size_t)y * p.W + x] = __fmul_rn(__uint2float_rn(min(T[0][r][c], T[1][r][c])), 1.0f / 65536.0f);
+    }
+}
+
+// (dn/s, do/s) in float32 exactly as NumPy does it (main.py:892-894): dist = uint * 2^-16, s = (dn + do) + 1e-6f
+__global__ void __launch_bounds__(128) k_dt_weights(BmDtPair pp, BmFramePlan plan, float* __restrict__ wn, float* __restrict__ wo,
+                                                    const int* __restrict__ flags) {
+    if (flags[0] == 0) return;
+    __shared__ __align__(16) u32 T[4][BM_BLK_ROWS][DT_TW];      // old down, old up, new down, new up
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x;
+    const int k = plan.reg.y0 / BM_BLK_ROWS + blockIdx.y;
+    const int tx0 = plan.rx0 + tile * BM_DT_TILE_VALID - 16;      // canvas column of the tile's first (halo) column
+    const int kn = k - plan.win.y0 / BM_BLK_ROWS;
+    const bool has_new = kn >= 0 && kn < pp.p[1].nb && tx0 + DT_TW > plan.win.x0 && tx0 < plan.win.x1;
+    if (warp < 2) dt_sweep_to_smem(pp.p[0], k, tx0 + 4 * lane, warp == 1, lane, T[warp]);
+    else if (has_new) dt_sweep_to_smem(pp.p[1], kn, tx0 - plan.win.x0 + 4 * lane, warp == 3, lane, T[warp]);
+    __syncthreads();
+    const float scale = 1.0f / 65536.0f;
+    for (int i = threadIdx.x; i < BM_BLK_ROWS * BM_DT_TILE_VALID; i += 128) {
+        const int r = i / BM_DT_TILE_VALID, c = 16 + i - r * BM_DT_TILE_VALID;
+        const int x = tx0 + c, y = k * BM_BLK_ROWS + r;
+        if (x < plan.reg.x0 || x >= plan.reg.x1 || y < plan.reg.y0 || y >= plan.reg.y1) continue;
+        const u32 d_old = min(T[0][r][c], T[1][r][c]);
+        u32 d_new = 0u;
+        if (has_new && x >= plan.win.x0 && x < plan.win.x1 && y >= plan.win.y0 && y < plan.win.y1) d_new = min(T[2][r][c], T[3][r][c]);
+        const float dn = __fmul_rn(__uint2float_rn(d_new), scale);
+        const float dold = __fmul_rn(__uint2float_rn(d_old), scale);
+        const float s = __fadd_rn(__fadd_rn(dn, dold), 1e-6f);
+        const size_t o = (size_t)(y - plan.reg.y0) * plan.rws + (x - plan.rx0);
+        wn[o] = __fdiv_rn(dn, s);
+        wo[o] = __fdiv_rn(dold, s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------
+cudaError_t bm_dt_alloc_plane(BmDtPlane* p, int Wcap, int Hcap, size_t px_cap) {
+    memset(p, 0, sizeof(*p));
+    // any live shape (W, H) with W <= Wcap, H <= Hcap, W*H <= px_cap must fit
+    p->g_cap = px_cap + (size_t)8 * Hcap + 64;
+    const size_t tsz = ((px_cap / BM_BLK_ROWS + (size_t)2 * (Wcap + 8) + (size_t)Hcap + 64) + 3) & ~(size_t)3;
+    p->tsz = tsz;
+    cudaError_t e;
+    if ((e = cudaMalloc(&p->g, p->g_cap * sizeof(uint16_t))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&p->LE, 4 * tsz * sizeof(uint32_t))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&p->CE, 4 * tsz * sizeof(uint32_t))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&p->CV, 2 * tsz * sizeof(uint32_t))) != cudaSuccess) return e;
+    bm_dt_shape_plane(p, Wcap, Hcap);
+    return cudaSuccess;
+}
+
+void bm_dt_free_plane(BmDtPlane* p) {
+    cudaFree(p->g); cudaFree(p->LE); cudaFree(p->CE); cudaFree(p->CV);
+    memset(p, 0, sizeof(*p));
+}
+
+bool bm_dt_shape_plane(BmDtPlane* p, int W, int H) {
+    p->W = W; p->H = H;
+    p->gs = bm_pad8(W); p->ts = bm_pad4(W);
+    p->nb = bm_div_up(H, BM_BLK_ROWS);
+    return (size_t)p->gs * H <= p->g_cap && (size_t)p->nb * p->ts <= p->tsz;
+}
+
+cudaError_t bm_launch_rowscan_bgrx(const uchar4* img, int img_stride, int img_col0, int img_row0, const BmDtPlane& p, int row0, int nrows,
+                                   const int* flags, int need_flag, cudaStream_t s) {
+    if (nrows <= 0) return cudaSuccess;
+    if (p.W > BM_ROWSCAN_CHUNK * BM_ROWSCAN_MAX_CHUNKS) return cudaErrorInvalidValue;
+    BM_COUNT_LAUNCHES(1), k_rowscan_bgrx<<<nrows, 256, 0, s>>>(img, img_stride, img_col0, img_row0, p.g, p.gs, p.W, row0, flags, need_flag);
+    return cudaGetLastError();
+}
+
+cudaError_t bm_launch_rowscan_u8(const uint8_t* mask, int stride, const BmDtPlane& p, cudaStream_t s) {
+    if (p.W > BM_ROWSCAN_CHUNK * BM_ROWSCAN_MAX_CHUNKS) return cudaErrorInvalidValue;
+    BM_COUNT_LAUNCHES(1), k_rowscan_mask<<<p.H, 256, 0, s>>>(mask, stride, p.g, p.gs, p.W);
+    return cudaGetLastError();
+}
+
+static inline int dt_tiles(int width) { return bm_div_up(width, BM_DT_TILE_VALID); }
+
+cudaError_t bm_launch_dt_local(const BmDtPlane& p, int kb0, int kb1, const int* flags, int need_flag, cudaStream_t s) {
+    if (kb1 <= kb0) return cudaSuccess;
+    BM_COUNT_LAUNCHES(1), k_dt_local<<<dim3(bm_div_up(dt_tiles(p.W), 2), kb1 - kb0), 128, 0, s>>>(p, kb0, flags, need_flag);
+    return cudaGetLastError();
+}
+
+cudaError_t bm_launch_dt_carries(const BmDtPair& pp, int nplanes, const int xa[2], const int xb[2], const int* flags, int need_flag,
+                                 cudaStream_t s) {
+    DtRange rg;
+    int max_lines = 0, max_tiles = 0, max_nb = 0, max_cols = 0;
+    for (int i = 0; i < 2; ++i) {
+        const int j = i < nplanes ? i : 0;
+        rg.xa[i] = xa[j]; rg.xb[i] = xb[j];
+        if (i >= nplanes) continue;
+        const BmDtPlane& p = pp.p[i];
+        max_lines = max_lines > p.W + 16 * (p.nb - 1) ? max_lines : p.W + 16 * (p.nb - 1);
+        max_tiles = max_tiles > dt_tiles(xb[i] - xa[i]) ? max_tiles : dt_tiles(xb[i] - xa[i]);
+        max_nb = max_nb > p.nb ? max_nb : p.nb;
+        max_cols = max_cols > xb[i] - xa[i] ? max_cols : xb[i] - xa[i];
+    }
+    if (max_nb == 0 || max_cols <= 0) return cudaSuccess;
+    BM_COUNT_LAUNCHES(1), k_dt_diag_chain<<<dim3(bm_div_up(max_lines, 128), 4, nplanes), 128, 0, s>>>(pp, flags, need_flag);
+    BM_COUNT_LAUNCHES(1), k_dt_vert_local<<<dim3(bm_div_up(max_tiles, 2), max_nb, nplanes), 128, 0, s>>>(pp, rg, flags, need_flag);
+    BM_COUNT_LAUNCHES(1), k_dt_vert_chain<<<dim3(bm_div_up(max_cols, 128), 2, nplanes), 128, 0, s>>>(pp, rg, flags, need_flag);
+    return cudaGetLastError();
+}
+
+cudaError_t bm_launch_dt_weights(const BmDtPair& pp, const BmFramePlan& plan, float* wn, float* wo, const int* flags, cudaStream_t s) {
+    const int nyb = (plan.reg.y1 - 1) / BM_BLK_ROWS - plan.reg.y0 / BM_BLK_ROWS + 1;
+    BM_COUNT_LAUNCHES(1), k_dt_weights<<<dim3(dt_tiles(plan.reg.x1 - plan.rx0), nyb), 128, 0, s>>>(pp, plan, wn, wo, flags);
+    return cudaGetLastError();
+}
+
+cudaError_t bm_launch_dt_map(const BmDtPlane& p, float* d_out, cudaStream_t s) {
+    BmDtPair pp; pp.p[0] = p; pp.p[1] = p;
+    cudaError_t e = bm_launch_dt_local(p, 0, p.nb, nullptr, 0, s);
+    if (e != cudaSuccess) return e;
+    const int xa[2] = {0, 0}, xb[2] = {p.W, p.W};
+    e = bm_launch_dt_carries(pp, 1, xa, xb, nullptr, 0, s);
+    if (e != cudaSuccess) return e;
+    BM_COUNT_LAUNCHES(1), k_dt_map<<<dim3(dt_tiles(p.W), p.nb), 64, 0, s>>>(p, d_out);
+    return cudaGetLastError();
+}

@@ -1,21 +1,17 @@
 // Launchers of the warp / distance-transform / blur / blend chain (warp_blend.cu).
 #pragma once
 #include "common.cuh"
+#include "dt.cuh"
 
 // Scratch + persistent buffers of one canvas.  All device memory.
 struct BmBlendBufs {
-    // persistent, canvas-sized
     uchar4* canvas;        // BGR + mask byte (255 iff any channel > 0)       [canvas_h * canvas_w]
-    uint16_t* g_old;       // horizontal distance to the nearest zero pixel in the row, BM_G_INF if none
-    uint16_t* gblk_old;    // min of g_old over blocks of BM_BLK_ROWS rows    [ceil(canvas_h/16) * canvas_w]
+    BmDtPair dt;           // sweep tables: [0] canvas plane (mask_old, persistent), [1] window plane (mask_new, per frame)
     // per-frame scratch, sized for the largest window
-    uchar4* wbuf;          // warped frame over W, .w = mask_new               [win_h * win_w]
-    uint16_t* g_new;       // same as g_old for mask_new, window-local          [win_h * win_w]
-    uint16_t* gblk_new;    //                                                   [ceil(win_h/16) * win_w]
-    float2* rbuf;          // (dn/s, do/s) over R                               [reg_h * reg_w]
-    float2* hbuf;          // row-filtered weights, W columns x R rows          [reg_h * win_w]
+    uchar4* wbuf;          // warped frame over W, .w = mask_new               [win_h][plan.ws]
+    float* wn;             // dn/s over R                                       [reg_h][plan.rws]
+    float* wo;             // do/s over R
     int* flags;            // [0] any_overlap
-    BmFramePlan* plan;     // device copy of the frame plan
     size_t scratch_px;     // capacity of the scratch buffers in pixels (reg_h*reg_w <= scratch_px)
     int canvas_w, canvas_h;
 };
@@ -25,9 +21,9 @@ void bm_make_plan(const double H[9], int src_w, int src_h, int canvas_w, int can
 void bm_invert3x3(const double H[9], double M[9]);
 
 cudaError_t bm_launch_full_rowscan(const BmBlendBufs& b, cudaStream_t s);          // rebuild g_old for all rows
-cudaError_t bm_launch_warp_blend(const BmBlendBufs& b, const uchar4* d_src_bgrx, const BmFramePlan& plan,
+cudaError_t bm_launch_warp_blend(BmBlendBufs& b, const uchar4* d_src_bgrx, const BmFramePlan& plan,
                                  cudaStream_t s);                                    // whole per-frame chain
-cudaError_t bm_launch_blend_from_wbuf(const BmBlendBufs& b, const BmFramePlan& plan, cudaStream_t s);
+cudaError_t bm_launch_blend_from_wbuf(BmBlendBufs& b, const BmFramePlan& plan, cudaStream_t s);
 cudaError_t bm_launch_warp_full_bgr(const uint8_t* d_src_bgr, int sh, int sw, const BmFramePlan& plan,
                                     uint8_t* d_dst_bgr, cudaStream_t s);
 cudaError_t bm_launch_pack_canvas(const uint8_t* d_bgr, uchar4* d_canvas, int n_px, cudaStream_t s);
@@ -36,6 +32,4 @@ cudaError_t bm_launch_extract_wbuf(const uint8_t* d_warped_bgr, const BmFramePla
                                    cudaStream_t s);
 cudaError_t bm_launch_paste(uchar4* canvas, int canvas_w, const uchar4* src, int sw, int sh, int ox, int oy,
                             cudaStream_t s);
-cudaError_t bm_launch_dt_mask(const uint8_t* d_mask, int h, int w, float* d_out, uint16_t* g, uint16_t* gblk,
-                              cudaStream_t s);
 cudaError_t bm_launch_blur31(const float* d_in, int h, int w, float* d_tmp, float* d_out, cudaStream_t s);

@@ -71,10 +71,19 @@ def _masks(rng):
     m2 = np.full((700, 900), 255, np.uint8); m2[3, 5] = 0; m2[650, 880] = 0
     m3 = np.zeros((128, 160), np.uint8); m3[30:100, 40:130] = 255
     m4 = np.full((90, 2304), 255, np.uint8); m4[:, 0] = 0
-    return [m1, m2, m3, m4]
+    # odd sizes (no multiple of 4 / 8 / 16), a convex quad like a warped frame, rows longer than one 2048-pixel scan chunk,
+    # distances of many 16-row blocks in every direction, and a mask without any zero pixel
+    m5 = np.zeros((333, 517), np.uint8)
+    cv2.fillConvexPoly(m5, np.array([[40, 20], [490, 55], [470, 310], [15, 280]], np.int32), 255)
+    m5[150, 260] = 0
+    m6 = np.full((70, 4500), 255, np.uint8); m6[33, 2047] = 0; m6[5, 4499] = 0; m6[60, 2048] = 0
+    m7 = np.full((1301, 1203), 255, np.uint8); m7[0, 0] = 0; m7[1300, 1202] = 0; m7[640, 17] = 0
+    m8 = np.full((100, 130), 255, np.uint8)
+    m9 = (rng.random((257, 391)) > 0.0005).astype(np.uint8) * 255
+    return [m1, m2, m3, m4, m5, m6, m7, m8, m9]
 
 
-@pytest.mark.parametrize("i", range(4))
+@pytest.mark.parametrize("i", range(9))
 def test_distance_transform_bit_exact(ops, rng, i):
     m = _masks(rng)[i]
     ref = cv2.distanceTransform(m, cv2.DIST_L2, 3)

@@ -1,5 +1,5 @@
 """warp+blend chain only (no features): drives VideMosaic.warp with the sweep's true homographies. For ncu captures."""
-import sys; sys.path.insert(0,'.')
+import sys, pathlib; sys.path.insert(0, str(pathlib.Path(__file__).resolve().parent.parent))
 import numpy as np, time
 import b200mosaic
 from b200mosaic.synth import DroneSweep
