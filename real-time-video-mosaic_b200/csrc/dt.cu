@@ -25,6 +25,7 @@
 #define A_ ((unsigned)BM_CHAMFER_A)
 #define B_ ((unsigned)BM_CHAMFER_B)
 typedef unsigned int u32;
+struct DtRange { int xa[2], xb[2]; };
 #define DT_CHAIN_BATCH 32
 #define FULL 0xffffffffu
 
@@ -76,17 +77,21 @@ __global__ void __launch_bounds__(256) k_rowscan_mask(const uint8_t* __restrict_
 // ------------------------------------------------------------------------------------------------------------------
 struct DtRows { uint2 g[BM_BLK_ROWS]; unsigned colmask; };
 
-// the 16 rows of block k for the lane's 4 columns [cx, cx+4) (cx is a multiple of 4, may lie outside the plane)
-__device__ __forceinline__ void dt_load_rows(const BmDtPlane& p, int k, int cx, DtRows& R) {
+// the 16 rows of block k for the lane's 4 columns [cx, cx+4) (cx is a multiple of 4, may lie outside the plane), in
+// PROCESSING order: R.g[i] is row i of the block for a downward sweep, row 15-i for an upward one -- one code path
+// serves both directions (and both planes), which keeps the unrolled sweeps small in the instruction cache
+__device__ __forceinline__ void dt_load_rows(const BmDtPlane& p, int k, int cx, bool up, DtRows& R) {
     R.colmask = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) if (cx + i >= 0 && cx + i < p.W) R.colmask |= 1u << i;
     const bool ld = cx >= 0 && cx < p.W;
-    const uint16_t* base = p.g + (size_t)(k * BM_BLK_ROWS) * p.gs + cx;
+    const int r0 = k * BM_BLK_ROWS + (up ? BM_BLK_ROWS - 1 : 0), dr = up ? -1 : 1;
+    const uint16_t* base = p.g + (size_t)r0 * p.gs + cx;
+    const ptrdiff_t step = (ptrdiff_t)dr * p.gs;
 #pragma unroll
-    for (int r = 0; r < BM_BLK_ROWS; ++r) {
-        R.g[r] = make_uint2(0xffffffffu, 0xffffffffu);
-        if (ld && k * BM_BLK_ROWS + r < p.H) R.g[r] = __ldg(reinterpret_cast<const uint2*>(base + (size_t)r * p.gs));
+    for (int i = 0; i < BM_BLK_ROWS; ++i) {
+        R.g[i] = make_uint2(0xffffffffu, 0xffffffffu);
+        if (ld && r0 + dr * i < p.H) R.g[i] = __ldg(reinterpret_cast<const uint2*>(base + i * step));
     }
 }
 
@@ -130,20 +135,19 @@ __device__ __forceinline__ void dt_store4(u32* __restrict__ tab, const BmDtPlane
 // lanes whose 4 columns are exact after 16 row steps (the outer 16 columns of the 128 miss contributions)
 __device__ __forceinline__ bool dt_lane_valid(int lane) { return lane >= 4 && lane < 28; }
 
-// one sweep direction over the 16 rows of a block (UP: rows 15..0).  row(r, V) is called after each row step.
-template <bool UP, bool WITH_V, class RowFn>
+// one sweep over the 16 rows of a block in processing order.  row(i, V) is called after row step i.
+template <bool WITH_V, class RowFn>
 __device__ __forceinline__ void dt_sweep(const DtRows& R, u32 (&E1)[4], u32 (&E2)[4], u32 (&V)[4], int lane, RowFn row) {
 #pragma unroll
     for (int i = 0; i < BM_BLK_ROWS; ++i) {
-        const int r = UP ? BM_BLK_ROWS - 1 - i : i;
         u32 s[4];
-        dt_seeds(R, r, s);
+        dt_seeds(R, i, s);
         dt_step(E1, E2, s, lane);
         if (WITH_V) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) V[c] = min(min(E1[c], E2[c]), V[c] + A_);
         }
-        row(r, V);
+        row(i, V);
     }
 }
 struct DtNoRow { __device__ __forceinline__ void operator()(int, const u32 (&)[4]) const {} };
@@ -159,11 +163,10 @@ __global__ void __launch_bounds__(128) k_dt_local(BmDtPlane p, int kb0, const in
     if (tile * BM_DT_TILE_VALID >= p.W) return;
     const int cx = tile * BM_DT_TILE_VALID - 16 + 4 * lane;
     DtRows R;
-    dt_load_rows(p, k, cx, R);
+    dt_load_rows(p, k, cx, up, R);
     u32 E1[4], E2[4], V[4];
     dt_fill(E1, BM_DT_INF); dt_fill(E2, BM_DT_INF); dt_fill(V, BM_DT_INF);
-    if (up) dt_sweep<true, false>(R, E1, E2, V, lane, DtNoRow());
-    else dt_sweep<false, false>(R, E1, E2, V, lane, DtNoRow());
+    dt_sweep<false>(R, E1, E2, V, lane, DtNoRow());
     if (dt_lane_valid(lane) && cx < p.W) {
         dt_store4(p.LE + (up ? 2 : 0) * p.tsz, p, k, cx, E1);
         dt_store4(p.LE + (up ? 3 : 1) * p.tsz, p, k, cx, E2);
@@ -204,11 +207,66 @@ __global__ void __launch_bounds__(128) k_dt_diag_chain(BmDtPair pp, const int* _
     }
 }
 
+// Parallel form of the same chains for nb <= 256 blocks: c_j = min_i<=j (L_i + (j - i) * K) is a prefix minimum, so a
+// line is cut into segments of 8 blocks handled by one thread each: local chain, segment ends exchanged through shared
+// memory, carry of all earlier segments applied.  CTA = 16 lines x nseg segments (lanes walk lines: 64-byte rows).
+// A line's in-plane elements are contiguous in j, so a finite segment end always reaches the following elements.
+#define DT_SEG 8
+template <class Addr>
+__device__ __forceinline__ void dt_chain_seg(const u32* __restrict__ L, u32* __restrict__ C, int nb, u32 K, Addr addr) {
+    __shared__ u32 E[32][17];
+    const int ll = threadIdx.x & 15, sg = threadIdx.x >> 4;
+    const int j0 = sg * DT_SEG;
+    int idx[DT_SEG];
+    u32 loc[DT_SEG];
+#pragma unroll
+    for (int u = 0; u < DT_SEG; ++u) {
+        idx[u] = j0 + u < nb ? addr(j0 + u) : -1;
+        loc[u] = idx[u] >= 0 ? __ldg(L + idx[u]) : BM_DT_INF;
+    }
+    u32 c = BM_DT_INF;
+#pragma unroll
+    for (int u = 0; u < DT_SEG; ++u) { c = idx[u] >= 0 ? min(loc[u], dt_add_sat(c, K)) : BM_DT_INF; loc[u] = c; }
+    E[sg][ll] = c;
+    __syncthreads();
+    u32 cin = BM_DT_INF;                                   // carry at the last element of segment sg-1
+    for (int s2 = 0; s2 < sg; ++s2) cin = min(E[s2][ll], dt_add_sat(cin, DT_SEG * K));      // Horner form of the prefix minimum
+#pragma unroll
+    for (int u = 0; u < DT_SEG; ++u)
+        if (idx[u] >= 0) C[idx[u]] = min(loc[u], dt_add_sat(cin, (u32)(u + 1) * K));
+}
+
+__global__ void __launch_bounds__(512) k_dt_diag_chain16(BmDtPair pp, const int* __restrict__ flags, int need_flag) {
+    if (need_flag && flags[0] == 0) return;
+    const BmDtPlane& p = pp.p[blockIdx.z];
+    const int type = blockIdx.y;
+    const int nlines = p.W + 16 * (p.nb - 1);
+    if (blockIdx.x * 16 >= nlines) return;
+    const int t = blockIdx.x * 16 + (threadIdx.x & 15);
+    const bool right = (type & 1) == 0, down = type < 2;
+    const int x0 = right ? t - 16 * (p.nb - 1) : t, dx = right ? 16 : -16;
+    const int nb = p.nb, W = p.W, ts = p.ts;
+    dt_chain_seg(p.LE + (size_t)type * p.tsz, p.CE + (size_t)type * p.tsz, nb, 16u * B_, [=](int j) -> int {
+        const int x = x0 + dx * j, k = down ? j : nb - 1 - j;
+        return (t < nlines && x >= 0 && x < W) ? k * ts + x : -1;
+    });
+}
+
+__global__ void __launch_bounds__(512) k_dt_vert_chain16(BmDtPair pp, DtRange rg, const int* __restrict__ flags, int need_flag) {
+    if (need_flag && flags[0] == 0) return;
+    const int pl = blockIdx.z;
+    const BmDtPlane& p = pp.p[pl];
+    if (rg.xa[pl] + blockIdx.x * 16 >= rg.xb[pl]) return;
+    const int x = rg.xa[pl] + blockIdx.x * 16 + (threadIdx.x & 15);
+    const bool ok = x < rg.xb[pl] && x < p.W, down = blockIdx.y == 0;
+    const int nb = p.nb, ts = p.ts;
+    u32* C = p.CV + (size_t)blockIdx.y * p.tsz;
+    dt_chain_seg(C, C, nb, 16u * A_, [=](int j) -> int { return ok ? (down ? j : nb - 1 - j) * ts + x : -1; });
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // phase 3: diagonal sweeps with carries -> block-local vertical sweep
 // ------------------------------------------------------------------------------------------------------------------
-struct DtRange { int xa[2], xb[2]; };
-
 __global__ void __launch_bounds__(128) k_dt_vert_local(BmDtPair pp, DtRange rg, const int* __restrict__ flags, int need_flag) {
     if (need_flag && flags[0] == 0) return;
     const int pl = blockIdx.z;
@@ -220,13 +278,12 @@ __global__ void __launch_bounds__(128) k_dt_vert_local(BmDtPair pp, DtRange rg, 
     if (k >= p.nb || xa + tile * BM_DT_TILE_VALID >= xb) return;
     const int cx = xa + tile * BM_DT_TILE_VALID - 16 + 4 * lane;
     DtRows R;
-    dt_load_rows(p, k, cx, R);
+    dt_load_rows(p, k, cx, up, R);
     u32 E1[4], E2[4], V[4];
     dt_carry4(p.CE + (up ? 2 : 0) * p.tsz, p, up ? k + 1 : k - 1, cx, E1);
     dt_carry4(p.CE + (up ? 3 : 1) * p.tsz, p, up ? k + 1 : k - 1, cx, E2);
     dt_fill(V, BM_DT_INF);
-    if (up) dt_sweep<true, true>(R, E1, E2, V, lane, DtNoRow());
-    else dt_sweep<false, true>(R, E1, E2, V, lane, DtNoRow());
+    dt_sweep<true>(R, E1, E2, V, lane, DtNoRow());
     if (dt_lane_valid(lane) && cx < xb && cx < p.W) dt_store4(p.CV + (up ? 1 : 0) * p.tsz, p, k, cx, V);
 }
 
@@ -264,14 +321,16 @@ __global__ void __launch_bounds__(128) k_dt_vert_chain(BmDtPair pp, DtRange rg, 
 #define DT_TW 128
 __device__ __forceinline__ void dt_sweep_to_smem(const BmDtPlane& p, int k, int cx, bool up, int lane, u32 (*T)[DT_TW]) {
     DtRows R;
-    dt_load_rows(p, k, cx, R);
+    dt_load_rows(p, k, cx, up, R);
     u32 E1[4], E2[4], V[4];
     dt_carry4(p.CE + (up ? 2 : 0) * p.tsz, p, up ? k + 1 : k - 1, cx, E1);
     dt_carry4(p.CE + (up ? 3 : 1) * p.tsz, p, up ? k + 1 : k - 1, cx, E2);
     dt_carry4(p.CV + (up ? 1 : 0) * p.tsz, p, up ? k + 1 : k - 1, cx, V);
-    auto put = [&](int r, const u32 (&v)[4]) { *reinterpret_cast<uint4*>(&T[r][4 * lane]) = make_uint4(v[0], v[1], v[2], v[3]); };
-    if (up) dt_sweep<true, true>(R, E1, E2, V, lane, put);
-    else dt_sweep<false, true>(R, E1, E2, V, lane, put);
+    auto put = [&](int i, const u32 (&v)[4]) {
+        const int r = up ? BM_BLK_ROWS - 1 - i : i;
+        *reinterpret_cast<uint4*>(&T[r][4 * lane]) = make_uint4(v[0], v[1], v[2], v[3]);
+    };
+    dt_sweep<true>(R, E1, E2, V, lane, put);
 }
 
 __global__ void __launch_bounds__(64) k_dt_map(BmDtPlane p, float* __restrict__ out) {
@@ -299,8 +358,8 @@ __global__ void __launch_bounds__(128) k_dt_weights(BmDtPair pp, BmFramePlan pla
     const int tx0 = plan.rx0 + tile * BM_DT_TILE_VALID - 16;      // canvas column of the tile's first (halo) column
     const int kn = k - plan.win.y0 / BM_BLK_ROWS;
     const bool has_new = kn >= 0 && kn < pp.p[1].nb && tx0 + DT_TW > plan.win.x0 && tx0 < plan.win.x1;
-    if (warp < 2) dt_sweep_to_smem(pp.p[0], k, tx0 + 4 * lane, warp == 1, lane, T[warp]);
-    else if (has_new) dt_sweep_to_smem(pp.p[1], kn, tx0 - plan.win.x0 + 4 * lane, warp == 3, lane, T[warp]);
+    if (warp < 2 || has_new)                                     // one code path: (plane, direction) are data
+        dt_sweep_to_smem(pp.p[warp >> 1], warp < 2 ? k : kn, tx0 - (warp < 2 ? 0 : plan.win.x0) + 4 * lane, warp & 1, lane, T[warp]);
     __syncthreads();
     const float scale = 1.0f / 65536.0f;
     for (int i = threadIdx.x; i < BM_BLK_ROWS * BM_DT_TILE_VALID; i += 128) {
@@ -386,9 +445,14 @@ cudaError_t bm_launch_dt_carries(const BmDtPair& pp, int nplanes, const int xa[2
         max_cols = max_cols > xb[i] - xa[i] ? max_cols : xb[i] - xa[i];
     }
     if (max_nb == 0 || max_cols <= 0) return cudaSuccess;
-    BM_COUNT_LAUNCHES(1), k_dt_diag_chain<<<dim3(bm_div_up(max_lines, 128), 4, nplanes), 128, 0, s>>>(pp, flags, need_flag);
+    // segment-parallel chains (table index fits 32 bits); longer lines fall back to one thread per line
+    const bool par = max_nb <= 256 && pp.p[0].tsz < ((size_t)1 << 31) && pp.p[1].tsz < ((size_t)1 << 31);
+    const int chain_threads = 32 * bm_div_up(bm_div_up(max_nb, DT_SEG), 2);     // 16 lines x ceil(nb / 8) segments
+    if (par) BM_COUNT_LAUNCHES(1), k_dt_diag_chain16<<<dim3(bm_div_up(max_lines, 16), 4, nplanes), chain_threads, 0, s>>>(pp, flags, need_flag);
+    else BM_COUNT_LAUNCHES(1), k_dt_diag_chain<<<dim3(bm_div_up(max_lines, 128), 4, nplanes), 128, 0, s>>>(pp, flags, need_flag);
     BM_COUNT_LAUNCHES(1), k_dt_vert_local<<<dim3(bm_div_up(max_tiles, 2), max_nb, nplanes), 128, 0, s>>>(pp, rg, flags, need_flag);
-    BM_COUNT_LAUNCHES(1), k_dt_vert_chain<<<dim3(bm_div_up(max_cols, 128), 2, nplanes), 128, 0, s>>>(pp, rg, flags, need_flag);
+    if (par) BM_COUNT_LAUNCHES(1), k_dt_vert_chain16<<<dim3(bm_div_up(max_cols, 16), 2, nplanes), chain_threads, 0, s>>>(pp, rg, flags, need_flag);
+    else BM_COUNT_LAUNCHES(1), k_dt_vert_chain<<<dim3(bm_div_up(max_cols, 128), 2, nplanes), 128, 0, s>>>(pp, rg, flags, need_flag);
     return cudaGetLastError();
 }
 

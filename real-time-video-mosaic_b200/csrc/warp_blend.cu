@@ -163,6 +163,33 @@ __device__ __forceinline__ uchar4 warp_sample(const Src& s, int X, int Y) {
     return o;
 }
 
+// border / outside pixels: per-tap path, kept out of line (rare; keeps the hot loop small)
+__device__ __noinline__ uchar4 warp_sample_border(const uchar4* __restrict__ src, int w, int h, int X, int Y) {
+    const SrcBGRX s{src, w, h};
+    return warp_sample(s, X, Y);
+}
+
+// BGRX fast path: the 4 taps as 32-bit words, B and R interpolated together in 16-bit lanes.  Integer arithmetic is exact and
+// distributive: sum_ij p_ij*wx_i*wy_j = wy0*(p00*wx0 + p01*wx1) + wy1*(p10*wx0 + p11*wx1); the horizontal sums are <= 255*32.
+__device__ __forceinline__ uchar4 warp_sample_bgrx(const uchar4* __restrict__ src, int w, int h, int X, int Y) {
+    int sx = X >> 5, sy = Y >> 5;
+    sx = max(-32768, min(32767, sx));
+    sy = max(-32768, min(32767, sy));
+    if (!((unsigned)sx < (unsigned)(w - 1) && (unsigned)sy < (unsigned)(h - 1))) return warp_sample_border(src, w, h, X, Y);
+    const unsigned ax = X & 31, ay = Y & 31, bxw = 32u - ax, byw = 32u - ay;
+    const unsigned* p = reinterpret_cast<const unsigned*>(src) + (size_t)sy * w + sx;
+    const unsigned a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + w), d = __ldg(p + w + 1);
+    const unsigned h0br = (a & 0x00ff00ffu) * bxw + (b & 0x00ff00ffu) * ax, h1br = (c & 0x00ff00ffu) * bxw + (d & 0x00ff00ffu) * ax;
+    const unsigned h0g = ((a >> 8) & 0xffu) * bxw + ((b >> 8) & 0xffu) * ax, h1g = ((c >> 8) & 0xffu) * bxw + ((d >> 8) & 0xffu) * ax;
+    const unsigned B = ((h0br & 0xffffu) * byw + (h1br & 0xffffu) * ay + 512u) >> 10;
+    const unsigned R = ((h0br >> 16) * byw + (h1br >> 16) * ay + 512u) >> 10;
+    const unsigned G = (h0g * byw + h1g * ay + 512u) >> 10;
+    uchar4 o;
+    o.x = (unsigned char)B; o.y = (unsigned char)G; o.z = (unsigned char)R;
+    o.w = (B | G | R) ? 255 : 0;
+    return o;
+}
+
 // K1: one CTA per window row: warp the frame into the window scratch (8 consecutive pixels per thread: the homography
 // terms of OpenCV's 64-column evaluation block are shared), detect np.any(overlap), and produce the nearest-zero row scan
 // of mask_new from the mask bits still in registers.
@@ -173,10 +200,8 @@ __global__ void __launch_bounds__(256) k_warp_rows(const uchar4* __restrict__ sr
     const int nch = (ww + BM_ROWSCAN_CHUNK - 1) / BM_ROWSCAN_CHUNK;
     const uchar4* crow = canvas + (size_t)y * plan.canvas_w + plan.win.x0;
     uchar4* wrow = wbuf + (size_t)ly * plan.ws;
-    const SrcBGRX s{src, plan.src_w, plan.src_h};
     const double* M = plan.M;
     const double dy = (double)y;
-    const bool shared_block = (plan.block_w & 7) == 0;
     BmZeroBits zb; zb.clear();
     bool ov = false;
     for (int c = 0; c < nch; ++c) {
@@ -184,7 +209,7 @@ __global__ void __launch_bounds__(256) k_warp_rows(const uchar4* __restrict__ sr
         if (base >= ww) continue;
         const int x0 = plan.win.x0 + base;
         uchar4 o[8];
-        if (shared_block) {
+        {
             const int bx = (x0 / plan.block_w) * plan.block_w;
             const double dbx = (double)bx;
             const double X0 = __dadd_rn(__dadd_rn(__dmul_rn(M[0], dbx), __dmul_rn(M[1], dy)), M[2]);
@@ -195,18 +220,10 @@ __global__ void __launch_bounds__(256) k_warp_rows(const uchar4* __restrict__ sr
                 const double x1 = (double)(x0 + i - bx);
                 double W = __dadd_rn(W0, __dmul_rn(M[6], x1));
                 W = (W != 0.0) ? __ddiv_rn(32.0, W) : 0.0;
-                double fX = __dmul_rn(__dadd_rn(X0, __dmul_rn(M[0], x1)), W);
-                double fY = __dmul_rn(__dadd_rn(Y0, __dmul_rn(M[3], x1)), W);
-                fX = fmax(-2147483648.0, fmin(2147483647.0, fX));
-                fY = fmax(-2147483648.0, fmin(2147483647.0, fY));
-                o[i] = warp_sample(s, __double2int_rn(fX), __double2int_rn(fY));
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                int X, Y;
-                warp_coords(M, plan.block_w, x0 + i, y, X, Y);
-                o[i] = warp_sample(s, X, Y);
+                // cv2 clamps to [INT_MIN, INT_MAX] and then rounds (cvRound); cvt.rni.s32.f64 saturates to the same values
+                const double fX = __dmul_rn(__dadd_rn(X0, __dmul_rn(M[0], x1)), W);
+                const double fY = __dmul_rn(__dadd_rn(Y0, __dmul_rn(M[3], x1)), W);
+                o[i] = warp_sample_bgrx(src, plan.src_w, plan.src_h, __double2int_rn(fX), __double2int_rn(fY));
             }
         }
         unsigned b = 0;
@@ -256,11 +273,23 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 #define FB_TH 32
 #define FB_SW (FB_TW + 2 * BM_BLUR_R)      // 94
 #define FB_SH (FB_TH + 2 * BM_BLUR_R)      // 62
+struct FbSmem {
+    float tile[2][FB_SH][FB_SW + 1];     // both weight planes with halo, filled by cp.async while the CTA starts computing
+    float hrow[FB_SH][FB_TW + 1];        // row-filtered plane
+};
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src, bool valid) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 4 : 0;        // src-size 0: the 4 bytes are zero-filled, nothing is read
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sa), "l"(gmem_src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __global__ void __launch_bounds__(256, 3) k_blur_blend(BmFramePlan plan, const float* __restrict__ wnp, const float* __restrict__ wop,
                                                        const uchar4* __restrict__ wbuf, uchar4* __restrict__ canvas,
                                                        const int* __restrict__ flags) {
-    __shared__ float tile[FB_SH][FB_SW + 1];
-    __shared__ float hrow[FB_SH][FB_TW + 1];
+    extern __shared__ __align__(16) unsigned char fb_smem_raw[];
+    FbSmem& sm = *reinterpret_cast<FbSmem*>(fb_smem_raw);
     const int tid = threadIdx.x;
     const int bx = plan.win.x0 + blockIdx.x * FB_TW, by = plan.win.y0 + blockIdx.y * FB_TH;     // canvas coords of the tile origin
     const int c = tid & (FB_TW - 1), r0 = (tid >> 6) * 8;       // column pass / blend: 64 columns x 4 groups of 8 rows
@@ -297,24 +326,30 @@ __global__ void __launch_bounds__(256, 3) k_blur_blend(BmFramePlan plan, const f
         for (int j = 0; j < 3; ++j) {
             const int tx = lane + 32 * j;
             const int gx = reflect101(bx + tx - BM_BLUR_R, plan.canvas_w);
-            gxok[j] = tx < FB_SW && gx >= plan.reg.x0 && gx < plan.reg.x1;     // beyond R only in partial edge tiles: never used
-            gxo[j] = gx - plan.rx0;
+            gxok[j] = gx >= plan.reg.x0 && gx < plan.reg.x1;     // beyond R only in partial edge tiles: never used
+            gxo[j] = gxok[j] ? gx - plan.rx0 : 0;
         }
 #pragma unroll
         for (int pl = 0; pl < 2; ++pl) {
             const float* __restrict__ src = pl ? wop : wnp;
-            if (pl) __syncthreads();                       // previous plane's column pass is done with hrow
             for (int ty = warp; ty < FB_SH; ty += 8) {
                 const int gy = reflect101(by + ty - BM_BLUR_R, plan.canvas_h);
                 const bool yok = gy >= plan.reg.y0 && gy < plan.reg.y1;
-                const float* __restrict__ rowp = src + (size_t)(gy - plan.reg.y0) * plan.rws;
+                const float* __restrict__ rowp = src + (yok ? (size_t)(gy - plan.reg.y0) * plan.rws : 0);
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
                     const int tx = lane + 32 * j;
-                    if (tx < FB_SW) tile[ty][tx] = (yok && gxok[j]) ? __ldg(rowp + gxo[j]) : 0.f;
+                    if (tx < FB_SW) cp_async4(&sm.tile[pl][ty][tx], rowp + gxo[j], yok && gxok[j]);
                 }
             }
-            __syncthreads();
+            cp_async_commit();
+        }
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {
+            if (pl == 0) cp_async_wait<1>(); else cp_async_wait<0>();
+            __syncthreads();                               // tile[pl] complete for all threads; previous column pass done with hrow
+            float (*tile)[FB_SW + 1] = sm.tile[pl];
+            float (*hrow)[FB_TW + 1] = sm.hrow;
             if (tid < FB_SH * (FB_TW / 16)) {              // 62 rows x 4 segments of 16 outputs; lanes walk rows
                 const int seg = tid / FB_SH, r = tid - seg * FB_SH, c0 = seg * 16;
                 float acc[16];
@@ -450,6 +485,8 @@ cudaError_t bm_launch_full_rowscan(const BmBlendBufs& b, cudaStream_t s) {
 
 // chain after wbuf, g_new (rows of the window plane) and flags[0] are filled.  b.dt.p[1] is shaped for the window.
 static cudaError_t blend_tail(const BmBlendBufs& b, const BmFramePlan& plan, cudaStream_t s) {
+    static cudaError_t attr = cudaFuncSetAttribute(k_blur_blend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FbSmem));
+    if (attr != cudaSuccess) return attr;
     const int ww = bm_win_w(plan.win), wh = bm_win_h(plan.win);
     const BmDtPlane& po = b.dt.p[0];
     const BmDtPlane& pn = b.dt.p[1];
@@ -459,7 +496,7 @@ static cudaError_t blend_tail(const BmBlendBufs& b, const BmFramePlan& plan, cud
     const int xa[2] = {plan.rx0, 0}, xb[2] = {plan.reg.x1, ww};
     if ((e = bm_launch_dt_carries(b.dt, 2, xa, xb, b.flags, 1, s)) != cudaSuccess) return e;
     if ((e = bm_launch_dt_weights(b.dt, plan, b.wn, b.wo, b.flags, s)) != cudaSuccess) return e;
-    BM_COUNT_LAUNCHES(1), k_blur_blend<<<dim3(bm_div_up(ww, FB_TW), bm_div_up(wh, FB_TH)), 256, 0, s>>>(plan, b.wn, b.wo, b.wbuf, b.canvas, b.flags);
+    BM_COUNT_LAUNCHES(1), k_blur_blend<<<dim3(bm_div_up(ww, FB_TW), bm_div_up(wh, FB_TH)), 256, sizeof(FbSmem), s>>>(plan, b.wn, b.wo, b.wbuf, b.canvas, b.flags);
     // refresh the persistent tables of the canvas plane for the rows the frame touched
     if ((e = bm_launch_rowscan_bgrx(b.canvas, b.canvas_w, 0, plan.win.y0, po, plan.win.y0, wh, b.flags, 0, s)) != cudaSuccess) return e;
     return bm_launch_dt_local(po, plan.win.y0 / BM_BLK_ROWS, bm_div_up(plan.win.y1, BM_BLK_ROWS), b.flags, 0, s);
@@ -476,7 +513,8 @@ cudaError_t bm_launch_blend_from_wbuf(BmBlendBufs& b, const BmFramePlan& plan, c
 cudaError_t bm_launch_warp_blend(BmBlendBufs& b, const uchar4* d_src, const BmFramePlan& plan, cudaStream_t s) {
     if (!plan.valid) return cudaSuccess;
     const int ww = bm_win_w(plan.win), wh = bm_win_h(plan.win);
-    if (ww > BM_ROWSCAN_CHUNK * BM_ROWSCAN_MAX_CHUNKS || !bm_dt_shape_plane(&b.dt.p[1], ww, wh)) return cudaErrorInvalidValue;
+    // (block_w is 64 for every canvas >= 64 px wide; the row kernel shares the block terms between 8 consecutive pixels)
+    if ((plan.block_w & 7) || ww > BM_ROWSCAN_CHUNK * BM_ROWSCAN_MAX_CHUNKS || !bm_dt_shape_plane(&b.dt.p[1], ww, wh)) return cudaErrorInvalidValue;
     cudaError_t e = cudaMemsetAsync(b.flags, 0, 4 * sizeof(int), s);
     if (e != cudaSuccess) return e;
     BM_COUNT_LAUNCHES(1), k_warp_rows<<<wh, 256, 0, s>>>(d_src, plan, b.canvas, b.wbuf, b.dt.p[1].g, b.dt.p[1].gs, b.flags);
