@@ -26,6 +26,7 @@
 #define SIFT_BORDER 5
 #define SIFT_CAND_CAP (1 << 17)
 #define SIFT_KP_CAP (1 << 17)
+#define SIFT_RAW_CAP (1 << 21)
 
 struct SiftOct { int w, h; long long g[6]; long long d[5]; long long claim; };   // float offsets; claim: bit offset / 32
 struct SiftLayout { int noct; SiftOct o[SIFT_MAX_OCT]; };
@@ -43,7 +44,9 @@ struct BmSift {
     float* up;               // 2x upsampled gray (float)
     unsigned* claim;         // one bit per (octave, layer, pixel)
     size_t claim_words;
-    SiftCand* cand; int* ctr;            // ctr[0] = #cand, ctr[1] = #kp (pre-select), ctr[2] = overflow, ctr[3] = #selected
+    SiftCand* cand; int* ctr;            // ctr[0] = #cand, ctr[1] = #kp (pre-select), ctr[2] = overflow, ctr[3] = #selected, ctr[4] = #raw
+    unsigned* raw;           // raw extrema before refinement: o<<28 | (layer-1)<<26 | r<<13 | c
+    float* cresp; int* csel; // candidate responses, candidates that can survive retainBest (ctr[5] = threshold bits, ctr[7] = count, ctr[6] = #kp after pass A)
     float2* kpt; float* ksize; float* kangle; float* kresp; int* koct;     // pre-select keypoint list (SIFT_KP_CAP)
     int* sel;                // indices of the selected keypoints
     unsigned* hist;          // radix-select scratch
@@ -79,40 +82,80 @@ __device__ __forceinline__ int refl101(int i, int n) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// fused separable Gaussian (radius R) + DoG.  Tile 32x32 outputs, 256 threads.
+// fused separable Gaussian + DoG (+ the decimated copy that seeds the next octave).  One instantiation per pyramid level
+// (kernel taps are compile-time constant-bank operands).  CTA = 256 threads, tile 64 x TH outputs with TH = 64 - 2R
+// (rounded to 4) so that the row pass has <= 256 (row, 16-output segment) units:
+//   load : cp.async of the tile + halo (reflect-101 coordinates are always inside the image, so no zero fill)
+//   rows : one thread = 16 consecutive outputs from a (16 + 2R)-value register window, cv2 order (tap 0 product, FMAs
+//          left to right); lanes walk rows, shared-memory strides are odd -> conflict free
+//   cols : one thread = TH/4 consecutive outputs of one column from a register window, cv2's symmetric FMA form
 // ------------------------------------------------------------------------------------------------------------------
-template <int R>
+__device__ __forceinline__ void sift_cp_async4(float* smem_dst, const float* gmem_src) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+__host__ __device__ constexpr int sift_level_radius(int level) { return level <= 1 ? 5 : level == 2 ? 6 : level == 3 ? 8 : level == 4 ? 10 : 13; }
+__host__ __device__ constexpr int sift_tile_h(int level) { return ((64 - 2 * sift_level_radius(level)) / 4) * 4; }
+
+template <int LEVEL>
 __global__ void __launch_bounds__(256) k_sift_blur(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ dog,
-                                                   int w, int h, int kidx) {
-    constexpr int T = 32, S = T + 2 * R, K = 2 * R + 1;
-    __shared__ float tile[S][S + 1];
-    __shared__ float rowf[S][T + 1];
-    const int bx = blockIdx.x * T, by = blockIdx.y * T;
-    const int tid = threadIdx.y * 32 + threadIdx.x;
-    for (int i = tid; i < S * S; i += 256) {
-        const int ty = i / S, tx = i % S;
-        const int gx = refl101(bx + tx - R, w), gy = refl101(by + ty - R, h);
-        tile[ty][tx] = in[(size_t)gy * w + gx];
+                                                   float* __restrict__ dec, int w, int h) {
+    constexpr int R = sift_level_radius(LEVEL), K = 2 * R + 1, TW = 64, TH = sift_tile_h(LEVEL), SW = TW + 2 * R, SH = TH + 2 * R, NO = TH / 4;
+    __shared__ float tile[SH][SW + 1];
+    __shared__ float rowf[SH][TW + 1];
+    const int bx = blockIdx.x * TW, by = blockIdx.y * TH;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    {
+        int gx[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) gx[j] = refl101(bx + lane + 32 * j - R, w);
+        for (int ty = warp; ty < SH; ty += 8) {
+            const float* __restrict__ rowp = in + (size_t)refl101(by + ty - R, h) * w;
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                if (lane + 32 * j < SW) sift_cp_async4(&tile[ty][lane + 32 * j], rowp + gx[j]);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
-    const float* kk = c_sift_k[kidx];
-    for (int i = tid; i < S * T; i += 256) {          // row pass: first tap a product, then FMAs left to right
-        const int ty = i / T, tx = i % T;
-        float a = __fmul_rn(kk[0], tile[ty][tx]);
+    if (tid < SH * 4) {
+        const int seg = tid / SH, r = tid - seg * SH, c0 = seg * 16;
+        float acc[16];
 #pragma unroll
-        for (int t = 1; t < K; ++t) a = __fmaf_rn(kk[t], tile[ty][tx + t], a);
-        rowf[ty][tx] = a;
+        for (int t = 0; t < 16 + 2 * R; ++t) {
+            const float v = tile[r][c0 + t];
+#pragma unroll
+            for (int o = 0; o < 16; ++o) {
+                const int k = t - o;
+                if (k == 0) acc[o] = __fmul_rn(c_sift_k[LEVEL][0], v);
+                else if (k > 0 && k < K) acc[o] = __fmaf_rn(c_sift_k[LEVEL][k], v, acc[o]);
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < 16; ++o) rowf[r][c0 + o] = acc[o];
     }
     __syncthreads();
-    for (int i = tid; i < T * T; i += 256) {          // column pass: symmetric FMA form
-        const int ty = i / T, tx = i % T;
-        const int gx = bx + tx, gy = by + ty;
-        if (gx >= w || gy >= h) continue;
-        float a = __fmul_rn(kk[R], rowf[ty + R][tx]);
+    {
+        const int c = tid & 63, r0 = (tid >> 6) * NO;
+        const int gx = bx + c;
+        float hh[NO + 2 * R];
 #pragma unroll
-        for (int t = 1; t <= R; ++t) a = __fmaf_rn(kk[R + t], __fadd_rn(rowf[ty + R + t][tx], rowf[ty + R - t][tx]), a);
-        out[(size_t)gy * w + gx] = a;
-        if (dog) dog[(size_t)gy * w + gx] = __fsub_rn(a, tile[ty + R][tx + R]);
+        for (int t = 0; t < NO + 2 * R; ++t) hh[t] = rowf[r0 + t][c];
+        if (gx < w) {
+#pragma unroll
+            for (int o = 0; o < NO; ++o) {
+                const int gy = by + r0 + o;
+                if (gy >= h) break;
+                float a = __fmul_rn(c_sift_k[LEVEL][R], hh[o + R]);
+#pragma unroll
+                for (int t = 1; t <= R; ++t) a = __fmaf_rn(c_sift_k[LEVEL][R + t], __fadd_rn(hh[o + R + t], hh[o + R - t]), a);
+                out[(size_t)gy * w + gx] = a;
+                if (dog) dog[(size_t)gy * w + gx] = __fsub_rn(a, tile[r0 + o + R][c + R]);
+                // next octave base = this level decimated by 2 (INTER_NEAREST: dst(x,y) = src(2x,2y))
+                if (dec && !((gx | gy) & 1) && (gx >> 1) < (w >> 1) && (gy >> 1) < (h >> 1)) dec[(size_t)(gy >> 1) * (w >> 1) + (gx >> 1)] = a;
+            }
+        }
     }
 }
 
@@ -187,47 +230,75 @@ __device__ bool adjust_local_extrema(const float* __restrict__ pyr, const SiftOc
     return true;
 }
 
-// one thread per pixel of DoG layers 1..3 of octave `o` (blockIdx.z = layer-1)
-__global__ void __launch_bounds__(256) k_sift_extrema(SiftLayout lay, int o, const float* __restrict__ pyr, unsigned* __restrict__ claim,
-                                                      SiftCand* __restrict__ cand, int* __restrict__ ctr) {
+// 26-neighbour test of one DoG sample; prv / cur / nxt point at the sample in the three layers
+__device__ __forceinline__ bool sift_is_extremum(const float* __restrict__ prv, const float* __restrict__ cur, const float* __restrict__ nxt,
+                                                 int w, float v) {
+    if (v > 0) {
+        return v >= cur[-1] && v >= cur[1] && v >= cur[-w - 1] && v >= cur[-w] && v >= cur[-w + 1] && v >= cur[w - 1] && v >= cur[w] && v >= cur[w + 1] &&
+               v >= nxt[-1] && v >= nxt[1] && v >= nxt[-w - 1] && v >= nxt[-w] && v >= nxt[-w + 1] && v >= nxt[w - 1] && v >= nxt[w] && v >= nxt[w + 1] &&
+               v >= prv[-1] && v >= prv[1] && v >= prv[-w - 1] && v >= prv[-w] && v >= prv[-w + 1] && v >= prv[w - 1] && v >= prv[w] && v >= prv[w + 1];
+    }
+    return v <= cur[-1] && v <= cur[1] && v <= cur[-w - 1] && v <= cur[-w] && v <= cur[-w + 1] && v <= cur[w - 1] && v <= cur[w] && v <= cur[w + 1] &&
+           v <= nxt[-1] && v <= nxt[1] && v <= nxt[-w - 1] && v <= nxt[-w] && v <= nxt[-w + 1] && v <= nxt[w - 1] && v <= nxt[w] && v <= nxt[w + 1] &&
+           v <= prv[-1] && v <= prv[1] && v <= prv[-w - 1] && v <= prv[-w] && v <= prv[-w + 1] && v <= prv[w - 1] && v <= prv[w] && v <= prv[w + 1];
+}
+
+// Phase 1 -- one thread per pixel of octave `o`: the 5 DoG samples of the pixel are read once (coalesced); a sample of
+// layers 1..3 is a candidate only if it beats the threshold and the samples directly above / below it -- which rejects
+// almost everything before any neighbour is touched.  The conjunction is the same 26-neighbour test as cv2's, only its
+// order differs.  Raw extrema are compacted (ballot / popc) into a list; the divergent sub-pixel refinement runs densely
+// over that list in phase 2 instead of stalling 31 lanes of the detecting warp.
+__global__ void __launch_bounds__(256) k_sift_extrema(SiftLayout lay, int o, const float* __restrict__ pyr, unsigned* __restrict__ raw,
+                                                      int* __restrict__ ctr) {
     const SiftOct O = lay.o[o];
     const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y * blockDim.y + threadIdx.y;
-    int layer = blockIdx.z + 1;
     const int w = O.w, h = O.h;
+    const bool inside = c >= SIFT_BORDER && c < w - SIFT_BORDER && r >= SIFT_BORDER && r < h - SIFT_BORDER;
+    const size_t p = (size_t)r * w + c;
+    float d[5];
+#pragma unroll
+    for (int l = 0; l < 5; ++l) d[l] = inside ? __ldg(pyr + O.d[l] + p) : 0.f;
+#pragma unroll
+    for (int l0 = 1; l0 <= SIFT_LAYERS; ++l0) {
+        const float v = d[l0];
+        // threshold = cvFloor(0.5*0.04/3*255) = 1
+        const bool found = inside && fabsf(v) > 1.0f && (v > 0 ? (v >= d[l0 - 1] && v >= d[l0 + 1]) : (v <= d[l0 - 1] && v <= d[l0 + 1])) &&
+                           sift_is_extremum(pyr + O.d[l0 - 1] + p, pyr + O.d[l0] + p, pyr + O.d[l0 + 1] + p, w, v);
+        const unsigned bal = __ballot_sync(0xffffffffu, found);
+        if (bal) {
+            const int lane = threadIdx.x & 31, leader = __ffs(bal) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&ctr[4], __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (found) {
+                const int idx = base + __popc(bal & ((1u << lane) - 1u));
+                if (idx < SIFT_RAW_CAP) raw[idx] = ((unsigned)o << 28) | ((unsigned)(l0 - 1) << 26) | ((unsigned)r << 13) | (unsigned)c;
+                else ctr[2] = 1;
+            }
+        }
+    }
+}
+
+// Phase 2 -- adjustLocalExtrema: one thread per raw extremum
+__global__ void __launch_bounds__(128) k_sift_refine(SiftLayout lay, const float* __restrict__ pyr, const unsigned* __restrict__ raw,
+                                                     unsigned* __restrict__ claim, SiftCand* __restrict__ cand, float* __restrict__ cresp,
+                                                     int* __restrict__ ctr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int n = ctr[4]; if (n > SIFT_RAW_CAP) n = SIFT_RAW_CAP;
+    if (blockIdx.x * blockDim.x >= n) return;
     bool found = false;
     SiftCand cd;
-    if (c >= SIFT_BORDER && c < w - SIFT_BORDER && r >= SIFT_BORDER && r < h - SIFT_BORDER) {
-        const float* cur = pyr + O.d[layer];
-        const size_t p = (size_t)r * w + c;
-        const float v = cur[p];
-        if (fabsf(v) > 1.0f) {                 // threshold = cvFloor(0.5*0.04/3*255) = 1
-            const float* prv = pyr + O.d[layer - 1]; const float* nxt = pyr + O.d[layer + 1];
-            bool ext;
-            if (v > 0) {
-                ext = v >= cur[p - 1] && v >= cur[p + 1] && v >= cur[p - w - 1] && v >= cur[p - w] && v >= cur[p - w + 1] &&
-                      v >= cur[p + w - 1] && v >= cur[p + w] && v >= cur[p + w + 1];
-                if (ext) ext = v >= nxt[p] && v >= nxt[p - 1] && v >= nxt[p + 1] && v >= nxt[p - w - 1] && v >= nxt[p - w] && v >= nxt[p - w + 1] &&
-                               v >= nxt[p + w - 1] && v >= nxt[p + w] && v >= nxt[p + w + 1];
-                if (ext) ext = v >= prv[p] && v >= prv[p - 1] && v >= prv[p + 1] && v >= prv[p - w - 1] && v >= prv[p - w] && v >= prv[p - w + 1] &&
-                               v >= prv[p + w - 1] && v >= prv[p + w] && v >= prv[p + w + 1];
-            } else {
-                ext = v <= cur[p - 1] && v <= cur[p + 1] && v <= cur[p - w - 1] && v <= cur[p - w] && v <= cur[p - w + 1] &&
-                      v <= cur[p + w - 1] && v <= cur[p + w] && v <= cur[p + w + 1];
-                if (ext) ext = v <= nxt[p] && v <= nxt[p - 1] && v <= nxt[p + 1] && v <= nxt[p - w - 1] && v <= nxt[p - w] && v <= nxt[p - w + 1] &&
-                               v <= nxt[p + w - 1] && v <= nxt[p + w] && v <= nxt[p + w + 1];
-                if (ext) ext = v <= prv[p] && v <= prv[p - 1] && v <= prv[p + 1] && v <= prv[p - w - 1] && v <= prv[p - w] && v <= prv[p - w + 1] &&
-                               v <= prv[p + w - 1] && v <= prv[p + w] && v <= prv[p + w + 1];
-            }
-            if (ext) {
-                int r1 = r, c1 = c;
-                if (adjust_local_extrema(pyr, O, o, layer, r1, c1, cd)) {
-                    // duplicate removal: the first start pixel that reaches a cell claims it
-                    const long long bit = O.claim + ((long long)(layer - 1) * h + r1) * w + c1;
-                    const unsigned m = 1u << (bit & 31);
-                    const unsigned old = atomicOr(&claim[bit >> 5], m);
-                    found = (old & m) == 0;
-                }
-            }
+    if (i < n) {
+        const unsigned u = raw[i];
+        const int o = u >> 28;
+        int layer = ((u >> 26) & 3) + 1, r1 = (u >> 13) & 8191, c1 = u & 8191;
+        const SiftOct O = lay.o[o];
+        if (adjust_local_extrema(pyr, O, o, layer, r1, c1, cd)) {
+            // duplicate removal: the first start pixel that reaches a cell claims it
+            const long long bit = O.claim + ((long long)(layer - 1) * O.h + r1) * O.w + c1;
+            const unsigned m = 1u << (bit & 31);
+            const unsigned old = atomicOr(&claim[bit >> 5], m);
+            found = (old & m) == 0;
         }
     }
     const unsigned bal = __ballot_sync(0xffffffffu, found);
@@ -238,7 +309,7 @@ __global__ void __launch_bounds__(256) k_sift_extrema(SiftLayout lay, int o, con
         base = __shfl_sync(0xffffffffu, base, leader);
         if (found) {
             const int idx = base + __popc(bal & ((1u << lane) - 1u));
-            if (idx < SIFT_CAND_CAP) cand[idx] = cd; else ctr[2] = 1;
+            if (idx < SIFT_CAND_CAP) { cand[idx] = cd; cresp[idx] = cd.response; } else ctr[2] = 1;
         }
     }
 }
@@ -257,17 +328,26 @@ __device__ __forceinline__ float sift_atan2_deg(float y, float x) {
     return a;
 }
 
-// calcOrientationHist + peak extraction: one warp per refined candidate
-__global__ void __launch_bounds__(256) k_sift_orient(SiftLayout lay, const float* __restrict__ pyr, const SiftCand* __restrict__ cand,
+// calcOrientationHist + peak extraction: one warp per refined candidate.  Every lane accumulates its pixels into a private
+// column of the warp's histogram (2^-24 fixed point: integer sums are order independent, so the result is deterministic and
+// needs no atomics), the 32 columns are then summed with a skewed, conflict-free read.
+#define SIFT_ORI_WARPS 4
+// retainBest(nfeatures) keeps keypoints by response, and a keypoint's response is its candidate's: with T' = the nfeatures-th
+// largest CANDIDATE response, pass A (rest == 0) builds histograms only for the candidates listed in csel (response >= T').
+// If they yield >= nfeatures keypoints, the nfeatures-th largest keypoint response is >= T' and no other candidate can
+// survive; otherwise (a candidate without any peak -- practically never) pass B (rest == 1) processes the remaining ones.
+__global__ void __launch_bounds__(32 * SIFT_ORI_WARPS) k_sift_orient(SiftLayout lay, const float* __restrict__ pyr, const SiftCand* __restrict__ cand,
+                                                     const int* __restrict__ csel, int rest, int nfeatures,
                                                      int* __restrict__ ctr, float2* __restrict__ kpt, float* __restrict__ ksize,
                                                      float* __restrict__ kangle, float* __restrict__ kresp, int* __restrict__ koct) {
-    __shared__ unsigned long long sh_hist[8][36];
-    __shared__ float sh_f[8][40];
+    __shared__ unsigned long long sh_priv[SIFT_ORI_WARPS][36][32];
+    __shared__ float sh_f[SIFT_ORI_WARPS][40];
     const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ci = blockIdx.x * 8 + wi;
     int ncand = ctr[0]; if (ncand > SIFT_CAND_CAP) ncand = SIFT_CAND_CAP;
-    if (ci >= ncand) return;
-    const SiftCand cd = cand[ci];
+    if (rest && (ctr[6] >= nfeatures || ctr[7] >= ncand)) return;      // pass A was enough / had everything
+  for (int ci = blockIdx.x * SIFT_ORI_WARPS + wi; ci < (rest ? ncand : ctr[7]); ci += gridDim.x * SIFT_ORI_WARPS) {
+    if (rest && __float_as_uint(cand[ci].response) >= (unsigned)ctr[5]) continue;     // done in pass A
+    const SiftCand cd = cand[rest ? ci : csel[ci]];
     const SiftOct O = lay.o[cd.o];
     const float* img = pyr + O.g[cd.layer];
     const int w = O.w, h = O.h;
@@ -275,8 +355,8 @@ __global__ void __launch_bounds__(256) k_sift_orient(SiftLayout lay, const float
     const int radius = __float2int_rn(4.5f * scl_octv);
     const float sigma = 1.5f * scl_octv;
     const float expf_scale = -1.f / (2.f * sigma * sigma);
-    for (int i = lane; i < 36; i += 32) sh_hist[wi][i] = 0ull;
-    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 36; ++i) sh_priv[wi][i][lane] = 0ull;
     const int side = 2 * radius + 1, len = side * side;
     for (int k = lane; k < len; k += 32) {
         const int i = k / side - radius, j = k % side - radius;
@@ -290,11 +370,15 @@ __global__ void __launch_bounds__(256) k_sift_orient(SiftLayout lay, const float
         int bin = __float2int_rn((36.f / 360.f) * ori);
         if (bin >= 36) bin -= 36;
         if (bin < 0) bin += 36;
-        // deterministic accumulation: 2^-24 fixed point, integer atomics
-        atomicAdd(&sh_hist[wi][bin], (unsigned long long)__float2ll_rn(wgt * mag * 16777216.f));
+        sh_priv[wi][bin][lane] += (unsigned long long)__float2ll_rn(wgt * mag * 16777216.f);
     }
     __syncwarp();
-    for (int i = lane; i < 36; i += 32) sh_f[wi][i + 2] = (float)((double)sh_hist[wi][i] * (1.0 / 16777216.0));
+    for (int b = lane; b < 36; b += 32) {
+        unsigned long long t = 0ull;
+#pragma unroll
+        for (int l = 0; l < 32; ++l) t += sh_priv[wi][b][(l + lane) & 31];
+        sh_f[wi][b + 2] = (float)((double)t * (1.0 / 16777216.0));
+    }
     __syncwarp();
     if (lane == 0) { sh_f[wi][0] = sh_f[wi][36]; sh_f[wi][1] = sh_f[wi][37]; sh_f[wi][38] = sh_f[wi][2]; sh_f[wi][39] = sh_f[wi][3]; }
     __syncwarp();
@@ -343,16 +427,24 @@ __global__ void __launch_bounds__(256) k_sift_orient(SiftLayout lay, const float
             }
         }
     }
+    __syncwarp();
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 // retainBest(nfeatures) (ties kept) via radix select on the response bits, then cv2's KeyPoint_LessThan order
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_sift_select(int nfeatures, int* __restrict__ ctr, const float* __restrict__ kresp, int* __restrict__ sel) {
+// Generic form: keep the values >= the K-th largest (ties kept).  n = min(*n_ptr, ncap) values; indices of the kept values go
+// to sel (any order), their number to *out_count (capped at BM_KP_CAP, overflow flagged in ctr[2]), the threshold bits to
+// *out_thr.  Used twice: on the candidates' responses BEFORE orientation assignment (only candidates that can survive
+// retainBest get an orientation histogram) and on the final keypoint list.
+__global__ void __launch_bounds__(1024) k_sift_select(int nfeatures, const int* __restrict__ n_ptr, int ncap, int* __restrict__ ctr,
+                                                      const float* __restrict__ kresp, int* __restrict__ sel, int* __restrict__ out_count,
+                                                      unsigned* __restrict__ out_thr) {
     __shared__ unsigned hist[2048];
-    __shared__ unsigned s_prefix, s_mask, s_remaining;
+    __shared__ unsigned s_prefix, s_mask, s_remaining, s_wsum[32];
     __shared__ int s_count;
-    int n = ctr[1]; if (n > SIFT_KP_CAP) n = SIFT_KP_CAP;
+    int n = *n_ptr; if (n > ncap) n = ncap;
     const int tid = threadIdx.x;
     unsigned thr_bits = 0;      // keep response bits >= thr_bits
     if (n > nfeatures) {
@@ -363,18 +455,45 @@ __global__ void __launch_bounds__(1024) k_sift_select(int nfeatures, int* __rest
             for (int i = tid; i < 2048; i += blockDim.x) hist[i] = 0;
             __syncthreads();
             const unsigned prefix = s_prefix, mask = s_mask;
-            for (int i = tid; i < n; i += blockDim.x) {
-                const unsigned b = __float_as_uint(kresp[i]);
-                if ((b & mask) == prefix) atomicAdd(&hist[(b >> shifts[pass]) & ((1u << bitsn[pass]) - 1u)], 1u);
+            for (int i0 = tid; i0 < n; i0 += 8 * blockDim.x) {          // 8 independent loads in flight per thread
+                unsigned b[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; b[u] = i < n ? __float_as_uint(__ldg(kresp + i)) : 0xffffffffu; }
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (i0 + u * (int)blockDim.x < n && (b[u] & mask) == prefix) atomicAdd(&hist[(b[u] >> shifts[pass]) & ((1u << bitsn[pass]) - 1u)], 1u);
             }
             __syncthreads();
-            if (tid == 0) {
-                unsigned rem = s_remaining, cum = 0; int bin = (1 << bitsn[pass]) - 1;
-                for (; bin >= 0; --bin) { if (cum + hist[bin] >= rem) break; cum += hist[bin]; }
-                if (bin < 0) bin = 0;
-                s_remaining = rem - cum;
-                s_prefix = prefix | ((unsigned)bin << shifts[pass]);
-                s_mask = mask | (((1u << bitsn[pass]) - 1u) << shifts[pass]);
+            {   // the bin holding the rem-th largest key: suffix sums over the bins by a block-wide scan (2 bins per thread,
+                // bins in descending order), exactly one bin satisfies cum_before < rem <= cum_before + hist[bin]
+                const int nbins = 1 << bitsn[pass];
+                const int j0 = 2 * tid, b0 = nbins - 1 - j0, b1 = b0 - 1;            // descending bin order
+                const unsigned h0 = b0 >= 0 ? hist[b0] : 0u, h1 = b1 >= 0 ? hist[b1] : 0u;
+                unsigned incl = h0 + h1;
+                const int lane = tid & 31, wp = tid >> 5;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += u; }
+                if (lane == 31) s_wsum[wp] = incl;
+                __syncthreads();
+                if (wp == 0) {
+                    unsigned v = s_wsum[lane];
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += u; }
+                    s_wsum[lane] = v;
+                }
+                __syncthreads();
+                const unsigned before = incl - (h0 + h1) + (wp ? s_wsum[wp - 1] : 0u);   // keys in bins above b0
+                const unsigned rem = s_remaining, total = s_wsum[31];
+                __syncthreads();
+                int bin = -1; unsigned cum = 0;
+                if (b0 >= 0 && before < rem && before + h0 >= rem) { bin = b0; cum = before; }
+                else if (b1 >= 0 && before + h0 < rem && before + h0 + h1 >= rem) { bin = b1; cum = before + h0; }
+                if (total < rem && tid == 0) { bin = 0; cum = total - hist[0]; }       // cannot happen (n > nfeatures), kept for safety
+                if (bin >= 0) {
+                    s_remaining = rem - cum;
+                    s_prefix = prefix | ((unsigned)bin << shifts[pass]);
+                    s_mask = mask | (((1u << bitsn[pass]) - 1u) << shifts[pass]);
+                }
             }
             __syncthreads();
         }
@@ -382,11 +501,18 @@ __global__ void __launch_bounds__(1024) k_sift_select(int nfeatures, int* __rest
     }
     if (tid == 0) s_count = 0;
     __syncthreads();
-    for (int i = tid; i < n; i += blockDim.x) {
-        if (__float_as_uint(kresp[i]) >= thr_bits) { const int p = atomicAdd(&s_count, 1); if (p < BM_KP_CAP) sel[p] = i; }
+    for (int i0 = tid; i0 < n; i0 += 8 * blockDim.x) {
+        unsigned b[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; b[u] = i < n ? __float_as_uint(__ldg(kresp + i)) : 0u; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * blockDim.x;
+            if (i < n && b[u] >= thr_bits) { const int p = atomicAdd(&s_count, 1); if (p < BM_KP_CAP) sel[p] = i; }
+        }
     }
     __syncthreads();
-    if (tid == 0) { int m = s_count; if (m > BM_KP_CAP) { m = BM_KP_CAP; ctr[2] = 1; } ctr[3] = m; }
+    if (tid == 0) { int m = s_count; if (m > BM_KP_CAP) { m = BM_KP_CAP; ctr[2] = 1; } *out_count = m; if (out_thr) *out_thr = thr_bits; }
 }
 
 __device__ __forceinline__ bool kp_less(float ax, float ay, float as, float aa, float ar, int ao, int ai,
@@ -405,23 +531,39 @@ __global__ void __launch_bounds__(1024) k_sift_emit(const int* __restrict__ ctr,
                                                     const float* __restrict__ ksize, const float* __restrict__ kangle, const float* __restrict__ kresp,
                                                     const int* __restrict__ koct, BmKeypoints out) {
     const int m = ctr[3];
-    for (int a = threadIdx.x; a < m; a += blockDim.x) {
-        const int i = sel[a];
-        const float2 pi = kpt[i]; const float si = ksize[i], ai = kangle[i], ri = kresp[i]; const int oi = koct[i];
+    __shared__ float s_x[1024], s_y[1024], s_s[1024], s_a[1024], s_r[1024];
+    __shared__ int s_o[1024], s_i[1024];
+    for (int a0 = 0; a0 < m; a0 += blockDim.x) {               // (one round for m <= 1024)
+        const int a = a0 + threadIdx.x;
+        const int i = a < m ? sel[a] : 0;
+        float2 pi = make_float2(0.f, 0.f); float si = 0.f, ai = 0.f, ri = 0.f; int oi = 0;
+        if (a < m) { pi = kpt[i]; si = ksize[i]; ai = kangle[i]; ri = kresp[i]; oi = koct[i]; }
         int rank = 0;
-        for (int b = 0; b < m; ++b) {
-            const int j = sel[b];
-            const float2 pj = kpt[j];
-            rank += kp_less(pj.x, pj.y, ksize[j], kangle[j], kresp[j], koct[j], j, pi.x, pi.y, si, ai, ri, oi, i) ? 1 : 0;
+        for (int b0 = 0; b0 < m; b0 += 1024) {                 // rank = number of selected keypoints ordered before this one
+            __syncthreads();
+            const int b = b0 + threadIdx.x;
+            if (b < m) {
+                const int j = sel[b];
+                const float2 pj = kpt[j];
+                s_x[threadIdx.x] = pj.x; s_y[threadIdx.x] = pj.y; s_s[threadIdx.x] = ksize[j]; s_a[threadIdx.x] = kangle[j];
+                s_r[threadIdx.x] = kresp[j]; s_o[threadIdx.x] = koct[j]; s_i[threadIdx.x] = j;
+            }
+            __syncthreads();
+            const int nb = min(1024, m - b0);
+            if (a < m)
+                for (int q = 0; q < nb; ++q)
+                    rank += kp_less(s_x[q], s_y[q], s_s[q], s_a[q], s_r[q], s_o[q], s_i[q], pi.x, pi.y, si, ai, ri, oi, i) ? 1 : 0;
         }
-        // firstOctave = -1: octave byte -1, pt and size halved
-        const int oc = (oi & ~255) | ((oi - 1) & 255);
-        out.pt[rank] = make_float2(pi.x * 0.5f, pi.y * 0.5f);
-        out.size[rank] = si * 0.5f;
-        out.angle[rank] = ai;
-        out.response[rank] = ri;
-        out.octave[rank] = oc;
-        out.lxy[rank] = make_int2(0, 0);
+        if (a < m) {
+            // firstOctave = -1: octave byte -1, pt and size halved
+            const int oc = (oi & ~255) | ((oi - 1) & 255);
+            out.pt[rank] = make_float2(pi.x * 0.5f, pi.y * 0.5f);
+            out.size[rank] = si * 0.5f;
+            out.angle[rank] = ai;
+            out.response[rank] = ri;
+            out.octave[rank] = oc;
+            out.lxy[rank] = make_int2(0, 0);
+        }
     }
     if (threadIdx.x == 0) *out.count = m;
 }
@@ -535,6 +677,7 @@ int bm_sift_create(BmSift** out, int h, int w, int nfeatures, cudaStream_t s) {
     memset(o, 0, sizeof(*o));
     o->w = w; o->h = h; o->nfeatures = nfeatures; o->stream = s;
     const int bw = 2 * w, bh = 2 * h;
+    if (bw > 8191 || bh > 8191) { bm_set_error("SIFT: frames larger than 4095 px are not supported"); delete o; return -1; }   // raw extrema pack r, c in 13 bits
     int noct = (int)nearbyint(log((double)(bw < bh ? bw : bh)) / log(2.0) - 2.0) + 1;
     if (noct < 1) noct = 1;
     if (noct > SIFT_MAX_OCT) noct = SIFT_MAX_OCT;
@@ -571,7 +714,8 @@ int bm_sift_create(BmSift** out, int h, int w, int nfeatures, cudaStream_t s) {
               cudaMalloc(&o->ctr, 16 * sizeof(int)) == cudaSuccess && cudaMalloc(&o->kpt, SIFT_KP_CAP * sizeof(float2)) == cudaSuccess &&
               cudaMalloc(&o->ksize, SIFT_KP_CAP * 4) == cudaSuccess && cudaMalloc(&o->kangle, SIFT_KP_CAP * 4) == cudaSuccess &&
               cudaMalloc(&o->kresp, SIFT_KP_CAP * 4) == cudaSuccess && cudaMalloc(&o->koct, SIFT_KP_CAP * 4) == cudaSuccess &&
-              cudaMalloc(&o->sel, BM_KP_CAP * 4) == cudaSuccess;
+              cudaMalloc(&o->sel, BM_KP_CAP * 4) == cudaSuccess && cudaMalloc(&o->raw, (size_t)SIFT_RAW_CAP * 4) == cudaSuccess &&
+              cudaMalloc(&o->cresp, SIFT_CAND_CAP * 4) == cudaSuccess && cudaMalloc(&o->csel, BM_KP_CAP * 4) == cudaSuccess;
     if (ok) ok = cudaMemcpyToSymbol(c_sift_k, hk, sizeof(hk)) == cudaSuccess;
     if (!ok) { bm_set_error("bm_sift_create: %s", cudaGetErrorString(cudaGetLastError())); bm_sift_destroy(o); return -1; }
     *out = o;
@@ -581,23 +725,23 @@ int bm_sift_create(BmSift** out, int h, int w, int nfeatures, cudaStream_t s) {
 void bm_sift_destroy(BmSift* o) {
     if (!o) return;
     cudaFree(o->pyr); cudaFree(o->up); cudaFree(o->claim); cudaFree(o->cand); cudaFree(o->ctr); cudaFree(o->kpt); cudaFree(o->ksize);
-    cudaFree(o->kangle); cudaFree(o->kresp); cudaFree(o->koct); cudaFree(o->sel);
+    cudaFree(o->kangle); cudaFree(o->kresp); cudaFree(o->koct); cudaFree(o->sel); cudaFree(o->raw); cudaFree(o->cresp); cudaFree(o->csel);
     delete o;
 }
 
-template <int R>
-static void launch_blur(const float* in, float* out, float* dog, int w, int h, int kidx, cudaStream_t s) {
-    BM_COUNT_LAUNCHES(1), k_sift_blur<R><<<dim3((w + 31) / 32, (h + 31) / 32), dim3(32, 8), 0, s>>>(in, out, dog, w, h, kidx);
+template <int LEVEL>
+static void launch_blur(const float* in, float* out, float* dog, float* dec, int w, int h, cudaStream_t s) {
+    BM_COUNT_LAUNCHES(1), k_sift_blur<LEVEL><<<dim3((w + 63) / 64, (h + sift_tile_h(LEVEL) - 1) / sift_tile_h(LEVEL)), 256, 0, s>>>(in, out, dog, dec, w, h);
 }
 
-static void blur_level(int level, const float* in, float* out, float* dog, int w, int h, cudaStream_t s) {
+static void blur_level(int level, const float* in, float* out, float* dog, float* dec, int w, int h, cudaStream_t s) {
     switch (level) {
-        case 0: launch_blur<5>(in, out, dog, w, h, 0, s); break;
-        case 1: launch_blur<5>(in, out, dog, w, h, 1, s); break;
-        case 2: launch_blur<6>(in, out, dog, w, h, 2, s); break;
-        case 3: launch_blur<8>(in, out, dog, w, h, 3, s); break;
-        case 4: launch_blur<10>(in, out, dog, w, h, 4, s); break;
-        default: launch_blur<13>(in, out, dog, w, h, 5, s); break;
+        case 0: launch_blur<0>(in, out, dog, dec, w, h, s); break;
+        case 1: launch_blur<1>(in, out, dog, dec, w, h, s); break;
+        case 2: launch_blur<2>(in, out, dog, dec, w, h, s); break;
+        case 3: launch_blur<3>(in, out, dog, dec, w, h, s); break;
+        case 4: launch_blur<4>(in, out, dog, dec, w, h, s); break;
+        default: launch_blur<5>(in, out, dog, dec, w, h, s); break;
     }
 }
 
@@ -608,6 +752,7 @@ const float* bm_sift_level_ptr(BmSift* o, int octave, int level, int dog, int* w
     return o->pyr + (dog ? O.d[level] : O.g[level]);
 }
 int bm_sift_num_octaves(BmSift* o) { return o->lay.noct; }
+void bm_sift_counters(BmSift* o, int out[8]) { cudaStreamSynchronize(o->stream); cudaMemcpy(out, o->ctr, 8 * sizeof(int), cudaMemcpyDeviceToHost); }
 
 cudaError_t bm_sift_detect(BmSift* o, const uint8_t* d_gray, BmKeypoints* out) {
     cudaStream_t s = o->stream;
@@ -620,20 +765,22 @@ cudaError_t bm_sift_detect(BmSift* o, const uint8_t* d_gray, BmKeypoints* out) {
     BM_COUNT_LAUNCHES(1), k_sift_upsample<<<dim3((bw + 31) / 32, (bh + 7) / 8), blk, 0, s>>>(d_gray, o->w, o->h, o->up);
     for (int oc = 0; oc < L.noct; ++oc) {
         const SiftOct& O = L.o[oc];
-        if (oc == 0) blur_level(0, o->up, o->pyr + O.g[0], nullptr, O.w, O.h, s);
-        else {
-            const SiftOct& P = L.o[oc - 1];
-            BM_COUNT_LAUNCHES(1), k_sift_decimate<<<dim3((O.w + 31) / 32, (O.h + 7) / 8), blk, 0, s>>>(o->pyr + P.g[3], P.w, o->pyr + O.g[0], O.w, O.h);
-        }
-        for (int l = 1; l < 6; ++l) blur_level(l, o->pyr + O.g[l - 1], o->pyr + O.g[l], o->pyr + O.d[l - 1], O.w, O.h, s);
+        if (oc == 0) blur_level(0, o->up, o->pyr + O.g[0], nullptr, nullptr, O.w, O.h, s);
+        // level 3 also writes the next octave's base (its 2x decimation)
+        for (int l = 1; l < 6; ++l)
+            blur_level(l, o->pyr + O.g[l - 1], o->pyr + O.g[l], o->pyr + O.d[l - 1], (l == 3 && oc + 1 < L.noct) ? o->pyr + L.o[oc + 1].g[0] : nullptr, O.w, O.h, s);
     }
     for (int oc = 0; oc < L.noct; ++oc) {
         const SiftOct& O = L.o[oc];
         if (O.w <= 2 * SIFT_BORDER || O.h <= 2 * SIFT_BORDER) continue;
-        BM_COUNT_LAUNCHES(1), k_sift_extrema<<<dim3((O.w + 31) / 32, (O.h + 7) / 8, 3), blk, 0, s>>>(L, oc, o->pyr, o->claim, o->cand, o->ctr);
+        BM_COUNT_LAUNCHES(1), k_sift_extrema<<<dim3((O.w + 31) / 32, (O.h + 7) / 8), blk, 0, s>>>(L, oc, o->pyr, o->raw, o->ctr);
     }
-    BM_COUNT_LAUNCHES(1), k_sift_orient<<<SIFT_CAND_CAP / 8, 256, 0, s>>>(L, o->pyr, o->cand, o->ctr, o->kpt, o->ksize, o->kangle, o->kresp, o->koct);
-    BM_COUNT_LAUNCHES(1), k_sift_select<<<1, 1024, 0, s>>>(o->nfeatures, o->ctr, o->kresp, o->sel);
+    BM_COUNT_LAUNCHES(1), k_sift_refine<<<SIFT_RAW_CAP / 128, 128, 0, s>>>(L, o->pyr, o->raw, o->claim, o->cand, o->cresp, o->ctr);
+    BM_COUNT_LAUNCHES(1), k_sift_select<<<1, 1024, 0, s>>>(o->nfeatures, o->ctr + 0, SIFT_CAND_CAP, o->ctr, o->cresp, o->csel, o->ctr + 7, (unsigned*)(o->ctr + 5));
+    BM_COUNT_LAUNCHES(1), k_sift_orient<<<512, 32 * SIFT_ORI_WARPS, 0, s>>>(L, o->pyr, o->cand, o->csel, 0, o->nfeatures, o->ctr, o->kpt, o->ksize, o->kangle, o->kresp, o->koct);
+    if ((e = cudaMemcpyAsync(o->ctr + 6, o->ctr + 1, sizeof(int), cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return e;
+    BM_COUNT_LAUNCHES(1), k_sift_orient<<<1024, 32 * SIFT_ORI_WARPS, 0, s>>>(L, o->pyr, o->cand, o->csel, 1, o->nfeatures, o->ctr, o->kpt, o->ksize, o->kangle, o->kresp, o->koct);
+    BM_COUNT_LAUNCHES(1), k_sift_select<<<1, 1024, 0, s>>>(o->nfeatures, o->ctr + 1, SIFT_KP_CAP, o->ctr, o->kresp, o->sel, o->ctr + 3, nullptr);
     BM_COUNT_LAUNCHES(1), k_sift_emit<<<1, 1024, 0, s>>>(o->ctr, o->sel, o->kpt, o->ksize, o->kangle, o->kresp, o->koct, *out);
     BM_COUNT_LAUNCHES(1), k_sift_describe<<<BM_KP_CAP, 256, 0, s>>>(L, o->pyr, *out);
     return cudaGetLastError();

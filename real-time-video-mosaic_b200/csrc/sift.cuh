@@ -9,3 +9,5 @@ void bm_sift_destroy(BmSift* o);
 cudaError_t bm_sift_detect(BmSift* o, const uint8_t* d_gray, BmKeypoints* out);
 const float* bm_sift_level_ptr(BmSift* o, int octave, int level, int dog, int* w, int* h);
 int bm_sift_num_octaves(BmSift* o);
+// device counters of the last detect (cand, kp, overflow flag, selected, raw, threshold bits, kp after pass A, listed candidates)
+void bm_sift_counters(BmSift* o, int out[8]);

@@ -8,6 +8,7 @@
 #include <vector>
 #include <string.h>
 #include <math.h>
+#include <stdlib.h>
 
 extern "C" int bm_keypoint_capacity(void) { return BM_KP_CAP; }
 
@@ -62,6 +63,12 @@ extern "C" bm_status bm_sift_detect_and_compute(const uint8_t* d_gray, int h, in
     std::vector<uint8_t> d8((size_t)cap * 128);
     int n = 0;
     if (st == BM_OK) st = bm_download_keypoints(k, 128, h_kp, d8.data(), cap, &n, nullptr);
+    if (st == BM_OK) {
+        int c[8];
+        bm_sift_counters(o, c);
+        if (getenv("BM_SIFT_DEBUG")) fprintf(stderr, "sift counters: cand %d kp %d overflow %d selected %d raw %d thr %08x kpA %d listed %d\n", c[0], c[1], c[2], c[3], c[4], (unsigned)c[5], c[6], c[7]);
+        if (c[2]) { bm_set_error("SIFT candidate / keypoint capacity exceeded"); st = BM_ERR_UNSUPPORTED; }
+    }
     if (st == BM_OK) { if (h_desc) for (size_t i = 0; i < (size_t)n * 128; ++i) h_desc[i] = (float)d8[i]; if (n_out) *n_out = n; }
     bm_kp_free(&k); bm_sift_destroy(o);
     return st;
