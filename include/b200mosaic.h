@@ -79,6 +79,14 @@ bm_status bm_process_frame_device(bm_handle h, const uint8_t* d_bgr, bm_frame_in
 bm_status bm_process_frame_begin(bm_handle h, const uint8_t* h_bgr, size_t stride_bytes);
 bm_status bm_process_frame_begin_device(bm_handle h, const uint8_t* d_bgr);
 bm_status bm_process_frame_end(bm_handle h, bm_frame_info* info);
+/* double-buffered ingest (north_star: "pinned, double-buffered H2D copies"): start the H2D + BGR->gray/BGRX of the NEXT frame on
+ * the copy stream while the current one is processed; the following bm_process_frame / _begin / bm_warp_frame / bm_estimate_frame
+ * call with the same host pointer consumes the staged copy instead of uploading again.  The buffer must stay unchanged in
+ * between (pageable buffers are copied to pinned staging memory immediately). */
+bm_status bm_prefetch_frame(bm_handle h, const uint8_t* h_bgr, size_t stride_bytes);
+/* 1 (default): the warp/blend chain of frame t runs concurrently with detect/match/RANSAC of frame t+1 (separate streams);
+ * 0: strictly one after the other (used to time the chain alone) */
+bm_status bm_set_overlap(bm_handle h, int on);
 /* offline pair-sharded mode (config 3 at N GPUs): features of this frame, matches and RANSAC against the previous frame of
  * this handle, NO validation / warp; the frame always becomes the new "previous".  info->H_rel, n_matches, status
  * (BM_OK | BM_SKIP_FEW_MATCHES | BM_SKIP_NO_H) are filled. */

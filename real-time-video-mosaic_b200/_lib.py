@@ -71,6 +71,8 @@ def load():
     _sig(lib, "bm_process_frame_begin_device", i, vp, vp)
     _sig(lib, "bm_process_frame_end", i, vp, C.POINTER(BmFrameInfo))
     _sig(lib, "bm_estimate_frame", i, vp, vp, sz, C.POINTER(BmFrameInfo))
+    _sig(lib, "bm_prefetch_frame", i, vp, vp, sz)
+    _sig(lib, "bm_set_overlap", i, vp, i)
     _sig(lib, "bm_clear_canvas", i, vp)
     _sig(lib, "bm_get_canvas_device", i, vp, vp)
     _sig(lib, "bm_timing_enable", i, vp, i)

@@ -50,9 +50,19 @@ static bm_status alloc_blend(BmBlendBufs& b, int canvas_h, int canvas_w, size_t 
     return BM_OK;
 }
 
+// Three streams per handle:
+//   stream   : detect / match / RANSAC of frame t (the host waits on it once per frame for the homography)
+//   s_chain  : warp / blend chain of frame t -- runs concurrently with detect of frame t+1 (it only touches the canvas)
+//   s_copy   : H2D + ingest of the next frame (bm_prefetch_frame) while the current one is being processed
+// Frame slots are double buffered; events order  upload(slot) -> detect / chain(slot) -> next upload(slot).
 struct bm_mosaic_s {
     bm_config cfg;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, s_chain = nullptr, s_copy = nullptr;
+    cudaEvent_t ev_up[2] = {nullptr, nullptr};          // upload + ingest of the slot finished
+    cudaEvent_t ev_chain[2] = {nullptr, nullptr};       // last chain that read the slot's BGRX finished
+    int overlap = 1;                                    // 0: detect waits for the previous chain (clean chain timing)
+    const uint8_t* prefetched = nullptr;                // host pointer staged by bm_prefetch_frame ...
+    int prefetched_slot = -1;                           // ... into this slot
     BmBlendBufs blend;
     // frame staging: double-buffered pinned host + device buffers
     uint8_t* h_stage[2] = {nullptr, nullptr};
@@ -95,6 +105,12 @@ extern "C" bm_status bm_create(const bm_config* cfg, bm_handle* out) {
     m->cfg = *cfg;
     if (m->cfg.nfeatures <= 0) m->cfg.nfeatures = 700;
     BM_CUDA_OK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    BM_CUDA_OK(cudaStreamCreateWithFlags(&m->s_chain, cudaStreamNonBlocking));
+    BM_CUDA_OK(cudaStreamCreateWithFlags(&m->s_copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        BM_CUDA_OK(cudaEventCreateWithFlags(&m->ev_up[i], cudaEventDisableTiming));
+        BM_CUDA_OK(cudaEventCreateWithFlags(&m->ev_chain[i], cudaEventDisableTiming));
+    }
     // scratch: the window of a frame is at most the canvas; typical is frame-sized.  Size for the whole canvas when
     // it is small (<= 64 Mpx), otherwise for 4x the frame area plus margins (config 5: 32768^2 canvas, 4K frames).
     const size_t canvas_px = (size_t)cfg->canvas_h * cfg->canvas_w;
@@ -122,7 +138,7 @@ extern "C" bm_status bm_create(const bm_config* cfg, bm_handle* out) {
 extern "C" bm_status bm_destroy(bm_handle m) {
     if (!m) return BM_OK;
     cudaSetDevice(m->cfg.device);
-    cudaStreamSynchronize(m->stream);
+    cudaStreamSynchronize(m->stream); cudaStreamSynchronize(m->s_chain); cudaStreamSynchronize(m->s_copy);
     bm_pipeline_destroy(m->pipe);
     free_blend(m->blend);
     for (int i = 0; i < 2; ++i) {
@@ -131,7 +147,8 @@ extern "C" bm_status bm_destroy(bm_handle m) {
     }
     cudaFree(m->d_canvas_bgr);
     for (int i = 0; i < bm_mosaic_s::kEvRing; ++i) { cudaEventDestroy(m->ev0[i]); cudaEventDestroy(m->ev1[i]); }
-    cudaStreamDestroy(m->stream);
+    for (int i = 0; i < 2; ++i) { if (m->ev_up[i]) cudaEventDestroy(m->ev_up[i]); if (m->ev_chain[i]) cudaEventDestroy(m->ev_chain[i]); }
+    cudaStreamDestroy(m->stream); cudaStreamDestroy(m->s_chain); cudaStreamDestroy(m->s_copy);
     delete m;
     return BM_OK;
 }
@@ -153,29 +170,54 @@ static bm_status upload(bm_mosaic_s* m, const uint8_t* h_bgr, size_t stride, int
         else for (int y = 0; y < fh; ++y) memcpy(m->h_stage[slot] + (size_t)y * rowb, h_bgr + (size_t)y * stride, rowb);
         src = m->h_stage[slot];
     }
-    BM_CUDA_OK(cudaMemcpyAsync(m->d_bgr[slot], src, fb, cudaMemcpyHostToDevice, m->stream));
-    BM_CUDA_OK(cudaEventRecord(m->ev_h2d[slot], m->stream));
-    BM_CUDA_OK(bm_launch_ingest(m->d_bgr[slot], fh, fw, m->d_gray[slot], m->d_bgrx[slot], m->stream));
+    // the slot's previous tenant: its detect finished (the host waited for it), its chain may still be reading the BGRX copy
+    BM_CUDA_OK(cudaStreamWaitEvent(m->s_copy, m->ev_chain[slot], 0));
+    BM_CUDA_OK(cudaMemcpyAsync(m->d_bgr[slot], src, fb, cudaMemcpyHostToDevice, m->s_copy));
+    BM_CUDA_OK(cudaEventRecord(m->ev_h2d[slot], m->s_copy));
+    BM_CUDA_OK(bm_launch_ingest(m->d_bgr[slot], fh, fw, m->d_gray[slot], m->d_bgrx[slot], m->s_copy));
+    BM_CUDA_OK(cudaEventRecord(m->ev_up[slot], m->s_copy));
     return BM_OK;
 }
+
+// frame -> slot `slot` unless bm_prefetch_frame already staged exactly this host buffer there; then make `consumer` wait for it
+static bm_status stage_frame(bm_mosaic_s* m, const uint8_t* h_bgr, size_t stride, int slot, cudaStream_t consumer) {
+    if (!(m->prefetched && m->prefetched == h_bgr && m->prefetched_slot == slot)) BM_TRY(upload(m, h_bgr, stride, slot));
+    m->prefetched = nullptr;
+    BM_CUDA_OK(cudaStreamWaitEvent(consumer, m->ev_up[slot], 0));
+    return BM_OK;
+}
+
+extern "C" bm_status bm_prefetch_frame(bm_handle m, const uint8_t* h_bgr, size_t stride) {
+    if (!m || !h_bgr) { bm_set_error("bm_prefetch_frame: null"); return BM_ERR_ARG; }
+    BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+    BM_TRY(upload(m, h_bgr, stride, m->cur ^ 1));
+    m->prefetched = h_bgr; m->prefetched_slot = m->cur ^ 1;
+    return BM_OK;
+}
+
+extern "C" bm_status bm_set_overlap(bm_handle m, int on) { if (!m) return BM_ERR_ARG; m->overlap = on ? 1 : 0; return BM_OK; }
 
 extern "C" bm_status bm_first_frame(bm_handle m, const uint8_t* h_bgr, size_t stride) {
     if (!m || !h_bgr) { bm_set_error("bm_first_frame: null"); return BM_ERR_ARG; }
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
     const int fh = m->cfg.frame_h, fw = m->cfg.frame_w, ch = m->cfg.canvas_h, cw = m->cfg.canvas_w;
-    m->cur = 0;
+    m->cur = 0; m->prefetched = nullptr;
     BM_TRY(upload(m, h_bgr, stride, 0));
+    BM_CUDA_OK(cudaStreamWaitEvent(m->stream, m->ev_up[0], 0));
+    BM_CUDA_OK(cudaStreamWaitEvent(m->s_chain, m->ev_up[0], 0));
     // main.py:86-87 (the reference's names are swapped: w_offset is the ROW offset)
     m->w_offset = (int)((double)ch / 1 - (double)fh / 1);
     m->h_offset = (int)((double)cw / 2 - (double)fw / 2);
-    BM_CUDA_OK(cudaMemsetAsync(m->blend.canvas, 0, (size_t)ch * cw * sizeof(uchar4), m->stream));
-    BM_CUDA_OK(bm_launch_paste(m->blend.canvas, cw, m->d_bgrx[0], fw, fh, m->h_offset, m->w_offset, m->stream));   // main.py:89-90
-    BM_CUDA_OK(bm_launch_full_rowscan(m->blend, m->stream));
+    BM_CUDA_OK(cudaMemsetAsync(m->blend.canvas, 0, (size_t)ch * cw * sizeof(uchar4), m->s_chain));
+    BM_CUDA_OK(bm_launch_paste(m->blend.canvas, cw, m->d_bgrx[0], fw, fh, m->h_offset, m->w_offset, m->s_chain));   // main.py:89-90
+    BM_CUDA_OK(bm_launch_full_rowscan(m->blend, m->s_chain));
+    BM_CUDA_OK(cudaEventRecord(m->ev_chain[0], m->s_chain));
     for (int i = 0; i < 9; ++i) m->H_old[i] = (i % 4 == 0) ? 1.0 : 0.0;      // main.py:92-94
     m->H_old[2] = m->h_offset; m->H_old[5] = m->w_offset;
     m->history_len = 0;
     BM_TRY(bm_pipeline_first_frame(m->pipe, m->d_gray[0]));                  // main.py:104-112
     BM_CUDA_OK(cudaStreamSynchronize(m->stream));
+    BM_CUDA_OK(cudaStreamSynchronize(m->s_chain));
     return BM_OK;
 }
 
@@ -206,16 +248,17 @@ extern "C" bm_status bm_timing_read(bm_handle m, double* ms, double* bytes, int*
     return BM_OK;
 }
 
-static bm_status warp_device(bm_mosaic_s* m, const uchar4* d_bgrx, const double H[9], bm_frame_info* info, bool want_flag) {
+static bm_status warp_device(bm_mosaic_s* m, const uchar4* d_bgrx, const double H[9], bm_frame_info* info, bool want_flag, int slot = -1) {
     BmFramePlan plan;
     bm_make_plan(H, m->cfg.frame_w, m->cfg.frame_h, m->cfg.canvas_w, m->cfg.canvas_h, &plan);
     const size_t need = (size_t)bm_win_w(plan.reg) * bm_win_h(plan.reg);
     if (plan.valid && need > m->blend.scratch_px) { bm_set_error("warp window %zu px exceeds scratch %zu px", need, m->blend.scratch_px); return BM_ERR_UNSUPPORTED; }
     if (m->timing && m->ev_pending == bm_mosaic_s::kEvRing) BM_TRY(timing_drain(m));
-    if (m->timing) BM_CUDA_OK(cudaEventRecord(m->ev0[m->ev_pending], m->stream));
-    BM_CUDA_OK(bm_launch_warp_blend(m->blend, d_bgrx, plan, m->stream));
+    if (m->timing) BM_CUDA_OK(cudaEventRecord(m->ev0[m->ev_pending], m->s_chain));
+    BM_CUDA_OK(bm_launch_warp_blend(m->blend, d_bgrx, plan, m->s_chain));
+    if (slot >= 0) BM_CUDA_OK(cudaEventRecord(m->ev_chain[slot], m->s_chain));
     if (m->timing) {
-        BM_CUDA_OK(cudaEventRecord(m->ev1[m->ev_pending], m->stream));
+        BM_CUDA_OK(cudaEventRecord(m->ev1[m->ev_pending], m->s_chain));
         m->ev_pending++;
         const double N = (double)m->cfg.frame_w * m->cfg.frame_h, A = plan.valid ? (double)bm_win_w(plan.win) * bm_win_h(plan.win) : 0.0;
         m->t_bytes += 3.0 * N + 6.0 * A; m->t_frames++;
@@ -223,8 +266,8 @@ static bm_status warp_device(bm_mosaic_s* m, const uchar4* d_bgrx, const double 
     fill_info_plan(info, plan);
     if (info && want_flag) {
         int f = 0;
-        if (plan.valid) BM_CUDA_OK(cudaMemcpyAsync(&f, m->blend.flags, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
-        BM_CUDA_OK(cudaStreamSynchronize(m->stream));
+        if (plan.valid) BM_CUDA_OK(cudaMemcpyAsync(&f, m->blend.flags, sizeof(int), cudaMemcpyDeviceToHost, m->s_chain));
+        BM_CUDA_OK(cudaStreamSynchronize(m->s_chain));
         info->any_overlap = f;
     }
     return BM_OK;
@@ -234,9 +277,9 @@ extern "C" bm_status bm_warp_frame(bm_handle m, const uint8_t* h_bgr, size_t str
     if (!m || !h_bgr || !H) { bm_set_error("bm_warp_frame: null"); return BM_ERR_ARG; }
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
     m->cur ^= 1;
-    BM_TRY(upload(m, h_bgr, stride, m->cur));
+    BM_TRY(stage_frame(m, h_bgr, stride, m->cur, m->s_chain));
     if (info) { memset(info, 0, sizeof(*info)); memcpy(info->H, H, 9 * sizeof(double)); }
-    return warp_device(m, m->d_bgrx[m->cur], H, info, true);
+    return warp_device(m, m->d_bgrx[m->cur], H, info, true, m->cur);
 }
 
 extern "C" bm_status bm_warp_frame_device(bm_handle m, const uint8_t* d_bgrx, const double H[9], bm_frame_info* info) {
@@ -249,14 +292,16 @@ extern "C" bm_status bm_upload_frame(bm_handle m, const uint8_t* h_bgr, size_t s
     if (!m || !h_bgr) return BM_ERR_ARG;
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
     m->cur ^= 1;
-    BM_TRY(upload(m, h_bgr, stride, m->cur));
+    BM_TRY(stage_frame(m, h_bgr, stride, m->cur, m->s_chain));
     if (d_out) *d_out = reinterpret_cast<const uint8_t*>(m->d_bgrx[m->cur]);
     return BM_OK;
 }
 
 extern "C" bm_status bm_sync(bm_handle m) {
     if (!m) return BM_ERR_ARG;
+    BM_CUDA_OK(cudaStreamSynchronize(m->s_copy));
     BM_CUDA_OK(cudaStreamSynchronize(m->stream));
+    BM_CUDA_OK(cudaStreamSynchronize(m->s_chain));
     return BM_OK;
 }
 extern "C" void* bm_stream(bm_handle m) { return m ? (void*)m->stream : nullptr; }
@@ -265,9 +310,9 @@ extern "C" bm_status bm_get_canvas(bm_handle m, uint8_t* h_out) {
     if (!m || !h_out) return BM_ERR_ARG;
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
     const size_t n = (size_t)m->cfg.canvas_h * m->cfg.canvas_w;
-    BM_CUDA_OK(bm_launch_unpack_canvas(m->blend.canvas, m->d_canvas_bgr, (int)n, m->stream));
-    BM_CUDA_OK(cudaMemcpyAsync(h_out, m->d_canvas_bgr, n * 3, cudaMemcpyDeviceToHost, m->stream));
-    BM_CUDA_OK(cudaStreamSynchronize(m->stream));
+    BM_CUDA_OK(bm_launch_unpack_canvas(m->blend.canvas, m->d_canvas_bgr, (int)n, m->s_chain));
+    BM_CUDA_OK(cudaMemcpyAsync(h_out, m->d_canvas_bgr, n * 3, cudaMemcpyDeviceToHost, m->s_chain));
+    BM_CUDA_OK(cudaStreamSynchronize(m->s_chain));
     return BM_OK;
 }
 
@@ -346,7 +391,7 @@ static bm_status finish_frame(bm_mosaic_s* m, int slot, bm_frame_info* info_out)
     smooth_h(m, Hv, Hs);
     matmul3(m->H_old, Hs, Habs);
     memcpy(info.H, Habs, 72);
-    BM_TRY(warp_device(m, m->d_bgrx[slot], Habs, &info, false));
+    BM_TRY(warp_device(m, m->d_bgrx[slot], Habs, &info, false, slot));
     memcpy(m->H_old, Habs, 72);
     bm_pipeline_advance(m->pipe);                                     // kp_prev/des_prev <- cur (main.py:756-759)
     info.status = ret;
@@ -354,11 +399,20 @@ static bm_status finish_frame(bm_mosaic_s* m, int slot, bm_frame_info* info_out)
     return ret;
 }
 
+// overlap == 0: detect of this frame starts only after the previous frame's chain (used for clean chain timing)
+static bm_status order_after_chain(bm_mosaic_s* m) {
+    if (m->overlap) return BM_OK;
+    BM_CUDA_OK(cudaStreamWaitEvent(m->stream, m->ev_chain[0], 0));
+    BM_CUDA_OK(cudaStreamWaitEvent(m->stream, m->ev_chain[1], 0));
+    return BM_OK;
+}
+
 extern "C" bm_status bm_process_frame_begin(bm_handle m, const uint8_t* h_bgr, size_t stride) {
     if (!m || !h_bgr) { bm_set_error("bm_process_frame_begin: null"); return BM_ERR_ARG; }
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
     m->cur ^= 1;
-    BM_TRY(upload(m, h_bgr, stride, m->cur));
+    BM_TRY(stage_frame(m, h_bgr, stride, m->cur, m->stream));
+    BM_TRY(order_after_chain(m));
     bm_status st = bm_pipeline_estimate_begin(m->pipe, m->d_gray[m->cur]);
     if (st < 0) m->cur ^= 1;
     return st;
@@ -367,8 +421,11 @@ extern "C" bm_status bm_process_frame_begin(bm_handle m, const uint8_t* h_bgr, s
 extern "C" bm_status bm_process_frame_begin_device(bm_handle m, const uint8_t* d_bgr) {
     if (!m || !d_bgr) { bm_set_error("bm_process_frame_begin_device: null"); return BM_ERR_ARG; }
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
-    m->cur ^= 1;
+    m->cur ^= 1; m->prefetched = nullptr;
+    BM_CUDA_OK(cudaStreamWaitEvent(m->stream, m->ev_chain[m->cur], 0));      // the slot's previous chain still reads its BGRX copy
     BM_CUDA_OK(bm_launch_ingest(d_bgr, m->cfg.frame_h, m->cfg.frame_w, m->d_gray[m->cur], m->d_bgrx[m->cur], m->stream));
+    BM_CUDA_OK(cudaEventRecord(m->ev_up[m->cur], m->stream));
+    BM_TRY(order_after_chain(m));
     bm_status st = bm_pipeline_estimate_begin(m->pipe, m->d_gray[m->cur]);
     if (st < 0) m->cur ^= 1;
     return st;
@@ -396,7 +453,7 @@ extern "C" bm_status bm_estimate_frame(bm_handle m, const uint8_t* h_bgr, size_t
     if (!m || !h_bgr) { bm_set_error("bm_estimate_frame: null"); return BM_ERR_ARG; }
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
     m->cur ^= 1;
-    BM_TRY(upload(m, h_bgr, stride, m->cur));
+    BM_TRY(stage_frame(m, h_bgr, stride, m->cur, m->stream));
     bm_frame_info info; memset(&info, 0, sizeof(info));
     double H_rel[9]; int have_h = 0;
     bm_status st = bm_pipeline_estimate(m->pipe, m->d_gray[m->cur], &info, H_rel, &have_h);
@@ -414,17 +471,17 @@ extern "C" bm_status bm_estimate_frame(bm_handle m, const uint8_t* h_bgr, size_t
 extern "C" bm_status bm_clear_canvas(bm_handle m) {
     if (!m) return BM_ERR_ARG;
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
-    BM_CUDA_OK(cudaMemsetAsync(m->blend.canvas, 0, (size_t)m->cfg.canvas_h * m->cfg.canvas_w * sizeof(uchar4), m->stream));
-    BM_CUDA_OK(bm_launch_full_rowscan(m->blend, m->stream));
-    BM_CUDA_OK(cudaStreamSynchronize(m->stream));
+    BM_CUDA_OK(cudaMemsetAsync(m->blend.canvas, 0, (size_t)m->cfg.canvas_h * m->cfg.canvas_w * sizeof(uchar4), m->s_chain));
+    BM_CUDA_OK(bm_launch_full_rowscan(m->blend, m->s_chain));
+    BM_CUDA_OK(cudaStreamSynchronize(m->s_chain));
     return BM_OK;
 }
 
 extern "C" bm_status bm_get_canvas_device(bm_handle m, uint8_t* d_out) {
     if (!m || !d_out) return BM_ERR_ARG;
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
-    BM_CUDA_OK(bm_launch_unpack_canvas(m->blend.canvas, d_out, (int)((size_t)m->cfg.canvas_h * m->cfg.canvas_w), m->stream));
-    BM_CUDA_OK(cudaStreamSynchronize(m->stream));
+    BM_CUDA_OK(bm_launch_unpack_canvas(m->blend.canvas, d_out, (int)((size_t)m->cfg.canvas_h * m->cfg.canvas_w), m->s_chain));
+    BM_CUDA_OK(cudaStreamSynchronize(m->s_chain));
     return BM_OK;
 }
 

@@ -37,6 +37,8 @@ struct SiftCand {            // refined extremum (adjustLocalExtrema output)
     int octave_packed;
 };
 
+struct SiftGraph { const uint8_t* gray; const void* out_pt; cudaGraphExec_t exec; int launches; };
+
 struct BmSift {
     int w, h, nfeatures;
     SiftLayout lay;
@@ -52,6 +54,13 @@ struct BmSift {
     unsigned* hist;          // radix-select scratch
     float* kernels_dev;      // 6 kernels x 32 taps
     cudaStream_t stream;
+    // fork / join streams + events of the captured detect graph, and the graph cache
+    cudaStream_t s2, s3;
+    cudaEvent_t ev_fork, ev_l3[SIFT_MAX_OCT], ev_l5[SIFT_MAX_OCT], ev_join2, ev_join3;
+    static const int kMaxGraphs = 8;
+    SiftGraph graphs[kMaxGraphs];
+    int ngraphs;
+    bool graphs_enabled;
 };
 
 __constant__ float c_sift_k[6][32];     // [0] = base blur (sigma 1.249), [1..5] = level blurs; taps 0..K-1
@@ -572,12 +581,12 @@ __global__ void __launch_bounds__(1024) k_sift_emit(const int* __restrict__ ctr,
 // calcSIFTDescriptor: one CTA per keypoint
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_sift_describe(SiftLayout lay, const float* __restrict__ pyr, BmKeypoints kp) {
-    const int k = blockIdx.x;
-    if (k >= *kp.count) return;
     __shared__ unsigned long long hist[6 * 6 * 10];
     __shared__ float raw[128];
     __shared__ float red[8];
     const int tid = threadIdx.x;
+  for (int k = blockIdx.x; k < *kp.count; k += gridDim.x) {
+    __syncthreads();                                       // previous keypoint of this CTA is done with the shared arrays
     for (int i = tid; i < 360; i += 256) hist[i] = 0ull;
     const int packed = kp.octave[k];
     int octave = packed & 255; const int layer = (packed >> 8) & 255;
@@ -658,6 +667,7 @@ __global__ void __launch_bounds__(256) k_sift_describe(SiftLayout lay, const flo
         const int q = __float2int_rn(v * n2);
         kp.desc[(size_t)k * 128 + tid] = (uint8_t)max(0, min(255, q));
     }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -717,6 +727,12 @@ int bm_sift_create(BmSift** out, int h, int w, int nfeatures, cudaStream_t s) {
               cudaMalloc(&o->sel, BM_KP_CAP * 4) == cudaSuccess && cudaMalloc(&o->raw, (size_t)SIFT_RAW_CAP * 4) == cudaSuccess &&
               cudaMalloc(&o->cresp, SIFT_CAND_CAP * 4) == cudaSuccess && cudaMalloc(&o->csel, BM_KP_CAP * 4) == cudaSuccess;
     if (ok) ok = cudaMemcpyToSymbol(c_sift_k, hk, sizeof(hk)) == cudaSuccess;
+    if (ok) ok = cudaStreamCreateWithFlags(&o->s2, cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&o->s3, cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&o->ev_fork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&o->ev_join2, cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&o->ev_join3, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; ok && i < SIFT_MAX_OCT; ++i)
+        ok = cudaEventCreateWithFlags(&o->ev_l3[i], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&o->ev_l5[i], cudaEventDisableTiming) == cudaSuccess;
+    o->graphs_enabled = true;
     if (!ok) { bm_set_error("bm_sift_create: %s", cudaGetErrorString(cudaGetLastError())); bm_sift_destroy(o); return -1; }
     *out = o;
     return 0;
@@ -724,6 +740,13 @@ int bm_sift_create(BmSift** out, int h, int w, int nfeatures, cudaStream_t s) {
 
 void bm_sift_destroy(BmSift* o) {
     if (!o) return;
+    for (int i = 0; i < o->ngraphs; ++i) cudaGraphExecDestroy(o->graphs[i].exec);
+    if (o->s2) cudaStreamDestroy(o->s2);
+    if (o->s3) cudaStreamDestroy(o->s3);
+    if (o->ev_fork) cudaEventDestroy(o->ev_fork);
+    if (o->ev_join2) cudaEventDestroy(o->ev_join2);
+    if (o->ev_join3) cudaEventDestroy(o->ev_join3);
+    for (int i = 0; i < SIFT_MAX_OCT; ++i) { if (o->ev_l3[i]) cudaEventDestroy(o->ev_l3[i]); if (o->ev_l5[i]) cudaEventDestroy(o->ev_l5[i]); }
     cudaFree(o->pyr); cudaFree(o->up); cudaFree(o->claim); cudaFree(o->cand); cudaFree(o->ctr); cudaFree(o->kpt); cudaFree(o->ksize);
     cudaFree(o->kangle); cudaFree(o->kresp); cudaFree(o->koct); cudaFree(o->sel); cudaFree(o->raw); cudaFree(o->cresp); cudaFree(o->csel);
     delete o;
@@ -754,12 +777,17 @@ const float* bm_sift_level_ptr(BmSift* o, int octave, int level, int dog, int* w
 int bm_sift_num_octaves(BmSift* o) { return o->lay.noct; }
 void bm_sift_counters(BmSift* o, int out[8]) { cudaStreamSynchronize(o->stream); cudaMemcpy(out, o->ctr, 8 * sizeof(int), cudaMemcpyDeviceToHost); }
 
-cudaError_t bm_sift_detect(BmSift* o, const uint8_t* d_gray, BmKeypoints* out) {
-    cudaStream_t s = o->stream;
+// The whole detectAndCompute as one enqueue.  With `forked`, levels 4-5 of every octave run on a second stream and the
+// extrema scans on a third, so that the dependency chain is only  level 1 -> 2 -> 3 (-> next octave's base)  per octave:
+// the seven smallest octaves are one-CTA kernels whose ~4 us latencies would otherwise add up serially.
+static cudaError_t sift_enqueue(BmSift* o, const uint8_t* d_gray, BmKeypoints* out, bool forked) {
+    cudaStream_t s = o->stream, s2 = forked ? o->s2 : s, s3 = forked ? o->s3 : s;
     const SiftLayout& L = o->lay;
     cudaError_t e;
-    if ((e = cudaMemsetAsync(o->ctr, 0, 16 * sizeof(int), s)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(o->claim, 0, o->claim_words * 4, s)) != cudaSuccess) return e;
+#define SIFT_OK(x) do { if ((e = (x)) != cudaSuccess) return e; } while (0)
+    SIFT_OK(cudaMemsetAsync(o->ctr, 0, 16 * sizeof(int), s));
+    if (forked) { SIFT_OK(cudaEventRecord(o->ev_fork, s)); SIFT_OK(cudaStreamWaitEvent(s3, o->ev_fork, 0)); }
+    SIFT_OK(cudaMemsetAsync(o->claim, 0, o->claim_words * 4, s3));
     const dim3 blk(32, 8);
     const int bw = 2 * o->w, bh = 2 * o->h;
     BM_COUNT_LAUNCHES(1), k_sift_upsample<<<dim3((bw + 31) / 32, (bh + 7) / 8), blk, 0, s>>>(d_gray, o->w, o->h, o->up);
@@ -767,21 +795,59 @@ cudaError_t bm_sift_detect(BmSift* o, const uint8_t* d_gray, BmKeypoints* out) {
         const SiftOct& O = L.o[oc];
         if (oc == 0) blur_level(0, o->up, o->pyr + O.g[0], nullptr, nullptr, O.w, O.h, s);
         // level 3 also writes the next octave's base (its 2x decimation)
-        for (int l = 1; l < 6; ++l)
+        for (int l = 1; l <= 3; ++l)
             blur_level(l, o->pyr + O.g[l - 1], o->pyr + O.g[l], o->pyr + O.d[l - 1], (l == 3 && oc + 1 < L.noct) ? o->pyr + L.o[oc + 1].g[0] : nullptr, O.w, O.h, s);
-    }
-    for (int oc = 0; oc < L.noct; ++oc) {
-        const SiftOct& O = L.o[oc];
+        if (forked) { SIFT_OK(cudaEventRecord(o->ev_l3[oc], s)); SIFT_OK(cudaStreamWaitEvent(s2, o->ev_l3[oc], 0)); }
+        for (int l = 4; l <= 5; ++l) blur_level(l, o->pyr + O.g[l - 1], o->pyr + O.g[l], o->pyr + O.d[l - 1], nullptr, O.w, O.h, s2);
         if (O.w <= 2 * SIFT_BORDER || O.h <= 2 * SIFT_BORDER) continue;
-        BM_COUNT_LAUNCHES(1), k_sift_extrema<<<dim3((O.w + 31) / 32, (O.h + 7) / 8), blk, 0, s>>>(L, oc, o->pyr, o->raw, o->ctr);
+        if (forked) { SIFT_OK(cudaEventRecord(o->ev_l5[oc], s2)); SIFT_OK(cudaStreamWaitEvent(s3, o->ev_l5[oc], 0)); }
+        BM_COUNT_LAUNCHES(1), k_sift_extrema<<<dim3((O.w + 31) / 32, (O.h + 7) / 8), blk, 0, s3>>>(L, oc, o->pyr, o->raw, o->ctr);
+    }
+    if (forked) {
+        SIFT_OK(cudaEventRecord(o->ev_join2, s2)); SIFT_OK(cudaEventRecord(o->ev_join3, s3));
+        SIFT_OK(cudaStreamWaitEvent(s, o->ev_join2, 0)); SIFT_OK(cudaStreamWaitEvent(s, o->ev_join3, 0));
     }
     BM_COUNT_LAUNCHES(1), k_sift_refine<<<SIFT_RAW_CAP / 128, 128, 0, s>>>(L, o->pyr, o->raw, o->claim, o->cand, o->cresp, o->ctr);
     BM_COUNT_LAUNCHES(1), k_sift_select<<<1, 1024, 0, s>>>(o->nfeatures, o->ctr + 0, SIFT_CAND_CAP, o->ctr, o->cresp, o->csel, o->ctr + 7, (unsigned*)(o->ctr + 5));
     BM_COUNT_LAUNCHES(1), k_sift_orient<<<512, 32 * SIFT_ORI_WARPS, 0, s>>>(L, o->pyr, o->cand, o->csel, 0, o->nfeatures, o->ctr, o->kpt, o->ksize, o->kangle, o->kresp, o->koct);
-    if ((e = cudaMemcpyAsync(o->ctr + 6, o->ctr + 1, sizeof(int), cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return e;
+    SIFT_OK(cudaMemcpyAsync(o->ctr + 6, o->ctr + 1, sizeof(int), cudaMemcpyDeviceToDevice, s));
     BM_COUNT_LAUNCHES(1), k_sift_orient<<<1024, 32 * SIFT_ORI_WARPS, 0, s>>>(L, o->pyr, o->cand, o->csel, 1, o->nfeatures, o->ctr, o->kpt, o->ksize, o->kangle, o->kresp, o->koct);
     BM_COUNT_LAUNCHES(1), k_sift_select<<<1, 1024, 0, s>>>(o->nfeatures, o->ctr + 1, SIFT_KP_CAP, o->ctr, o->kresp, o->sel, o->ctr + 3, nullptr);
     BM_COUNT_LAUNCHES(1), k_sift_emit<<<1, 1024, 0, s>>>(o->ctr, o->sel, o->kpt, o->ksize, o->kangle, o->kresp, o->koct, *out);
-    BM_COUNT_LAUNCHES(1), k_sift_describe<<<BM_KP_CAP, 256, 0, s>>>(L, o->pyr, *out);
+    BM_COUNT_LAUNCHES(1), k_sift_describe<<<1024, 256, 0, s>>>(L, o->pyr, *out);
+#undef SIFT_OK
     return cudaGetLastError();
+}
+
+// detectAndCompute is a fixed launch sequence per (input buffer, output buffer): it is captured once into a CUDA graph with the
+// fork / join structure above and replayed -- one launch call per frame instead of ~90, and the independent branches overlap.
+cudaError_t bm_sift_detect(BmSift* o, const uint8_t* d_gray, BmKeypoints* out) {
+    if (o->stream == nullptr || !o->graphs_enabled) return sift_enqueue(o, d_gray, out, false);   // legacy stream cannot be captured
+    for (int i = 0; i < o->ngraphs; ++i)
+        if (o->graphs[i].gray == d_gray && o->graphs[i].out_pt == (const void*)out->pt) {
+            BM_COUNT_LAUNCHES(o->graphs[i].launches);
+            return cudaGraphLaunch(o->graphs[i].exec, o->stream);
+        }
+    if (o->ngraphs >= BmSift::kMaxGraphs) return sift_enqueue(o, d_gray, out, true);
+    const long long before = g_bm_launches;
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(o->stream, cudaStreamCaptureModeRelaxed);
+    if (e != cudaSuccess) return e;
+    e = sift_enqueue(o, d_gray, out, true);
+    const cudaError_t e2 = cudaStreamEndCapture(o->stream, &graph);
+    const int launches = (int)(g_bm_launches - before);
+    g_bm_launches = before;                                   // nothing ran during capture
+    cudaGraphExec_t exec = nullptr;
+    if (e == cudaSuccess && e2 == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
+    else if (e == cudaSuccess) e = e2;
+    if (graph) cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {                                    // fall back to plain stream launches from now on
+        cudaGetLastError();
+        o->graphs_enabled = false;
+        return sift_enqueue(o, d_gray, out, false);
+    }
+    SiftGraph& g = o->graphs[o->ngraphs++];
+    g.gray = d_gray; g.out_pt = out->pt; g.exec = exec; g.launches = launches;
+    BM_COUNT_LAUNCHES(launches);
+    return cudaGraphLaunch(exec, o->stream);
 }

@@ -108,15 +108,25 @@ class VideMosaic:
         return self._canvas_cache
 
     # ---- main.py:710-759 -------------------------------------------------------------------------------------
-    def process_frame(self, frame_cur, frame_count=0):
+    def process_frame(self, frame_cur, frame_count=0, next_frame=None):
+        """main.py:710-759.  `next_frame` (optional, not in the reference): the frame of the NEXT call, if the caller already
+        has it -- its H2D copy then overlaps this frame's processing (double-buffered ingest); pass the same array object
+        to the next process_frame call."""
         frame_cur = self._check_frame(frame_cur)
         if frame_cur.shape != self._frame_shape:
             raise ValueError(f"frame shape {frame_cur.shape} != first frame shape {self._frame_shape}")
         self.frame_cur = frame_cur
         self._sync_knobs()
         info = _lib.BmFrameInfo()
-        st = _lib.check(self._lib.bm_process_frame(self._h, frame_cur.ctypes.data_as(C.c_void_p), 0, C.byref(info)),
-                        "bm_process_frame")
+        if next_frame is None:
+            st = _lib.check(self._lib.bm_process_frame(self._h, frame_cur.ctypes.data_as(C.c_void_p), 0, C.byref(info)),
+                            "bm_process_frame")
+        else:
+            next_frame = self._check_frame(next_frame)
+            _lib.check(self._lib.bm_process_frame_begin(self._h, frame_cur.ctypes.data_as(C.c_void_p), 0), "bm_process_frame_begin")
+            _lib.check(self._lib.bm_prefetch_frame(self._h, next_frame.ctypes.data_as(C.c_void_p), 0), "bm_prefetch_frame")
+            self._next_frame_ref = next_frame                      # keep the staged buffer alive / unchanged until it is consumed
+            st = _lib.check(self._lib.bm_process_frame_end(self._h, C.byref(info)), "bm_process_frame_end")
         self.last_info = info
         if st == _lib.BM_SKIP_FEW_MATCHES:
             print(f"Предупреждение: Недостаточно совпадений ({info.n_matches}), пропуск кадра")          # :723
@@ -141,10 +151,16 @@ class VideMosaic:
         self._canvas_cache = None
 
     # ---- device-resident / raw-pointer variants used by bench.py ------------------------------------------------
-    def process_frame_ptr(self, host_ptr):
-        """process_frame on a raw host pointer (e.g. pinned memory): no NumPy checks, no prints.  Returns the status."""
+    def process_frame_ptr(self, host_ptr, next_ptr=None):
+        """process_frame on a raw host pointer (e.g. pinned memory): no NumPy checks, no prints.  Returns the status.
+        next_ptr: host pointer of the next frame, staged (H2D + ingest on the copy stream) while this one is processed."""
         info = _lib.BmFrameInfo()
-        st = _lib.check(self._lib.bm_process_frame(self._h, C.c_void_p(host_ptr), 0, C.byref(info)), "bm_process_frame")
+        if next_ptr is None:
+            st = _lib.check(self._lib.bm_process_frame(self._h, C.c_void_p(host_ptr), 0, C.byref(info)), "bm_process_frame")
+        else:
+            _lib.check(self._lib.bm_process_frame_begin(self._h, C.c_void_p(host_ptr), 0), "bm_process_frame_begin")
+            _lib.check(self._lib.bm_prefetch_frame(self._h, C.c_void_p(next_ptr), 0), "bm_prefetch_frame")
+            st = _lib.check(self._lib.bm_process_frame_end(self._h, C.byref(info)), "bm_process_frame_end")
         self.last_info = info
         self._canvas_cache = None
         return st
@@ -181,6 +197,10 @@ class VideMosaic:
         self.last_info = info
         H = np.array(info.H_rel, dtype=np.float64).reshape(3, 3) if st == _lib.BM_OK else None
         return st, H, info.n_matches
+
+    def set_overlap(self, on):
+        """True (default): the warp/blend chain of frame t overlaps detect/match/RANSAC of frame t+1; False: strictly serial"""
+        _lib.check(self._lib.bm_set_overlap(self._h, 1 if on else 0), "bm_set_overlap")
 
     def clear_canvas(self):
         _lib.check(self._lib.bm_clear_canvas(self._h), "bm_clear_canvas")
