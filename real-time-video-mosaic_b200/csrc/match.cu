@@ -1,7 +1,8 @@
 // match.cu -- VideMosaic.match on the device (reference: main.py:676-698; tie rules: SURVEY.md A.6, oracle/matching.py).
 //   ORB : 256-bit Hamming on CUDA cores (__popc), warp-shuffle arg-min, both directions, mutual-NN filter.
-//   SIFT: exact integer L2 (descriptors are integers 0..255): sum(a-b)^2 = |a|^2+|b|^2-2ab with __dp4a; top-2 per query with
-//         (distance, trainIdx) lexicographic ties; Lowe ratio in double on float32 distances as the reference does.
+//   SIFT: exact integer L2 (descriptors are integers 0..255): sum(a-b)^2 = |a|^2+|b|^2-2ab with the dot products on the tensor
+//         cores (tcgen05 bf16 -> fp32 in TMEM, match_tc.cu); top-2 per query with (distance, trainIdx) lexicographic ties; Lowe
+//         ratio in double on float32 distances as the reference does.
 //   Both: stable sort by distance (the reference's sorted(key=distance)) as an O(m^2) rank count in one block.
 #include "match.cuh"
 #include <string.h>
@@ -13,14 +14,15 @@ int bm_matches_alloc(BmMatches* m) {
               cudaMalloc(&m->src, n * 8) == cudaSuccess && cudaMalloc(&m->dst, n * 8) == cudaSuccess && cudaMalloc(&m->count, 4) == cudaSuccess &&
               cudaMalloc(&m->nn_q2t, n * 4) == cudaSuccess && cudaMalloc(&m->nn_t2q, n * 4) == cudaSuccess && cudaMalloc(&m->tq, n * 4) == cudaSuccess &&
               cudaMalloc(&m->tt, n * 4) == cudaSuccess && cudaMalloc(&m->d_q2t, n * 4) == cudaSuccess && cudaMalloc(&m->d_t2q, n * 4) == cudaSuccess &&
-              cudaMalloc(&m->td, n * 4) == cudaSuccess && cudaMalloc(&m->d2_q2t, n * 4) == cudaSuccess && cudaMalloc(&m->nn2_q2t, n * 4) == cudaSuccess;
+              cudaMalloc(&m->td, n * 4) == cudaSuccess && cudaMalloc(&m->d2_q2t, n * 4) == cudaSuccess && cudaMalloc(&m->nn2_q2t, n * 4) == cudaSuccess &&
+              cudaMalloc(&m->l2_part, n * BM_L2_SPLIT * sizeof(int4)) == cudaSuccess;
     if (ok) cudaMemset(m->count, 0, 4);
     return ok ? 0 : -1;
 }
 void bm_matches_free(BmMatches* m) {
     cudaFree(m->q); cudaFree(m->t); cudaFree(m->dist); cudaFree(m->src); cudaFree(m->dst); cudaFree(m->count); cudaFree(m->nn_q2t);
     cudaFree(m->nn_t2q); cudaFree(m->tq); cudaFree(m->tt); cudaFree(m->d_q2t); cudaFree(m->d_t2q); cudaFree(m->td); cudaFree(m->d2_q2t);
-    cudaFree(m->nn2_q2t);
+    cudaFree(m->nn2_q2t); cudaFree(m->l2_part);
     memset(m, 0, sizeof(*m));
 }
 
@@ -46,57 +48,6 @@ __global__ void __launch_bounds__(256) k_hamming_nn(const uint8_t* __restrict__ 
         if (od < best || (od == best && oi < bi)) { best = od; bi = oi; }
     }
     if (lane == 0) { nn[a] = (nB > 0) ? bi : -1; nd[a] = (float)best; }
-}
-
-// exact integer L2: two nearest rows of B per row of A, ties -> lower index.  Descriptors: u8[128].
-__global__ void __launch_bounds__(256) k_l2_knn2(const uint8_t* __restrict__ A, const int* __restrict__ nAp, const uint8_t* __restrict__ B,
-                                                 const int* __restrict__ nBp, int* __restrict__ nn1, float* __restrict__ d1o,
-                                                 int* __restrict__ nn2, float* __restrict__ d2o) {
-    const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    const int nA = *nAp, nB = *nBp;
-    if (a >= nA) return;
-    unsigned av[32];
-    const uint4* ap = reinterpret_cast<const uint4*>(A + (size_t)a * 128);
-    int na = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const uint4 v = __ldg(ap + i);
-        av[4 * i] = v.x; av[4 * i + 1] = v.y; av[4 * i + 2] = v.z; av[4 * i + 3] = v.w;
-    }
-#pragma unroll
-    for (int i = 0; i < 32; ++i) na = __dp4a(av[i], av[i], (unsigned)na);
-    int b1 = 1 << 30, i1 = 1 << 30, b2 = 1 << 30, i2 = 1 << 30;
-    for (int b = lane; b < nB; b += 32) {
-        const uint4* bp = reinterpret_cast<const uint4*>(B + (size_t)b * 128);
-        unsigned nb = 0, ab = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const uint4 v = __ldg(bp + i);
-            nb = __dp4a(v.x, v.x, nb); nb = __dp4a(v.y, v.y, nb); nb = __dp4a(v.z, v.z, nb); nb = __dp4a(v.w, v.w, nb);
-            ab = __dp4a(av[4 * i], v.x, ab); ab = __dp4a(av[4 * i + 1], v.y, ab); ab = __dp4a(av[4 * i + 2], v.z, ab); ab = __dp4a(av[4 * i + 3], v.w, ab);
-        }
-        const int d = na + (int)nb - 2 * (int)ab;
-        if (d < b1) { b2 = b1; i2 = i1; b1 = d; i1 = b; }
-        else if (d < b2) { b2 = d; i2 = b; }
-    }
-    // merge the per-lane (best, second) pairs: lexicographic (distance, index)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const int ob1 = __shfl_xor_sync(0xffffffffu, b1, o), oi1 = __shfl_xor_sync(0xffffffffu, i1, o);
-        const int ob2 = __shfl_xor_sync(0xffffffffu, b2, o), oi2 = __shfl_xor_sync(0xffffffffu, i2, o);
-        // candidates: (b1,i1) (b2,i2) (ob1,oi1) (ob2,oi2), each pair already ordered
-        const bool o_first = (ob1 < b1) || (ob1 == b1 && oi1 < i1);
-        int n1d, n1i, c1d, c1i, c2d, c2i;
-        if (o_first) { n1d = ob1; n1i = oi1; c1d = b1; c1i = i1; c2d = ob2; c2i = oi2; }
-        else { n1d = b1; n1i = i1; c1d = ob1; c1i = oi1; c2d = b2; c2i = i2; }
-        const bool c2_first = (c2d < c1d) || (c2d == c1d && c2i < c1i);
-        b1 = n1d; i1 = n1i;
-        b2 = c2_first ? c2d : c1d; i2 = c2_first ? c2i : c1i;
-    }
-    if (lane == 0) {
-        nn1[a] = i1 < (1 << 30) ? i1 : -1; nn2[a] = i2 < (1 << 30) ? i2 : -1;
-        d1o[a] = __fsqrt_rn((float)b1); d2o[a] = __fsqrt_rn((float)b2);
-    }
 }
 
 // block-wide ordered compaction helper: returns the exclusive prefix of `flag` over the block and the block total
@@ -158,8 +109,8 @@ cudaError_t bm_match_hamming(const BmKeypoints& cur, const BmKeypoints& prev, Bm
 }
 
 cudaError_t bm_match_l2_ratio(const BmKeypoints& cur, const BmKeypoints& prev, BmMatches& m, double ratio, cudaStream_t s) {
-    const int blocks = (BM_KP_CAP * 32) / 256;
-    BM_COUNT_LAUNCHES(1), k_l2_knn2<<<blocks, 256, 0, s>>>(cur.desc, cur.count, prev.desc, prev.count, m.nn_q2t, m.d_q2t, m.nn2_q2t, m.d2_q2t);
+    cudaError_t e = bm_launch_l2_knn2_tc(cur.desc, cur.count, prev.desc, prev.count, m.l2_part, m.nn_q2t, m.d_q2t, m.nn2_q2t, m.d2_q2t, s);
+    if (e != cudaSuccess) return e;
     BM_COUNT_LAUNCHES(1), k_select_sort<<<1, 1024, 0, s>>>(1, ratio, cur.count, prev.count, m, cur.pt, prev.pt);
     return cudaGetLastError();
 }

@@ -337,6 +337,38 @@ struct RfShared {
     double sums[46];
 };
 
+// Gauss-Jordan elimination WITHOUT pivoting of a symmetric positive definite NxN system M[r][0..N) | M[r][N] by one warp: every
+// lane owns up to three of the N*(N+1) augmented entries and all rows are eliminated at once, so a pivot step costs one
+// round of shared-memory reads instead of a serial loop over the rows (the stage-2 systems -- LtL + shift*I of the inverse
+// iteration, JtJ + lambda*diag of Levenberg-Marquardt -- are SPD, for which elimination without pivoting is as stable as
+// Cholesky).  Solution in X[0..N).  Returns false on a non-positive / non-finite pivot.
+__device__ __noinline__ bool warp_solve_spd(double (*M)[10], double* X, int N) {
+    const int lane = threadIdx.x & 31;
+    const int ne = N * (N + 1);
+    int er[3], ek[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { const int e = lane + 32 * j; er[j] = e < ne ? e / (N + 1) : -1; ek[j] = e < ne ? e - er[j] * (N + 1) : 0; }
+    bool ok = true;
+    for (int c = 0; c < N; ++c) {
+        const double piv = M[c][c];
+        if (!(piv > 0.0) || !isfinite(piv)) ok = false;
+        const double inv = __drcp_rn(piv);
+        double nv[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            nv[j] = 0.0;
+            if (er[j] >= 0 && er[j] != c && ek[j] > c) nv[j] = M[er[j]][ek[j]] - (M[er[j]][c] * inv) * M[c][ek[j]];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 3; ++j) if (er[j] >= 0 && er[j] != c && ek[j] > c) M[er[j]][ek[j]] = nv[j];
+        __syncwarp();
+    }
+    if (lane < N) X[lane] = M[lane][N] / M[lane][lane];
+    __syncwarp();
+    return ok;
+}
+
 template <int NV>
 __device__ __forceinline__ void warp_sum(RfShared& sh, const double (&v)[NV]) {
     const int lane = threadIdx.x & 31;
@@ -459,7 +491,7 @@ __global__ void __launch_bounds__(32, 1) k_ransac_refine(const float2* __restric
                 sh.M[lane][9] = sh.V[lane];
             }
             __syncwarp();
-            warp_solve(sh.M, sh.X, sh.P, 9, 0.0);
+            warp_solve_spd(sh.M, sh.X, 9);
             double nrm = 0, dot = 0;
             for (int k = 0; k < 9; ++k) { nrm += sh.X[k] * sh.X[k]; dot += sh.X[k] * sh.V[k]; }
             const double inv = rsqrt(nrm) * (dot < 0 ? -1.0 : 1.0);
@@ -515,7 +547,7 @@ __global__ void __launch_bounds__(32, 1) k_ransac_refine(const float2* __restric
             sh.M[lane][8] = sh.lmv[lane];
         }
         __syncwarp();
-        const bool ok = warp_solve(sh.M, sh.X, sh.P, 8, 0.0);
+        const bool ok = warp_solve_spd(sh.M, sh.X, 8);
         if (lane < 8) { const double d = ok ? sh.X[lane] : 0.0; sh.lmd[lane] = d; sh.lmxd[lane] = sh.lmx[lane] - d; }
         __syncwarp();
         rf_accumulate(sh, src, dst, mask, n, sh.lmxd, false);
@@ -540,7 +572,7 @@ __global__ void __launch_bounds__(32, 1) k_ransac_refine(const float2* __restric
                         sh.M[lane][8] = (lane == c) ? 1.0 : 0.0;
                     }
                     __syncwarp();
-                    if (warp_solve(sh.M, sh.X, sh.P, 8, 0.0)) maxval = fmax(maxval, fabs(sh.X[c]));
+                    if (warp_solve_spd(sh.M, sh.X, 8)) maxval = fmax(maxval, fabs(sh.X[c]));
                     __syncwarp();
                 }
                 lambda = lc = 1.0 / maxval;

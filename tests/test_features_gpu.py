@@ -89,6 +89,19 @@ def test_l2_ratio_exact(ops, golden_dir):
     assert np.array_equal(ops.match_l2_ratio(s["des0"], s["des1"]), omt.match_l2_ratio(s["des0"], s["des1"]))
 
 
+@pytest.mark.parametrize("nq,nt", [(1, 2), (5, 3), (127, 255), (128, 256), (129, 257), (700, 701), (1500, 900), (300, 2)])
+def test_l2_ratio_tensor_core_tiles_and_ties(ops, nq, nt):
+    """tcgen05 matcher (match_tc.cu): query tiles of 128, train tiles of 256, ragged edges, exact duplicates (distance ties must
+    go to the lower train index) and the k=2 corner cases -- bit-exact against the oracle's stable argsort."""
+    rng = np.random.default_rng(nq * 1000 + nt)
+    base = rng.integers(0, 60, (max(nt // 3, 1), 128))
+    t = base[rng.integers(0, len(base), nt)] + (rng.random((nt, 128)) < 0.02) * rng.integers(0, 196, (nt, 128))
+    q = t[rng.integers(0, nt, nq)] + (rng.random((nq, 128)) < 0.05) * rng.integers(0, 60, (nq, 128))
+    q = np.clip(q, 0, 255).astype(np.float32); t = np.clip(t, 0, 255).astype(np.float32)
+    for ratio in (0.7, 1.01):
+        assert np.array_equal(ops.match_l2_ratio(q, t, ratio), omt.match_l2_ratio(q, t, ratio))
+
+
 def _reproj(Ha, Hb, w, h):
     ys, xs = np.mgrid[0:h:16, 0:w:16]
     p = np.stack([xs.ravel(), ys.ravel(), np.ones(xs.size)])
