@@ -106,6 +106,8 @@ bm_status bm_free_pinned(void* p);
 /* VideMosaic.warp(frame, H) on the handle's canvas (main.py:861-927): warpPerspective + blend, device canvas. */
 bm_status bm_warp_frame(bm_handle h, const uint8_t* h_bgr, size_t stride_bytes, const double H[9], bm_frame_info* info);
 /* same with the frame already resident on the device as packed BGRX (uchar4); used by the kernel-only bench leg */
+/* same as bm_warp_frame but only enqueues (no any_overlap read-back, no wait): canvas-tile mode warps many frames back to back */
+bm_status bm_warp_frame_async(bm_handle h, const uint8_t* h_bgr, size_t stride_bytes, const double H[9]);
 bm_status bm_warp_frame_device(bm_handle h, const uint8_t* d_bgrx, const double H[9], bm_frame_info* info);
 /* timing helpers: last warp/blend chain duration measured with CUDA events on the handle's stream (ms) */
 bm_status bm_sync(bm_handle h);

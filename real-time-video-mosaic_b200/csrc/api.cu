@@ -282,6 +282,14 @@ extern "C" bm_status bm_warp_frame(bm_handle m, const uint8_t* h_bgr, size_t str
     return warp_device(m, m->d_bgrx[m->cur], H, info, true, m->cur);
 }
 
+extern "C" bm_status bm_warp_frame_async(bm_handle m, const uint8_t* h_bgr, size_t stride, const double H[9]) {
+    if (!m || !h_bgr || !H) { bm_set_error("bm_warp_frame_async: null"); return BM_ERR_ARG; }
+    BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+    m->cur ^= 1;
+    BM_TRY(stage_frame(m, h_bgr, stride, m->cur, m->s_chain));
+    return warp_device(m, m->d_bgrx[m->cur], H, nullptr, false, m->cur);
+}
+
 extern "C" bm_status bm_warp_frame_device(bm_handle m, const uint8_t* d_bgrx, const double H[9], bm_frame_info* info) {
     if (!m || !d_bgrx || !H) { bm_set_error("bm_warp_frame_device: null"); return BM_ERR_ARG; }
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));

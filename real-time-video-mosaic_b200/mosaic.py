@@ -335,6 +335,14 @@ class VideMosaic:
             cv2.imshow('output', tmp / 255.)
         return self.output_img
 
+    def warp_nosync(self, frame_cur, H):
+        """warp(frame, H) without the display tail and without waiting for the device (canvas-tile mode)"""
+        frame_cur = self._check_frame(frame_cur)
+        _a, hp = _lib.dbl9(H)
+        self._keep = frame_cur                                     # pageable frames are staged synchronously; keep pinned ones alive
+        _lib.check(self._lib.bm_warp_frame_async(self._h, frame_cur.ctypes.data_as(C.c_void_p), 0, hp), "bm_warp_frame_async")
+        self._canvas_cache = None
+
     @staticmethod
     def get_transformed_corners(frame_cur, H):                     # main.py:938-962 (4 points, host)
         h, w = frame_cur.shape[:2]

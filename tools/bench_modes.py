@@ -1,0 +1,174 @@
+#!/usr/bin/env python
+"""Sharded modes of the stitching path (SURVEY.md 8e / BASELINE.json configs 3-5) -- one JSON line per run.
+
+    python tools/bench_modes.py --mode streams [--streams 64] [--frames 16] [--size 1280x720] [--detector orb]
+    python tools/bench_modes.py --mode pairs   [--frames 64] [--size 1920x1080] [--detector sift]
+    python tools/bench_modes.py --mode tiles   [--frames 48] [--size 3840x2160] [--canvas 16384x16384]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/bench_modes.py --mode ...
+
+streams : independent streams, stream s -> rank s % N, no data-path collective (config 4).  All streams of a rank are advanced
+          together: bm_process_frame_begin on every handle, then bm_process_frame_end on every handle, so their kernels overlap.
+pairs   : offline frame-pair sharding (config 3 at N GPUs): contiguous chunks of pairs per rank (1-frame halo), per-pair
+          detect / match / RANSAC on the device, ONE all_gather of the 3x3 relative homographies (72 B per pair), then the
+          reference's sequential validate / smooth / prefix composition on every rank.
+tiles   : canvas row tiles (config 5): rank g owns rows [g*Hc/N, (g+1)*Hc/N) and warps + blends every frame whose window touches
+          its tile (homographies known: the sweep's ground truth), tiles gathered with one NCCL all_gather at the end.
+Timing: barrier + synchronize on both sides, max over ranks; frames are synthetic (b200mosaic.synth).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+import cv2
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mode", required=True, choices=["streams", "pairs", "tiles"])
+    ap.add_argument("--streams", type=int, default=64)
+    ap.add_argument("--frames", type=int, default=16, help="timed frames (per stream / in total)")
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--size", default=None)
+    ap.add_argument("--canvas", default="16384x16384")
+    ap.add_argument("--detector", default=None)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    import b200mosaic
+    from b200mosaic import sharding as sh
+    from b200mosaic.synth import DroneSweep, make_ground
+    if not torch.cuda.is_available():
+        raise SystemExit("needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    out = {"mode": args.mode, "n_gpus": world, "data": "synthetic", "higher_is_better": True, "scaling": "weak" if args.mode == "streams" else "strong"}
+    if args.mode == "streams":
+        w, h = map(int, (args.size or "1280x720").split("x"))
+        det = args.detector or "orb"
+        n = args.frames + args.warmup + 1
+        ground = make_ground(4096, 2000)
+        nseq = 8                                                 # distinct sweeps; stream s replays sweep s % 8 (content is irrelevant for throughput)
+        seqs = [torch.from_numpy(np.stack(DroneSweep(w, h, seed=2000 + q, ground=ground, max_step=10.0, max_travel=0.6 * h).frames(n))).pin_memory()
+                for q in range(nseq)]
+        fb = h * w * 3
+        mine = sh.shard_streams(args.streams, rank, world)
+        vms = [b200mosaic.VideMosaic(seqs[s % nseq][0].numpy(), detector_type=det, show_intermediate=False, visualize=False, device=local) for s in mine]
+        def step(i):
+            for vm, s in zip(vms, mine):
+                vm.begin_frame_ptr(seqs[s % nseq].data_ptr() + i * fb)
+            return [vm.end_frame() for vm in vms]
+        for i in range(1, args.warmup + 1):
+            step(i)
+        for vm in vms:
+            vm.sync()
+        barrier()
+        t0 = time.perf_counter()
+        ok = 0
+        for i in range(args.warmup + 1, n):
+            ok += sum(1 for st in step(i) if st == 0)
+        for vm in vms:
+            vm.sync()
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        total = args.streams * args.frames
+        out.update({"metric": f"aggregate mosaic frames/sec over {args.streams} concurrent {w}x{h} {det.upper()} streams", "value": total / dt,
+                    "unit": "frames/s", "ms_per_step": 1e3 * dt / args.frames, "steps": args.frames, "warmup": args.warmup,
+                    "config": {"workload": f"{args.streams} streams x {args.frames} frames, {w}x{h}, detector={det}, stream s -> rank s % {world}, "
+                                           f"{len(mine)} streams on rank 0, begin/end interleaved", "frames_ok_rank0": ok}})
+    elif args.mode == "pairs":
+        w, h = map(int, (args.size or "1920x1080").split("x"))
+        det = args.detector or "sift"
+        n = args.frames + 1
+        frames = DroneSweep(w, h, seed=1234, ground_size=4096, max_step=12.0, max_travel=0.8 * h).frames(n)
+        s, e = sh.shard_pairs(n, rank, world)
+        # warm-up on the first pair of the chunk (graph capture, allocations)
+        if e > s:
+            sh.estimate_pairs(frames, s, min(s + 2, e), detector_type=det, device=local)
+        barrier()
+        t0 = time.perf_counter()
+        st, Hs = sh.estimate_pairs(frames, s, e, detector_type=det, device=local)
+        rows = sh.all_gather_pairs(sh.pack_pairs(st, Hs), n, rank, world, dist, device="cuda")
+        rel = sh.unpack_pairs(rows)
+        H0 = np.eye(3); H0[0, 2] = int(1.2 * w) / 2 - w / 2; H0[1, 2] = int(2 * h) - h
+        Habs = sh.compose_chain(H0, rel)
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        out.update({"metric": f"frame pairs/sec (detect + match + RANSAC, {det.upper()}, {w}x{h}) sharded over ranks + all_gather + prefix composition",
+                    "value": (n - 1) / dt, "unit": "pairs/s", "ms_per_step": 1e3 * dt / (n - 1), "steps": n - 1, "warmup": 1,
+                    "config": {"workload": f"{n} frames, pairs [{s},{e}) on rank 0 of {world}", "pairs_ok": int(sum(1 for r in rel if r is not None)),
+                               "composed": int(sum(1 for H in Habs if H is not None))}})
+    else:
+        w, h = map(int, (args.size or "3840x2160").split("x"))
+        Wc, Hc = map(int, args.canvas.split("x"))
+        n = args.frames + args.warmup + 1
+        ground = make_ground(4096, 77)
+        nseq = min(n, 12)                                        # frame CONTENT is recycled (irrelevant for throughput); poses are not
+        base = DroneSweep(w, h, seed=77, ground=cv2.resize(ground, (2 * 4096, 2 * 4096)) if max(w, h) > 3000 else ground, max_step=40.0,
+                          noise_sigma=2.0).frames(nseq)
+        frames = [base[t % nseq] for t in range(n)]
+        y0, y1 = sh.tile_rows(Hc, rank, world)
+        # the camera climbs the whole canvas in n frames (so every row tile gets work), with a slow sideways weave and rotation
+        Hs = []
+        for t in range(n):
+            ang = np.deg2rad(2.0 * np.sin(t / 7.0))
+            R = np.array([[np.cos(ang), -np.sin(ang), 0.0], [np.sin(ang), np.cos(ang), 0.0], [0.0, 0.0, 1.0]])
+            T = np.eye(3); T[0, 2] = Wc / 2 - w / 2 + 0.05 * Wc * np.sin(t / 5.0); T[1, 2] = (Hc - h - 8) * (1.0 - t / max(n - 1, 1)) + 4
+            Hs.append(T @ R)
+        vm = b200mosaic.VideMosaic(frames[0], detector_type="orb", show_intermediate=False, visualize=False, canvas_size=(y1 - y0, Wc), device=local)
+        vm.clear_canvas()
+        def put(t):
+            if sh.touches_tile(Hs[t], w, h, y0, y1):
+                vm.warp_nosync(frames[t], sh.tile_homography(Hs[t], y0))
+                return 1
+            return 0
+        for t in range(0, args.warmup + 1):
+            put(t)
+        vm.sync()
+        barrier()
+        t0 = time.perf_counter()
+        mine = sum(put(t) for t in range(args.warmup + 1, n))
+        tile = torch.empty((y1 - y0, Wc, 3), dtype=torch.uint8, device="cuda")
+        vm.canvas_to_device(tile.data_ptr())
+        torch.cuda.synchronize()
+        t_warp = max_over_ranks(time.perf_counter() - t0)
+        full = sh.gather_tiles(tile, Hc, rank, world, dist)
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        out.update({"metric": f"frames/sec warped + blended into a {Wc}x{Hc} canvas sharded in {world} row tiles, incl. the final NCCL all_gather",
+                    "value": args.frames / dt, "unit": "frames/s", "ms_per_step": 1e3 * dt / args.frames, "steps": args.frames, "warmup": args.warmup,
+                    "config": {"workload": f"{w}x{h} frames, tile rows [{y0},{y1}) on rank 0, {mine} of {args.frames} frames touch it",
+                               "gather_ms": 1e3 * (dt - t_warp), "canvas_bytes": int(full.numel())}})
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
