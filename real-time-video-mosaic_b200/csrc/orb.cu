@@ -62,80 +62,145 @@ __device__ __forceinline__ bool tile_xy(const BmOrbLevel& L, int& x, int& y) {
     return ty * 8 < L.h;
 }
 
-__global__ void __launch_bounds__(256) k_fast_score(BmOrbLevels lv, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ score) {
-    const BmOrbLevel L = lv.l[blockIdx.y];
-    int x, y;
-    if (!tile_xy(L, x, y)) return;
-    if (x >= L.w || y >= L.h) return;
-    const uint8_t* img = pyr + L.off;
-    int s = 0;
-    if (x >= 3 && y >= 3 && x < L.w - 3 && y < L.h - 3) {
-        const uint8_t* p = img + (size_t)y * L.w + x;
-        const int w = L.w;
-        const int c = p[0];
-        int d[16];
-        d[0] = c - p[3 * w];          d[1] = c - p[3 * w + 1];   d[2] = c - p[2 * w + 2];   d[3] = c - p[w + 3];
-        d[4] = c - p[3];              d[5] = c - p[-w + 3];      d[6] = c - p[-2 * w + 2];  d[7] = c - p[-3 * w + 1];
-        d[8] = c - p[-3 * w];         d[9] = c - p[-3 * w - 1];  d[10] = c - p[-2 * w - 2]; d[11] = c - p[-w - 3];
-        d[12] = c - p[-3];            d[13] = c - p[w - 3];      d[14] = c - p[2 * w - 2];  d[15] = c - p[3 * w - 1];
-        unsigned P = 0, N = 0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) { P |= (unsigned)(d[i] > FAST_THR) << i; N |= (unsigned)(d[i] < -FAST_THR) << i; }
-        if (has9(P) || has9(N)) {
-            // cornerScore<16>: max over the 16 arcs of min(d) and of min(-d), minus 1 (window minima / maxima by doubling)
-            int lo2[16], hi2[16], lo4[16], hi4[16], lo8[16], hi8[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) { lo2[i] = min(d[i], d[(i + 1) & 15]); hi2[i] = max(d[i], d[(i + 1) & 15]); }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) { lo4[i] = min(lo2[i], lo2[(i + 2) & 15]); hi4[i] = max(hi2[i], hi2[(i + 2) & 15]); }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) { lo8[i] = min(lo4[i], lo4[(i + 4) & 15]); hi8[i] = max(hi4[i], hi4[(i + 4) & 15]); }
-            int amax = -100000, bmin = 100000;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                amax = max(amax, min(lo8[i], d[(i + 8) & 15]));
-                bmin = min(bmin, max(hi8[i], d[(i + 8) & 15]));
-            }
-            int best = FAST_THR;
-            if (amax > best) best = amax;
-            if (0 - bmin > best) best = 0 - bmin;
-            s = best - 1;
-        }
-    }
-    score[L.off + (size_t)y * L.w + x] = (uint8_t)s;
+// FAST-9/16 in three dense passes (a per-pixel score + NMS pass spends most of its time in the divergent score branch and in
+// contended histogram atomics):
+//   k_fast_detect : one thread per pixel: 16 ring differences as two bit masks, 9-contiguous-arc test; corners are compacted
+//                   (ballot / popc) into a per-level list, the score map is zeroed
+//   k_fast_cscore : one thread per corner: cornerScore<16> (window minima / maxima by doubling) -> score map
+//   k_fast_cnms   : one thread per corner: 3x3 non-maximum suppression on the score map, border filter, candidate list and a
+//                   per-CTA shared-memory score histogram (for retainBest(2 * quota))
+__device__ __forceinline__ void fast_ring(const uint8_t* __restrict__ p, int w, int (&d)[16]) {
+    const int c = p[0];
+    d[0] = c - p[3 * w];          d[1] = c - p[3 * w + 1];   d[2] = c - p[2 * w + 2];   d[3] = c - p[w + 3];
+    d[4] = c - p[3];              d[5] = c - p[-w + 3];      d[6] = c - p[-2 * w + 2];  d[7] = c - p[-3 * w + 1];
+    d[8] = c - p[-3 * w];         d[9] = c - p[-3 * w - 1];  d[10] = c - p[-2 * w - 2]; d[11] = c - p[-w - 3];
+    d[12] = c - p[-3];            d[13] = c - p[w - 3];      d[14] = c - p[2 * w - 2];  d[15] = c - p[3 * w - 1];
 }
 
-// NMS + border filter + histogram + per-warp compaction (ballot / popc)
-__global__ void __launch_bounds__(256) k_fast_nms(BmOrbLevels lv, const uint8_t* __restrict__ score, uint2* __restrict__ cand,
-                                                  int* __restrict__ ctr, int* __restrict__ hist) {
+// tile = 32 x 32 pixels per CTA (4 rows per thread: a CTA with one pixel per thread costs more to schedule than to run);
+// blockIdx.x enumerates the tiles of all levels back to back
+__device__ __forceinline__ bool fast_tile(const BmOrbLevels& lv, int& level, int& x0, int& y0) {
+    int t = blockIdx.x;
+    for (level = 0; level < BM_ORB_LEVELS; ++level) {
+        const int tx = (lv.l[level].w + 31) >> 5, ty = (lv.l[level].h + 31) >> 5;
+        if (t < tx * ty) { x0 = (t % tx) * 32; y0 = (t / tx) * 32; return true; }
+        t -= tx * ty;
+    }
+    return false;
+}
+static int fast_total_tiles(const BmOrbLevels& lv) {
+    int n = 0;
+    for (int l = 0; l < BM_ORB_LEVELS; ++l) n += ((lv.l[l].w + 31) >> 5) * ((lv.l[l].h + 31) >> 5);
+    return n;
+}
+
+__global__ void __launch_bounds__(256) k_fast_detect(BmOrbLevels lv, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ score,
+                                                     unsigned* __restrict__ corners, int* __restrict__ ctr) {
+    int level, x0, y0;
+    if (!fast_tile(lv, level, x0, y0)) return;
+    const BmOrbLevel L = lv.l[level];
+    const int x = x0 + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int y = y0 + threadIdx.y + 8 * k;
+        bool corner = false;
+        if (x < L.w && y < L.h) {
+            if (x >= 3 && y >= 3 && x < L.w - 3 && y < L.h - 3) {
+                int d[16];
+                fast_ring(pyr + L.off + (size_t)y * L.w + x, L.w, d);
+                unsigned P = 0, N = 0;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { P |= (unsigned)(d[i] > FAST_THR) << i; N |= (unsigned)(d[i] < -FAST_THR) << i; }
+                corner = has9(P) || has9(N);
+            }
+            score[L.off + (size_t)y * L.w + x] = 0;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, corner);
+        if (bal) {
+            const int lane = threadIdx.x & 31, leader = __ffs(bal) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&ctr[40 + level], __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (corner) {
+                const int idx = base + __popc(bal & ((1u << lane) - 1u));
+                if (idx < (L.w * L.h) / 2) corners[L.off / 2 + idx] = (unsigned)x | ((unsigned)y << 16);
+                else ctr[32] = 1;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_fast_cscore(BmOrbLevels lv, const uint8_t* __restrict__ pyr, const unsigned* __restrict__ corners,
+                                                     const int* __restrict__ ctr, uint8_t* __restrict__ score) {
     const int level = blockIdx.y;
     const BmOrbLevel L = lv.l[level];
-    int x, y;
-    if (!tile_xy(L, x, y)) return;
+    const int n = min(ctr[40 + level], (L.w * L.h) / 2);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {      // fixed grid, strided: few, busy CTAs
+    const unsigned xy = corners[L.off / 2 + i];
+    const int x = xy & 0xffff, y = xy >> 16;
+    int d[16];
+    fast_ring(pyr + L.off + (size_t)y * L.w + x, L.w, d);
+    // cornerScore<16>: max over the 16 arcs of min(d) and of min(-d), minus 1
+    int lo2[16], hi2[16], lo4[16], hi4[16], lo8[16], hi8[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { lo2[k] = min(d[k], d[(k + 1) & 15]); hi2[k] = max(d[k], d[(k + 1) & 15]); }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { lo4[k] = min(lo2[k], lo2[(k + 2) & 15]); hi4[k] = max(hi2[k], hi2[(k + 2) & 15]); }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { lo8[k] = min(lo4[k], lo4[(k + 4) & 15]); hi8[k] = max(hi4[k], hi4[(k + 4) & 15]); }
+    int amax = -100000, bmin = 100000;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        amax = max(amax, min(lo8[k], d[(k + 8) & 15]));
+        bmin = min(bmin, max(hi8[k], d[(k + 8) & 15]));
+    }
+    int best = FAST_THR;
+    if (amax > best) best = amax;
+    if (0 - bmin > best) best = 0 - bmin;
+    score[L.off + (size_t)y * L.w + x] = (uint8_t)(best - 1);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_fast_cnms(BmOrbLevels lv, const uint8_t* __restrict__ score, const unsigned* __restrict__ corners,
+                                                   uint2* __restrict__ cand, int* __restrict__ ctr, int* __restrict__ hist) {
+    __shared__ int sh[256];
+    const int level = blockIdx.y;
+    const BmOrbLevel L = lv.l[level];
+    const int n = min(ctr[40 + level], (L.w * L.h) / 2);
+    if ((int)(blockIdx.x * blockDim.x) >= n) return;
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+  for (int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {                 // CTA-uniform trip count
+    const int i = i0 + threadIdx.x;
     bool keep = false;
-    int s = 0;
-    if (x >= ORB_EDGE && y >= ORB_EDGE && x < L.w - ORB_EDGE && y < L.h - ORB_EDGE) {
-        const uint8_t* p = score + L.off + (size_t)y * L.w + x;
-        const int w = L.w;
-        s = p[0];
-        keep = s > 0 && s > p[-1] && s > p[1] && s > p[-w - 1] && s > p[-w] && s > p[-w + 1] && s > p[w - 1] && s > p[w] && s > p[w + 1];
+    int x = 0, y = 0, sc = 0;
+    if (i < n) {
+        const unsigned xy = corners[L.off / 2 + i];
+        x = xy & 0xffff; y = xy >> 16;
+        if (x >= ORB_EDGE && y >= ORB_EDGE && x < L.w - ORB_EDGE && y < L.h - ORB_EDGE) {
+            const uint8_t* p = score + L.off + (size_t)y * L.w + x;
+            const int w = L.w;
+            sc = p[0];
+            keep = sc > 0 && sc > p[-1] && sc > p[1] && sc > p[-w - 1] && sc > p[-w] && sc > p[-w + 1] && sc > p[w - 1] && sc > p[w] && sc > p[w + 1];
+        }
     }
     const unsigned bal = __ballot_sync(0xffffffffu, keep);
     if (bal) {
-        const int lane = threadIdx.x & 31;
-        const int leader = __ffs(bal) - 1;
+        const int lane = threadIdx.x & 31, leader = __ffs(bal) - 1;
         int base = 0;
         if (lane == leader) base = atomicAdd(&ctr[level], __popc(bal));
         base = __shfl_sync(0xffffffffu, base, leader);
         if (keep) {
             const int idx = base + __popc(bal & ((1u << lane) - 1u));
-            if (idx < L.cand_cap) cand[L.cand_off + idx] = make_uint2((unsigned)x | ((unsigned)y << 16), (unsigned)s);
-            atomicAdd(&hist[level * 256 + s], 1);
+            if (idx < L.cand_cap) cand[L.cand_off + idx] = make_uint2((unsigned)x | ((unsigned)y << 16), (unsigned)sc);
+            atomicAdd(&sh[sc], 1);
         }
     }
+  }
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(&hist[level * 256 + threadIdx.x], sh[threadIdx.x]);
 }
 
-// retainBest(2*quota) threshold on the integer FAST scores: thr = the n-th largest score (ties are all kept)
 __global__ void k_fast_threshold(BmOrbLevels lv, int* __restrict__ ctr, const int* __restrict__ hist) {
     const int level = threadIdx.x;
     if (level >= BM_ORB_LEVELS) return;
@@ -421,14 +486,15 @@ int bm_orb_create(BmOrb** out, int h, int w, int nfeatures, cudaStream_t s) {
               cudaMalloc(&o->cand, (size_t)o->lv.total_cand * sizeof(uint2)) == cudaSuccess &&
               cudaMalloc(&o->cand2, (size_t)o->lv.total_cand * sizeof(uint2)) == cudaSuccess &&
               cudaMalloc(&o->keep, o->lv.total_cand) == cudaSuccess && cudaMalloc(&o->ctr, 64 * sizeof(int)) == cudaSuccess &&
-              cudaMalloc(&o->hist, BM_ORB_LEVELS * 256 * sizeof(int)) == cudaSuccess;
+              cudaMalloc(&o->hist, BM_ORB_LEVELS * 256 * sizeof(int)) == cudaSuccess &&
+              cudaMalloc(&o->corners, ((size_t)o->lv.total_px / 2 + 64) * sizeof(unsigned)) == cudaSuccess;
     if (!ok) { bm_orb_destroy(o); return -1; }
     *out = o;
     return 0;
 }
 void bm_orb_destroy(BmOrb* o) {
     if (!o) return;
-    cudaFree(o->pyr); cudaFree(o->score); cudaFree(o->cand); cudaFree(o->cand2); cudaFree(o->keep); cudaFree(o->ctr); cudaFree(o->hist);
+    cudaFree(o->pyr); cudaFree(o->score); cudaFree(o->cand); cudaFree(o->cand2); cudaFree(o->keep); cudaFree(o->ctr); cudaFree(o->hist); cudaFree(o->corners);
     delete o;
 }
 
@@ -445,8 +511,10 @@ cudaError_t bm_orb_detect(BmOrb* o, const uint8_t* d_gray, BmKeypoints* out) {
         BM_COUNT_LAUNCHES(1), k_resize_exact<<<dim3((L.w + 31) / 32, (L.h + 7) / 8), blk, 0, s>>>(o->pyr + P.off, P.w, P.h, o->pyr + L.off, L.w, L.h);
     }
     const int tiles0 = ((lv.l[0].w + 31) / 32) * ((lv.l[0].h + 7) / 8);
-    BM_COUNT_LAUNCHES(1), k_fast_score<<<dim3(tiles0, BM_ORB_LEVELS), blk, 0, s>>>(lv, o->pyr, o->score);
-    BM_COUNT_LAUNCHES(1), k_fast_nms<<<dim3(tiles0, BM_ORB_LEVELS), blk, 0, s>>>(lv, o->score, o->cand, o->ctr, o->hist);
+    const int cblocks = 148;                               // per level; the per-corner kernels stride over the corner lists
+    BM_COUNT_LAUNCHES(1), k_fast_detect<<<fast_total_tiles(lv), blk, 0, s>>>(lv, o->pyr, o->score, o->corners, o->ctr);
+    BM_COUNT_LAUNCHES(1), k_fast_cscore<<<dim3(cblocks, BM_ORB_LEVELS), 256, 0, s>>>(lv, o->pyr, o->corners, o->ctr, o->score);
+    BM_COUNT_LAUNCHES(1), k_fast_cnms<<<dim3(cblocks, BM_ORB_LEVELS), 256, 0, s>>>(lv, o->score, o->corners, o->cand, o->ctr, o->hist);
     BM_COUNT_LAUNCHES(1), k_fast_threshold<<<1, 32, 0, s>>>(lv, o->ctr, o->hist);
     BM_COUNT_LAUNCHES(1), k_harris<<<(lv.total_cand + 255) / 256, 256, 0, s>>>(lv, o->pyr, o->cand, o->cand2, o->ctr);
     BM_COUNT_LAUNCHES(1), k_harris_select<<<BM_ORB_LEVELS, 1024, 0, s>>>(lv, o->cand2, o->ctr, o->keep);

@@ -33,7 +33,8 @@ struct BmOrb {
     BmOrbLevels lv;
     uint8_t *pyr, *blur, *score;
     uint2 *cand, *cand2;
-    int* ctr;           // device counters: [0..7] cnt1, [8..15] cnt2, [16..23] thr, [24..31] kept, [32] overflow flag
+    unsigned* corners;  // FAST corners before NMS, x | y << 16; level l owns [off_l / 2, off_l / 2 + w_l * h_l / 2)
+    int* ctr;           // device counters: [0..7] cnt1, [8..15] cnt2, [16..23] thr, [24..31] kept, [32] overflow flag, [40..47] FAST corners
     int* hist;          // [8][256]
     uint8_t* keep;      // keep flags for cand2
     cudaStream_t stream;

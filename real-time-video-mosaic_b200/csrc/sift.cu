@@ -70,17 +70,24 @@ static const int h_sift_ksize[6] = {11, 11, 13, 17, 21, 27};
 // 2x bilinear upsample of the gray image to float (cv2.resize INTER_LINEAR: weights .25/.75, edge replicate; exact)
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_sift_upsample(const uint8_t* __restrict__ gray, int w, int h, float* __restrict__ up) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int W = 2 * w, H = 2 * h;
-    if (x >= W || y >= H) return;
+    if (x >= W) return;
     // fx = x/2 - 0.25: even x -> (.25, .75) on (k-1, k); odd x -> (.75, .25) on (k, k+1)
-    const int kx = x >> 1, ky = y >> 1;
-    int x0, x1, y0, y1; float ax, ay;      // weight of the SECOND tap
+    const int kx = x >> 1;
+    int x0, x1; float ax;      // weight of the SECOND tap
     if (x & 1) { x0 = kx; x1 = min(kx + 1, w - 1); ax = 0.25f; } else { x0 = max(kx - 1, 0); x1 = kx; ax = 0.75f; }
-    if (y & 1) { y0 = ky; y1 = min(ky + 1, h - 1); ay = 0.25f; } else { y0 = max(ky - 1, 0); y1 = ky; ay = 0.75f; }
-    const float r0 = (float)gray[(size_t)y0 * w + x0] * (1.f - ax) + (float)gray[(size_t)y0 * w + x1] * ax;
-    const float r1 = (float)gray[(size_t)y1 * w + x0] * (1.f - ax) + (float)gray[(size_t)y1 * w + x1] * ax;
-    up[(size_t)y * W + x] = r0 * (1.f - ay) + r1 * ay;
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {                      // 4 rows per thread (32 x 32 pixels per CTA)
+        const int y = blockIdx.y * 32 + threadIdx.y + 8 * rr;
+        if (y >= H) break;
+        const int ky = y >> 1;
+        int y0, y1; float ay;
+        if (y & 1) { y0 = ky; y1 = min(ky + 1, h - 1); ay = 0.25f; } else { y0 = max(ky - 1, 0); y1 = ky; ay = 0.75f; }
+        const float r0 = (float)gray[(size_t)y0 * w + x0] * (1.f - ax) + (float)gray[(size_t)y0 * w + x1] * ax;
+        const float r1 = (float)gray[(size_t)y1 * w + x0] * (1.f - ax) + (float)gray[(size_t)y1 * w + x1] * ax;
+        up[(size_t)y * W + x] = r0 * (1.f - ay) + r1 * ay;
+    }
 }
 
 __device__ __forceinline__ int refl101(int i, int n) {
@@ -260,8 +267,10 @@ __device__ __forceinline__ bool sift_is_extremum(const float* __restrict__ prv, 
 __global__ void __launch_bounds__(256) k_sift_extrema(SiftLayout lay, int o, const float* __restrict__ pyr, unsigned* __restrict__ raw,
                                                       int* __restrict__ ctr) {
     const SiftOct O = lay.o[o];
-    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y * blockDim.y + threadIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int w = O.w, h = O.h;
+  {
+    const int r = blockIdx.y * 8 + threadIdx.y;
     const bool inside = c >= SIFT_BORDER && c < w - SIFT_BORDER && r >= SIFT_BORDER && r < h - SIFT_BORDER;
     const size_t p = (size_t)r * w + c;
     float d[5];
@@ -286,6 +295,7 @@ __global__ void __launch_bounds__(256) k_sift_extrema(SiftLayout lay, int o, con
             }
         }
     }
+  }
 }
 
 // Phase 2 -- adjustLocalExtrema: one thread per raw extremum
@@ -790,7 +800,7 @@ static cudaError_t sift_enqueue(BmSift* o, const uint8_t* d_gray, BmKeypoints* o
     SIFT_OK(cudaMemsetAsync(o->claim, 0, o->claim_words * 4, s3));
     const dim3 blk(32, 8);
     const int bw = 2 * o->w, bh = 2 * o->h;
-    BM_COUNT_LAUNCHES(1), k_sift_upsample<<<dim3((bw + 31) / 32, (bh + 7) / 8), blk, 0, s>>>(d_gray, o->w, o->h, o->up);
+    BM_COUNT_LAUNCHES(1), k_sift_upsample<<<dim3((bw + 31) / 32, (bh + 31) / 32), blk, 0, s>>>(d_gray, o->w, o->h, o->up);
     for (int oc = 0; oc < L.noct; ++oc) {
         const SiftOct& O = L.o[oc];
         if (oc == 0) blur_level(0, o->up, o->pyr + O.g[0], nullptr, nullptr, O.w, O.h, s);
