@@ -252,6 +252,18 @@ def main():
             peaks = json.loads(pk.read_text())
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = (wb_bytes / 1e9) / (wb_ms / 1e3) if wb_ms > 0 else 0.0
+        # DRAM traffic of the chain per frame from the committed `ncu --set full` capture (profiles/): sum over its launches
+        traffic, traffic_src = None, None
+        tj = ROOT / "profiles" / "r01_chain_ncu.json"
+        if tj.exists() and w == 1920 and h == 1080:
+            try:
+                kk = json.loads(tj.read_text())["kernels"]
+                per_frame = {"k_warp_rows": 1, "k_dt_local": 2, "k_dt_diag_chain16": 1, "k_dt_vert_local": 1, "k_dt_vert_chain16": 1,
+                             "k_dt_weights": 1, "k_blur_blend": 1, "k_rowscan_bgrx": 1}
+                traffic = float(sum(c * (kk[k]["dram_read"] + kk[k]["dram_write"]) for k, c in per_frame.items()))
+                traffic_src = "profiles/r01_chain_ncu.json (ncu --set full of tools/chain_only.py, caches flushed per kernel replay)"
+            except (KeyError, ValueError):
+                traffic = None
         cpu = None
         if not args.no_cpu_baseline and world >= 1:
             cores = os.cpu_count() or 1
@@ -270,7 +282,8 @@ def main():
                 "gpu_launches": int(launches),
                 "clocks": clocks,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak if peak else None, "traffic": None,
+                             "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
+                             "algorithmic_bytes_per_frame": wb_bytes / max(wb_frames, 1),
                              "kernel": "warp/blend chain (k_warp_rows, k_dt_*, k_blur_blend, k_rowscan_bgrx), 3N+6A bytes per frame; timed with "
                                        "CUDA events on its launching stream in a separate pass without detect overlap",
                              "frames": int(wb_frames),

@@ -569,9 +569,14 @@ __global__ void __launch_bounds__(1024) k_sift_emit(const int* __restrict__ ctr,
             }
             __syncthreads();
             const int nb = min(1024, m - b0);
-            if (a < m)
-                for (int q = 0; q < nb; ++q)
-                    rank += kp_less(s_x[q], s_y[q], s_s[q], s_a[q], s_r[q], s_o[q], s_i[q], pi.x, pi.y, si, ai, ri, oi, i) ? 1 : 0;
+            if (a < m) {
+                // the primary key (x) almost never ties: count on it alone, and run the full comparison only over the ties
+                int ties = 0;
+                for (int q = 0; q < nb; ++q) { const float xq = s_x[q]; rank += xq < pi.x ? 1 : 0; ties += xq == pi.x ? 1 : 0; }
+                if (ties > (b0 <= a && a < b0 + nb ? 1 : 0))
+                    for (int q = 0; q < nb; ++q)
+                        if (s_x[q] == pi.x) rank += kp_less(s_x[q], s_y[q], s_s[q], s_a[q], s_r[q], s_o[q], s_i[q], pi.x, pi.y, si, ai, ri, oi, i) ? 1 : 0;
+            }
         }
         if (a < m) {
             // firstOctave = -1: octave byte -1, pt and size halved
@@ -591,13 +596,15 @@ __global__ void __launch_bounds__(1024) k_sift_emit(const int* __restrict__ ctr,
 // calcSIFTDescriptor: one CTA per keypoint
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_sift_describe(SiftLayout lay, const float* __restrict__ pyr, BmKeypoints kp) {
-    __shared__ unsigned long long hist[6 * 6 * 10];
+    // 2^-24 fixed-point histogram (integer sums are order independent -> deterministic).  64-bit shared atomics compile to a
+    // compare-and-swap spin loop, so a bin is two 32-bit words updated with native 32-bit adds and an explicit carry.
+    __shared__ unsigned hist_lo[6 * 6 * 10], hist_hi[6 * 6 * 10];
     __shared__ float raw[128];
     __shared__ float red[8];
     const int tid = threadIdx.x;
   for (int k = blockIdx.x; k < *kp.count; k += gridDim.x) {
     __syncthreads();                                       // previous keypoint of this CTA is done with the shared arrays
-    for (int i = tid; i < 360; i += 256) hist[i] = 0ull;
+    for (int i = tid; i < 360; i += 256) { hist_lo[i] = 0u; hist_hi[i] = 0u; }
     const int packed = kp.octave[k];
     int octave = packed & 255; const int layer = (packed >> 8) & 255;
     octave = octave < 128 ? octave : (-128 | octave);
@@ -641,7 +648,9 @@ __global__ void __launch_bounds__(256) k_sift_describe(SiftLayout lay, const flo
         const float v011 = v_rc01 * obin, v010 = v_rc01 - v011, v001 = v_rc00 * obin, v000 = v_rc00 - v001;
         const int idx = ((r0 + 1) * 6 + c0 + 1) * 10 + o0;
         const float FX = 16777216.f;
-#define HADD(off, v) atomicAdd(&hist[idx + (off)], (unsigned long long)__float2ll_rn((v) * FX))
+#define HADD(off, v) do { const unsigned long long _q = (unsigned long long)__float2ll_rn((v) * FX); const unsigned _l = (unsigned)_q; \
+                          const unsigned _o = atomicAdd(&hist_lo[idx + (off)], _l); const unsigned _h = (unsigned)(_q >> 32) + ((_o + _l < _o) ? 1u : 0u); \
+                          if (_h) atomicAdd(&hist_hi[idx + (off)], _h); } while (0)
         HADD(0, v000); HADD(1, v001); HADD(10, v010); HADD(11, v011); HADD(60, v100); HADD(61, v101); HADD(70, v110); HADD(71, v111);
 #undef HADD
     }
@@ -650,9 +659,10 @@ __global__ void __launch_bounds__(256) k_sift_describe(SiftLayout lay, const flo
     if (tid < 128) {
         const int i = tid >> 5, j = (tid >> 3) & 3, o = tid & 7;
         const int idx = ((i + 1) * 6 + (j + 1)) * 10;
-        long long v = (long long)hist[idx + o];
-        if (o == 0) v += (long long)hist[idx + 8];
-        if (o == 1) v += (long long)hist[idx + 9];
+        auto bin = [&](int q) { return (long long)(((unsigned long long)hist_hi[q] << 32) | hist_lo[q]); };
+        long long v = bin(idx + o);
+        if (o == 0) v += bin(idx + 8);
+        if (o == 1) v += bin(idx + 9);
         raw[tid] = (float)((double)v * (1.0 / 16777216.0));
     }
     __syncthreads();

@@ -313,13 +313,10 @@ __global__ void __launch_bounds__(256, 3) k_blur_blend(BmFramePlan plan, const f
         }
         return;
     }
-    bool need = false;
-#pragma unroll
-    for (int o = 0; o < 8; ++o)
-        if (o < nrow && wcol[(size_t)o * plan.ws].w && ccol[(size_t)o * plan.canvas_w].w) need = true;
     float wgt[2][8];
-    if (__syncthreads_or(need)) {                          // tiles without a single overlap pixel need no weights
+    {
         const int warp = tid >> 5, lane = tid & 31;
+        // both weight planes (tile + 15 px halo) are requested first: the copies fly while the overlap test below loads wbuf / canvas.
         // tile columns of this lane (3 per row) and their source columns, fixed for the whole tile
         int gxo[3]; bool gxok[3];
 #pragma unroll
@@ -344,6 +341,12 @@ __global__ void __launch_bounds__(256, 3) k_blur_blend(BmFramePlan plan, const f
             }
             cp_async_commit();
         }
+    }
+    bool need = false;
+#pragma unroll
+    for (int o = 0; o < 8; ++o)
+        if (o < nrow && wcol[(size_t)o * plan.ws].w && ccol[(size_t)o * plan.canvas_w].w) need = true;
+    if (__syncthreads_or(need)) {                          // tiles without a single overlap pixel need no weights
 #pragma unroll
         for (int pl = 0; pl < 2; ++pl) {
             if (pl == 0) cp_async_wait<1>(); else cp_async_wait<0>();
@@ -379,6 +382,7 @@ __global__ void __launch_bounds__(256, 3) k_blur_blend(BmFramePlan plan, const f
             }
         }
     } else {
+        cp_async_wait<0>();                                // nothing may be in flight into shared memory when the CTA exits
 #pragma unroll
         for (int o = 0; o < 8; ++o) { wgt[0][o] = 0.f; wgt[1][o] = 0.f; }
     }
