@@ -96,8 +96,14 @@ static int fast_total_tiles(const BmOrbLevels& lv) {
 
 __global__ void __launch_bounds__(256) k_fast_detect(BmOrbLevels lv, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ score,
                                                      unsigned* __restrict__ corners, int* __restrict__ ctr) {
+    // corners of the tile are collected in shared memory and appended with ONE global atomic per CTA: a per-warp atomicAdd on the
+    // level counter serialises ~10^5 same-address atomics per frame in L2
+    __shared__ unsigned s_list[1024];
+    __shared__ int s_n, s_base;
     int level, x0, y0;
     if (!fast_tile(lv, level, x0, y0)) return;
+    if (threadIdx.x == 0 && threadIdx.y == 0) s_n = 0;
+    __syncthreads();
     const BmOrbLevel L = lv.l[level];
     const int x = x0 + threadIdx.x;
 #pragma unroll
@@ -119,14 +125,18 @@ __global__ void __launch_bounds__(256) k_fast_detect(BmOrbLevels lv, const uint8
         if (bal) {
             const int lane = threadIdx.x & 31, leader = __ffs(bal) - 1;
             int base = 0;
-            if (lane == leader) base = atomicAdd(&ctr[40 + level], __popc(bal));
+            if (lane == leader) base = atomicAdd(&s_n, __popc(bal));
             base = __shfl_sync(0xffffffffu, base, leader);
-            if (corner) {
-                const int idx = base + __popc(bal & ((1u << lane) - 1u));
-                if (idx < (L.w * L.h) / 2) corners[L.off / 2 + idx] = (unsigned)x | ((unsigned)y << 16);
-                else ctr[32] = 1;
-            }
+            if (corner) s_list[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned)x | ((unsigned)y << 16);
         }
+    }
+    __syncthreads();
+    const int n = s_n, cap = (L.w * L.h) / 2;
+    if (threadIdx.x == 0 && threadIdx.y == 0 && n > 0) s_base = atomicAdd(&ctr[40 + level], n);
+    __syncthreads();
+    for (int i = threadIdx.y * 32 + threadIdx.x; i < n; i += 256) {
+        if (s_base + i < cap) corners[L.off / 2 + s_base + i] = s_list[i];
+        else ctr[32] = 1;
     }
 }
 
@@ -164,6 +174,7 @@ __global__ void __launch_bounds__(256) k_fast_cscore(BmOrbLevels lv, const uint8
 __global__ void __launch_bounds__(256) k_fast_cnms(BmOrbLevels lv, const uint8_t* __restrict__ score, const unsigned* __restrict__ corners,
                                                    uint2* __restrict__ cand, int* __restrict__ ctr, int* __restrict__ hist) {
     __shared__ int sh[256];
+    __shared__ int s_n, s_base;
     const int level = blockIdx.y;
     const BmOrbLevel L = lv.l[level];
     const int n = min(ctr[40 + level], (L.w * L.h) / 2);
@@ -184,17 +195,24 @@ __global__ void __launch_bounds__(256) k_fast_cnms(BmOrbLevels lv, const uint8_t
             keep = sc > 0 && sc > p[-1] && sc > p[1] && sc > p[-w - 1] && sc > p[-w] && sc > p[-w + 1] && sc > p[w - 1] && sc > p[w] && sc > p[w + 1];
         }
     }
+    // CTA-aggregated append: one global atomic per CTA iteration instead of one per warp
     const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    int slot = -1;
     if (bal) {
         const int lane = threadIdx.x & 31, leader = __ffs(bal) - 1;
         int base = 0;
-        if (lane == leader) base = atomicAdd(&ctr[level], __popc(bal));
+        if (lane == leader) base = atomicAdd(&s_n, __popc(bal));
         base = __shfl_sync(0xffffffffu, base, leader);
-        if (keep) {
-            const int idx = base + __popc(bal & ((1u << lane) - 1u));
-            if (idx < L.cand_cap) cand[L.cand_off + idx] = make_uint2((unsigned)x | ((unsigned)y << 16), (unsigned)sc);
-            atomicAdd(&sh[sc], 1);
-        }
+        if (keep) { slot = base + __popc(bal & ((1u << lane) - 1u)); atomicAdd(&sh[sc], 1); }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_n > 0) s_base = atomicAdd(&ctr[level], s_n);
+    __syncthreads();
+    if (slot >= 0) {
+        const int idx = s_base + slot;
+        if (idx < L.cand_cap) cand[L.cand_off + idx] = make_uint2((unsigned)x | ((unsigned)y << 16), (unsigned)sc);
     }
   }
     __syncthreads();

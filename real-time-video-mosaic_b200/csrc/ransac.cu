@@ -330,11 +330,15 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_ransac_homography(const float
 // code in a one-warp kernel (34.7k vs 2.9k cycles for the pivot searches of a 9x9 solve), so the serial algebra lives in
 // its own 32-thread launch; the 45-term normal-equation sums are strided over the lanes and reduced with shuffles.
 // ------------------------------------------------------------------------------------------------------------------
+#define RF_WARPS 4            // warp 0 runs the serial algebra; all four warps share the sums over the points
 struct RfShared {
     double A[9][9], V[9];
     double lmA[8][8], lmv[8], lmd[8], lmx[8], lmxd[8], lmD[8];
     double M[9][10], X[9], P[9];
     double sums[46];
+    double wsum[RF_WARPS][46];      // per-warp partial sums of rf_accumulate
+    const double* cmd_h;            // command block for the helper warps: parameter vector, Jacobian wanted, 0 = exit
+    int cmd, cmd_want_j;
 };
 
 // Gauss-Jordan elimination WITHOUT pivoting of a symmetric positive definite NxN system M[r][0..N) | M[r][N] by one warp: every
@@ -382,13 +386,17 @@ __device__ __forceinline__ void warp_sum(RfShared& sh, const double (&v)[NV]) {
     __syncwarp();
 }
 
-__device__ __noinline__ void rf_accumulate(RfShared& sh, const float2* src, const float2* dst, const uint8_t* mask, int n, const double* h, bool want_j) {
-    const int lane = threadIdx.x & 31;
+// HomographyRefineCallback sums over this warp's share of the points (i = tid, tid + 128, ...): JtJ (36), JtR (8), |r|^2, max |r|.
+// The Jacobian rows are j0 = (Mx*ww, My*ww, ww, 0, 0, 0, -Mx*ww*xi, -My*ww*xi), j1 = (0, 0, 0, Mx*ww, My*ww, ww, -Mx*ww*yi, -My*ww*yi):
+// products with a structural zero are skipped (0*x + y = y and s + 0 = s exactly, so the sums are bit-identical to the dense form).
+__device__ __noinline__ void rf_partial(RfShared& sh, const float2* src, const float2* dst, const uint8_t* mask, int n, const double* h, bool want_j) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr bool nz0[8] = {true, true, true, false, false, false, true, true}, nz1[8] = {false, false, false, true, true, true, true, true};
     double acc[45];
 #pragma unroll
     for (int k = 0; k < 45; ++k) acc[k] = 0.0;
     double rmax = 0.0;
-    for (int i = lane; i < n; i += 32) {
+    for (int i = threadIdx.x; i < n; i += 32 * RF_WARPS) {
         if (!mask[i]) continue;
         const double Mx = src[i].x, My = src[i].y;
         const double ww = __drcp_rn(h[6] * Mx + h[7] * My + 1.0);
@@ -403,32 +411,72 @@ __device__ __noinline__ void rf_accumulate(RfShared& sh, const float2* src, cons
 #pragma unroll
             for (int a = 0; a < 8; ++a) {
 #pragma unroll
-                for (int b = a; b < 8; ++b) acc[k++] += j0[a] * j0[b] + j1[a] * j1[b];
+                for (int b = a; b < 8; ++b) {
+                    if (nz0[a] && nz0[b] && nz1[a] && nz1[b]) acc[k] += j0[a] * j0[b] + j1[a] * j1[b];
+                    else if (nz0[a] && nz0[b]) acc[k] += j0[a] * j0[b];
+                    else if (nz1[a] && nz1[b]) acc[k] += j1[a] * j1[b];
+                    ++k;
+                }
             }
 #pragma unroll
-            for (int a = 0; a < 8; ++a) acc[36 + a] += j0[a] * rx + j1[a] * ry;
+            for (int a = 0; a < 8; ++a) {
+                if (nz0[a] && nz1[a]) acc[36 + a] += j0[a] * rx + j1[a] * ry;
+                else if (nz0[a]) acc[36 + a] += j0[a] * rx;
+                else acc[36 + a] += j1[a] * ry;
+            }
         }
     }
     for (int o = 16; o > 0; o >>= 1) rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
-    if (want_j) warp_sum<45>(sh, acc);
-    else { const double one[1] = {acc[44]}; warp_sum<1>(sh, one); if (lane == 0) sh.sums[44] = sh.sums[0]; }
-    if (lane == 0) sh.sums[45] = rmax;
+#pragma unroll
+    for (int k = 0; k < 45; ++k) {
+        if (!want_j && k != 44) continue;
+        double x = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) sh.wsum[warp][k] = x;
+    }
+    if (lane == 0) sh.wsum[warp][45] = rmax;
+}
+
+// called by warp 0: wake the helper warps, take a share, combine the per-warp partials (fixed order: deterministic)
+__device__ __noinline__ void rf_accumulate(RfShared& sh, const float2* src, const float2* dst, const uint8_t* mask, int n, const double* h, bool want_j) {
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) { sh.cmd_h = h; sh.cmd_want_j = want_j ? 1 : 0; sh.cmd = 1; }
+    __syncthreads();
+    rf_partial(sh, src, dst, mask, n, h, want_j);
+    __syncthreads();
+    for (int k = lane; k < 46; k += 32) {
+        if (!want_j && k < 44) continue;
+        double t = sh.wsum[0][k];
+#pragma unroll
+        for (int w = 1; w < RF_WARPS; ++w) t = (k == 45) ? fmax(t, sh.wsum[w][k]) : t + sh.wsum[w][k];
+        sh.sums[k] = t;
+    }
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(32, 1) k_ransac_refine(const float2* __restrict__ gsrc, const float2* __restrict__ gdst, const int* __restrict__ countp,
+__global__ void __launch_bounds__(32 * RF_WARPS, 1) k_ransac_refine(const float2* __restrict__ gsrc, const float2* __restrict__ gdst, const int* __restrict__ countp,
                                                          const uint8_t* __restrict__ mask, BmRansacResult* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RfShared& sh = *reinterpret_cast<RfShared*>(smem_raw);
     float2* spts = reinterpret_cast<float2*>(smem_raw + ((sizeof(RfShared) + 15) & ~(size_t)15));
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
     if (out->ok != 2) return;                   // nothing to refine (no model, or the 4-point special case)
     const long long t_start = clock64();
     const int n = *countp, cnt = out->n_inliers;
     const float2* src = gsrc; const float2* dst = gdst;
     if (n <= RS_SMEM_PTS) {
-        for (int i = lane; i < n; i += 32) { spts[i] = gsrc[i]; spts[RS_SMEM_PTS + i] = gdst[i]; }
+        for (int i = threadIdx.x; i < n; i += 32 * RF_WARPS) { spts[i] = gsrc[i]; spts[RS_SMEM_PTS + i] = gdst[i]; }
         src = spts; dst = spts + RS_SMEM_PTS;
+    }
+    __syncthreads();
+    if (threadIdx.x >= 32) {                    // helper warps: serve rf_accumulate requests of warp 0 until told to exit
+        while (true) {
+            __syncthreads();
+            if (sh.cmd == 0) return;
+            rf_partial(sh, src, dst, mask, n, sh.cmd_h, sh.cmd_want_j != 0);
+            __syncthreads();
+        }
     }
     if (lane < 9) sh.V[lane] = out->H[lane];     // bestH of stage 1
     __syncwarp();
@@ -605,7 +653,10 @@ __global__ void __launch_bounds__(32, 1) k_ransac_refine(const float2* __restric
         out->H[8] = 1.0;
         out->ok = 1; out->lm_iters = it; out->jacobi_sweeps = eig_iters;
         out->cyc[4] = t_eig - t_start; out->cyc[5] = clock64() - t_eig; out->cyc[7] = clock64() - t_start;
+        sh.cmd = 0;
     }
+    __syncwarp();
+    __syncthreads();                            // releases the helper warps (cmd == 0)
 }
 
 cudaError_t bm_launch_ransac(const float2* d_src, const float2* d_dst, const int* d_count, double thresh, int max_iters, double confidence,
@@ -625,6 +676,6 @@ cudaError_t bm_launch_ransac(const float2* d_src, const float2* d_dst, const int
         attr2_set = true;
     }
     BM_COUNT_LAUNCHES(1), k_ransac_homography<<<1, RS_THREADS, smem, s>>>(d_src, d_dst, d_count, thresh, max_iters, confidence, d_mask, d_out);
-    BM_COUNT_LAUNCHES(1), k_ransac_refine<<<1, 32, smem2, s>>>(d_src, d_dst, d_count, d_mask, d_out);
+    BM_COUNT_LAUNCHES(1), k_ransac_refine<<<1, 32 * RF_WARPS, smem2, s>>>(d_src, d_dst, d_count, d_mask, d_out);
     return cudaGetLastError();
 }

@@ -267,10 +267,8 @@ __device__ __forceinline__ bool sift_is_extremum(const float* __restrict__ prv, 
 __global__ void __launch_bounds__(256) k_sift_extrema(SiftLayout lay, int o, const float* __restrict__ pyr, unsigned* __restrict__ raw,
                                                       int* __restrict__ ctr) {
     const SiftOct O = lay.o[o];
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y * blockDim.y + threadIdx.y;
     const int w = O.w, h = O.h;
-  {
-    const int r = blockIdx.y * 8 + threadIdx.y;
     const bool inside = c >= SIFT_BORDER && c < w - SIFT_BORDER && r >= SIFT_BORDER && r < h - SIFT_BORDER;
     const size_t p = (size_t)r * w + c;
     float d[5];
@@ -295,7 +293,6 @@ __global__ void __launch_bounds__(256) k_sift_extrema(SiftLayout lay, int o, con
             }
         }
     }
-  }
 }
 
 // Phase 2 -- adjustLocalExtrema: one thread per raw extremum
