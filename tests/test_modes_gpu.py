@@ -94,3 +94,29 @@ def test_canvas_row_tiles_match_untiled(sweep_frames):
     assert np.array_equal(got, want)
     y0, y1 = sh.tile_rows(Hc, 0, 2)
     assert got[:y1].max() == 0                            # the upper tile was never touched
+
+
+def test_prefetch_and_overlap_do_not_change_results(sweep_frames):
+    """double-buffered ingest (next_frame=) and the detect / chain stream overlap are scheduling only: the canvas and the
+    trajectory must be bit-identical to the plain sequential calls, also when a prefetched frame is not the one processed next"""
+    import b200mosaic
+    frames, _ = sweep_frames
+    ref = b200mosaic.VideMosaic(frames[0], detector_type="orb", show_intermediate=False, visualize=False)
+    ref.set_overlap(False)
+    for t in range(1, 7):
+        ref.process_frame(frames[t], t)
+    want_canvas, want_H = ref.output_img.copy(), ref.H.copy()
+    vm = b200mosaic.VideMosaic(frames[0], detector_type="orb", show_intermediate=False, visualize=False)
+    for t in range(1, 7):
+        nxt = frames[t + 1] if t + 1 < 7 else None
+        if t == 3:
+            nxt = frames[1]                      # a stale prefetch: frame 4 must be uploaded again, not taken from the staged copy
+        vm.process_frame(frames[t], t, next_frame=nxt)
+    assert np.array_equal(vm.output_img, want_canvas)
+    assert np.array_equal(vm.H, want_H)
+    pin = torch.from_numpy(np.stack(frames)).pin_memory()
+    fb = frames[0].nbytes
+    vp = b200mosaic.VideMosaic(frames[0], detector_type="orb", show_intermediate=False, visualize=False)
+    for t in range(1, 7):
+        assert vp.process_frame_ptr(pin.data_ptr() + t * fb, pin.data_ptr() + (t + 1) * fb if t + 1 < 7 else None) == 0
+    assert np.array_equal(vp.output_img, want_canvas)
