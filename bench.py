@@ -236,6 +236,11 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     info_bytes = 160 + 16
+    # SURVEY 8f rank 1 (outside the timed region): crop_black_areas + scale_to_screen of the final canvas on the device
+    vm2.finalize()
+    tf = time.perf_counter()
+    final_img = vm2.finalize()
+    finalize_ms = 1e3 * (time.perf_counter() - tf)
     del vm2
 
     # ---------------- max over ranks ----------------
@@ -275,6 +280,12 @@ def main():
             cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                    "sample": f"first {nf - 1} frames of the same sweep ({dt:.1f} s), oracle.mosaic_ref.RefMosaic = the reference's "
                              f"cv2 {cv2.__version__}/NumPy calls, cv2.setNumThreads({cores}), IPP on"}
+        finalize_cpu_ms = None
+        if cpu is not None:                               # the reference's own functions on the same canvas, same host
+            from oracle import finalize as ofin
+            tc = time.perf_counter()
+            ofin.scale_to_screen(ofin.crop_black_areas(canvas, threshold=80, margin=30))
+            finalize_cpu_ms = 1e3 * (time.perf_counter() - tc)
         line = {"metric": "mosaic frames/sec at 1080p", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": 1e3 * dev_s / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8 / s32 fixed point (warp, DT, ORB) + f32 (blend weights, SIFT) + f64 (RANSAC/LM)", "data": "synthetic",
@@ -292,7 +303,10 @@ def main():
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s",
                              "ms_per_frame": wb_ms / max(wb_frames, 1)},
                 "cpu_baseline": cpu,
-                "frames_ok": n_ok, "event_ms_per_step": ev_ms / K}
+                "frames_ok": n_ok, "event_ms_per_step": ev_ms / K,
+                "finalize": {"what": "crop_black_areas(80, 30) + scale_to_screen of the final canvas (main.py:1647-1659) via bm_finalize, "
+                                     "result copied to the host", "device_ms": finalize_ms, "out_shape": list(final_img.shape),
+                             "cpu_ms": finalize_cpu_ms}}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

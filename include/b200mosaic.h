@@ -97,6 +97,12 @@ bm_status bm_clear_canvas(bm_handle h);
 bm_status bm_get_canvas_device(bm_handle h, uint8_t* d_bgr_out);
 /* output_img (uint8, Hc x Wc x 3): lazy D2H of the device canvas                     main.py:1632,1649 */
 bm_status bm_get_canvas(bm_handle h, uint8_t* h_bgr_out);
+/* mosaic finalisation on the device: crop_black_areas(output_img, threshold, margin) (main.py:980-1003) followed by
+ * scale_to_screen(cropped, target_w, target_h) (main.py:1006-1038; target <= 0 -> 1920 x 1080 like the reference off Windows), as
+ * main() does before writing mosaic.jpg (main.py:1647-1659).  out_wh = (width, height) of the result, rect = (x, y, w, h) of the
+ * crop.  h_out == NULL only computes the sizes; otherwise h_out receives height x width x 3 BGR bytes. */
+bm_status bm_finalize(bm_handle h, int threshold, int margin, int target_w, int target_h, uint8_t* h_bgr_out, size_t cap_bytes,
+                      int out_wh[2], int rect[4]);
 bm_status bm_get_state(bm_handle h, double H_old[9], int* history_len, double* history /* <=5*9 */);
 bm_status bm_set_stabilization(bm_handle h, int enabled, int history_size, double translation_threshold,
                                double scale_threshold);                          /* main.py:97-101 */

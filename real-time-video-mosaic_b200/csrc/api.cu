@@ -6,6 +6,7 @@
 #include "ingest.cuh"
 #include "warp_blend.cuh"
 #include "pipeline.cuh"
+#include "finalize.cuh"
 #include <stdarg.h>
 #include <string.h>
 #include <math.h>
@@ -73,6 +74,8 @@ struct bm_mosaic_s {
     int cur = 0;
     // canvas export
     uint8_t* d_canvas_bgr = nullptr;
+    uint8_t* d_final = nullptr; size_t final_cap = 0;      // finalisation result (screen sized), allocated on first use
+    int* d_bounds = nullptr;
     // stitcher state (main.py:92-102)
     double H_old[9];
     double history[5][9];
@@ -145,7 +148,7 @@ extern "C" bm_status bm_destroy(bm_handle m) {
         cudaFreeHost(m->h_stage[i]); cudaFree(m->d_bgr[i]); cudaFree(m->d_bgrx[i]); cudaFree(m->d_gray[i]);
         if (m->ev_h2d[i]) cudaEventDestroy(m->ev_h2d[i]);
     }
-    cudaFree(m->d_canvas_bgr);
+    cudaFree(m->d_canvas_bgr); cudaFree(m->d_final); cudaFree(m->d_bounds);
     for (int i = 0; i < bm_mosaic_s::kEvRing; ++i) { cudaEventDestroy(m->ev0[i]); cudaEventDestroy(m->ev1[i]); }
     for (int i = 0; i < 2; ++i) { if (m->ev_up[i]) cudaEventDestroy(m->ev_up[i]); if (m->ev_chain[i]) cudaEventDestroy(m->ev_chain[i]); }
     cudaStreamDestroy(m->stream); cudaStreamDestroy(m->s_chain); cudaStreamDestroy(m->s_copy);
@@ -320,6 +323,49 @@ extern "C" bm_status bm_get_canvas(bm_handle m, uint8_t* h_out) {
     const size_t n = (size_t)m->cfg.canvas_h * m->cfg.canvas_w;
     BM_CUDA_OK(bm_launch_unpack_canvas(m->blend.canvas, m->d_canvas_bgr, (int)n, m->s_chain));
     BM_CUDA_OK(cudaMemcpyAsync(h_out, m->d_canvas_bgr, n * 3, cudaMemcpyDeviceToHost, m->s_chain));
+    BM_CUDA_OK(cudaStreamSynchronize(m->s_chain));
+    return BM_OK;
+}
+
+// crop_black_areas(output_img, threshold, margin) + scale_to_screen(cropped, target_w, target_h) (main.py:980-1038, as called
+// at :1647-1659) on the device canvas.  h_out == NULL: only the sizes are computed (out_wh, rect), so that the caller can allocate.
+extern "C" bm_status bm_finalize(bm_handle m, int threshold, int margin, int target_w, int target_h, uint8_t* h_out, size_t cap_bytes,
+                                 int out_wh[2], int rect[4]) {
+    if (!m || !out_wh) return BM_ERR_ARG;
+    BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+    const int cw = m->cfg.canvas_w, ch = m->cfg.canvas_h;
+    if (!m->d_bounds) BM_CUDA_OK(cudaMalloc(&m->d_bounds, 4 * sizeof(int)));
+    int b[4];
+    BM_CUDA_OK(bm_launch_crop_bounds(m->blend.canvas, cw, ch, threshold, m->d_bounds, m->s_chain));
+    BM_CUDA_OK(cudaMemcpyAsync(b, m->d_bounds, sizeof(b), cudaMemcpyDeviceToHost, m->s_chain));
+    BM_CUDA_OK(cudaStreamSynchronize(m->s_chain));
+    int x = 0, y = 0, w = cw, h = ch;
+    if (b[2] >= 0) {                                         // main.py:996-1003 (coords is None -> the image itself)
+        const int bx = b[0], by = b[1], bw = b[2] - b[0] + 1, bh = b[3] - b[1] + 1;
+        x = bx + margin > 0 ? bx + margin : 0;
+        y = by + margin > 0 ? by + margin : 0;
+        w = cw - x < bw - 2 * margin ? cw - x : bw - 2 * margin;
+        h = ch - y < bh - 2 * margin ? ch - y : bh - 2 * margin;
+    }
+    if (rect) { rect[0] = x; rect[1] = y; rect[2] = w; rect[3] = h; }
+    if (w <= 0 || h <= 0) { bm_set_error("bm_finalize: the crop is empty (%d x %d)", w, h); return BM_ERR_UNSUPPORTED; }
+    const double sw_ = target_w > 0 && target_h > 0 ? target_w : 1920, sh_ = target_w > 0 && target_h > 0 ? target_h : 1080;   // main.py:1013-1024 off Windows
+    double scale = sw_ / (double)w < sh_ / (double)h ? sw_ / (double)w : sh_ / (double)h;
+    if (scale <= 0) scale = 1.0;
+    int nw = (int)(w * scale), nh = (int)(h * scale);
+    if (nw < 1) nw = 1;
+    if (nh < 1) nh = 1;
+    out_wh[0] = nw; out_wh[1] = nh;
+    if (!h_out) return BM_OK;
+    const size_t need = (size_t)nw * nh * 3;
+    if (cap_bytes < need) { bm_set_error("bm_finalize: output buffer too small (%zu < %zu)", cap_bytes, need); return BM_ERR_ARG; }
+    if (m->final_cap < need) {
+        cudaFree(m->d_final); m->d_final = nullptr; m->final_cap = 0;
+        BM_CUDA_OK(cudaMalloc(&m->d_final, need + 16));
+        m->final_cap = need;
+    }
+    BM_CUDA_OK(bm_launch_resize_linear(m->blend.canvas, cw, x, y, w, h, m->d_final, nw, nh, m->s_chain));
+    BM_CUDA_OK(cudaMemcpyAsync(h_out, m->d_final, need, cudaMemcpyDeviceToHost, m->s_chain));
     BM_CUDA_OK(cudaStreamSynchronize(m->s_chain));
     return BM_OK;
 }

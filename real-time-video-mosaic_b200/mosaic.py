@@ -198,6 +198,19 @@ class VideMosaic:
         H = np.array(info.H_rel, dtype=np.float64).reshape(3, 3) if st == _lib.BM_OK else None
         return st, H, info.n_matches
 
+    def finalize(self, threshold=80, margin=30, target_w=None, target_h=None):
+        """crop_black_areas(output_img, threshold, margin) + scale_to_screen(cropped, target_w, target_h) (main.py:980-1038) on the
+        device canvas, as main() does before cv2.imwrite('mosaic.jpg') (main.py:1647-1659): only the screen-sized result is copied
+        to the host.  Returns the uint8 BGR image; `self.last_crop_rect` = (x, y, w, h) of the crop."""
+        wh = (C.c_int * 2)(); rect = (C.c_int * 4)()
+        tw, th = (int(target_w), int(target_h)) if target_w and target_h else (0, 0)
+        _lib.check(self._lib.bm_finalize(self._h, int(threshold), int(margin), tw, th, None, 0, wh, rect), "bm_finalize")
+        out = np.empty((wh[1], wh[0], 3), dtype=np.uint8)
+        _lib.check(self._lib.bm_finalize(self._h, int(threshold), int(margin), tw, th, out.ctypes.data_as(C.c_void_p), out.nbytes, wh, rect),
+                   "bm_finalize")
+        self.last_crop_rect = tuple(rect)
+        return out
+
     def set_overlap(self, on):
         """True (default): the warp/blend chain of frame t overlaps detect/match/RANSAC of frame t+1; False: strictly serial"""
         _lib.check(self._lib.bm_set_overlap(self._h, 1 if on else 0), "bm_set_overlap")

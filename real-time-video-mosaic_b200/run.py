@@ -4,7 +4,8 @@ B200 implementation.
     python -m b200mosaic.run <video> [--reference-dir DIR] [--output-dir D] [--detector sift|orb]
 
 `--reference-dir` is the checkout that holds the reference's main.py (it is imported, never modified).  YOLO detection,
-A* navigation, cropping / scaling / mosaic.jpg writing all stay on the reference's own code path."""
+A* navigation and the mosaic.jpg writing stay on the reference's own code path; `crop_black_areas` + `scale_to_screen` of the
+final canvas (main.py:1647-1659) run on the device (`bm_finalize`) so that only the screen-sized image is copied back."""
 from __future__ import annotations
 
 import argparse
@@ -73,7 +74,48 @@ def main(argv=None):
             super().__init__(first_image, *args, **kw)
 
     ref.VideMosaic = _Swapped
+    install_device_finalize(ref, _Swapped)
     ref.main(video_path=a.video, show_intermediate=False, output_dir=a.output_dir)
+
+
+def install_device_finalize(ref, mosaic_cls):
+    """main() calls  cropped = crop_black_areas(video_mosaic.output_img, threshold=80, margin=30)  and then
+    scaled = scale_to_screen(cropped)  (main.py:1647-1659).  When the first call receives the live canvas of a B200 mosaic, the
+    pair is served by bm_finalize on the device: crop_black_areas returns a zero-copy placeholder of the cropped SHAPE (main()
+    only prints it) that remembers the mosaic, scale_to_screen recognises it and returns the device result.  Any other use of
+    the two functions falls through to the reference's implementation."""
+    import numpy as np
+    ref_crop, ref_scale = ref.crop_black_areas, ref.scale_to_screen
+    live = []
+    orig_init = mosaic_cls.__init__
+
+    def _init(self, *a, **k):
+        orig_init(self, *a, **k)
+        live.append(self)
+    mosaic_cls.__init__ = _init
+
+    class _Placeholder(np.ndarray):
+        pass
+
+    def crop_black_areas(image, threshold=15, margin=5):
+        for vm in live:
+            if image is getattr(vm, "_canvas_cache", None):
+                try:
+                    out = vm.finalize(threshold, margin)
+                except Exception:
+                    break
+                x, y, w, h = vm.last_crop_rect
+                ph = np.lib.stride_tricks.as_strided(np.zeros(1, np.uint8), shape=(h, w, 3), strides=(0, 0, 0)).view(_Placeholder)
+                ph._b200_result = out
+                return ph
+        return ref_crop(image, threshold, margin)
+
+    def scale_to_screen(image, target_w=None, target_h=None):
+        if isinstance(image, _Placeholder) and target_w is None and target_h is None and getattr(image, "_b200_result", None) is not None:
+            return image._b200_result
+        return ref_scale(image, target_w, target_h)
+
+    ref.crop_black_areas, ref.scale_to_screen = crop_black_areas, scale_to_screen
 
 
 if __name__ == "__main__":
