@@ -27,8 +27,14 @@ void bm_matches_free(BmMatches* m) {
 }
 
 // one warp per row of A: nearest row of B under Hamming, first index on ties
-__global__ void __launch_bounds__(256) k_hamming_nn(const uint8_t* __restrict__ A, const int* __restrict__ nAp, const uint8_t* __restrict__ B,
-                                                    const int* __restrict__ nBp, int* __restrict__ nn, float* __restrict__ nd) {
+// blockIdx.y = 0: rows of A against B; 1: rows of B against A (both directions of the cross check in one launch)
+__global__ void __launch_bounds__(256) k_hamming_nn(const uint8_t* __restrict__ A0, const int* __restrict__ nA0p, const uint8_t* __restrict__ B0,
+                                                    const int* __restrict__ nB0p, int* __restrict__ nn0, float* __restrict__ nd0,
+                                                    int* __restrict__ nn1, float* __restrict__ nd1) {
+    const bool rev = blockIdx.y != 0;
+    const uint8_t* __restrict__ A = rev ? B0 : A0; const uint8_t* __restrict__ B = rev ? A0 : B0;
+    const int* nAp = rev ? nB0p : nA0p; const int* nBp = rev ? nA0p : nB0p;
+    int* __restrict__ nn = rev ? nn1 : nn0; float* __restrict__ nd = rev ? nd1 : nd0;
     const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int nA = *nAp, nB = *nBp;
     if (a >= nA) return;
@@ -102,8 +108,7 @@ __global__ void __launch_bounds__(1024) k_select_sort(int mode, double ratio, co
 
 cudaError_t bm_match_hamming(const BmKeypoints& cur, const BmKeypoints& prev, BmMatches& m, cudaStream_t s) {
     const int blocks = (BM_KP_CAP * 32) / 256;
-    BM_COUNT_LAUNCHES(1), k_hamming_nn<<<blocks, 256, 0, s>>>(cur.desc, cur.count, prev.desc, prev.count, m.nn_q2t, m.d_q2t);
-    BM_COUNT_LAUNCHES(1), k_hamming_nn<<<blocks, 256, 0, s>>>(prev.desc, prev.count, cur.desc, cur.count, m.nn_t2q, m.d_t2q);
+    BM_COUNT_LAUNCHES(1), k_hamming_nn<<<dim3(blocks, 2), 256, 0, s>>>(cur.desc, cur.count, prev.desc, prev.count, m.nn_q2t, m.d_q2t, m.nn_t2q, m.d_t2q);
     BM_COUNT_LAUNCHES(1), k_select_sort<<<1, 1024, 0, s>>>(0, 0.0, cur.count, prev.count, m, cur.pt, prev.pt);
     return cudaGetLastError();
 }

@@ -219,24 +219,32 @@ __global__ void __launch_bounds__(256) k_fast_cnms(BmOrbLevels lv, const uint8_t
     if (sh[threadIdx.x]) atomicAdd(&hist[level * 256 + threadIdx.x], sh[threadIdx.x]);
 }
 
-__global__ void k_fast_threshold(BmOrbLevels lv, int* __restrict__ ctr, const int* __restrict__ hist) {
-    const int level = threadIdx.x;
+// retainBest(2 * quota) threshold per level from the score histogram: one warp per level, 8 bins per lane in descending score
+// order, warp prefix sum, the first bin whose cumulative count reaches 2 * quota
+__global__ void __launch_bounds__(256) k_fast_threshold(BmOrbLevels lv, int* __restrict__ ctr, const int* __restrict__ hist) {
+    const int level = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (level >= BM_ORB_LEVELS) return;
     const BmOrbLevel L = lv.l[level];
     int n1 = ctr[level];
-    if (n1 > L.cand_cap) { n1 = L.cand_cap; ctr[32] = 1; }
-    ctr[level] = n1;
+    if (n1 > L.cand_cap) { n1 = L.cand_cap; if (lane == 0) ctr[32] = 1; }
     const int n = 2 * L.quota;
+    int h[8], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { h[k] = __ldg(hist + level * 256 + 255 - (lane * 8 + k)); sum += h[k]; }
+    int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += u; }
+    int cum = incl - sum, first = 256;            // `first` = descending-order index of the first bin with cum >= n
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { cum += h[k]; if (first == 256 && cum >= n) first = lane * 8 + k; }
+    first = __reduce_min_sync(0xffffffffu, first);
     int thr = 0;
     if (n <= 0) thr = 256;
-    else if (n1 > n) {
-        int cum = 0;
-        for (int s = 255; s >= 0; --s) { cum += hist[level * 256 + s]; if (cum >= n) { thr = s; break; } }
-    }
-    ctr[16 + level] = thr;
+    else if (n1 > n && first < 256) thr = 255 - first;
+    __syncwarp();
+    if (lane == 0) { ctr[level] = n1; ctr[16 + level] = thr; }
 }
 
-// HarrisResponses (blockSize 7, k = 0.04) on the FAST survivors; second compaction
 __global__ void __launch_bounds__(256) k_harris(BmOrbLevels lv, const uint8_t* __restrict__ pyr, const uint2* __restrict__ cand,
                                                 uint2* __restrict__ cand2, int* __restrict__ ctr) {
     const int gi = blockIdx.x * blockDim.x + threadIdx.x;
@@ -512,11 +520,12 @@ int bm_orb_create(BmOrb** out, int h, int w, int nfeatures, cudaStream_t s) {
 }
 void bm_orb_destroy(BmOrb* o) {
     if (!o) return;
+    for (int i = 0; i < o->ngraphs; ++i) cudaGraphExecDestroy(o->graphs[i].exec);
     cudaFree(o->pyr); cudaFree(o->score); cudaFree(o->cand); cudaFree(o->cand2); cudaFree(o->keep); cudaFree(o->ctr); cudaFree(o->hist); cudaFree(o->corners);
     delete o;
 }
 
-cudaError_t bm_orb_detect(BmOrb* o, const uint8_t* d_gray, BmKeypoints* out) {
+static cudaError_t orb_enqueue(BmOrb* o, const uint8_t* d_gray, BmKeypoints* out) {
     cudaStream_t s = o->stream;
     const BmOrbLevels& lv = o->lv;
     cudaError_t e;
@@ -533,11 +542,40 @@ cudaError_t bm_orb_detect(BmOrb* o, const uint8_t* d_gray, BmKeypoints* out) {
     BM_COUNT_LAUNCHES(1), k_fast_detect<<<fast_total_tiles(lv), blk, 0, s>>>(lv, o->pyr, o->score, o->corners, o->ctr);
     BM_COUNT_LAUNCHES(1), k_fast_cscore<<<dim3(cblocks, BM_ORB_LEVELS), 256, 0, s>>>(lv, o->pyr, o->corners, o->ctr, o->score);
     BM_COUNT_LAUNCHES(1), k_fast_cnms<<<dim3(cblocks, BM_ORB_LEVELS), 256, 0, s>>>(lv, o->score, o->corners, o->cand, o->ctr, o->hist);
-    BM_COUNT_LAUNCHES(1), k_fast_threshold<<<1, 32, 0, s>>>(lv, o->ctr, o->hist);
+    BM_COUNT_LAUNCHES(1), k_fast_threshold<<<1, 256, 0, s>>>(lv, o->ctr, o->hist);
     BM_COUNT_LAUNCHES(1), k_harris<<<(lv.total_cand + 255) / 256, 256, 0, s>>>(lv, o->pyr, o->cand, o->cand2, o->ctr);
     BM_COUNT_LAUNCHES(1), k_harris_select<<<BM_ORB_LEVELS, 1024, 0, s>>>(lv, o->cand2, o->ctr, o->keep);
     BM_COUNT_LAUNCHES(1), k_orb_emit<<<BM_ORB_LEVELS, 1024, 0, s>>>(lv, o->cand2, o->ctr, o->keep, *out);
     BM_COUNT_LAUNCHES(1), k_ic_angle<<<(BM_KP_CAP * 32) / 256, 256, 0, s>>>(lv, o->pyr, *out);
     BM_COUNT_LAUNCHES(1), k_orb_describe<<<BM_KP_CAP, 256, 0, s>>>(lv, o->pyr, *out);
     return cudaGetLastError();
+}
+
+// detectAndCompute is a fixed launch sequence per (input buffer, output buffer): captured once into a CUDA graph and replayed
+// (one launch call per frame instead of ~22; the kernels of the sequence run back to back without host launch gaps)
+cudaError_t bm_orb_detect(BmOrb* o, const uint8_t* d_gray, BmKeypoints* out) {
+    if (o->stream == nullptr || o->graphs_disabled) return orb_enqueue(o, d_gray, out);          // legacy stream cannot be captured
+    for (int i = 0; i < o->ngraphs; ++i)
+        if (o->graphs[i].gray == d_gray && o->graphs[i].out_pt == (const void*)out->pt) {
+            BM_COUNT_LAUNCHES(o->graphs[i].launches);
+            return cudaGraphLaunch(o->graphs[i].exec, o->stream);
+        }
+    if (o->ngraphs >= 8) return orb_enqueue(o, d_gray, out);
+    const long long before = g_bm_launches;
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(o->stream, cudaStreamCaptureModeRelaxed);
+    if (e != cudaSuccess) return e;
+    e = orb_enqueue(o, d_gray, out);
+    const cudaError_t e2 = cudaStreamEndCapture(o->stream, &graph);
+    const int launches = (int)(g_bm_launches - before);
+    g_bm_launches = before;
+    cudaGraphExec_t exec = nullptr;
+    if (e == cudaSuccess && e2 == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
+    else if (e == cudaSuccess) e = e2;
+    if (graph) cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { cudaGetLastError(); o->graphs_disabled = 1; return orb_enqueue(o, d_gray, out); }
+    BmOrbGraph& g = o->graphs[o->ngraphs++];
+    g.gray = d_gray; g.out_pt = out->pt; g.exec = exec; g.launches = launches;
+    BM_COUNT_LAUNCHES(launches);
+    return cudaGraphLaunch(exec, o->stream);
 }

@@ -28,6 +28,8 @@ struct BmKeypoints {
     int* count;         // device scalar
 };
 
+struct BmOrbGraph { const uint8_t* gray; const void* out_pt; cudaGraphExec_t exec; int launches; };
+
 struct BmOrb {
     int w, h, nfeatures;
     BmOrbLevels lv;
@@ -38,6 +40,8 @@ struct BmOrb {
     int* hist;          // [8][256]
     uint8_t* keep;      // keep flags for cand2
     cudaStream_t stream;
+    BmOrbGraph graphs[8];   // captured detect sequences, one per (input buffer, output buffer)
+    int ngraphs, graphs_disabled;
 };
 
 int bm_orb_create(BmOrb** out, int h, int w, int nfeatures, cudaStream_t s);
