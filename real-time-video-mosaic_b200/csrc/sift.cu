@@ -543,26 +543,25 @@ __device__ __forceinline__ bool kp_less(float ax, float ay, float as, float aa, 
 }
 
 // order the selected keypoints (cv2's KeyPoint_LessThan), rescale to the input image (first octave -1), emit
-__global__ void __launch_bounds__(1024) k_sift_emit(const int* __restrict__ ctr, const int* __restrict__ sel, const float2* __restrict__ kpt,
+__global__ void __launch_bounds__(256) k_sift_emit(const int* __restrict__ ctr, const int* __restrict__ sel, const float2* __restrict__ kpt,
                                                     const float* __restrict__ ksize, const float* __restrict__ kangle, const float* __restrict__ kresp,
                                                     const int* __restrict__ koct, BmKeypoints out) {
     const int m = ctr[3];
     __shared__ float s_x[1024], s_y[1024], s_s[1024], s_a[1024], s_r[1024];
     __shared__ int s_o[1024], s_i[1024];
-    for (int a0 = 0; a0 < m; a0 += blockDim.x) {               // (one round for m <= 1024)
-        const int a = a0 + threadIdx.x;
+    if ((int)(blockIdx.x * blockDim.x) >= m && blockIdx.x != 0) return;      // CTA b ranks keypoints [256 b, 256 b + 256)
+    {
+        const int a = blockIdx.x * blockDim.x + threadIdx.x;
         const int i = a < m ? sel[a] : 0;
         float2 pi = make_float2(0.f, 0.f); float si = 0.f, ai = 0.f, ri = 0.f; int oi = 0;
         if (a < m) { pi = kpt[i]; si = ksize[i]; ai = kangle[i]; ri = kresp[i]; oi = koct[i]; }
         int rank = 0;
         for (int b0 = 0; b0 < m; b0 += 1024) {                 // rank = number of selected keypoints ordered before this one
             __syncthreads();
-            const int b = b0 + threadIdx.x;
-            if (b < m) {
-                const int j = sel[b];
+            for (int b = b0 + threadIdx.x; b < min(m, b0 + 1024); b += blockDim.x) {
+                const int j = sel[b], q = b - b0;
                 const float2 pj = kpt[j];
-                s_x[threadIdx.x] = pj.x; s_y[threadIdx.x] = pj.y; s_s[threadIdx.x] = ksize[j]; s_a[threadIdx.x] = kangle[j];
-                s_r[threadIdx.x] = kresp[j]; s_o[threadIdx.x] = koct[j]; s_i[threadIdx.x] = j;
+                s_x[q] = pj.x; s_y[q] = pj.y; s_s[q] = ksize[j]; s_a[q] = kangle[j]; s_r[q] = kresp[j]; s_o[q] = koct[j]; s_i[q] = j;
             }
             __syncthreads();
             const int nb = min(1024, m - b0);
@@ -586,7 +585,7 @@ __global__ void __launch_bounds__(1024) k_sift_emit(const int* __restrict__ ctr,
             out.lxy[rank] = make_int2(0, 0);
         }
     }
-    if (threadIdx.x == 0) *out.count = m;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *out.count = m;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -830,7 +829,7 @@ static cudaError_t sift_enqueue(BmSift* o, const uint8_t* d_gray, BmKeypoints* o
     SIFT_OK(cudaMemcpyAsync(o->ctr + 6, o->ctr + 1, sizeof(int), cudaMemcpyDeviceToDevice, s));
     BM_COUNT_LAUNCHES(1), k_sift_orient<<<1024, 32 * SIFT_ORI_WARPS, 0, s>>>(L, o->pyr, o->cand, o->csel, 1, o->nfeatures, o->ctr, o->kpt, o->ksize, o->kangle, o->kresp, o->koct);
     BM_COUNT_LAUNCHES(1), k_sift_select<<<1, 1024, 0, s>>>(o->nfeatures, o->ctr + 1, SIFT_KP_CAP, o->ctr, o->kresp, o->sel, o->ctr + 3, nullptr);
-    BM_COUNT_LAUNCHES(1), k_sift_emit<<<1, 1024, 0, s>>>(o->ctr, o->sel, o->kpt, o->ksize, o->kangle, o->kresp, o->koct, *out);
+    BM_COUNT_LAUNCHES(1), k_sift_emit<<<BM_KP_CAP / 256, 256, 0, s>>>(o->ctr, o->sel, o->kpt, o->ksize, o->kangle, o->kresp, o->koct, *out);
     BM_COUNT_LAUNCHES(1), k_sift_describe<<<1024, 256, 0, s>>>(L, o->pyr, *out);
 #undef SIFT_OK
     return cudaGetLastError();
