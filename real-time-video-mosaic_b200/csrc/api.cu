@@ -64,6 +64,7 @@ struct bm_mosaic_s {
     int overlap = 1;                                    // 0: detect waits for the previous chain (clean chain timing)
     const uint8_t* prefetched = nullptr;                // host pointer staged by bm_prefetch_frame ...
     int prefetched_slot = -1;                           // ... into this slot
+    const uint8_t* begun = nullptr;                     // frame whose detect / match / RANSAC was already enqueued by the previous _end
     BmBlendBufs blend;
     // frame staging: double-buffered pinned host + device buffers
     uint8_t* h_stage[2] = {nullptr, nullptr};
@@ -92,6 +93,7 @@ struct bm_mosaic_s {
     double t_ms = 0.0, t_bytes = 0.0; int t_frames = 0;
 };
 
+static void cancel_early_begin(bm_mosaic_s* m);
 static size_t frame_bytes(const bm_config& c) { return (size_t)c.frame_h * c.frame_w * 3; }
 
 extern "C" bm_status bm_create(const bm_config* cfg, bm_handle* out) {
@@ -204,7 +206,7 @@ extern "C" bm_status bm_first_frame(bm_handle m, const uint8_t* h_bgr, size_t st
     if (!m || !h_bgr) { bm_set_error("bm_first_frame: null"); return BM_ERR_ARG; }
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
     const int fh = m->cfg.frame_h, fw = m->cfg.frame_w, ch = m->cfg.canvas_h, cw = m->cfg.canvas_w;
-    m->cur = 0; m->prefetched = nullptr;
+    m->cur = 0; m->prefetched = nullptr; m->begun = nullptr;
     BM_TRY(upload(m, h_bgr, stride, 0));
     BM_CUDA_OK(cudaStreamWaitEvent(m->stream, m->ev_up[0], 0));
     BM_CUDA_OK(cudaStreamWaitEvent(m->s_chain, m->ev_up[0], 0));
@@ -279,6 +281,7 @@ static bm_status warp_device(bm_mosaic_s* m, const uchar4* d_bgrx, const double 
 extern "C" bm_status bm_warp_frame(bm_handle m, const uint8_t* h_bgr, size_t stride, const double H[9], bm_frame_info* info) {
     if (!m || !h_bgr || !H) { bm_set_error("bm_warp_frame: null"); return BM_ERR_ARG; }
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+    cancel_early_begin(m);
     m->cur ^= 1;
     BM_TRY(stage_frame(m, h_bgr, stride, m->cur, m->s_chain));
     if (info) { memset(info, 0, sizeof(*info)); memcpy(info->H, H, 9 * sizeof(double)); }
@@ -288,6 +291,7 @@ extern "C" bm_status bm_warp_frame(bm_handle m, const uint8_t* h_bgr, size_t str
 extern "C" bm_status bm_warp_frame_async(bm_handle m, const uint8_t* h_bgr, size_t stride, const double H[9]) {
     if (!m || !h_bgr || !H) { bm_set_error("bm_warp_frame_async: null"); return BM_ERR_ARG; }
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+    cancel_early_begin(m);
     m->cur ^= 1;
     BM_TRY(stage_frame(m, h_bgr, stride, m->cur, m->s_chain));
     return warp_device(m, m->d_bgrx[m->cur], H, nullptr, false, m->cur);
@@ -302,6 +306,7 @@ extern "C" bm_status bm_warp_frame_device(bm_handle m, const uint8_t* d_bgrx, co
 extern "C" bm_status bm_upload_frame(bm_handle m, const uint8_t* h_bgr, size_t stride, const uint8_t** d_out) {
     if (!m || !h_bgr) return BM_ERR_ARG;
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+    cancel_early_begin(m);
     m->cur ^= 1;
     BM_TRY(stage_frame(m, h_bgr, stride, m->cur, m->s_chain));
     if (d_out) *d_out = reinterpret_cast<const uint8_t*>(m->d_bgrx[m->cur]);
@@ -428,14 +433,32 @@ static void matmul3(const double* A, const double* B, double* C) {
     }
 }
 
+// If bm_prefetch_frame staged the next frame into the free slot, start its detect / match / RANSAC now (the following
+// bm_process_frame_begin with the same pointer is then a no-op).  Only with stream overlap on.
+static bm_status early_begin(bm_mosaic_s* m) {
+    if (!m->overlap || !m->prefetched || m->prefetched_slot != (m->cur ^ 1)) return BM_OK;
+    m->cur ^= 1;
+    BM_CUDA_OK(cudaStreamWaitEvent(m->stream, m->ev_up[m->cur], 0));
+    bm_status st = bm_pipeline_estimate_begin(m->pipe, m->d_gray[m->cur]);
+    if (st < 0) { m->cur ^= 1; return st; }
+    m->begun = m->prefetched;
+    m->prefetched = nullptr;
+    return BM_OK;
+}
+
+// an early-begun frame that is not the one the caller continues with: its enqueued work is simply ignored
+static void cancel_early_begin(bm_mosaic_s* m) {
+    if (m->begun) { m->begun = nullptr; m->cur ^= 1; }
+}
+
 static bm_status finish_frame(bm_mosaic_s* m, int slot, bm_frame_info* info_out) {
     bm_frame_info info; memset(&info, 0, sizeof(info));
     // one small D2H read of (n_matches, H_rel): the reference's control flow (skip / reject prints) needs them on the host
     double H_rel[9]; int have_h = 0;
     bm_status st = bm_pipeline_estimate_end(m->pipe, &info, H_rel, &have_h);
     if (st < 0) { m->cur ^= 1; return st; }
-    if (info.n_matches < 4) { info.status = BM_SKIP_FEW_MATCHES; m->cur ^= 1; if (info_out) *info_out = info; return BM_SKIP_FEW_MATCHES; }
-    if (!have_h) { info.status = BM_SKIP_NO_H; m->cur ^= 1; if (info_out) *info_out = info; return BM_SKIP_NO_H; }
+    if (info.n_matches < 4) { info.status = BM_SKIP_FEW_MATCHES; m->cur ^= 1; BM_TRY(early_begin(m)); if (info_out) *info_out = info; return BM_SKIP_FEW_MATCHES; }
+    if (!have_h) { info.status = BM_SKIP_NO_H; m->cur ^= 1; BM_TRY(early_begin(m)); if (info_out) *info_out = info; return BM_SKIP_NO_H; }
     memcpy(info.H_rel, H_rel, 72);
     double Hv[9]; memcpy(Hv, H_rel, 72);
     info.validate_reason = validate_h(m, H_rel, &info.validate_value);
@@ -445,9 +468,12 @@ static bm_status finish_frame(bm_mosaic_s* m, int slot, bm_frame_info* info_out)
     smooth_h(m, Hv, Hs);
     matmul3(m->H_old, Hs, Habs);
     memcpy(info.H, Habs, 72);
+    bm_pipeline_advance(m->pipe);                                     // kp_prev/des_prev <- cur (main.py:756-759)
+    // the host decision is final: the staged next frame (if any) goes to the detect stream BEFORE this frame's chain is enqueued,
+    // so the device never waits for the ~10 launch calls of the chain
+    BM_TRY(early_begin(m));
     BM_TRY(warp_device(m, m->d_bgrx[slot], Habs, &info, false, slot));
     memcpy(m->H_old, Habs, 72);
-    bm_pipeline_advance(m->pipe);                                     // kp_prev/des_prev <- cur (main.py:756-759)
     info.status = ret;
     if (info_out) *info_out = info;
     return ret;
@@ -464,6 +490,8 @@ static bm_status order_after_chain(bm_mosaic_s* m) {
 extern "C" bm_status bm_process_frame_begin(bm_handle m, const uint8_t* h_bgr, size_t stride) {
     if (!m || !h_bgr) { bm_set_error("bm_process_frame_begin: null"); return BM_ERR_ARG; }
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+    if (m->begun == h_bgr) { m->begun = nullptr; return BM_OK; }      // already enqueued by the previous frame's _end
+    cancel_early_begin(m);
     m->cur ^= 1;
     BM_TRY(stage_frame(m, h_bgr, stride, m->cur, m->stream));
     BM_TRY(order_after_chain(m));
@@ -475,6 +503,7 @@ extern "C" bm_status bm_process_frame_begin(bm_handle m, const uint8_t* h_bgr, s
 extern "C" bm_status bm_process_frame_begin_device(bm_handle m, const uint8_t* d_bgr) {
     if (!m || !d_bgr) { bm_set_error("bm_process_frame_begin_device: null"); return BM_ERR_ARG; }
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+    cancel_early_begin(m);
     m->cur ^= 1; m->prefetched = nullptr;
     BM_CUDA_OK(cudaStreamWaitEvent(m->stream, m->ev_chain[m->cur], 0));      // the slot's previous chain still reads its BGRX copy
     BM_CUDA_OK(bm_launch_ingest(d_bgr, m->cfg.frame_h, m->cfg.frame_w, m->d_gray[m->cur], m->d_bgrx[m->cur], m->stream));
@@ -506,6 +535,7 @@ extern "C" bm_status bm_process_frame_device(bm_handle m, const uint8_t* d_bgr, 
 extern "C" bm_status bm_estimate_frame(bm_handle m, const uint8_t* h_bgr, size_t stride, bm_frame_info* info_out) {
     if (!m || !h_bgr) { bm_set_error("bm_estimate_frame: null"); return BM_ERR_ARG; }
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+    cancel_early_begin(m);
     m->cur ^= 1;
     BM_TRY(stage_frame(m, h_bgr, stride, m->cur, m->stream));
     bm_frame_info info; memset(&info, 0, sizeof(info));

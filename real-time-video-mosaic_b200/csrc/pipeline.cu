@@ -20,7 +20,8 @@ struct BmPipeline {
     BmSift* sift = nullptr;
     BmKeypoints kp[2];
     int prev = 0;
-    BmMatches m;
+    BmMatches m[2];          // double buffered: the next frame may be matched while the last one's matches are still readable
+    int mcur = 0, mdone = 0;
     uint8_t* d_mask = nullptr;
     BmRansacResult* d_res = nullptr;
     BmHostReadback* h_rb = nullptr;
@@ -31,9 +32,9 @@ bm_status bm_pipeline_create(BmPipeline** out, const bm_config& cfg, cudaStream_
     BmPipeline* p = new (std::nothrow) BmPipeline();
     if (!p) return BM_ERR_ARG;
     p->cfg = cfg; p->stream = stream;
-    memset(p->kp, 0, sizeof(p->kp)); memset(&p->m, 0, sizeof(p->m));
+    memset(p->kp, 0, sizeof(p->kp)); memset(p->m, 0, sizeof(p->m));
     const int desc_bytes = cfg.detector == BM_DET_ORB ? 32 : 128;
-    bool ok = bm_kp_alloc(&p->kp[0], desc_bytes) == 0 && bm_kp_alloc(&p->kp[1], desc_bytes) == 0 && bm_matches_alloc(&p->m) == 0 &&
+    bool ok = bm_kp_alloc(&p->kp[0], desc_bytes) == 0 && bm_kp_alloc(&p->kp[1], desc_bytes) == 0 && bm_matches_alloc(&p->m[0]) == 0 && bm_matches_alloc(&p->m[1]) == 0 &&
               cudaMalloc(&p->d_mask, BM_KP_CAP) == cudaSuccess && cudaMalloc(&p->d_res, sizeof(BmRansacResult)) == cudaSuccess &&
               cudaHostAlloc(&p->h_rb, sizeof(BmHostReadback), cudaHostAllocDefault) == cudaSuccess;
     if (ok) {
@@ -48,7 +49,7 @@ bm_status bm_pipeline_create(BmPipeline** out, const bm_config& cfg, cudaStream_
 void bm_pipeline_destroy(BmPipeline* p) {
     if (!p) return;
     bm_orb_destroy(p->orb); bm_sift_destroy(p->sift);
-    bm_kp_free(&p->kp[0]); bm_kp_free(&p->kp[1]); bm_matches_free(&p->m);
+    bm_kp_free(&p->kp[0]); bm_kp_free(&p->kp[1]); bm_matches_free(&p->m[0]); bm_matches_free(&p->m[1]);
     cudaFree(p->d_mask); cudaFree(p->d_res); cudaFreeHost(p->h_rb);
     delete p;
 }
@@ -71,19 +72,22 @@ bm_status bm_pipeline_estimate_begin(BmPipeline* p, const uint8_t* d_gray) {
     BmKeypoints& cur = p->kp[p->prev ^ 1];
     BmKeypoints& prev = p->kp[p->prev];
     BM_CUDA_OK(detect(p, d_gray, &cur));
-    if (p->orb) BM_CUDA_OK(bm_match_hamming(cur, prev, p->m, s));
-    else BM_CUDA_OK(bm_match_l2_ratio(cur, prev, p->m, 0.7, s));                         // main.py:691
-    BM_CUDA_OK(bm_launch_ransac(p->m.src, p->m.dst, p->m.count, 2.0, 2000, 0.995, p->d_mask, p->d_res, s));   // main.py:857
+    p->mcur ^= 1;
+    BmMatches& mm = p->m[p->mcur];
+    if (p->orb) BM_CUDA_OK(bm_match_hamming(cur, prev, mm, s));
+    else BM_CUDA_OK(bm_match_l2_ratio(cur, prev, mm, 0.7, s));                           // main.py:691
+    BM_CUDA_OK(bm_launch_ransac(mm.src, mm.dst, mm.count, 2.0, 2000, 0.995, p->d_mask, p->d_res, s));   // main.py:857
     BmHostReadback* rb = p->h_rb;
     BM_CUDA_OK(cudaMemcpyAsync(&rb->r, p->d_res, sizeof(BmRansacResult), cudaMemcpyDeviceToHost, s));
     BM_CUDA_OK(cudaMemcpyAsync(&rb->n_cur, cur.count, sizeof(int), cudaMemcpyDeviceToHost, s));
     BM_CUDA_OK(cudaMemcpyAsync(&rb->n_prev, prev.count, sizeof(int), cudaMemcpyDeviceToHost, s));
-    BM_CUDA_OK(cudaMemcpyAsync(&rb->n_matches, p->m.count, sizeof(int), cudaMemcpyDeviceToHost, s));
+    BM_CUDA_OK(cudaMemcpyAsync(&rb->n_matches, mm.count, sizeof(int), cudaMemcpyDeviceToHost, s));
     return BM_OK;
 }
 
 bm_status bm_pipeline_estimate_end(BmPipeline* p, bm_frame_info* info, double H_rel[9], int* have_h) {
     BM_CUDA_OK(cudaStreamSynchronize(p->stream));
+    p->mdone = p->mcur;
     BmHostReadback* rb = p->h_rb;
     info->n_kp_cur = rb->n_cur; info->n_kp_prev = rb->n_prev; info->n_matches = rb->n_matches;
     info->ransac_iters = rb->r.iters; info->n_inliers = rb->r.n_inliers;
@@ -101,4 +105,4 @@ bm_status bm_pipeline_estimate(BmPipeline* p, const uint8_t* d_gray, bm_frame_in
 void bm_pipeline_advance(BmPipeline* p) { p->prev ^= 1; }
 
 BmKeypoints* bm_pipeline_keypoints(BmPipeline* p, int which) { return &p->kp[which ? (p->prev ^ 1) : p->prev]; }
-BmMatches* bm_pipeline_matches(BmPipeline* p) { return &p->m; }
+BmMatches* bm_pipeline_matches(BmPipeline* p) { return &p->m[p->mdone]; }      // matches of the last frame that was waited for
