@@ -120,3 +120,23 @@ def test_prefetch_and_overlap_do_not_change_results(sweep_frames):
     for t in range(1, 7):
         assert vp.process_frame_ptr(pin.data_ptr() + t * fb, pin.data_ptr() + (t + 1) * fb if t + 1 < 7 else None) == 0
     assert np.array_equal(vp.output_img, want_canvas)
+
+
+def test_pipelined_calls_survive_skipped_frames(sweep_frames):
+    """a featureless frame in the middle is skipped (main.py:722-724: state not advanced); with next_frame= pipelining (staged
+    upload + early begin) the statuses, the trajectory and the canvas must equal the plain sequential run"""
+    import b200mosaic
+    frames, _ = sweep_frames
+    seq = list(frames[:3]) + [np.full_like(frames[0], 7)] + list(frames[3:])
+    def run(pipelined):
+        vm = b200mosaic.VideMosaic(seq[0], detector_type="orb", show_intermediate=False, visualize=False)
+        st = []
+        for t in range(1, len(seq)):
+            nxt = seq[t + 1] if (pipelined and t + 1 < len(seq)) else None
+            vm.process_frame(seq[t], t, next_frame=nxt)
+            st.append(vm.last_info.status)
+        return st, vm.H.copy(), vm.output_img.copy(), [(m.queryIdx, m.trainIdx) for m in vm.matches]
+    a, b = run(False), run(True)
+    assert a[0] == b[0] and a[0][2] != 0 and a[0].count(0) == len(seq) - 2      # exactly the blank frame is skipped
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert a[3] == b[3]                                                         # matches of the last finished frame
