@@ -177,7 +177,7 @@ def main():
     vm = b200mosaic.VideMosaic(frames[0], detector_type=args.detector, show_intermediate=False, visualize=False, device=local_rank)
     base = dev_frames.data_ptr()
     for i in range(1, W + 1):
-        vm.process_frame_device(base + i * fb)
+        vm.process_frame_device(base + i * fb, base + (i + 1) * fb)
     vm.sync()
     launches0 = lib.bm_kernel_launches()
     statuses = []
@@ -189,7 +189,7 @@ def main():
     e0.record()
     t0 = time.perf_counter()
     for i in range(W + 1, n):
-        statuses.append(vm.process_frame_device(base + i * fb))
+        statuses.append(vm.process_frame_device(base + i * fb, base + (i + 1) * fb if i + 1 < n else None))
     vm.sync()
     e1.record()
     torch.cuda.synchronize()

@@ -84,6 +84,7 @@ bm_status bm_process_frame_end(bm_handle h, bm_frame_info* info);
  * call with the same host pointer consumes the staged copy instead of uploading again.  The buffer must stay unchanged in
  * between (pageable buffers are copied to pinned staging memory immediately). */
 bm_status bm_prefetch_frame(bm_handle h, const uint8_t* h_bgr, size_t stride_bytes);
+bm_status bm_prefetch_frame_device(bm_handle h, const uint8_t* d_bgr);     /* frame already in device memory (packed BGR) */
 /* 1 (default): the warp/blend chain of frame t runs concurrently with detect/match/RANSAC of frame t+1 (separate streams);
  * 0: strictly one after the other (used to time the chain alone) */
 bm_status bm_set_overlap(bm_handle h, int on);

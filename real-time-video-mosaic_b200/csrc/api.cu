@@ -200,6 +200,18 @@ extern "C" bm_status bm_prefetch_frame(bm_handle m, const uint8_t* h_bgr, size_t
     return BM_OK;
 }
 
+// same for a frame that already lives in device memory (packed BGR): ingest into the free slot on the copy stream
+extern "C" bm_status bm_prefetch_frame_device(bm_handle m, const uint8_t* d_bgr) {
+    if (!m || !d_bgr) { bm_set_error("bm_prefetch_frame_device: null"); return BM_ERR_ARG; }
+    BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+    const int slot = m->cur ^ 1;
+    BM_CUDA_OK(cudaStreamWaitEvent(m->s_copy, m->ev_chain[slot], 0));
+    BM_CUDA_OK(bm_launch_ingest(d_bgr, m->cfg.frame_h, m->cfg.frame_w, m->d_gray[slot], m->d_bgrx[slot], m->s_copy));
+    BM_CUDA_OK(cudaEventRecord(m->ev_up[slot], m->s_copy));
+    m->prefetched = d_bgr; m->prefetched_slot = slot;
+    return BM_OK;
+}
+
 extern "C" bm_status bm_set_overlap(bm_handle m, int on) { if (!m) return BM_ERR_ARG; m->overlap = on ? 1 : 0; return BM_OK; }
 
 extern "C" bm_status bm_first_frame(bm_handle m, const uint8_t* h_bgr, size_t stride) {
@@ -503,11 +515,17 @@ extern "C" bm_status bm_process_frame_begin(bm_handle m, const uint8_t* h_bgr, s
 extern "C" bm_status bm_process_frame_begin_device(bm_handle m, const uint8_t* d_bgr) {
     if (!m || !d_bgr) { bm_set_error("bm_process_frame_begin_device: null"); return BM_ERR_ARG; }
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+    if (m->begun == d_bgr) { m->begun = nullptr; return BM_OK; }      // already enqueued by the previous frame's _end
     cancel_early_begin(m);
-    m->cur ^= 1; m->prefetched = nullptr;
-    BM_CUDA_OK(cudaStreamWaitEvent(m->stream, m->ev_chain[m->cur], 0));      // the slot's previous chain still reads its BGRX copy
-    BM_CUDA_OK(bm_launch_ingest(d_bgr, m->cfg.frame_h, m->cfg.frame_w, m->d_gray[m->cur], m->d_bgrx[m->cur], m->stream));
-    BM_CUDA_OK(cudaEventRecord(m->ev_up[m->cur], m->stream));
+    m->cur ^= 1;
+    if (m->prefetched == d_bgr && m->prefetched_slot == m->cur) {
+        BM_CUDA_OK(cudaStreamWaitEvent(m->stream, m->ev_up[m->cur], 0));
+    } else {
+        BM_CUDA_OK(cudaStreamWaitEvent(m->stream, m->ev_chain[m->cur], 0));      // the slot's previous chain still reads its BGRX copy
+        BM_CUDA_OK(bm_launch_ingest(d_bgr, m->cfg.frame_h, m->cfg.frame_w, m->d_gray[m->cur], m->d_bgrx[m->cur], m->stream));
+        BM_CUDA_OK(cudaEventRecord(m->ev_up[m->cur], m->stream));
+    }
+    m->prefetched = nullptr;
     BM_TRY(order_after_chain(m));
     bm_status st = bm_pipeline_estimate_begin(m->pipe, m->d_gray[m->cur]);
     if (st < 0) m->cur ^= 1;

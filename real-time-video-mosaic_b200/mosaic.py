@@ -165,10 +165,16 @@ class VideMosaic:
         self._canvas_cache = None
         return st
 
-    def process_frame_device(self, dev_ptr):
-        """process_frame on a frame already in device memory (packed BGR).  Returns the status."""
+    def process_frame_device(self, dev_ptr, next_ptr=None):
+        """process_frame on a frame already in device memory (packed BGR).  Returns the status.  next_ptr: device pointer of the
+        next frame (ingested and started while this one is finished, like process_frame_ptr's next_ptr)."""
         info = _lib.BmFrameInfo()
-        st = _lib.check(self._lib.bm_process_frame_device(self._h, C.c_void_p(dev_ptr), C.byref(info)), "bm_process_frame_device")
+        if next_ptr is None:
+            st = _lib.check(self._lib.bm_process_frame_device(self._h, C.c_void_p(dev_ptr), C.byref(info)), "bm_process_frame_device")
+        else:
+            _lib.check(self._lib.bm_process_frame_begin_device(self._h, C.c_void_p(dev_ptr)), "bm_process_frame_begin_device")
+            _lib.check(self._lib.bm_prefetch_frame_device(self._h, C.c_void_p(next_ptr)), "bm_prefetch_frame_device")
+            st = _lib.check(self._lib.bm_process_frame_end(self._h, C.byref(info)), "bm_process_frame_end")
         self.last_info = info
         self._canvas_cache = None
         return st
