@@ -264,13 +264,14 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i;
 }
 
-// K4: GaussianBlur(31) of both weight planes + blend + canvas update, one kernel.  CTA = 64 x 32 output pixels of W.
+// K4: GaussianBlur(31) of both weight planes + blend + canvas update, one kernel.  CTA = 64 x 64 output pixels of W (512 threads).
 // Per weight plane: tile with a 15 px halo (reflect-101 at the canvas border) -> shared memory; row pass, 8 consecutive
 // outputs per thread from a 38-value register window (cv2 order: tap 0 product, then FMAs left to right); column pass,
 // 8 consecutive outputs per thread from a 38-value window (cv2's symmetric FMA form).  Then the blend of main.py:905-927.
 // Shared-memory strides are odd and lanes walk rows (row pass) / columns (column pass): no bank conflicts.
 #define FB_TW 64
-#define FB_TH 32
+#define FB_TH 64
+#define FB_NT 512                         // threads: 64 columns x 8 groups of 8 rows in the column pass
 #define FB_SW (FB_TW + 2 * BM_BLUR_R)      // 94
 #define FB_SH (FB_TH + 2 * BM_BLUR_R)      // 62
 struct FbSmem {
@@ -285,14 +286,14 @@ __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(256, 3) k_blur_blend(BmFramePlan plan, const float* __restrict__ wnp, const float* __restrict__ wop,
+__global__ void __launch_bounds__(FB_NT, 2) k_blur_blend(BmFramePlan plan, const float* __restrict__ wnp, const float* __restrict__ wop,
                                                        const uchar4* __restrict__ wbuf, uchar4* __restrict__ canvas,
                                                        const int* __restrict__ flags) {
     extern __shared__ __align__(16) unsigned char fb_smem_raw[];
     FbSmem& sm = *reinterpret_cast<FbSmem*>(fb_smem_raw);
     const int tid = threadIdx.x;
     const int bx = plan.win.x0 + blockIdx.x * FB_TW, by = plan.win.y0 + blockIdx.y * FB_TH;     // canvas coords of the tile origin
-    const int c = tid & (FB_TW - 1), r0 = (tid >> 6) * 8;       // column pass / blend: 64 columns x 4 groups of 8 rows
+    const int c = tid & (FB_TW - 1), r0 = (tid >> 6) * 8;       // column pass / blend: 64 columns x 8 groups of 8 rows
     const int x = bx + c;
     const bool xin = x < plan.win.x1;
     const uchar4* __restrict__ wcol = wbuf + (size_t)(by + r0 - plan.win.y0) * plan.ws + (x - plan.win.x0);
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(256, 3) k_blur_blend(BmFramePlan plan, const f
 #pragma unroll
         for (int pl = 0; pl < 2; ++pl) {
             const float* __restrict__ src = pl ? wop : wnp;
-            for (int ty = warp; ty < FB_SH; ty += 8) {
+            for (int ty = warp; ty < FB_SH; ty += FB_NT / 32) {
                 const int gy = reflect101(by + ty - BM_BLUR_R, plan.canvas_h);
                 const bool yok = gy >= plan.reg.y0 && gy < plan.reg.y1;
                 const float* __restrict__ rowp = src + (yok ? (size_t)(gy - plan.reg.y0) * plan.rws : 0);
@@ -500,7 +501,7 @@ static cudaError_t blend_tail(const BmBlendBufs& b, const BmFramePlan& plan, cud
     const int xa[2] = {plan.rx0, 0}, xb[2] = {plan.reg.x1, ww};
     if ((e = bm_launch_dt_carries(b.dt, 2, xa, xb, b.flags, 1, s)) != cudaSuccess) return e;
     if ((e = bm_launch_dt_weights(b.dt, plan, b.wn, b.wo, b.flags, s)) != cudaSuccess) return e;
-    BM_COUNT_LAUNCHES(1), k_blur_blend<<<dim3(bm_div_up(ww, FB_TW), bm_div_up(wh, FB_TH)), 256, sizeof(FbSmem), s>>>(plan, b.wn, b.wo, b.wbuf, b.canvas, b.flags);
+    BM_COUNT_LAUNCHES(1), k_blur_blend<<<dim3(bm_div_up(ww, FB_TW), bm_div_up(wh, FB_TH)), FB_NT, sizeof(FbSmem), s>>>(plan, b.wn, b.wo, b.wbuf, b.canvas, b.flags);
     // refresh the persistent tables of the canvas plane for the rows the frame touched
     if ((e = bm_launch_rowscan_bgrx(b.canvas, b.canvas_w, 0, plan.win.y0, po, plan.win.y0, wh, b.flags, 0, s)) != cudaSuccess) return e;
     return bm_launch_dt_local(po, plan.win.y0 / BM_BLK_ROWS, bm_div_up(plan.win.y1, BM_BLK_ROWS), b.flags, 0, s);
