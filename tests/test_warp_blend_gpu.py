@@ -152,3 +152,27 @@ def test_handle_first_frame_and_warp_sequence(rng):
         assert d.max() <= 1 and np.mean(d > 0) < 2e-3
         assert vm.last_info.any_overlap == 1
     assert worst <= 1
+
+
+def test_full_size_1080p_chain_and_4k_distance_transform(ops, rng):
+    """the bench configuration itself: 1080p frames into the default 2160 x 2304 canvas (window ~ 1.1k x 1.9k, distances of
+    several hundred pixels), per step against the oracle on identical inputs; and the distance transform of a 4K-frame-sized
+    quad (two scan chunks per row, 140 row blocks)."""
+    import b200mosaic
+    from b200mosaic.synth import DroneSweep
+    sweep = DroneSweep(1920, 1080, seed=3, ground_size=4096, max_step=12.0)
+    frames = sweep.frames(4)
+    vm = b200mosaic.VideMosaic(frames[0], detector_type="orb", show_intermediate=False, visualize=False)
+    H = vm.H_old.copy()
+    for t in range(1, 4):
+        H = H @ sweep.D_true[t - 1]
+        before = vm.output_img.copy()
+        out = vm.warp(frames[t], H)
+        warped = cv2.warpPerspective(frames[t], H, (before.shape[1], before.shape[0]), flags=cv2.INTER_LINEAR)
+        want = blend_step_cv(before, warped)
+        d = np.abs(want.astype(np.int16) - out.astype(np.int16))
+        assert d.max() <= 1 and np.mean(d > 0) < 2e-3, (t, d.max(), np.mean(d > 0))
+    m = np.zeros((2240, 3904), np.uint8)
+    cv2.fillConvexPoly(m, np.array([[30, 40], [3870, 25], [3890, 2200], [12, 2215]], np.int32), 255)
+    m[1100, 2047] = 0
+    assert np.array_equal(cv2.distanceTransform(m, cv2.DIST_L2, 3), ops.distance_transform(dev(m)).cpu().numpy())
