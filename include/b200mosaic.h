@@ -90,8 +90,9 @@ bm_status bm_prefetch_frame_device(bm_handle h, const uint8_t* d_bgr);     /* fr
 bm_status bm_set_overlap(bm_handle h, int on);
 /* offline pair-sharded mode (config 3 at N GPUs): features of this frame, matches and RANSAC against the previous frame of
  * this handle, NO validation / warp; the frame always becomes the new "previous".  info->H_rel, n_matches, status
- * (BM_OK | BM_SKIP_FEW_MATCHES | BM_SKIP_NO_H) are filled. */
-bm_status bm_estimate_frame(bm_handle h, const uint8_t* h_bgr, size_t stride_bytes, bm_frame_info* info);
+ * (BM_OK | BM_SKIP_FEW_MATCHES | BM_SKIP_NO_H) are filled.  h_next (optional): the frame of the next call, staged (H2D + ingest) while
+ * this pair is estimated. */
+bm_status bm_estimate_frame(bm_handle h, const uint8_t* h_bgr, size_t stride_bytes, const uint8_t* h_next_or_null, bm_frame_info* info);
 /* canvas row-tile mode (config 5): empty the canvas (the caller then warps frame 0 with its own homography) */
 bm_status bm_clear_canvas(bm_handle h);
 /* canvas as packed BGR into a DEVICE buffer (e.g. a torch tensor that NCCL then gathers) */

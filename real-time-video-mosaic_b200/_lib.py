@@ -70,7 +70,7 @@ def load():
     _sig(lib, "bm_process_frame_begin", i, vp, vp, sz)
     _sig(lib, "bm_process_frame_begin_device", i, vp, vp)
     _sig(lib, "bm_process_frame_end", i, vp, C.POINTER(BmFrameInfo))
-    _sig(lib, "bm_estimate_frame", i, vp, vp, sz, C.POINTER(BmFrameInfo))
+    _sig(lib, "bm_estimate_frame", i, vp, vp, sz, vp, C.POINTER(BmFrameInfo))
     _sig(lib, "bm_prefetch_frame", i, vp, vp, sz)
     _sig(lib, "bm_prefetch_frame_device", i, vp, vp)
     _sig(lib, "bm_finalize", i, vp, i, i, i, i, vp, sz, ip, ip)

@@ -550,7 +550,7 @@ extern "C" bm_status bm_process_frame_device(bm_handle m, const uint8_t* d_bgr, 
     return bm_process_frame_end(m, info_out);
 }
 
-extern "C" bm_status bm_estimate_frame(bm_handle m, const uint8_t* h_bgr, size_t stride, bm_frame_info* info_out) {
+extern "C" bm_status bm_estimate_frame(bm_handle m, const uint8_t* h_bgr, size_t stride, const uint8_t* h_next, bm_frame_info* info_out) {
     if (!m || !h_bgr) { bm_set_error("bm_estimate_frame: null"); return BM_ERR_ARG; }
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
     cancel_early_begin(m);
@@ -558,7 +558,13 @@ extern "C" bm_status bm_estimate_frame(bm_handle m, const uint8_t* h_bgr, size_t
     BM_TRY(stage_frame(m, h_bgr, stride, m->cur, m->stream));
     bm_frame_info info; memset(&info, 0, sizeof(info));
     double H_rel[9]; int have_h = 0;
-    bm_status st = bm_pipeline_estimate(m->pipe, m->d_gray[m->cur], &info, H_rel, &have_h);
+    bm_status st = bm_pipeline_estimate_begin(m->pipe, m->d_gray[m->cur]);
+    if (st < 0) { m->cur ^= 1; return st; }
+    if (h_next) {                                  // the next frame's H2D + ingest overlap this pair's estimation
+        BM_TRY(upload(m, h_next, stride, m->cur ^ 1));
+        m->prefetched = h_next; m->prefetched_slot = m->cur ^ 1;
+    }
+    st = bm_pipeline_estimate_end(m->pipe, &info, H_rel, &have_h);
     if (st < 0) { m->cur ^= 1; return st; }
     bm_pipeline_advance(m->pipe);                  // pair (t-1, t): the frame always becomes "previous"
     bm_status ret = BM_OK;

@@ -170,18 +170,22 @@ def gather_tiles(tile, canvas_h, rank, world, dist=None):
 # ---------------------------------------------------------------------------------------------------------------
 # drivers on top of VideMosaic handles (GPU)
 # ---------------------------------------------------------------------------------------------------------------
-def estimate_pairs(frames, t_start, t_end, detector_type="sift", device=0):
-    """per-pair relative homographies for pairs t_start <= t < t_end; `frames` is indexable by absolute frame index."""
+def estimate_pairs(frames, t_start, t_end, detector_type="sift", device=0, vm=None):
+    """per-pair relative homographies for pairs t_start <= t < t_end; `frames` is indexable by absolute frame index.
+    `vm`: an existing handle whose previous frame is frames[t_start - 1] (reused, not closed); otherwise one is created."""
     from .mosaic import VideMosaic
     if t_end <= t_start:
         return [], []
-    vm = VideMosaic(frames[t_start - 1], detector_type=detector_type, show_intermediate=False, visualize=False, device=device)
+    own = vm is None
+    if own:
+        vm = VideMosaic(frames[t_start - 1], detector_type=detector_type, show_intermediate=False, visualize=False, device=device)
     st, Hs = [], []
     for t in range(t_start, t_end):
-        s, H, _ = vm.estimate_frame(frames[t])
+        s, H, _ = vm.estimate_frame(frames[t], frames[t + 1] if t + 1 < t_end else None)      # next frame's upload overlaps
         st.append(s)
         Hs.append(H)
-    vm.close()
+    if own:
+        vm.close()
     return st, Hs
 
 
