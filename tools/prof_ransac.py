@@ -1,8 +1,8 @@
-import sys; sys.path.insert(0,'.')
+import sys, pathlib; sys.path.insert(0, str(pathlib.Path(__file__).resolve().parent.parent))
 import numpy as np, ctypes as C
 from b200mosaic import _lib
 lib=_lib.load()
-g=np.load('tests/golden/clip01_orb.npz')
+g=np.load(str(pathlib.Path(__file__).resolve().parent.parent / 'tests/golden/clip01_orb.npz'))
 mm=g['matches1']; src=g['kp1'][mm[:,0].astype(int),:2].astype(np.float32); dst=g['kp0'][mm[:,1].astype(int),:2].astype(np.float32)
 def run(src,dst):
     H=np.zeros(9); cyc=np.zeros(8,np.int64); lm=C.c_int(0); js=C.c_int(0)
