@@ -463,6 +463,31 @@ __global__ void __launch_bounds__(1024) k_sift_select(int nfeatures, const int* 
     int n = *n_ptr; if (n > ncap) n = ncap;
     const int tid = threadIdx.x;
     unsigned thr_bits = 0;      // keep response bits >= thr_bits
+    if (n > nfeatures && n <= 1024) {
+        // short lists (the final keypoint list: ~900 entries): one value per thread, rank by counting -- a value is kept iff fewer
+        // than nfeatures values are strictly greater, which is exactly ">= the nfeatures-th largest, ties kept"
+        unsigned* vals = hist;
+        const unsigned mine = tid < n ? __float_as_uint(__ldg(kresp + tid)) : 0u;
+        vals[tid] = mine;
+        if (tid == 0) s_count = 0;
+        __syncthreads();
+        int greater = 0;
+        for (int j = 0; j < n; ++j) greater += vals[j] > mine ? 1 : 0;
+        const bool keep = tid < n && greater < nfeatures;
+        if (keep) { const int p = atomicAdd(&s_count, 1); if (p < BM_KP_CAP) sel[p] = tid; }
+        // threshold bits = the smallest kept value
+        unsigned kmin = keep ? mine : 0xffffffffu;
+        kmin = __reduce_min_sync(0xffffffffu, kmin);
+        if ((tid & 31) == 0) s_wsum[tid >> 5] = kmin;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned t = 0xffffffffu;
+            for (int w = 0; w < 32; ++w) t = min(t, s_wsum[w]);
+            *out_count = s_count;
+            if (out_thr) *out_thr = t;
+        }
+        return;
+    }
     if (n > nfeatures) {
         if (tid == 0) { s_prefix = 0; s_mask = 0; s_remaining = (unsigned)nfeatures; }
         __syncthreads();
