@@ -242,6 +242,11 @@ def main():
     tf = time.perf_counter()
     final_img = vm2.finalize()
     finalize_ms = 1e3 * (time.perf_counter() - tf)
+    # SURVEY 8f rank 3 (outside the timed region): the GUI's 400 x 300 progress thumbnail made on the device
+    vm2.preview()
+    tf = time.perf_counter()
+    thumb = vm2.preview()
+    preview_ms = 1e3 * (time.perf_counter() - tf)
     del vm2
 
     # ---------------- max over ranks ----------------
@@ -287,6 +292,15 @@ def main():
             tc = time.perf_counter()
             ofin.scale_to_screen(ofin.crop_black_areas(canvas, threshold=80, margin=30))
             finalize_cpu_ms = 1e3 * (time.perf_counter() - tc)
+        preview_cpu_ms = None
+        if cpu is not None:                               # gui.py:143-158 on the copy main.py:1630-1632 hands over (host side only)
+            try:
+                from oracle import preview as opv
+                tc = time.perf_counter()
+                opv.gui_thumbnail(canvas.copy())
+                preview_cpu_ms = 1e3 * (time.perf_counter() - tc)
+            except ImportError:
+                pass
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": 1e3 * dev_s / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8 / u32 fixed point (warp, DT, ORB) + f32 (blend weights, SIFT pyramid) + bf16 x bf16 -> f32 tensor cores (SIFT matching, exact) + f64 (RANSAC/LM)", "data": "synthetic",
@@ -307,7 +321,10 @@ def main():
                 "frames_ok": n_ok, "event_ms_per_step": ev_ms / K,
                 "finalize": {"what": "crop_black_areas(80, 30) + scale_to_screen of the final canvas (main.py:1647-1659) via bm_finalize, "
                                      "result copied to the host", "device_ms": finalize_ms, "out_shape": list(final_img.shape),
-                             "cpu_ms": finalize_cpu_ms}}
+                             "cpu_ms": finalize_cpu_ms},
+                "preview": {"what": "400 x 300 RGB progress thumbnail of the live canvas (gui.py:143-158: cvtColor + Pillow bicubic resize) via "
+                                    "bm_preview, result copied to the host; cpu_ms excludes the full-canvas D2H the reference path would need",
+                            "device_ms": preview_ms, "out_shape": list(thumb.shape), "cpu_ms": preview_cpu_ms}}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

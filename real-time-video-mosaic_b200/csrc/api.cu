@@ -7,6 +7,7 @@
 #include "warp_blend.cuh"
 #include "pipeline.cuh"
 #include "finalize.cuh"
+#include "preview.cuh"
 #include <stdarg.h>
 #include <string.h>
 #include <math.h>
@@ -77,6 +78,7 @@ struct bm_mosaic_s {
     uint8_t* d_canvas_bgr = nullptr;
     uint8_t* d_final = nullptr; size_t final_cap = 0;      // finalisation result (screen sized), allocated on first use
     int* d_bounds = nullptr;
+    BmPreviewPlan preview;                                  // thumbnail tables / buffers, built on first use
     // stitcher state (main.py:92-102)
     double H_old[9];
     double history[5][9];
@@ -151,6 +153,7 @@ extern "C" bm_status bm_destroy(bm_handle m) {
         if (m->ev_h2d[i]) cudaEventDestroy(m->ev_h2d[i]);
     }
     cudaFree(m->d_canvas_bgr); cudaFree(m->d_final); cudaFree(m->d_bounds);
+    bm_preview_free(&m->preview);
     for (int i = 0; i < bm_mosaic_s::kEvRing; ++i) { cudaEventDestroy(m->ev0[i]); cudaEventDestroy(m->ev1[i]); }
     for (int i = 0; i < 2; ++i) { if (m->ev_up[i]) cudaEventDestroy(m->ev_up[i]); if (m->ev_chain[i]) cudaEventDestroy(m->ev_chain[i]); }
     cudaStreamDestroy(m->stream); cudaStreamDestroy(m->s_chain); cudaStreamDestroy(m->s_copy);
@@ -383,6 +386,20 @@ extern "C" bm_status bm_finalize(bm_handle m, int threshold, int margin, int tar
     }
     BM_CUDA_OK(bm_launch_resize_linear(m->blend.canvas, cw, x, y, w, h, m->d_final, nw, nh, m->s_chain));
     BM_CUDA_OK(cudaMemcpyAsync(h_out, m->d_final, need, cudaMemcpyDeviceToHost, m->s_chain));
+    BM_CUDA_OK(cudaStreamSynchronize(m->s_chain));
+    return BM_OK;
+}
+
+// Thumbnail of the live canvas for progress callbacks: cv2.cvtColor(BGR2RGB) + PIL Image.resize((out_w, out_h)) of output_img
+// (gui.py:143-158 on the copy main.py:1630-1632 hands over), made on the device; ordered after the frames issued so far.
+extern "C" bm_status bm_preview(bm_handle m, int out_w, int out_h, int rgb, uint8_t* h_out, size_t cap_bytes) {
+    if (!m || !h_out || out_w < 1 || out_h < 1) return BM_ERR_ARG;
+    const size_t need = (size_t)out_w * out_h * 3;
+    if (cap_bytes < need) { bm_set_error("bm_preview: output buffer too small (%zu < %zu)", cap_bytes, need); return BM_ERR_ARG; }
+    BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+    BM_CUDA_OK(bm_preview_prepare(&m->preview, m->cfg.canvas_w, m->cfg.canvas_h, out_w, out_h, m->s_chain));
+    BM_CUDA_OK(bm_launch_preview(m->preview, m->blend.canvas, rgb, m->s_chain));
+    BM_CUDA_OK(cudaMemcpyAsync(h_out, m->preview.d_out, need, cudaMemcpyDeviceToHost, m->s_chain));
     BM_CUDA_OK(cudaStreamSynchronize(m->s_chain));
     return BM_OK;
 }

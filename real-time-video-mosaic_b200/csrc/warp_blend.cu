@@ -343,10 +343,20 @@ __global__ void __launch_bounds__(FB_NT, 2) k_blur_blend(BmFramePlan plan, const
             cp_async_commit();
         }
     }
+    // the thread's 8 warped and 8 canvas pixels: 16 independent loads issued together (a short-circuit test would chain them), kept
+    // in registers for the blend at the end -- this CTA is the only writer of these canvas pixels
+    unsigned wv[8], cv8[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+        wv[o] = 0u; cv8[o] = 0u;
+        if (o < nrow) {
+            wv[o] = __ldg(reinterpret_cast<const unsigned*>(wcol + (size_t)o * plan.ws));
+            cv8[o] = *reinterpret_cast<const unsigned*>(ccol + (size_t)o * plan.canvas_w);
+        }
+    }
     bool need = false;
 #pragma unroll
-    for (int o = 0; o < 8; ++o)
-        if (o < nrow && wcol[(size_t)o * plan.ws].w && ccol[(size_t)o * plan.canvas_w].w) need = true;
+    for (int o = 0; o < 8; ++o) need |= (wv[o] >> 24) && (cv8[o] >> 24);
     if (__syncthreads_or(need)) {                          // tiles without a single overlap pixel need no weights
 #pragma unroll
         for (int pl = 0; pl < 2; ++pl) {
@@ -390,19 +400,16 @@ __global__ void __launch_bounds__(FB_NT, 2) k_blur_blend(BmFramePlan plan, const
 #pragma unroll
     for (int o = 0; o < 8; ++o) {
         if (o >= nrow) break;
-        const uchar4 w = wcol[(size_t)o * plan.ws];
-        if (!w.w) continue;                                // canvas keeps its value where mask_new == 0
-        uchar4* cp = ccol + (size_t)o * plan.canvas_w;
-        const uchar4 cv = *cp;
-        if (!cv.w) { *cp = w; continue; }                  // non-overlap new: pixel copy (main.py:922-924)
+        const unsigned w = wv[o], cv = cv8[o];
+        if (!(w >> 24)) continue;                          // canvas keeps its value where mask_new == 0 (nrow rows only: wv = 0 beyond)
+        unsigned* cp = reinterpret_cast<unsigned*>(ccol + (size_t)o * plan.canvas_w);
+        if (!(cv >> 24)) { *cp = w; continue; }            // non-overlap new: pixel copy (main.py:922-924)
         const float wn = wgt[0][o], wo = wgt[1][o];
-        uchar4 ov;
         // float32(canvas)*w_old + float32(warped)*w_new, then astype(uint8) = truncation (main.py:905-910)
-        ov.x = (unsigned char)__float2int_rz(__fadd_rn(__fmul_rn((float)cv.x, wo), __fmul_rn((float)w.x, wn)));
-        ov.y = (unsigned char)__float2int_rz(__fadd_rn(__fmul_rn((float)cv.y, wo), __fmul_rn((float)w.y, wn)));
-        ov.z = (unsigned char)__float2int_rz(__fadd_rn(__fmul_rn((float)cv.z, wo), __fmul_rn((float)w.z, wn)));
-        ov.w = (ov.x | ov.y | ov.z) ? 255 : 0;
-        *cp = ov;
+        const unsigned ox = (unsigned)__float2int_rz(__fadd_rn(__fmul_rn((float)(cv & 255u), wo), __fmul_rn((float)(w & 255u), wn))) & 255u;
+        const unsigned oy = (unsigned)__float2int_rz(__fadd_rn(__fmul_rn((float)((cv >> 8) & 255u), wo), __fmul_rn((float)((w >> 8) & 255u), wn))) & 255u;
+        const unsigned oz = (unsigned)__float2int_rz(__fadd_rn(__fmul_rn((float)((cv >> 16) & 255u), wo), __fmul_rn((float)((w >> 16) & 255u), wn))) & 255u;
+        *cp = ox | (oy << 8) | (oz << 16) | ((ox | oy | oz) ? 0xff000000u : 0u);
     }
 }
 

@@ -222,6 +222,15 @@ class VideMosaic:
         self.last_crop_rect = tuple(rect)
         return out
 
+    def preview(self, size=(400, 300), rgb=True):
+        """Thumbnail of the live canvas made on the device: bit-identical to what the GUI computes from `output_img.copy()`
+        (main.py:1630-1632 -> gui.py:143-158: cv2.cvtColor(BGR2RGB), Image.fromarray(...).resize(size), Pillow's default bicubic),
+        but only size[0] * size[1] * 3 bytes are copied to the host.  Returns uint8 (size[1], size[0], 3), RGB (or BGR)."""
+        w, h = int(size[0]), int(size[1])
+        out = np.empty((h, w, 3), dtype=np.uint8)
+        _lib.check(self._lib.bm_preview(self._h, w, h, 1 if rgb else 0, out.ctypes.data_as(C.c_void_p), out.nbytes), "bm_preview")
+        return out
+
     def set_overlap(self, on):
         """True (default): the warp/blend chain of frame t overlaps detect/match/RANSAC of frame t+1; False: strictly serial"""
         _lib.check(self._lib.bm_set_overlap(self._h, 1 if on else 0), "bm_set_overlap")
