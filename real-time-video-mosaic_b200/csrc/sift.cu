@@ -295,6 +295,134 @@ __global__ void __launch_bounds__(256) k_sift_extrema(SiftLayout lay, int o, con
     }
 }
 
+// Tiled form of phase 1 for octaves whose rows are 16-byte aligned (w % 4 == 0, w >= 64): 12 % of the samples pass the cheap
+// centre-column test, but 82 % of all warps hold at least one of them, so in the per-pixel kernel nearly every warp pays for the
+// (serialised, short-circuit) 26-neighbour test of every layer.  Here a CTA stages a 64 x 16 tile (+1 halo) of the 5 DoG planes in
+// shared memory with whole-row float4 loads, compacts the samples that pass the centre-column test into a CTA list and runs the
+// neighbour test densely over that list (24 independent shared loads + a max / min tree).  Found extrema are collected per CTA:
+// one atomic on the global list counter per CTA instead of one per warp.  Same conjunction as cv2's test, evaluated in another order.
+#define EX_TW 64
+#define EX_TH 14                       // interior rows; 16 rows are staged (one float4 per thread and plane)
+#define EX_STRIDE 72                   // floats per tile row: [3] left halo, [4, 68) interior (16-byte aligned), [68] right halo
+#define EX_FOUND_CAP 256
+__global__ void __launch_bounds__(256) k_sift_extrema_tile(SiftLayout lay, int o, int kt, const float* __restrict__ pyr,
+                                                           unsigned* __restrict__ raw, int* __restrict__ ctr) {
+    __shared__ __align__(16) float sm[5][EX_TH + 2][EX_STRIDE];
+    __shared__ unsigned short s_list[EX_TW * EX_TH * 3];
+    __shared__ unsigned s_found[EX_FOUND_CAP];
+    __shared__ int s_n, s_nf, s_base;
+    const SiftOct& O = lay.o[o];                                     // stays in the parameter bank
+    const int w = O.w, h = O.h;
+    const size_t pn = (size_t)w * h;                                 // the 5 DoG planes of an octave are consecutive (checked by the launcher)
+    const float* __restrict__ dog = pyr + O.d[0];
+    const int tid = threadIdx.x, lane = tid & 31, q = tid & 15, rr = tid >> 4;
+    const int x0 = blockIdx.x * EX_TW, gx = x0 + 4 * q;
+    const int hl = tid >> 5, hr = (tid & 31) >> 1, side = tid & 1;   // halo duty of threads 0..159: plane, tile row, left / right
+    const int hx = side ? x0 + EX_TW : x0 - 1;
+    float* const my_sm = &sm[0][rr][4 + 4 * q];
+    float* const my_halo = &sm[tid < 160 ? hl : 0][hr][side ? 4 + EX_TW : 3];
+    const unsigned ebase = ((unsigned)rr << 8) | ((unsigned)(4 * q) << 2);
+    if (tid == 0) { s_n = 0; s_nf = 0; }
+    // a CTA walks kt vertically adjacent tiles: the per-thread address set-up is paid once
+    for (int it = 0; it < kt; ++it) {
+        const int y0 = (blockIdx.y * kt + it) * EX_TH - 1;           // tile row rr <-> image row y0 + rr
+        if (y0 + 1 >= h) break;
+        const int r = y0 + rr;
+        // stage the tile: the thread's own 4 pixels of the 5 planes stay in registers for the centre-column test
+        float4 d4[5];
+        {
+            const bool ok = gx < w && r >= 0 && r < h;
+            const float* __restrict__ src = dog + (size_t)(ok ? r : 0) * w + (ok ? gx : 0);
+#pragma unroll
+            for (int l = 0; l < 5; ++l) d4[l] = ok ? __ldg(reinterpret_cast<const float4*>(src + l * pn)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float hv = 0.f;
+            if (tid < 160) {
+                const int hy = y0 + hr;
+                if (hx >= 0 && hx < w && hy >= 0 && hy < h) hv = __ldg(dog + hl * pn + (size_t)hy * w + hx);
+            }
+#pragma unroll
+            for (int l = 0; l < 5; ++l) *reinterpret_cast<float4*>(my_sm + l * (EX_TH + 2) * EX_STRIDE) = d4[l];
+            if (tid < 160) *my_halo = hv;
+        }
+        // centre-column test of the thread's 4 pixels x 3 layers -> 12-bit mask (bit 3 j + l0 - 1); threshold = cvFloor(0.5*0.04/3*255) = 1
+        unsigned mask = 0;
+        if (rr >= 1 && rr <= EX_TH && r >= SIFT_BORDER && r < h - SIFT_BORDER) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = gx + j;
+                const bool inside = c >= SIFT_BORDER && c < w - SIFT_BORDER;
+                float d[5];
+#pragma unroll
+                for (int l = 0; l < 5; ++l) d[l] = j == 0 ? d4[l].x : j == 1 ? d4[l].y : j == 2 ? d4[l].z : d4[l].w;
+#pragma unroll
+                for (int l0 = 1; l0 <= SIFT_LAYERS; ++l0) {
+                    const float v = d[l0], hi = fmaxf(d[l0 - 1], d[l0 + 1]), lo = fminf(d[l0 - 1], d[l0 + 1]);
+                    const bool pre = inside & ((v > 1.0f & v >= hi) | (v < -1.0f & v <= lo));
+                    mask |= (pre ? 1u : 0u) << (3 * j + l0 - 1);
+                }
+            }
+        }
+        {   // CTA list of the survivors: warp scan of the counts, one shared atomic per warp
+            const int cnt = __popc(mask);
+            int inc = cnt;
+#pragma unroll
+            for (int dlt = 1; dlt < 32; dlt <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, dlt); if (lane >= dlt) inc += u; }
+            __syncthreads();                                           // counters are zero; the tile is complete
+            int base = 0;
+            if (lane == 31 && inc) base = atomicAdd(&s_n, inc);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            int at = base + inc - cnt;
+            while (mask) {
+                const unsigned b = __ffs(mask) - 1; mask &= mask - 1;
+                const unsigned j = (b * 11u) >> 5;                     // b / 3 for b < 12
+                s_list[at++] = (unsigned short)(ebase + (j << 2) + (b - 3u * j));
+            }
+        }
+        __syncthreads();
+        const int n = s_n;
+        for (int i = tid; i < n; i += 256) {
+            const unsigned e = s_list[i];
+            const int l0 = (e & 3) + 1, col = (e >> 2) & 63, row = e >> 8;
+            const float* __restrict__ ctrp = &sm[l0][row][4 + col];
+            const float v = *ctrp;
+            float mx = v, mn = v;
+#pragma unroll
+            for (int dl = -1; dl <= 1; ++dl)
+#pragma unroll
+                for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        if (dy == 0 && dx == 0) continue;          // the column itself was tested above
+                        const float t = ctrp[(dl * (EX_TH + 2) + dy) * EX_STRIDE + dx];
+                        mx = fmaxf(mx, t); mn = fminf(mn, t);
+                    }
+            if (v > 0 ? mx <= v : mn >= v) {
+                const unsigned word = ((unsigned)o << 28) | ((unsigned)(l0 - 1) << 26) | ((unsigned)(y0 + row) << 13) | (unsigned)(x0 + col);
+                const int k = atomicAdd(&s_nf, 1);
+                if (k < EX_FOUND_CAP) s_found[k] = word;
+                else {                                              // more than the CTA buffer holds: straight to the global list
+                    const int idx = atomicAdd(&ctr[4], 1);
+                    if (idx < SIFT_RAW_CAP) raw[idx] = word; else ctr[2] = 1;
+                }
+            }
+        }
+        __syncthreads();                                            // the tile and the list are free again; s_nf is final
+        const int nf = min(s_nf, EX_FOUND_CAP);
+        if (nf) {                                                   // (uniform) one atomic on the global list counter per CTA and tile
+            if (tid == 0) s_base = atomicAdd(&ctr[4], nf);
+            __syncthreads();
+            if (tid < nf) {
+                const int idx = s_base + tid;
+                if (idx < SIFT_RAW_CAP) raw[idx] = s_found[tid]; else ctr[2] = 1;
+            }
+        }
+        if (it + 1 < kt) {
+            __syncthreads();                                        // everybody has read s_n / s_nf / s_found
+            if (tid == 0) { s_n = 0; s_nf = 0; }
+        }
+    }
+}
+
 // Phase 2 -- adjustLocalExtrema: one thread per raw extremum
 __global__ void __launch_bounds__(128) k_sift_refine(SiftLayout lay, const float* __restrict__ pyr, const unsigned* __restrict__ raw,
                                                      unsigned* __restrict__ claim, SiftCand* __restrict__ cand, float* __restrict__ cresp,
@@ -842,7 +970,14 @@ static cudaError_t sift_enqueue(BmSift* o, const uint8_t* d_gray, BmKeypoints* o
         for (int l = 4; l <= 5; ++l) blur_level(l, o->pyr + O.g[l - 1], o->pyr + O.g[l], o->pyr + O.d[l - 1], nullptr, O.w, O.h, s2);
         if (O.w <= 2 * SIFT_BORDER || O.h <= 2 * SIFT_BORDER) continue;
         if (forked) { SIFT_OK(cudaEventRecord(o->ev_l5[oc], s2)); SIFT_OK(cudaStreamWaitEvent(s3, o->ev_l5[oc], 0)); }
-        BM_COUNT_LAUNCHES(1), k_sift_extrema<<<dim3((O.w + 31) / 32, (O.h + 7) / 8), blk, 0, s3>>>(L, oc, o->pyr, o->raw, o->ctr);
+        bool tiled = O.w >= EX_TW && (O.w & 3) == 0 && (reinterpret_cast<uintptr_t>(o->pyr) & 15) == 0;
+        for (int l = 0; l < 5; ++l) tiled = tiled && (O.d[l] & 3) == 0 && O.d[l] == O.d[0] + (long long)l * O.w * O.h;
+        if (tiled) {
+            const int tx = (O.w + EX_TW - 1) / EX_TW, ty = (O.h + EX_TH - 1) / EX_TH;
+            const int kt = tx * ty >= 8000 ? 4 : tx * ty >= 2000 ? 2 : 1;      // tiles walked by one CTA (keeps >= 2 waves of CTAs)
+            BM_COUNT_LAUNCHES(1), k_sift_extrema_tile<<<dim3(tx, (ty + kt - 1) / kt), 256, 0, s3>>>(L, oc, kt, o->pyr, o->raw, o->ctr);
+        }
+        else BM_COUNT_LAUNCHES(1), k_sift_extrema<<<dim3((O.w + 31) / 32, (O.h + 7) / 8), blk, 0, s3>>>(L, oc, o->pyr, o->raw, o->ctr);
     }
     if (forked) {
         SIFT_OK(cudaEventRecord(o->ev_join2, s2)); SIFT_OK(cudaEventRecord(o->ev_join3, s3));
