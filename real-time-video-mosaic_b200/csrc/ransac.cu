@@ -330,11 +330,12 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_ransac_homography(const float
 // code in a one-warp kernel (34.7k vs 2.9k cycles for the pivot searches of a 9x9 solve), so the serial algebra lives in
 // its own 32-thread launch; the 45-term normal-equation sums are strided over the lanes and reduced with shuffles.
 // ------------------------------------------------------------------------------------------------------------------
-#define RF_WARPS 4            // warp 0 runs the serial algebra; all four warps share the sums over the points
+#define RF_WARPS 4            // warp 0 runs the serial algebra; all four warps share the sums over the points (8 warps measured no faster)
 struct RfShared {
     double A[9][9], V[9];
     double lmA[8][8], lmv[8], lmd[8], lmx[8], lmxd[8], lmD[8];
     double M[9][10], X[9], P[9];
+    double G[9 * 18], Ainv[9][9];   // [A | I] elimination workspace, explicit inverse of the shifted LtL
     double sums[46];
     double wsum[RF_WARPS][46];      // per-warp partial sums of rf_accumulate
     const double* cmd_h;            // command block for the helper warps: parameter vector, Jacobian wanted, 0 = exit
@@ -373,6 +374,35 @@ __device__ __noinline__ bool warp_solve_spd(double (*M)[10], double* X, int N) {
     return ok;
 }
 
+// The same elimination on an N x NC augmented matrix (row-major, NC > N): with [A | I] the right half becomes inv(A) once every
+// row is divided by its pivot.  Columns evolve independently, so column N + c equals the right-hand side of a separate solve of
+// A x = e_c bit for bit -- eight 8x8 solves or six 9x9 factorizations collapse into one pass.
+template <int N, int NC>
+__device__ __noinline__ bool warp_gj_spd(double* M) {
+    constexpr int EPL = (N * NC + 31) / 32;
+    const int lane = threadIdx.x & 31;
+    int er[EPL], ek[EPL];
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) { const int e = lane + 32 * j; er[j] = e < N * NC ? e / NC : -1; ek[j] = e < N * NC ? e - er[j] * NC : 0; }
+    bool ok = true;
+    for (int c = 0; c < N; ++c) {
+        const double piv = M[c * NC + c];
+        if (!(piv > 0.0) || !isfinite(piv)) ok = false;
+        const double inv = __drcp_rn(piv);
+        double nv[EPL];
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) {
+            nv[j] = 0.0;
+            if (er[j] >= 0 && er[j] != c && ek[j] > c) nv[j] = M[er[j] * NC + ek[j]] - (M[er[j] * NC + c] * inv) * M[c * NC + ek[j]];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) if (er[j] >= 0 && er[j] != c && ek[j] > c) M[er[j] * NC + ek[j]] = nv[j];
+        __syncwarp();
+    }
+    return ok;
+}
+
 template <int NV>
 __device__ __forceinline__ void warp_sum(RfShared& sh, const double (&v)[NV]) {
     const int lane = threadIdx.x & 31;
@@ -386,9 +416,20 @@ __device__ __forceinline__ void warp_sum(RfShared& sh, const double (&v)[NV]) {
     __syncwarp();
 }
 
+template <int HALF>
+__device__ __forceinline__ void rf_halve(double (&v)[64], int hi, int xor_mask) {
+#pragma unroll
+    for (int i = 0; i < HALF; ++i) {
+        const double a = v[i], b = v[i + HALF];
+        const double send = hi ? a : b, keep = hi ? b : a;
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, xor_mask);
+    }
+}
+
 // HomographyRefineCallback sums over this warp's share of the points (i = tid, tid + 128, ...): JtJ (36), JtR (8), |r|^2, max |r|.
 // The Jacobian rows are j0 = (Mx*ww, My*ww, ww, 0, 0, 0, -Mx*ww*xi, -My*ww*xi), j1 = (0, 0, 0, Mx*ww, My*ww, ww, -Mx*ww*yi, -My*ww*yi):
-// products with a structural zero are skipped (0*x + y = y and s + 0 = s exactly, so the sums are bit-identical to the dense form).
+// products with a structural zero are skipped; the sums use fused multiply-adds (cv2's own gemm order is not reproducible either --
+// the refined H is compared within 0.5 px, tests/test_features_gpu.py).
 __device__ __noinline__ void rf_partial(RfShared& sh, const float2* src, const float2* dst, const uint8_t* mask, int n, const double* h, bool want_j) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr bool nz0[8] = {true, true, true, false, false, false, true, true}, nz1[8] = {false, false, false, true, true, true, true, true};
@@ -412,28 +453,36 @@ __device__ __noinline__ void rf_partial(RfShared& sh, const float2* src, const f
             for (int a = 0; a < 8; ++a) {
 #pragma unroll
                 for (int b = a; b < 8; ++b) {
-                    if (nz0[a] && nz0[b] && nz1[a] && nz1[b]) acc[k] += j0[a] * j0[b] + j1[a] * j1[b];
-                    else if (nz0[a] && nz0[b]) acc[k] += j0[a] * j0[b];
-                    else if (nz1[a] && nz1[b]) acc[k] += j1[a] * j1[b];
+                    if (nz0[a] && nz0[b] && nz1[a] && nz1[b]) acc[k] = __fma_rn(j1[a], j1[b], __fma_rn(j0[a], j0[b], acc[k]));
+                    else if (nz0[a] && nz0[b]) acc[k] = __fma_rn(j0[a], j0[b], acc[k]);
+                    else if (nz1[a] && nz1[b]) acc[k] = __fma_rn(j1[a], j1[b], acc[k]);
                     ++k;
                 }
             }
 #pragma unroll
             for (int a = 0; a < 8; ++a) {
-                if (nz0[a] && nz1[a]) acc[36 + a] += j0[a] * rx + j1[a] * ry;
-                else if (nz0[a]) acc[36 + a] += j0[a] * rx;
-                else acc[36 + a] += j1[a] * ry;
+                if (nz0[a] && nz1[a]) acc[36 + a] = __fma_rn(j1[a], ry, __fma_rn(j0[a], rx, acc[36 + a]));
+                else if (nz0[a]) acc[36 + a] = __fma_rn(j0[a], rx, acc[36 + a]);
+                else acc[36 + a] = __fma_rn(j1[a], ry, acc[36 + a]);
             }
         }
     }
     for (int o = 16; o > 0; o >>= 1) rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+    if (want_j) {
+        // 45 sums over 32 lanes by recursive halving: at every step a lane hands one half of its values to its partner and adds
+        // the partner's copy of the other half -- 62 exchanges instead of 45 x 5 (the shuffle unit is the bottleneck of this kernel)
+        double v[64];
 #pragma unroll
-    for (int k = 0; k < 45; ++k) {
-        if (!want_j && k != 44) continue;
-        double x = acc[k];
+        for (int k = 0; k < 64; ++k) v[k] = k < 45 ? acc[k] : 0.0;
+        rf_halve<32>(v, lane & 16, 16); rf_halve<16>(v, lane & 8, 8); rf_halve<8>(v, lane & 4, 4); rf_halve<4>(v, lane & 2, 2);
+        rf_halve<2>(v, lane & 1, 1);
+        if (2 * lane < 45) sh.wsum[warp][2 * lane] = v[0];            // lane L ends up with the totals of values 2L and 2L + 1
+        if (2 * lane + 1 < 45) sh.wsum[warp][2 * lane + 1] = v[1];
+    } else {
+        double x = acc[44];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if (lane == 0) sh.wsum[warp][k] = x;
+        if (lane == 0) sh.wsum[warp][44] = x;
     }
     if (lane == 0) sh.wsum[warp][45] = rmax;
 }
@@ -516,7 +565,7 @@ __global__ void __launch_bounds__(32 * RF_WARPS, 1) k_ransac_refine(const float2
 #pragma unroll
             for (int a = 0; a < 9; ++a) {
 #pragma unroll
-                for (int b = a; b < 9; ++b) acc[k++] += Lx[a] * Lx[b] + Ly[a] * Ly[b];
+                for (int b = a; b < 9; ++b) { acc[k] = __fma_rn(Ly[a], Ly[b], __fma_rn(Lx[a], Lx[b], acc[k])); ++k; }
             }
         }
         warp_sum<45>(sh, acc);
@@ -533,23 +582,34 @@ __global__ void __launch_bounds__(32 * RF_WARPS, 1) k_ransac_refine(const float2
         const double shift = 1e-13 * tr + 1e-300;
         if (lane < 9) sh.V[lane] = 1.0 + 0.37 * lane;
         __syncwarp();
+        // (A + shift I) is inverted once; every iteration is then a 9x9 matrix-vector product
+        for (int e = lane; e < 9 * 18; e += 32) {
+            const int r = e / 18, k = e - r * 18;
+            sh.G[e] = k < 9 ? sh.A[r][k] + (k == r ? shift : 0.0) : (k - 9 == r ? 1.0 : 0.0);
+        }
+        __syncwarp();
+        warp_gj_spd<9, 18>(sh.G);
+        for (int e = lane; e < 81; e += 32) { const int r = e / 9, k = e - r * 9; sh.Ainv[r][k] = sh.G[r * 18 + 9 + k] / sh.G[r * 18 + r]; }
+        __syncwarp();
+        // six inverse-iteration steps, normalised once at the end: the growth per step is bounded by 1 / shift <= 1e13 / trace, far
+        // from overflow, and the sign of the vector is irrelevant (H is scaled by 1 / h33 below)
+        double x = 0;
         for (int it = 0; it < 6; ++it) {
-            if (lane < 9) {
-                for (int k = 0; k < 9; ++k) sh.M[lane][k] = sh.A[lane][k] + (k == lane ? shift : 0.0);
-                sh.M[lane][9] = sh.V[lane];
-            }
+            x = 0;
+            if (lane < 9) for (int k = 0; k < 9; ++k) x = __fma_rn(sh.Ainv[lane][k], sh.V[k], x);
             __syncwarp();
-            warp_solve_spd(sh.M, sh.X, 9);
-            double nrm = 0, dot = 0;
-            for (int k = 0; k < 9; ++k) { nrm += sh.X[k] * sh.X[k]; dot += sh.X[k] * sh.V[k]; }
-            const double inv = rsqrt(nrm) * (dot < 0 ? -1.0 : 1.0);
-            double diff = 0;
-            for (int k = 0; k < 9; ++k) diff = fmax(diff, fabs(sh.X[k] * inv - sh.V[k]));
+            if (lane < 9) sh.V[lane] = x;
             __syncwarp();
-            if (lane < 9) sh.V[lane] = sh.X[lane] * inv;
+        }
+        {
+            double nrm = 0;
+            const double xx = lane < 9 ? x * x : 0.0;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) nrm += __shfl_sync(0xffffffffu, xx, k);
+            const double inv = rsqrt(nrm);
+            if (lane < 9) sh.V[lane] = x * inv;
             __syncwarp();
-            eig_iters = it + 1;
-            if (it > 0 && diff < 1e-15) break;
+            eig_iters = 6;
         }
         double h0[9];
 #pragma unroll
@@ -598,31 +658,37 @@ __global__ void __launch_bounds__(32 * RF_WARPS, 1) k_ransac_refine(const float2
         const bool ok = warp_solve_spd(sh.M, sh.X, 8);
         if (lane < 8) { const double d = ok ? sh.X[lane] : 0.0; sh.lmd[lane] = d; sh.lmxd[lane] = sh.lmx[lane] - d; }
         __syncwarp();
-        rf_accumulate(sh, src, dst, mask, n, sh.lmxd, false);
+        // error AND normal equations at the trial point in one pass over the points: when the step is accepted (the usual case) the
+        // sums are simply adopted below instead of being recomputed (same code, same order: bit-identical to a second pass)
+        rf_accumulate(sh, src, dst, mask, n, sh.lmxd, true);
         const double Sd = sh.sums[44];
-        double dS = 0, tdv = 0;
-        for (int a = 0; a < 8; ++a) {
+        // dS = d . (-A d + 2 v), tdv = d . v: lane a forms row a, the eight terms are added in index order (as a serial loop would)
+        double ta = 0, ua = 0;
+        if (lane < 8) {
             double Ad = 0;
-            for (int b = 0; b < 8; ++b) Ad += sh.lmA[a][b] * sh.lmd[b];
-            dS += sh.lmd[a] * (-Ad + 2.0 * sh.lmv[a]);
-            tdv += sh.lmd[a] * sh.lmv[a];
+            for (int b = 0; b < 8; ++b) Ad += sh.lmA[lane][b] * sh.lmd[b];
+            ta = sh.lmd[lane] * (-Ad + 2.0 * sh.lmv[lane]);
+            ua = sh.lmd[lane] * sh.lmv[lane];
         }
+        double dS = 0, tdv = 0;
+#pragma unroll
+        for (int a = 0; a < 8; ++a) { dS += __shfl_sync(0xffffffffu, ta, a); tdv += __shfl_sync(0xffffffffu, ua, a); }
         const double R = (S - Sd) / (fabs(dS) > DBL_EPSILON ? dS : 1.0);
         if (R > 0.75) { lambda *= 0.5; if (lambda < lc) lambda = 0.0; }
         else if (R < 0.25) {
             double nu = (Sd - S) / (fabs(tdv) > DBL_EPSILON ? tdv : 1.0) + 2.0;
             nu = fmin(fmax(nu, 2.0), 10.0);
             if (lambda == 0.0) {
-                double maxval = DBL_EPSILON;       // max |diag(inv(A))|: eight small solves
-                for (int c = 0; c < 8; ++c) {
-                    if (lane < 8) {
-                        for (int k = 0; k < 8; ++k) sh.M[lane][k] = sh.lmA[lane][k];
-                        sh.M[lane][8] = (lane == c) ? 1.0 : 0.0;
-                    }
-                    __syncwarp();
-                    if (warp_solve_spd(sh.M, sh.X, 8)) maxval = fmax(maxval, fabs(sh.X[c]));
-                    __syncwarp();
+                double maxval = DBL_EPSILON;       // max |diag(inv(A))|: one elimination of [A | I]
+                for (int e = lane; e < 8 * 16; e += 32) {
+                    const int r = e >> 4, k = e & 15;
+                    sh.G[e] = k < 8 ? sh.lmA[r][k] : (k - 8 == r ? 1.0 : 0.0);
                 }
+                __syncwarp();
+                if (warp_gj_spd<8, 16>(sh.G)) {
+                    for (int c = 0; c < 8; ++c) maxval = fmax(maxval, fabs(sh.G[c * 16 + 8 + c] / sh.G[c * 16 + c]));
+                }
+                __syncwarp();
                 lambda = lc = 1.0 / maxval;
                 nu *= 0.5;
             }
@@ -632,20 +698,21 @@ __global__ void __launch_bounds__(32 * RF_WARPS, 1) k_ransac_refine(const float2
         __syncwarp();
         if (accept) {
             S = Sd;
-            if (lane < 8) sh.lmx[lane] = sh.lmxd[lane];
-            __syncwarp();
-            rf_accumulate(sh, src, dst, mask, n, sh.lmx, true);
-            if (lane == 0) {
-                int k = 0;
-                for (int a = 0; a < 8; ++a) for (int b = a; b < 8; ++b) { sh.lmA[a][b] = sh.sums[k]; sh.lmA[b][a] = sh.sums[k]; ++k; }
-                for (int a = 0; a < 8; ++a) sh.lmv[a] = sh.sums[36 + a];
+            if (lane < 8) { sh.lmx[lane] = sh.lmxd[lane]; sh.lmv[lane] = sh.sums[36 + lane]; }
+            for (int t = lane; t < 36; t += 32) {          // unpack the upper triangle of JtJ
+                int a = 0, k = t;
+                while (k >= 8 - a) { k -= 8 - a; ++a; }
+                const int b = a + k;
+                sh.lmA[a][b] = sh.sums[t]; sh.lmA[b][a] = sh.sums[t];
             }
             __syncwarp();
             rinf = sh.sums[45];
         }
         ++it;
-        double dinf = 0;
-        for (int a = 0; a < 8; ++a) dinf = fmax(dinf, fabs(sh.lmd[a]));
+        double dinf = lane < 8 ? fabs(sh.lmd[lane]) : 0.0;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) dinf = fmax(dinf, __shfl_xor_sync(0xffffffffu, dinf, o));
+        dinf = __shfl_sync(0xffffffffu, dinf, 0);
         if (!(it < 10 && dinf >= (double)FLT_EPSILON && rinf >= (double)FLT_EPSILON)) break;
     }
     if (lane == 0) {
