@@ -62,6 +62,7 @@ struct bm_mosaic_s {
     cudaStream_t stream = nullptr, s_chain = nullptr, s_copy = nullptr;
     cudaEvent_t ev_up[2] = {nullptr, nullptr};          // upload + ingest of the slot finished
     cudaEvent_t ev_chain[2] = {nullptr, nullptr};       // last chain that read the slot's BGRX finished
+    cudaEvent_t ev_spec[2] = {nullptr, nullptr};        // last detect-ahead that read the slot's gray plane finished
     int overlap = 1;                                    // 0: detect waits for the previous chain (clean chain timing)
     const uint8_t* prefetched = nullptr;                // host pointer staged by bm_prefetch_frame ...
     int prefetched_slot = -1;                           // ... into this slot
@@ -117,6 +118,7 @@ extern "C" bm_status bm_create(const bm_config* cfg, bm_handle* out) {
     for (int i = 0; i < 2; ++i) {
         BM_CUDA_OK(cudaEventCreateWithFlags(&m->ev_up[i], cudaEventDisableTiming));
         BM_CUDA_OK(cudaEventCreateWithFlags(&m->ev_chain[i], cudaEventDisableTiming));
+        BM_CUDA_OK(cudaEventCreateWithFlags(&m->ev_spec[i], cudaEventDisableTiming));
     }
     // scratch: the window of a frame is at most the canvas; typical is frame-sized.  Size for the whole canvas when
     // it is small (<= 64 Mpx), otherwise for 4x the frame area plus margins (config 5: 32768^2 canvas, 4K frames).
@@ -155,7 +157,7 @@ extern "C" bm_status bm_destroy(bm_handle m) {
     cudaFree(m->d_canvas_bgr); cudaFree(m->d_final); cudaFree(m->d_bounds);
     bm_preview_free(&m->preview);
     for (int i = 0; i < bm_mosaic_s::kEvRing; ++i) { cudaEventDestroy(m->ev0[i]); cudaEventDestroy(m->ev1[i]); }
-    for (int i = 0; i < 2; ++i) { if (m->ev_up[i]) cudaEventDestroy(m->ev_up[i]); if (m->ev_chain[i]) cudaEventDestroy(m->ev_chain[i]); }
+    for (int i = 0; i < 2; ++i) { if (m->ev_up[i]) cudaEventDestroy(m->ev_up[i]); if (m->ev_chain[i]) cudaEventDestroy(m->ev_chain[i]); if (m->ev_spec[i]) cudaEventDestroy(m->ev_spec[i]); }
     cudaStreamDestroy(m->stream); cudaStreamDestroy(m->s_chain); cudaStreamDestroy(m->s_copy);
     delete m;
     return BM_OK;
@@ -179,7 +181,10 @@ static bm_status upload(bm_mosaic_s* m, const uint8_t* h_bgr, size_t stride, int
         src = m->h_stage[slot];
     }
     // the slot's previous tenant: its detect finished (the host waited for it), its chain may still be reading the BGRX copy
+    // (a detect-ahead of a frame the caller did not continue with may also still be reading the gray plane)
     BM_CUDA_OK(cudaStreamWaitEvent(m->s_copy, m->ev_chain[slot], 0));
+    BM_CUDA_OK(cudaStreamWaitEvent(m->s_copy, m->ev_spec[slot], 0));
+    bm_pipeline_drop_ahead(m->pipe, m->d_gray[slot]);
     BM_CUDA_OK(cudaMemcpyAsync(m->d_bgr[slot], src, fb, cudaMemcpyHostToDevice, m->s_copy));
     BM_CUDA_OK(cudaEventRecord(m->ev_h2d[slot], m->s_copy));
     BM_CUDA_OK(bm_launch_ingest(m->d_bgr[slot], fh, fw, m->d_gray[slot], m->d_bgrx[slot], m->s_copy));
@@ -209,6 +214,8 @@ extern "C" bm_status bm_prefetch_frame_device(bm_handle m, const uint8_t* d_bgr)
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
     const int slot = m->cur ^ 1;
     BM_CUDA_OK(cudaStreamWaitEvent(m->s_copy, m->ev_chain[slot], 0));
+    BM_CUDA_OK(cudaStreamWaitEvent(m->s_copy, m->ev_spec[slot], 0));
+    bm_pipeline_drop_ahead(m->pipe, m->d_gray[slot]);
     BM_CUDA_OK(bm_launch_ingest(d_bgr, m->cfg.frame_h, m->cfg.frame_w, m->d_gray[slot], m->d_bgrx[slot], m->s_copy));
     BM_CUDA_OK(cudaEventRecord(m->ev_up[slot], m->s_copy));
     m->prefetched = d_bgr; m->prefetched_slot = slot;
@@ -475,6 +482,18 @@ static bm_status early_begin(bm_mosaic_s* m) {
     return BM_OK;
 }
 
+// The next frame is staged and the current frame's detect / match / RANSAC are queued: queue the next frame's detectAndCompute behind
+// them NOW, before the host blocks on the RANSAC result -- the detect stream then runs straight on while the host takes the
+// skip / validate / smooth decision and issues the chain.  Without it the device idles for the wake-up + launch latency every frame.
+static bm_status detect_ahead(bm_mosaic_s* m) {
+    if (!m->overlap || !m->prefetched || m->prefetched_slot != (m->cur ^ 1)) return BM_OK;
+    const int slot = m->cur ^ 1;
+    BM_CUDA_OK(cudaStreamWaitEvent(m->stream, m->ev_up[slot], 0));
+    BM_TRY(bm_pipeline_detect_ahead(m->pipe, m->d_gray[slot]));
+    BM_CUDA_OK(cudaEventRecord(m->ev_spec[slot], m->stream));
+    return BM_OK;
+}
+
 // an early-begun frame that is not the one the caller continues with: its enqueued work is simply ignored
 static void cancel_early_begin(bm_mosaic_s* m) {
     if (m->begun) { m->begun = nullptr; m->cur ^= 1; }
@@ -484,6 +503,7 @@ static bm_status finish_frame(bm_mosaic_s* m, int slot, bm_frame_info* info_out)
     bm_frame_info info; memset(&info, 0, sizeof(info));
     // one small D2H read of (n_matches, H_rel): the reference's control flow (skip / reject prints) needs them on the host
     double H_rel[9]; int have_h = 0;
+    BM_TRY(detect_ahead(m));
     bm_status st = bm_pipeline_estimate_end(m->pipe, &info, H_rel, &have_h);
     if (st < 0) { m->cur ^= 1; return st; }
     if (info.n_matches < 4) { info.status = BM_SKIP_FEW_MATCHES; m->cur ^= 1; BM_TRY(early_begin(m)); if (info_out) *info_out = info; return BM_SKIP_FEW_MATCHES; }
@@ -539,6 +559,7 @@ extern "C" bm_status bm_process_frame_begin_device(bm_handle m, const uint8_t* d
         BM_CUDA_OK(cudaStreamWaitEvent(m->stream, m->ev_up[m->cur], 0));
     } else {
         BM_CUDA_OK(cudaStreamWaitEvent(m->stream, m->ev_chain[m->cur], 0));      // the slot's previous chain still reads its BGRX copy
+        bm_pipeline_drop_ahead(m->pipe, m->d_gray[m->cur]);                       // (a detect-ahead on m->stream is ordered before this ingest)
         BM_CUDA_OK(bm_launch_ingest(d_bgr, m->cfg.frame_h, m->cfg.frame_w, m->d_gray[m->cur], m->d_bgrx[m->cur], m->stream));
         BM_CUDA_OK(cudaEventRecord(m->ev_up[m->cur], m->stream));
     }
@@ -580,6 +601,7 @@ extern "C" bm_status bm_estimate_frame(bm_handle m, const uint8_t* h_bgr, size_t
     if (h_next) {                                  // the next frame's H2D + ingest overlap this pair's estimation
         BM_TRY(upload(m, h_next, stride, m->cur ^ 1));
         m->prefetched = h_next; m->prefetched_slot = m->cur ^ 1;
+        BM_TRY(detect_ahead(m));                   // and its features are computed while the host waits for this pair
     }
     st = bm_pipeline_estimate_end(m->pipe, &info, H_rel, &have_h);
     if (st < 0) { m->cur ^= 1; return st; }

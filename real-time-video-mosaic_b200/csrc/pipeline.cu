@@ -18,8 +18,11 @@ struct BmPipeline {
     cudaStream_t stream;
     BmOrb* orb = nullptr;
     BmSift* sift = nullptr;
-    BmKeypoints kp[2];
-    int prev = 0;
+    BmKeypoints kp[3];       // previous / current / detected ahead (the next frame's features may be computed before the host
+    int prev = 0, cur = 1;   // knows whether the current frame becomes "previous")
+    const uint8_t* ahead_gray = nullptr;     // gray buffer whose features were enqueued into kp[ahead_slot] by bm_pipeline_detect_ahead
+    int ahead_slot = -1;
+    cudaEvent_t ev_done = nullptr;           // RANSAC result + counts of the current frame are in the pinned readback
     BmMatches m[2];          // double buffered: the next frame may be matched while the last one's matches are still readable
     int mcur = 0, mdone = 0;
     uint8_t* d_mask = nullptr;
@@ -34,7 +37,8 @@ bm_status bm_pipeline_create(BmPipeline** out, const bm_config& cfg, cudaStream_
     p->cfg = cfg; p->stream = stream;
     memset(p->kp, 0, sizeof(p->kp)); memset(p->m, 0, sizeof(p->m));
     const int desc_bytes = cfg.detector == BM_DET_ORB ? 32 : 128;
-    bool ok = bm_kp_alloc(&p->kp[0], desc_bytes) == 0 && bm_kp_alloc(&p->kp[1], desc_bytes) == 0 && bm_matches_alloc(&p->m[0]) == 0 && bm_matches_alloc(&p->m[1]) == 0 &&
+    bool ok = bm_kp_alloc(&p->kp[0], desc_bytes) == 0 && bm_kp_alloc(&p->kp[1], desc_bytes) == 0 && bm_kp_alloc(&p->kp[2], desc_bytes) == 0 &&
+              cudaEventCreateWithFlags(&p->ev_done, cudaEventDisableTiming) == cudaSuccess && bm_matches_alloc(&p->m[0]) == 0 && bm_matches_alloc(&p->m[1]) == 0 &&
               cudaMalloc(&p->d_mask, BM_KP_CAP) == cudaSuccess && cudaMalloc(&p->d_res, sizeof(BmRansacResult)) == cudaSuccess &&
               cudaHostAlloc(&p->h_rb, sizeof(BmHostReadback), cudaHostAllocDefault) == cudaSuccess;
     if (ok) {
@@ -49,7 +53,9 @@ bm_status bm_pipeline_create(BmPipeline** out, const bm_config& cfg, cudaStream_
 void bm_pipeline_destroy(BmPipeline* p) {
     if (!p) return;
     bm_orb_destroy(p->orb); bm_sift_destroy(p->sift);
-    bm_kp_free(&p->kp[0]); bm_kp_free(&p->kp[1]); bm_matches_free(&p->m[0]); bm_matches_free(&p->m[1]);
+    bm_kp_free(&p->kp[0]); bm_kp_free(&p->kp[1]); bm_kp_free(&p->kp[2]);
+    if (p->ev_done) cudaEventDestroy(p->ev_done);
+    bm_matches_free(&p->m[0]); bm_matches_free(&p->m[1]);
     cudaFree(p->d_mask); cudaFree(p->d_res); cudaFreeHost(p->h_rb);
     delete p;
 }
@@ -60,7 +66,7 @@ static cudaError_t detect(BmPipeline* p, const uint8_t* d_gray, BmKeypoints* out
 }
 
 bm_status bm_pipeline_first_frame(BmPipeline* p, const uint8_t* d_gray) {
-    p->prev = 0;
+    p->prev = 0; p->cur = 1; p->ahead_gray = nullptr;
     BM_CUDA_OK(detect(p, d_gray, &p->kp[0]));
     p->have_prev = true;
     return BM_OK;
@@ -69,9 +75,11 @@ bm_status bm_pipeline_first_frame(BmPipeline* p, const uint8_t* d_gray) {
 bm_status bm_pipeline_estimate_begin(BmPipeline* p, const uint8_t* d_gray) {
     if (!p->have_prev) { bm_set_error("process_frame before first frame"); return BM_ERR_ARG; }
     cudaStream_t s = p->stream;
-    BmKeypoints& cur = p->kp[p->prev ^ 1];
+    if (p->ahead_gray == d_gray && p->ahead_slot != p->prev) p->cur = p->ahead_slot;      // features already enqueued (detect_ahead)
+    else { p->cur = (p->prev + 1) % 3; BM_CUDA_OK(detect(p, d_gray, &p->kp[p->cur])); }
+    p->ahead_gray = nullptr;
+    BmKeypoints& cur = p->kp[p->cur];
     BmKeypoints& prev = p->kp[p->prev];
-    BM_CUDA_OK(detect(p, d_gray, &cur));
     p->mcur ^= 1;
     BmMatches& mm = p->m[p->mcur];
     if (p->orb) BM_CUDA_OK(bm_match_hamming(cur, prev, mm, s));
@@ -82,11 +90,26 @@ bm_status bm_pipeline_estimate_begin(BmPipeline* p, const uint8_t* d_gray) {
     BM_CUDA_OK(cudaMemcpyAsync(&rb->n_cur, cur.count, sizeof(int), cudaMemcpyDeviceToHost, s));
     BM_CUDA_OK(cudaMemcpyAsync(&rb->n_prev, prev.count, sizeof(int), cudaMemcpyDeviceToHost, s));
     BM_CUDA_OK(cudaMemcpyAsync(&rb->n_matches, mm.count, sizeof(int), cudaMemcpyDeviceToHost, s));
+    BM_CUDA_OK(cudaEventRecord(p->ev_done, s));
     return BM_OK;
 }
 
+// detectAndCompute of the NEXT frame, enqueued behind the current frame's RANSAC before the host has read its result: whichever way
+// the skip / accept decision goes (main.py:722-731), the features of the next frame are needed and depend on nothing else.  They go
+// to the third keypoint slot; the following estimate_begin with the same gray buffer only adds match + RANSAC.
+bm_status bm_pipeline_detect_ahead(BmPipeline* p, const uint8_t* d_gray) {
+    if (!p->have_prev) return BM_OK;
+    const int slot = 3 - p->prev - p->cur;
+    if (slot < 0 || slot > 2 || slot == p->prev || slot == p->cur) return BM_OK;
+    BM_CUDA_OK(detect(p, d_gray, &p->kp[slot]));
+    p->ahead_gray = d_gray; p->ahead_slot = slot;
+    return BM_OK;
+}
+// the buffer is about to be overwritten: features detected ahead from it no longer describe its contents
+void bm_pipeline_drop_ahead(BmPipeline* p, const uint8_t* d_gray) { if (p && p->ahead_gray == d_gray) p->ahead_gray = nullptr; }
+
 bm_status bm_pipeline_estimate_end(BmPipeline* p, bm_frame_info* info, double H_rel[9], int* have_h) {
-    BM_CUDA_OK(cudaStreamSynchronize(p->stream));
+    BM_CUDA_OK(cudaEventSynchronize(p->ev_done));           // not the stream: a detect-ahead of the next frame may be queued behind
     p->mdone = p->mcur;
     BmHostReadback* rb = p->h_rb;
     info->n_kp_cur = rb->n_cur; info->n_kp_prev = rb->n_prev; info->n_matches = rb->n_matches;
@@ -102,7 +125,7 @@ bm_status bm_pipeline_estimate(BmPipeline* p, const uint8_t* d_gray, bm_frame_in
     return bm_pipeline_estimate_end(p, info, H_rel, have_h);
 }
 
-void bm_pipeline_advance(BmPipeline* p) { p->prev ^= 1; }
+void bm_pipeline_advance(BmPipeline* p) { p->prev = p->cur; }
 
-BmKeypoints* bm_pipeline_keypoints(BmPipeline* p, int which) { return &p->kp[which ? (p->prev ^ 1) : p->prev]; }
+BmKeypoints* bm_pipeline_keypoints(BmPipeline* p, int which) { return &p->kp[which ? p->cur : p->prev]; }
 BmMatches* bm_pipeline_matches(BmPipeline* p) { return &p->m[p->mdone]; }      // matches of the last frame that was waited for
