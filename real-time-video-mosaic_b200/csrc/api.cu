@@ -339,6 +339,7 @@ extern "C" bm_status bm_sync(bm_handle m) {
     if (!m) return BM_ERR_ARG;
     BM_CUDA_OK(cudaStreamSynchronize(m->s_copy));
     BM_CUDA_OK(cudaStreamSynchronize(m->stream));
+    if (m->pipe) BM_CUDA_OK(bm_pipeline_sync_est(m->pipe));
     BM_CUDA_OK(cudaStreamSynchronize(m->s_chain));
     return BM_OK;
 }

@@ -23,6 +23,11 @@ struct BmPipeline {
     const uint8_t* ahead_gray = nullptr;     // gray buffer whose features were enqueued into kp[ahead_slot] by bm_pipeline_detect_ahead
     int ahead_slot = -1;
     cudaEvent_t ev_done = nullptr;           // RANSAC result + counts of the current frame are in the pinned readback
+    // match + RANSAC run on their own stream: a handful of small, latency-bound launches (one-CTA RANSAC stages, selection sort) that
+    // would otherwise sit between two detects on the detect stream; with a detect-ahead queued they overlap the next frame's pyramid
+    cudaStream_t s_est = nullptr;
+    cudaEvent_t ev_det[3] = {nullptr, nullptr, nullptr};   // features of the slot are complete (recorded on the detect stream)
+    cudaEvent_t ev_est = nullptr;            // last match that read the keypoint slots finished (a detect may overwrite a slot)
     BmMatches m[2];          // double buffered: the next frame may be matched while the last one's matches are still readable
     int mcur = 0, mdone = 0;
     uint8_t* d_mask = nullptr;
@@ -38,7 +43,12 @@ bm_status bm_pipeline_create(BmPipeline** out, const bm_config& cfg, cudaStream_
     memset(p->kp, 0, sizeof(p->kp)); memset(p->m, 0, sizeof(p->m));
     const int desc_bytes = cfg.detector == BM_DET_ORB ? 32 : 128;
     bool ok = bm_kp_alloc(&p->kp[0], desc_bytes) == 0 && bm_kp_alloc(&p->kp[1], desc_bytes) == 0 && bm_kp_alloc(&p->kp[2], desc_bytes) == 0 &&
-              cudaEventCreateWithFlags(&p->ev_done, cudaEventDisableTiming) == cudaSuccess && bm_matches_alloc(&p->m[0]) == 0 && bm_matches_alloc(&p->m[1]) == 0 &&
+              cudaEventCreateWithFlags(&p->ev_done, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&p->ev_est, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&p->ev_det[0], cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&p->ev_det[1], cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&p->ev_det[2], cudaEventDisableTiming) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&p->s_est, cudaStreamNonBlocking) == cudaSuccess && bm_matches_alloc(&p->m[0]) == 0 && bm_matches_alloc(&p->m[1]) == 0 &&
               cudaMalloc(&p->d_mask, BM_KP_CAP) == cudaSuccess && cudaMalloc(&p->d_res, sizeof(BmRansacResult)) == cudaSuccess &&
               cudaHostAlloc(&p->h_rb, sizeof(BmHostReadback), cudaHostAllocDefault) == cudaSuccess;
     if (ok) {
@@ -52,17 +62,24 @@ bm_status bm_pipeline_create(BmPipeline** out, const bm_config& cfg, cudaStream_
 
 void bm_pipeline_destroy(BmPipeline* p) {
     if (!p) return;
+    if (p->s_est) cudaStreamSynchronize(p->s_est);
+    if (p->stream) cudaStreamSynchronize(p->stream);
     bm_orb_destroy(p->orb); bm_sift_destroy(p->sift);
     bm_kp_free(&p->kp[0]); bm_kp_free(&p->kp[1]); bm_kp_free(&p->kp[2]);
     if (p->ev_done) cudaEventDestroy(p->ev_done);
+    if (p->ev_est) cudaEventDestroy(p->ev_est);
+    for (int i = 0; i < 3; ++i) if (p->ev_det[i]) cudaEventDestroy(p->ev_det[i]);
+    if (p->s_est) cudaStreamDestroy(p->s_est);
     bm_matches_free(&p->m[0]); bm_matches_free(&p->m[1]);
     cudaFree(p->d_mask); cudaFree(p->d_res); cudaFreeHost(p->h_rb);
     delete p;
 }
 
 static cudaError_t detect(BmPipeline* p, const uint8_t* d_gray, BmKeypoints* out) {
-    if (p->orb) return bm_orb_detect(p->orb, d_gray, out);
-    return bm_sift_detect(p->sift, d_gray, out);
+    const int slot = (int)(out - p->kp);
+    cudaError_t e = p->orb ? bm_orb_detect(p->orb, d_gray, out) : bm_sift_detect(p->sift, d_gray, out);
+    if (e != cudaSuccess) return e;
+    return cudaEventRecord(p->ev_det[slot], p->stream);
 }
 
 bm_status bm_pipeline_first_frame(BmPipeline* p, const uint8_t* d_gray) {
@@ -74,12 +91,20 @@ bm_status bm_pipeline_first_frame(BmPipeline* p, const uint8_t* d_gray) {
 
 bm_status bm_pipeline_estimate_begin(BmPipeline* p, const uint8_t* d_gray) {
     if (!p->have_prev) { bm_set_error("process_frame before first frame"); return BM_ERR_ARG; }
-    cudaStream_t s = p->stream;
+    cudaStream_t s = p->s_est;
     if (p->ahead_gray == d_gray && p->ahead_slot != p->prev) p->cur = p->ahead_slot;      // features already enqueued (detect_ahead)
-    else { p->cur = (p->prev + 1) % 3; BM_CUDA_OK(detect(p, d_gray, &p->kp[p->cur])); }
+    else {
+        p->cur = (p->prev + 1) % 3;
+        // the slot may still be read by the match of a frame the caller abandoned (a detect-ahead never needs this: its slot is
+        // neither operand of the match in flight, and everything older has been waited for by the host)
+        BM_CUDA_OK(cudaStreamWaitEvent(p->stream, p->ev_est, 0));
+        BM_CUDA_OK(detect(p, d_gray, &p->kp[p->cur]));
+    }
     p->ahead_gray = nullptr;
     BmKeypoints& cur = p->kp[p->cur];
     BmKeypoints& prev = p->kp[p->prev];
+    BM_CUDA_OK(cudaStreamWaitEvent(s, p->ev_det[p->cur], 0));
+    BM_CUDA_OK(cudaStreamWaitEvent(s, p->ev_det[p->prev], 0));
     p->mcur ^= 1;
     BmMatches& mm = p->m[p->mcur];
     if (p->orb) BM_CUDA_OK(bm_match_hamming(cur, prev, mm, s));
@@ -91,6 +116,7 @@ bm_status bm_pipeline_estimate_begin(BmPipeline* p, const uint8_t* d_gray) {
     BM_CUDA_OK(cudaMemcpyAsync(&rb->n_prev, prev.count, sizeof(int), cudaMemcpyDeviceToHost, s));
     BM_CUDA_OK(cudaMemcpyAsync(&rb->n_matches, mm.count, sizeof(int), cudaMemcpyDeviceToHost, s));
     BM_CUDA_OK(cudaEventRecord(p->ev_done, s));
+    BM_CUDA_OK(cudaEventRecord(p->ev_est, s));
     return BM_OK;
 }
 
@@ -126,6 +152,7 @@ bm_status bm_pipeline_estimate(BmPipeline* p, const uint8_t* d_gray, bm_frame_in
 }
 
 void bm_pipeline_advance(BmPipeline* p) { p->prev = p->cur; }
+cudaError_t bm_pipeline_sync_est(BmPipeline* p) { return cudaStreamSynchronize(p->s_est); }
 
 BmKeypoints* bm_pipeline_keypoints(BmPipeline* p, int which) { return &p->kp[which ? p->cur : p->prev]; }
 BmMatches* bm_pipeline_matches(BmPipeline* p) { return &p->m[p->mdone]; }      // matches of the last frame that was waited for
