@@ -94,48 +94,108 @@ static int fast_total_tiles(const BmOrbLevels& lv) {
     return n;
 }
 
-__global__ void __launch_bounds__(256) k_fast_detect(BmOrbLevels lv, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ score,
-                                                     unsigned* __restrict__ corners, int* __restrict__ ctr) {
-    // corners of the tile are collected in shared memory and appended with ONE global atomic per CTA: a per-warp atomicAdd on the
-    // level counter serialises ~10^5 same-address atomics per frame in L2
+#define FT_S 40                        // row stride (bytes) of the staged 38 x 38 tile
+__global__ void __launch_bounds__(256) k_fast_detect(BmOrbLevels lv, const uint8_t* __restrict__ pyr, unsigned* __restrict__ corners,
+                                                     int* __restrict__ ctr) {
+    // The 32 x 32 tile (+3 ring) is staged in shared memory once.  Pass 1 applies the necessary condition "every opposite pair
+    // {k, k+8} holds a brighter (darker) pixel" on the four pairs k = 0, 2, 4, 6 -- any arc of 9 ring pixels contains at least one
+    // pixel of every pair -- which leaves a few percent of the pixels; they are compacted into a CTA list and pass 2 runs the full
+    // 16-pixel ring / 9-arc test densely over that list (per-pixel rejection alone does not help: nearly every warp holds a survivor).
+    // Corners are collected in shared memory and appended with ONE global atomic per CTA: a per-warp atomicAdd on the level counter
+    // serialises ~10^5 same-address atomics per frame in L2.  (The score map is cleared by a memset node in front of this kernel.)
     __shared__ unsigned s_list[1024];
-    __shared__ int s_n, s_base;
+    __shared__ unsigned short s_cand[1024];
+    __shared__ __align__(4) uint8_t tile[38 * FT_S];
+    __shared__ int s_n, s_nc, s_base;
     int level, x0, y0;
     if (!fast_tile(lv, level, x0, y0)) return;
-    if (threadIdx.x == 0 && threadIdx.y == 0) s_n = 0;
-    __syncthreads();
-    const BmOrbLevel L = lv.l[level];
-    const int x = x0 + threadIdx.x;
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx, lane = tx;
+    if (tid == 0) { s_n = 0; s_nc = 0; }
+    const int Lw = lv.l[level].w, Lh = lv.l[level].h;
+    {   // stage: thread (tx, ty) copies rows ty, ty + 8, ... of column tx (and column tx + 32 for tx < 6)
+        const int gx0 = x0 - 3 + tx, gx1 = gx0 + 32;
+        const bool ok0 = gx0 >= 0 && gx0 < Lw, ok1 = tx < 6 && gx1 < Lw;
+        int gy = y0 - 3 + ty;
+        const uint8_t* __restrict__ src = pyr + lv.l[level].off + (ptrdiff_t)gy * Lw + gx0;
+        uint8_t* dst = &tile[ty * FT_S + tx];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int y = y0 + threadIdx.y + 8 * k;
-        bool corner = false;
-        if (x < L.w && y < L.h) {
-            if (x >= 3 && y >= 3 && x < L.w - 3 && y < L.h - 3) {
-                int d[16];
-                fast_ring(pyr + L.off + (size_t)y * L.w + x, L.w, d);
-                unsigned P = 0, N = 0;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) { P |= (unsigned)(d[i] > FAST_THR) << i; N |= (unsigned)(d[i] < -FAST_THR) << i; }
-                corner = has9(P) || has9(N);
+        for (int it = 0; it < 5; ++it) {
+            if (it < 4 || ty < 6) {
+                const bool oky = gy >= 0 && gy < Lh;
+                dst[0] = (oky && ok0) ? __ldg(src) : (uint8_t)0;
+                if (tx < 6) dst[32] = (oky && ok1) ? __ldg(src + 32) : (uint8_t)0;
             }
-            score[L.off + (size_t)y * L.w + x] = 0;
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, corner);
-        if (bal) {
-            const int lane = threadIdx.x & 31, leader = __ffs(bal) - 1;
-            int base = 0;
-            if (lane == leader) base = atomicAdd(&s_n, __popc(bal));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (corner) s_list[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned)x | ((unsigned)y << 16);
+            gy += 8; src += 8 * Lw; dst += 8 * FT_S;
         }
     }
     __syncthreads();
-    const int n = s_n, cap = (L.w * L.h) / 2;
-    if (threadIdx.x == 0 && threadIdx.y == 0 && n > 0) s_base = atomicAdd(&ctr[40 + level], n);
+    const int x = x0 + tx;
+    unsigned surv = 0;                                    // bit k: pixel (tx, ty + 8k) passed the pair test
+    if (x >= 3 && x < Lw - 3) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int ly = ty + 8 * k, y = y0 + ly;
+            if (y >= 3 && y < Lh - 3) {
+                const uint8_t* p = &tile[(ly + 3) * FT_S + tx + 3];
+                const int c = p[0], lo = c - FAST_THR, hi = c + FAST_THR;      // ring pixel brighter-than-centre bit: c - r > thr <=> r < lo
+                const int r0 = p[3 * FT_S], r8 = p[-3 * FT_S], r4 = p[3], r12 = p[-3];
+                const int r2 = p[2 * FT_S + 2], r10 = p[-2 * FT_S - 2], r6 = p[-2 * FT_S + 2], r14 = p[2 * FT_S - 2];
+                // min of a pair < lo <=> one of them is; max of a pair > hi likewise
+                const int mn = max(max(min(r0, r8), min(r4, r12)), max(min(r2, r10), min(r6, r14)));
+                const int mx = min(min(max(r0, r8), max(r4, r12)), min(max(r2, r10), max(r6, r14)));
+                if (mn < lo || mx > hi) surv |= 1u << k;
+            }
+        }
+    }
+    {   // CTA list of the survivors: warp scan of the counts, one shared atomic per warp
+        const int cnt = __popc(surv);
+        int inc = cnt;
+#pragma unroll
+        for (int dlt = 1; dlt < 32; dlt <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, dlt); if (lane >= dlt) inc += u; }
+        int base = 0;
+        if (lane == 31 && inc) base = atomicAdd(&s_nc, inc);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        int at = base + inc - cnt;
+        while (surv) {
+            const int k = __ffs(surv) - 1; surv &= surv - 1;
+            s_cand[at++] = (unsigned short)(((ty + 8 * k) << 5) | tx);
+        }
+    }
     __syncthreads();
-    for (int i = threadIdx.y * 32 + threadIdx.x; i < n; i += 256) {
-        if (s_base + i < cap) corners[L.off / 2 + s_base + i] = s_list[i];
+    const int nc = s_nc;
+    for (int i0 = 0; i0 < nc; i0 += 256) {
+        if (i0 + (tid & ~31) >= nc) break;                 // (warp-uniform) nothing left for this warp
+        const int i = i0 + tid;
+        bool corner = false;
+        unsigned xy = 0;
+        if (i < nc) {
+            const unsigned e = s_cand[i];
+            const int lx = e & 31, ly = e >> 5;
+            int d[16];
+            fast_ring(&tile[(ly + 3) * FT_S + lx + 3], FT_S, d);
+            unsigned P = 0, N = 0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { P |= (unsigned)(d[j] > FAST_THR) << j; N |= (unsigned)(d[j] < -FAST_THR) << j; }
+            corner = has9(P) || has9(N);
+            xy = (unsigned)(x0 + lx) | ((unsigned)(y0 + ly) << 16);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, corner);
+        if (bal) {
+            const int leader = __ffs(bal) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&s_n, __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (corner) s_list[base + __popc(bal & ((1u << lane) - 1u))] = xy;
+        }
+    }
+    __syncthreads();
+    const int n = s_n;
+    if (n == 0) return;
+    const int cap = (Lw * Lh) / 2, off2 = lv.l[level].off / 2;
+    if (tid == 0) s_base = atomicAdd(&ctr[40 + level], n);
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) {
+        if (s_base + i < cap) corners[off2 + s_base + i] = s_list[i];
         else ctr[32] = 1;
     }
 }
@@ -539,7 +599,8 @@ static cudaError_t orb_enqueue(BmOrb* o, const uint8_t* d_gray, BmKeypoints* out
     }
     const int tiles0 = ((lv.l[0].w + 31) / 32) * ((lv.l[0].h + 7) / 8);
     const int cblocks = 148;                               // per level; the per-corner kernels stride over the corner lists
-    BM_COUNT_LAUNCHES(1), k_fast_detect<<<fast_total_tiles(lv), blk, 0, s>>>(lv, o->pyr, o->score, o->corners, o->ctr);
+    if ((e = cudaMemsetAsync(o->score, 0, (size_t)lv.total_px, s)) != cudaSuccess) return e;
+    BM_COUNT_LAUNCHES(1), k_fast_detect<<<fast_total_tiles(lv), blk, 0, s>>>(lv, o->pyr, o->corners, o->ctr);
     BM_COUNT_LAUNCHES(1), k_fast_cscore<<<dim3(cblocks, BM_ORB_LEVELS), 256, 0, s>>>(lv, o->pyr, o->corners, o->ctr, o->score);
     BM_COUNT_LAUNCHES(1), k_fast_cnms<<<dim3(cblocks, BM_ORB_LEVELS), 256, 0, s>>>(lv, o->score, o->corners, o->cand, o->ctr, o->hist);
     BM_COUNT_LAUNCHES(1), k_fast_threshold<<<1, 256, 0, s>>>(lv, o->ctr, o->hist);
