@@ -62,7 +62,7 @@ struct bm_mosaic_s {
     cudaStream_t stream = nullptr, s_chain = nullptr, s_copy = nullptr;
     cudaEvent_t ev_up[2] = {nullptr, nullptr};          // upload + ingest of the slot finished
     cudaEvent_t ev_chain[2] = {nullptr, nullptr};       // last chain that read the slot's BGRX finished
-    cudaEvent_t ev_spec[2] = {nullptr, nullptr};        // last detect-ahead that read the slot's gray plane finished
+    cudaEvent_t ev_spec[2] = {nullptr, nullptr};        // last detect-ahead that read the slot's gray plane finished (owned by the pipeline)
     int overlap = 1;                                    // 0: detect waits for the previous chain (clean chain timing)
     const uint8_t* prefetched = nullptr;                // host pointer staged by bm_prefetch_frame ...
     int prefetched_slot = -1;                           // ... into this slot
@@ -118,7 +118,6 @@ extern "C" bm_status bm_create(const bm_config* cfg, bm_handle* out) {
     for (int i = 0; i < 2; ++i) {
         BM_CUDA_OK(cudaEventCreateWithFlags(&m->ev_up[i], cudaEventDisableTiming));
         BM_CUDA_OK(cudaEventCreateWithFlags(&m->ev_chain[i], cudaEventDisableTiming));
-        BM_CUDA_OK(cudaEventCreateWithFlags(&m->ev_spec[i], cudaEventDisableTiming));
     }
     // scratch: the window of a frame is at most the canvas; typical is frame-sized.  Size for the whole canvas when
     // it is small (<= 64 Mpx), otherwise for 4x the frame area plus margins (config 5: 32768^2 canvas, 4K frames).
@@ -148,6 +147,7 @@ extern "C" bm_status bm_destroy(bm_handle m) {
     if (!m) return BM_OK;
     cudaSetDevice(m->cfg.device);
     cudaStreamSynchronize(m->stream); cudaStreamSynchronize(m->s_chain); cudaStreamSynchronize(m->s_copy);
+    if (m->pipe) bm_pipeline_sync_est(m->pipe);
     bm_pipeline_destroy(m->pipe);
     free_blend(m->blend);
     for (int i = 0; i < 2; ++i) {
@@ -157,7 +157,7 @@ extern "C" bm_status bm_destroy(bm_handle m) {
     cudaFree(m->d_canvas_bgr); cudaFree(m->d_final); cudaFree(m->d_bounds);
     bm_preview_free(&m->preview);
     for (int i = 0; i < bm_mosaic_s::kEvRing; ++i) { cudaEventDestroy(m->ev0[i]); cudaEventDestroy(m->ev1[i]); }
-    for (int i = 0; i < 2; ++i) { if (m->ev_up[i]) cudaEventDestroy(m->ev_up[i]); if (m->ev_chain[i]) cudaEventDestroy(m->ev_chain[i]); if (m->ev_spec[i]) cudaEventDestroy(m->ev_spec[i]); }
+    for (int i = 0; i < 2; ++i) { if (m->ev_up[i]) cudaEventDestroy(m->ev_up[i]); if (m->ev_chain[i]) cudaEventDestroy(m->ev_chain[i]); }
     cudaStreamDestroy(m->stream); cudaStreamDestroy(m->s_chain); cudaStreamDestroy(m->s_copy);
     delete m;
     return BM_OK;
@@ -183,7 +183,7 @@ static bm_status upload(bm_mosaic_s* m, const uint8_t* h_bgr, size_t stride, int
     // the slot's previous tenant: its detect finished (the host waited for it), its chain may still be reading the BGRX copy
     // (a detect-ahead of a frame the caller did not continue with may also still be reading the gray plane)
     BM_CUDA_OK(cudaStreamWaitEvent(m->s_copy, m->ev_chain[slot], 0));
-    BM_CUDA_OK(cudaStreamWaitEvent(m->s_copy, m->ev_spec[slot], 0));
+    if (m->ev_spec[slot]) BM_CUDA_OK(cudaStreamWaitEvent(m->s_copy, m->ev_spec[slot], 0));
     bm_pipeline_drop_ahead(m->pipe, m->d_gray[slot]);
     BM_CUDA_OK(cudaMemcpyAsync(m->d_bgr[slot], src, fb, cudaMemcpyHostToDevice, m->s_copy));
     BM_CUDA_OK(cudaEventRecord(m->ev_h2d[slot], m->s_copy));
@@ -214,7 +214,7 @@ extern "C" bm_status bm_prefetch_frame_device(bm_handle m, const uint8_t* d_bgr)
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
     const int slot = m->cur ^ 1;
     BM_CUDA_OK(cudaStreamWaitEvent(m->s_copy, m->ev_chain[slot], 0));
-    BM_CUDA_OK(cudaStreamWaitEvent(m->s_copy, m->ev_spec[slot], 0));
+    if (m->ev_spec[slot]) BM_CUDA_OK(cudaStreamWaitEvent(m->s_copy, m->ev_spec[slot], 0));
     bm_pipeline_drop_ahead(m->pipe, m->d_gray[slot]);
     BM_CUDA_OK(bm_launch_ingest(d_bgr, m->cfg.frame_h, m->cfg.frame_w, m->d_gray[slot], m->d_bgrx[slot], m->s_copy));
     BM_CUDA_OK(cudaEventRecord(m->ev_up[slot], m->s_copy));
@@ -244,6 +244,7 @@ extern "C" bm_status bm_first_frame(bm_handle m, const uint8_t* h_bgr, size_t st
     m->history_len = 0;
     BM_TRY(bm_pipeline_first_frame(m->pipe, m->d_gray[0]));                  // main.py:104-112
     BM_CUDA_OK(cudaStreamSynchronize(m->stream));
+    BM_CUDA_OK(bm_pipeline_sync_est(m->pipe));
     BM_CUDA_OK(cudaStreamSynchronize(m->s_chain));
     return BM_OK;
 }
@@ -491,7 +492,7 @@ static bm_status detect_ahead(bm_mosaic_s* m) {
     const int slot = m->cur ^ 1;
     BM_CUDA_OK(cudaStreamWaitEvent(m->stream, m->ev_up[slot], 0));
     BM_TRY(bm_pipeline_detect_ahead(m->pipe, m->d_gray[slot]));
-    BM_CUDA_OK(cudaEventRecord(m->ev_spec[slot], m->stream));
+    m->ev_spec[slot] = bm_pipeline_last_detect_event(m->pipe);
     return BM_OK;
 }
 
@@ -560,7 +561,8 @@ extern "C" bm_status bm_process_frame_begin_device(bm_handle m, const uint8_t* d
         BM_CUDA_OK(cudaStreamWaitEvent(m->stream, m->ev_up[m->cur], 0));
     } else {
         BM_CUDA_OK(cudaStreamWaitEvent(m->stream, m->ev_chain[m->cur], 0));      // the slot's previous chain still reads its BGRX copy
-        bm_pipeline_drop_ahead(m->pipe, m->d_gray[m->cur]);                       // (a detect-ahead on m->stream is ordered before this ingest)
+        if (m->ev_spec[m->cur]) BM_CUDA_OK(cudaStreamWaitEvent(m->stream, m->ev_spec[m->cur], 0));   // ... or an abandoned detect-ahead its gray plane
+        bm_pipeline_drop_ahead(m->pipe, m->d_gray[m->cur]);
         BM_CUDA_OK(bm_launch_ingest(d_bgr, m->cfg.frame_h, m->cfg.frame_w, m->d_gray[m->cur], m->d_bgrx[m->cur], m->stream));
         BM_CUDA_OK(cudaEventRecord(m->ev_up[m->cur], m->stream));
     }
@@ -641,6 +643,7 @@ bm_status bm_download_keypoints(const BmKeypoints& k, int desc_bytes, float* h_k
 extern "C" bm_status bm_get_keypoints(bm_handle m, int which, float* h_kp, uint8_t* h_desc, int cap, int* n_out) {
     if (!m) return BM_ERR_ARG;
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+    BM_CUDA_OK(bm_pipeline_sync_est(m->pipe));                // the features are written on the pipeline's detector streams
     return bm_download_keypoints(*bm_pipeline_keypoints(m->pipe, which), m->cfg.detector == BM_DET_ORB ? 32 : 128, h_kp, h_desc, cap, n_out, m->stream);
 }
 

@@ -16,8 +16,16 @@ struct BmHostReadback {      // pinned
 struct BmPipeline {
     bm_config cfg;
     cudaStream_t stream;
-    BmOrb* orb = nullptr;
-    BmSift* sift = nullptr;
+    // Two detector instances on two streams, used alternately: consecutive frames' detectAndCompute (the second one queued as a
+    // detect-ahead) run concurrently, so the latency-bound tail of one frame (selection, orientation, descriptors -- a few small or
+    // one-CTA kernels) is covered by the pyramid of the next.  `stream` only carries the orderings the caller sets up; every detect
+    // forks from it (ev_fork) and publishes ev_det[slot].
+    BmOrb* orb[2] = {nullptr, nullptr};
+    BmSift* sift[2] = {nullptr, nullptr};
+    cudaStream_t s_det[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr;
+    int det_toggle = 0, last_det_slot = 0;
+    bool is_orb = false;
     BmKeypoints kp[3];       // previous / current / detected ahead (the next frame's features may be computed before the host
     int prev = 0, cur = 1;   // knows whether the current frame becomes "previous")
     const uint8_t* ahead_gray = nullptr;     // gray buffer whose features were enqueued into kp[ahead_slot] by bm_pipeline_detect_ahead
@@ -51,9 +59,13 @@ bm_status bm_pipeline_create(BmPipeline** out, const bm_config& cfg, cudaStream_
               cudaStreamCreateWithFlags(&p->s_est, cudaStreamNonBlocking) == cudaSuccess && bm_matches_alloc(&p->m[0]) == 0 && bm_matches_alloc(&p->m[1]) == 0 &&
               cudaMalloc(&p->d_mask, BM_KP_CAP) == cudaSuccess && cudaMalloc(&p->d_res, sizeof(BmRansacResult)) == cudaSuccess &&
               cudaHostAlloc(&p->h_rb, sizeof(BmHostReadback), cudaHostAllocDefault) == cudaSuccess;
-    if (ok) {
-        if (cfg.detector == BM_DET_ORB) ok = bm_orb_create(&p->orb, cfg.frame_h, cfg.frame_w, cfg.nfeatures, stream) == 0;
-        else ok = bm_sift_create(&p->sift, cfg.frame_h, cfg.frame_w, cfg.nfeatures, stream) == 0;
+    p->is_orb = cfg.detector == BM_DET_ORB;
+    ok = ok && cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i) {
+        ok = cudaStreamCreateWithFlags(&p->s_det[i], cudaStreamNonBlocking) == cudaSuccess;
+        if (!ok) break;
+        if (p->is_orb) ok = bm_orb_create(&p->orb[i], cfg.frame_h, cfg.frame_w, cfg.nfeatures, p->s_det[i]) == 0;
+        else ok = bm_sift_create(&p->sift[i], cfg.frame_h, cfg.frame_w, cfg.nfeatures, p->s_det[i]) == 0;
     }
     if (!ok) { bm_set_error("bm_pipeline_create: allocation failed: %s", cudaGetErrorString(cudaGetLastError())); bm_pipeline_destroy(p); return BM_ERR_CUDA; }
     *out = p;
@@ -64,7 +76,12 @@ void bm_pipeline_destroy(BmPipeline* p) {
     if (!p) return;
     if (p->s_est) cudaStreamSynchronize(p->s_est);
     if (p->stream) cudaStreamSynchronize(p->stream);
-    bm_orb_destroy(p->orb); bm_sift_destroy(p->sift);
+    for (int i = 0; i < 2; ++i) {
+        if (p->s_det[i]) cudaStreamSynchronize(p->s_det[i]);
+        bm_orb_destroy(p->orb[i]); bm_sift_destroy(p->sift[i]);
+        if (p->s_det[i]) cudaStreamDestroy(p->s_det[i]);
+    }
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     bm_kp_free(&p->kp[0]); bm_kp_free(&p->kp[1]); bm_kp_free(&p->kp[2]);
     if (p->ev_done) cudaEventDestroy(p->ev_done);
     if (p->ev_est) cudaEventDestroy(p->ev_est);
@@ -77,9 +94,15 @@ void bm_pipeline_destroy(BmPipeline* p) {
 
 static cudaError_t detect(BmPipeline* p, const uint8_t* d_gray, BmKeypoints* out) {
     const int slot = (int)(out - p->kp);
-    cudaError_t e = p->orb ? bm_orb_detect(p->orb, d_gray, out) : bm_sift_detect(p->sift, d_gray, out);
+    const int i = p->det_toggle;
+    p->det_toggle ^= 1;
+    cudaError_t e = cudaEventRecord(p->ev_fork, p->stream);                  // everything the caller ordered on `stream` so far
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(p->s_det[i], p->ev_fork, 0);
     if (e != cudaSuccess) return e;
-    return cudaEventRecord(p->ev_det[slot], p->stream);
+    e = p->is_orb ? bm_orb_detect(p->orb[i], d_gray, out) : bm_sift_detect(p->sift[i], d_gray, out);
+    if (e != cudaSuccess) return e;
+    p->last_det_slot = slot;
+    return cudaEventRecord(p->ev_det[slot], p->s_det[i]);
 }
 
 bm_status bm_pipeline_first_frame(BmPipeline* p, const uint8_t* d_gray) {
@@ -107,7 +130,7 @@ bm_status bm_pipeline_estimate_begin(BmPipeline* p, const uint8_t* d_gray) {
     BM_CUDA_OK(cudaStreamWaitEvent(s, p->ev_det[p->prev], 0));
     p->mcur ^= 1;
     BmMatches& mm = p->m[p->mcur];
-    if (p->orb) BM_CUDA_OK(bm_match_hamming(cur, prev, mm, s));
+    if (p->is_orb) BM_CUDA_OK(bm_match_hamming(cur, prev, mm, s));
     else BM_CUDA_OK(bm_match_l2_ratio(cur, prev, mm, 0.7, s));                           // main.py:691
     BM_CUDA_OK(bm_launch_ransac(mm.src, mm.dst, mm.count, 2.0, 2000, 0.995, p->d_mask, p->d_res, s));   // main.py:857
     BmHostReadback* rb = p->h_rb;
@@ -152,7 +175,13 @@ bm_status bm_pipeline_estimate(BmPipeline* p, const uint8_t* d_gray, bm_frame_in
 }
 
 void bm_pipeline_advance(BmPipeline* p) { p->prev = p->cur; }
-cudaError_t bm_pipeline_sync_est(BmPipeline* p) { return cudaStreamSynchronize(p->s_est); }
+cudaError_t bm_pipeline_sync_est(BmPipeline* p) {       // everything the pipeline has queued on its own streams
+    cudaError_t e = cudaStreamSynchronize(p->s_det[0]);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(p->s_det[1]);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(p->s_est);
+    return e;
+}
+cudaEvent_t bm_pipeline_last_detect_event(BmPipeline* p) { return p->ev_det[p->last_det_slot]; }
 
 BmKeypoints* bm_pipeline_keypoints(BmPipeline* p, int which) { return &p->kp[which ? p->cur : p->prev]; }
 BmMatches* bm_pipeline_matches(BmPipeline* p) { return &p->m[p->mdone]; }      // matches of the last frame that was waited for
