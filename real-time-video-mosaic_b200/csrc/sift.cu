@@ -111,21 +111,34 @@ __device__ __forceinline__ void sift_cp_async4(float* smem_dst, const float* gme
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem_src) : "memory");
 }
 __host__ __device__ constexpr int sift_level_radius(int level) { return level <= 1 ? 5 : level == 2 ? 6 : level == 3 ? 8 : level == 4 ? 10 : 13; }
-__host__ __device__ constexpr int sift_tile_h(int level) { return ((64 - 2 * sift_level_radius(level)) / 4) * 4; }
+// a CTA stages SIFT_BLUR_SH rows: the row pass runs on all of them, the column pass keeps SH - 2R (rounded down to the number of
+// row groups) -- the taller the tile, the smaller the share of row-pass work spent on halo rows (R = 13: 1.33x at 128 rows, 1.72x at 64)
+// Measured on octave 0 (3840 x 2160): 128 rows win for the two widest kernels (level 5: 47.4 -> 41.6 us, level 4: 37.3 -> 35.5 us) and
+// lose 1-3 us on levels 0-3 (two 80 KB CTAs per SM hide less latency than five 40 KB ones), hence the split.
+__host__ __device__ constexpr int sift_blur_sh(int level) { return level >= 4 ? 128 : 64; }
+__host__ __device__ constexpr int sift_blur_nt(int level) { return 4 * sift_blur_sh(level); }      // one thread per (row, 16-output segment)
+__host__ __device__ constexpr int sift_blur_ng(int level) { return sift_blur_nt(level) / 64; }     // row groups of the column pass
+__host__ __device__ constexpr int sift_tile_h(int level) {
+    return ((sift_blur_sh(level) - 2 * sift_level_radius(level)) / sift_blur_ng(level)) * sift_blur_ng(level);
+}
+#define SIFT_BLUR_TSTRIDE (64 + 2 * 13 + 1)
+__host__ __device__ constexpr size_t sift_blur_smem(int level) { return (size_t)sift_blur_sh(level) * (SIFT_BLUR_TSTRIDE + 65) * sizeof(float); }
 
 template <int LEVEL>
-__global__ void __launch_bounds__(256) k_sift_blur(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ dog,
-                                                   float* __restrict__ dec, int w, int h) {
-    constexpr int R = sift_level_radius(LEVEL), K = 2 * R + 1, TW = 64, TH = sift_tile_h(LEVEL), SW = TW + 2 * R, SH = TH + 2 * R, NO = TH / 4;
-    __shared__ float tile[SH][SW + 1];
-    __shared__ float rowf[SH][TW + 1];
+__global__ void __launch_bounds__(sift_blur_nt(LEVEL), 2) k_sift_blur(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ dog,
+                                                               float* __restrict__ dec, int w, int h) {
+    constexpr int R = sift_level_radius(LEVEL), K = 2 * R + 1, TW = 64, TH = sift_tile_h(LEVEL), SW = TW + 2 * R, SH = TH + 2 * R,
+                  NO = TH / sift_blur_ng(LEVEL), NT = sift_blur_nt(LEVEL);
+    extern __shared__ __align__(16) unsigned char sift_blur_smem_raw[];
+    float (*tile)[SIFT_BLUR_TSTRIDE] = reinterpret_cast<float (*)[SIFT_BLUR_TSTRIDE]>(sift_blur_smem_raw);
+    float (*rowf)[64 + 1] = reinterpret_cast<float (*)[64 + 1]>(sift_blur_smem_raw + (size_t)sift_blur_sh(LEVEL) * SIFT_BLUR_TSTRIDE * sizeof(float));
     const int bx = blockIdx.x * TW, by = blockIdx.y * TH;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     {
         int gx[3];
 #pragma unroll
         for (int j = 0; j < 3; ++j) gx[j] = refl101(bx + lane + 32 * j - R, w);
-        for (int ty = warp; ty < SH; ty += 8) {
+        for (int ty = warp; ty < SH; ty += NT / 32) {
             const float* __restrict__ rowp = in + (size_t)refl101(by + ty - R, h) * w;
 #pragma unroll
             for (int j = 0; j < 3; ++j)
@@ -159,17 +172,25 @@ __global__ void __launch_bounds__(256) k_sift_blur(const float* __restrict__ in,
 #pragma unroll
         for (int t = 0; t < NO + 2 * R; ++t) hh[t] = rowf[r0 + t][c];
         if (gx < w) {
+            // 32-bit element offsets (a plane holds < 2^31 pixels) advanced by w per row: the three stores share one index
+            const int gy0 = by + r0, nrows = h - gy0;
+            unsigned idx = (unsigned)gy0 * (unsigned)w + (unsigned)gx;
+            const bool decx = LEVEL == 3 && dec != nullptr && !(gx & 1) && (gx >> 1) < (w >> 1);
 #pragma unroll
             for (int o = 0; o < NO; ++o) {
-                const int gy = by + r0 + o;
-                if (gy >= h) break;
-                float a = __fmul_rn(c_sift_k[LEVEL][R], hh[o + R]);
+                if (o < nrows) {
+                    float a = __fmul_rn(c_sift_k[LEVEL][R], hh[o + R]);
 #pragma unroll
-                for (int t = 1; t <= R; ++t) a = __fmaf_rn(c_sift_k[LEVEL][R + t], __fadd_rn(hh[o + R + t], hh[o + R - t]), a);
-                out[(size_t)gy * w + gx] = a;
-                if (dog) dog[(size_t)gy * w + gx] = __fsub_rn(a, tile[r0 + o + R][c + R]);
-                // next octave base = this level decimated by 2 (INTER_NEAREST: dst(x,y) = src(2x,2y))
-                if (dec && !((gx | gy) & 1) && (gx >> 1) < (w >> 1) && (gy >> 1) < (h >> 1)) dec[(size_t)(gy >> 1) * (w >> 1) + (gx >> 1)] = a;
+                    for (int t = 1; t <= R; ++t) a = __fmaf_rn(c_sift_k[LEVEL][R + t], __fadd_rn(hh[o + R + t], hh[o + R - t]), a);
+                    out[idx] = a;
+                    if (LEVEL >= 1) dog[idx] = __fsub_rn(a, tile[r0 + o + R][c + R]);
+                    if (LEVEL == 3) {
+                        // next octave base = this level decimated by 2 (INTER_NEAREST: dst(x,y) = src(2x,2y))
+                        const int gy = gy0 + o;
+                        if (decx && !(gy & 1) && (gy >> 1) < (h >> 1)) dec[(unsigned)(gy >> 1) * (unsigned)(w >> 1) + (unsigned)(gx >> 1)] = a;
+                    }
+                }
+                idx += (unsigned)w;
             }
         }
     }
@@ -923,7 +944,9 @@ void bm_sift_destroy(BmSift* o) {
 
 template <int LEVEL>
 static void launch_blur(const float* in, float* out, float* dog, float* dec, int w, int h, cudaStream_t s) {
-    BM_COUNT_LAUNCHES(1), k_sift_blur<LEVEL><<<dim3((w + 63) / 64, (h + sift_tile_h(LEVEL) - 1) / sift_tile_h(LEVEL)), 256, 0, s>>>(in, out, dog, dec, w, h);
+    static cudaError_t attr = cudaFuncSetAttribute(k_sift_blur<LEVEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sift_blur_smem(LEVEL));
+    (void)attr;
+    BM_COUNT_LAUNCHES(1), k_sift_blur<LEVEL><<<dim3((w + 63) / 64, (h + sift_tile_h(LEVEL) - 1) / sift_tile_h(LEVEL)), sift_blur_nt(LEVEL), sift_blur_smem(LEVEL), s>>>(in, out, dog, dec, w, h);
 }
 
 static void blur_level(int level, const float* in, float* out, float* dog, float* dec, int w, int h, cudaStream_t s) {
