@@ -96,17 +96,18 @@ def test_canvas_row_tiles_match_untiled(sweep_frames):
     assert got[:y1].max() == 0                            # the upper tile was never touched
 
 
-def test_prefetch_and_overlap_do_not_change_results(sweep_frames):
+@pytest.mark.parametrize("det", ["orb", "sift"])
+def test_prefetch_and_overlap_do_not_change_results(sweep_frames, det):
     """double-buffered ingest (next_frame=) and the detect / chain stream overlap are scheduling only: the canvas and the
     trajectory must be bit-identical to the plain sequential calls, also when a prefetched frame is not the one processed next"""
     import b200mosaic
     frames, _ = sweep_frames
-    ref = b200mosaic.VideMosaic(frames[0], detector_type="orb", show_intermediate=False, visualize=False)
+    ref = b200mosaic.VideMosaic(frames[0], detector_type=det, show_intermediate=False, visualize=False)
     ref.set_overlap(False)
     for t in range(1, 7):
         ref.process_frame(frames[t], t)
     want_canvas, want_H = ref.output_img.copy(), ref.H.copy()
-    vm = b200mosaic.VideMosaic(frames[0], detector_type="orb", show_intermediate=False, visualize=False)
+    vm = b200mosaic.VideMosaic(frames[0], detector_type=det, show_intermediate=False, visualize=False)
     for t in range(1, 7):
         nxt = frames[t + 1] if t + 1 < 7 else None
         if t == 3:
@@ -116,20 +117,21 @@ def test_prefetch_and_overlap_do_not_change_results(sweep_frames):
     assert np.array_equal(vm.H, want_H)
     pin = torch.from_numpy(np.stack(frames)).pin_memory()
     fb = frames[0].nbytes
-    vp = b200mosaic.VideMosaic(frames[0], detector_type="orb", show_intermediate=False, visualize=False)
+    vp = b200mosaic.VideMosaic(frames[0], detector_type=det, show_intermediate=False, visualize=False)
     for t in range(1, 7):
         assert vp.process_frame_ptr(pin.data_ptr() + t * fb, pin.data_ptr() + (t + 1) * fb if t + 1 < 7 else None) == 0
     assert np.array_equal(vp.output_img, want_canvas)
 
 
-def test_pipelined_calls_survive_skipped_frames(sweep_frames):
+@pytest.mark.parametrize("det", ["orb", "sift"])
+def test_pipelined_calls_survive_skipped_frames(sweep_frames, det):
     """a featureless frame in the middle is skipped (main.py:722-724: state not advanced); with next_frame= pipelining (staged
     upload + early begin) the statuses, the trajectory and the canvas must equal the plain sequential run"""
     import b200mosaic
     frames, _ = sweep_frames
     seq = list(frames[:3]) + [np.full_like(frames[0], 7)] + list(frames[3:])
     def run(pipelined):
-        vm = b200mosaic.VideMosaic(seq[0], detector_type="orb", show_intermediate=False, visualize=False)
+        vm = b200mosaic.VideMosaic(seq[0], detector_type=det, show_intermediate=False, visualize=False)
         st = []
         for t in range(1, len(seq)):
             nxt = seq[t + 1] if (pipelined and t + 1 < len(seq)) else None
@@ -140,3 +142,25 @@ def test_pipelined_calls_survive_skipped_frames(sweep_frames):
     assert a[0] == b[0] and a[0][2] != 0 and a[0].count(0) == len(seq) - 2      # exactly the blank frame is skipped
     assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
     assert a[3] == b[3]                                                         # matches of the last finished frame
+
+
+def test_long_pipelined_run_equals_serial(sweep_frames):
+    """30 frames with detect-ahead, the estimate stream and both detector instances in flight (next_frame= on every call) against
+    strictly serial calls with overlap off: same statuses, same trajectory, same canvas, same final features"""
+    import b200mosaic
+    from b200mosaic.synth import DroneSweep
+    frames = DroneSweep(640, 360, seed=21, ground_size=2048, max_step=7.0).frames(31)
+    def run(pipelined):
+        vm = b200mosaic.VideMosaic(frames[0], detector_type="sift", show_intermediate=False, visualize=False)
+        vm.set_overlap(pipelined)
+        st, Hs = [], []
+        for t in range(1, len(frames)):
+            vm.process_frame(frames[t], t, next_frame=frames[t + 1] if (pipelined and t + 1 < len(frames)) else None)
+            st.append(vm.last_info.status); Hs.append(vm.H.copy())
+        kp = np.array([[k.pt[0], k.pt[1], k.size, k.angle, k.response] for k in vm.kp_prev])
+        return st, np.array(Hs), vm.output_img.copy(), kp, np.asarray(vm.des_prev).copy()
+    a, b = run(False), run(True)
+    assert a[0] == b[0] and a[0].count(0) >= 28
+    assert np.array_equal(a[1], b[1])
+    assert np.array_equal(a[2], b[2])
+    assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
