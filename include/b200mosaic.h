@@ -109,6 +109,9 @@ bm_status bm_finalize(bm_handle h, int threshold, int margin, int target_w, int 
  * cv2.cvtColor(BGR2RGB), Image.fromarray, Image.resize((out_w, out_h)) with Pillow's default bicubic filter (gui.py:143-158 on the
  * copy handed over at main.py:1630-1632).  h_out receives out_h x out_w x 3 bytes, RGB when rgb != 0 (the GUI's order) else BGR. */
 bm_status bm_preview(bm_handle h, int out_w, int out_h, int rgb, uint8_t* h_out, size_t cap_bytes);
+/* optional: capture every CUDA graph the per-frame path replays now instead of lazily during the first frames of a stream (the
+ * reference has no equivalent; its first process_frame is as slow as any other, main.py:711).  Executes nothing. */
+bm_status bm_warm_up(bm_handle h);
 bm_status bm_get_state(bm_handle h, double H_old[9], int* history_len, double* history /* <=5*9 */);
 bm_status bm_set_stabilization(bm_handle h, int enabled, int history_size, double translation_threshold,
                                double scale_threshold);                          /* main.py:97-101 */

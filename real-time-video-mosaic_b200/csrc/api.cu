@@ -56,29 +56,37 @@ static bm_status alloc_blend(BmBlendBufs& b, int canvas_h, int canvas_w, size_t 
 //   stream   : detect / match / RANSAC of frame t (the host waits on it once per frame for the homography)
 //   s_chain  : warp / blend chain of frame t -- runs concurrently with detect of frame t+1 (it only touches the canvas)
 //   s_copy   : H2D + ingest of the next frame (bm_prefetch_frame) while the current one is being processed
-// Frame slots are double buffered; events order  upload(slot) -> detect / chain(slot) -> next upload(slot).
+// Frame slots rotate over three buffers; events order  upload(slot) -> detect / chain(slot) -> next upload(slot).  Three, not two:
+// the upload of frame t+1 must not wait for the chain of frame t-1, which is still reading that frame's BGRX copy when the caller
+// stages t+1 (with two slots the H2D copy of every frame started a whole chain late and sat on the critical path of the e2e rate).
+#define BM_SLOTS 3
+#define BM_CANVAS_STAGE_BYTES ((size_t)4 << 20)
+#define BM_SLOT_NEXT(c) (((c) + 1) % BM_SLOTS)
+#define BM_SLOT_PREV(c) (((c) + BM_SLOTS - 1) % BM_SLOTS)
 struct bm_mosaic_s {
     bm_config cfg;
     cudaStream_t stream = nullptr, s_chain = nullptr, s_copy = nullptr;
-    cudaEvent_t ev_up[2] = {nullptr, nullptr};          // upload + ingest of the slot finished
-    cudaEvent_t ev_chain[2] = {nullptr, nullptr};       // last chain that read the slot's BGRX finished
-    cudaEvent_t ev_spec[2] = {nullptr, nullptr};        // last detect-ahead that read the slot's gray plane finished (owned by the pipeline)
+    cudaEvent_t ev_up[BM_SLOTS] = {};          // upload + ingest of the slot finished
+    cudaEvent_t ev_chain[BM_SLOTS] = {};       // last chain that read the slot's BGRX finished
+    cudaEvent_t ev_spec[BM_SLOTS] = {};        // last detect-ahead that read the slot's gray plane finished (owned by the pipeline)
     int overlap = 1;                                    // 0: detect waits for the previous chain (clean chain timing)
     const uint8_t* prefetched = nullptr;                // host pointer staged by bm_prefetch_frame ...
     int prefetched_slot = -1;                           // ... into this slot
     const uint8_t* begun = nullptr;                     // frame whose detect / match / RANSAC was already enqueued by the previous _end
     BmBlendBufs blend;
     // frame staging: double-buffered pinned host + device buffers
-    uint8_t* h_stage[2] = {nullptr, nullptr};
-    uint8_t* d_bgr[2] = {nullptr, nullptr};
-    uchar4* d_bgrx[2] = {nullptr, nullptr};
-    uint8_t* d_gray[2] = {nullptr, nullptr};
-    cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
+    uint8_t* h_stage[BM_SLOTS] = {};
+    uint8_t* d_bgr[BM_SLOTS] = {};
+    uchar4* d_bgrx[BM_SLOTS] = {};
+    uint8_t* d_gray[BM_SLOTS] = {};
+    cudaEvent_t ev_h2d[BM_SLOTS] = {};
     int cur = 0;
     // canvas export
     uint8_t* d_canvas_bgr = nullptr;
     uint8_t* d_final = nullptr; size_t final_cap = 0;      // finalisation result (screen sized), allocated on first use
     int* d_bounds = nullptr;
+    uint8_t* h_cstage[2] = {nullptr, nullptr};              // pinned staging of bm_get_canvas for pageable destinations
+    cudaEvent_t ev_cstage[2] = {nullptr, nullptr};
     BmPreviewPlan preview;                                  // thumbnail tables / buffers, built on first use
     // stitcher state (main.py:92-102)
     double H_old[9];
@@ -115,9 +123,13 @@ extern "C" bm_status bm_create(const bm_config* cfg, bm_handle* out) {
     BM_CUDA_OK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
     BM_CUDA_OK(cudaStreamCreateWithFlags(&m->s_chain, cudaStreamNonBlocking));
     BM_CUDA_OK(cudaStreamCreateWithFlags(&m->s_copy, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < BM_SLOTS; ++i) {
         BM_CUDA_OK(cudaEventCreateWithFlags(&m->ev_up[i], cudaEventDisableTiming));
         BM_CUDA_OK(cudaEventCreateWithFlags(&m->ev_chain[i], cudaEventDisableTiming));
+    }
+    for (int k = 0; k < 2; ++k) {            // page-locking is slow (tens of ms): at creation, not in the first bm_get_canvas
+        BM_CUDA_OK(cudaHostAlloc(&m->h_cstage[k], BM_CANVAS_STAGE_BYTES, cudaHostAllocDefault));
+        BM_CUDA_OK(cudaEventCreateWithFlags(&m->ev_cstage[k], cudaEventDisableTiming));
     }
     // scratch: the window of a frame is at most the canvas; typical is frame-sized.  Size for the whole canvas when
     // it is small (<= 64 Mpx), otherwise for 4x the frame area plus margins (config 5: 32768^2 canvas, 4K frames).
@@ -127,7 +139,7 @@ extern "C" bm_status bm_create(const bm_config* cfg, bm_handle* out) {
     bm_status st = alloc_blend(m->blend, cfg->canvas_h, cfg->canvas_w, scratch);
     if (st != BM_OK) { delete m; return st; }
     const size_t fb = frame_bytes(*cfg), fpx = (size_t)cfg->frame_h * cfg->frame_w;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < BM_SLOTS; ++i) {
         BM_CUDA_OK(cudaHostAlloc(&m->h_stage[i], fb, cudaHostAllocDefault));
         BM_CUDA_OK(cudaMalloc(&m->d_bgr[i], fb + 16));
         BM_CUDA_OK(cudaMalloc(&m->d_bgrx[i], fpx * sizeof(uchar4)));
@@ -150,14 +162,15 @@ extern "C" bm_status bm_destroy(bm_handle m) {
     if (m->pipe) bm_pipeline_sync_est(m->pipe);
     bm_pipeline_destroy(m->pipe);
     free_blend(m->blend);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < BM_SLOTS; ++i) {
         cudaFreeHost(m->h_stage[i]); cudaFree(m->d_bgr[i]); cudaFree(m->d_bgrx[i]); cudaFree(m->d_gray[i]);
         if (m->ev_h2d[i]) cudaEventDestroy(m->ev_h2d[i]);
     }
     cudaFree(m->d_canvas_bgr); cudaFree(m->d_final); cudaFree(m->d_bounds);
     bm_preview_free(&m->preview);
+    for (int k = 0; k < 2; ++k) { if (m->h_cstage[k]) cudaFreeHost(m->h_cstage[k]); if (m->ev_cstage[k]) cudaEventDestroy(m->ev_cstage[k]); }
     for (int i = 0; i < bm_mosaic_s::kEvRing; ++i) { cudaEventDestroy(m->ev0[i]); cudaEventDestroy(m->ev1[i]); }
-    for (int i = 0; i < 2; ++i) { if (m->ev_up[i]) cudaEventDestroy(m->ev_up[i]); if (m->ev_chain[i]) cudaEventDestroy(m->ev_chain[i]); }
+    for (int i = 0; i < BM_SLOTS; ++i) { if (m->ev_up[i]) cudaEventDestroy(m->ev_up[i]); if (m->ev_chain[i]) cudaEventDestroy(m->ev_chain[i]); }
     cudaStreamDestroy(m->stream); cudaStreamDestroy(m->s_chain); cudaStreamDestroy(m->s_copy);
     delete m;
     return BM_OK;
@@ -203,8 +216,8 @@ static bm_status stage_frame(bm_mosaic_s* m, const uint8_t* h_bgr, size_t stride
 extern "C" bm_status bm_prefetch_frame(bm_handle m, const uint8_t* h_bgr, size_t stride) {
     if (!m || !h_bgr) { bm_set_error("bm_prefetch_frame: null"); return BM_ERR_ARG; }
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
-    BM_TRY(upload(m, h_bgr, stride, m->cur ^ 1));
-    m->prefetched = h_bgr; m->prefetched_slot = m->cur ^ 1;
+    BM_TRY(upload(m, h_bgr, stride, BM_SLOT_NEXT(m->cur)));
+    m->prefetched = h_bgr; m->prefetched_slot = BM_SLOT_NEXT(m->cur);
     return BM_OK;
 }
 
@@ -212,7 +225,7 @@ extern "C" bm_status bm_prefetch_frame(bm_handle m, const uint8_t* h_bgr, size_t
 extern "C" bm_status bm_prefetch_frame_device(bm_handle m, const uint8_t* d_bgr) {
     if (!m || !d_bgr) { bm_set_error("bm_prefetch_frame_device: null"); return BM_ERR_ARG; }
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
-    const int slot = m->cur ^ 1;
+    const int slot = BM_SLOT_NEXT(m->cur);
     BM_CUDA_OK(cudaStreamWaitEvent(m->s_copy, m->ev_chain[slot], 0));
     if (m->ev_spec[slot]) BM_CUDA_OK(cudaStreamWaitEvent(m->s_copy, m->ev_spec[slot], 0));
     bm_pipeline_drop_ahead(m->pipe, m->d_gray[slot]);
@@ -305,7 +318,7 @@ extern "C" bm_status bm_warp_frame(bm_handle m, const uint8_t* h_bgr, size_t str
     if (!m || !h_bgr || !H) { bm_set_error("bm_warp_frame: null"); return BM_ERR_ARG; }
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
     cancel_early_begin(m);
-    m->cur ^= 1;
+    m->cur = BM_SLOT_NEXT(m->cur);
     BM_TRY(stage_frame(m, h_bgr, stride, m->cur, m->s_chain));
     if (info) { memset(info, 0, sizeof(*info)); memcpy(info->H, H, 9 * sizeof(double)); }
     return warp_device(m, m->d_bgrx[m->cur], H, info, true, m->cur);
@@ -315,7 +328,7 @@ extern "C" bm_status bm_warp_frame_async(bm_handle m, const uint8_t* h_bgr, size
     if (!m || !h_bgr || !H) { bm_set_error("bm_warp_frame_async: null"); return BM_ERR_ARG; }
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
     cancel_early_begin(m);
-    m->cur ^= 1;
+    m->cur = BM_SLOT_NEXT(m->cur);
     BM_TRY(stage_frame(m, h_bgr, stride, m->cur, m->s_chain));
     return warp_device(m, m->d_bgrx[m->cur], H, nullptr, false, m->cur);
 }
@@ -330,10 +343,20 @@ extern "C" bm_status bm_upload_frame(bm_handle m, const uint8_t* h_bgr, size_t s
     if (!m || !h_bgr) return BM_ERR_ARG;
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
     cancel_early_begin(m);
-    m->cur ^= 1;
+    m->cur = BM_SLOT_NEXT(m->cur);
     BM_TRY(stage_frame(m, h_bgr, stride, m->cur, m->s_chain));
     if (d_out) *d_out = reinterpret_cast<const uint8_t*>(m->d_bgrx[m->cur]);
     return BM_OK;
+}
+
+// Optional: build every CUDA graph the per-frame path will replay (detector instance x frame slot x keypoint slot) up front, so a
+// real-time caller sees no capture / instantiation hiccup in its first frames.  Executes nothing; results are unaffected.
+extern "C" bm_status bm_warm_up(bm_handle m) {
+    if (!m) return BM_ERR_ARG;
+    BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+    const uint8_t* grays[BM_SLOTS];
+    for (int i = 0; i < BM_SLOTS; ++i) grays[i] = m->d_gray[i];
+    return bm_pipeline_warm_up(m->pipe, grays, BM_SLOTS);
 }
 
 extern "C" bm_status bm_sync(bm_handle m) {
@@ -351,8 +374,36 @@ extern "C" bm_status bm_get_canvas(bm_handle m, uint8_t* h_out) {
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
     const size_t n = (size_t)m->cfg.canvas_h * m->cfg.canvas_w;
     BM_CUDA_OK(bm_launch_unpack_canvas(m->blend.canvas, m->d_canvas_bgr, (int)n, m->s_chain));
-    BM_CUDA_OK(cudaMemcpyAsync(h_out, m->d_canvas_bgr, n * 3, cudaMemcpyDeviceToHost, m->s_chain));
-    BM_CUDA_OK(cudaStreamSynchronize(m->s_chain));
+    const size_t bytes = n * 3;
+    cudaPointerAttributes attr;
+    bool pinned = false;
+    if (cudaPointerGetAttributes(&attr, h_out) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
+    else cudaGetLastError();
+    if (pinned) {
+        BM_CUDA_OK(cudaMemcpyAsync(h_out, m->d_canvas_bgr, bytes, cudaMemcpyDeviceToHost, m->s_chain));
+        BM_CUDA_OK(cudaStreamSynchronize(m->s_chain));
+        return BM_OK;
+    }
+    // pageable destination (a NumPy array): the driver's own staging runs at a few GB/s; DMA into two pinned 4 MB buffers
+    // instead and copy chunk i to the caller while chunk i + 1 is in flight
+    const size_t CH = BM_CANVAS_STAGE_BYTES;
+    size_t prev_off = 0, prev_n = 0;
+    int idx = 0;
+    for (size_t off = 0; off < bytes; off += CH, ++idx) {
+        const int k = idx & 1;
+        const size_t cn = bytes - off < CH ? bytes - off : CH;
+        BM_CUDA_OK(cudaMemcpyAsync(m->h_cstage[k], m->d_canvas_bgr + off, cn, cudaMemcpyDeviceToHost, m->s_chain));
+        BM_CUDA_OK(cudaEventRecord(m->ev_cstage[k], m->s_chain));
+        if (prev_n) {                                    // the other buffer: its DMA was issued one iteration ago
+            BM_CUDA_OK(cudaEventSynchronize(m->ev_cstage[k ^ 1]));
+            memcpy(h_out + prev_off, m->h_cstage[k ^ 1], prev_n);
+        }
+        prev_off = off; prev_n = cn;
+    }
+    if (prev_n) {
+        BM_CUDA_OK(cudaEventSynchronize(m->ev_cstage[(idx - 1) & 1]));
+        memcpy(h_out + prev_off, m->h_cstage[(idx - 1) & 1], prev_n);
+    }
     return BM_OK;
 }
 
@@ -474,11 +525,11 @@ static void matmul3(const double* A, const double* B, double* C) {
 // If bm_prefetch_frame staged the next frame into the free slot, start its detect / match / RANSAC now (the following
 // bm_process_frame_begin with the same pointer is then a no-op).  Only with stream overlap on.
 static bm_status early_begin(bm_mosaic_s* m) {
-    if (!m->overlap || !m->prefetched || m->prefetched_slot != (m->cur ^ 1)) return BM_OK;
-    m->cur ^= 1;
+    if (!m->overlap || !m->prefetched || m->prefetched_slot != (BM_SLOT_NEXT(m->cur))) return BM_OK;
+    m->cur = BM_SLOT_NEXT(m->cur);
     BM_CUDA_OK(cudaStreamWaitEvent(m->stream, m->ev_up[m->cur], 0));
     bm_status st = bm_pipeline_estimate_begin(m->pipe, m->d_gray[m->cur]);
-    if (st < 0) { m->cur ^= 1; return st; }
+    if (st < 0) { m->cur = BM_SLOT_PREV(m->cur); return st; }
     m->begun = m->prefetched;
     m->prefetched = nullptr;
     return BM_OK;
@@ -488,8 +539,8 @@ static bm_status early_begin(bm_mosaic_s* m) {
 // them NOW, before the host blocks on the RANSAC result -- the detect stream then runs straight on while the host takes the
 // skip / validate / smooth decision and issues the chain.  Without it the device idles for the wake-up + launch latency every frame.
 static bm_status detect_ahead(bm_mosaic_s* m) {
-    if (!m->overlap || !m->prefetched || m->prefetched_slot != (m->cur ^ 1)) return BM_OK;
-    const int slot = m->cur ^ 1;
+    if (!m->overlap || !m->prefetched || m->prefetched_slot != (BM_SLOT_NEXT(m->cur))) return BM_OK;
+    const int slot = BM_SLOT_NEXT(m->cur);
     BM_CUDA_OK(cudaStreamWaitEvent(m->stream, m->ev_up[slot], 0));
     BM_TRY(bm_pipeline_detect_ahead(m->pipe, m->d_gray[slot]));
     m->ev_spec[slot] = bm_pipeline_last_detect_event(m->pipe);
@@ -498,7 +549,7 @@ static bm_status detect_ahead(bm_mosaic_s* m) {
 
 // an early-begun frame that is not the one the caller continues with: its enqueued work is simply ignored
 static void cancel_early_begin(bm_mosaic_s* m) {
-    if (m->begun) { m->begun = nullptr; m->cur ^= 1; }
+    if (m->begun) { m->begun = nullptr; m->cur = BM_SLOT_PREV(m->cur); }
 }
 
 static bm_status finish_frame(bm_mosaic_s* m, int slot, bm_frame_info* info_out) {
@@ -507,9 +558,9 @@ static bm_status finish_frame(bm_mosaic_s* m, int slot, bm_frame_info* info_out)
     double H_rel[9]; int have_h = 0;
     BM_TRY(detect_ahead(m));
     bm_status st = bm_pipeline_estimate_end(m->pipe, &info, H_rel, &have_h);
-    if (st < 0) { m->cur ^= 1; return st; }
-    if (info.n_matches < 4) { info.status = BM_SKIP_FEW_MATCHES; m->cur ^= 1; BM_TRY(early_begin(m)); if (info_out) *info_out = info; return BM_SKIP_FEW_MATCHES; }
-    if (!have_h) { info.status = BM_SKIP_NO_H; m->cur ^= 1; BM_TRY(early_begin(m)); if (info_out) *info_out = info; return BM_SKIP_NO_H; }
+    if (st < 0) { m->cur = BM_SLOT_PREV(m->cur); return st; }
+    if (info.n_matches < 4) { info.status = BM_SKIP_FEW_MATCHES; BM_TRY(early_begin(m)); if (info_out) *info_out = info; return BM_SKIP_FEW_MATCHES; }
+    if (!have_h) { info.status = BM_SKIP_NO_H; BM_TRY(early_begin(m)); if (info_out) *info_out = info; return BM_SKIP_NO_H; }
     memcpy(info.H_rel, H_rel, 72);
     double Hv[9]; memcpy(Hv, H_rel, 72);
     info.validate_reason = validate_h(m, H_rel, &info.validate_value);
@@ -533,8 +584,7 @@ static bm_status finish_frame(bm_mosaic_s* m, int slot, bm_frame_info* info_out)
 // overlap == 0: detect of this frame starts only after the previous frame's chain (used for clean chain timing)
 static bm_status order_after_chain(bm_mosaic_s* m) {
     if (m->overlap) return BM_OK;
-    BM_CUDA_OK(cudaStreamWaitEvent(m->stream, m->ev_chain[0], 0));
-    BM_CUDA_OK(cudaStreamWaitEvent(m->stream, m->ev_chain[1], 0));
+    for (int i = 0; i < BM_SLOTS; ++i) BM_CUDA_OK(cudaStreamWaitEvent(m->stream, m->ev_chain[i], 0));
     return BM_OK;
 }
 
@@ -543,11 +593,11 @@ extern "C" bm_status bm_process_frame_begin(bm_handle m, const uint8_t* h_bgr, s
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
     if (m->begun == h_bgr) { m->begun = nullptr; return BM_OK; }      // already enqueued by the previous frame's _end
     cancel_early_begin(m);
-    m->cur ^= 1;
+    m->cur = BM_SLOT_NEXT(m->cur);
     BM_TRY(stage_frame(m, h_bgr, stride, m->cur, m->stream));
     BM_TRY(order_after_chain(m));
     bm_status st = bm_pipeline_estimate_begin(m->pipe, m->d_gray[m->cur]);
-    if (st < 0) m->cur ^= 1;
+    if (st < 0) m->cur = BM_SLOT_PREV(m->cur);
     return st;
 }
 
@@ -556,7 +606,7 @@ extern "C" bm_status bm_process_frame_begin_device(bm_handle m, const uint8_t* d
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
     if (m->begun == d_bgr) { m->begun = nullptr; return BM_OK; }      // already enqueued by the previous frame's _end
     cancel_early_begin(m);
-    m->cur ^= 1;
+    m->cur = BM_SLOT_NEXT(m->cur);
     if (m->prefetched == d_bgr && m->prefetched_slot == m->cur) {
         BM_CUDA_OK(cudaStreamWaitEvent(m->stream, m->ev_up[m->cur], 0));
     } else {
@@ -569,7 +619,7 @@ extern "C" bm_status bm_process_frame_begin_device(bm_handle m, const uint8_t* d
     m->prefetched = nullptr;
     BM_TRY(order_after_chain(m));
     bm_status st = bm_pipeline_estimate_begin(m->pipe, m->d_gray[m->cur]);
-    if (st < 0) m->cur ^= 1;
+    if (st < 0) m->cur = BM_SLOT_PREV(m->cur);
     return st;
 }
 
@@ -595,19 +645,19 @@ extern "C" bm_status bm_estimate_frame(bm_handle m, const uint8_t* h_bgr, size_t
     if (!m || !h_bgr) { bm_set_error("bm_estimate_frame: null"); return BM_ERR_ARG; }
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
     cancel_early_begin(m);
-    m->cur ^= 1;
+    m->cur = BM_SLOT_NEXT(m->cur);
     BM_TRY(stage_frame(m, h_bgr, stride, m->cur, m->stream));
     bm_frame_info info; memset(&info, 0, sizeof(info));
     double H_rel[9]; int have_h = 0;
     bm_status st = bm_pipeline_estimate_begin(m->pipe, m->d_gray[m->cur]);
-    if (st < 0) { m->cur ^= 1; return st; }
+    if (st < 0) { m->cur = BM_SLOT_PREV(m->cur); return st; }
     if (h_next) {                                  // the next frame's H2D + ingest overlap this pair's estimation
-        BM_TRY(upload(m, h_next, stride, m->cur ^ 1));
-        m->prefetched = h_next; m->prefetched_slot = m->cur ^ 1;
+        BM_TRY(upload(m, h_next, stride, BM_SLOT_NEXT(m->cur)));
+        m->prefetched = h_next; m->prefetched_slot = BM_SLOT_NEXT(m->cur);
         BM_TRY(detect_ahead(m));                   // and its features are computed while the host waits for this pair
     }
     st = bm_pipeline_estimate_end(m->pipe, &info, H_rel, &have_h);
-    if (st < 0) { m->cur ^= 1; return st; }
+    if (st < 0) { m->cur = BM_SLOT_PREV(m->cur); return st; }
     bm_pipeline_advance(m->pipe);                  // pair (t-1, t): the frame always becomes "previous"
     bm_status ret = BM_OK;
     if (info.n_matches < 4) ret = BM_SKIP_FEW_MATCHES;

@@ -614,14 +614,15 @@ static cudaError_t orb_enqueue(BmOrb* o, const uint8_t* d_gray, BmKeypoints* out
 
 // detectAndCompute is a fixed launch sequence per (input buffer, output buffer): captured once into a CUDA graph and replayed
 // (one launch call per frame instead of ~22; the kernels of the sequence run back to back without host launch gaps)
-cudaError_t bm_orb_detect(BmOrb* o, const uint8_t* d_gray, BmKeypoints* out) {
+cudaError_t bm_orb_detect(BmOrb* o, const uint8_t* d_gray, BmKeypoints* out, bool launch) {
     if (o->stream == nullptr || o->graphs_disabled) return orb_enqueue(o, d_gray, out);          // legacy stream cannot be captured
     for (int i = 0; i < o->ngraphs; ++i)
         if (o->graphs[i].gray == d_gray && o->graphs[i].out_pt == (const void*)out->pt) {
+            if (!launch) return cudaSuccess;
             BM_COUNT_LAUNCHES(o->graphs[i].launches);
             return cudaGraphLaunch(o->graphs[i].exec, o->stream);
         }
-    if (o->ngraphs >= 8) return orb_enqueue(o, d_gray, out);
+    if (o->ngraphs >= 12) return orb_enqueue(o, d_gray, out);
     const long long before = g_bm_launches;
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamBeginCapture(o->stream, cudaStreamCaptureModeRelaxed);
@@ -637,6 +638,7 @@ cudaError_t bm_orb_detect(BmOrb* o, const uint8_t* d_gray, BmKeypoints* out) {
     if (e != cudaSuccess) { cudaGetLastError(); o->graphs_disabled = 1; return orb_enqueue(o, d_gray, out); }
     BmOrbGraph& g = o->graphs[o->ngraphs++];
     g.gray = d_gray; g.out_pt = out->pt; g.exec = exec; g.launches = launches;
+    if (!launch) return cudaSuccess;                          // capture only (bm_warm_up)
     BM_COUNT_LAUNCHES(launches);
     return cudaGraphLaunch(exec, o->stream);
 }

@@ -40,7 +40,7 @@ struct BmOrb {
     int* hist;          // [8][256]
     uint8_t* keep;      // keep flags for cand2
     cudaStream_t stream;
-    BmOrbGraph graphs[8];   // captured detect sequences, one per (input buffer, output buffer)
+    BmOrbGraph graphs[12];   // captured detect sequences, one per (input buffer, output buffer)
     int ngraphs, graphs_disabled;
 };
 
@@ -49,4 +49,5 @@ void bm_orb_destroy(BmOrb* o);
 int bm_kp_alloc(BmKeypoints* k, int desc_bytes);
 void bm_kp_free(BmKeypoints* k);
 // gray (device, tightly packed h*w) -> keypoints + descriptors into `out`
-cudaError_t bm_orb_detect(BmOrb* o, const uint8_t* d_gray, BmKeypoints* out);
+// launch == false: only capture + instantiate the graph of this (input, output) pair if it is not cached yet
+cudaError_t bm_orb_detect(BmOrb* o, const uint8_t* d_gray, BmKeypoints* out, bool launch = true);

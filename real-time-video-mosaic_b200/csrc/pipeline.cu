@@ -183,5 +183,15 @@ cudaError_t bm_pipeline_sync_est(BmPipeline* p) {       // everything the pipeli
 }
 cudaEvent_t bm_pipeline_last_detect_event(BmPipeline* p) { return p->ev_det[p->last_det_slot]; }
 
+// Capture the detector graph of every (detector instance, gray buffer, keypoint slot) combination now, so that no capture /
+// instantiation (milliseconds for the ~90-node SIFT graph) lands in the first frames of a stream.  Nothing is executed.
+bm_status bm_pipeline_warm_up(BmPipeline* p, const uint8_t* const* d_gray, int n_gray) {
+    for (int i = 0; i < 2; ++i)
+        for (int g = 0; g < n_gray; ++g)
+            for (int k = 0; k < 3; ++k)
+                BM_CUDA_OK(p->is_orb ? bm_orb_detect(p->orb[i], d_gray[g], &p->kp[k], false) : bm_sift_detect(p->sift[i], d_gray[g], &p->kp[k], false));
+    return BM_OK;
+}
+
 BmKeypoints* bm_pipeline_keypoints(BmPipeline* p, int which) { return &p->kp[which ? p->cur : p->prev]; }
 BmMatches* bm_pipeline_matches(BmPipeline* p) { return &p->m[p->mdone]; }      // matches of the last frame that was waited for

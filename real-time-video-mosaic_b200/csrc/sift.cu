@@ -57,7 +57,7 @@ struct BmSift {
     // fork / join streams + events of the captured detect graph, and the graph cache
     cudaStream_t s2, s3;
     cudaEvent_t ev_fork, ev_l3[SIFT_MAX_OCT], ev_l5[SIFT_MAX_OCT], ev_join2, ev_join3;
-    static const int kMaxGraphs = 8;
+    static const int kMaxGraphs = 12;
     SiftGraph graphs[kMaxGraphs];
     int ngraphs;
     bool graphs_enabled;
@@ -1020,10 +1020,11 @@ static cudaError_t sift_enqueue(BmSift* o, const uint8_t* d_gray, BmKeypoints* o
 
 // detectAndCompute is a fixed launch sequence per (input buffer, output buffer): it is captured once into a CUDA graph with the
 // fork / join structure above and replayed -- one launch call per frame instead of ~90, and the independent branches overlap.
-cudaError_t bm_sift_detect(BmSift* o, const uint8_t* d_gray, BmKeypoints* out) {
+cudaError_t bm_sift_detect(BmSift* o, const uint8_t* d_gray, BmKeypoints* out, bool launch) {
     if (o->stream == nullptr || !o->graphs_enabled) return sift_enqueue(o, d_gray, out, false);   // legacy stream cannot be captured
     for (int i = 0; i < o->ngraphs; ++i)
         if (o->graphs[i].gray == d_gray && o->graphs[i].out_pt == (const void*)out->pt) {
+            if (!launch) return cudaSuccess;
             BM_COUNT_LAUNCHES(o->graphs[i].launches);
             return cudaGraphLaunch(o->graphs[i].exec, o->stream);
         }
@@ -1047,6 +1048,7 @@ cudaError_t bm_sift_detect(BmSift* o, const uint8_t* d_gray, BmKeypoints* out) {
     }
     SiftGraph& g = o->graphs[o->ngraphs++];
     g.gray = d_gray; g.out_pt = out->pt; g.exec = exec; g.launches = launches;
+    if (!launch) return cudaSuccess;                          // capture only (bm_warm_up)
     BM_COUNT_LAUNCHES(launches);
     return cudaGraphLaunch(exec, o->stream);
 }

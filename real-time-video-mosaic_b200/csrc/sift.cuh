@@ -6,7 +6,8 @@
 struct BmSift;
 int bm_sift_create(BmSift** out, int h, int w, int nfeatures, cudaStream_t s);
 void bm_sift_destroy(BmSift* o);
-cudaError_t bm_sift_detect(BmSift* o, const uint8_t* d_gray, BmKeypoints* out);
+// launch == false: only capture + instantiate the graph of this (input, output) pair if it is not cached yet
+cudaError_t bm_sift_detect(BmSift* o, const uint8_t* d_gray, BmKeypoints* out, bool launch = true);
 const float* bm_sift_level_ptr(BmSift* o, int octave, int level, int dog, int* w, int* h);
 int bm_sift_num_octaves(BmSift* o);
 // device counters of the last detect (cand, kp, overflow flag, selected, raw, threshold bits, kp after pass A, listed candidates)

@@ -107,6 +107,14 @@ class VideMosaic:
             self._canvas_cache = out
         return self._canvas_cache
 
+    def read_canvas(self, out):
+        """canvas into a caller-owned uint8 (Hc, Wc, 3) C-contiguous array (e.g. a pinned buffer that is reused for every fetch:
+        the copy then runs at PCIe speed and no fresh 15 MB array is page-faulted in).  Returns `out`."""
+        if out.dtype != np.uint8 or tuple(out.shape) != tuple(self._shape) or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError(f"read_canvas needs a C-contiguous uint8 array of shape {tuple(self._shape)}")
+        _lib.check(self._lib.bm_get_canvas(self._h, out.ctypes.data_as(C.c_void_p)), "bm_get_canvas")
+        return out
+
     # ---- main.py:710-759 -------------------------------------------------------------------------------------
     def process_frame(self, frame_cur, frame_count=0, next_frame=None):
         """main.py:710-759.  `next_frame` (optional, not in the reference): the frame of the NEXT call, if the caller already
@@ -230,6 +238,10 @@ class VideMosaic:
         out = np.empty((h, w, 3), dtype=np.uint8)
         _lib.check(self._lib.bm_preview(self._h, w, h, 1 if rgb else 0, out.ctypes.data_as(C.c_void_p), out.nbytes), "bm_preview")
         return out
+
+    def warm_up(self):
+        """capture every CUDA graph of the per-frame path now (optional; avoids capture hiccups in the first frames)"""
+        _lib.check(self._lib.bm_warm_up(self._h), "bm_warm_up")
 
     def set_overlap(self, on):
         """True (default): the warp/blend chain of frame t overlaps detect/match/RANSAC of frame t+1; False: strictly serial"""

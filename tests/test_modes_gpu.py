@@ -108,6 +108,7 @@ def test_prefetch_and_overlap_do_not_change_results(sweep_frames, det):
         ref.process_frame(frames[t], t)
     want_canvas, want_H = ref.output_img.copy(), ref.H.copy()
     vm = b200mosaic.VideMosaic(frames[0], detector_type=det, show_intermediate=False, visualize=False)
+    vm.warm_up()                                 # graphs captured up front instead of lazily: scheduling only, too
     for t in range(1, 7):
         nxt = frames[t + 1] if t + 1 < 7 else None
         if t == 3:
@@ -164,3 +165,18 @@ def test_long_pipelined_run_equals_serial(sweep_frames):
     assert np.array_equal(a[1], b[1])
     assert np.array_equal(a[2], b[2])
     assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
+
+
+def test_read_canvas_into_caller_buffers(sweep_frames):
+    """bm_get_canvas into pinned and pageable caller-owned buffers (the pageable path is chunked through pinned staging)"""
+    import b200mosaic
+    frames, _ = sweep_frames
+    vm = b200mosaic.VideMosaic(frames[0], detector_type="orb", show_intermediate=False, visualize=False, canvas_size=(1500, 2100))
+    for t in range(1, 4):
+        vm.process_frame(frames[t], t)
+    want = vm.output_img
+    pinned = torch.empty(want.shape, dtype=torch.uint8).pin_memory().numpy()
+    assert np.array_equal(vm.read_canvas(pinned), want)                  # 9.4 MB: three staging chunks on the pageable path above
+    assert np.array_equal(vm.read_canvas(np.zeros_like(want)), want)
+    with pytest.raises(ValueError):
+        vm.read_canvas(np.zeros((4, 4, 3), np.uint8))
