@@ -115,23 +115,24 @@ __host__ __device__ constexpr int sift_level_radius(int level) { return level <=
 // row groups) -- the taller the tile, the smaller the share of row-pass work spent on halo rows (R = 13: 1.33x at 128 rows, 1.72x at 64)
 // Measured on octave 0 (3840 x 2160): 128 rows win for the two widest kernels (level 5: 47.4 -> 41.6 us, level 4: 37.3 -> 35.5 us) and
 // lose 1-3 us on levels 0-3 (two 80 KB CTAs per SM hide less latency than five 40 KB ones), hence the split.
-__host__ __device__ constexpr int sift_blur_sh(int level) { return level >= 4 ? 128 : 64; }
-__host__ __device__ constexpr int sift_blur_nt(int level) { return 4 * sift_blur_sh(level); }      // one thread per (row, 16-output segment)
-__host__ __device__ constexpr int sift_blur_ng(int level) { return sift_blur_nt(level) / 64; }     // row groups of the column pass
-__host__ __device__ constexpr int sift_tile_h(int level) {
-    return ((sift_blur_sh(level) - 2 * sift_level_radius(level)) / sift_blur_ng(level)) * sift_blur_ng(level);
+// SH (64 or 128 staged rows) is a template parameter: the tall tile is used for levels 4 / 5 of the LARGE octaves only -- on the small
+// ones fewer, bigger CTAs fill the SMs worse (aggregate over all octaves, ncu: level 4 +11 %, level 5 +3 % with tall tiles everywhere).
+__host__ __device__ constexpr int sift_blur_nt(int sh) { return 4 * sh; }                           // one thread per (row, 16-output segment)
+__host__ __device__ constexpr int sift_blur_ng(int sh) { return sift_blur_nt(sh) / 64; }            // row groups of the column pass
+__host__ __device__ constexpr int sift_tile_h(int level, int sh) {
+    return ((sh - 2 * sift_level_radius(level)) / sift_blur_ng(sh)) * sift_blur_ng(sh);
 }
 #define SIFT_BLUR_TSTRIDE (64 + 2 * 13 + 1)
-__host__ __device__ constexpr size_t sift_blur_smem(int level) { return (size_t)sift_blur_sh(level) * (SIFT_BLUR_TSTRIDE + 65) * sizeof(float); }
+__host__ __device__ constexpr size_t sift_blur_smem(int sh) { return (size_t)sh * (SIFT_BLUR_TSTRIDE + 65) * sizeof(float); }
 
-template <int LEVEL>
-__global__ void __launch_bounds__(sift_blur_nt(LEVEL), 2) k_sift_blur(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ dog,
+template <int LEVEL, int SHT>
+__global__ void __launch_bounds__(sift_blur_nt(SHT), 2) k_sift_blur(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ dog,
                                                                float* __restrict__ dec, int w, int h) {
-    constexpr int R = sift_level_radius(LEVEL), K = 2 * R + 1, TW = 64, TH = sift_tile_h(LEVEL), SW = TW + 2 * R, SH = TH + 2 * R,
-                  NO = TH / sift_blur_ng(LEVEL), NT = sift_blur_nt(LEVEL);
+    constexpr int R = sift_level_radius(LEVEL), K = 2 * R + 1, TW = 64, TH = sift_tile_h(LEVEL, SHT), SW = TW + 2 * R, SH = TH + 2 * R,
+                  NO = TH / sift_blur_ng(SHT), NT = sift_blur_nt(SHT);
     extern __shared__ __align__(16) unsigned char sift_blur_smem_raw[];
     float (*tile)[SIFT_BLUR_TSTRIDE] = reinterpret_cast<float (*)[SIFT_BLUR_TSTRIDE]>(sift_blur_smem_raw);
-    float (*rowf)[64 + 1] = reinterpret_cast<float (*)[64 + 1]>(sift_blur_smem_raw + (size_t)sift_blur_sh(LEVEL) * SIFT_BLUR_TSTRIDE * sizeof(float));
+    float (*rowf)[64 + 1] = reinterpret_cast<float (*)[64 + 1]>(sift_blur_smem_raw + (size_t)SHT * SIFT_BLUR_TSTRIDE * sizeof(float));
     const int bx = blockIdx.x * TW, by = blockIdx.y * TH;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     {
@@ -942,11 +943,17 @@ void bm_sift_destroy(BmSift* o) {
     delete o;
 }
 
+template <int LEVEL, int SHT>
+static void launch_blur_sh(const float* in, float* out, float* dog, float* dec, int w, int h, cudaStream_t s) {
+    static cudaError_t attr = cudaFuncSetAttribute(k_sift_blur<LEVEL, SHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sift_blur_smem(SHT));
+    (void)attr;
+    constexpr int TH = sift_tile_h(LEVEL, SHT);
+    BM_COUNT_LAUNCHES(1), k_sift_blur<LEVEL, SHT><<<dim3((w + 63) / 64, (h + TH - 1) / TH), sift_blur_nt(SHT), sift_blur_smem(SHT), s>>>(in, out, dog, dec, w, h);
+}
 template <int LEVEL>
 static void launch_blur(const float* in, float* out, float* dog, float* dec, int w, int h, cudaStream_t s) {
-    static cudaError_t attr = cudaFuncSetAttribute(k_sift_blur<LEVEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sift_blur_smem(LEVEL));
-    (void)attr;
-    BM_COUNT_LAUNCHES(1), k_sift_blur<LEVEL><<<dim3((w + 63) / 64, (h + sift_tile_h(LEVEL) - 1) / sift_tile_h(LEVEL)), sift_blur_nt(LEVEL), sift_blur_smem(LEVEL), s>>>(in, out, dog, dec, w, h);
+    if (LEVEL >= 4 && (long long)w * h >= (1 << 21)) launch_blur_sh<LEVEL, 128>(in, out, dog, dec, w, h, s);      // octave 0 of a 1080p frame (3840 x 2160)
+    else launch_blur_sh<LEVEL, 64>(in, out, dog, dec, w, h, s);
 }
 
 static void blur_level(int level, const float* in, float* out, float* dog, float* dec, int w, int h, cudaStream_t s) {
