@@ -27,9 +27,9 @@ def _synthetic_gray(w, h, seed):
     return cv2.cvtColor(DroneSweep(w, h, seed=seed, ground_size=2048).next(), cv2.COLOR_BGR2GRAY)
 
 
-def _orb_compare(ops, gray):
-    kp, des = ops.orb_detect_and_compute(torch.from_numpy(gray).cuda())
-    kc, dc = oorb.cv_detect_and_compute(gray)
+def _orb_compare(ops, gray, nfeatures=700):
+    kp, des = ops.orb_detect_and_compute(torch.from_numpy(gray).cuda(), nfeatures)
+    kc, dc = oorb.cv_detect_and_compute(gray, nfeatures)
     a, ad = oorb.canon(kp.astype(np.float64), des)
     b, bd = oorb.canon(kc, dc)
     assert a.shape == b.shape, (a.shape, b.shape)
@@ -60,6 +60,22 @@ def test_orb_bit_exact_on_clip_frames(ops, frames, i):
 @pytest.mark.parametrize("size", [(640, 360), (854, 480), (1280, 720), (1920, 1080)])
 def test_orb_bit_exact_on_synthetic(ops, size):
     _orb_compare(ops, _synthetic_gray(size[0], size[1], 21))
+
+
+@pytest.mark.parametrize("nfeatures,size", [(1000, (1280, 720)), (2000, (1280, 720)), (2000, (1920, 1080)), (300, (640, 360))])
+def test_orb_other_feature_budgets(ops, nfeatures, size):
+    """the reference's other ORB users run the same primitive with other budgets -- ORB_create(nfeatures=2000) in
+    slam.py:47 (keyframes, slam.py:332) and ORB_create(nfeatures=1000) + BFMatcher(HAMMING, crossCheck=True) in depth_to_3d.py:856-889.
+    Same kernels through the same stage entry points; the per-level quotas follow cv2's float32 geometric series."""
+    g = _synthetic_gray(size[0], size[1], 33)
+    _orb_compare(ops, g, nfeatures)
+    if nfeatures == 1000:                                    # depth_to_3d.py:884-885: bf.match(prev_desc, curr_desc), sorted by distance
+        g2 = np.roll(g, (3, 7), axis=(0, 1))
+        _, d1 = ops.orb_detect_and_compute(torch.from_numpy(g).cuda(), nfeatures)
+        _, d2 = ops.orb_detect_and_compute(torch.from_numpy(g2).cuda(), nfeatures)
+        bf = cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=True)
+        cvm = sorted(bf.match(d1, d2), key=lambda m: m.distance)
+        assert np.array_equal(ops.match_hamming_crosscheck(d1, d2), np.array([[m.queryIdx, m.trainIdx, m.distance] for m in cvm]))
 
 
 def test_orb_featureless_image(ops):
