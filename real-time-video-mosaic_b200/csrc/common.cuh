@@ -46,4 +46,17 @@ void bm_set_error(const char* fmt, ...);
 extern long long g_bm_launches;          // kernels launched by this library (bench.py reports it)
 #define BM_COUNT_LAUNCHES(n) (g_bm_launches += (n))
 
+// Opt a kernel into more than 48 KB of dynamic shared memory, once per (call site, device): the attribute is per device, and one
+// process may drive handles on several devices (bm_config.device).  `err` receives the CUDA status.
+#define BM_SMEM_OPTIN(kernel, bytes, err)                                                                                   \
+    do {                                                                                                                    \
+        static unsigned long long bm_optin_done_ = 0ull;                                                                    \
+        int bm_dev_ = 0;                                                                                                    \
+        (err) = cudaGetDevice(&bm_dev_);                                                                                    \
+        if ((err) == cudaSuccess && !((bm_optin_done_ >> (bm_dev_ & 63)) & 1ull)) {                                         \
+            (err) = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));                 \
+            if ((err) == cudaSuccess) bm_optin_done_ |= 1ull << (bm_dev_ & 63);                                             \
+        }                                                                                                                   \
+    } while (0)
+
 static inline int bm_div_up(int a, int b) { return (a + b - 1) / b; }

@@ -177,7 +177,8 @@ __global__ void __launch_bounds__(256) k_l2_knn2_merge(const int4* __restrict__ 
 
 cudaError_t bm_launch_l2_knn2_tc(const uint8_t* A, const int* nA, const uint8_t* B, const int* nB, int4* part, int* nn1, float* d1, int* nn2,
                                  float* d2, cudaStream_t s) {
-    static cudaError_t attr = cudaFuncSetAttribute(k_l2_knn2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcSmem) + 1024);
+    cudaError_t attr;
+    BM_SMEM_OPTIN(k_l2_knn2_tc, sizeof(TcSmem) + 1024, attr);
     if (attr != cudaSuccess) return attr;
     BM_COUNT_LAUNCHES(1), k_l2_knn2_tc<<<dim3(BM_KP_CAP / TC_M, TC_SPLIT), 128, sizeof(TcSmem) + 1024, s>>>(A, nA, B, nB, part);
     BM_COUNT_LAUNCHES(1), k_l2_knn2_merge<<<BM_KP_CAP / 256, 256, 0, s>>>(part, nA, nB, nn1, d1, nn2, d2);

@@ -728,20 +728,13 @@ __global__ void __launch_bounds__(32 * RF_WARPS, 1) k_ransac_refine(const float2
 
 cudaError_t bm_launch_ransac(const float2* d_src, const float2* d_dst, const int* d_count, double thresh, int max_iters, double confidence,
                              uint8_t* d_mask, BmRansacResult* d_out, cudaStream_t s) {
-    static bool attr_set = false;
     const size_t smem = ((sizeof(RsShared) + 15) & ~(size_t)15) + 2 * RS_SMEM_PTS * sizeof(float2);
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_ransac_homography, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    static bool attr2_set = false;
     const size_t smem2 = ((sizeof(RfShared) + 15) & ~(size_t)15) + 2 * RS_SMEM_PTS * sizeof(float2);
-    if (!attr2_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_ransac_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-        if (e != cudaSuccess) return e;
-        attr2_set = true;
-    }
+    cudaError_t e;
+    BM_SMEM_OPTIN(k_ransac_homography, smem, e);
+    if (e != cudaSuccess) return e;
+    BM_SMEM_OPTIN(k_ransac_refine, smem2, e);
+    if (e != cudaSuccess) return e;
     BM_COUNT_LAUNCHES(1), k_ransac_homography<<<1, RS_THREADS, smem, s>>>(d_src, d_dst, d_count, thresh, max_iters, confidence, d_mask, d_out);
     BM_COUNT_LAUNCHES(1), k_ransac_refine<<<1, 32 * RF_WARPS, smem2, s>>>(d_src, d_dst, d_count, d_mask, d_out);
     return cudaGetLastError();

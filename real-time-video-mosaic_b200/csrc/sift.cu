@@ -945,8 +945,9 @@ void bm_sift_destroy(BmSift* o) {
 
 template <int LEVEL, int SHT>
 static void launch_blur_sh(const float* in, float* out, float* dog, float* dec, int w, int h, cudaStream_t s) {
-    static cudaError_t attr = cudaFuncSetAttribute(k_sift_blur<LEVEL, SHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sift_blur_smem(SHT));
-    (void)attr;
+    cudaError_t attr;
+    BM_SMEM_OPTIN((k_sift_blur<LEVEL, SHT>), sift_blur_smem(SHT), attr);
+    (void)attr;                                    // a failure surfaces as the launch error picked up by the caller
     constexpr int TH = sift_tile_h(LEVEL, SHT);
     BM_COUNT_LAUNCHES(1), k_sift_blur<LEVEL, SHT><<<dim3((w + 63) / 64, (h + TH - 1) / TH), sift_blur_nt(SHT), sift_blur_smem(SHT), s>>>(in, out, dog, dec, w, h);
 }

@@ -497,7 +497,8 @@ cudaError_t bm_launch_full_rowscan(const BmBlendBufs& b, cudaStream_t s) {
 
 // chain after wbuf, g_new (rows of the window plane) and flags[0] are filled.  b.dt.p[1] is shaped for the window.
 static cudaError_t blend_tail(const BmBlendBufs& b, const BmFramePlan& plan, cudaStream_t s) {
-    static cudaError_t attr = cudaFuncSetAttribute(k_blur_blend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FbSmem));
+    cudaError_t attr;
+    BM_SMEM_OPTIN(k_blur_blend, sizeof(FbSmem), attr);
     if (attr != cudaSuccess) return attr;
     const int ww = bm_win_w(plan.win), wh = bm_win_h(plan.win);
     const BmDtPlane& po = b.dt.p[0];
