@@ -7,7 +7,8 @@
 #define BM_CHAMFER_A 62587          // cvRound(0.955f  * 65536), OpenCV distanceTransform DIST_L2 3x3
 #define BM_CHAMFER_B 89738          // cvRound(1.3693f * 65536)
 #define BM_DT_INIT 4294877557u      // OpenCV 4.x distanceTransform_3x3: DIST_MAX = UINT_MAX - DIAG_DIST (saturation value)
-#define BM_G_INF 0xFFFF             // "no zero pixel in this row"
+#define BM_G_INF 0xFFFF             // "no zero pixel in this row" (row-scan distances are clamped to it)
+#define BM_CHAMFER_SEED(gv) ((gv) == (unsigned)BM_G_INF ? BM_DT_INIT : (unsigned)BM_CHAMFER_A * (gv))   // g <= 65534 keeps a * g < DIST_MAX
 #define BM_BLK_ROWS 16              // rows per block of the distance-transform sweep tables
 #define BM_BLUR_R 15                // 31-tap Gaussian radius
 

@@ -33,7 +33,7 @@ struct DtRange { int xa[2], xb[2]; };
 // row scans
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_rowscan_bgrx(const uchar4* __restrict__ img, int img_stride, int img_col0, int img_row0,
-                                                      uint16_t* __restrict__ g, int gs, int n, int row0, const int* __restrict__ flags,
+                                                      uint32_t* __restrict__ g, int gs, int n, int row0, const int* __restrict__ flags,
                                                       int need_flag) {
     if (need_flag && flags[0] == 0) return;
     const int r = blockIdx.x, tid = threadIdx.x;
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256) k_rowscan_bgrx(const uchar4* __restrict__
     bm_rowscan_block(zb, nch, n, g + (size_t)(row0 + r) * gs);
 }
 
-__global__ void __launch_bounds__(256) k_rowscan_mask(const uint8_t* __restrict__ mask, int stride, uint16_t* __restrict__ g, int gs, int n) {
+__global__ void __launch_bounds__(256) k_rowscan_mask(const uint8_t* __restrict__ mask, int stride, uint32_t* __restrict__ g, int gs, int n) {
     const int r = blockIdx.x, tid = threadIdx.x;
     const uint8_t* row = mask + (size_t)r * stride;
     const int nch = (n + BM_ROWSCAN_CHUNK - 1) / BM_ROWSCAN_CHUNK;
@@ -75,34 +75,27 @@ __global__ void __launch_bounds__(256) k_rowscan_mask(const uint8_t* __restrict_
 // ------------------------------------------------------------------------------------------------------------------
 // warp-tile sweep primitives
 // ------------------------------------------------------------------------------------------------------------------
-struct DtRows { uint2 g[BM_BLK_ROWS]; unsigned colmask; };
+struct DtRows { uint4 g[BM_BLK_ROWS]; };
 
 // the 16 rows of block k for the lane's 4 columns [cx, cx+4) (cx is a multiple of 4, may lie outside the plane), in
 // PROCESSING order: R.g[i] is row i of the block for a downward sweep, row 15-i for an upward one -- one code path
 // serves both directions (and both planes), which keeps the unrolled sweeps small in the instruction cache
 __device__ __forceinline__ void dt_load_rows(const BmDtPlane& p, int k, int cx, bool up, DtRows& R) {
-    R.colmask = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) if (cx + i >= 0 && cx + i < p.W) R.colmask |= 1u << i;
-    const bool ld = cx >= 0 && cx < p.W;
+    const bool ld = cx >= 0 && cx < p.W;                  // columns [W, gs) of a row hold BM_DT_INF (row scan), so no per-column mask
     const int r0 = k * BM_BLK_ROWS + (up ? BM_BLK_ROWS - 1 : 0), dr = up ? -1 : 1;
-    const uint16_t* base = p.g + (size_t)r0 * p.gs + cx;
+    const uint32_t* base = p.g + (size_t)r0 * p.gs + cx;
     const ptrdiff_t step = (ptrdiff_t)dr * p.gs;
 #pragma unroll
     for (int i = 0; i < BM_BLK_ROWS; ++i) {
-        R.g[i] = make_uint2(0xffffffffu, 0xffffffffu);
-        if (ld && r0 + dr * i < p.H) R.g[i] = __ldg(reinterpret_cast<const uint2*>(base + i * step));
+        R.g[i] = make_uint4(BM_DT_INF, BM_DT_INF, BM_DT_INF, BM_DT_INF);
+        if (ld && r0 + dr * i < p.H) R.g[i] = __ldg(reinterpret_cast<const uint4*>(base + i * step));
     }
 }
 
-// seeds a * g in cv2's unsigned 16.16 arithmetic: g <= 65534 keeps a * g < DIST_MAX; g == 0xFFFF means "no zero in this row"
-__device__ __forceinline__ u32 dt_seed1(u32 g, bool colok) { return (colok && g != BM_G_INF) ? A_ * g : BM_DT_INF; }
+// seeds of row r: stored ready-made by the row scan (BmDtPlane::g)
 __device__ __forceinline__ void dt_seeds(const DtRows& R, int r, u32 (&s)[4]) {
-    const uint2 v = R.g[r];
-    s[0] = dt_seed1(v.x & 0xffffu, R.colmask & 1u);
-    s[1] = dt_seed1(v.x >> 16, R.colmask & 2u);
-    s[2] = dt_seed1(v.y & 0xffffu, R.colmask & 4u);
-    s[3] = dt_seed1(v.y >> 16, R.colmask & 8u);
+    const uint4 v = R.g[r];
+    s[0] = v.x; s[1] = v.y; s[2] = v.z; s[3] = v.w;
 }
 
 // one row step of both diagonal scans: E1 flows to the right (from column x-1 of the previous row), E2 to the left
@@ -388,7 +381,7 @@ cudaError_t bm_dt_alloc_plane(BmDtPlane* p, int Wcap, int Hcap, size_t px_cap) {
     const size_t tsz = ((px_cap / BM_BLK_ROWS + (size_t)2 * (Wcap + 8) + (size_t)Hcap + 64) + 3) & ~(size_t)3;
     p->tsz = tsz;
     cudaError_t e;
-    if ((e = cudaMalloc(&p->g, p->g_cap * sizeof(uint16_t))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&p->g, p->g_cap * sizeof(uint32_t))) != cudaSuccess) return e;
     if ((e = cudaMalloc(&p->LE, 4 * tsz * sizeof(uint32_t))) != cudaSuccess) return e;
     if ((e = cudaMalloc(&p->CE, 4 * tsz * sizeof(uint32_t))) != cudaSuccess) return e;
     if ((e = cudaMalloc(&p->CV, 2 * tsz * sizeof(uint32_t))) != cudaSuccess) return e;

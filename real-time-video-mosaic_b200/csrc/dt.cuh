@@ -14,7 +14,8 @@ static inline __host__ __device__ int bm_pad8(int v) { return (v + 7) & ~7; }
 // Sweep tables of one mask plane.  "Plane" = the pixel grid the mask lives on: the canvas for mask_old, the window for
 // mask_new.  All tables are indexed [table][block][column] with row stride ts; a block is BM_BLK_ROWS plane rows.
 struct BmDtPlane {
-    uint16_t* g;       // horizontal distance to the nearest zero pixel of the row, BM_G_INF if none     [H][gs]
+    uint32_t* g;       // sweep seeds a * (horizontal distance to the nearest zero pixel of the row) in cv2's 16.16 units, BM_DT_INF
+                       // if the row has no zero pixel and in the padding columns [W, gs): ready-made for the sweeps      [H][gs]
     int gs;            // row stride of g (multiple of 8)
     int W, H;          // plane size in pixels
     int nb;            // ceil(H / 16)

@@ -15,10 +15,11 @@ struct BmZeroBits {
 };
 
 // Thread t owns pixels [8t, 8t+8) of every 2048-pixel chunk of the row; bit i of zb.get(c) is set iff pixel i of its
-// group in chunk c is a zero pixel (pixels beyond n must be reported as non-zero).  Writes g[x] = min(distance to the
-// nearest zero pixel of the row, 0xFFFF) for x in [0, n) -- in whole groups of 8, the row buffer is padded to 8.
+// group in chunk c is a zero pixel (pixels beyond n must be reported as non-zero).  With d(x) = min(distance to the nearest zero
+// pixel of the row, 0xFFFF) it writes the sweep seed g[x] = a * d(x) (cv2's 16.16 axial step; BM_DT_INF for d = 0xFFFF = "no zero
+// in this row") for x in [0, n) and BM_DT_INF for the padding columns -- in whole groups of 8, the row buffer is padded to 8.
 // Every thread of the CTA must call it (it synchronises).
-static __device__ __forceinline__ void bm_rowscan_block(const BmZeroBits& zb, int nch, int n, uint16_t* __restrict__ grow) {
+static __device__ __forceinline__ void bm_rowscan_block(const BmZeroBits& zb, int nch, int n, uint32_t* __restrict__ grow) {
     __shared__ int s_wl[BM_ROWSCAN_MAX_CHUNKS][8], s_wf[BM_ROWSCAN_MAX_CHUNKS][8];
     __shared__ int s_cl[BM_ROWSCAN_MAX_CHUNKS], s_cf[BM_ROWSCAN_MAX_CHUNKS];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -56,7 +57,7 @@ static __device__ __forceinline__ void bm_rowscan_block(const BmZeroBits& zb, in
         for (int w = 0; w < warp; ++w) P = max(P, s_wl[c][w]);
         for (int w = warp + 1; w < 8; ++w) S = min(S, s_wf[c][w]);
         if (base < n) {
-            unsigned o[4] = {0u, 0u, 0u, 0u};
+            unsigned o[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const unsigned ml = b & ((2u << i) - 1u), mr = b >> i;
@@ -64,9 +65,10 @@ static __device__ __forceinline__ void bm_rowscan_block(const BmZeroBits& zb, in
                 const int left = ml ? base + 31 - __clz(ml) : P;
                 const int right = mr ? p + __ffs(mr) - 1 : S;
                 const unsigned gv = (unsigned)min(min(p - left, right - p), (int)BM_G_INF);
-                o[i >> 1] |= gv << (16 * (i & 1));
+                o[i] = p < n ? BM_CHAMFER_SEED(gv) : BM_DT_INIT;          // padding columns never seed a sweep
             }
             *reinterpret_cast<uint4*>(grow + base) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(grow + base + 4) = make_uint4(o[4], o[5], o[6], o[7]);
         }
     }
     __syncthreads();           // the shared tables may be reused by the next row of the same CTA

@@ -194,7 +194,7 @@ __device__ __forceinline__ uchar4 warp_sample_bgrx(const uchar4* __restrict__ sr
 // terms of OpenCV's 64-column evaluation block are shared), detect np.any(overlap), and produce the nearest-zero row scan
 // of mask_new from the mask bits still in registers.
 __global__ void __launch_bounds__(256) k_warp_rows(const uchar4* __restrict__ src, BmFramePlan plan, const uchar4* __restrict__ canvas,
-                                                   uchar4* __restrict__ wbuf, uint16_t* __restrict__ g_new, int gs, int* __restrict__ flags) {
+                                                   uchar4* __restrict__ wbuf, uint32_t* __restrict__ g_new, int gs, int* __restrict__ flags) {
     const int ly = blockIdx.x, tid = threadIdx.x;
     const int ww = bm_win_w(plan.win), y = plan.win.y0 + ly;
     const int nch = (ww + BM_ROWSCAN_CHUNK - 1) / BM_ROWSCAN_CHUNK;
