@@ -251,8 +251,12 @@ __global__ void __launch_bounds__(256) k_fast_cnms(BmOrbLevels lv, const uint8_t
         if (x >= ORB_EDGE && y >= ORB_EDGE && x < L.w - ORB_EDGE && y < L.h - ORB_EDGE) {
             const uint8_t* p = score + L.off + (size_t)y * L.w + x;
             const int w = L.w;
+            // nine independent loads, then one comparison against the neighbourhood maximum (a short-circuit && chain would issue the
+            // scattered byte loads one after the other)
             sc = p[0];
-            keep = sc > 0 && sc > p[-1] && sc > p[1] && sc > p[-w - 1] && sc > p[-w] && sc > p[-w + 1] && sc > p[w - 1] && sc > p[w] && sc > p[w + 1];
+            const int n0 = p[-1], n1 = p[1], n2 = p[-w - 1], n3 = p[-w], n4 = p[-w + 1], n5 = p[w - 1], n6 = p[w], n7 = p[w + 1];
+            const int nmax = max(max(max(n0, n1), max(n2, n3)), max(max(n4, n5), max(n6, n7)));
+            keep = sc > 0 && sc > nmax;
         }
     }
     // CTA-aggregated append: one global atomic per CTA iteration instead of one per warp
