@@ -197,13 +197,6 @@ __global__ void __launch_bounds__(sift_blur_nt(SHT), 2) k_sift_blur(const float*
     }
 }
 
-// next octave base = level 3 decimated by 2 (INTER_NEAREST: dst(x,y) = src(2x,2y))
-__global__ void __launch_bounds__(256) k_sift_decimate(const float* __restrict__ src, int sw, float* __restrict__ dst, int dw, int dh) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= dw || y >= dh) return;
-    dst[(size_t)y * dw + x] = src[(size_t)(2 * y) * sw + 2 * x];
-}
-
 // ------------------------------------------------------------------------------------------------------------------
 // scale-space extrema + adjustLocalExtrema
 // ------------------------------------------------------------------------------------------------------------------
