@@ -153,12 +153,19 @@ bm_status bm_blend_step_bgr(uint8_t* d_canvas_bgr, const uint8_t* d_warped_bgr, 
 
 /* ---- feature / matching / RANSAC stage entry points (small host arrays; parity tests + the Python mirror) ---------- */
 /* cv2.ORB_create(n).detectAndCompute(gray, None)  main.py:36,112,718.  h_kp rows: x, y, size, angle, response, octave
- * (float32 x 6); h_desc: n x 32 uint8.  Order: level-major, row-major inside a level (cv2's order is nth_element's). */
+ * (float32 x 6); h_desc: n x 32 uint8.  Order: cv2's own (level-major; inside a level the order KeyPointsFilter::retainBest,
+ * i.e. libstdc++'s nth_element + partition, leaves -- emulated on the device, see bm_cv_retain_best). */
 bm_status bm_orb_detect_and_compute(const uint8_t* d_gray, int h, int w, int nfeatures, float* h_kp, uint8_t* h_desc,
                                     int cap, int* n_out);
 /* cv2.SIFT_create(n).detectAndCompute(gray, None)  main.py:33,112,718.  h_desc: n x 128 float32 (integer valued). */
 bm_status bm_sift_detect_and_compute(const uint8_t* d_gray, int h, int w, int nfeatures, float* h_kp, float* h_desc,
                                      int cap, int* n_out);
+/* cv::KeyPointsFilter::retainBest(keypoints, n_points) as the detectors above apply it (inside detectAndCompute, main.py:112,718):
+ * which of the n items (responses h_resp, input order) survive and IN WHICH ORDER -- std::nth_element(begin, begin + n_points - 1,
+ * end, response >) + std::partition(begin + n_points, end, response >= boundary) of libstdc++, reproduced element for element by
+ * parallel pairing passes on one CTA.  as_u8 != 0: keys are integers 0..255 (FAST scores) handled as bytes.  h_idx_out (capacity n)
+ * receives the surviving input indices in output order, *m_out their number. */
+bm_status bm_cv_retain_best(const float* h_resp, int n, int n_points, int as_u8, int* h_idx_out, int* m_out);
 /* BFMatcher(NORM_HAMMING, crossCheck=True).match + sorted(key=distance)  main.py:694-698 */
 bm_status bm_match_hamming_crosscheck(const uint8_t* h_des_q, int nq, const uint8_t* h_des_t, int nt,
                                       int* h_q, int* h_t, float* h_dist, int* m_out);

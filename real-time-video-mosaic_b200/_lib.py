@@ -93,6 +93,7 @@ def load():
     fp = C.POINTER(C.c_float)
     _sig(lib, "bm_orb_detect_and_compute", i, vp, i, i, i, vp, vp, i, ip)
     _sig(lib, "bm_sift_detect_and_compute", i, vp, i, i, i, vp, vp, i, ip)
+    _sig(lib, "bm_cv_retain_best", i, vp, i, i, i, vp, ip)
     _sig(lib, "bm_match_hamming_crosscheck", i, vp, i, vp, i, vp, vp, vp, ip)
     _sig(lib, "bm_match_l2_knn2_ratio", i, vp, i, vp, i, C.c_double, vp, vp, vp, ip)
     _sig(lib, "bm_ransac_homography", i, vp, vp, i, C.c_double, i, C.c_double, dp, ip, ip, ip)

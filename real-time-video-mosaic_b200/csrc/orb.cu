@@ -5,15 +5,18 @@
 // (except the resize chain, which is inherently sequential level to level):
 //   resize chain (8.8 fixed point)            -> pyr
 //   FAST-9 score map (bitmask arc test)       -> score (u8)
-//   3x3 NMS + border filter                   -> candidate list via per-warp ballot/popc compaction + 256-bin histograms
-//   retainBest(2q) by FAST score              -> exact threshold from the histogram (scores are integers <= 254)
-//   Harris on survivors                       -> second compaction
-//   retainBest(q) by Harris (ties kept)       -> O(n^2) rank count per level, deterministic (y,x) ordering
+//   3x3 NMS + border filter                   -> one bit per pixel; a warp per row expands it into the row-major survivor list
+//                                                (cv2's FAST output order, no sort)
+//   retainBest(2q) by FAST score, Harris on
+//   the survivors, retainBest(q) by Harris    -> one CTA per level, with cv2's exact OUTPUT ORDER (libstdc++ introselect +
+//                                                partition emulated as parallel pairing passes, cvorder.cuh): keypoints,
+//                                                descriptors, matches and RANSAC samples come out as in the reference run
 //   IC angle (warp per keypoint)              -> fastAtan2 in non-contracted float32
 //   fused patch blur + rBRIEF                 -> the 7x7 sigma-2 Gaussian is evaluated only on the 37x37 patch around
 //                                                each keypoint (in shared memory) instead of blurring every level
 #include "orb.cuh"
 #include "orb_pattern.cuh"
+#include "cvorder.cuh"
 #include <math.h>
 #include <string.h>
 #include <new>
@@ -67,8 +70,7 @@ __device__ __forceinline__ bool tile_xy(const BmOrbLevel& L, int& x, int& y) {
 //   k_fast_detect : one thread per pixel: 16 ring differences as two bit masks, 9-contiguous-arc test; corners are compacted
 //                   (ballot / popc) into a per-level list, the score map is zeroed
 //   k_fast_cscore : one thread per corner: cornerScore<16> (window minima / maxima by doubling) -> score map
-//   k_fast_cnms   : one thread per corner: 3x3 non-maximum suppression on the score map, border filter, candidate list and a
-//                   per-CTA shared-memory score histogram (for retainBest(2 * quota))
+//   k_fast_cnms   : one thread per corner: 3x3 non-maximum suppression on the score map, border filter, survivor bitmap
 __device__ __forceinline__ void fast_ring(const uint8_t* __restrict__ p, int w, int (&d)[16]) {
     const int c = p[0];
     d[0] = c - p[3 * w];          d[1] = c - p[3 * w + 1];   d[2] = c - p[2 * w + 2];   d[3] = c - p[w + 3];
@@ -232,166 +234,141 @@ __global__ void __launch_bounds__(256) k_fast_cscore(BmOrbLevels lv, const uint8
 }
 
 __global__ void __launch_bounds__(256) k_fast_cnms(BmOrbLevels lv, const uint8_t* __restrict__ score, const unsigned* __restrict__ corners,
-                                                   uint2* __restrict__ cand, int* __restrict__ ctr, int* __restrict__ hist) {
-    __shared__ int sh[256];
-    __shared__ int s_n, s_base;
+                                                   const int* __restrict__ ctr, unsigned* __restrict__ nmsbits, int* __restrict__ rowcnt) {
     const int level = blockIdx.y;
     const BmOrbLevel L = lv.l[level];
     const int n = min(ctr[40 + level], (L.w * L.h) / 2);
-    if ((int)(blockIdx.x * blockDim.x) >= n) return;
-    sh[threadIdx.x] = 0;
-    __syncthreads();
-  for (int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {                 // CTA-uniform trip count
-    const int i = i0 + threadIdx.x;
-    bool keep = false;
-    int x = 0, y = 0, sc = 0;
-    if (i < n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const unsigned xy = corners[L.off / 2 + i];
-        x = xy & 0xffff; y = xy >> 16;
+        const int x = xy & 0xffff, y = xy >> 16;
         if (x >= ORB_EDGE && y >= ORB_EDGE && x < L.w - ORB_EDGE && y < L.h - ORB_EDGE) {
             const uint8_t* p = score + L.off + (size_t)y * L.w + x;
             const int w = L.w;
             // nine independent loads, then one comparison against the neighbourhood maximum (a short-circuit && chain would issue the
             // scattered byte loads one after the other)
-            sc = p[0];
+            const int sc = p[0];
             const int n0 = p[-1], n1 = p[1], n2 = p[-w - 1], n3 = p[-w], n4 = p[-w + 1], n5 = p[w - 1], n6 = p[w], n7 = p[w + 1];
             const int nmax = max(max(max(n0, n1), max(n2, n3)), max(max(n4, n5), max(n6, n7)));
-            keep = sc > 0 && sc > nmax;
-        }
-    }
-    // CTA-aggregated append: one global atomic per CTA iteration instead of one per warp
-    const unsigned bal = __ballot_sync(0xffffffffu, keep);
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
-    int slot = -1;
-    if (bal) {
-        const int lane = threadIdx.x & 31, leader = __ffs(bal) - 1;
-        int base = 0;
-        if (lane == leader) base = atomicAdd(&s_n, __popc(bal));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (keep) { slot = base + __popc(bal & ((1u << lane) - 1u)); atomicAdd(&sh[sc], 1); }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && s_n > 0) s_base = atomicAdd(&ctr[level], s_n);
-    __syncthreads();
-    if (slot >= 0) {
-        const int idx = s_base + slot;
-        if (idx < L.cand_cap) cand[L.cand_off + idx] = make_uint2((unsigned)x | ((unsigned)y << 16), (unsigned)sc);
-    }
-  }
-    __syncthreads();
-    if (sh[threadIdx.x]) atomicAdd(&hist[level * 256 + threadIdx.x], sh[threadIdx.x]);
-}
-
-// retainBest(2 * quota) threshold per level from the score histogram: one warp per level, 8 bins per lane in descending score
-// order, warp prefix sum, the first bin whose cumulative count reaches 2 * quota
-__global__ void __launch_bounds__(256) k_fast_threshold(BmOrbLevels lv, int* __restrict__ ctr, const int* __restrict__ hist) {
-    const int level = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (level >= BM_ORB_LEVELS) return;
-    const BmOrbLevel L = lv.l[level];
-    int n1 = ctr[level];
-    if (n1 > L.cand_cap) { n1 = L.cand_cap; if (lane == 0) ctr[32] = 1; }
-    const int n = 2 * L.quota;
-    int h[8], sum = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { h[k] = __ldg(hist + level * 256 + 255 - (lane * 8 + k)); sum += h[k]; }
-    int incl = sum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += u; }
-    int cum = incl - sum, first = 256;            // `first` = descending-order index of the first bin with cum >= n
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { cum += h[k]; if (first == 256 && cum >= n) first = lane * 8 + k; }
-    first = __reduce_min_sync(0xffffffffu, first);
-    int thr = 0;
-    if (n <= 0) thr = 256;
-    else if (n1 > n && first < 256) thr = 255 - first;
-    __syncwarp();
-    if (lane == 0) { ctr[level] = n1; ctr[16 + level] = thr; }
-}
-
-__global__ void __launch_bounds__(256) k_harris(BmOrbLevels lv, const uint8_t* __restrict__ pyr, const uint2* __restrict__ cand,
-                                                uint2* __restrict__ cand2, int* __restrict__ ctr) {
-    const int gi = blockIdx.x * blockDim.x + threadIdx.x;
-    int level = 0;
-#pragma unroll
-    for (int l = 1; l < BM_ORB_LEVELS; ++l) if (gi >= lv.l[l].cand_off) level = l;
-    const BmOrbLevel L = lv.l[level];
-    const int li = gi - L.cand_off;
-    bool ok = gi < lv.total_cand && li < ctr[level];
-    uint2 cd = make_uint2(0, 0);
-    if (ok) { cd = cand[gi]; ok = (int)cd.y >= ctr[16 + level]; }
-    float resp = 0.f;
-    if (ok) {
-        const int x0 = cd.x & 0xffff, y0 = cd.x >> 16, w = L.w;
-        const uint8_t* p0 = pyr + L.off + (size_t)(y0 - 3) * w + (x0 - 3);
-        int a = 0, b = 0, c = 0;
-        for (int dy = 0; dy < 7; ++dy) {
-            const uint8_t* p = p0 + dy * w;
-#pragma unroll
-            for (int dx = 0; dx < 7; ++dx, ++p) {
-                const int Ix = (p[1] - p[-1]) * 2 + (p[-w + 1] - p[-w - 1]) + (p[w + 1] - p[w - 1]);
-                const int Iy = (p[w] - p[-w]) * 2 + (p[w - 1] - p[-w - 1]) + (p[w + 1] - p[-w + 1]);
-                a += Ix * Ix; b += Iy * Iy; c += Ix * Iy;
+            if (sc > 0 && sc > nmax) {
+                // cv2's FAST emits its keypoints row by row, left to right; the bitmap keeps that order without a sort
+                atomicOr(&nmsbits[L.bits_off + y * L.wpr + (x >> 5)], 1u << (x & 31));
+                atomicAdd(&rowcnt[L.row_off + y], 1);
             }
         }
-        const float fa = (float)a, fb = (float)b, fc = (float)c;
-        const float scale = __fdiv_rn(1.0f, __fmul_rn(28.0f, 255.0f));
-        const float s4 = __fmul_rn(__fmul_rn(__fmul_rn(scale, scale), scale), scale);
-        const float sum = __fadd_rn(fa, fb);
-        const float t = __fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), __fmul_rn(__fmul_rn(0.04f, sum), sum));
-        resp = __fmul_rn(t, s4);
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, ok);
-    if (bal) {
-        const int lane = threadIdx.x & 31, leader = __ffs(bal) - 1;
-        int base = 0;
-        if (lane == leader) base = atomicAdd(&ctr[8 + level], __popc(bal));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (ok) cand2[L.cand_off + base + __popc(bal & ((1u << lane) - 1u))] = make_uint2(cd.x, __float_as_uint(resp));
     }
 }
 
-// retainBest(quota) on Harris responses: keep i iff fewer than quota candidates have a strictly larger response
-__global__ void __launch_bounds__(1024) k_harris_select(BmOrbLevels lv, const uint2* __restrict__ cand2, int* __restrict__ ctr,
-                                                        uint8_t* __restrict__ keep) {
-    const int level = blockIdx.x;
+// NMS bitmap -> survivor list of every level in row-major order (the order cv2's FAST + runByImageBorder hand to retainBest):
+// one warp per (level, row); its base is the sum of the counts of the rows above
+__global__ void __launch_bounds__(256) k_orb_compact(BmOrbLevels lv, const uint8_t* __restrict__ score, const unsigned* __restrict__ nmsbits,
+                                                     const int* __restrict__ rowcnt, int* __restrict__ ctr, uint8_t* __restrict__ ckey,
+                                                     unsigned* __restrict__ cxy) {
+    int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= lv.total_rows) return;
+    int level = 0;
+#pragma unroll
+    for (int l = 1; l < BM_ORB_LEVELS; ++l) if (row >= lv.l[l].row_off) level = l;
     const BmOrbLevel L = lv.l[level];
-    const int n2 = ctr[8 + level];
-    __shared__ int kept;
-    if (threadIdx.x == 0) kept = 0;
-    __syncthreads();
-    const uint2* c = cand2 + L.cand_off;
-    int mine = 0;
-    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
-        const float r = __uint_as_float(c[i].y);
-        int greater = 0;
-        if (n2 > L.quota)
-            for (int j = 0; j < n2; ++j) greater += (__uint_as_float(c[j].y) > r) ? 1 : 0;
-        const bool k = greater < L.quota;
-        keep[L.cand_off + i] = k ? 1 : 0;
-        mine += k ? 1 : 0;
+    const int y = row - L.row_off;
+    const int cnt = rowcnt[row];
+    if (cnt == 0 && y != L.h - 1) return;
+    int base = 0;
+    for (int r = lane; r < y; r += 32) base += rowcnt[L.row_off + r];
+    base = __reduce_add_sync(0xffffffffu, base);
+    if (y == L.h - 1 && lane == 0) {
+        int n1 = base + cnt;
+        if (n1 > L.cand_cap) { n1 = L.cand_cap; ctr[32] = 1; }
+        ctr[level] = n1;
     }
-    if (mine) atomicAdd(&kept, mine);
-    __syncthreads();
-    if (threadIdx.x == 0) ctr[24 + level] = kept;
+    int run = base;
+    for (int j0 = 0; j0 < L.wpr; j0 += 32) {
+        const int j = j0 + lane;
+        unsigned word = j < L.wpr ? nmsbits[L.bits_off + y * L.wpr + j] : 0u;
+        const int c = __popc(word);
+        int inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+        int pos = run + inc - c;
+        while (word) {
+            const int b = __ffs(word) - 1; word &= word - 1;
+            const int x = j * 32 + b;
+            if (pos < L.cand_cap) {
+                ckey[L.cand_off + pos] = score[L.off + (size_t)y * L.w + x];
+                cxy[L.cand_off + pos] = (unsigned)x | ((unsigned)y << 16);
+            }
+            ++pos;
+        }
+        run += __shfl_sync(0xffffffffu, inc, 31);
+    }
 }
 
-// final keypoint list: level-major, (y,x) order inside a level
-__global__ void __launch_bounds__(1024) k_orb_emit(BmOrbLevels lv, const uint2* __restrict__ cand2, int* ctr,
-                                                   const uint8_t* __restrict__ keep, BmKeypoints out) {
+__device__ __forceinline__ float harris_response(const uint8_t* __restrict__ pyr, const BmOrbLevel& L, unsigned xy) {
+    const int x0 = xy & 0xffff, y0 = xy >> 16, w = L.w;
+    const uint8_t* p0 = pyr + L.off + (size_t)(y0 - 3) * w + (x0 - 3);
+    int a = 0, b = 0, c = 0;
+    for (int dy = 0; dy < 7; ++dy) {
+        const uint8_t* p = p0 + dy * w;
+#pragma unroll
+        for (int dx = 0; dx < 7; ++dx, ++p) {
+            const int Ix = (p[1] - p[-1]) * 2 + (p[-w + 1] - p[-w - 1]) + (p[w + 1] - p[w - 1]);
+            const int Iy = (p[w] - p[-w]) * 2 + (p[w - 1] - p[-w - 1]) + (p[w + 1] - p[-w + 1]);
+            a += Ix * Ix; b += Iy * Iy; c += Ix * Iy;
+        }
+    }
+    const float fa = (float)a, fb = (float)b, fc = (float)c;
+    const float scale = __fdiv_rn(1.0f, __fmul_rn(28.0f, 255.0f));
+    const float s4 = __fmul_rn(__fmul_rn(__fmul_rn(scale, scale), scale), scale);
+    const float sum = __fadd_rn(fa, fb);
+    const float t = __fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), __fmul_rn(__fmul_rn(0.04f, sum), sum));
+    return __fmul_rn(t, s4);
+}
+
+// Per level (one CTA each), exactly as cv2's computeKeyPoints: retainBest(2 * quota) on the FAST scores of the row-major list,
+// HarrisResponses of the survivors, retainBest(quota) on those -- both with cv2's output order (cvorder.cuh).
+#define ORB_SEL_SMEM (200 * 1024)
+__global__ void __launch_bounds__(CVO_THREADS) k_orb_select(BmOrbLevels lv, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ ckey,
+                                                            const unsigned* __restrict__ cxy, int* __restrict__ idx, int* __restrict__ idx2,
+                                                            int* __restrict__ lists, float* __restrict__ resp2, uint2* __restrict__ cand2,
+                                                            int* __restrict__ ctr) {
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    __shared__ CvoShared sh;
     const int level = blockIdx.x;
     const BmOrbLevel L = lv.l[level];
-    const int n2 = ctr[8 + level];
+    const int n1 = min(ctr[level], L.cand_cap);
+    uint8_t* k8 = ckey + L.cand_off;
+    int* id1 = idx + L.cand_off;
+    int* id2 = idx2 + L.cand_off;
+    int* listL = lists + 2 * L.cand_off + 4 * level;
+    int* listR = listL + L.cand_cap + 2;
+    if (n1 <= ORB_SEL_SMEM) {
+        uint8_t* s8 = sel_smem;
+        for (int i = threadIdx.x; i < n1; i += CVO_THREADS) s8[i] = k8[i];
+        k8 = s8;
+    }
+    for (int i = threadIdx.x; i < n1; i += CVO_THREADS) id1[i] = i;
+    __syncthreads();
+    const int m1 = cvo_retain_best<uint8_t>(k8, id1, listL, listR, n1, 2 * L.quota, sh);
+    float* kf = (size_t)m1 * 4 <= ORB_SEL_SMEM ? reinterpret_cast<float*>(sel_smem) : resp2 + L.cand_off;
+    const unsigned* xy = cxy + L.cand_off;
+    for (int i = threadIdx.x; i < m1; i += CVO_THREADS) { kf[i] = harris_response(pyr, L, xy[id1[i]]); id2[i] = i; }
+    __syncthreads();
+    const int m2 = cvo_retain_best<float>(kf, id2, listL, listR, m1, L.quota, sh);
+    for (int i = threadIdx.x; i < m2; i += CVO_THREADS)
+        cand2[L.cand_off + i] = make_uint2(xy[id1[id2[i]]], __float_as_uint(kf[i]));
+    if (threadIdx.x == 0) ctr[24 + level] = m2;
+}
+
+// final keypoint list: level-major, cv2's order inside a level
+__global__ void __launch_bounds__(1024) k_orb_emit(BmOrbLevels lv, const uint2* __restrict__ cand2, int* ctr, BmKeypoints out) {
+    const int level = blockIdx.x;
+    const BmOrbLevel L = lv.l[level];
+    const int m2 = ctr[24 + level];
     int base = 0;
     for (int l = 0; l < level; ++l) base += ctr[24 + l];
     const uint2* c = cand2 + L.cand_off;
-    const uint8_t* kf = keep + L.cand_off;
-    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
-        if (!kf[i]) continue;
-        const unsigned key = ((c[i].x >> 16) << 16) | (c[i].x & 0xffff);     // (y << 16) | x
-        int rank = 0;
-        for (int j = 0; j < n2; ++j) rank += (kf[j] && c[j].x < key) ? 1 : 0;  // cand.x is already (y<<16)|x
-        const int o = base + rank;
+    for (int i = threadIdx.x; i < m2; i += blockDim.x) {
+        const int o = base + i;
         if (o < BM_KP_CAP) {
             const int x = c[i].x & 0xffff, y = c[i].x >> 16;
             out.pt[o] = make_float2(__fmul_rn((float)x, L.scale), __fmul_rn((float)y, L.scale));
@@ -402,7 +379,7 @@ __global__ void __launch_bounds__(1024) k_orb_emit(BmOrbLevels lv, const uint2* 
         }
     }
     if (level == BM_ORB_LEVELS - 1 && threadIdx.x == 0) {
-        int tot = base + ctr[24 + level];
+        int tot = base + m2;
         if (tot > BM_KP_CAP) { tot = BM_KP_CAP; ctr[32] = 1; }
         *out.count = tot;
     }
@@ -528,7 +505,7 @@ static void make_levels(BmOrbLevels* lv, int w, int h, int nfeatures) {
     // nfeaturesPerLevel (orb.cpp computeKeyPoints)
     const float factor = (float)(1.0 / sf);
     float nd = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)BM_ORB_LEVELS));
-    int sum = 0, off = 0, coff = 0;
+    int sum = 0, off = 0, coff = 0, roff = 0, boff = 0;
     for (int l = 0; l < BM_ORB_LEVELS; ++l) {
         BmOrbLevel& L = lv->l[l];
         L.scale = (float)pow(sf, (double)l);
@@ -542,9 +519,14 @@ static void make_levels(BmOrbLevels* lv, int w, int h, int nfeatures) {
         L.cand_off = coff;
         L.cand_cap = ((L.w * L.h / 4 + 1024) + 255) & ~255;
         coff += L.cand_cap;
+        L.wpr = (L.w + 31) / 32;
+        L.row_off = roff; roff += L.h;
+        L.bits_off = boff; boff += L.wpr * L.h;
     }
     lv->total_px = off;
     lv->total_cand = coff;
+    lv->total_rows = roff;
+    lv->total_words = boff;
 }
 
 int bm_kp_alloc(BmKeypoints* k, int desc_bytes) {
@@ -572,20 +554,29 @@ int bm_orb_create(BmOrb** out, int h, int w, int nfeatures, cudaStream_t s) {
     memset(o, 0, sizeof(*o));
     o->w = w; o->h = h; o->nfeatures = nfeatures; o->stream = s;
     make_levels(&o->lv, w, h, nfeatures);
+    const size_t tc = (size_t)o->lv.total_cand;
+    o->zero_bytes = (64 + (size_t)o->lv.total_rows + (size_t)o->lv.total_words) * sizeof(int);
     bool ok = cudaMalloc(&o->pyr, o->lv.total_px + 64) == cudaSuccess && cudaMalloc(&o->score, o->lv.total_px + 64) == cudaSuccess &&
-              cudaMalloc(&o->cand, (size_t)o->lv.total_cand * sizeof(uint2)) == cudaSuccess &&
-              cudaMalloc(&o->cand2, (size_t)o->lv.total_cand * sizeof(uint2)) == cudaSuccess &&
-              cudaMalloc(&o->keep, o->lv.total_cand) == cudaSuccess && cudaMalloc(&o->ctr, 64 * sizeof(int)) == cudaSuccess &&
-              cudaMalloc(&o->hist, BM_ORB_LEVELS * 256 * sizeof(int)) == cudaSuccess &&
+              cudaMalloc(&o->ctr, o->zero_bytes) == cudaSuccess &&
+              cudaMalloc(&o->ckey, tc) == cudaSuccess && cudaMalloc(&o->cxy, tc * sizeof(unsigned)) == cudaSuccess &&
+              cudaMalloc(&o->idx, tc * sizeof(int)) == cudaSuccess && cudaMalloc(&o->idx2, tc * sizeof(int)) == cudaSuccess &&
+              cudaMalloc(&o->lists, (2 * tc + 4 * BM_ORB_LEVELS + 8) * sizeof(int)) == cudaSuccess &&
+              cudaMalloc(&o->resp2, tc * sizeof(float)) == cudaSuccess && cudaMalloc(&o->cand2, tc * sizeof(uint2)) == cudaSuccess &&
               cudaMalloc(&o->corners, ((size_t)o->lv.total_px / 2 + 64) * sizeof(unsigned)) == cudaSuccess;
     if (!ok) { bm_orb_destroy(o); return -1; }
+    o->rowcnt = o->ctr + 64;
+    o->nmsbits = reinterpret_cast<unsigned*>(o->rowcnt + o->lv.total_rows);
+    cudaError_t e;
+    BM_SMEM_OPTIN(k_orb_select, ORB_SEL_SMEM, e);
+    if (e != cudaSuccess) { bm_orb_destroy(o); return -1; }
     *out = o;
     return 0;
 }
 void bm_orb_destroy(BmOrb* o) {
     if (!o) return;
     for (int i = 0; i < o->ngraphs; ++i) cudaGraphExecDestroy(o->graphs[i].exec);
-    cudaFree(o->pyr); cudaFree(o->score); cudaFree(o->cand); cudaFree(o->cand2); cudaFree(o->keep); cudaFree(o->ctr); cudaFree(o->hist); cudaFree(o->corners);
+    cudaFree(o->pyr); cudaFree(o->score); cudaFree(o->ctr); cudaFree(o->ckey); cudaFree(o->cxy); cudaFree(o->idx); cudaFree(o->idx2);
+    cudaFree(o->lists); cudaFree(o->resp2); cudaFree(o->cand2); cudaFree(o->corners);
     delete o;
 }
 
@@ -593,24 +584,21 @@ static cudaError_t orb_enqueue(BmOrb* o, const uint8_t* d_gray, BmKeypoints* out
     cudaStream_t s = o->stream;
     const BmOrbLevels& lv = o->lv;
     cudaError_t e;
-    if ((e = cudaMemsetAsync(o->ctr, 0, 64 * sizeof(int), s)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(o->hist, 0, BM_ORB_LEVELS * 256 * sizeof(int), s)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(o->ctr, 0, o->zero_bytes, s)) != cudaSuccess) return e;      // counters, row counts, NMS bitmap
     if ((e = cudaMemcpyAsync(o->pyr, d_gray, (size_t)o->w * o->h, cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return e;
     const dim3 blk(32, 8);
     for (int l = 1; l < BM_ORB_LEVELS; ++l) {
         const BmOrbLevel &P = lv.l[l - 1], &L = lv.l[l];
         BM_COUNT_LAUNCHES(1), k_resize_exact<<<dim3((L.w + 31) / 32, (L.h + 7) / 8), blk, 0, s>>>(o->pyr + P.off, P.w, P.h, o->pyr + L.off, L.w, L.h);
     }
-    const int tiles0 = ((lv.l[0].w + 31) / 32) * ((lv.l[0].h + 7) / 8);
     const int cblocks = 148;                               // per level; the per-corner kernels stride over the corner lists
     if ((e = cudaMemsetAsync(o->score, 0, (size_t)lv.total_px, s)) != cudaSuccess) return e;
     BM_COUNT_LAUNCHES(1), k_fast_detect<<<fast_total_tiles(lv), blk, 0, s>>>(lv, o->pyr, o->corners, o->ctr);
     BM_COUNT_LAUNCHES(1), k_fast_cscore<<<dim3(cblocks, BM_ORB_LEVELS), 256, 0, s>>>(lv, o->pyr, o->corners, o->ctr, o->score);
-    BM_COUNT_LAUNCHES(1), k_fast_cnms<<<dim3(cblocks, BM_ORB_LEVELS), 256, 0, s>>>(lv, o->score, o->corners, o->cand, o->ctr, o->hist);
-    BM_COUNT_LAUNCHES(1), k_fast_threshold<<<1, 256, 0, s>>>(lv, o->ctr, o->hist);
-    BM_COUNT_LAUNCHES(1), k_harris<<<(lv.total_cand + 255) / 256, 256, 0, s>>>(lv, o->pyr, o->cand, o->cand2, o->ctr);
-    BM_COUNT_LAUNCHES(1), k_harris_select<<<BM_ORB_LEVELS, 1024, 0, s>>>(lv, o->cand2, o->ctr, o->keep);
-    BM_COUNT_LAUNCHES(1), k_orb_emit<<<BM_ORB_LEVELS, 1024, 0, s>>>(lv, o->cand2, o->ctr, o->keep, *out);
+    BM_COUNT_LAUNCHES(1), k_fast_cnms<<<dim3(cblocks, BM_ORB_LEVELS), 256, 0, s>>>(lv, o->score, o->corners, o->ctr, o->nmsbits, o->rowcnt);
+    BM_COUNT_LAUNCHES(1), k_orb_compact<<<(lv.total_rows * 32 + 255) / 256, 256, 0, s>>>(lv, o->score, o->nmsbits, o->rowcnt, o->ctr, o->ckey, o->cxy);
+    BM_COUNT_LAUNCHES(1), k_orb_select<<<BM_ORB_LEVELS, CVO_THREADS, ORB_SEL_SMEM, s>>>(lv, o->pyr, o->ckey, o->cxy, o->idx, o->idx2, o->lists, o->resp2, o->cand2, o->ctr);
+    BM_COUNT_LAUNCHES(1), k_orb_emit<<<BM_ORB_LEVELS, 1024, 0, s>>>(lv, o->cand2, o->ctr, *out);
     BM_COUNT_LAUNCHES(1), k_ic_angle<<<(BM_KP_CAP * 32) / 256, 256, 0, s>>>(lv, o->pyr, *out);
     BM_COUNT_LAUNCHES(1), k_orb_describe<<<BM_KP_CAP, 256, 0, s>>>(lv, o->pyr, *out);
     return cudaGetLastError();

@@ -11,12 +11,15 @@ struct BmOrbLevel {
     int cand_off;       // offset of the level's segment in the candidate arrays
     int cand_cap;
     int quota;          // features to keep on this level (cv2: nfeaturesPerLevel)
+    int wpr;            // words per row of the level's NMS bitmap
+    int bits_off;       // word offset of the level in nmsbits
+    int row_off;        // offset of the level's rows in rowcnt
     float scale;        // layerScale (float32 pow(1.2f, l))
     float inv_scale;    // 1.f / scale
 };
-struct BmOrbLevels { BmOrbLevel l[BM_ORB_LEVELS]; int total_px; int total_cand; };
+struct BmOrbLevels { BmOrbLevel l[BM_ORB_LEVELS]; int total_px; int total_cand; int total_rows; int total_words; };
 
-// final keypoints, SoA on the device; order: level-major, (y,x) row-major inside a level
+// final keypoints, SoA on the device; order: cv2's (level-major; inside a level whatever KeyPointsFilter::retainBest leaves, cvorder.cuh)
 struct BmKeypoints {
     float2* pt;         // image coordinates (level coords * scale)
     float* size;
@@ -34,11 +37,18 @@ struct BmOrb {
     int w, h, nfeatures;
     BmOrbLevels lv;
     uint8_t *pyr, *blur, *score;
-    uint2 *cand, *cand2;
     unsigned* corners;  // FAST corners before NMS, x | y << 16; level l owns [off_l / 2, off_l / 2 + w_l * h_l / 2)
-    int* ctr;           // device counters: [0..7] cnt1, [8..15] cnt2, [16..23] thr, [24..31] kept, [32] overflow flag, [40..47] FAST corners
-    int* hist;          // [8][256]
-    uint8_t* keep;      // keep flags for cand2
+    // one allocation, cleared by one memset per frame: ctr | rowcnt | nmsbits
+    int* ctr;           // device counters: [0..7] NMS survivors n1, [24..31] kept, [32] overflow flag, [40..47] FAST corners
+    int* rowcnt;        // NMS survivors per (level, row)
+    unsigned* nmsbits;  // NMS survivors, one bit per pixel (row-major FAST output order = cv2's, before retainBest)
+    size_t zero_bytes;
+    uint8_t* ckey;      // [total_cand] FAST scores of the survivors in row-major order (permuted in place by the selection)
+    unsigned* cxy;      // [total_cand] x | y << 16 of the survivors, row-major
+    int *idx, *idx2;    // [total_cand] permutations of the two retainBest stages
+    int* lists;         // [2 * total_cand + 4 * levels] stopper lists of cvo_pair_pass
+    float* resp2;       // [total_cand] Harris responses when they do not fit in shared memory
+    uint2* cand2;       // [total_cand] per level: the final keypoints (xy, response bits) in cv2's order
     cudaStream_t stream;
     BmOrbGraph graphs[12];   // captured detect sequences, one per (input buffer, output buffer)
     int ngraphs, graphs_disabled;

@@ -78,7 +78,7 @@ def _np_ptr(a):
 
 def orb_detect_and_compute(gray: torch.Tensor, nfeatures: int = 700):
     """cv2.ORB_create(nfeatures).detectAndCompute(gray, None) (main.py:36,112,718).  gray (H,W) uint8 cuda.
-    Returns (kp float32 (n,6): x,y,size,angle,response,octave; des uint8 (n,32)), level-major / row-major order."""
+    Returns (kp float32 (n,6): x,y,size,angle,response,octave; des uint8 (n,32)) in cv2's own order."""
     lib = _lib.load()
     h, w = gray.shape
     cap = lib.bm_keypoint_capacity()
@@ -99,6 +99,15 @@ def sift_detect_and_compute(gray: torch.Tensor, nfeatures: int = 700):
     _lib.check(lib.bm_sift_detect_and_compute(_ptr(gray), h, w, nfeatures, _np_ptr(kp), _np_ptr(des), cap, C.byref(n)),
                "bm_sift_detect_and_compute")
     return kp[:n.value].copy(), des[:n.value].copy()
+
+
+def cv_retain_best(resp: np.ndarray, n_points: int, as_u8: bool = False) -> np.ndarray:
+    """KeyPointsFilter::retainBest (inside detectAndCompute, main.py:112,718): surviving input indices in cv2's output order."""
+    lib = _lib.load()
+    r = np.ascontiguousarray(resp, np.float32)
+    out = np.empty(max(len(r), 1), np.int32); m = C.c_int(0)
+    _lib.check(lib.bm_cv_retain_best(_np_ptr(r), len(r), int(n_points), int(as_u8), _np_ptr(out), C.byref(m)), "bm_cv_retain_best")
+    return out[:m.value].astype(np.int64)
 
 
 def match_hamming_crosscheck(des_q: np.ndarray, des_t: np.ndarray):

@@ -37,8 +37,8 @@ def _orb_compare(ops, gray, nfeatures=700):
     assert np.array_equal(a[:, 4], b[:, 4]), np.abs(a[:, 4] - b[:, 4]).max()   # Harris response bit-equal
     assert np.array_equal(a[:, 3], b[:, 3]), np.abs(a[:, 3] - b[:, 3]).max()   # IC angle bit-equal
     assert np.array_equal(ad, bd), np.mean((ad == bd).all(axis=1))
-    # our own order is deterministic: level-major, then (y, x)
-    assert np.array_equal(kp, a.astype(np.float32))
+    # and the order is cv2's own (cvorder.cuh): row for row, no canonical sort needed
+    assert np.array_equal(kp, kc.astype(np.float32)) and np.array_equal(des, dc)
 
 
 def test_orb_pyramid_and_fast_scores_bit_exact(ops, frames):

@@ -1,0 +1,79 @@
+"""cv2's keypoint ORDER on the device (csrc/cvorder.cuh): the parallel introselect / partition emulation against the real
+libstdc++ algorithms, and the ORB detector's output order against live cv2."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _build_ref():
+    from oracle import build_ref
+    build_ref.build()
+
+
+def test_retain_best_equals_real_libstdcxx():
+    from b200mosaic import ops
+    from oracle import cvorder
+    rng = np.random.default_rng(3)
+    cases = [(1, 1, 5), (3, 2, 5), (4, 1, 3), (5, 2, 2), (10, 3, 4), (50, 50, 9), (51, 50, 9), (500, 304, 60), (500, 152, 10 ** 6),
+             (4096, 700, 200), (20000, 304, 235), (20000, 1, 235), (20000, 19999, 235), (3000, 0, 5), (777, 776, 2),
+             (80461, 304, 235), (130000, 254, 235), (326106, 304, 235), (65000, 700, 10 ** 7)]
+    for n, k, hi in cases:
+        r = rng.integers(0, hi, n).astype(np.float32)
+        want = cvorder.stl_retain_best(r, k)
+        assert np.array_equal(ops.cv_retain_best(r, k), want), (n, k, hi, "f32")
+        if hi <= 256:
+            assert np.array_equal(ops.cv_retain_best(r, k, as_u8=True), want), (n, k, hi, "u8")
+    r = np.zeros(5000, np.float32)
+    assert np.array_equal(ops.cv_retain_best(r, 10), cvorder.stl_retain_best(r, 10))
+    r = np.arange(5000, dtype=np.float32)
+    assert np.array_equal(ops.cv_retain_best(r, 100), cvorder.stl_retain_best(r, 100))
+    assert np.array_equal(ops.cv_retain_best(r[::-1].copy(), 100), cvorder.stl_retain_best(r[::-1].copy(), 100))
+    r = rng.standard_normal(30000).astype(np.float32)                     # negative values, no ties
+    assert np.array_equal(ops.cv_retain_best(r, 700), cvorder.stl_retain_best(r, 700))
+
+
+def test_retain_best_heap_select_fallback():
+    from b200mosaic import ops
+    from oracle import cvorder
+    for n, nth in [(2000, 1000), (5000, 303), (1500, 1400)]:
+        r = cvorder.adversarial_input(n, nth)
+        assert np.array_equal(ops.cv_retain_best(r, nth + 1), cvorder.stl_retain_best(r, nth + 1)), (n, nth)
+
+
+def _gpu_orb(gray, nfeatures=700):
+    from b200mosaic import ops
+    kp, des = ops.orb_detect_and_compute(torch.from_numpy(gray).cuda(), nfeatures)
+    return kp.astype(np.float64), des
+
+
+@pytest.mark.parametrize("size", [(427, 240), (640, 360), (1280, 720), (1920, 1080)])
+def test_orb_order_equals_cv2(size):
+    """keypoints AND descriptors row for row in cv2's order -- no canonical sort"""
+    import cv2
+    from b200mosaic.synth import DroneSweep
+    from oracle import orb as oorb
+    w, h = size
+    frames = DroneSweep(w, h, seed=11, ground_size=max(2048, 2 * w), max_step=9.0).frames(2)
+    for f in frames:
+        gray = cv2.cvtColor(f, cv2.COLOR_BGR2GRAY)
+        kp, des = _gpu_orb(gray)
+        kp_cv, des_cv = oorb.cv_detect_and_compute(gray)
+        assert kp.shape == kp_cv.shape
+        assert np.array_equal(kp.astype(np.float32), kp_cv.astype(np.float32))
+        assert np.array_equal(des, des_cv)
+
+
+def test_orb_order_clip_frames_and_budgets(golden_dir):
+    import cv2
+    from oracle import orb as oorb
+    frames = np.load(golden_dir / "clip01_frames.npz")["frames"]
+    for t in range(len(frames)):
+        gray = cv2.cvtColor(frames[t], cv2.COLOR_BGR2GRAY)
+        for nf in (700, 300, 2000):
+            kp, des = _gpu_orb(gray, nf)
+            kp_cv, des_cv = oorb.cv_detect_and_compute(gray, nf)
+            assert np.array_equal(kp.astype(np.float32), kp_cv.astype(np.float32)), (t, nf)
+            assert np.array_equal(des, des_cv), (t, nf)
