@@ -43,8 +43,6 @@ typedef struct {
     int detector;              /* BM_DET_SIFT | BM_DET_ORB                    main.py:32-37       */
     int nfeatures;             /* 700                                         main.py:33,36       */
     int device;                /* CUDA device ordinal                                             */
-    int row_tile_y0;           /* canvas row-tile sharding (config 5): this handle owns canvas    */
-    int row_tile_y1;           /*   rows [y0,y1); 0,0 = whole canvas                              */
 } bm_config;
 
 typedef struct {
@@ -95,6 +93,8 @@ bm_status bm_set_overlap(bm_handle h, int on);
 bm_status bm_estimate_frame(bm_handle h, const uint8_t* h_bgr, size_t stride_bytes, const uint8_t* h_next_or_null, bm_frame_info* info);
 /* canvas row-tile mode (config 5): empty the canvas (the caller then warps frame 0 with its own homography) */
 bm_status bm_clear_canvas(bm_handle h);
+/* `output_img = image` (callers of the reference may assign the attribute): replace the canvas by a host image, Hc x Wc x 3 BGR */
+bm_status bm_set_canvas(bm_handle h, const uint8_t* h_bgr);
 /* canvas as packed BGR into a DEVICE buffer (e.g. a torch tensor that NCCL then gathers) */
 bm_status bm_get_canvas_device(bm_handle h, uint8_t* d_bgr_out);
 /* output_img (uint8, Hc x Wc x 3): lazy D2H of the device canvas                     main.py:1632,1649 */
@@ -115,6 +115,10 @@ bm_status bm_warm_up(bm_handle h);
 bm_status bm_get_state(bm_handle h, double H_old[9], int* history_len, double* history /* <=5*9 */);
 bm_status bm_set_stabilization(bm_handle h, int enabled, int history_size, double translation_threshold,
                                double scale_threshold);                          /* main.py:97-101 */
+/* validate_homography(H) (main.py:761-801): returns BM_VAL_OK or the reason of the rejection; *value = the translation (px) or
+ * scale the reference prints.  Reproduces the quirk that a negative 2x2 determinant gives sqrt -> NaN and therefore PASSES.
+ * Host-only (no device needed); the frame loop, the Python mirror and the pair-sharding chain all use this one implementation. */
+int bm_validate_homography(const double H[9], double translation_threshold, double scale_threshold, double* value);
 /* pinned staging memory a decoder can write into directly (cv2.VideoCapture stays on the host)           */
 bm_status bm_alloc_pinned(size_t bytes, void** out);
 bm_status bm_free_pinned(void* p);

@@ -83,7 +83,7 @@ class RefMosaic:
         H, _mask = cv2.findHomography(pa, pb, cv2.RANSAC, ransacReprojThreshold=RANSAC_THRESH)
         return H
 
-    # ---- main.py:761-801 (prints omitted; same decisions) -----------------------------------
+    # ---- main.py:761-801 (same decisions, same printed warnings) ------------------------------
     def validate_homography(self, H):
         if H is None:
             return False
@@ -93,10 +93,13 @@ class RefMosaic:
         with np.errstate(invalid="ignore"):
             scale = np.sqrt(np.linalg.det(H[:2, :2]))     # NaN when det<0 -> both tests False (quirk A.11)
         if translation > self.translation_threshold:
+            print(f"Предупреждение: Обнаружено большое смещение ({translation:.1f}px), возможна тряска")          # :788
             return False
         if abs(scale - 1.0) > self.scale_threshold:
+            print(f"Предупреждение: Обнаружено большое изменение масштаба ({scale:.2f}), возможна тряска")      # :793
             return False
         if abs(H[2, 0]) > 0.001 or abs(H[2, 1]) > 0.001:
+            print("Предупреждение: Обнаружены сильные перспективные искажения")                                # :798
             return False
         return True
 
@@ -130,13 +133,16 @@ class RefMosaic:
         self.kp_cur, self.des_cur = self.detector.detectAndCompute(gray, None)
         self.matches = self.match(self.des_cur, self.des_prev)
         if len(self.matches) < 4:
+            print(f"Предупреждение: Недостаточно совпадений ({len(self.matches)}), пропуск кадра")          # :723
             self.last_status = "skip_few_matches"          # :722-724, state not advanced
             return
         H_rel = self.findHomography(self.kp_cur, self.kp_prev, self.matches)
         if H_rel is None:
+            print("Предупреждение: Не удалось вычислить гомографию, пропуск кадра")                      # :730
             self.last_status = "skip_no_h"                 # :729-731
             return
         if not self.validate_homography(H_rel):
+            print("Предупреждение: Невалидная гомография (тряска/размытие), использую последнюю валидную")  # :735
             H_rel = np.eye(3)                              # :734-737
             self.last_status = "rejected_identity"
         else:

@@ -16,8 +16,7 @@ BM_VAL_OK, BM_VAL_NAN, BM_VAL_TRANSLATION, BM_VAL_SCALE, BM_VAL_PERSPECTIVE = ra
 
 class BmConfig(C.Structure):
     _fields_ = [("frame_h", C.c_int), ("frame_w", C.c_int), ("canvas_h", C.c_int), ("canvas_w", C.c_int),
-                ("detector", C.c_int), ("nfeatures", C.c_int), ("device", C.c_int),
-                ("row_tile_y0", C.c_int), ("row_tile_y1", C.c_int)]
+                ("detector", C.c_int), ("nfeatures", C.c_int), ("device", C.c_int)]
 
 
 class BmFrameInfo(C.Structure):
@@ -46,8 +45,10 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
-        from . import build as _build
+    # build.build() is digest-stamped: it returns at once when lib/ matches the sources and rebuilds a stale binary otherwise
+    # (the directory is git-ignored but travels with the tree).  Without the sources next to it the library is used as is.
+    from . import build as _build
+    if not LIB_PATH.exists() or (_build.CSRC.exists() and any(_build.CSRC.glob("*.cu")) and os.path.exists(_build.NVCC)):
         _build.build()
     lib = C.CDLL(str(LIB_PATH))
     vp, i, sz, dp = C.c_void_p, C.c_int, C.c_size_t, C.POINTER(C.c_double)
@@ -59,8 +60,10 @@ def load():
     _sig(lib, "bm_first_frame", i, vp, vp, sz)
     _sig(lib, "bm_process_frame", i, vp, vp, sz, C.POINTER(BmFrameInfo))
     _sig(lib, "bm_get_canvas", i, vp, vp)
+    _sig(lib, "bm_set_canvas", i, vp, vp)
     _sig(lib, "bm_get_state", i, vp, dp, ip, dp)
     _sig(lib, "bm_set_stabilization", i, vp, i, i, C.c_double, C.c_double)
+    _sig(lib, "bm_validate_homography", i, dp, C.c_double, C.c_double, dp)
     _sig(lib, "bm_alloc_pinned", i, sz, C.POINTER(vp))
     _sig(lib, "bm_free_pinned", i, vp)
     _sig(lib, "bm_warp_frame", i, vp, vp, sz, dp, C.POINTER(BmFrameInfo))
@@ -112,6 +115,16 @@ def check(status: int, what: str = "") -> int:
         msg = load().bm_last_error().decode("utf-8", "replace")
         raise B200MosaicError(f"{what or 'libb200mosaic'} failed ({status}): {msg}")
     return status
+
+
+def validate_homography(H, translation_threshold=50.0, scale_threshold=0.3):
+    """main.py:761-801 through the one native implementation.  Returns (BM_VAL_* reason, value)."""
+    if H is None:
+        return BM_VAL_NAN, 0.0
+    _a, hp = dbl9(H)
+    v = C.c_double(0.0)
+    r = load().bm_validate_homography(hp, float(translation_threshold), float(scale_threshold), C.byref(v))
+    return r, v.value
 
 
 def dbl9(H):

@@ -99,12 +99,13 @@ struct bm_mosaic_s {
     // optional CUDA-event timing of the warp/blend chain
     int timing = 0;
     static const int kEvRing = 64;
-    cudaEvent_t ev0[kEvRing], ev1[kEvRing];
+    cudaEvent_t ev0[kEvRing] = {}, ev1[kEvRing] = {};
     int ev_pending = 0;
     double t_ms = 0.0, t_bytes = 0.0; int t_frames = 0;
 };
 
 static void cancel_early_begin(bm_mosaic_s* m);
+extern "C" bm_status bm_destroy(bm_handle m);
 static size_t frame_bytes(const bm_config& c) { return (size_t)c.frame_h * c.frame_w * 3; }
 
 extern "C" bm_status bm_create(const bm_config* cfg, bm_handle* out) {
@@ -112,24 +113,37 @@ extern "C" bm_status bm_create(const bm_config* cfg, bm_handle* out) {
         bm_set_error("bm_create: bad config"); return BM_ERR_ARG;
     }
     if (cfg->detector != BM_DET_SIFT && cfg->detector != BM_DET_ORB) { bm_set_error("bm_create: detector must be sift|orb"); return BM_ERR_ARG; }
+    *out = nullptr;
     int ndev = 0;
     BM_CUDA_OK(cudaGetDeviceCount(&ndev));
     if (cfg->device < 0 || cfg->device >= ndev) { bm_set_error("bm_create: no CUDA device %d", cfg->device); return BM_ERR_CUDA; }
     BM_CUDA_OK(cudaSetDevice(cfg->device));
+    // every failure below releases what was created so far (bm_destroy tolerates a half-built handle): OOM at creation is the
+    // expected failure for config-5 sized canvases and many-stream runs
+#define BM_CREATE_OK(expr)                                                                 \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            bm_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            bm_destroy(m);                                                                 \
+            cudaGetLastError();                                                            \
+            return BM_ERR_CUDA;                                                            \
+        }                                                                                  \
+    } while (0)
     bm_mosaic_s* m = new (std::nothrow) bm_mosaic_s();
     if (!m) return BM_ERR_ARG;
     m->cfg = *cfg;
     if (m->cfg.nfeatures <= 0) m->cfg.nfeatures = 700;
-    BM_CUDA_OK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
-    BM_CUDA_OK(cudaStreamCreateWithFlags(&m->s_chain, cudaStreamNonBlocking));
-    BM_CUDA_OK(cudaStreamCreateWithFlags(&m->s_copy, cudaStreamNonBlocking));
+    BM_CREATE_OK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    BM_CREATE_OK(cudaStreamCreateWithFlags(&m->s_chain, cudaStreamNonBlocking));
+    BM_CREATE_OK(cudaStreamCreateWithFlags(&m->s_copy, cudaStreamNonBlocking));
     for (int i = 0; i < BM_SLOTS; ++i) {
-        BM_CUDA_OK(cudaEventCreateWithFlags(&m->ev_up[i], cudaEventDisableTiming));
-        BM_CUDA_OK(cudaEventCreateWithFlags(&m->ev_chain[i], cudaEventDisableTiming));
+        BM_CREATE_OK(cudaEventCreateWithFlags(&m->ev_up[i], cudaEventDisableTiming));
+        BM_CREATE_OK(cudaEventCreateWithFlags(&m->ev_chain[i], cudaEventDisableTiming));
     }
     for (int k = 0; k < 2; ++k) {            // page-locking is slow (tens of ms): at creation, not in the first bm_get_canvas
-        BM_CUDA_OK(cudaHostAlloc(&m->h_cstage[k], BM_CANVAS_STAGE_BYTES, cudaHostAllocDefault));
-        BM_CUDA_OK(cudaEventCreateWithFlags(&m->ev_cstage[k], cudaEventDisableTiming));
+        BM_CREATE_OK(cudaHostAlloc(&m->h_cstage[k], BM_CANVAS_STAGE_BYTES, cudaHostAllocDefault));
+        BM_CREATE_OK(cudaEventCreateWithFlags(&m->ev_cstage[k], cudaEventDisableTiming));
     }
     // scratch: the window of a frame is at most the canvas; typical is frame-sized.  Size for the whole canvas when
     // it is small (<= 64 Mpx), otherwise for 4x the frame area plus margins (config 5: 32768^2 canvas, 4K frames).
@@ -137,28 +151,32 @@ extern "C" bm_status bm_create(const bm_config* cfg, bm_handle* out) {
     size_t scratch = canvas_px;
     if (canvas_px > ((size_t)64 << 20)) scratch = (size_t)4 * (cfg->frame_h + 64) * (cfg->frame_w + 64);
     bm_status st = alloc_blend(m->blend, cfg->canvas_h, cfg->canvas_w, scratch);
-    if (st != BM_OK) { delete m; return st; }
+    if (st != BM_OK) { bm_destroy(m); return st; }
     const size_t fb = frame_bytes(*cfg), fpx = (size_t)cfg->frame_h * cfg->frame_w;
     for (int i = 0; i < BM_SLOTS; ++i) {
-        BM_CUDA_OK(cudaHostAlloc(&m->h_stage[i], fb, cudaHostAllocDefault));
-        BM_CUDA_OK(cudaMalloc(&m->d_bgr[i], fb + 16));
-        BM_CUDA_OK(cudaMalloc(&m->d_bgrx[i], fpx * sizeof(uchar4)));
-        BM_CUDA_OK(cudaMalloc(&m->d_gray[i], fpx + 16));
-        BM_CUDA_OK(cudaEventCreateWithFlags(&m->ev_h2d[i], cudaEventDisableTiming));
+        BM_CREATE_OK(cudaHostAlloc(&m->h_stage[i], fb, cudaHostAllocDefault));
+        BM_CREATE_OK(cudaMalloc(&m->d_bgr[i], fb + 16));
+        BM_CREATE_OK(cudaMalloc(&m->d_bgrx[i], fpx * sizeof(uchar4)));
+        BM_CREATE_OK(cudaMalloc(&m->d_gray[i], fpx + 16));
+        BM_CREATE_OK(cudaEventCreateWithFlags(&m->ev_h2d[i], cudaEventDisableTiming));
     }
-    BM_CUDA_OK(cudaMalloc(&m->d_canvas_bgr, canvas_px * 3 + 16));
+    BM_CREATE_OK(cudaMalloc(&m->d_canvas_bgr, canvas_px * 3 + 16));
     for (int i = 0; i < 9; ++i) m->H_old[i] = (i % 4 == 0) ? 1.0 : 0.0;
-    for (int i = 0; i < bm_mosaic_s::kEvRing; ++i) { BM_CUDA_OK(cudaEventCreate(&m->ev0[i])); BM_CUDA_OK(cudaEventCreate(&m->ev1[i])); }
+    for (int i = 0; i < bm_mosaic_s::kEvRing; ++i) { BM_CREATE_OK(cudaEventCreate(&m->ev0[i])); BM_CREATE_OK(cudaEventCreate(&m->ev1[i])); }
     st = bm_pipeline_create(&m->pipe, m->cfg, m->stream);
-    if (st != BM_OK) { delete m; return st; }
+    if (st != BM_OK) { bm_destroy(m); return st; }
     *out = m;
     return BM_OK;
 }
 
+#undef BM_CREATE_OK
+
 extern "C" bm_status bm_destroy(bm_handle m) {
     if (!m) return BM_OK;
     cudaSetDevice(m->cfg.device);
-    cudaStreamSynchronize(m->stream); cudaStreamSynchronize(m->s_chain); cudaStreamSynchronize(m->s_copy);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    if (m->s_chain) cudaStreamSynchronize(m->s_chain);
+    if (m->s_copy) cudaStreamSynchronize(m->s_copy);
     if (m->pipe) bm_pipeline_sync_est(m->pipe);
     bm_pipeline_destroy(m->pipe);
     free_blend(m->blend);
@@ -169,9 +187,11 @@ extern "C" bm_status bm_destroy(bm_handle m) {
     cudaFree(m->d_canvas_bgr); cudaFree(m->d_final); cudaFree(m->d_bounds);
     bm_preview_free(&m->preview);
     for (int k = 0; k < 2; ++k) { if (m->h_cstage[k]) cudaFreeHost(m->h_cstage[k]); if (m->ev_cstage[k]) cudaEventDestroy(m->ev_cstage[k]); }
-    for (int i = 0; i < bm_mosaic_s::kEvRing; ++i) { cudaEventDestroy(m->ev0[i]); cudaEventDestroy(m->ev1[i]); }
+    for (int i = 0; i < bm_mosaic_s::kEvRing; ++i) { if (m->ev0[i]) cudaEventDestroy(m->ev0[i]); if (m->ev1[i]) cudaEventDestroy(m->ev1[i]); }
     for (int i = 0; i < BM_SLOTS; ++i) { if (m->ev_up[i]) cudaEventDestroy(m->ev_up[i]); if (m->ev_chain[i]) cudaEventDestroy(m->ev_chain[i]); }
-    cudaStreamDestroy(m->stream); cudaStreamDestroy(m->s_chain); cudaStreamDestroy(m->s_copy);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    if (m->s_chain) cudaStreamDestroy(m->s_chain);
+    if (m->s_copy) cudaStreamDestroy(m->s_copy);
     delete m;
     return BM_OK;
 }
@@ -488,14 +508,21 @@ extern "C" bm_status bm_free_pinned(void* p) { BM_CUDA_OK(cudaFreeHost(p)); retu
 // ------------------------------------------------------------------------------------------------------------------
 // host control flow of process_frame: validate (main.py:761-801), smooth (:803-834), compose (:746)
 // ------------------------------------------------------------------------------------------------------------------
-static int validate_h(const bm_mosaic_s* m, const double* H, double* value) {
+// The ONE implementation of validate_homography (main.py:761-801): the frame loop below, the Python mirror's method and the
+// offline pair-sharding chain (sharding.py) all call it.  Pure host code, usable without a device.
+extern "C" int bm_validate_homography(const double H[9], double translation_threshold, double scale_threshold, double* value) {
+    if (value) *value = 0.0;
+    if (!H) return BM_VAL_NAN;
     for (int i = 0; i < 9; ++i) if (isnan(H[i]) || isinf(H[i])) return BM_VAL_NAN;
     const double tr = sqrt(H[2] * H[2] + H[5] * H[5]);
     const double sc = sqrt(H[0] * H[4] - H[1] * H[3]);          // NaN for det < 0: both comparisons false (quirk A.11)
-    if (tr > m->translation_threshold) { if (value) *value = tr; return BM_VAL_TRANSLATION; }
-    if (fabs(sc - 1.0) > m->scale_threshold) { if (value) *value = sc; return BM_VAL_SCALE; }
+    if (tr > translation_threshold) { if (value) *value = tr; return BM_VAL_TRANSLATION; }
+    if (fabs(sc - 1.0) > scale_threshold) { if (value) *value = sc; return BM_VAL_SCALE; }
     if (fabs(H[6]) > 0.001 || fabs(H[7]) > 0.001) return BM_VAL_PERSPECTIVE;
     return BM_VAL_OK;
+}
+static int validate_h(const bm_mosaic_s* m, const double* H, double* value) {
+    return bm_validate_homography(H, m->translation_threshold, m->scale_threshold, value);
 }
 
 static void smooth_h(bm_mosaic_s* m, const double* H, double* out) {
@@ -567,9 +594,23 @@ static bm_status finish_frame(bm_mosaic_s* m, int slot, bm_frame_info* info_out)
     bm_status ret = BM_OK;
     if (info.validate_reason != BM_VAL_OK) { for (int i = 0; i < 9; ++i) Hv[i] = (i % 4 == 0) ? 1.0 : 0.0; ret = BM_REJECTED_IDENTITY; }
     double Hs[9], Habs[9];
+    double hist_save[5][9]; const int hist_len_save = m->history_len;
+    memcpy(hist_save, m->history, sizeof(hist_save));
     smooth_h(m, Hv, Hs);
     matmul3(m->H_old, Hs, Habs);
     memcpy(info.H, Habs, 72);
+    {   // nothing is committed before the warp is known to be executable: a window larger than the scratch planes (canvases over
+        // 64 Mpx) must leave H_old, the smoothing history and the "previous" features as they were, like a skipped frame
+        BmFramePlan plan;
+        bm_make_plan(Habs, m->cfg.frame_w, m->cfg.frame_h, m->cfg.canvas_w, m->cfg.canvas_h, &plan);
+        const size_t need = (size_t)bm_win_w(plan.reg) * bm_win_h(plan.reg);
+        if (plan.valid && need > m->blend.scratch_px) {
+            memcpy(m->history, hist_save, sizeof(hist_save)); m->history_len = hist_len_save;
+            bm_set_error("warp window %zu px exceeds scratch %zu px", need, m->blend.scratch_px);
+            BM_TRY(early_begin(m));
+            return BM_ERR_UNSUPPORTED;
+        }
+    }
     bm_pipeline_advance(m->pipe);                                     // kp_prev/des_prev <- cur (main.py:756-759)
     // the host decision is final: the staged next frame (if any) goes to the detect stream BEFORE this frame's chain is enqueued,
     // so the device never waits for the ~10 launch calls of the chain
@@ -672,6 +713,19 @@ extern "C" bm_status bm_clear_canvas(bm_handle m) {
     if (!m) return BM_ERR_ARG;
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
     BM_CUDA_OK(cudaMemsetAsync(m->blend.canvas, 0, (size_t)m->cfg.canvas_h * m->cfg.canvas_w * sizeof(uchar4), m->s_chain));
+    BM_CUDA_OK(bm_launch_full_rowscan(m->blend, m->s_chain));
+    BM_CUDA_OK(cudaStreamSynchronize(m->s_chain));
+    return BM_OK;
+}
+
+// `video_mosaic.output_img = img` of a reference caller: replace the device canvas by a host image (packed BGR, Hc x Wc x 3)
+extern "C" bm_status bm_set_canvas(bm_handle m, const uint8_t* h_bgr) {
+    if (!m || !h_bgr) return BM_ERR_ARG;
+    BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+    const size_t n = (size_t)m->cfg.canvas_h * m->cfg.canvas_w;
+    BM_CUDA_OK(cudaStreamSynchronize(m->s_chain));
+    BM_CUDA_OK(cudaMemcpy(m->d_canvas_bgr, h_bgr, n * 3, cudaMemcpyHostToDevice));
+    BM_CUDA_OK(bm_launch_pack_canvas(m->d_canvas_bgr, m->blend.canvas, (int)n, m->s_chain));
     BM_CUDA_OK(bm_launch_full_rowscan(m->blend, m->s_chain));
     BM_CUDA_OK(cudaStreamSynchronize(m->s_chain));
     return BM_OK;

@@ -382,6 +382,7 @@ __global__ void __launch_bounds__(1024) k_orb_emit(BmOrbLevels lv, const uint2* 
         int tot = base + m2;
         if (tot > BM_KP_CAP) { tot = BM_KP_CAP; ctr[32] = 1; }
         *out.count = tot;
+        out.flags[0] = ctr[32];                             // every overflow upstream of here was flagged in ctr[32]
     }
 }
 
@@ -539,12 +540,14 @@ int bm_kp_alloc(BmKeypoints* k, int desc_bytes) {
     if (cudaMalloc(&k->lxy, BM_KP_CAP * sizeof(int2)) != cudaSuccess) return -1;
     if (cudaMalloc(&k->desc, (size_t)BM_KP_CAP * desc_bytes) != cudaSuccess) return -1;
     if (cudaMalloc(&k->count, sizeof(int)) != cudaSuccess) return -1;
+    if (cudaMalloc(&k->flags, 4 * sizeof(int)) != cudaSuccess) return -1;
     cudaMemset(k->count, 0, sizeof(int));
+    cudaMemset(k->flags, 0, 4 * sizeof(int));
     return 0;
 }
 void bm_kp_free(BmKeypoints* k) {
     cudaFree(k->pt); cudaFree(k->size); cudaFree(k->angle); cudaFree(k->response); cudaFree(k->octave); cudaFree(k->lxy);
-    cudaFree(k->desc); cudaFree(k->count);
+    cudaFree(k->desc); cudaFree(k->count); cudaFree(k->flags);
     memset(k, 0, sizeof(*k));
 }
 

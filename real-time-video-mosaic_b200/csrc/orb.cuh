@@ -29,6 +29,7 @@ struct BmKeypoints {
     int2* lxy;          // level coordinates (ORB) / unused (SIFT)
     uint8_t* desc;      // ORB: 32 B per keypoint; SIFT: 128 floats per keypoint (512 B)
     int* count;         // device scalar
+    int* flags;         // device, [0] != 0: a candidate / keypoint list overflowed while these features were made (result unusable)
 };
 
 struct BmOrbGraph { const uint8_t* gray; const void* out_pt; cudaGraphExec_t exec; int launches; };

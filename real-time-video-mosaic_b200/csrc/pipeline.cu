@@ -10,7 +10,7 @@
 
 struct BmHostReadback {      // pinned
     BmRansacResult r;
-    int n_cur, n_prev, n_matches, overflow;
+    int n_cur, n_prev, n_matches, overflow_cur, overflow_prev;
 };
 
 struct BmPipeline {
@@ -138,6 +138,8 @@ bm_status bm_pipeline_estimate_begin(BmPipeline* p, const uint8_t* d_gray) {
     BM_CUDA_OK(cudaMemcpyAsync(&rb->n_cur, cur.count, sizeof(int), cudaMemcpyDeviceToHost, s));
     BM_CUDA_OK(cudaMemcpyAsync(&rb->n_prev, prev.count, sizeof(int), cudaMemcpyDeviceToHost, s));
     BM_CUDA_OK(cudaMemcpyAsync(&rb->n_matches, mm.count, sizeof(int), cudaMemcpyDeviceToHost, s));
+    BM_CUDA_OK(cudaMemcpyAsync(&rb->overflow_cur, cur.flags, sizeof(int), cudaMemcpyDeviceToHost, s));
+    BM_CUDA_OK(cudaMemcpyAsync(&rb->overflow_prev, prev.flags, sizeof(int), cudaMemcpyDeviceToHost, s));
     BM_CUDA_OK(cudaEventRecord(p->ev_done, s));
     BM_CUDA_OK(cudaEventRecord(p->ev_est, s));
     return BM_OK;
@@ -161,6 +163,11 @@ bm_status bm_pipeline_estimate_end(BmPipeline* p, bm_frame_info* info, double H_
     BM_CUDA_OK(cudaEventSynchronize(p->ev_done));           // not the stream: a detect-ahead of the next frame may be queued behind
     p->mdone = p->mcur;
     BmHostReadback* rb = p->h_rb;
+    if (rb->overflow_cur || rb->overflow_prev) {
+        // a detector list ran out of capacity: which candidates were kept depends on atomic order, the features are not cv2's
+        bm_set_error("%s detector: candidate / keypoint list capacity exceeded on the %s frame", p->is_orb ? "ORB" : "SIFT", rb->overflow_cur ? "current" : "previous");
+        return BM_ERR_UNSUPPORTED;
+    }
     info->n_kp_cur = rb->n_cur; info->n_kp_prev = rb->n_prev; info->n_matches = rb->n_matches;
     info->ransac_iters = rb->r.iters; info->n_inliers = rb->r.n_inliers;
     *have_h = rb->r.ok == 1;

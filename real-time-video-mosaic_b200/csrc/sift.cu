@@ -24,12 +24,13 @@
 #define SIFT_MAX_OCT 12
 #define SIFT_LAYERS 3
 #define SIFT_BORDER 5
-#define SIFT_CAND_CAP (1 << 17)
-#define SIFT_KP_CAP (1 << 17)
-#define SIFT_RAW_CAP (1 << 21)
+// List capacities scale with the frame (SiftLayout::raw_cap / cand_cap / kp_cap, set in bm_sift_create): a scale-space extremum is a
+// strict 3x3x3 optimum, so a layer holds at most one per 2x2 block -- raw extrema <= 3 layers * (16 N / 3) / 4 = 4 N for an N-pixel
+// frame: raw_cap = 4 N cannot overflow; cand_cap = kp_cap = max(2^17, N / 2) is ~10x what richly textured frames produce (1080p
+// synthetic sweep: 55 k candidates) and an overflow is reported through BmKeypoints::flags -> BM_ERR_UNSUPPORTED, never silently.
 
 struct SiftOct { int w, h; long long g[6]; long long d[5]; long long claim; };   // float offsets; claim: bit offset / 32
-struct SiftLayout { int noct; SiftOct o[SIFT_MAX_OCT]; };
+struct SiftLayout { int noct; int raw_cap, cand_cap, kp_cap; SiftOct o[SIFT_MAX_OCT]; };
 
 struct SiftCand {            // refined extremum (adjustLocalExtrema output)
     int o, layer, r, c;
@@ -49,7 +50,7 @@ struct BmSift {
     SiftCand* cand; int* ctr;            // ctr[0] = #cand, ctr[1] = #kp (pre-select), ctr[2] = overflow, ctr[3] = #selected, ctr[4] = #raw
     unsigned* raw;           // raw extrema before refinement: o<<28 | (layer-1)<<26 | r<<13 | c
     float* cresp; int* csel; // candidate responses, candidates that can survive retainBest (ctr[5] = threshold bits, ctr[7] = count, ctr[6] = #kp after pass A)
-    float2* kpt; float* ksize; float* kangle; float* kresp; int* koct;     // pre-select keypoint list (SIFT_KP_CAP)
+    float2* kpt; float* ksize; float* kangle; float* kresp; int* koct;     // pre-select keypoint list (lay.kp_cap)
     int* sel;                // indices of the selected keypoints
     unsigned* hist;          // radix-select scratch
     float* kernels_dev;      // 6 kernels x 32 taps
@@ -303,7 +304,7 @@ __global__ void __launch_bounds__(256) k_sift_extrema(SiftLayout lay, int o, con
             base = __shfl_sync(0xffffffffu, base, leader);
             if (found) {
                 const int idx = base + __popc(bal & ((1u << lane) - 1u));
-                if (idx < SIFT_RAW_CAP) raw[idx] = ((unsigned)o << 28) | ((unsigned)(l0 - 1) << 26) | ((unsigned)r << 13) | (unsigned)c;
+                if (idx < lay.raw_cap) raw[idx] = ((unsigned)o << 28) | ((unsigned)(l0 - 1) << 26) | ((unsigned)r << 13) | (unsigned)c;
                 else ctr[2] = 1;
             }
         }
@@ -417,7 +418,7 @@ __global__ void __launch_bounds__(256) k_sift_extrema_tile(SiftLayout lay, int o
                 if (k < EX_FOUND_CAP) s_found[k] = word;
                 else {                                              // more than the CTA buffer holds: straight to the global list
                     const int idx = atomicAdd(&ctr[4], 1);
-                    if (idx < SIFT_RAW_CAP) raw[idx] = word; else ctr[2] = 1;
+                    if (idx < lay.raw_cap) raw[idx] = word; else ctr[2] = 1;
                 }
             }
         }
@@ -428,7 +429,7 @@ __global__ void __launch_bounds__(256) k_sift_extrema_tile(SiftLayout lay, int o
             __syncthreads();
             if (tid < nf) {
                 const int idx = s_base + tid;
-                if (idx < SIFT_RAW_CAP) raw[idx] = s_found[tid]; else ctr[2] = 1;
+                if (idx < lay.raw_cap) raw[idx] = s_found[tid]; else ctr[2] = 1;
             }
         }
         if (it + 1 < kt) {
@@ -442,9 +443,9 @@ __global__ void __launch_bounds__(256) k_sift_extrema_tile(SiftLayout lay, int o
 __global__ void __launch_bounds__(128) k_sift_refine(SiftLayout lay, const float* __restrict__ pyr, const unsigned* __restrict__ raw,
                                                      unsigned* __restrict__ claim, SiftCand* __restrict__ cand, float* __restrict__ cresp,
                                                      int* __restrict__ ctr) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int n = ctr[4]; if (n > SIFT_RAW_CAP) n = SIFT_RAW_CAP;
-    if (blockIdx.x * blockDim.x >= n) return;
+    int n = ctr[4]; if (n > lay.raw_cap) n = lay.raw_cap;
+  for (int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {                   // fixed grid, CTA-uniform trip count
+    const int i = i0 + threadIdx.x;
     bool found = false;
     SiftCand cd;
     if (i < n) {
@@ -468,9 +469,10 @@ __global__ void __launch_bounds__(128) k_sift_refine(SiftLayout lay, const float
         base = __shfl_sync(0xffffffffu, base, leader);
         if (found) {
             const int idx = base + __popc(bal & ((1u << lane) - 1u));
-            if (idx < SIFT_CAND_CAP) { cand[idx] = cd; cresp[idx] = cd.response; } else ctr[2] = 1;
+            if (idx < lay.cand_cap) { cand[idx] = cd; cresp[idx] = cd.response; } else ctr[2] = 1;
         }
     }
+  }
 }
 
 // hal::fastAtan2 (vector path: FMA Horner), degrees
@@ -502,7 +504,7 @@ __global__ void __launch_bounds__(32 * SIFT_ORI_WARPS) k_sift_orient(SiftLayout 
     __shared__ unsigned long long sh_priv[SIFT_ORI_WARPS][36][32];
     __shared__ float sh_f[SIFT_ORI_WARPS][40];
     const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int ncand = ctr[0]; if (ncand > SIFT_CAND_CAP) ncand = SIFT_CAND_CAP;
+    int ncand = ctr[0]; if (ncand > lay.cand_cap) ncand = lay.cand_cap;
     if (rest && (ctr[6] >= nfeatures || ctr[7] >= ncand)) return;      // pass A was enough / had everything
   for (int ci = blockIdx.x * SIFT_ORI_WARPS + wi; ci < (rest ? ncand : ctr[7]); ci += gridDim.x * SIFT_ORI_WARPS) {
     if (rest && __float_as_uint(cand[ci].response) >= (unsigned)ctr[5]) continue;     // done in pass A
@@ -580,7 +582,7 @@ __global__ void __launch_bounds__(32 * SIFT_ORI_WARPS) k_sift_orient(SiftLayout 
             base = __shfl_sync(0xffffffffu, base, leader);
             if (peak) {
                 const int idx = base + __popc(bal & ((1u << lane) - 1u));
-                if (idx < SIFT_KP_CAP) {
+                if (idx < lay.kp_cap) {
                     kpt[idx] = make_float2(cd.ptx, cd.pty); ksize[idx] = cd.size; kangle[idx] = angle; kresp[idx] = cd.response; koct[idx] = cd.octave_packed;
                 } else ctr[2] = 1;
             }
@@ -753,7 +755,7 @@ __global__ void __launch_bounds__(256) k_sift_emit(const int* __restrict__ ctr, 
             out.lxy[rank] = make_int2(0, 0);
         }
     }
-    if (threadIdx.x == 0 && blockIdx.x == 0) *out.count = m;
+    if (threadIdx.x == 0 && blockIdx.x == 0) { *out.count = m; out.flags[0] = ctr[2]; }   // ctr[2]: a list overflowed somewhere upstream
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -876,6 +878,11 @@ int bm_sift_create(BmSift** out, int h, int w, int nfeatures, cudaStream_t s) {
     if (noct < 1) noct = 1;
     if (noct > SIFT_MAX_OCT) noct = SIFT_MAX_OCT;
     o->lay.noct = noct;
+    {
+        const long long N = (long long)w * h;
+        o->lay.raw_cap = (int)(4 * N < (1LL << 21) ? (1LL << 21) : 4 * N);
+        o->lay.cand_cap = o->lay.kp_cap = (int)(N / 2 < (1LL << 17) ? (1LL << 17) : N / 2);
+    }
     long long off = 0, cbits = 0;
     int ow = bw, oh = bh;
     for (int i = 0; i < noct; ++i) {
@@ -904,12 +911,12 @@ int bm_sift_create(BmSift** out, int h, int w, int nfeatures, cudaStream_t s) {
         }
     }
     bool ok = cudaMalloc(&o->pyr, (size_t)off * sizeof(float)) == cudaSuccess && cudaMalloc(&o->up, (size_t)bw * bh * sizeof(float)) == cudaSuccess &&
-              cudaMalloc(&o->claim, o->claim_words * 4) == cudaSuccess && cudaMalloc(&o->cand, SIFT_CAND_CAP * sizeof(SiftCand)) == cudaSuccess &&
-              cudaMalloc(&o->ctr, 16 * sizeof(int)) == cudaSuccess && cudaMalloc(&o->kpt, SIFT_KP_CAP * sizeof(float2)) == cudaSuccess &&
-              cudaMalloc(&o->ksize, SIFT_KP_CAP * 4) == cudaSuccess && cudaMalloc(&o->kangle, SIFT_KP_CAP * 4) == cudaSuccess &&
-              cudaMalloc(&o->kresp, SIFT_KP_CAP * 4) == cudaSuccess && cudaMalloc(&o->koct, SIFT_KP_CAP * 4) == cudaSuccess &&
-              cudaMalloc(&o->sel, BM_KP_CAP * 4) == cudaSuccess && cudaMalloc(&o->raw, (size_t)SIFT_RAW_CAP * 4) == cudaSuccess &&
-              cudaMalloc(&o->cresp, SIFT_CAND_CAP * 4) == cudaSuccess && cudaMalloc(&o->csel, BM_KP_CAP * 4) == cudaSuccess;
+              cudaMalloc(&o->claim, o->claim_words * 4) == cudaSuccess && cudaMalloc(&o->cand, (size_t)o->lay.cand_cap * sizeof(SiftCand)) == cudaSuccess &&
+              cudaMalloc(&o->ctr, 16 * sizeof(int)) == cudaSuccess && cudaMalloc(&o->kpt, (size_t)o->lay.kp_cap * sizeof(float2)) == cudaSuccess &&
+              cudaMalloc(&o->ksize, (size_t)o->lay.kp_cap * 4) == cudaSuccess && cudaMalloc(&o->kangle, (size_t)o->lay.kp_cap * 4) == cudaSuccess &&
+              cudaMalloc(&o->kresp, (size_t)o->lay.kp_cap * 4) == cudaSuccess && cudaMalloc(&o->koct, (size_t)o->lay.kp_cap * 4) == cudaSuccess &&
+              cudaMalloc(&o->sel, BM_KP_CAP * 4) == cudaSuccess && cudaMalloc(&o->raw, (size_t)o->lay.raw_cap * 4) == cudaSuccess &&
+              cudaMalloc(&o->cresp, (size_t)o->lay.cand_cap * 4) == cudaSuccess && cudaMalloc(&o->csel, BM_KP_CAP * 4) == cudaSuccess;
     if (ok) ok = cudaMemcpyToSymbol(c_sift_k, hk, sizeof(hk)) == cudaSuccess;
     if (ok) ok = cudaStreamCreateWithFlags(&o->s2, cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&o->s3, cudaStreamNonBlocking) == cudaSuccess &&
                  cudaEventCreateWithFlags(&o->ev_fork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&o->ev_join2, cudaEventDisableTiming) == cudaSuccess &&
@@ -1007,12 +1014,12 @@ static cudaError_t sift_enqueue(BmSift* o, const uint8_t* d_gray, BmKeypoints* o
         SIFT_OK(cudaEventRecord(o->ev_join2, s2)); SIFT_OK(cudaEventRecord(o->ev_join3, s3));
         SIFT_OK(cudaStreamWaitEvent(s, o->ev_join2, 0)); SIFT_OK(cudaStreamWaitEvent(s, o->ev_join3, 0));
     }
-    BM_COUNT_LAUNCHES(1), k_sift_refine<<<SIFT_RAW_CAP / 128, 128, 0, s>>>(L, o->pyr, o->raw, o->claim, o->cand, o->cresp, o->ctr);
-    BM_COUNT_LAUNCHES(1), k_sift_select<<<1, 1024, 0, s>>>(o->nfeatures, o->ctr + 0, SIFT_CAND_CAP, o->ctr, o->cresp, o->csel, o->ctr + 7, (unsigned*)(o->ctr + 5));
+    BM_COUNT_LAUNCHES(1), k_sift_refine<<<148 * 8, 128, 0, s>>>(L, o->pyr, o->raw, o->claim, o->cand, o->cresp, o->ctr);
+    BM_COUNT_LAUNCHES(1), k_sift_select<<<1, 1024, 0, s>>>(o->nfeatures, o->ctr + 0, L.cand_cap, o->ctr, o->cresp, o->csel, o->ctr + 7, (unsigned*)(o->ctr + 5));
     BM_COUNT_LAUNCHES(1), k_sift_orient<<<512, 32 * SIFT_ORI_WARPS, 0, s>>>(L, o->pyr, o->cand, o->csel, 0, o->nfeatures, o->ctr, o->kpt, o->ksize, o->kangle, o->kresp, o->koct);
     SIFT_OK(cudaMemcpyAsync(o->ctr + 6, o->ctr + 1, sizeof(int), cudaMemcpyDeviceToDevice, s));
     BM_COUNT_LAUNCHES(1), k_sift_orient<<<1024, 32 * SIFT_ORI_WARPS, 0, s>>>(L, o->pyr, o->cand, o->csel, 1, o->nfeatures, o->ctr, o->kpt, o->ksize, o->kangle, o->kresp, o->koct);
-    BM_COUNT_LAUNCHES(1), k_sift_select<<<1, 1024, 0, s>>>(o->nfeatures, o->ctr + 1, SIFT_KP_CAP, o->ctr, o->kresp, o->sel, o->ctr + 3, nullptr);
+    BM_COUNT_LAUNCHES(1), k_sift_select<<<1, 1024, 0, s>>>(o->nfeatures, o->ctr + 1, L.kp_cap, o->ctr, o->kresp, o->sel, o->ctr + 3, nullptr);
     BM_COUNT_LAUNCHES(1), k_sift_emit<<<BM_KP_CAP / 256, 256, 0, s>>>(o->ctr, o->sel, o->kpt, o->ksize, o->kangle, o->kresp, o->koct, *out);
     BM_COUNT_LAUNCHES(1), k_sift_describe<<<1024, 256, 0, s>>>(L, o->pyr, *out);
 #undef SIFT_OK

@@ -58,7 +58,7 @@ class VideMosaic:
         self._lib = _lib.load()
         cfg = _lib.BmConfig(frame_h=fh, frame_w=fw, canvas_h=ch, canvas_w=cw,
                             detector=_lib.BM_DET_SIFT if detector_type == "sift" else _lib.BM_DET_ORB,
-                            nfeatures=nfeatures, device=device, row_tile_y0=0, row_tile_y1=0)
+                            nfeatures=nfeatures, device=device)
         self._h = C.c_void_p()
         _lib.check(self._lib.bm_create(C.byref(cfg), C.byref(self._h)), "bm_create")
         self._shape = (ch, cw, fc)
@@ -101,11 +101,24 @@ class VideMosaic:
     # ---- output_img: lazy device->host copy, cached until the next frame -----------------------
     @property
     def output_img(self):
+        """The canvas as a uint8 (Hc, Wc, 3) array (the reference holds float64 that only ever contains integers; every caller
+        casts or copies).  The array is a host COPY of the device canvas, cached until the next frame: writes into it
+        do not reach the device -- assign a whole image (`vm.output_img = img`) to replace the canvas."""
         if self._canvas_cache is None:
             out = np.empty(self._shape, dtype=np.uint8)
             _lib.check(self._lib.bm_get_canvas(self._h, out.ctypes.data_as(C.c_void_p)), "bm_get_canvas")
             self._canvas_cache = out
         return self._canvas_cache
+
+    @output_img.setter
+    def output_img(self, img):
+        """`vm.output_img = array` as reference callers may do: replaces the device canvas (values are truncated to uint8 like
+        every consumer of the reference's float64 canvas does)."""
+        a = np.ascontiguousarray(np.asarray(img).astype(np.uint8))
+        if tuple(a.shape) != tuple(self._shape):
+            raise ValueError(f"output_img must have shape {tuple(self._shape)}")
+        _lib.check(self._lib.bm_set_canvas(self._h, a.ctypes.data_as(C.c_void_p)), "bm_set_canvas")
+        self._canvas_cache = None
 
     def read_canvas(self, out):
         """canvas into a caller-owned uint8 (Hc, Wc, 3) C-contiguous array (e.g. a pinned buffer that is reused for every fetch:
@@ -150,9 +163,10 @@ class VideMosaic:
         else:
             self.last_valid_H = H_rel.copy()
             H_used = H_rel
-        self.homography_history.append(H_used.copy())
-        if len(self.homography_history) > self.history_size:
-            self.homography_history.pop(0)
+        if self.stabilization_enabled:                             # smooth_homography returns before appending otherwise (:812-816)
+            self.homography_history.append(H_used.copy())
+            if len(self.homography_history) > self.history_size:
+                self.homography_history.pop(0)
         self.H = np.array(info.H, dtype=np.float64).reshape(3, 3)
         self.H_old = self.H
         self.frame_prev = frame_cur
@@ -286,6 +300,15 @@ class VideMosaic:
         return self._fetch_kp(0)[1]
 
     @property
+    def kp_cur(self):
+        """keypoints of the last processed frame (main.py:718).  After an accepted frame they are also `kp_prev` (main.py:757)."""
+        return self._fetch_kp(1)[0]
+
+    @property
+    def des_cur(self):
+        return self._fetch_kp(1)[1]
+
+    @property
     def matches(self):
         cap = self._lib.bm_keypoint_capacity()
         q = np.empty(cap, np.int32); t = np.empty(cap, np.int32); d = np.empty(cap, np.float32); m = C.c_int(0)
@@ -331,21 +354,9 @@ class VideMosaic:
     def validate_homography(self, H):
         if H is None:
             return False
-        if np.any(np.isnan(H)) or np.any(np.isinf(H)):
-            return False
-        translation = np.sqrt(H[0, 2] ** 2 + H[1, 2] ** 2)
-        with np.errstate(invalid="ignore"):
-            scale = np.sqrt(np.linalg.det(H[:2, :2]))
-        if translation > self.translation_threshold:
-            self._print_validate(_lib.BM_VAL_TRANSLATION, translation)
-            return False
-        if abs(scale - 1.0) > self.scale_threshold:
-            self._print_validate(_lib.BM_VAL_SCALE, scale)
-            return False
-        if abs(H[2, 0]) > 0.001 or abs(H[2, 1]) > 0.001:
-            self._print_validate(_lib.BM_VAL_PERSPECTIVE, 0.0)
-            return False
-        return True
+        reason, value = _lib.validate_homography(H, self.translation_threshold, self.scale_threshold)
+        self._print_validate(reason, value)
+        return reason == _lib.BM_VAL_OK
 
     # ---- main.py:803-834 ---------------------------------------------------------------------------------------
     def smooth_homography(self, H):

@@ -51,18 +51,9 @@ def tile_rows(canvas_h: int, rank: int, world: int):
 # the reference's host control flow on a list of per-pair results (main.py:734-746), used after the all_gather
 # ---------------------------------------------------------------------------------------------------------------
 def validate_homography(H, translation_threshold=50.0, scale_threshold=0.3):
-    """main.py:761-801 without the prints."""
-    if H is None or np.any(np.isnan(H)) or np.any(np.isinf(H)):
-        return False
-    if np.sqrt(H[0, 2] ** 2 + H[1, 2] ** 2) > translation_threshold:
-        return False
-    with np.errstate(invalid="ignore"):
-        scale = np.sqrt(np.linalg.det(H[:2, :2]))
-    if abs(scale - 1.0) > scale_threshold:
-        return False
-    if abs(H[2, 0]) > 0.001 or abs(H[2, 1]) > 0.001:
-        return False
-    return True
+    """main.py:761-801 without the prints: the library's one implementation (host-only entry point, no device needed)."""
+    from . import _lib
+    return _lib.validate_homography(H, translation_threshold, scale_threshold)[0] == _lib.BM_VAL_OK
 
 
 def compose_chain(H0, rel, history_size=5):

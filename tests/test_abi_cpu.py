@@ -56,3 +56,38 @@ def test_product_does_not_import_oracle():
         if p.is_file() and p.suffix in (".py", ".cu", ".cuh", ".h"):
             t = p.read_text(errors="ignore")
             assert "import oracle" not in t and "from oracle" not in t, p
+
+
+def test_validate_homography_single_native_implementation():
+    """bm_validate_homography (host-only) == the reference's method on accept / every reject branch / the NaN quirk
+    (main.py:761-801); the Python mirror and sharding.py route through it."""
+    import contextlib
+    import io
+    import b200mosaic
+    from b200mosaic import _lib, sharding
+    from oracle.mosaic_ref import RefMosaic
+    frame = np.zeros((64, 96, 3), np.uint8); frame[8:40, 8:60] = 200
+    ref = RefMosaic(frame, detector_type="orb")
+    rng = np.random.default_rng(1)
+    cases = [np.eye(3)]
+    for _ in range(200):
+        H = np.eye(3)
+        H[:2, :2] += rng.normal(size=(2, 2)) * rng.choice([0.01, 0.2, 0.6])
+        H[:2, 2] = rng.normal(size=2) * rng.choice([5.0, 40.0, 80.0])
+        H[2, :2] = rng.normal(size=2) * rng.choice([1e-5, 8e-4, 3e-3])
+        cases.append(H)
+    neg = np.eye(3); neg[0, 0] = -1.0                      # det(H[:2,:2]) < 0 -> sqrt = NaN -> comparisons False -> PASSES
+    nan = np.eye(3); nan[1, 1] = np.nan
+    inf = np.eye(3); inf[0, 2] = np.inf
+    cases += [neg, nan, inf]
+    reasons = set()
+    for H in cases:
+        with contextlib.redirect_stdout(io.StringIO()), np.errstate(invalid="ignore"):
+            want = bool(ref.validate_homography(H))
+        r, _v = _lib.validate_homography(H)
+        reasons.add(r)
+        assert (r == _lib.BM_VAL_OK) == want, (H, r)
+        assert sharding.validate_homography(H) == want
+    assert reasons == {_lib.BM_VAL_OK, _lib.BM_VAL_NAN, _lib.BM_VAL_TRANSLATION, _lib.BM_VAL_SCALE, _lib.BM_VAL_PERSPECTIVE}
+    assert _lib.validate_homography(neg)[0] == _lib.BM_VAL_OK
+    assert _lib.validate_homography(None)[0] == _lib.BM_VAL_NAN

@@ -180,3 +180,75 @@ def test_read_canvas_into_caller_buffers(sweep_frames):
     assert np.array_equal(vm.read_canvas(np.zeros_like(want)), want)
     with pytest.raises(ValueError):
         vm.read_canvas(np.zeros((4, 4, 3), np.uint8))
+
+
+# ---- validate_homography rejections driven through bm_process_frame (main.py:734-737, 786-799) -----------------------------------
+def _reject_case(kind):
+    """(frame0, frame1): frame1 relates to frame0 by a homography the reference rejects for `kind`"""
+    import cv2
+    from b200mosaic.synth import make_ground
+    g = make_ground(1536, seed=21)
+    w, h = 640, 360
+    x0, y0 = 400, 500
+    f0 = g[y0:y0 + h, x0:x0 + w].copy()
+    if kind == "translation":                              # 80 px > translation_threshold 50
+        f1 = g[y0 - 80:y0 - 80 + h, x0:x0 + w].copy()
+    elif kind == "scale":                                  # 1.5x zoom about the origin: no translation, sqrt(det) = 0.667 -> 0.33 > 0.3
+        f1 = cv2.resize(f0[0:240, 0:427], (w, h), interpolation=cv2.INTER_LINEAR)
+    elif kind == "perspective":                            # projective term about the origin: no translation, det = 1, |h31| = 1.5e-3 > 1e-3
+        M = np.array([[1, 0, 0], [0, 1, 0], [1.5e-3, 0, 1.0]])
+        f1 = cv2.warpPerspective(f0, M, (w, h), flags=cv2.INTER_LINEAR, borderValue=(1, 1, 1))
+    else:
+        f1 = g[y0 - 9:y0 - 9 + h, x0 + 2:x0 + 2 + w].copy()
+    return f0, f1
+
+
+@pytest.mark.parametrize("kind,reason", [("accept", 0), ("translation", 2), ("scale", 3), ("perspective", 4)])
+def test_validate_rejections_through_the_abi(kind, reason, capsys):
+    """the reject -> identity branch with its printed warnings, status BM_REJECTED_IDENTITY, state advance and history, against
+    the oracle's RefMosaic on the same two frames"""
+    import contextlib
+    import io
+    import b200mosaic
+    from b200mosaic import _lib
+    from oracle.mosaic_ref import RefMosaic
+    f0, f1 = _reject_case(kind)
+    ref = RefMosaic(f0, detector_type="orb")
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        ref.process_frame(f1)
+    want_reject = "Невалидная гомография" in buf.getvalue()
+    assert want_reject == (reason != 0), buf.getvalue()
+    vm = b200mosaic.VideMosaic(f0, detector_type="orb", show_intermediate=False, visualize=False)
+    capsys.readouterr()
+    vm.process_frame(f1, 1)
+    out = capsys.readouterr().out
+    info = vm.last_info
+    assert info.status == (_lib.BM_REJECTED_IDENTITY if reason else _lib.BM_OK)
+    assert info.validate_reason == reason
+    assert out.strip().splitlines() == buf.getvalue().strip().splitlines()          # the same warnings, word for word
+    assert np.abs(vm.H - ref.H).max() < 1e-6 and np.abs(vm.H_old - ref.H_old).max() < 1e-6
+    assert len(vm.homography_history) == len(ref.homography_history) == 1
+    if reason:
+        assert np.array_equal(vm.homography_history[0], np.eye(3))
+    # the rejected frame still became "previous" (main.py:756-759) and was warped with the substituted identity
+    kp = np.array([[k.pt[0], k.pt[1]] for k in vm.kp_prev], np.float32)
+    kr = np.array([[k.pt[0], k.pt[1]] for k in ref.kp_prev], np.float32)
+    assert np.array_equal(kp, kr)
+    d = np.abs(vm.output_img.astype(np.int16) - ref.output_img.astype(np.int16))
+    assert d.max() <= 1
+
+
+def test_kp_cur_des_cur_and_output_img_setter():
+    import b200mosaic
+    f0, f1 = _reject_case("accept")
+    vm = b200mosaic.VideMosaic(f0, detector_type="orb", show_intermediate=False, visualize=False)
+    vm.process_frame(f1, 1)
+    assert len(vm.kp_cur) == len(vm.des_cur) == vm.last_info.n_kp_cur
+    assert np.array_equal(vm.des_cur, vm.des_prev)                       # accepted frame: cur became prev (main.py:757-758)
+    img = np.full(vm.output_img.shape, 0, np.uint8); img[10:50, 20:90] = (5, 6, 7)
+    vm.output_img = img.astype(np.float64)                               # reference callers hold a float64 canvas
+    assert np.array_equal(vm.output_img, img)
+    vm.stabilization_enabled = False
+    vm.process_frame(f1, 2)
+    assert len(vm.homography_history) == 1                               # smooth_homography returns before appending (:812-816)
