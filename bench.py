@@ -11,6 +11,12 @@ One "step" = one `process_frame` of the stitching hot path on the next synthetic
  * roofline   : the warp/blend chain (graded kernel group): algorithmic bytes 3N + 6A per frame over its
                 CUDA-event time on the launching stream, against MEASURED_PEAKS.json's HBM copy bandwidth.
  * cpu_baseline: the oracle's cv2 path (same calls as the reference's VideMosaic) on the first frames, all host threads.
+ * regions    : every leg times R regions of exactly K steps (barrier + synchronize on both sides, max over ranks per region);
+                value / e2e are the MEDIAN region, min / max and the per-rank times are reported next to them.
+ * <other detector>: the same legs for the detector that is not the headline (the metric names SIFT & ORB).
+ * roofline_pyramid: the SIFT Gaussian + DoG pyramid alone (256 N algorithmic bytes per frame).
+ * modes      : the sharded modes of SURVEY 8e over the N ranks of this launch -- 64 x 720p ORB streams (config 4), offline frame-pair
+                sharding with its all_gather (config 3 at N GPUs), 4K frames into a 32768^2 canvas in N row tiles + NCCL gather (config 5).
 N > 1: one process per GPU, each rank stitches its own independent sweep (streams sharded one per GPU, SURVEY.md 8e);
 no data-path collective; weak scaling; time = max over ranks.
 `--impl reference` times the reference's CPU path (oracle.mosaic_ref.RefMosaic: the same cv2/NumPy calls as main.py) on rank 0.
@@ -43,6 +49,9 @@ def parse_args():
     ap.add_argument("--size", default="1920x1080")
     ap.add_argument("--cpu-frames", type=int, default=12, help="frames of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--regions", type=int, default=0, help="timed regions of exactly --steps steps each (0: min(5, 360 // steps))")
+    ap.add_argument("--single-detector", action="store_true", help="skip the sub-record of the other detector")
+    ap.add_argument("--no-modes", action="store_true", help="skip the sharded-mode records (configs 3 offline / 4 / 5)")
     return ap.parse_args()
 
 
@@ -116,13 +125,16 @@ def run_reference(args, rank, world):
     from oracle.mosaic_ref import RefMosaic
     cores = os.cpu_count() or 1
     cv2.setNumThreads(cores)
+    import contextlib
+    import io
     m = RefMosaic(frames[0], detector_type=args.detector)
-    for i in range(1, args.warmup + 1):
-        m.process_frame(frames[i], i)
-    t0 = time.perf_counter()
-    for i in range(args.warmup + 1, n):
-        m.process_frame(frames[i], i)
-    dt = time.perf_counter() - t0
+    with contextlib.redirect_stdout(io.StringIO()):          # the reference's warnings (main.py:723-798) must not break the one-line contract
+        for i in range(1, args.warmup + 1):
+            m.process_frame(frames[i], i)
+        t0 = time.perf_counter()
+        for i in range(args.warmup + 1, n):
+            m.process_frame(frames[i], i)
+        dt = time.perf_counter() - t0
     fps = args.steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
@@ -130,7 +142,8 @@ def run_reference(args, rank, world):
             "config": workload_config(args, w, h, frames[0]),
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                              "sample": f"{args.steps} frames of the same sweep, oracle.mosaic_ref.RefMosaic (cv2 {cv2.__version__}, "
-                                       f"same calls as the reference's VideMosaic), cv2.setNumThreads({cores}), IPP on"},
+                                       f"the reference's VideMosaic calls minus its display-only canvas copy / draw_border / gc.collect, so the port is "
+                                       f"slightly FASTER than the reference), cv2.setNumThreads({cores}), IPP on"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -146,6 +159,133 @@ def workload_config(args, w, h, frame0):
                    "< 126 MB L2); inputs differ every step, no explicit L2 flush -- the ORB path is L2 resident by design")}
 
 
+def pin_rank_cores(local_rank, world):
+    """each rank's launch thread on its own cores: the per-frame loop is host driven, and 8 ranks x (python + driver threads)
+    otherwise migrate over the box's cores (8-GPU efficiency 0.88 with max-over-ranks on a 13 ms window)"""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cores) // max(world, 1))
+        mine = cores[local_rank * per:(local_rank + 1) * per] or cores
+        os.sched_setaffinity(0, mine)
+        return cores, mine
+    except (AttributeError, OSError):
+        return None, None
+
+
+def ramp_clocks(torch, ms=120.0):
+    """untimed: keep the SMs busy for ~ms so that the timed region does not start on an idle-clocked GPU (host-side setup such as
+    page-locking hundreds of MB leaves the device idle for 100s of ms; the N=1 e2e leg of round 1 measured 16 % low for that reason)"""
+    a = torch.empty((4096, 4096), device="cuda", dtype=torch.bfloat16).normal_()
+    t0 = time.perf_counter()
+    while (time.perf_counter() - t0) * 1e3 < ms:
+        for _ in range(8):
+            a = (a @ a).clamp_(-1, 1)
+        torch.cuda.synchronize()
+
+
+def regions_max_over_ranks(torch, dist, times):
+    """times: this rank's per-region seconds.  Returns (per-region max over ranks, all ranks' rows)."""
+    t = torch.tensor(times, device="cuda", dtype=torch.float64)
+    if dist is None:
+        return list(times), [list(times)]
+    rows = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(rows, t)
+    allr = torch.stack(rows)
+    return [float(v) for v in allr.max(dim=0).values], [[float(v) for v in r] for r in allr]
+
+
+def headline(args, det, frames, dev_frames, pinned, ctx, lib, want_chain, sample_clocks):
+    """legs 1 (frames resident in HBM), 1b (chain alone, roofline) and 2 (end to end from pinned host frames) for one detector;
+    every leg is R regions of exactly K steps, each region bracketed by barrier + synchronize, timed per rank, max over ranks"""
+    import b200mosaic
+    torch, dist, rank, local_rank = ctx.torch, ctx.dist, ctx.rank, ctx.local
+    h, w = frames[0].shape[:2]
+    fb = h * w * 3
+    K, W, R = args.steps, args.warmup, args.regions
+    n = len(frames)
+    out = {}
+    # ---------------- leg 1: frames resident in HBM ----------------
+    vm = b200mosaic.VideMosaic(frames[0], detector_type=det, show_intermediate=False, visualize=False, device=local_rank)
+    base = dev_frames.data_ptr()
+    vm.warm_up()                                   # setup: CUDA graphs of the detector captured up front (executes nothing)
+    ramp_clocks(torch)
+    for i in range(1, W + 1):
+        vm.process_frame_device(base + i * fb, base + (i + 1) * fb)
+    vm.sync()
+    statuses, t_dev, ev_ms = [], [], []
+    launches0 = lib.bm_kernel_launches()
+    sampler = ClockSampler(local_rank) if (rank == 0 and sample_clocks) else None
+    i = W + 1
+    for r in range(R):
+        ctx.barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            statuses.append(vm.process_frame_device(base + i * fb, base + (i + 1) * fb if i + 1 < n else None))
+            i += 1
+        vm.sync()
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ev_ms.append(e0.elapsed_time(e1))
+        t_dev.append(max(wall, ev_ms[-1] * 1e-3))         # the step loop is host-driven; wall >= device span
+    out["launches"] = (lib.bm_kernel_launches() - launches0) / R
+    out["clocks"] = sampler.stop() if sampler else None
+    out["frames_ok"] = sum(1 for s in statuses if s == 0)
+    out["t_dev"], out["ev_ms"] = t_dev, ev_ms
+    del vm
+
+    # ---------------- leg 1b: the warp/blend chain alone (roofline) ----------------
+    # same frames and pipeline, but detect of frame t+1 is ordered after the chain of frame t (no overlap), so the CUDA events
+    # around the chain on its launching stream measure the chain and nothing else
+    if want_chain:
+        vmr = b200mosaic.VideMosaic(frames[0], detector_type=det, show_intermediate=False, visualize=False, device=local_rank)
+        vmr.set_overlap(False)
+        Kr = min(n - W - 2, 60)
+        for i in range(1, W + 1):
+            vmr.process_frame_device(base + i * fb)
+        vmr.sync()
+        vmr.timing(enable=True, reset=True)
+        for i in range(W + 1, W + 1 + Kr):
+            vmr.process_frame_device(base + i * fb)
+        vmr.sync()
+        out["chain"] = vmr.timing(reset=True)
+        del vmr
+
+    # ---------------- leg 2: end to end through the host-facing call ----------------
+    vm2 = b200mosaic.VideMosaic(frames[0], detector_type=det, show_intermediate=False, visualize=False, device=local_rank)
+    pbase = pinned.data_ptr()
+    canvas_host = torch.empty(tuple(vm2.output_img.shape), dtype=torch.uint8).pin_memory().numpy()     # setup: reusable host buffer
+    vm2.warm_up()
+    ramp_clocks(torch)
+    for i in range(1, W + 1):
+        vm2.process_frame_ptr(pbase + i * fb, pbase + (i + 1) * fb)
+    vm2.sync()
+    t_e2e = []
+    i = W + 1
+    canvas = None
+    for r in range(R):
+        ctx.barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            # H2D (double buffered: the copy of frame i+1 is started while frame i is processed) + all kernels + D2H of (counts, H)
+            vm2.process_frame_ptr(pbase + i * fb, pbase + (i + 1) * fb if i + 1 < n else None)
+            i += 1
+        canvas = vm2.read_canvas(canvas_host)          # the canvas (what becomes mosaic.jpg) D2H into the caller's pinned buffer, every region
+        torch.cuda.synchronize()
+        t_e2e.append(time.perf_counter() - t0)
+    out["t_e2e"] = t_e2e
+    out["canvas"] = canvas
+    out["vm2"] = vm2
+    return out
+
+
+def stats(xs):
+    xs = sorted(xs)
+    return {"min": xs[0], "median": xs[len(xs) // 2] if len(xs) % 2 else 0.5 * (xs[len(xs) // 2 - 1] + xs[len(xs) // 2]), "max": xs[-1]}
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -155,111 +295,89 @@ def main():
         run_reference(args, rank, world)
         return
 
+    import contextlib
+    import io
     import torch
     import b200mosaic
     from b200mosaic import _lib
+    sys.path.insert(0, str(ROOT / "tools"))
+    import bench_modes
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    all_cores, my_cores = pin_rank_cores(local_rank, world)
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = bench_modes.Ctx(rank, world, local_rank, dist, torch)
     lib = _lib.load()
     w, h = map(int, args.size.lower().split("x"))
     K, W = args.steps, args.warmup
-    n = K + W + 1
+    if args.regions <= 0:
+        args.regions = max(1, min(5, 360 // max(K, 1)))
+    R = args.regions
+    n = R * K + W + 2
     frames, sweep = make_frames(w, h, n, 1234 + 1000 * rank)
     fb = h * w * 3
-
-    # ---------------- leg 1: frames resident in HBM ----------------
     dev_frames = torch.from_numpy(np.stack(frames)).cuda(local_rank)          # (n, h, w, 3) u8
-    vm = b200mosaic.VideMosaic(frames[0], detector_type=args.detector, show_intermediate=False, visualize=False, device=local_rank)
-    base = dev_frames.data_ptr()
-    vm.warm_up()                                   # setup: CUDA graphs of the detector captured up front (executes nothing)
-    for i in range(1, W + 1):
-        vm.process_frame_device(base + i * fb, base + (i + 1) * fb)
-    vm.sync()
-    launches0 = lib.bm_kernel_launches()
-    statuses = []
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record()
-    t0 = time.perf_counter()
-    for i in range(W + 1, n):
-        statuses.append(vm.process_frame_device(base + i * fb, base + (i + 1) * fb if i + 1 < n else None))
-    vm.sync()
-    e1.record()
-    torch.cuda.synchronize()
-    wall = time.perf_counter() - t0
-    ev_ms = e0.elapsed_time(e1)
-    launches = lib.bm_kernel_launches() - launches0
-    dev_s = max(wall, ev_ms * 1e-3)          # the step loop is host-driven; wall >= device span
-    clocks = sampler.stop() if sampler else None
-    canvas_dev_leg = vm.output_img
-    n_ok = sum(1 for s in statuses if s == 0)
-    del vm
-
-    # ---------------- leg 1b: the warp/blend chain alone (roofline) ----------------
-    # same frames and pipeline, but detect of frame t+1 is ordered after the chain of frame t (no overlap), so the CUDA events
-    # around the chain on its launching stream measure the chain and nothing else
-    vmr = b200mosaic.VideMosaic(frames[0], detector_type=args.detector, show_intermediate=False, visualize=False, device=local_rank)
-    vmr.set_overlap(False)
-    Kr = min(K, 40)
-    for i in range(1, W + 1):
-        vmr.process_frame_device(base + i * fb)
-    vmr.sync()
-    vmr.timing(enable=True, reset=True)
-    for i in range(W + 1, W + 1 + Kr):
-        vmr.process_frame_device(base + i * fb)
-    vmr.sync()
-    wb_ms, wb_bytes, wb_frames = vmr.timing(reset=True)
-    del vmr
-
-    # ---------------- leg 2: end to end through the host-facing call ----------------
     pinned = torch.from_numpy(np.stack(frames)).pin_memory()
-    vm2 = b200mosaic.VideMosaic(frames[0], detector_type=args.detector, show_intermediate=False, visualize=False, device=local_rank)
-    pbase = pinned.data_ptr()
-    canvas_host = torch.empty(tuple(vm2.output_img.shape), dtype=torch.uint8).pin_memory().numpy()     # setup: reusable host buffer
-    vm2.warm_up()
-    for i in range(1, W + 1):
-        vm2.process_frame_ptr(pbase + i * fb, pbase + (i + 1) * fb)
-    vm2.sync()
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for i in range(W + 1, n):
-        # H2D (double buffered: the copy of frame i+1 is started while frame i is processed) + all kernels + D2H of (counts, H)
-        vm2.process_frame_ptr(pbase + i * fb, pbase + (i + 1) * fb if i + 1 < n else None)
-    canvas = vm2.read_canvas(canvas_host)              # final canvas D2H (what becomes mosaic.jpg) into the caller's pinned buffer
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    info_bytes = 160 + 16
-    # SURVEY 8f rank 1 (outside the timed region): crop_black_areas + scale_to_screen of the final canvas on the device
+
+    dets = [args.detector] + ([d for d in ("sift", "orb") if d != args.detector] if not args.single_detector else [])
+    res = {}
+    for di, det in enumerate(dets):
+        res[det] = headline(args, det, frames, dev_frames, pinned, ctx, lib, want_chain=(di == 0), sample_clocks=(di == 0))
+    main_det = dets[0]
+    hm = res[main_det]
+
+    # SURVEY 8f rank 1 / 3 (outside the timed regions): finalisation and preview thumbnail of the final canvas on the device
+    vm2 = hm["vm2"]
     vm2.finalize()
     tf = time.perf_counter()
     final_img = vm2.finalize()
     finalize_ms = 1e3 * (time.perf_counter() - tf)
-    # SURVEY 8f rank 3 (outside the timed region): the GUI's 400 x 300 progress thumbnail made on the device
     vm2.preview()
     tf = time.perf_counter()
     thumb = vm2.preview()
     preview_ms = 1e3 * (time.perf_counter() - tf)
-    del vm2
+    canvas = hm["canvas"]
+    for det in dets:
+        res[det].pop("vm2").close()
 
-    # ---------------- max over ranks ----------------
-    if dist is not None:
-        t = torch.tensor([dev_s, e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_s, e2e_s = float(t[0]), float(t[1])
+    # SIFT pyramid alone (roofline_pyramid): its kernels back to back on one stream between two CUDA events
+    pyr = None
+    if rank == 0:
+        import ctypes as C
+        gray = torch.from_numpy(np.ascontiguousarray(frames[1][:, :, 1])).cuda(local_rank)
+        ms = C.c_double(0); by = C.c_double(0)
+        torch.cuda.synchronize()
+        if lib.bm_sift_pyramid_ms(C.c_void_p(gray.data_ptr()), h, w, 20, C.byref(ms), C.byref(by)) == 0:
+            pyr = (ms.value, by.value)
+    del dev_frames
+
+    # ---------------- max over ranks, per region ----------------
+    agg = {}
+    for det in dets:
+        dmax, drows = regions_max_over_ranks(torch, dist, res[det]["t_dev"])
+        emax, erows = regions_max_over_ranks(torch, dist, res[det]["t_e2e"])
+        agg[det] = {"dev": dmax, "e2e": emax, "dev_rows": drows, "e2e_rows": erows}
     total_frames = K * world
-    value = total_frames / dev_s
-    e2e_value = total_frames / e2e_s
+
+    # ---------------- sharded modes (configs 3 offline / 4 / 5), bounded ----------------
+    modes = None
+    if not args.no_modes:
+        modes = []
+        for fn, kw in ((bench_modes.run_streams, dict(streams=64, frames=8, warmup=2)),
+                       (bench_modes.run_pairs, dict(frames=40 + world)),
+                       (bench_modes.run_tiles, dict(frames=24, warmup=2, size="3840x2160", canvas="32768x32768"))):
+            try:
+                torch.cuda.empty_cache()
+                m = fn(ctx, **kw)
+                m["n_gpus"] = world
+            except Exception as ex:                     # a mode that cannot run is reported, never silently dropped
+                m = {"mode": fn.__name__, "error": f"{type(ex).__name__}: {ex}"[:300]}
+            modes.append(m)
 
     if rank == 0:
         peaks = {}
@@ -267,67 +385,103 @@ def main():
         if pk.exists():
             peaks = json.loads(pk.read_text())
         peak = float(peaks.get("hbm_gbs", 6650.0))
+        wb_ms, wb_bytes, wb_frames = hm["chain"]
         achieved = (wb_bytes / 1e9) / (wb_ms / 1e3) if wb_ms > 0 else 0.0
-        # DRAM traffic of the chain per frame from the committed `ncu --set full` capture (profiles/): sum over its launches
-        traffic, traffic_src = None, None
-        tj = ROOT / "profiles" / "r01_chain_ncu.json"
-        if tj.exists() and w == 1920 and h == 1080:
+        # DRAM traffic of the chain per frame from the committed ncu captures (profiles/): cold-cache `--set full` replay and the
+        # in-pipeline figure (range replay without cache control), both per frame like `achieved`
+        traffic, traffic_src, traffic_in_pipeline = None, None, None
+        for name in ("r02_chain_ncu.json", "r01_chain_ncu.json"):
+            tj = ROOT / "profiles" / name
+            if tj.exists() and w == 1920 and h == 1080:
+                try:
+                    j = json.loads(tj.read_text())
+                    kk = j["kernels"]
+                    per_frame = j.get("launches_per_frame") or {"k_warp_rows": 1, "k_dt_local": 2, "k_dt_diag_chain16": 1, "k_dt_vert_local": 1,
+                                                                "k_dt_vert_chain16": 1, "k_dt_weights": 1, "k_blur_blend": 1, "k_rowscan_bgrx": 1}
+                    traffic = float(sum(c * (kk[k]["dram_read"] + kk[k]["dram_write"]) for k, c in per_frame.items() if k in kk))
+                    traffic_src = f"profiles/{name} (ncu --set full, caches flushed per kernel replay)"
+                    traffic_in_pipeline = j.get("in_pipeline_dram_bytes_per_frame")
+                    break
+                except (KeyError, ValueError):
+                    traffic = None
+        if all_cores:
             try:
-                kk = json.loads(tj.read_text())["kernels"]
-                per_frame = {"k_warp_rows": 1, "k_dt_local": 2, "k_dt_diag_chain16": 1, "k_dt_vert_local": 1, "k_dt_vert_chain16": 1,
-                             "k_dt_weights": 1, "k_blur_blend": 1, "k_rowscan_bgrx": 1}
-                traffic = float(sum(c * (kk[k]["dram_read"] + kk[k]["dram_write"]) for k, c in per_frame.items()))
-                traffic_src = "profiles/r01_chain_ncu.json (ncu --set full of tools/chain_only.py, caches flushed per kernel replay)"
-            except (KeyError, ValueError):
-                traffic = None
-        cpu = None
-        if not args.no_cpu_baseline and world >= 1:
+                os.sched_setaffinity(0, all_cores)     # the CPU baseline may use every host core
+            except OSError:
+                pass
+        cpus = {}
+        if not args.no_cpu_baseline:
+            import cv2
             cores = os.cpu_count() or 1
             nf = min(args.cpu_frames + 1, len(frames))
-            fps, dt = cpu_reference_fps(frames[:nf], args.detector, cores)
-            import cv2
-            cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                   "sample": f"first {nf - 1} frames of the same sweep ({dt:.1f} s), oracle.mosaic_ref.RefMosaic = the reference's "
-                             f"cv2 {cv2.__version__}/NumPy calls, cv2.setNumThreads({cores}), IPP on"}
-        finalize_cpu_ms = None
-        if cpu is not None:                               # the reference's own functions on the same canvas, same host
+            for det in dets:
+                with contextlib.redirect_stdout(io.StringIO()):
+                    fps, dt = cpu_reference_fps(frames[:nf], det, cores)
+                cpus[det] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "sample": f"first {nf - 1} frames of the same sweep ({dt:.1f} s), detector={det}, oracle.mosaic_ref.RefMosaic = the "
+                                       f"reference's cv2 {cv2.__version__}/NumPy calls minus its display-only copies, cv2.setNumThreads({cores}), IPP on"}
+        finalize_cpu_ms = preview_cpu_ms = None
+        if cpus:                                          # the reference's own functions on the same canvas, same host
             from oracle import finalize as ofin
             tc = time.perf_counter()
             ofin.scale_to_screen(ofin.crop_black_areas(canvas, threshold=80, margin=30))
             finalize_cpu_ms = 1e3 * (time.perf_counter() - tc)
-        preview_cpu_ms = None
-        if cpu is not None:                               # gui.py:143-158 on the copy main.py:1630-1632 hands over (host side only)
-            try:
+            try:                                          # gui.py:143-158 on the copy main.py:1630-1632 hands over (host side only)
                 from oracle import preview as opv
                 tc = time.perf_counter()
                 opv.gui_thumbnail(canvas.copy())
                 preview_cpu_ms = 1e3 * (time.perf_counter() - tc)
             except ImportError:
                 pass
-        line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": 1e3 * dev_s / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        info_bytes = 160 + 16
+
+        def record(det):
+            a = agg[det]
+            sd, se = stats(a["dev"]), stats(a["e2e"])
+            return {"value": total_frames / sd["median"], "ms_per_step": 1e3 * sd["median"] / K,
+                    "e2e": {"value": total_frames / se["median"], "unit": "frames/s", "h2d_bytes_per_step": fb,
+                            "d2h_bytes_per_step": info_bytes + int(canvas.nbytes / K)},
+                    "regions": {"count": R, "steps_each": K,
+                                "value_min_median_max": [total_frames / sd["max"], total_frames / sd["median"], total_frames / sd["min"]],
+                                "e2e_min_median_max": [total_frames / se["max"], total_frames / se["median"], total_frames / se["min"]],
+                                "per_rank_ms_per_step": [[1e3 * t / K for t in row] for row in a["dev_rows"]],
+                                "per_rank_e2e_ms_per_step": [[1e3 * t / K for t in row] for row in a["e2e_rows"]]},
+                    "gpu_launches": int(round(res[det]["launches"])), "frames_ok": res[det]["frames_ok"],
+                    "event_ms_per_step": float(np.median(res[det]["ev_ms"])) / K, "cpu_baseline": cpus.get(det)}
+        rm = record(main_det)
+        line = {"metric": METRIC, "value": rm["value"], "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": rm["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8 / u32 fixed point (warp, DT, ORB) + f32 (blend weights, SIFT pyramid) + bf16 x bf16 -> f32 tensor cores (SIFT matching, exact) + f64 (RANSAC/LM)", "data": "synthetic",
                 "config": workload_config(args, w, h, frames[0]),
-                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": fb,
-                        "d2h_bytes_per_step": info_bytes + int(canvas.nbytes / K)},
-                "gpu_launches": int(launches),
-                "clocks": clocks,
+                "e2e": rm["e2e"], "gpu_launches": rm["gpu_launches"], "clocks": hm["clocks"],
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
+                             "traffic_in_pipeline": traffic_in_pipeline,
                              "algorithmic_bytes_per_frame": wb_bytes / max(wb_frames, 1),
                              "kernel": "warp/blend chain (k_warp_rows, k_dt_*, k_blur_blend, k_rowscan_bgrx), 3N+6A bytes per frame; timed with "
                                        "CUDA events on its launching stream in a separate pass without detect overlap",
                              "frames": int(wb_frames),
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s",
                              "ms_per_frame": wb_ms / max(wb_frames, 1)},
-                "cpu_baseline": cpu,
-                "frames_ok": n_ok, "event_ms_per_step": ev_ms / K,
+                "roofline_pyramid": None if pyr is None else {
+                    "bound": "hbm", "achieved": (pyr[1] / 1e9) / (pyr[0] / 1e3), "peak": peak, "unit": "GB/s",
+                    "frac": (pyr[1] / 1e9) / (pyr[0] / 1e3) / peak, "algorithmic_bytes_per_frame": pyr[1], "ms_per_frame": pyr[0],
+                    "kernel": "SIFT Gaussian + DoG pyramid (k_sift_upsample + k_sift_blur<0..5> over all octaves), 256 N bytes per frame "
+                              "(SURVEY 8d); the kernels back to back on one stream between two CUDA events (bm_sift_pyramid_ms)"},
+                "cpu_baseline": rm["cpu_baseline"], "frames_ok": rm["frames_ok"], "event_ms_per_step": rm["event_ms_per_step"],
+                "regions": rm["regions"],
                 "finalize": {"what": "crop_black_areas(80, 30) + scale_to_screen of the final canvas (main.py:1647-1659) via bm_finalize, "
                                      "result copied to the host", "device_ms": finalize_ms, "out_shape": list(final_img.shape),
                              "cpu_ms": finalize_cpu_ms},
                 "preview": {"what": "400 x 300 RGB progress thumbnail of the live canvas (gui.py:143-158: cvtColor + Pillow bicubic resize) via "
                                     "bm_preview, result copied to the host; cpu_ms excludes the full-canvas D2H the reference path would need",
-                            "device_ms": preview_ms, "out_shape": list(thumb.shape), "cpu_ms": preview_cpu_ms}}
+                            "device_ms": preview_ms, "out_shape": list(thumb.shape), "cpu_ms": preview_cpu_ms},
+                "host_cores_per_rank": len(my_cores) if my_cores else None}
+        for det in dets[1:]:
+            r = record(det)
+            line[det] = {"metric": f"mosaic frames/sec at {w}x{h}, detector={det} (same sweep, same legs as the headline)", "unit": "frames/s", **r}
+        if modes is not None:
+            line["modes"] = modes
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

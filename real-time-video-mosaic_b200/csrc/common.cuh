@@ -61,3 +61,15 @@ extern long long g_bm_launches;          // kernels launched by this library (be
     } while (0)
 
 static inline int bm_div_up(int a, int b) { return (a + b - 1) / b; }
+
+// Stream priorities: the per-frame rate is bound by the LATENCY of detect -> match -> RANSAC (the caller hands frames over one ahead, so
+// a frame period is (L_detect + L_estimate) / 2), while the warp/blend chain only has to keep up.  level 2 = latency critical
+// (match + RANSAC: a few one-CTA kernels), 1 = detectors, 0 = chain / copies.
+static inline cudaError_t bm_stream_create(cudaStream_t* s, int level) {
+    int lo = 0, hi = 0;                                   // lo = least urgent (numerically largest), hi = most urgent
+    cudaError_t e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (e != cudaSuccess) return e;
+    int prio = lo - level;
+    if (prio < hi) prio = hi;
+    return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, prio);
+}

@@ -326,34 +326,40 @@ __device__ __forceinline__ float harris_response(const uint8_t* __restrict__ pyr
 
 // Per level (one CTA each), exactly as cv2's computeKeyPoints: retainBest(2 * quota) on the FAST scores of the row-major list,
 // HarrisResponses of the survivors, retainBest(quota) on those -- both with cv2's output order (cvorder.cuh).
-#define ORB_SEL_SMEM (200 * 1024)
+#define ORB_SEL_SMEM (220 * 1024)
 __global__ void __launch_bounds__(CVO_THREADS) k_orb_select(BmOrbLevels lv, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ ckey,
                                                             const unsigned* __restrict__ cxy, int* __restrict__ idx, int* __restrict__ idx2,
-                                                            int* __restrict__ lists, float* __restrict__ resp2, uint2* __restrict__ cand2,
-                                                            int* __restrict__ ctr) {
+                                                            float* __restrict__ resp2, uint2* __restrict__ cand2, int* __restrict__ ctr) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     __shared__ CvoShared sh;
     const int level = blockIdx.x;
     const BmOrbLevel L = lv.l[level];
-    const int n1 = min(ctr[level], L.cand_cap);
+    int n1 = min(ctr[level], L.cand_cap);
+    // shared memory: the row scratch of the pairing passes, then the keys (FAST scores as bytes / Harris responses) when they fit
+    int nrows = cvo_rows_needed(n1);
+    if (CvoRows::bytes(nrows) > ORB_SEL_SMEM) {                     // > ~450 k corners on one level: not rankable by one CTA
+        if (threadIdx.x == 0) ctr[32] = 1;
+        n1 = 0; nrows = cvo_rows_needed(0);
+    }
+    CvoRows rows;
+    rows.bind(sel_smem, nrows);
+    unsigned char* kbase = sel_smem + CvoRows::bytes(nrows);
+    const size_t kroom = ORB_SEL_SMEM - CvoRows::bytes(nrows);
     uint8_t* k8 = ckey + L.cand_off;
     int* id1 = idx + L.cand_off;
     int* id2 = idx2 + L.cand_off;
-    int* listL = lists + 2 * L.cand_off + 4 * level;
-    int* listR = listL + L.cand_cap + 2;
-    if (n1 <= ORB_SEL_SMEM) {
-        uint8_t* s8 = sel_smem;
-        for (int i = threadIdx.x; i < n1; i += CVO_THREADS) s8[i] = k8[i];
-        k8 = s8;
+    if ((size_t)n1 <= kroom) {
+        for (int i = threadIdx.x; i < n1; i += CVO_THREADS) kbase[i] = k8[i];
+        k8 = kbase;
     }
     for (int i = threadIdx.x; i < n1; i += CVO_THREADS) id1[i] = i;
     __syncthreads();
-    const int m1 = cvo_retain_best<uint8_t>(k8, id1, listL, listR, n1, 2 * L.quota, sh);
-    float* kf = (size_t)m1 * 4 <= ORB_SEL_SMEM ? reinterpret_cast<float*>(sel_smem) : resp2 + L.cand_off;
+    const int m1 = cvo_retain_best<uint8_t>(k8, id1, n1, 2 * L.quota, sh, rows);
+    float* kf = (size_t)m1 * 4 <= kroom ? reinterpret_cast<float*>(kbase) : resp2 + L.cand_off;
     const unsigned* xy = cxy + L.cand_off;
     for (int i = threadIdx.x; i < m1; i += CVO_THREADS) { kf[i] = harris_response(pyr, L, xy[id1[i]]); id2[i] = i; }
     __syncthreads();
-    const int m2 = cvo_retain_best<float>(kf, id2, listL, listR, m1, L.quota, sh);
+    const int m2 = cvo_retain_best<float>(kf, id2, m1, L.quota, sh, rows);
     for (int i = threadIdx.x; i < m2; i += CVO_THREADS)
         cand2[L.cand_off + i] = make_uint2(xy[id1[id2[i]]], __float_as_uint(kf[i]));
     if (threadIdx.x == 0) ctr[24 + level] = m2;
@@ -563,7 +569,6 @@ int bm_orb_create(BmOrb** out, int h, int w, int nfeatures, cudaStream_t s) {
               cudaMalloc(&o->ctr, o->zero_bytes) == cudaSuccess &&
               cudaMalloc(&o->ckey, tc) == cudaSuccess && cudaMalloc(&o->cxy, tc * sizeof(unsigned)) == cudaSuccess &&
               cudaMalloc(&o->idx, tc * sizeof(int)) == cudaSuccess && cudaMalloc(&o->idx2, tc * sizeof(int)) == cudaSuccess &&
-              cudaMalloc(&o->lists, (2 * tc + 4 * BM_ORB_LEVELS + 8) * sizeof(int)) == cudaSuccess &&
               cudaMalloc(&o->resp2, tc * sizeof(float)) == cudaSuccess && cudaMalloc(&o->cand2, tc * sizeof(uint2)) == cudaSuccess &&
               cudaMalloc(&o->corners, ((size_t)o->lv.total_px / 2 + 64) * sizeof(unsigned)) == cudaSuccess;
     if (!ok) { bm_orb_destroy(o); return -1; }
@@ -579,7 +584,7 @@ void bm_orb_destroy(BmOrb* o) {
     if (!o) return;
     for (int i = 0; i < o->ngraphs; ++i) cudaGraphExecDestroy(o->graphs[i].exec);
     cudaFree(o->pyr); cudaFree(o->score); cudaFree(o->ctr); cudaFree(o->ckey); cudaFree(o->cxy); cudaFree(o->idx); cudaFree(o->idx2);
-    cudaFree(o->lists); cudaFree(o->resp2); cudaFree(o->cand2); cudaFree(o->corners);
+    cudaFree(o->resp2); cudaFree(o->cand2); cudaFree(o->corners);
     delete o;
 }
 
@@ -600,7 +605,7 @@ static cudaError_t orb_enqueue(BmOrb* o, const uint8_t* d_gray, BmKeypoints* out
     BM_COUNT_LAUNCHES(1), k_fast_cscore<<<dim3(cblocks, BM_ORB_LEVELS), 256, 0, s>>>(lv, o->pyr, o->corners, o->ctr, o->score);
     BM_COUNT_LAUNCHES(1), k_fast_cnms<<<dim3(cblocks, BM_ORB_LEVELS), 256, 0, s>>>(lv, o->score, o->corners, o->ctr, o->nmsbits, o->rowcnt);
     BM_COUNT_LAUNCHES(1), k_orb_compact<<<(lv.total_rows * 32 + 255) / 256, 256, 0, s>>>(lv, o->score, o->nmsbits, o->rowcnt, o->ctr, o->ckey, o->cxy);
-    BM_COUNT_LAUNCHES(1), k_orb_select<<<BM_ORB_LEVELS, CVO_THREADS, ORB_SEL_SMEM, s>>>(lv, o->pyr, o->ckey, o->cxy, o->idx, o->idx2, o->lists, o->resp2, o->cand2, o->ctr);
+    BM_COUNT_LAUNCHES(1), k_orb_select<<<BM_ORB_LEVELS, CVO_THREADS, ORB_SEL_SMEM, s>>>(lv, o->pyr, o->ckey, o->cxy, o->idx, o->idx2, o->resp2, o->cand2, o->ctr);
     BM_COUNT_LAUNCHES(1), k_orb_emit<<<BM_ORB_LEVELS, 1024, 0, s>>>(lv, o->cand2, o->ctr, *out);
     BM_COUNT_LAUNCHES(1), k_ic_angle<<<(BM_KP_CAP * 32) / 256, 256, 0, s>>>(lv, o->pyr, *out);
     BM_COUNT_LAUNCHES(1), k_orb_describe<<<BM_KP_CAP, 256, 0, s>>>(lv, o->pyr, *out);

@@ -47,7 +47,6 @@ struct BmOrb {
     uint8_t* ckey;      // [total_cand] FAST scores of the survivors in row-major order (permuted in place by the selection)
     unsigned* cxy;      // [total_cand] x | y << 16 of the survivors, row-major
     int *idx, *idx2;    // [total_cand] permutations of the two retainBest stages
-    int* lists;         // [2 * total_cand + 4 * levels] stopper lists of cvo_pair_pass
     float* resp2;       // [total_cand] Harris responses when they do not fit in shared memory
     uint2* cand2;       // [total_cand] per level: the final keypoints (xy, response bits) in cv2's order
     cudaStream_t stream;

@@ -7,6 +7,7 @@
 #include "ransac.cuh"
 #include <new>
 #include <string.h>
+#include <stdlib.h>
 
 struct BmHostReadback {      // pinned
     BmRansacResult r;
@@ -42,6 +43,11 @@ struct BmPipeline {
     BmRansacResult* d_res = nullptr;
     BmHostReadback* h_rb = nullptr;
     bool have_prev = false;
+    // BM_PROFILE=1: in-pipeline latency of the detect graph and of match + RANSAC (CUDA events on their own streams), printed at destroy
+    bool prof = false;
+    cudaEvent_t pd0[2] = {nullptr, nullptr}, pd1[2] = {nullptr, nullptr}, pe0 = nullptr, pe1 = nullptr;
+    bool pd_pending[2] = {false, false}, pe_pending = false;
+    double pd_ms = 0.0, pe_ms = 0.0; long pd_n = 0, pe_n = 0;
 };
 
 bm_status bm_pipeline_create(BmPipeline** out, const bm_config& cfg, cudaStream_t stream) {
@@ -56,13 +62,15 @@ bm_status bm_pipeline_create(BmPipeline** out, const bm_config& cfg, cudaStream_
               cudaEventCreateWithFlags(&p->ev_det[0], cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&p->ev_det[1], cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&p->ev_det[2], cudaEventDisableTiming) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&p->s_est, cudaStreamNonBlocking) == cudaSuccess && bm_matches_alloc(&p->m[0]) == 0 && bm_matches_alloc(&p->m[1]) == 0 &&
+              bm_stream_create(&p->s_est, 2) == cudaSuccess && bm_matches_alloc(&p->m[0]) == 0 && bm_matches_alloc(&p->m[1]) == 0 &&
               cudaMalloc(&p->d_mask, BM_KP_CAP) == cudaSuccess && cudaMalloc(&p->d_res, sizeof(BmRansacResult)) == cudaSuccess &&
               cudaHostAlloc(&p->h_rb, sizeof(BmHostReadback), cudaHostAllocDefault) == cudaSuccess;
     p->is_orb = cfg.detector == BM_DET_ORB;
+    p->prof = getenv("BM_PROFILE") != nullptr;
+    if (p->prof) { for (int i = 0; i < 2; ++i) { cudaEventCreate(&p->pd0[i]); cudaEventCreate(&p->pd1[i]); } cudaEventCreate(&p->pe0); cudaEventCreate(&p->pe1); }
     ok = ok && cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 2 && ok; ++i) {
-        ok = cudaStreamCreateWithFlags(&p->s_det[i], cudaStreamNonBlocking) == cudaSuccess;
+        ok = bm_stream_create(&p->s_det[i], 1) == cudaSuccess;
         if (!ok) break;
         if (p->is_orb) ok = bm_orb_create(&p->orb[i], cfg.frame_h, cfg.frame_w, cfg.nfeatures, p->s_det[i]) == 0;
         else ok = bm_sift_create(&p->sift[i], cfg.frame_h, cfg.frame_w, cfg.nfeatures, p->s_det[i]) == 0;
@@ -76,6 +84,9 @@ void bm_pipeline_destroy(BmPipeline* p) {
     if (!p) return;
     if (p->s_est) cudaStreamSynchronize(p->s_est);
     if (p->stream) cudaStreamSynchronize(p->stream);
+    if (p->prof && p->pd_n > 0)
+        fprintf(stderr, "[bm profile] detect graph: %.1f us avg over %ld (in pipeline), match + RANSAC: %.1f us avg over %ld\n",
+                1e3 * p->pd_ms / p->pd_n, p->pd_n, p->pe_n ? 1e3 * p->pe_ms / p->pe_n : 0.0, p->pe_n);
     for (int i = 0; i < 2; ++i) {
         if (p->s_det[i]) cudaStreamSynchronize(p->s_det[i]);
         bm_orb_destroy(p->orb[i]); bm_sift_destroy(p->sift[i]);
@@ -99,8 +110,13 @@ static cudaError_t detect(BmPipeline* p, const uint8_t* d_gray, BmKeypoints* out
     cudaError_t e = cudaEventRecord(p->ev_fork, p->stream);                  // everything the caller ordered on `stream` so far
     if (e == cudaSuccess) e = cudaStreamWaitEvent(p->s_det[i], p->ev_fork, 0);
     if (e != cudaSuccess) return e;
+    if (p->prof) {
+        if (p->pd_pending[i] && cudaEventSynchronize(p->pd1[i]) == cudaSuccess) { float ms = 0.f; cudaEventElapsedTime(&ms, p->pd0[i], p->pd1[i]); p->pd_ms += ms; p->pd_n++; }
+        cudaEventRecord(p->pd0[i], p->s_det[i]);
+    }
     e = p->is_orb ? bm_orb_detect(p->orb[i], d_gray, out) : bm_sift_detect(p->sift[i], d_gray, out);
     if (e != cudaSuccess) return e;
+    if (p->prof) { cudaEventRecord(p->pd1[i], p->s_det[i]); p->pd_pending[i] = true; }
     p->last_det_slot = slot;
     return cudaEventRecord(p->ev_det[slot], p->s_det[i]);
 }
@@ -130,6 +146,10 @@ bm_status bm_pipeline_estimate_begin(BmPipeline* p, const uint8_t* d_gray) {
     BM_CUDA_OK(cudaStreamWaitEvent(s, p->ev_det[p->prev], 0));
     p->mcur ^= 1;
     BmMatches& mm = p->m[p->mcur];
+    if (p->prof) {
+        if (p->pe_pending && cudaEventSynchronize(p->pe1) == cudaSuccess) { float ms = 0.f; cudaEventElapsedTime(&ms, p->pe0, p->pe1); p->pe_ms += ms; p->pe_n++; }
+        cudaEventRecord(p->pe0, s);
+    }
     if (p->is_orb) BM_CUDA_OK(bm_match_hamming(cur, prev, mm, s));
     else BM_CUDA_OK(bm_match_l2_ratio(cur, prev, mm, 0.7, s));                           // main.py:691
     BM_CUDA_OK(bm_launch_ransac(mm.src, mm.dst, mm.count, 2.0, 2000, 0.995, p->d_mask, p->d_res, s));   // main.py:857
@@ -140,6 +160,7 @@ bm_status bm_pipeline_estimate_begin(BmPipeline* p, const uint8_t* d_gray) {
     BM_CUDA_OK(cudaMemcpyAsync(&rb->n_matches, mm.count, sizeof(int), cudaMemcpyDeviceToHost, s));
     BM_CUDA_OK(cudaMemcpyAsync(&rb->overflow_cur, cur.flags, sizeof(int), cudaMemcpyDeviceToHost, s));
     BM_CUDA_OK(cudaMemcpyAsync(&rb->overflow_prev, prev.flags, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (p->prof) { cudaEventRecord(p->pe1, s); p->pe_pending = true; }
     BM_CUDA_OK(cudaEventRecord(p->ev_done, s));
     BM_CUDA_OK(cudaEventRecord(p->ev_est, s));
     return BM_OK;

@@ -918,7 +918,7 @@ int bm_sift_create(BmSift** out, int h, int w, int nfeatures, cudaStream_t s) {
               cudaMalloc(&o->sel, BM_KP_CAP * 4) == cudaSuccess && cudaMalloc(&o->raw, (size_t)o->lay.raw_cap * 4) == cudaSuccess &&
               cudaMalloc(&o->cresp, (size_t)o->lay.cand_cap * 4) == cudaSuccess && cudaMalloc(&o->csel, BM_KP_CAP * 4) == cudaSuccess;
     if (ok) ok = cudaMemcpyToSymbol(c_sift_k, hk, sizeof(hk)) == cudaSuccess;
-    if (ok) ok = cudaStreamCreateWithFlags(&o->s2, cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&o->s3, cudaStreamNonBlocking) == cudaSuccess &&
+    if (ok) ok = bm_stream_create(&o->s2, 1) == cudaSuccess && bm_stream_create(&o->s3, 1) == cudaSuccess &&
                  cudaEventCreateWithFlags(&o->ev_fork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&o->ev_join2, cudaEventDisableTiming) == cudaSuccess &&
                  cudaEventCreateWithFlags(&o->ev_join3, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; ok && i < SIFT_MAX_OCT; ++i)
@@ -1024,6 +1024,35 @@ static cudaError_t sift_enqueue(BmSift* o, const uint8_t* d_gray, BmKeypoints* o
     BM_COUNT_LAUNCHES(1), k_sift_describe<<<1024, 256, 0, s>>>(L, o->pyr, *out);
 #undef SIFT_OK
     return cudaGetLastError();
+}
+
+// Gaussian + DoG pyramid alone (upsample + all blur levels, serially on the detector's stream), `reps` times between two CUDA events:
+// the figure behind bench.py's `roofline_pyramid` (256 N algorithmic bytes per frame).
+cudaError_t bm_sift_time_pyramid(BmSift* o, const uint8_t* d_gray, int reps, float* ms_total) {
+    cudaStream_t s = o->stream;
+    const SiftLayout& L = o->lay;
+    cudaEvent_t e0, e1;
+    cudaError_t e = cudaEventCreate(&e0);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaEventCreate(&e1)) != cudaSuccess) { cudaEventDestroy(e0); return e; }
+    const dim3 blk(32, 8);
+    const int bw = 2 * o->w, bh = 2 * o->h;
+    for (int r = -1; r < reps; ++r) {                      // r == -1: warm-up
+        if (r == 0) cudaEventRecord(e0, s);
+        BM_COUNT_LAUNCHES(1), k_sift_upsample<<<dim3((bw + 31) / 32, (bh + 31) / 32), blk, 0, s>>>(d_gray, o->w, o->h, o->up);
+        for (int oc = 0; oc < L.noct; ++oc) {
+            const SiftOct& O = L.o[oc];
+            if (oc == 0) blur_level(0, o->up, o->pyr + O.g[0], nullptr, nullptr, O.w, O.h, s);
+            for (int l = 1; l <= 5; ++l)
+                blur_level(l, o->pyr + O.g[l - 1], o->pyr + O.g[l], o->pyr + O.d[l - 1], (l == 3 && oc + 1 < L.noct) ? o->pyr + L.o[oc + 1].g[0] : nullptr, O.w, O.h, s);
+        }
+    }
+    cudaEventRecord(e1, s);
+    e = cudaEventSynchronize(e1);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(ms_total, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    return e;
 }
 
 // detectAndCompute is a fixed launch sequence per (input buffer, output buffer): it is captured once into a CUDA graph with the

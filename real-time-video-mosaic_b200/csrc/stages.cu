@@ -171,6 +171,21 @@ extern "C" bm_status bm_orb_debug_level(const uint8_t* d_gray, int h, int w, int
     return BM_OK;
 }
 
+extern "C" bm_status bm_sift_pyramid_ms(const uint8_t* d_gray, int h, int w, int reps, double* ms_per_frame, double* algorithmic_bytes) {
+    if (!d_gray || reps < 1 || !ms_per_frame) return BM_ERR_ARG;
+    BmSift* o = nullptr;
+    cudaStream_t s = nullptr;
+    BM_CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    if (bm_sift_create(&o, h, w, 700, s) != 0) { cudaStreamDestroy(s); return BM_ERR_CUDA; }
+    float ms = 0.f;
+    cudaError_t e = bm_sift_time_pyramid(o, d_gray, reps, &ms);
+    bm_sift_destroy(o); cudaStreamDestroy(s);
+    BM_CUDA_OK(e);
+    *ms_per_frame = (double)ms / reps;
+    if (algorithmic_bytes) *algorithmic_bytes = 256.0 * (double)h * (double)w;
+    return BM_OK;
+}
+
 extern "C" bm_status bm_sift_debug_level(const uint8_t* d_gray, int h, int w, int octave, int level, int dog, float* h_out, int* lw, int* lh, int* noct) {
     if (!d_gray) return BM_ERR_ARG;
     BmSift* o = nullptr; BmKeypoints k;

@@ -207,3 +207,39 @@ def fixup_skipped(frames, rel, detector_type="sift", device=0):
         vm.close()
         t = u + 1
     return rel
+
+
+class TileStitcher:
+    """config 5: this rank's row tile of a (Wc, Hc) canvas.  `put(frame, H)` warps + blends the frame into the tile if its window
+    touches the tile's rows (H is the absolute canvas homography, shifted here by the tile origin); `tile_tensor()` returns the
+    tile as a packed-BGR torch tensor for the final gather."""
+
+    exchange = False        # boundary exchange between neighbouring tiles (see DESIGN section 7)
+
+    def __init__(self, frame0, canvas_w, canvas_h, rank, world, dist=None, device=0):
+        from .mosaic import VideMosaic
+        self.rank, self.world, self.dist = rank, world, dist
+        self.Wc, self.Hc = int(canvas_w), int(canvas_h)
+        self.fh, self.fw = frame0.shape[:2]
+        self.y0, self.y1 = tile_rows(self.Hc, rank, world)
+        self.vm = VideMosaic(frame0, detector_type="orb", show_intermediate=False, visualize=False,
+                             canvas_size=(self.y1 - self.y0, self.Wc), device=device)
+        self.vm.clear_canvas()
+
+    def put(self, frame, H):
+        if not touches_tile(H, self.fw, self.fh, self.y0, self.y1):
+            return 0
+        self.vm.warp_nosync(frame, tile_homography(H, self.y0))
+        return 1
+
+    def sync(self):
+        self.vm.sync()
+
+    def tile_tensor(self):
+        import torch
+        t = torch.empty((self.y1 - self.y0, self.Wc, 3), dtype=torch.uint8, device="cuda")
+        self.vm.canvas_to_device(t.data_ptr())
+        return t
+
+    def close(self):
+        self.vm.close()

@@ -1,9 +1,11 @@
 """GPU parity for SIFT (cv2.SIFT_create(700), main.py:33,112,718).  SIFT is a float32 pipeline whose near-threshold
-decisions depend on the last bits of the pyramid; stated tolerances (north_star: "SIFT descriptors within a stated L2
-tolerance"):
+decisions depend on the last bits of the pyramid, and cv2's own SIFT is not bit-repeatable from call to call (orientation angles
+jitter by an ulp, a keypoint at the 0.8-of-maximum orientation threshold may come or go: tests/test_oracle_order_cpu.py).  Stated
+tolerances (north_star: "SIFT descriptors within a stated L2 tolerance"), all as MAXIMA over the reproduced keypoints:
   * Gaussian / DoG pyramid: max |diff| <= 2e-4 grey levels vs the cv2 primitive chain (same FMA order as cv2's AVX2 filters)
-  * keypoints: >= 97 % of cv2's 700 keypoints reproduced at |dx|+|dy|+|dsize| < 0.02 px with |dangle| < 0.5 deg
-  * descriptors of the reproduced keypoints: L2 distance <= 16 (3 % of the 512 norm) for >= 97 %, median <= 3
+  * keypoints: >= 99.5 % of cv2's keypoints reproduced at |dx|+|dy|+|dsize| < 0.02 px (measured: 100 % on every frame below),
+    EVERY one of them with |dangle| < 0.01 deg, response within 1e-6 (8 float32 ulps) and the packed octave / layer field exact
+  * descriptors: EVERY reproduced keypoint's descriptor within L2 16 of cv2's (3 % of the 512 norm; measured: max 1, >= 99.8 % exact)
 """
 import numpy as np
 import cv2
@@ -48,23 +50,22 @@ def test_sift_pyramid_close_to_cv2_chain(ops, frames):
     assert worst <= 2e-4, worst
 
 
-def _compare(ops, gray, min_frac=0.97):
+def _compare(ops, gray, min_frac=0.995):
     kp, des = ops.sift_detect_and_compute(torch.from_numpy(gray).cuda())
     kc, dc = osift.cv_detect_and_compute(gray)
-    assert abs(len(kp) - len(kc)) <= 0.03 * len(kc) + 3, (len(kp), len(kc))
+    assert abs(len(kp) - len(kc)) <= 0.005 * len(kc) + 2, (len(kp), len(kc))
     assert np.array_equal(des, np.floor(des)) and des.min() >= 0 and des.max() <= 255
     pairs = osift.match_keypoints(kc, kp.astype(np.float64))
     frac = len(pairs) / max(len(kc), 1)
     assert frac >= min_frac, frac
     ia, ib = pairs[:, 0], pairs[:, 1]
     dang = np.abs(((kp[ib, 3] - kc[ia, 3]) + 180.0) % 360.0 - 180.0)
-    assert np.mean(dang < 0.5) >= 0.97, np.mean(dang < 0.5)
+    assert dang.max() < 0.01, dang.max()                                                       # every reproduced keypoint, not a percentile
     assert np.array_equal(kp[ib, 5].astype(np.int64), kc[ia, 5].astype(np.int64))              # packed octave/layer/xi
-    assert np.abs(kp[ib, 4] - kc[ia, 4]).max() < 1e-4                                        # response
-    good = dang < 0.5
-    l2 = np.linalg.norm(des[ib][good].astype(np.float64) - dc[ia][good].astype(np.float64), axis=1)
-    assert np.median(l2) <= 3.0, np.median(l2)
-    assert np.mean(l2 <= 16.0) >= 0.97, np.mean(l2 <= 16.0)
+    assert np.abs(kp[ib, 4] - kc[ia, 4]).max() < 1e-6                                        # response
+    l2 = np.linalg.norm(des[ib].astype(np.float64) - dc[ia].astype(np.float64), axis=1)
+    assert l2.max() <= 16.0, (l2.max(), int((l2 > 16).sum()))                                  # a maximum, not a percentile
+    assert np.mean(l2 == 0) >= 0.98, np.mean(l2 == 0)
     return frac
 
 
@@ -73,11 +74,35 @@ def test_sift_on_clip_frames(ops, frames, i):
     _compare(ops, cv2.cvtColor(frames[i], cv2.COLOR_BGR2GRAY))
 
 
-@pytest.mark.parametrize("size", [(640, 360), (1920, 1080)])
-def test_sift_on_synthetic(ops, size):
+@pytest.mark.parametrize("size,seed", [((640, 360), 9), ((1920, 1080), 9), ((1920, 1080), 31), ((1280, 720), 5)])
+def test_sift_on_synthetic(ops, size, seed):
     from b200mosaic.synth import DroneSweep
-    g = cv2.cvtColor(DroneSweep(size[0], size[1], seed=9, ground_size=2048).next(), cv2.COLOR_BGR2GRAY)
+    g = cv2.cvtColor(DroneSweep(size[0], size[1], seed=seed, ground_size=2048).next(), cv2.COLOR_BGR2GRAY)
     _compare(ops, g)
+
+
+def test_sift_on_4k_frame(ops):
+    """config 5 frame size (3840 x 2160): ~220 k refined candidates, 4x the 1080p lists -- list capacities scale with the frame
+    (an overflow would surface as BM_ERR_UNSUPPORTED, never as silently truncated lists)"""
+    from b200mosaic.synth import DroneSweep, make_ground
+    ground = cv2.resize(make_ground(4096, 77), (8192, 8192))
+    g = cv2.cvtColor(DroneSweep(3840, 2160, seed=77, ground=ground, max_step=40.0).next(), cv2.COLOR_BGR2GRAY)
+    _compare(ops, g)
+
+
+def test_sift_full_clip_frames(ops, golden_dir):
+    """every 37th frame of the real clip at its native 854 x 480"""
+    cap = cv2.VideoCapture(str(golden_dir / "clip01.mp4"))
+    t, n = 0, 0
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        if t % 37 == 0:
+            _compare(ops, cv2.cvtColor(f, cv2.COLOR_BGR2GRAY))
+            n += 1
+        t += 1
+    assert n >= 15
 
 
 def test_sift_output_order_is_cv2_keypoint_lessthan(ops, frames):

@@ -31,6 +31,154 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
 
+class Ctx:
+    """process-group context shared by the mode runners (bench.py builds one too)"""
+
+    def __init__(self, rank, world, local, dist, torch):
+        self.rank, self.world, self.local, self.dist, self.torch = rank, world, local, dist, torch
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        if self.dist is None:
+            return x
+        t = self.torch.tensor([x], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t[0])
+
+
+def run_streams(ctx, streams=64, frames=16, warmup=3, size="1280x720", det="orb"):
+    """config 4: `streams` concurrent streams, stream s -> rank s % N, no data-path collective"""
+    import b200mosaic
+    from b200mosaic import sharding as sh
+    from b200mosaic.synth import DroneSweep, make_ground
+    torch = ctx.torch
+    w, h = map(int, size.split("x"))
+    n = frames + warmup + 1
+    ground = make_ground(4096, 2000)
+    nseq = 8                                                 # distinct sweeps; stream s replays sweep s % 8 (content is irrelevant for throughput)
+    seqs = [torch.from_numpy(np.stack(DroneSweep(w, h, seed=2000 + q, ground=ground, max_step=10.0, max_travel=0.6 * h).frames(n))).pin_memory()
+            for q in range(nseq)]
+    fb = h * w * 3
+    mine = sh.shard_streams(streams, ctx.rank, ctx.world)
+    vms = [b200mosaic.VideMosaic(seqs[s % nseq][0].numpy(), detector_type=det, show_intermediate=False, visualize=False, device=ctx.local) for s in mine]
+
+    def step(i):
+        for vm, s in zip(vms, mine):
+            vm.begin_frame_ptr(seqs[s % nseq].data_ptr() + i * fb)
+        return [vm.end_frame() for vm in vms]
+    for i in range(1, warmup + 1):
+        step(i)
+    for vm in vms:
+        vm.sync()
+    ctx.barrier()
+    t0 = time.perf_counter()
+    ok = 0
+    for i in range(warmup + 1, n):
+        ok += sum(1 for st in step(i) if st == 0)
+    for vm in vms:
+        vm.sync()
+    torch.cuda.synchronize()
+    dt = ctx.max_over_ranks(time.perf_counter() - t0)
+    for vm in vms:
+        vm.close()
+    total = streams * frames
+    return {"mode": "streams", "scaling": "strong", "metric": f"aggregate mosaic frames/sec over {streams} concurrent {w}x{h} {det.upper()} streams",
+            "value": total / dt, "unit": "frames/s", "ms_per_step": 1e3 * dt / frames, "steps": frames, "warmup": warmup,
+            "config": {"workload": f"{streams} streams x {frames} frames, {w}x{h}, detector={det}, stream s -> rank s % {ctx.world}, "
+                                   f"{len(mine)} streams on rank 0, begin/end interleaved, host frames in pinned memory (H2D inside)",
+                       "frames_ok_rank0": ok, "collective": "none"}}
+
+
+def run_pairs(ctx, frames=64, size="1920x1080", det="sift"):
+    """config 3 offline at N GPUs: contiguous chunks of frame pairs per rank, ONE all_gather of the relative homographies"""
+    import b200mosaic
+    from b200mosaic import sharding as sh
+    from b200mosaic.synth import DroneSweep
+    torch = ctx.torch
+    w, h = map(int, size.split("x"))
+    n = frames + 1
+    pinned = torch.from_numpy(np.stack(DroneSweep(w, h, seed=1234, ground_size=4096, max_step=12.0, max_travel=0.8 * h).frames(n))).pin_memory()
+    fr = [pinned[t].numpy() for t in range(n)]               # views into pinned memory: DMA'd directly
+    s, e = sh.shard_pairs(n, ctx.rank, ctx.world)
+    # handle creation (allocations, graph capture) and the chunk's first pair are the untimed warm-up
+    vm = b200mosaic.VideMosaic(fr[s - 1], detector_type=det, show_intermediate=False, visualize=False, device=ctx.local) if e > s else None
+    st0, Hs0 = sh.estimate_pairs(fr, s, min(s + 1, e), detector_type=det, device=ctx.local, vm=vm)
+    sh.all_gather_pairs(sh.pack_pairs(st0, Hs0), n, ctx.rank, ctx.world, ctx.dist, device="cuda")      # untimed: first use of the collective
+    ctx.barrier()
+    t0 = time.perf_counter()
+    st, Hs = sh.estimate_pairs(fr, s + 1, e, detector_type=det, device=ctx.local, vm=vm)
+    st, Hs = st0 + st, Hs0 + Hs
+    torch.cuda.synchronize()
+    t_est = ctx.max_over_ranks(time.perf_counter() - t0)
+    rows = sh.all_gather_pairs(sh.pack_pairs(st, Hs), n, ctx.rank, ctx.world, ctx.dist, device="cuda")
+    rel = sh.unpack_pairs(rows)
+    H0 = np.eye(3); H0[0, 2] = int(1.2 * w) / 2 - w / 2; H0[1, 2] = int(2 * h) - h
+    Habs = sh.compose_chain(H0, rel)
+    torch.cuda.synchronize()
+    dt = ctx.max_over_ranks(time.perf_counter() - t0)
+    if vm is not None:
+        vm.close()
+    timed = n - 1 - ctx.world
+    return {"mode": "pairs", "scaling": "strong",
+            "metric": f"frame pairs/sec (detect + match + RANSAC, {det.upper()}, {w}x{h}) sharded over ranks + all_gather + prefix composition",
+            "value": timed / dt, "unit": "pairs/s", "ms_per_step": 1e3 * dt / timed, "steps": timed, "warmup": 1,
+            "config": {"workload": f"{n} frames, pairs [{s},{e}) on rank 0 of {ctx.world}", "pairs_ok": int(sum(1 for r in rel if r is not None)),
+                       "composed": int(sum(1 for H in Habs if H is not None)), "collective": "all_gather of 80 B per pair (NCCL)",
+                       "all_gather_plus_compose_ms": 1e3 * (dt - t_est)}}
+
+
+def run_tiles(ctx, frames=48, warmup=3, size="3840x2160", canvas="16384x16384"):
+    """config 5: canvas row tiles, every rank warps + blends the frames that touch its rows (boundary rows exchanged with the
+    neighbours, see sharding.TileExchange), final NCCL all_gather of the tiles"""
+    import b200mosaic
+    from b200mosaic import sharding as sh
+    from b200mosaic.synth import DroneSweep, make_ground
+    torch = ctx.torch
+    w, h = map(int, size.split("x"))
+    Wc, Hc = map(int, canvas.split("x"))
+    n = frames + warmup + 1
+    ground = make_ground(4096, 77)
+    nseq = min(n, 12)                                        # frame CONTENT is recycled (irrelevant for throughput); poses are not
+    base = DroneSweep(w, h, seed=77, ground=cv2.resize(ground, (2 * 4096, 2 * 4096)) if max(w, h) > 3000 else ground, max_step=40.0,
+                      noise_sigma=2.0).frames(nseq)
+    fr = [base[t % nseq] for t in range(n)]
+    y0, y1 = sh.tile_rows(Hc, ctx.rank, ctx.world)
+    # the camera climbs the whole canvas in n frames (so every row tile gets work), with a slow sideways weave and rotation
+    Hs = []
+    for t in range(n):
+        ang = np.deg2rad(2.0 * np.sin(t / 7.0))
+        R = np.array([[np.cos(ang), -np.sin(ang), 0.0], [np.sin(ang), np.cos(ang), 0.0], [0.0, 0.0, 1.0]])
+        T = np.eye(3); T[0, 2] = Wc / 2 - w / 2 + 0.05 * Wc * np.sin(t / 5.0); T[1, 2] = (Hc - h - 8) * (1.0 - t / max(n - 1, 1)) + 4
+        Hs.append(T @ R)
+    tiler = sh.TileStitcher(fr[0], Wc, Hc, ctx.rank, ctx.world, ctx.dist, device=ctx.local)
+    for t in range(0, warmup + 1):
+        tiler.put(fr[t], Hs[t])
+    tiler.sync()
+    ctx.barrier()
+    t0 = time.perf_counter()
+    mine = sum(tiler.put(fr[t], Hs[t]) for t in range(warmup + 1, n))
+    tile = tiler.tile_tensor()
+    torch.cuda.synchronize()
+    t_warp = ctx.max_over_ranks(time.perf_counter() - t0)
+    full = sh.gather_tiles(tile, Hc, ctx.rank, ctx.world, ctx.dist)
+    torch.cuda.synchronize()
+    dt = ctx.max_over_ranks(time.perf_counter() - t0)
+    nbytes = int(full.numel())
+    del full, tile
+    tiler.close()
+    return {"mode": "tiles", "scaling": "strong",
+            "metric": f"frames/sec warped + blended into a {Wc}x{Hc} canvas sharded in {ctx.world} row tiles, incl. the final NCCL all_gather",
+            "value": frames / dt, "unit": "frames/s", "ms_per_step": 1e3 * dt / frames, "steps": frames, "warmup": warmup,
+            "config": {"workload": f"{w}x{h} frames, tile rows [{y0},{y1}) on rank 0, {mine} of {frames} frames touch it",
+                       "warp_blend_fps": frames / t_warp, "gather_ms": 1e3 * (dt - t_warp), "canvas_bytes": nbytes,
+                       "collective": "per-frame neighbour exchange of boundary rows (NCCL send/recv) + final all_gather of the tiles",
+                       "boundary_exchange": bool(getattr(tiler, "exchange", False))}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--mode", required=True, choices=["streams", "pairs", "tiles"])
@@ -43,9 +191,6 @@ def main():
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     import torch
-    import b200mosaic
-    from b200mosaic import sharding as sh
-    from b200mosaic.synth import DroneSweep, make_ground
     if not torch.cuda.is_available():
         raise SystemExit("needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
@@ -53,118 +198,14 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0])
-
-    out = {"mode": args.mode, "n_gpus": world, "data": "synthetic", "higher_is_better": True, "scaling": "weak" if args.mode == "streams" else "strong"}
+    ctx = Ctx(rank, world, local, dist, torch)
     if args.mode == "streams":
-        w, h = map(int, (args.size or "1280x720").split("x"))
-        det = args.detector or "orb"
-        n = args.frames + args.warmup + 1
-        ground = make_ground(4096, 2000)
-        nseq = 8                                                 # distinct sweeps; stream s replays sweep s % 8 (content is irrelevant for throughput)
-        seqs = [torch.from_numpy(np.stack(DroneSweep(w, h, seed=2000 + q, ground=ground, max_step=10.0, max_travel=0.6 * h).frames(n))).pin_memory()
-                for q in range(nseq)]
-        fb = h * w * 3
-        mine = sh.shard_streams(args.streams, rank, world)
-        vms = [b200mosaic.VideMosaic(seqs[s % nseq][0].numpy(), detector_type=det, show_intermediate=False, visualize=False, device=local) for s in mine]
-        def step(i):
-            for vm, s in zip(vms, mine):
-                vm.begin_frame_ptr(seqs[s % nseq].data_ptr() + i * fb)
-            return [vm.end_frame() for vm in vms]
-        for i in range(1, args.warmup + 1):
-            step(i)
-        for vm in vms:
-            vm.sync()
-        barrier()
-        t0 = time.perf_counter()
-        ok = 0
-        for i in range(args.warmup + 1, n):
-            ok += sum(1 for st in step(i) if st == 0)
-        for vm in vms:
-            vm.sync()
-        torch.cuda.synchronize()
-        dt = max_over_ranks(time.perf_counter() - t0)
-        total = args.streams * args.frames
-        out.update({"metric": f"aggregate mosaic frames/sec over {args.streams} concurrent {w}x{h} {det.upper()} streams", "value": total / dt,
-                    "unit": "frames/s", "ms_per_step": 1e3 * dt / args.frames, "steps": args.frames, "warmup": args.warmup,
-                    "config": {"workload": f"{args.streams} streams x {args.frames} frames, {w}x{h}, detector={det}, stream s -> rank s % {world}, "
-                                           f"{len(mine)} streams on rank 0, begin/end interleaved", "frames_ok_rank0": ok}})
+        out = run_streams(ctx, args.streams, args.frames, args.warmup, args.size or "1280x720", args.detector or "orb")
     elif args.mode == "pairs":
-        w, h = map(int, (args.size or "1920x1080").split("x"))
-        det = args.detector or "sift"
-        n = args.frames + 1
-        pinned = torch.from_numpy(np.stack(DroneSweep(w, h, seed=1234, ground_size=4096, max_step=12.0, max_travel=0.8 * h).frames(n))).pin_memory()
-        frames = [pinned[t].numpy() for t in range(n)]           # views into pinned memory: DMA'd directly
-        s, e = sh.shard_pairs(n, rank, world)
-        # handle creation (allocations, graph capture) and the chunk's first pair are the untimed warm-up
-        vm = b200mosaic.VideMosaic(frames[s - 1], detector_type=det, show_intermediate=False, visualize=False, device=local) if e > s else None
-        st0, Hs0 = sh.estimate_pairs(frames, s, min(s + 1, e), detector_type=det, device=local, vm=vm)
-        barrier()
-        t0 = time.perf_counter()
-        st, Hs = sh.estimate_pairs(frames, s + 1, e, detector_type=det, device=local, vm=vm)
-        st, Hs = st0 + st, Hs0 + Hs
-        rows = sh.all_gather_pairs(sh.pack_pairs(st, Hs), n, rank, world, dist, device="cuda")
-        rel = sh.unpack_pairs(rows)
-        H0 = np.eye(3); H0[0, 2] = int(1.2 * w) / 2 - w / 2; H0[1, 2] = int(2 * h) - h
-        Habs = sh.compose_chain(H0, rel)
-        torch.cuda.synchronize()
-        dt = max_over_ranks(time.perf_counter() - t0)
-        out.update({"metric": f"frame pairs/sec (detect + match + RANSAC, {det.upper()}, {w}x{h}) sharded over ranks + all_gather + prefix composition",
-                    "value": (n - 1 - world) / dt, "unit": "pairs/s", "ms_per_step": 1e3 * dt / (n - 1 - world), "steps": n - 1 - world, "warmup": 1,
-                    "config": {"workload": f"{n} frames, pairs [{s},{e}) on rank 0 of {world}", "pairs_ok": int(sum(1 for r in rel if r is not None)),
-                               "composed": int(sum(1 for H in Habs if H is not None))}})
+        out = run_pairs(ctx, args.frames, args.size or "1920x1080", args.detector or "sift")
     else:
-        w, h = map(int, (args.size or "3840x2160").split("x"))
-        Wc, Hc = map(int, args.canvas.split("x"))
-        n = args.frames + args.warmup + 1
-        ground = make_ground(4096, 77)
-        nseq = min(n, 12)                                        # frame CONTENT is recycled (irrelevant for throughput); poses are not
-        base = DroneSweep(w, h, seed=77, ground=cv2.resize(ground, (2 * 4096, 2 * 4096)) if max(w, h) > 3000 else ground, max_step=40.0,
-                          noise_sigma=2.0).frames(nseq)
-        frames = [base[t % nseq] for t in range(n)]
-        y0, y1 = sh.tile_rows(Hc, rank, world)
-        # the camera climbs the whole canvas in n frames (so every row tile gets work), with a slow sideways weave and rotation
-        Hs = []
-        for t in range(n):
-            ang = np.deg2rad(2.0 * np.sin(t / 7.0))
-            R = np.array([[np.cos(ang), -np.sin(ang), 0.0], [np.sin(ang), np.cos(ang), 0.0], [0.0, 0.0, 1.0]])
-            T = np.eye(3); T[0, 2] = Wc / 2 - w / 2 + 0.05 * Wc * np.sin(t / 5.0); T[1, 2] = (Hc - h - 8) * (1.0 - t / max(n - 1, 1)) + 4
-            Hs.append(T @ R)
-        vm = b200mosaic.VideMosaic(frames[0], detector_type="orb", show_intermediate=False, visualize=False, canvas_size=(y1 - y0, Wc), device=local)
-        vm.clear_canvas()
-        def put(t):
-            if sh.touches_tile(Hs[t], w, h, y0, y1):
-                vm.warp_nosync(frames[t], sh.tile_homography(Hs[t], y0))
-                return 1
-            return 0
-        for t in range(0, args.warmup + 1):
-            put(t)
-        vm.sync()
-        barrier()
-        t0 = time.perf_counter()
-        mine = sum(put(t) for t in range(args.warmup + 1, n))
-        tile = torch.empty((y1 - y0, Wc, 3), dtype=torch.uint8, device="cuda")
-        vm.canvas_to_device(tile.data_ptr())
-        torch.cuda.synchronize()
-        t_warp = max_over_ranks(time.perf_counter() - t0)
-        full = sh.gather_tiles(tile, Hc, rank, world, dist)
-        torch.cuda.synchronize()
-        dt = max_over_ranks(time.perf_counter() - t0)
-        out.update({"metric": f"frames/sec warped + blended into a {Wc}x{Hc} canvas sharded in {world} row tiles, incl. the final NCCL all_gather",
-                    "value": args.frames / dt, "unit": "frames/s", "ms_per_step": 1e3 * dt / args.frames, "steps": args.frames, "warmup": args.warmup,
-                    "config": {"workload": f"{w}x{h} frames, tile rows [{y0},{y1}) on rank 0, {mine} of {args.frames} frames touch it",
-                               "gather_ms": 1e3 * (dt - t_warp), "canvas_bytes": int(full.numel())}})
+        out = run_tiles(ctx, args.frames, args.warmup, args.size or "3840x2160", args.canvas)
+    out.update({"n_gpus": world, "data": "synthetic", "higher_is_better": True})
     if rank == 0:
         print(json.dumps(out), flush=True)
     if dist is not None:
