@@ -15,6 +15,8 @@
 //  * retainBest(700): 3-pass radix select on the float response bits (ties kept), final order = cv2's
 //    KeyPoint_LessThan order (x, y, size desc, angle, response desc, octave desc) by rank counting.
 #include "sift.cuh"
+#include <cuda.h>          // CUtensorMap / cuTensorMapEncodeTiled (TMA descriptors of the pyramid levels)
+#include <stdlib.h>
 #include <float.h>
 #include <math.h>
 #include <string.h>
@@ -54,6 +56,9 @@ struct BmSift {
     int* sel;                // indices of the selected keypoints
     unsigned* hist;          // radix-select scratch
     float* kernels_dev;      // 6 kernels x 32 taps
+    CUtensorMap tmap[SIFT_MAX_OCT][6];   // TMA descriptor of the SOURCE image of blur level l in octave o (box 32 x 64|128 floats, SWIZZLE_128B)
+    bool tma_ok[SIFT_MAX_OCT][6];
+    bool use_tma;
     cudaStream_t stream;
     // fork / join streams + events of the captured detect graph, and the graph cache
     cudaStream_t s2, s3;
@@ -188,6 +193,129 @@ __global__ void __launch_bounds__(sift_blur_nt(SHT), 2) k_sift_blur(const float*
                     if (LEVEL >= 1) dog[idx] = __fsub_rn(a, tile[r0 + o + R][c + R]);
                     if (LEVEL == 3) {
                         // next octave base = this level decimated by 2 (INTER_NEAREST: dst(x,y) = src(2x,2y))
+                        const int gy = gy0 + o;
+                        if (decx && !(gy & 1) && (gy >> 1) < (h >> 1)) dec[(unsigned)(gy >> 1) * (unsigned)(w >> 1) + (unsigned)(gx >> 1)] = a;
+                    }
+                }
+                idx += (unsigned)w;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// TMA form of the same kernel (same arithmetic, same outputs).  The tile + halo is fetched by the TMA unit instead of one 4-byte
+// cp.async per element with reflect-101 index math: three 2-D box loads (32 floats x SHT rows each, SWIZZLE_128B) issued by ONE
+// thread land the 96-column tile in shared memory and complete on an mbarrier.  SWIZZLE_128B XORs the 16-byte chunk index of every
+// 128-byte line with the line number mod 8, so the row pass -- lanes walk ROWS -- reads its window as LDS.128: the 8 lanes of a
+// quarter warp hit 8 different chunks (conflict free) and a thread needs (16 + 2R) / 4 loads instead of 16 + 2R.  The TMA unit
+// zero-fills outside the image, OpenCV wants BORDER_REFLECT_101, and a box must start on a 16-byte boundary of its row (it begins
+// RA = R rounded up to 4 columns left of the tile; an unaligned start faults with "illegal instruction"): tiles whose box leaves the image (the frame's rim, ~12 % of octave
+// 0) fill the same swizzled layout with the per-element path.
+// ------------------------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr size_t sift_blur_tma_smem(int sh) { return (size_t)sh * (3 * 128 + 65 * sizeof(float)) + 1024; }
+
+__device__ __forceinline__ unsigned sift_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+// byte offset of tile element (row, col) in the three-box swizzled layout; col in [0, 96)
+template <int SHT>
+__device__ __forceinline__ unsigned sift_swz(int row, int col) {
+    const int q = col >> 2;                                   // 16-byte chunk column
+    return (unsigned)((q >> 3) * (SHT * 128) + row * 128 + (((q & 7) ^ (row & 7)) << 4) + ((col & 3) << 2));
+}
+
+template <int LEVEL, int SHT>
+__global__ void __launch_bounds__(sift_blur_nt(SHT), 2) k_sift_blur_tma(const __grid_constant__ CUtensorMap tm, const float* __restrict__ in,
+                                                                   float* __restrict__ out, float* __restrict__ dog, float* __restrict__ dec,
+                                                                   int w, int h) {
+    constexpr int R = sift_level_radius(LEVEL), K = 2 * R + 1, TW = 64, TH = sift_tile_h(LEVEL, SHT), SH = TH + 2 * R,
+                  NO = TH / sift_blur_ng(SHT), NT = sift_blur_nt(SHT),
+                  RA = (R + 3) & ~3,          // the box must start on a 16-byte boundary of its row: it begins RA >= R columns left of the tile
+                  D = RA - R, NQ = (D + 16 + 2 * R + 3) / 4;
+    static_assert(64 + R + RA <= 96, "tile + halo must fit the three 32-column boxes");
+    extern __shared__ unsigned char sift_blur_smem_raw2[];
+    __shared__ __align__(8) unsigned long long mbar;
+    unsigned char* tile = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(sift_blur_smem_raw2) + 1023) & ~(uintptr_t)1023);
+    float (*rowf)[64 + 1] = reinterpret_cast<float (*)[64 + 1]>(tile + (size_t)SHT * 384);
+    const int bx = blockIdx.x * TW, by = blockIdx.y * TH;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool interior = bx - RA >= 0 && bx - RA + 96 <= w && by - R >= 0 && by - R + SHT <= h;      // (CTA uniform)
+    if (interior) {
+        if (tid == 0) {
+            const unsigned mb = sift_smem_u32(&mbar);
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((unsigned)(3 * SHT * 128)) : "memory");
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                             ::"r"(sift_smem_u32(tile + (size_t)b * SHT * 128)), "l"(&tm), "r"(bx - RA + 32 * b), "r"(by - R), "r"(mb)
+                             : "memory");
+        }
+        __syncthreads();                                       // the barrier is initialised for everyone
+        {
+            const unsigned mb = sift_smem_u32(&mbar);
+            unsigned done = 0;
+            while (!done)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(mb), "r"(0u) : "memory");
+        }
+    } else {
+        int gx[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) gx[j] = refl101(bx + lane + 32 * j - RA, w);
+        for (int ty = warp; ty < SH; ty += NT / 32) {
+            const float* __restrict__ rowp = in + (size_t)refl101(by + ty - R, h) * w;
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                sift_cp_async4(reinterpret_cast<float*>(tile + sift_swz<SHT>(ty, lane + 32 * j)), rowp + gx[j]);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+    }
+    if (tid < SH * 4) {
+        const int seg = tid / SH, r = tid - seg * SH, c0 = seg * 16;
+        float acc[16];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const float4 v4 = *reinterpret_cast<const float4*>(tile + sift_swz<SHT>(r, c0 + 4 * q));
+            const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int t = 4 * q + e - D;                          // window index of tile column c0 + 4 q + e
+                if (t >= 0 && t < 16 + 2 * R) {
+#pragma unroll
+                    for (int o = 0; o < 16; ++o) {
+                        const int k = t - o;
+                        if (k == 0) acc[o] = __fmul_rn(c_sift_k[LEVEL][0], vv[e]);
+                        else if (k > 0 && k < K) acc[o] = __fmaf_rn(c_sift_k[LEVEL][k], vv[e], acc[o]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < 16; ++o) rowf[r][c0 + o] = acc[o];
+    }
+    __syncthreads();
+    {
+        const int c = tid & 63, r0 = (tid >> 6) * NO;
+        const int gx = bx + c;
+        float hh[NO + 2 * R];
+#pragma unroll
+        for (int t = 0; t < NO + 2 * R; ++t) hh[t] = rowf[r0 + t][c];
+        if (gx < w) {
+            const int gy0 = by + r0, nrows = h - gy0;
+            unsigned idx = (unsigned)gy0 * (unsigned)w + (unsigned)gx;
+            const bool decx = LEVEL == 3 && dec != nullptr && !(gx & 1) && (gx >> 1) < (w >> 1);
+#pragma unroll
+            for (int o = 0; o < NO; ++o) {
+                if (o < nrows) {
+                    float a = __fmul_rn(c_sift_k[LEVEL][R], hh[o + R]);
+#pragma unroll
+                    for (int t = 1; t <= R; ++t) a = __fmaf_rn(c_sift_k[LEVEL][R + t], __fadd_rn(hh[o + R + t], hh[o + R - t]), a);
+                    out[idx] = a;
+                    if (LEVEL >= 1) dog[idx] = __fsub_rn(a, *reinterpret_cast<const float*>(tile + sift_swz<SHT>(r0 + o + R, c + RA)));
+                    if (LEVEL == 3) {
                         const int gy = gy0 + o;
                         if (decx && !(gy & 1) && (gy >> 1) < (h >> 1)) dec[(unsigned)(gy >> 1) * (unsigned)(w >> 1) + (unsigned)(gx >> 1)] = a;
                     }
@@ -867,6 +995,8 @@ static void gaussian_kernel(int ksize, double sigma, float* out) {
     for (int i = 0; i < ksize; ++i) out[i] = (float)(k[i] / sum);
 }
 
+static void sift_make_tensor_maps(BmSift* o);
+
 int bm_sift_create(BmSift** out, int h, int w, int nfeatures, cudaStream_t s) {
     BmSift* o = new (std::nothrow) BmSift();
     if (!o) return -1;
@@ -924,6 +1054,7 @@ int bm_sift_create(BmSift** out, int h, int w, int nfeatures, cudaStream_t s) {
     for (int i = 0; ok && i < SIFT_MAX_OCT; ++i)
         ok = cudaEventCreateWithFlags(&o->ev_l3[i], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&o->ev_l5[i], cudaEventDisableTiming) == cudaSuccess;
     o->graphs_enabled = true;
+    if (ok) sift_make_tensor_maps(o);
     if (!ok) { bm_set_error("bm_sift_create: %s", cudaGetErrorString(cudaGetLastError())); bm_sift_destroy(o); return -1; }
     *out = o;
     return 0;
@@ -943,28 +1074,67 @@ void bm_sift_destroy(BmSift* o) {
     delete o;
 }
 
+__host__ __device__ constexpr int sift_blur_sht(int level, long long px) { return (level >= 4 && px >= (1 << 21)) ? 128 : 64; }   // octave 0 of a 1080p frame (3840 x 2160)
+
 template <int LEVEL, int SHT>
-static void launch_blur_sh(const float* in, float* out, float* dog, float* dec, int w, int h, cudaStream_t s) {
+static void launch_blur_sh(const CUtensorMap* tm, const float* in, float* out, float* dog, float* dec, int w, int h, cudaStream_t s) {
     cudaError_t attr;
+    constexpr int TH = sift_tile_h(LEVEL, SHT);
+    const dim3 grid((w + 63) / 64, (h + TH - 1) / TH);
+    if (tm) {
+        BM_SMEM_OPTIN((k_sift_blur_tma<LEVEL, SHT>), sift_blur_tma_smem(SHT), attr);
+        (void)attr;
+        BM_COUNT_LAUNCHES(1), k_sift_blur_tma<LEVEL, SHT><<<grid, sift_blur_nt(SHT), sift_blur_tma_smem(SHT), s>>>(*tm, in, out, dog, dec, w, h);
+        return;
+    }
     BM_SMEM_OPTIN((k_sift_blur<LEVEL, SHT>), sift_blur_smem(SHT), attr);
     (void)attr;                                    // a failure surfaces as the launch error picked up by the caller
-    constexpr int TH = sift_tile_h(LEVEL, SHT);
-    BM_COUNT_LAUNCHES(1), k_sift_blur<LEVEL, SHT><<<dim3((w + 63) / 64, (h + TH - 1) / TH), sift_blur_nt(SHT), sift_blur_smem(SHT), s>>>(in, out, dog, dec, w, h);
+    BM_COUNT_LAUNCHES(1), k_sift_blur<LEVEL, SHT><<<grid, sift_blur_nt(SHT), sift_blur_smem(SHT), s>>>(in, out, dog, dec, w, h);
 }
 template <int LEVEL>
-static void launch_blur(const float* in, float* out, float* dog, float* dec, int w, int h, cudaStream_t s) {
-    if (LEVEL >= 4 && (long long)w * h >= (1 << 21)) launch_blur_sh<LEVEL, 128>(in, out, dog, dec, w, h, s);      // octave 0 of a 1080p frame (3840 x 2160)
-    else launch_blur_sh<LEVEL, 64>(in, out, dog, dec, w, h, s);
+static void launch_blur(const CUtensorMap* tm, const float* in, float* out, float* dog, float* dec, int w, int h, cudaStream_t s) {
+    if (sift_blur_sht(LEVEL, (long long)w * h) == 128) launch_blur_sh<LEVEL, 128>(tm, in, out, dog, dec, w, h, s);
+    else launch_blur_sh<LEVEL, 64>(tm, in, out, dog, dec, w, h, s);
 }
 
-static void blur_level(int level, const float* in, float* out, float* dog, float* dec, int w, int h, cudaStream_t s) {
+static void blur_level(const BmSift* o, int oc, int level, const float* in, float* out, float* dog, float* dec, int w, int h, cudaStream_t s) {
+    const CUtensorMap* tm = (o->use_tma && o->tma_ok[oc][level]) ? &o->tmap[oc][level] : nullptr;
     switch (level) {
-        case 0: launch_blur<0>(in, out, dog, dec, w, h, s); break;
-        case 1: launch_blur<1>(in, out, dog, dec, w, h, s); break;
-        case 2: launch_blur<2>(in, out, dog, dec, w, h, s); break;
-        case 3: launch_blur<3>(in, out, dog, dec, w, h, s); break;
-        case 4: launch_blur<4>(in, out, dog, dec, w, h, s); break;
-        default: launch_blur<5>(in, out, dog, dec, w, h, s); break;
+        case 0: launch_blur<0>(tm, in, out, dog, dec, w, h, s); break;
+        case 1: launch_blur<1>(tm, in, out, dog, dec, w, h, s); break;
+        case 2: launch_blur<2>(tm, in, out, dog, dec, w, h, s); break;
+        case 3: launch_blur<3>(tm, in, out, dog, dec, w, h, s); break;
+        case 4: launch_blur<4>(tm, in, out, dog, dec, w, h, s); break;
+        default: launch_blur<5>(tm, in, out, dog, dec, w, h, s); break;
+    }
+}
+
+// TMA descriptors of every blur source: 2-D float tensor (w, h), box 32 x SHT, SWIZZLE_128B, zero fill outside (only tiles whose box
+// lies inside the image use it).  A level whose rows are not 16-byte multiples keeps the per-element path.
+static void sift_make_tensor_maps(BmSift* o) {
+    // A/B (profiles/r02_pyramid_tma_ab.md): the TMA form is not faster than the cp.async form at 1080p (the kernel is bound by the
+    // FMA / LDS issue of its two passes, not by the tile fill), so it is opt-in: BM_SIFT_TMA=1
+    o->use_tma = getenv("BM_SIFT_TMA") != nullptr && getenv("BM_SIFT_NO_TMA") == nullptr;
+    for (int oc = 0; oc < o->lay.noct; ++oc) {
+        const SiftOct& O = o->lay.o[oc];
+        for (int l = 0; l < 6; ++l) {
+            o->tma_ok[oc][l] = false;
+            const float* src = l == 0 ? (oc == 0 ? o->up : nullptr) : o->pyr + O.g[l - 1];
+            const int sht = sift_blur_sht(l, (long long)O.w * O.h);
+            if (!src || (O.w & 3) || O.w < 96 || O.h < sht || (reinterpret_cast<uintptr_t>(src) & 15)) continue;
+            const cuuint64_t gdim[2] = {(cuuint64_t)O.w, (cuuint64_t)O.h};
+            const cuuint64_t gstr[1] = {(cuuint64_t)O.w * sizeof(float)};
+            const cuuint32_t box[2] = {32u, (cuuint32_t)sht};
+            const cuuint32_t estr[2] = {1u, 1u};
+            const CUresult r = cuTensorMapEncodeTiled(&o->tmap[oc][l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(src), gdim, gstr, box, estr,
+                                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            o->tma_ok[oc][l] = r == CUDA_SUCCESS;
+            if (const char* only = getenv("BM_SIFT_TMA_ONLY")) {               // debug: "oc,level" enables the TMA form for one launch only
+                int a = -1, b = -1;
+                if (sscanf(only, "%d,%d", &a, &b) == 2 && (a != oc || b != l)) o->tma_ok[oc][l] = false;
+            }
+        }
     }
 }
 
@@ -993,12 +1163,12 @@ static cudaError_t sift_enqueue(BmSift* o, const uint8_t* d_gray, BmKeypoints* o
     BM_COUNT_LAUNCHES(1), k_sift_upsample<<<dim3((bw + 31) / 32, (bh + 31) / 32), blk, 0, s>>>(d_gray, o->w, o->h, o->up);
     for (int oc = 0; oc < L.noct; ++oc) {
         const SiftOct& O = L.o[oc];
-        if (oc == 0) blur_level(0, o->up, o->pyr + O.g[0], nullptr, nullptr, O.w, O.h, s);
+        if (oc == 0) blur_level(o, oc, 0, o->up, o->pyr + O.g[0], nullptr, nullptr, O.w, O.h, s);
         // level 3 also writes the next octave's base (its 2x decimation)
         for (int l = 1; l <= 3; ++l)
-            blur_level(l, o->pyr + O.g[l - 1], o->pyr + O.g[l], o->pyr + O.d[l - 1], (l == 3 && oc + 1 < L.noct) ? o->pyr + L.o[oc + 1].g[0] : nullptr, O.w, O.h, s);
+            blur_level(o, oc, l, o->pyr + O.g[l - 1], o->pyr + O.g[l], o->pyr + O.d[l - 1], (l == 3 && oc + 1 < L.noct) ? o->pyr + L.o[oc + 1].g[0] : nullptr, O.w, O.h, s);
         if (forked) { SIFT_OK(cudaEventRecord(o->ev_l3[oc], s)); SIFT_OK(cudaStreamWaitEvent(s2, o->ev_l3[oc], 0)); }
-        for (int l = 4; l <= 5; ++l) blur_level(l, o->pyr + O.g[l - 1], o->pyr + O.g[l], o->pyr + O.d[l - 1], nullptr, O.w, O.h, s2);
+        for (int l = 4; l <= 5; ++l) blur_level(o, oc, l, o->pyr + O.g[l - 1], o->pyr + O.g[l], o->pyr + O.d[l - 1], nullptr, O.w, O.h, s2);
         if (O.w <= 2 * SIFT_BORDER || O.h <= 2 * SIFT_BORDER) continue;
         if (forked) { SIFT_OK(cudaEventRecord(o->ev_l5[oc], s2)); SIFT_OK(cudaStreamWaitEvent(s3, o->ev_l5[oc], 0)); }
         bool tiled = O.w >= EX_TW && (O.w & 3) == 0 && (reinterpret_cast<uintptr_t>(o->pyr) & 15) == 0;
@@ -1042,9 +1212,9 @@ cudaError_t bm_sift_time_pyramid(BmSift* o, const uint8_t* d_gray, int reps, flo
         BM_COUNT_LAUNCHES(1), k_sift_upsample<<<dim3((bw + 31) / 32, (bh + 31) / 32), blk, 0, s>>>(d_gray, o->w, o->h, o->up);
         for (int oc = 0; oc < L.noct; ++oc) {
             const SiftOct& O = L.o[oc];
-            if (oc == 0) blur_level(0, o->up, o->pyr + O.g[0], nullptr, nullptr, O.w, O.h, s);
+            if (oc == 0) blur_level(o, oc, 0, o->up, o->pyr + O.g[0], nullptr, nullptr, O.w, O.h, s);
             for (int l = 1; l <= 5; ++l)
-                blur_level(l, o->pyr + O.g[l - 1], o->pyr + O.g[l], o->pyr + O.d[l - 1], (l == 3 && oc + 1 < L.noct) ? o->pyr + L.o[oc + 1].g[0] : nullptr, O.w, O.h, s);
+                blur_level(o, oc, l, o->pyr + O.g[l - 1], o->pyr + O.g[l], o->pyr + O.d[l - 1], (l == 3 && oc + 1 < L.noct) ? o->pyr + L.o[oc + 1].g[0] : nullptr, O.w, O.h, s);
         }
     }
     cudaEventRecord(e1, s);
