@@ -6,9 +6,13 @@ ORB is bit-exact stage by stage INCLUDING keypoint order, so the trajectory must
 keypoints and matches on every frame, every absolute homography within 0.5 px corner reprojection (north_star's bar; measured
 here: < 1e-3 px -- RANSAC draws the same cv::RNG subsets from the same point order, the LM refit agrees to ~1e-9), and the canvas
 within a few grey levels (the blend itself is +-1 LSB per step against cv2, and the canvas is fed back 591 times).
-SIFT is tolerance-based by north_star (descriptors "within a stated L2 tolerance"; cv2's own SIFT is not bit-repeatable between two
-calls -- orientation angles jitter by an ulp, see tests/test_oracle_order_cpu.py), so its trajectory is held to the 0.5 px bar on
-the RELATIVE homographies and to a stated drift bound on the absolute ones.
+SIFT is tolerance-based by north_star (descriptors "within a stated L2 tolerance"), and the reference's own SIFT run is not
+repeatable: a SECOND run of the unmodified reference over this clip differs from the goldens by up to 0.88 px in the relative
+homographies (33 of 591 frames above 1e-3 px, 4 above 0.5 px, 1.15 px absolute drift; tests/golden/clip01_sift_repeatability.json) --
+cv2's orientation angles jitter by an ulp between calls and a keypoint at the 0.8-of-maximum threshold comes or goes, which
+reshuffles retainBest's order and with it the cv::RNG subsets.  Our keypoints and descriptors reproduce cv2's (tests/test_sift_gpu.py:
+100 %, descriptors exact), in KeyPoint_LessThan order rather than retainBest's, so the trajectory is held to the same kind of bar:
+median identical (< 1e-5 px), 97 % of the frames within north_star's 0.5 px, none beyond 1 px, stated drift bound on the absolute pose.
 """
 import zlib
 
