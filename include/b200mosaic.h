@@ -95,6 +95,14 @@ bm_status bm_estimate_frame(bm_handle h, const uint8_t* h_bgr, size_t stride_byt
 bm_status bm_clear_canvas(bm_handle h);
 /* `output_img = image` (callers of the reference may assign the attribute): replace the canvas by a host image, Hc x Wc x 3 BGR */
 bm_status bm_set_canvas(bm_handle h, const uint8_t* h_bgr);
+/* ---- canvas row tiles (config 5: a canvas sharded into row tiles over several GPUs).  The reference has no such mode (its blend,
+ * main.py:878-927, is global over the canvas); these four calls carry across tile boundaries exactly what that global blend needs, so
+ * that tiles reproduce the untiled canvas bit for bit: the sweep state of cv2.distanceTransform(mask_old) (main.py:889) entering a
+ * tile from the rows above / below, and the pixels of halo rows.  See real-time-video-mosaic_b200/sharding.py (TileGroup). ---- */
+bm_status bm_tile_set_ghost(bm_handle h, int side /*0 above, 1 below*/, const uint32_t* d_rows /*[3][canvas_w] or NULL = canvas border*/);
+bm_status bm_tile_export_carries(bm_handle h, int up, int block, uint32_t* d_out /*[3][canvas_w]*/);
+bm_status bm_tile_export_rect(bm_handle h, int x0, int y0, int w, int hgt, uint8_t* d_out_bgrx /* w * hgt * 4 bytes */);
+bm_status bm_tile_import_rect(bm_handle h, int x0, int y0, int w, int hgt, const uint8_t* d_in_bgrx);
 /* canvas as packed BGR into a DEVICE buffer (e.g. a torch tensor that NCCL then gathers) */
 bm_status bm_get_canvas_device(bm_handle h, uint8_t* d_bgr_out);
 /* output_img (uint8, Hc x Wc x 3): lazy D2H of the device canvas                     main.py:1632,1649 */

@@ -83,6 +83,10 @@ def load():
     _sig(lib, "bm_set_overlap", i, vp, i)
     _sig(lib, "bm_clear_canvas", i, vp)
     _sig(lib, "bm_get_canvas_device", i, vp, vp)
+    _sig(lib, "bm_tile_set_ghost", i, vp, i, vp)
+    _sig(lib, "bm_tile_export_carries", i, vp, i, i, vp)
+    _sig(lib, "bm_tile_export_rect", i, vp, i, i, i, i, vp)
+    _sig(lib, "bm_tile_import_rect", i, vp, i, i, i, i, vp)
     _sig(lib, "bm_timing_enable", i, vp, i)
     _sig(lib, "bm_timing_read", i, vp, dp, dp, ip, i)
     _sig(lib, "bm_kernel_launches", C.c_longlong)

@@ -83,6 +83,7 @@ struct bm_mosaic_s {
     int cur = 0;
     // canvas export
     uint8_t* d_canvas_bgr = nullptr;
+    uint32_t* d_ghost[2] = {nullptr, nullptr};             // row-tile mode: carries entering the canvas plane from the tile above / below, [3][ts]
     uint8_t* d_final = nullptr; size_t final_cap = 0;      // finalisation result (screen sized), allocated on first use
     int* d_bounds = nullptr;
     uint8_t* h_cstage[2] = {nullptr, nullptr};              // pinned staging of bm_get_canvas for pageable destinations
@@ -184,7 +185,7 @@ extern "C" bm_status bm_destroy(bm_handle m) {
         cudaFreeHost(m->h_stage[i]); cudaFree(m->d_bgr[i]); cudaFree(m->d_bgrx[i]); cudaFree(m->d_gray[i]);
         if (m->ev_h2d[i]) cudaEventDestroy(m->ev_h2d[i]);
     }
-    cudaFree(m->d_canvas_bgr); cudaFree(m->d_final); cudaFree(m->d_bounds);
+    cudaFree(m->d_canvas_bgr); cudaFree(m->d_final); cudaFree(m->d_bounds); cudaFree(m->d_ghost[0]); cudaFree(m->d_ghost[1]);
     bm_preview_free(&m->preview);
     for (int k = 0; k < 2; ++k) { if (m->h_cstage[k]) cudaFreeHost(m->h_cstage[k]); if (m->ev_cstage[k]) cudaEventDestroy(m->ev_cstage[k]); }
     for (int i = 0; i < bm_mosaic_s::kEvRing; ++i) { if (m->ev0[i]) cudaEventDestroy(m->ev0[i]); if (m->ev1[i]) cudaEventDestroy(m->ev1[i]); }
@@ -727,6 +728,65 @@ extern "C" bm_status bm_set_canvas(bm_handle m, const uint8_t* h_bgr) {
     BM_CUDA_OK(cudaMemcpy(m->d_canvas_bgr, h_bgr, n * 3, cudaMemcpyHostToDevice));
     BM_CUDA_OK(bm_launch_pack_canvas(m->d_canvas_bgr, m->blend.canvas, (int)n, m->s_chain));
     BM_CUDA_OK(bm_launch_full_rowscan(m->blend, m->s_chain));
+    BM_CUDA_OK(cudaStreamSynchronize(m->s_chain));
+    return BM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// canvas row tiles (config 5): the handle's canvas is one tile (+ halo rows) of a larger canvas; what crosses tile boundaries is
+// (a) the distance-transform sweep state at the tile's top / bottom edge and (b) the pixels of halo rows a neighbour changed
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_copy_rect(const uchar4* __restrict__ src, int src_stride, uchar4* __restrict__ dst, int dst_stride, int w, int h) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x < w && y < h) dst[(size_t)y * dst_stride + x] = src[(size_t)y * src_stride + x];
+}
+
+// side 0: the rows above the tile (downward sweeps enter through the top edge), 1: below.  d_rows: [3][canvas_w] u32 (E1, E2, V) as
+// exported by the neighbour, or NULL for "canvas border" (cv2's semantics: nothing beyond).
+extern "C" bm_status bm_tile_set_ghost(bm_handle m, int side, const uint32_t* d_rows) {
+    if (!m || side < 0 || side > 1) return BM_ERR_ARG;
+    BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+    BmDtPlane& p = m->blend.dt.p[0];
+    if (!d_rows) { (side ? p.gh_bot : p.gh_top) = nullptr; return BM_OK; }
+    if (!m->d_ghost[side]) BM_CUDA_OK(cudaMalloc(&m->d_ghost[side], (size_t)3 * p.ts * sizeof(uint32_t)));
+    for (int i = 0; i < 3; ++i)
+        BM_CUDA_OK(cudaMemcpyAsync(m->d_ghost[side] + (size_t)i * p.ts, d_rows + (size_t)i * p.W, (size_t)p.W * sizeof(uint32_t), cudaMemcpyDeviceToDevice, m->s_chain));
+    (side ? p.gh_bot : p.gh_top) = m->d_ghost[side];
+    BM_CUDA_OK(cudaStreamSynchronize(m->s_chain));          // the caller may reuse d_rows
+    return BM_OK;
+}
+
+// the carries a neighbouring tile needs: up == 0 -> downward sweeps at the LAST row of 16-row block `block` (for the tile below),
+// up == 1 -> upward sweeps at the FIRST row of `block` (for the tile above).  d_out: [3][canvas_w] u32.  Enqueued on the chain stream
+// (after every frame blended so far); bm_sync / a stream wait makes the result visible.
+extern "C" bm_status bm_tile_export_carries(bm_handle m, int up, int block, uint32_t* d_out) {
+    if (!m || !d_out) return BM_ERR_ARG;
+    BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+    BM_CUDA_OK(bm_launch_dt_export_carries(m->blend.dt.p[0], up ? 1 : 0, block, d_out, m->s_chain));
+    BM_CUDA_OK(cudaStreamSynchronize(m->s_chain));
+    return BM_OK;
+}
+
+// canvas rectangle (x0, y0, w, h) <-> a dense device buffer of w * h uchar4 (B, G, R, mask).  Import also refreshes the persistent
+// row seeds and block-local sweeps of the rows it touched, exactly like a blend does.
+extern "C" bm_status bm_tile_export_rect(bm_handle m, int x0, int y0, int w, int h, uint8_t* d_out_bgrx) {
+    if (!m || !d_out_bgrx || x0 < 0 || y0 < 0 || w <= 0 || h <= 0 || x0 + w > m->cfg.canvas_w || y0 + h > m->cfg.canvas_h) return BM_ERR_ARG;
+    BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+    BM_COUNT_LAUNCHES(1), k_copy_rect<<<dim3(bm_div_up(w, 256), h), 256, 0, m->s_chain>>>(m->blend.canvas + (size_t)y0 * m->cfg.canvas_w + x0, m->cfg.canvas_w,
+                                                                                        reinterpret_cast<uchar4*>(d_out_bgrx), w, w, h);
+    BM_CUDA_OK(cudaGetLastError());
+    BM_CUDA_OK(cudaStreamSynchronize(m->s_chain));
+    return BM_OK;
+}
+extern "C" bm_status bm_tile_import_rect(bm_handle m, int x0, int y0, int w, int h, const uint8_t* d_in_bgrx) {
+    if (!m || !d_in_bgrx || x0 < 0 || y0 < 0 || w <= 0 || h <= 0 || x0 + w > m->cfg.canvas_w || y0 + h > m->cfg.canvas_h) return BM_ERR_ARG;
+    BM_CUDA_OK(cudaSetDevice(m->cfg.device));
+    BM_COUNT_LAUNCHES(1), k_copy_rect<<<dim3(bm_div_up(w, 256), h), 256, 0, m->s_chain>>>(reinterpret_cast<const uchar4*>(d_in_bgrx), w,
+                                                                                        m->blend.canvas + (size_t)y0 * m->cfg.canvas_w + x0, m->cfg.canvas_w, w, h);
+    BM_CUDA_OK(cudaGetLastError());
+    const BmDtPlane& po = m->blend.dt.p[0];
+    BM_CUDA_OK(bm_launch_rowscan_bgrx(m->blend.canvas, m->cfg.canvas_w, 0, y0, po, y0, h, m->blend.flags, 0, m->s_chain));
+    BM_CUDA_OK(bm_launch_dt_local(po, y0 / BM_BLK_ROWS, bm_div_up(y0 + h, BM_BLK_ROWS), m->blend.flags, 0, m->s_chain));
     BM_CUDA_OK(cudaStreamSynchronize(m->s_chain));
     return BM_OK;
 }

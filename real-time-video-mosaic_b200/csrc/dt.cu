@@ -111,10 +111,18 @@ __device__ __forceinline__ void dt_step(u32 (&E1)[4], u32 (&E2)[4], const u32 (&
 __device__ __forceinline__ void dt_fill(u32 (&v)[4], u32 x) { v[0] = v[1] = v[2] = v[3] = x; }
 
 // 4 carry values of table row `k` at columns [cx, cx+4); BM_DT_INF outside the plane / block range
-__device__ __forceinline__ void dt_carry4(const u32* __restrict__ tab, const BmDtPlane& p, int k, int cx, u32 (&o)[4]) {
+// `kind`: 0 = E1, 1 = E2, 2 = V -- selects the row of the plane's ghost carries used when k is the block just outside the plane
+__device__ __forceinline__ void dt_carry4(const u32* __restrict__ tab, const BmDtPlane& p, int k, int cx, u32 (&o)[4], int kind) {
     dt_fill(o, BM_DT_INF);
-    if (k < 0 || k >= p.nb || cx < 0 || cx >= p.W) return;
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(tab + (size_t)k * p.ts + cx));
+    if (cx < 0 || cx >= p.W) return;
+    const u32* row;
+    if (k >= 0 && k < p.nb) row = tab + (size_t)k * p.ts;
+    else {
+        const u32* gh = k < 0 ? p.gh_top : p.gh_bot;
+        if (gh == nullptr || (k != -1 && k != p.nb)) return;
+        row = gh + (size_t)kind * p.ts;
+    }
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + cx));
     o[0] = v.x;
     if (cx + 1 < p.W) o[1] = v.y;
     if (cx + 2 < p.W) o[2] = v.z;
@@ -168,6 +176,20 @@ __global__ void __launch_bounds__(128) k_dt_local(BmDtPlane p, int kb0, const in
 
 __device__ __forceinline__ u32 dt_add_sat(u32 c, u32 d) { return c > BM_DT_INF - d ? BM_DT_INF : c + d; }
 
+// carry entering a diagonal line from outside the plane: the line's first block (j = 0) sits at column x0, its predecessor in the
+// neighbouring tile at column x0 - dx of the ghost row (E1 for the lines flowing right, E2 for those flowing left)
+__device__ __forceinline__ u32 dt_ghost_diag(const BmDtPlane& p, int type, int x0, int dx) {
+    const u32* gh = type < 2 ? p.gh_top : p.gh_bot;
+    const int xg = x0 - dx;
+    if (gh == nullptr || x0 < 0 || x0 >= p.W || xg < 0 || xg >= p.W) return BM_DT_INF;
+    return __ldg(gh + (size_t)(type & 1) * p.ts + xg);
+}
+__device__ __forceinline__ u32 dt_ghost_vert(const BmDtPlane& p, bool down, int x) {
+    const u32* gh = down ? p.gh_top : p.gh_bot;
+    if (gh == nullptr || x < 0 || x >= p.W) return BM_DT_INF;
+    return __ldg(gh + (size_t)2 * p.ts + x);
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // phase 2: diagonal carries.  type 0: down, from x-16; 1: down, from x+16; 2: up, from x-16; 3: up, from x+16
 // ------------------------------------------------------------------------------------------------------------------
@@ -182,7 +204,7 @@ __global__ void __launch_bounds__(128) k_dt_diag_chain(BmDtPair pp, const int* _
     const int x0 = right ? t - 16 * (p.nb - 1) : t, dx = right ? 16 : -16;
     const u32* __restrict__ L = p.LE + (size_t)type * p.tsz;
     u32* __restrict__ C = p.CE + (size_t)type * p.tsz;
-    u32 c = BM_DT_INF;
+    u32 c = dt_ghost_diag(p, type, x0, dx);
     // the loads do not depend on the chain: issue DT_CHAIN_BATCH of them at once, then walk
     for (int j0 = 0; j0 < p.nb; j0 += DT_CHAIN_BATCH) {
         u32 v[DT_CHAIN_BATCH];
@@ -204,9 +226,9 @@ __global__ void __launch_bounds__(128) k_dt_diag_chain(BmDtPair pp, const int* _
 // line is cut into segments of 8 blocks handled by one thread each: local chain, segment ends exchanged through shared
 // memory, carry of all earlier segments applied.  CTA = 16 lines x nseg segments (lanes walk lines: 64-byte rows).
 // A line's in-plane elements are contiguous in j, so a finite segment end always reaches the following elements.
-#define DT_SEG 8
-template <class Addr>
-__device__ __forceinline__ void dt_chain_seg(const u32* __restrict__ L, u32* __restrict__ C, int nb, u32 K, Addr addr) {
+// SEG = 8 blocks per thread serves planes of up to 256 blocks (4096 rows), SEG = 32 up to 1024 blocks (the extended row tiles of config 5)
+template <int DT_SEG, class Addr>
+__device__ __forceinline__ void dt_chain_seg(const u32* __restrict__ L, u32* __restrict__ C, int nb, u32 K, Addr addr, u32 gin) {
     __shared__ u32 E[32][17];
     const int ll = threadIdx.x & 15, sg = threadIdx.x >> 4;
     const int j0 = sg * DT_SEG;
@@ -222,13 +244,14 @@ __device__ __forceinline__ void dt_chain_seg(const u32* __restrict__ L, u32* __r
     for (int u = 0; u < DT_SEG; ++u) { c = idx[u] >= 0 ? min(loc[u], dt_add_sat(c, K)) : BM_DT_INF; loc[u] = c; }
     E[sg][ll] = c;
     __syncthreads();
-    u32 cin = BM_DT_INF;                                   // carry at the last element of segment sg-1
+    u32 cin = gin;                                         // carry at the last element of segment sg-1 (gin: entering from outside the plane)
     for (int s2 = 0; s2 < sg; ++s2) cin = min(E[s2][ll], dt_add_sat(cin, DT_SEG * K));      // Horner form of the prefix minimum
 #pragma unroll
     for (int u = 0; u < DT_SEG; ++u)
         if (idx[u] >= 0) C[idx[u]] = min(loc[u], dt_add_sat(cin, (u32)(u + 1) * K));
 }
 
+template <int DT_SEG>
 __global__ void __launch_bounds__(512) k_dt_diag_chain16(BmDtPair pp, const int* __restrict__ flags, int need_flag) {
     if (need_flag && flags[0] == 0) return;
     const BmDtPlane& p = pp.p[blockIdx.z];
@@ -239,12 +262,13 @@ __global__ void __launch_bounds__(512) k_dt_diag_chain16(BmDtPair pp, const int*
     const bool right = (type & 1) == 0, down = type < 2;
     const int x0 = right ? t - 16 * (p.nb - 1) : t, dx = right ? 16 : -16;
     const int nb = p.nb, W = p.W, ts = p.ts;
-    dt_chain_seg(p.LE + (size_t)type * p.tsz, p.CE + (size_t)type * p.tsz, nb, 16u * B_, [=](int j) -> int {
+    dt_chain_seg<DT_SEG>(p.LE + (size_t)type * p.tsz, p.CE + (size_t)type * p.tsz, nb, 16u * B_, [=](int j) -> int {
         const int x = x0 + dx * j, k = down ? j : nb - 1 - j;
         return (t < nlines && x >= 0 && x < W) ? k * ts + x : -1;
-    });
+    }, t < nlines ? dt_ghost_diag(p, type, x0, dx) : BM_DT_INF);
 }
 
+template <int DT_SEG>
 __global__ void __launch_bounds__(512) k_dt_vert_chain16(BmDtPair pp, DtRange rg, const int* __restrict__ flags, int need_flag) {
     if (need_flag && flags[0] == 0) return;
     const int pl = blockIdx.z;
@@ -254,7 +278,7 @@ __global__ void __launch_bounds__(512) k_dt_vert_chain16(BmDtPair pp, DtRange rg
     const bool ok = x < rg.xb[pl] && x < p.W, down = blockIdx.y == 0;
     const int nb = p.nb, ts = p.ts;
     u32* C = p.CV + (size_t)blockIdx.y * p.tsz;
-    dt_chain_seg(C, C, nb, 16u * A_, [=](int j) -> int { return ok ? (down ? j : nb - 1 - j) * ts + x : -1; });
+    dt_chain_seg<DT_SEG>(C, C, nb, 16u * A_, [=](int j) -> int { return ok ? (down ? j : nb - 1 - j) * ts + x : -1; }, ok ? dt_ghost_vert(p, down, x) : BM_DT_INF);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -273,8 +297,8 @@ __global__ void __launch_bounds__(128) k_dt_vert_local(BmDtPair pp, DtRange rg, 
     DtRows R;
     dt_load_rows(p, k, cx, up, R);
     u32 E1[4], E2[4], V[4];
-    dt_carry4(p.CE + (up ? 2 : 0) * p.tsz, p, up ? k + 1 : k - 1, cx, E1);
-    dt_carry4(p.CE + (up ? 3 : 1) * p.tsz, p, up ? k + 1 : k - 1, cx, E2);
+    dt_carry4(p.CE + (up ? 2 : 0) * p.tsz, p, up ? k + 1 : k - 1, cx, E1, 0);
+    dt_carry4(p.CE + (up ? 3 : 1) * p.tsz, p, up ? k + 1 : k - 1, cx, E2, 1);
     dt_fill(V, BM_DT_INF);
     dt_sweep<true>(R, E1, E2, V, lane, DtNoRow());
     if (dt_lane_valid(lane) && cx < xb && cx < p.W) dt_store4(p.CV + (up ? 1 : 0) * p.tsz, p, k, cx, V);
@@ -291,7 +315,7 @@ __global__ void __launch_bounds__(128) k_dt_vert_chain(BmDtPair pp, DtRange rg, 
     if (x >= rg.xb[pl] || x >= p.W) return;
     const bool down = blockIdx.y == 0;
     u32* __restrict__ C = p.CV + (size_t)blockIdx.y * p.tsz;
-    u32 c = BM_DT_INF;
+    u32 c = dt_ghost_vert(p, down, x);
     for (int j0 = 0; j0 < p.nb; j0 += DT_CHAIN_BATCH) {
         u32 v[DT_CHAIN_BATCH];
 #pragma unroll
@@ -316,9 +340,9 @@ __device__ __forceinline__ void dt_sweep_to_smem(const BmDtPlane& p, int k, int 
     DtRows R;
     dt_load_rows(p, k, cx, up, R);
     u32 E1[4], E2[4], V[4];
-    dt_carry4(p.CE + (up ? 2 : 0) * p.tsz, p, up ? k + 1 : k - 1, cx, E1);
-    dt_carry4(p.CE + (up ? 3 : 1) * p.tsz, p, up ? k + 1 : k - 1, cx, E2);
-    dt_carry4(p.CV + (up ? 1 : 0) * p.tsz, p, up ? k + 1 : k - 1, cx, V);
+    dt_carry4(p.CE + (up ? 2 : 0) * p.tsz, p, up ? k + 1 : k - 1, cx, E1, 0);
+    dt_carry4(p.CE + (up ? 3 : 1) * p.tsz, p, up ? k + 1 : k - 1, cx, E2, 1);
+    dt_carry4(p.CV + (up ? 1 : 0) * p.tsz, p, up ? k + 1 : k - 1, cx, V, 2);
     auto put = [&](int i, const u32 (&v)[4]) {
         const int r = up ? BM_BLK_ROWS - 1 - i : i;
         *reinterpret_cast<uint4*>(&T[r][4 * lane]) = make_uint4(v[0], v[1], v[2], v[3]);
@@ -375,7 +399,7 @@ __global__ void __launch_bounds__(128) k_dt_weights(BmDtPair pp, BmFramePlan pla
 // host side
 // ------------------------------------------------------------------------------------------------------------------
 cudaError_t bm_dt_alloc_plane(BmDtPlane* p, int Wcap, int Hcap, size_t px_cap) {
-    memset(p, 0, sizeof(*p));
+    memset(p, 0, sizeof(*p));                             // (gh_top / gh_bot = nullptr: image border)
     // any live shape (W, H) with W <= Wcap, H <= Hcap, W*H <= px_cap must fit
     p->g_cap = px_cap + (size_t)8 * Hcap + 64;
     const size_t tsz = ((px_cap / BM_BLK_ROWS + (size_t)2 * (Wcap + 8) + (size_t)Hcap + 64) + 3) & ~(size_t)3;
@@ -439,12 +463,15 @@ cudaError_t bm_launch_dt_carries(const BmDtPair& pp, int nplanes, const int xa[2
     }
     if (max_nb == 0 || max_cols <= 0) return cudaSuccess;
     // segment-parallel chains (table index fits 32 bits); longer lines fall back to one thread per line
-    const bool par = max_nb <= 256 && pp.p[0].tsz < ((size_t)1 << 31) && pp.p[1].tsz < ((size_t)1 << 31);
-    const int chain_threads = 32 * bm_div_up(bm_div_up(max_nb, DT_SEG), 2);     // 16 lines x ceil(nb / 8) segments
-    if (par) BM_COUNT_LAUNCHES(1), k_dt_diag_chain16<<<dim3(bm_div_up(max_lines, 16), 4, nplanes), chain_threads, 0, s>>>(pp, flags, need_flag);
+    const bool par = max_nb <= 1024 && pp.p[0].tsz < ((size_t)1 << 31) && pp.p[1].tsz < ((size_t)1 << 31);
+    const int seg = max_nb <= 256 ? 8 : 32;
+    const int chain_threads = 32 * bm_div_up(bm_div_up(max_nb, seg), 2);        // 16 lines x ceil(nb / seg) segments
+    if (par && seg == 8) BM_COUNT_LAUNCHES(1), k_dt_diag_chain16<8><<<dim3(bm_div_up(max_lines, 16), 4, nplanes), chain_threads, 0, s>>>(pp, flags, need_flag);
+    else if (par) BM_COUNT_LAUNCHES(1), k_dt_diag_chain16<32><<<dim3(bm_div_up(max_lines, 16), 4, nplanes), chain_threads, 0, s>>>(pp, flags, need_flag);
     else BM_COUNT_LAUNCHES(1), k_dt_diag_chain<<<dim3(bm_div_up(max_lines, 128), 4, nplanes), 128, 0, s>>>(pp, flags, need_flag);
     BM_COUNT_LAUNCHES(1), k_dt_vert_local<<<dim3(bm_div_up(max_tiles, 2), max_nb, nplanes), 128, 0, s>>>(pp, rg, flags, need_flag);
-    if (par) BM_COUNT_LAUNCHES(1), k_dt_vert_chain16<<<dim3(bm_div_up(max_cols, 16), 2, nplanes), chain_threads, 0, s>>>(pp, rg, flags, need_flag);
+    if (par && seg == 8) BM_COUNT_LAUNCHES(1), k_dt_vert_chain16<8><<<dim3(bm_div_up(max_cols, 16), 2, nplanes), chain_threads, 0, s>>>(pp, rg, flags, need_flag);
+    else if (par) BM_COUNT_LAUNCHES(1), k_dt_vert_chain16<32><<<dim3(bm_div_up(max_cols, 16), 2, nplanes), chain_threads, 0, s>>>(pp, rg, flags, need_flag);
     else BM_COUNT_LAUNCHES(1), k_dt_vert_chain<<<dim3(bm_div_up(max_cols, 128), 2, nplanes), 128, 0, s>>>(pp, rg, flags, need_flag);
     return cudaGetLastError();
 }
@@ -453,6 +480,18 @@ cudaError_t bm_launch_dt_weights(const BmDtPair& pp, const BmFramePlan& plan, fl
     const int nyb = (plan.reg.y1 - 1) / BM_BLK_ROWS - plan.reg.y0 / BM_BLK_ROWS + 1;
     BM_COUNT_LAUNCHES(1), k_dt_weights<<<dim3(dt_tiles(plan.reg.x1 - plan.rx0), nyb), 128, 0, s>>>(pp, plan, wn, wo, flags);
     return cudaGetLastError();
+}
+
+cudaError_t bm_launch_dt_export_carries(const BmDtPlane& p, int up, int block, uint32_t* d_out, cudaStream_t s) {
+    if (block < 0 || block >= p.nb) return cudaErrorInvalidValue;
+    BmDtPair pp; pp.p[0] = p; pp.p[1] = p;
+    const int xa[2] = {0, 0}, xb[2] = {p.W, p.W};
+    cudaError_t e = bm_launch_dt_carries(pp, 1, xa, xb, nullptr, 0, s);
+    if (e != cudaSuccess) return e;
+    const uint32_t* src[3] = {p.CE + (size_t)(up ? 2 : 0) * p.tsz, p.CE + (size_t)(up ? 3 : 1) * p.tsz, p.CV + (size_t)(up ? 1 : 0) * p.tsz};
+    for (int i = 0; i < 3 && e == cudaSuccess; ++i)
+        e = cudaMemcpyAsync(d_out + (size_t)i * p.W, src[i] + (size_t)block * p.ts, (size_t)p.W * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s);
+    return e;
 }
 
 cudaError_t bm_launch_dt_map(const BmDtPlane& p, float* d_out, cudaStream_t s) {

@@ -26,6 +26,11 @@ struct BmDtPlane {
     uint32_t* CE;       // [4][tsz] the same with the carries of all blocks above / below
     uint32_t* CV;       // [2][tsz] vertical sweep at the block's last row (down) / first row (up); local, then with carries
     size_t g_cap;      // capacity of g in elements (for bm_dt_shape_plane)
+    // Row tiles of a larger canvas: sweep state entering the plane from the rows above / below it, i.e. the
+    // carries a neighbouring tile's plane holds at the adjoining block boundary.  [3][ts]: E1, E2, V.  nullptr = image border (no
+    // zero pixel beyond: BM_DT_INF, cv2's semantics at the canvas edge).
+    const uint32_t* gh_top;   // downward sweeps: values at the row just above row 0
+    const uint32_t* gh_bot;   // upward sweeps: values at the row just below row H - 1
 };
 
 struct BmDtPair { BmDtPlane p[2]; };   // [0] = canvas (mask_old), [1] = window (mask_new)
@@ -47,5 +52,8 @@ cudaError_t bm_launch_dt_carries(const BmDtPair& pp, int nplanes, const int xa[2
                                  cudaStream_t s);
 // (dn/s, do/s) over R (main.py:888-894) -> two float planes with origin (plan.rx0, plan.reg.y0) and row stride plan.rws
 cudaError_t bm_launch_dt_weights(const BmDtPair& pp, const BmFramePlan& plan, float* wn, float* wo, const int* flags, cudaStream_t s);
+// canvas-plane carries over the full width, then the three carry rows (E1, E2, V) a neighbouring tile needs: downward sweeps at the
+// last row of block `block` (up == 0) or upward sweeps at the first row of block `block` (up == 1) -> d_out [3][p.W]
+cudaError_t bm_launch_dt_export_carries(const BmDtPlane& p, int up, int block, uint32_t* d_out, cudaStream_t s);
 // plain distance map of one plane (stage entry bm_distance_transform)
 cudaError_t bm_launch_dt_map(const BmDtPlane& p, float* d_out, cudaStream_t s);

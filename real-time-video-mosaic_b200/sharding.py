@@ -209,6 +209,201 @@ def fixup_skipped(frames, rel, detector_type="sift", device=0):
     return rel
 
 
+def frame_window(H, frame_w, frame_h):
+    """conservative integer bounding box (x0, y0, x1, y1), half open, of the warped frame quad on the full canvas (+-4 px slack);
+    every process computes the same box from the same H, which is what keeps the tile protocol below in lock step"""
+    c = np.array([[-1, -1, 1], [frame_w, -1, 1], [frame_w, frame_h, 1], [-1, frame_h, 1]], np.float64).T
+    q = np.asarray(H, np.float64) @ c
+    if np.any(q[2] <= 1e-9):
+        raise ValueError("frame_window: homography sends a frame corner to infinity")
+    x, y = q[0] / q[2], q[1] / q[2]
+    return int(np.floor(x.min())) - 4, int(np.floor(y.min())) - 4, int(np.ceil(x.max())) + 5, int(np.ceil(y.max())) + 5
+
+
+class TileGroup:
+    """config 5: a (Wc, Hc) canvas cut into `world` row tiles that reproduce the UNTILED canvas bit for bit.
+
+    Tile g owns rows [y0_g, y1_g) and keeps an extended local canvas [y0_g - P, y1_g + P) (P = halo_rows): a frame that touches a
+    tile's own rows lies entirely inside the extended canvas, so warpPerspective, mask_new and cv2.distanceTransform(mask_new)
+    (main.py:871-888) are computed locally exactly as on the full canvas.  cv2.distanceTransform(mask_old) (main.py:889) is global
+    over the canvas; its sweeps are continued across tile boundaries: the downward sweep state (E1, E2, V per column, see dt.cu) at
+    the row just above a tile's extended canvas comes from the tile above, the upward state from the tile below (bm_tile_export_carries
+    -> bm_tile_set_ghost, 3 x Wc x 4 bytes per hop).  They are refreshed LAZILY: every process tracks, from the frames' windows alone,
+    which boundary states are out of date, and a hop (or a chain of hops through unchanged tiles) only happens when a tile is about to
+    blend and something above / below it has changed since.  Halo rows changed by a neighbour that did not blend the frame itself are
+    copied over (bm_tile_export_rect -> bm_tile_import_rect).  A camera that stays inside one tile needs no communication at all.
+
+    `local_tiles`: the tiles this process holds -- [rank] in a distributed run (one tile per rank, NCCL send / recv between
+    neighbours), all of them in a single-process run (tests: the same protocol with device-to-device copies)."""
+
+    exchange = True
+
+    def __init__(self, frame0, canvas_w, canvas_h, world, local_tiles, halo_rows, dist=None, device=0):
+        import torch
+        from .mosaic import VideMosaic
+        self.torch, self.dist, self.G = torch, dist, int(world)
+        self.Wc, self.Hc = int(canvas_w), int(canvas_h)
+        self.fh, self.fw = frame0.shape[:2]
+        self.P = int(halo_rows)
+        if self.P % 16:
+            raise ValueError("halo_rows must be a multiple of 16 (the block grid of the distance-transform tables)")
+        self.own = [tile_rows(self.Hc, g, self.G) for g in range(self.G)]
+        T = min(y1 - y0 for y0, y1 in self.own[:-1]) if self.G > 1 else self.Hc
+        if self.G > 1 and self.P > T - 16:
+            raise ValueError(f"halo_rows {self.P} must be <= tile height - 16 = {T - 16}: a halo may only reach into the adjacent tile")
+        self.ext = [(max(0, y0 - self.P), min(self.Hc, y1 + self.P)) if self.G > 1 else (0, self.Hc) for y0, y1 in self.own]
+        self.local = {}
+        for g in local_tiles:
+            Y0, Y1 = self.ext[g]
+            vm = VideMosaic(frame0, detector_type="orb", show_intermediate=False, visualize=False, canvas_size=(Y1 - Y0, self.Wc), device=device)
+            vm.clear_canvas()
+            self.local[g] = vm
+        # boundary sweep states: stale_down[k] = "ghost_top of tile k+1 does not reflect the current canvas above it", stale_up[k] likewise
+        # for ghost_bot of tile k-1.  Everything is stale at the start (an empty canvas above is all zero pixels, not a border).
+        self.stale_down = [True] * self.G
+        self.stale_up = [True] * self.G
+        self.hops = 0
+        self.rect_bytes = 0
+        if dist is not None and self.G > 1:                    # open the neighbour channels now (NCCL sets P2P connections up on first use)
+            t = torch.zeros(8, dtype=torch.int32, device="cuda")
+            ops = []
+            for g in self.local:
+                for n in (g - 1, g + 1):
+                    if 0 <= n < self.G and n not in self.local:
+                        ops.append(dist.P2POp(dist.isend, t, n))
+                        ops.append(dist.P2POp(dist.irecv, torch.empty_like(t), n))
+            if ops:
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+            torch.cuda.synchronize()
+
+    # ---- transport: tile a -> tile b; every process walks the same sequence of calls ------------------------------------------
+    def _xfer(self, a, b, make, consume, shape, dtype):
+        torch = self.torch
+        if a in self.local and b in self.local:
+            consume(make())
+        elif a in self.local:
+            t = make()
+            torch.cuda.current_stream().synchronize()
+            self.dist.send(t, dst=b)
+        elif b in self.local:
+            t = torch.empty(shape, dtype=dtype, device="cuda")
+            self.dist.recv(t, src=a)
+            torch.cuda.current_stream().synchronize()
+            consume(t)
+
+    def _export_carries(self, g, up, block):
+        import ctypes as C
+        from . import _lib
+        vm = self.local[g]
+        t = self.torch.empty((3, self.Wc), dtype=self.torch.int32, device="cuda")
+        _lib.check(vm._lib.bm_tile_export_carries(vm._h, int(up), int(block), C.c_void_p(t.data_ptr())), "bm_tile_export_carries")
+        return t
+
+    def _set_ghost(self, g, side, t):
+        import ctypes as C
+        from . import _lib
+        vm = self.local[g]
+        _lib.check(vm._lib.bm_tile_set_ghost(vm._h, int(side), C.c_void_p(t.data_ptr()) if t is not None else None), "bm_tile_set_ghost")
+
+    def _refresh_down(self, k):
+        """ghost_top of tile k + 1 <- downward sweep state of tile k at the row just above tile k + 1's extended canvas"""
+        if k < 0 or k >= self.G - 1 or not self.stale_down[k]:
+            return
+        self._refresh_down(k - 1)                               # tile k's own incoming state first
+        block = (self.ext[k + 1][0] - self.ext[k][0]) // 16 - 1
+        self._xfer(k, k + 1, lambda: self._export_carries(k, 0, block), lambda t: self._set_ghost(k + 1, 0, t), (3, self.Wc), self.torch.int32)
+        self.stale_down[k] = False
+        self.hops += 1
+
+    def _refresh_up(self, k):
+        """ghost_bot of tile k - 1 <- upward sweep state of tile k at the row just below tile k - 1's extended canvas"""
+        if k <= 0 or k > self.G - 1 or not self.stale_up[k]:
+            return
+        if self.ext[k - 1][1] >= self.Hc:                       # tile k - 1's extended canvas reaches the canvas bottom: border
+            self.stale_up[k] = False
+            return
+        self._refresh_up(k + 1)
+        block = (self.ext[k - 1][1] - self.ext[k][0]) // 16
+        self._xfer(k, k - 1, lambda: self._export_carries(k, 1, block), lambda t: self._set_ghost(k - 1, 1, t), (3, self.Wc), self.torch.int32)
+        self.stale_up[k] = False
+        self.hops += 1
+
+    def _copy_rect(self, g, n, x0, ya, w, h):
+        import ctypes as C
+        from . import _lib
+        torch = self.torch
+
+        def make():
+            vm = self.local[g]
+            t = torch.empty((h, w, 4), dtype=torch.uint8, device="cuda")
+            _lib.check(vm._lib.bm_tile_export_rect(vm._h, x0, ya - self.ext[g][0], w, h, C.c_void_p(t.data_ptr())), "bm_tile_export_rect")
+            return t
+
+        def consume(t):
+            vm = self.local[n]
+            _lib.check(vm._lib.bm_tile_import_rect(vm._h, x0, ya - self.ext[n][0], w, h, C.c_void_p(t.data_ptr())), "bm_tile_import_rect")
+            vm._canvas_cache = None
+        self._xfer(g, n, make, consume, (h, w, 4), torch.uint8)
+        self.rect_bytes += h * w * 4
+
+    def put(self, frame, H):
+        """VideMosaic.warp(frame, H) (main.py:861-927) on the tiled canvas; H is the absolute canvas homography.  Returns how many of
+        this process's tiles blended the frame."""
+        xa, wa, xb, wb = frame_window(H, self.fw, self.fh)
+        wa, wb = max(wa, 0), min(wb, self.Hc)
+        xa, xb = max(xa, 0), min(xb, self.Wc)
+        if wa >= wb or xa >= xb:
+            return 0
+        S = [g for g in range(self.G) if self.own[g][0] < wb and self.own[g][1] > wa]
+        for g in S:
+            if self.ext[g][0] > wa or self.ext[g][1] < wb:
+                raise ValueError(f"frame rows [{wa},{wb}) leave the extended canvas {self.ext[g]} of tile {g}: halo_rows = {self.P} is too small")
+        for g in S:                                             # the boundary states the blending tiles need, refreshed if out of date
+            self._refresh_down(g - 1)
+            self._refresh_up(g + 1)
+        done = 0
+        for g in S:
+            if g in self.local:
+                self.local[g].warp_nosync(frame, tile_homography(H, self.ext[g][0]))
+                done += 1
+        for g in S:                                             # halo rows of neighbours that did not blend this frame themselves
+            for n in (g - 1, g + 1):
+                if n < 0 or n >= self.G or n in S:
+                    continue
+                ya, yb = max(wa, self.own[g][0], self.ext[n][0]), min(wb, self.own[g][1], self.ext[n][1])
+                if ya < yb:
+                    self._copy_rect(g, n, xa, ya, xb - xa, yb - ya)
+        for k in range(self.G - 1):                             # rows [wa, wb) changed: which exported states they feed
+            if self.ext[k + 1][0] - 1 >= wa:
+                self.stale_down[k] = True
+        for k in range(1, self.G):
+            if self.ext[k - 1][1] < wb:
+                self.stale_up[k] = True
+        return done
+
+    def sync(self):
+        for vm in self.local.values():
+            vm.sync()
+
+    def tile_tensor(self, g=None):
+        """own rows of tile g (default: this process's only tile) as a packed-BGR uint8 cuda tensor"""
+        torch = self.torch
+        if g is None:
+            (g,) = self.local.keys()
+        vm = self.local[g]
+        Y0, Y1 = self.ext[g]
+        t = torch.empty((Y1 - Y0, self.Wc, 3), dtype=torch.uint8, device="cuda")
+        vm.canvas_to_device(t.data_ptr())
+        y0, y1 = self.own[g]
+        return t[y0 - Y0:y1 - Y0].contiguous()
+
+    def close(self):
+        for vm in self.local.values():
+            vm.close()
+        self.local = {}
+
+
 class TileStitcher:
     """config 5: this rank's row tile of a (Wc, Hc) canvas.  `put(frame, H)` warps + blends the frame into the tile if its window
     touches the tile's rows (H is the absolute canvas homography, shifted here by the tile origin); `tile_tensor()` returns the

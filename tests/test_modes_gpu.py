@@ -252,3 +252,65 @@ def test_kp_cur_des_cur_and_output_img_setter():
     vm.stabilization_enabled = False
     vm.process_frame(f1, 2)
     assert len(vm.homography_history) == 1                               # smooth_homography returns before appending (:812-816)
+
+
+def _tile_path(n_up=30, n_down=10, Wc=448, Hc=1024, fw=320, fh=180):
+    """camera poses: from the canvas bottom up across every tile boundary with a sideways weave and +-3 degrees of rotation, then
+    part of the way back down (revisits: boundary states go stale in both directions)"""
+    ys = [Hc - fh - 6 - 25.0 * t for t in range(n_up)] + [Hc - fh - 6 - 25.0 * (n_up - 1) + 31.0 * t for t in range(1, n_down + 1)]
+    Hs = []
+    for t, y in enumerate(ys):
+        ang = np.deg2rad(3.0 * np.sin(t / 4.0))
+        c, s = np.cos(ang), np.sin(ang)
+        R = np.array([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]])
+        C = np.array([[1, 0, fw / 2], [0, 1, fh / 2], [0, 0, 1.0]])
+        T = np.eye(3); T[0, 2] = (Wc - fw) / 2 + 40.0 * np.sin(t / 3.0); T[1, 2] = y
+        Hs.append(T @ C @ R @ np.linalg.inv(C))
+    return Hs
+
+
+def test_row_tiles_with_boundary_exchange_equal_untiled_canvas():
+    """four row tiles, frames that STRADDLE every tile boundary (and come back), frames with black holes.  With
+    the sweep-state hand-over and the halo copies of sharding.TileGroup the assembled tiles equal the untiled canvas bit for bit
+    ('a frame straddling a tile boundary blends differently from the untiled canvas = parity failure by design')."""
+    import b200mosaic
+    from b200mosaic import sharding as sh
+    from b200mosaic.synth import DroneSweep
+    fw, fh, Wc, Hc = 320, 180, 448, 1024
+    Hs = _tile_path(Wc=Wc, Hc=Hc, fw=fw, fh=fh)
+    base = DroneSweep(fw, fh, seed=5, ground_size=1024, max_step=6.0).frames(8)
+    frames = []
+    for t in range(len(Hs)):
+        f = base[t % len(base)].copy()
+        f[20 + 5 * (t % 7):44 + 5 * (t % 7), 30 + 11 * (t % 9):90 + 11 * (t % 9)] = 0      # holes in mask_new / mask_old
+        if t % 5 == 0:
+            f[:, 150:153] = 0                                                              # a black line from edge to edge
+        frames.append(f)
+    full = b200mosaic.VideMosaic(frames[0], detector_type="orb", show_intermediate=False, visualize=False, canvas_size=(Hc, Wc))
+    full.clear_canvas()
+    for f, H in zip(frames, Hs):
+        full.warp_nosync(f, H)
+    want = full.output_img.copy()
+    tg = sh.TileGroup(frames[0], Wc, Hc, world=4, local_tiles=[0, 1, 2, 3], halo_rows=208)
+    touched = 0
+    for f, H in zip(frames, Hs):
+        touched += tg.put(f, H)
+    tg.sync()
+    got = torch.cat([tg.tile_tensor(g) for g in range(4)], dim=0).cpu().numpy()
+    assert got.shape == want.shape
+    assert touched > len(frames) + 8                       # many frames were blended by two tiles
+    assert tg.hops >= 6 and tg.rect_bytes > 0              # sweep states crossed boundaries, halo rows were copied
+    d = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    assert np.array_equal(got, want), (int(d.max()), int((d > 0).sum()), sorted(set((np.nonzero(d.max(axis=(1, 2)))[0] // 256).tolist())))
+    # and the exchange matters: tiles that ignore their neighbours (the round-1 mode) do differ on this path
+    plain = []
+    for g in range(4):
+        y0, y1 = sh.tile_rows(Hc, g, 4)
+        vm = b200mosaic.VideMosaic(frames[0], detector_type="orb", show_intermediate=False, visualize=False, canvas_size=(y1 - y0, Wc))
+        vm.clear_canvas()
+        for f, H in zip(frames, Hs):
+            if sh.touches_tile(H, fw, fh, y0, y1):
+                vm.warp_nosync(f, sh.tile_homography(H, y0))
+        plain.append(vm.output_img.copy())
+    assert not np.array_equal(np.concatenate(plain, axis=0), want)
+    tg.close()

@@ -154,7 +154,9 @@ def run_tiles(ctx, frames=48, warmup=3, size="3840x2160", canvas="16384x16384"):
         R = np.array([[np.cos(ang), -np.sin(ang), 0.0], [np.sin(ang), np.cos(ang), 0.0], [0.0, 0.0, 1.0]])
         T = np.eye(3); T[0, 2] = Wc / 2 - w / 2 + 0.05 * Wc * np.sin(t / 5.0); T[1, 2] = (Hc - h - 8) * (1.0 - t / max(n - 1, 1)) + 4
         Hs.append(T @ R)
-    tiler = sh.TileStitcher(fr[0], Wc, Hc, ctx.rank, ctx.world, ctx.dist, device=ctx.local)
+    # halo: the tallest warped frame (+-2 degrees of rotation) + slack, a multiple of 16 rows
+    halo = -(-int(h * np.cos(np.deg2rad(2.0)) + w * np.sin(np.deg2rad(2.0)) + 40) // 16) * 16
+    tiler = sh.TileGroup(fr[0], Wc, Hc, ctx.world, [ctx.rank], halo, ctx.dist, device=ctx.local)
     for t in range(0, warmup + 1):
         tiler.put(fr[t], Hs[t])
     tiler.sync()
@@ -168,6 +170,7 @@ def run_tiles(ctx, frames=48, warmup=3, size="3840x2160", canvas="16384x16384"):
     torch.cuda.synchronize()
     dt = ctx.max_over_ranks(time.perf_counter() - t0)
     nbytes = int(full.numel())
+    hops, rect_bytes = tiler.hops, tiler.rect_bytes
     del full, tile
     tiler.close()
     return {"mode": "tiles", "scaling": "strong",
@@ -176,7 +179,7 @@ def run_tiles(ctx, frames=48, warmup=3, size="3840x2160", canvas="16384x16384"):
             "config": {"workload": f"{w}x{h} frames, tile rows [{y0},{y1}) on rank 0, {mine} of {frames} frames touch it",
                        "warp_blend_fps": frames / t_warp, "gather_ms": 1e3 * (dt - t_warp), "canvas_bytes": nbytes,
                        "collective": "per-frame neighbour exchange of boundary rows (NCCL send/recv) + final all_gather of the tiles",
-                       "boundary_exchange": bool(getattr(tiler, "exchange", False))}}
+                       "boundary_exchange": True, "halo_rows": halo, "carry_hops": hops, "halo_rect_bytes": rect_bytes}}
 
 
 def main():
