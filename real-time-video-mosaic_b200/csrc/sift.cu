@@ -1111,14 +1111,28 @@ static void blur_level(const BmSift* o, int oc, int level, const float* in, floa
 
 // TMA descriptors of every blur source: 2-D float tensor (w, h), box 32 x SHT, SWIZZLE_128B, zero fill outside (only tiles whose box
 // lies inside the image use it).  A level whose rows are not 16-byte multiples keeps the per-element path.
+// cuTensorMapEncodeTiled is resolved through the runtime (cudaGetDriverEntryPoint) instead of linking libcuda: the library must load
+// on a machine without a driver (the CPU-side tests check its exports there)
+typedef CUresult (*bm_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                       const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static bm_encode_tiled_fn sift_encode_tiled() {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) { cudaGetLastError(); return nullptr; }
+    return reinterpret_cast<bm_encode_tiled_fn>(fn);
+}
+
 static void sift_make_tensor_maps(BmSift* o) {
     // A/B (profiles/r02_pyramid_tma_ab.md): the TMA form is not faster than the cp.async form at 1080p (the kernel is bound by the
     // FMA / LDS issue of its two passes, not by the tile fill), so it is opt-in: BM_SIFT_TMA=1
     o->use_tma = getenv("BM_SIFT_TMA") != nullptr && getenv("BM_SIFT_NO_TMA") == nullptr;
+    const bm_encode_tiled_fn encode = o->use_tma ? sift_encode_tiled() : nullptr;
+    if (!encode) o->use_tma = false;
     for (int oc = 0; oc < o->lay.noct; ++oc) {
         const SiftOct& O = o->lay.o[oc];
         for (int l = 0; l < 6; ++l) {
             o->tma_ok[oc][l] = false;
+            if (!encode) continue;
             const float* src = l == 0 ? (oc == 0 ? o->up : nullptr) : o->pyr + O.g[l - 1];
             const int sht = sift_blur_sht(l, (long long)O.w * O.h);
             if (!src || (O.w & 3) || O.w < 96 || O.h < sht || (reinterpret_cast<uintptr_t>(src) & 15)) continue;
@@ -1126,7 +1140,7 @@ static void sift_make_tensor_maps(BmSift* o) {
             const cuuint64_t gstr[1] = {(cuuint64_t)O.w * sizeof(float)};
             const cuuint32_t box[2] = {32u, (cuuint32_t)sht};
             const cuuint32_t estr[2] = {1u, 1u};
-            const CUresult r = cuTensorMapEncodeTiled(&o->tmap[oc][l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(src), gdim, gstr, box, estr,
+            const CUresult r = encode(&o->tmap[oc][l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(src), gdim, gstr, box, estr,
                                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             o->tma_ok[oc][l] = r == CUDA_SUCCESS;

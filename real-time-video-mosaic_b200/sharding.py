@@ -220,6 +220,75 @@ def frame_window(H, frame_w, frame_h):
     return int(np.floor(x.min())) - 4, int(np.floor(y.min())) - 4, int(np.ceil(x.max())) + 5, int(np.ceil(y.max())) + 5
 
 
+class TilePlanner:
+    """Host-side protocol of the row tiles (pure logic, no device): which tiles blend a frame, which boundary sweep states have to be
+    handed over first, which halo rectangles have to be copied afterwards.  Every process runs an identical planner on the same
+    homographies, so all of them derive the same ordered list of operations and execute the ones they take part in."""
+
+    def __init__(self, canvas_w, canvas_h, world, frame_w, frame_h, halo_rows):
+        self.G, self.Wc, self.Hc = int(world), int(canvas_w), int(canvas_h)
+        self.fw, self.fh, self.P = int(frame_w), int(frame_h), int(halo_rows)
+        if self.P % 16:
+            raise ValueError("halo_rows must be a multiple of 16 (the block grid of the distance-transform tables)")
+        self.own = [tile_rows(self.Hc, g, self.G) for g in range(self.G)]
+        T = min(y1 - y0 for y0, y1 in self.own[:-1]) if self.G > 1 else self.Hc
+        if self.G > 1 and self.P > T - 16:
+            raise ValueError(f"halo_rows {self.P} must be <= tile height - 16 = {T - 16}: a halo may only reach into the adjacent tile")
+        self.ext = [(max(0, y0 - self.P), min(self.Hc, y1 + self.P)) if self.G > 1 else (0, self.Hc) for y0, y1 in self.own]
+        # stale_down[k] = "ghost_top of tile k+1 does not reflect the current canvas above it"; stale_up[k] likewise for ghost_bot of
+        # tile k-1.  Everything is stale at the start (an empty canvas above is all zero pixels, not a border).
+        self.stale_down = [True] * self.G
+        self.stale_up = [True] * self.G
+
+    def _down(self, k, ops):
+        if k < 0 or k >= self.G - 1 or not self.stale_down[k]:
+            return
+        self._down(k - 1, ops)                                  # tile k's own incoming state first
+        ops.append(("carry", k, k + 1, 0, (self.ext[k + 1][0] - self.ext[k][0]) // 16 - 1))
+        self.stale_down[k] = False
+
+    def _up(self, k, ops):
+        if k <= 0 or k > self.G - 1 or not self.stale_up[k]:
+            return
+        if self.ext[k - 1][1] >= self.Hc:                       # tile k-1's extended canvas reaches the canvas bottom: border
+            self.stale_up[k] = False
+            return
+        self._up(k + 1, ops)
+        ops.append(("carry", k, k - 1, 1, (self.ext[k - 1][1] - self.ext[k][0]) // 16))
+        self.stale_up[k] = False
+
+    def plan(self, H):
+        """ordered operations for one frame: ("carry", src, dst, up, block) | ("blend", tile) | ("rect", src, dst, x0, y_abs, w, h)"""
+        xa, wa, xb, wb = frame_window(H, self.fw, self.fh)
+        wa, wb = max(wa, 0), min(wb, self.Hc)
+        xa, xb = max(xa, 0), min(xb, self.Wc)
+        ops = []
+        if wa >= wb or xa >= xb:
+            return ops
+        S = [g for g in range(self.G) if self.own[g][0] < wb and self.own[g][1] > wa]
+        for g in S:
+            if self.ext[g][0] > wa or self.ext[g][1] < wb:
+                raise ValueError(f"frame rows [{wa},{wb}) leave the extended canvas {self.ext[g]} of tile {g}: halo_rows = {self.P} is too small")
+        for g in S:                                             # the boundary states the blending tiles need, refreshed if out of date
+            self._down(g - 1, ops)
+            self._up(g + 1, ops)
+        ops += [("blend", g) for g in S]
+        for g in S:                                             # halo rows of neighbours that did not blend this frame themselves
+            for n in (g - 1, g + 1):
+                if n < 0 or n >= self.G or n in S:
+                    continue
+                ya, yb = max(wa, self.own[g][0], self.ext[n][0]), min(wb, self.own[g][1], self.ext[n][1])
+                if ya < yb:
+                    ops.append(("rect", g, n, xa, ya, xb - xa, yb - ya))
+        for k in range(self.G - 1):                             # rows [wa, wb) changed: which exported states they feed
+            if self.ext[k + 1][0] - 1 >= wa:
+                self.stale_down[k] = True
+        for k in range(1, self.G):
+            if self.ext[k - 1][1] < wb:
+                self.stale_up[k] = True
+        return ops
+
+
 class TileGroup:
     """config 5: a (Wc, Hc) canvas cut into `world` row tiles that reproduce the UNTILED canvas bit for bit.
 
@@ -241,27 +310,16 @@ class TileGroup:
     def __init__(self, frame0, canvas_w, canvas_h, world, local_tiles, halo_rows, dist=None, device=0):
         import torch
         from .mosaic import VideMosaic
-        self.torch, self.dist, self.G = torch, dist, int(world)
-        self.Wc, self.Hc = int(canvas_w), int(canvas_h)
-        self.fh, self.fw = frame0.shape[:2]
-        self.P = int(halo_rows)
-        if self.P % 16:
-            raise ValueError("halo_rows must be a multiple of 16 (the block grid of the distance-transform tables)")
-        self.own = [tile_rows(self.Hc, g, self.G) for g in range(self.G)]
-        T = min(y1 - y0 for y0, y1 in self.own[:-1]) if self.G > 1 else self.Hc
-        if self.G > 1 and self.P > T - 16:
-            raise ValueError(f"halo_rows {self.P} must be <= tile height - 16 = {T - 16}: a halo may only reach into the adjacent tile")
-        self.ext = [(max(0, y0 - self.P), min(self.Hc, y1 + self.P)) if self.G > 1 else (0, self.Hc) for y0, y1 in self.own]
+        self.torch, self.dist = torch, dist
+        self.planner = TilePlanner(canvas_w, canvas_h, world, frame0.shape[1], frame0.shape[0], halo_rows)
+        self.G, self.Wc, self.Hc, self.P = self.planner.G, self.planner.Wc, self.planner.Hc, self.planner.P
+        self.own, self.ext = self.planner.own, self.planner.ext
         self.local = {}
         for g in local_tiles:
             Y0, Y1 = self.ext[g]
             vm = VideMosaic(frame0, detector_type="orb", show_intermediate=False, visualize=False, canvas_size=(Y1 - Y0, self.Wc), device=device)
             vm.clear_canvas()
             self.local[g] = vm
-        # boundary sweep states: stale_down[k] = "ghost_top of tile k+1 does not reflect the current canvas above it", stale_up[k] likewise
-        # for ghost_bot of tile k-1.  Everything is stale at the start (an empty canvas above is all zero pixels, not a border).
-        self.stale_down = [True] * self.G
-        self.stale_up = [True] * self.G
         self.hops = 0
         self.rect_bytes = 0
         if dist is not None and self.G > 1:                    # open the neighbour channels now (NCCL sets P2P connections up on first use)
@@ -306,29 +364,6 @@ class TileGroup:
         vm = self.local[g]
         _lib.check(vm._lib.bm_tile_set_ghost(vm._h, int(side), C.c_void_p(t.data_ptr()) if t is not None else None), "bm_tile_set_ghost")
 
-    def _refresh_down(self, k):
-        """ghost_top of tile k + 1 <- downward sweep state of tile k at the row just above tile k + 1's extended canvas"""
-        if k < 0 or k >= self.G - 1 or not self.stale_down[k]:
-            return
-        self._refresh_down(k - 1)                               # tile k's own incoming state first
-        block = (self.ext[k + 1][0] - self.ext[k][0]) // 16 - 1
-        self._xfer(k, k + 1, lambda: self._export_carries(k, 0, block), lambda t: self._set_ghost(k + 1, 0, t), (3, self.Wc), self.torch.int32)
-        self.stale_down[k] = False
-        self.hops += 1
-
-    def _refresh_up(self, k):
-        """ghost_bot of tile k - 1 <- upward sweep state of tile k at the row just below tile k - 1's extended canvas"""
-        if k <= 0 or k > self.G - 1 or not self.stale_up[k]:
-            return
-        if self.ext[k - 1][1] >= self.Hc:                       # tile k - 1's extended canvas reaches the canvas bottom: border
-            self.stale_up[k] = False
-            return
-        self._refresh_up(k + 1)
-        block = (self.ext[k - 1][1] - self.ext[k][0]) // 16
-        self._xfer(k, k - 1, lambda: self._export_carries(k, 1, block), lambda t: self._set_ghost(k - 1, 1, t), (3, self.Wc), self.torch.int32)
-        self.stale_up[k] = False
-        self.hops += 1
-
     def _copy_rect(self, g, n, x0, ya, w, h):
         import ctypes as C
         from . import _lib
@@ -350,36 +385,19 @@ class TileGroup:
     def put(self, frame, H):
         """VideMosaic.warp(frame, H) (main.py:861-927) on the tiled canvas; H is the absolute canvas homography.  Returns how many of
         this process's tiles blended the frame."""
-        xa, wa, xb, wb = frame_window(H, self.fw, self.fh)
-        wa, wb = max(wa, 0), min(wb, self.Hc)
-        xa, xb = max(xa, 0), min(xb, self.Wc)
-        if wa >= wb or xa >= xb:
-            return 0
-        S = [g for g in range(self.G) if self.own[g][0] < wb and self.own[g][1] > wa]
-        for g in S:
-            if self.ext[g][0] > wa or self.ext[g][1] < wb:
-                raise ValueError(f"frame rows [{wa},{wb}) leave the extended canvas {self.ext[g]} of tile {g}: halo_rows = {self.P} is too small")
-        for g in S:                                             # the boundary states the blending tiles need, refreshed if out of date
-            self._refresh_down(g - 1)
-            self._refresh_up(g + 1)
         done = 0
-        for g in S:
-            if g in self.local:
-                self.local[g].warp_nosync(frame, tile_homography(H, self.ext[g][0]))
-                done += 1
-        for g in S:                                             # halo rows of neighbours that did not blend this frame themselves
-            for n in (g - 1, g + 1):
-                if n < 0 or n >= self.G or n in S:
-                    continue
-                ya, yb = max(wa, self.own[g][0], self.ext[n][0]), min(wb, self.own[g][1], self.ext[n][1])
-                if ya < yb:
-                    self._copy_rect(g, n, xa, ya, xb - xa, yb - ya)
-        for k in range(self.G - 1):                             # rows [wa, wb) changed: which exported states they feed
-            if self.ext[k + 1][0] - 1 >= wa:
-                self.stale_down[k] = True
-        for k in range(1, self.G):
-            if self.ext[k - 1][1] < wb:
-                self.stale_up[k] = True
+        for op in self.planner.plan(H):
+            if op[0] == "carry":
+                _, a, b, up, block = op
+                self._xfer(a, b, lambda: self._export_carries(a, up, block), lambda t: self._set_ghost(b, 1 if up else 0, t), (3, self.Wc), self.torch.int32)
+                self.hops += 1
+            elif op[0] == "blend":
+                if op[1] in self.local:
+                    self.local[op[1]].warp_nosync(frame, tile_homography(H, self.ext[op[1]][0]))
+                    done += 1
+            else:
+                _, g, n, x0, ya, w, h = op
+                self._copy_rect(g, n, x0, ya, w, h)
         return done
 
     def sync(self):

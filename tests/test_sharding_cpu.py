@@ -109,3 +109,101 @@ def test_gloo_world2_collectives():
         assert np.array_equal(full[:, 0, 0], np.arange(100, dtype=np.uint8))
         y0, y1 = sh.tile_rows(100, 1, 2)
         assert (full[:y0, 1:, :] == 1).all() and (full[y0:, 1:, :] == 2).all()
+
+
+# ---- row tiles: the boundary-exchange protocol (host logic only; the device side is tests/test_modes_gpu.py) ------------------
+def _tile_Hs(n=60, Wc=448, Hc=1024, fw=320, fh=180):
+    rng = np.random.default_rng(3)
+    Hs, y = [], Hc - fh - 6.0
+    for t in range(n):
+        y += rng.choice([-37.0, -25.0, 31.0, -90.0, 55.0])          # a camera that wanders across the tile boundaries both ways
+        y = float(np.clip(y, 4.0, Hc - fh - 6.0))
+        T = np.eye(3); T[0, 2] = (Wc - fw) / 2 + 30.0 * np.sin(t / 3.0); T[1, 2] = y
+        Hs.append(T)
+    return Hs
+
+
+def test_tile_planner_invariants():
+    """every blend sees fresh boundary states, hops only happen when something changed, planners in lock step"""
+    fw, fh, Wc, Hc = 320, 180, 448, 1024
+    a = sh.TilePlanner(Wc, Hc, 4, fw, fh, 208)
+    b = sh.TilePlanner(Wc, Hc, 4, fw, fh, 208)
+    n_carry = 0
+    for H in _tile_Hs():
+        was_down, was_up = list(a.stale_down), list(a.stale_up)
+        ops = a.plan(H)
+        assert ops == b.plan(H)                                       # deterministic: two processes derive the same list
+        blends = [o[1] for o in ops if o[0] == "blend"]
+        assert 1 <= len(blends) <= 2
+        fresh_d, fresh_u = list(was_down), list(was_up)
+        for o in ops:
+            if o[0] == "carry":
+                _, src, dst, up, block = o
+                n_carry += 1
+                assert abs(src - dst) == 1 and dst == (src - 1 if up else src + 1)
+                assert (was_up if up else was_down)[src]              # only stale states are refreshed
+                if up:
+                    assert src == 3 or not fresh_u[src + 1]           # the sender's own incoming state was refreshed first
+                    fresh_u[src] = False
+                else:
+                    assert src == 0 or not fresh_d[src - 1]
+                    fresh_d[src] = False
+                assert 0 <= block < (a.ext[src][1] - a.ext[src][0] + 15) // 16
+            elif o[0] == "blend":
+                g = o[1]
+                assert g == 0 or not fresh_d[g - 1]                   # ghost_top of g is fresh when g blends
+                assert g == 3 or not fresh_u[g + 1] or a.ext[g][1] >= Hc
+            else:
+                _, g, n, x0, ya, w, h = o
+                assert g in blends and n not in blends and abs(g - n) == 1
+                assert a.own[g][0] <= ya and ya + h <= a.own[g][1]    # only the owner's own rows travel ...
+                assert a.ext[n][0] <= ya and ya + h <= a.ext[n][1]    # ... into the neighbour's halo
+    assert n_carry >= 10
+    with pytest.raises(ValueError):
+        sh.TilePlanner(Wc, Hc, 4, fw, fh, 100)                        # not a multiple of 16
+    with pytest.raises(ValueError):
+        sh.TilePlanner(Wc, Hc, 4, fw, fh, 256)                        # halo reaches beyond the adjacent tile
+    with pytest.raises(ValueError):
+        sh.TilePlanner(Wc, Hc, 4, fw, fh, 64).plan(_tile_Hs(1)[0] @ np.diag([1.0, 1.0, 1.0]) + np.array([[0, 0, 0], [0, 0, -500.0], [0, 0, 0]]))
+
+
+def _tile_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    import torch
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pl = sh.TilePlanner(448, 1024, world, 320, 180, 208)
+    log = []
+    for H in _tile_Hs(40):
+        for op in pl.plan(H):
+            if op[0] == "blend":
+                continue
+            src, dst = op[1], op[2]
+            payload = torch.tensor([(len(op[0]) * 7919 + sum(int(v) * (i + 1) for i, v in enumerate(op[1:]))) % 1000003], dtype=torch.int64)
+            if src == rank:
+                dist.send(payload, dst=dst)
+                log.append(("s", dst, int(payload)))
+            elif dst == rank:
+                got = torch.zeros(1, dtype=torch.int64)
+                dist.recv(got, src=src)
+                assert int(got) == int(payload)                      # the matching operation of the sender's identical plan
+                log.append(("r", src, int(got)))
+    dist.barrier()
+    q.put((rank, len(log)))
+    dist.destroy_process_group()
+
+
+def test_tile_protocol_gloo_world2():
+    """two processes, one tile each: every send of the shared plan meets its recv in order (no deadlock, same payload)"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_tile_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    counts = dict(q.get(timeout=5) for _ in range(2))
+    assert counts[0] == counts[1] and counts[0] > 0
