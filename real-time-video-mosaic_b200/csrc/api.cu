@@ -59,7 +59,8 @@ static bm_status alloc_blend(BmBlendBufs& b, int canvas_h, int canvas_w, size_t 
 // Frame slots rotate over three buffers; events order  upload(slot) -> detect / chain(slot) -> next upload(slot).  Three, not two:
 // the upload of frame t+1 must not wait for the chain of frame t-1, which is still reading that frame's BGRX copy when the caller
 // stages t+1 (with two slots the H2D copy of every frame started a whole chain late and sat on the critical path of the e2e rate).
-#define BM_SLOTS 3
+#define BM_SLOTS 4
+#define BM_LOOKAHEAD 2                  // frames that may be staged (and detected) ahead of the current one
 #define BM_CANVAS_STAGE_BYTES ((size_t)4 << 20)
 #define BM_SLOT_NEXT(c) (((c) + 1) % BM_SLOTS)
 #define BM_SLOT_PREV(c) (((c) + BM_SLOTS - 1) % BM_SLOTS)
@@ -70,8 +71,11 @@ struct bm_mosaic_s {
     cudaEvent_t ev_chain[BM_SLOTS] = {};       // last chain that read the slot's BGRX finished
     cudaEvent_t ev_spec[BM_SLOTS] = {};        // last detect-ahead that read the slot's gray plane finished (owned by the pipeline)
     int overlap = 1;                                    // 0: detect waits for the previous chain (clean chain timing)
-    const uint8_t* prefetched = nullptr;                // host pointer staged by bm_prefetch_frame ...
-    int prefetched_slot = -1;                           // ... into this slot
+    // frames staged ahead by bm_prefetch_frame, in the order the caller will process them: q[0] is the next frame.  Their H2D copy +
+    // ingest run on the copy stream, their detectAndCompute is queued at the start of the next _end ("detect-ahead"): with two frames
+    // ahead three detects are in flight and the frame period is no longer tied to the detect latency.
+    struct Staged { const uint8_t* ptr; int slot; bool detected; } q[BM_LOOKAHEAD] = {};
+    int nq = 0;
     const uint8_t* begun = nullptr;                     // frame whose detect / match / RANSAC was already enqueued by the previous _end
     BmBlendBufs blend;
     // frame staging: double-buffered pinned host + device buffers
@@ -226,34 +230,66 @@ static bm_status upload(bm_mosaic_s* m, const uint8_t* h_bgr, size_t stride, int
     return BM_OK;
 }
 
-// frame -> slot `slot` unless bm_prefetch_frame already staged exactly this host buffer there; then make `consumer` wait for it
-static bm_status stage_frame(bm_mosaic_s* m, const uint8_t* h_bgr, size_t stride, int slot, cudaStream_t consumer) {
-    if (!(m->prefetched && m->prefetched == h_bgr && m->prefetched_slot == slot)) BM_TRY(upload(m, h_bgr, stride, slot));
-    m->prefetched = nullptr;
-    BM_CUDA_OK(cudaStreamWaitEvent(consumer, m->ev_up[slot], 0));
+static void q_clear(bm_mosaic_s* m) {
+    for (int i = 0; i < m->nq; ++i) bm_pipeline_drop_ahead(m->pipe, m->d_gray[m->q[i].slot]);
+    m->nq = 0;
+}
+static int q_find(const bm_mosaic_s* m, const uint8_t* ptr) {
+    for (int i = 0; i < m->nq; ++i) if (m->q[i].ptr == ptr) return i;
+    return -1;
+}
+static void q_pop_front(bm_mosaic_s* m) {
+    for (int i = 1; i < m->nq; ++i) m->q[i - 1] = m->q[i];
+    m->nq--;
+}
+
+// device frame (packed BGR) -> slot, ingest on the copy stream
+static bm_status ingest_device(bm_mosaic_s* m, const uint8_t* d_bgr, int slot, cudaStream_t s) {
+    BM_CUDA_OK(cudaStreamWaitEvent(s, m->ev_chain[slot], 0));              // the slot's previous chain still reads its BGRX copy
+    if (m->ev_spec[slot]) BM_CUDA_OK(cudaStreamWaitEvent(s, m->ev_spec[slot], 0));   // ... or an abandoned detect-ahead its gray plane
+    bm_pipeline_drop_ahead(m->pipe, m->d_gray[slot]);
+    BM_CUDA_OK(bm_launch_ingest(d_bgr, m->cfg.frame_h, m->cfg.frame_w, m->d_gray[slot], m->d_bgrx[slot], s));
+    BM_CUDA_OK(cudaEventRecord(m->ev_up[slot], s));
+    return BM_OK;
+}
+
+// Make `ptr` the current frame (m->cur): the staged copy if it is the next staged frame, otherwise every staged frame is stale (the
+// caller continued with another frame) and the frame is uploaded / ingested now.  `consumer` then waits for the slot's upload.
+static bm_status take_frame(bm_mosaic_s* m, const uint8_t* ptr, size_t stride, bool device, cudaStream_t consumer) {
+    if (m->nq > 0 && m->q[0].ptr == ptr) {
+        m->cur = m->q[0].slot;
+        q_pop_front(m);
+    } else {
+        q_clear(m);
+        m->cur = BM_SLOT_NEXT(m->cur);
+        if (device) BM_TRY(ingest_device(m, ptr, m->cur, m->s_copy));
+        else BM_TRY(upload(m, ptr, stride, m->cur));
+    }
+    BM_CUDA_OK(cudaStreamWaitEvent(consumer, m->ev_up[m->cur], 0));
+    return BM_OK;
+}
+
+static bm_status prefetch(bm_mosaic_s* m, const uint8_t* ptr, size_t stride, bool device) {
+    if (m->begun == ptr || q_find(m, ptr) >= 0 || m->nq >= BM_LOOKAHEAD) return BM_OK;     // already staged / no room: nothing to do
+    const int slot = (m->cur + 1 + m->nq) % BM_SLOTS;
+    if (device) BM_TRY(ingest_device(m, ptr, slot, m->s_copy));
+    else BM_TRY(upload(m, ptr, stride, slot));
+    m->q[m->nq].ptr = ptr; m->q[m->nq].slot = slot; m->q[m->nq].detected = false;
+    m->nq++;
     return BM_OK;
 }
 
 extern "C" bm_status bm_prefetch_frame(bm_handle m, const uint8_t* h_bgr, size_t stride) {
     if (!m || !h_bgr) { bm_set_error("bm_prefetch_frame: null"); return BM_ERR_ARG; }
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
-    BM_TRY(upload(m, h_bgr, stride, BM_SLOT_NEXT(m->cur)));
-    m->prefetched = h_bgr; m->prefetched_slot = BM_SLOT_NEXT(m->cur);
-    return BM_OK;
+    return prefetch(m, h_bgr, stride, false);
 }
 
 // same for a frame that already lives in device memory (packed BGR): ingest into the free slot on the copy stream
 extern "C" bm_status bm_prefetch_frame_device(bm_handle m, const uint8_t* d_bgr) {
     if (!m || !d_bgr) { bm_set_error("bm_prefetch_frame_device: null"); return BM_ERR_ARG; }
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
-    const int slot = BM_SLOT_NEXT(m->cur);
-    BM_CUDA_OK(cudaStreamWaitEvent(m->s_copy, m->ev_chain[slot], 0));
-    if (m->ev_spec[slot]) BM_CUDA_OK(cudaStreamWaitEvent(m->s_copy, m->ev_spec[slot], 0));
-    bm_pipeline_drop_ahead(m->pipe, m->d_gray[slot]);
-    BM_CUDA_OK(bm_launch_ingest(d_bgr, m->cfg.frame_h, m->cfg.frame_w, m->d_gray[slot], m->d_bgrx[slot], m->s_copy));
-    BM_CUDA_OK(cudaEventRecord(m->ev_up[slot], m->s_copy));
-    m->prefetched = d_bgr; m->prefetched_slot = slot;
-    return BM_OK;
+    return prefetch(m, d_bgr, 0, true);
 }
 
 extern "C" bm_status bm_set_overlap(bm_handle m, int on) { if (!m) return BM_ERR_ARG; m->overlap = on ? 1 : 0; return BM_OK; }
@@ -262,7 +298,7 @@ extern "C" bm_status bm_first_frame(bm_handle m, const uint8_t* h_bgr, size_t st
     if (!m || !h_bgr) { bm_set_error("bm_first_frame: null"); return BM_ERR_ARG; }
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
     const int fh = m->cfg.frame_h, fw = m->cfg.frame_w, ch = m->cfg.canvas_h, cw = m->cfg.canvas_w;
-    m->cur = 0; m->prefetched = nullptr; m->begun = nullptr;
+    m->cur = 0; m->nq = 0; m->begun = nullptr;
     BM_TRY(upload(m, h_bgr, stride, 0));
     BM_CUDA_OK(cudaStreamWaitEvent(m->stream, m->ev_up[0], 0));
     BM_CUDA_OK(cudaStreamWaitEvent(m->s_chain, m->ev_up[0], 0));
@@ -339,8 +375,7 @@ extern "C" bm_status bm_warp_frame(bm_handle m, const uint8_t* h_bgr, size_t str
     if (!m || !h_bgr || !H) { bm_set_error("bm_warp_frame: null"); return BM_ERR_ARG; }
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
     cancel_early_begin(m);
-    m->cur = BM_SLOT_NEXT(m->cur);
-    BM_TRY(stage_frame(m, h_bgr, stride, m->cur, m->s_chain));
+    BM_TRY(take_frame(m, h_bgr, stride, false, m->s_chain));
     if (info) { memset(info, 0, sizeof(*info)); memcpy(info->H, H, 9 * sizeof(double)); }
     return warp_device(m, m->d_bgrx[m->cur], H, info, true, m->cur);
 }
@@ -349,8 +384,7 @@ extern "C" bm_status bm_warp_frame_async(bm_handle m, const uint8_t* h_bgr, size
     if (!m || !h_bgr || !H) { bm_set_error("bm_warp_frame_async: null"); return BM_ERR_ARG; }
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
     cancel_early_begin(m);
-    m->cur = BM_SLOT_NEXT(m->cur);
-    BM_TRY(stage_frame(m, h_bgr, stride, m->cur, m->s_chain));
+    BM_TRY(take_frame(m, h_bgr, stride, false, m->s_chain));
     return warp_device(m, m->d_bgrx[m->cur], H, nullptr, false, m->cur);
 }
 
@@ -364,8 +398,7 @@ extern "C" bm_status bm_upload_frame(bm_handle m, const uint8_t* h_bgr, size_t s
     if (!m || !h_bgr) return BM_ERR_ARG;
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
     cancel_early_begin(m);
-    m->cur = BM_SLOT_NEXT(m->cur);
-    BM_TRY(stage_frame(m, h_bgr, stride, m->cur, m->s_chain));
+    BM_TRY(take_frame(m, h_bgr, stride, false, m->s_chain));
     if (d_out) *d_out = reinterpret_cast<const uint8_t*>(m->d_bgrx[m->cur]);
     return BM_OK;
 }
@@ -550,28 +583,36 @@ static void matmul3(const double* A, const double* B, double* C) {
     }
 }
 
-// If bm_prefetch_frame staged the next frame into the free slot, start its detect / match / RANSAC now (the following
-// bm_process_frame_begin with the same pointer is then a no-op).  Only with stream overlap on.
+// If the next frame is staged, start its match / RANSAC now (its features were detected ahead); the following
+// bm_process_frame_begin with the same pointer is then a no-op.  Only with stream overlap on.
 static bm_status early_begin(bm_mosaic_s* m) {
-    if (!m->overlap || !m->prefetched || m->prefetched_slot != (BM_SLOT_NEXT(m->cur))) return BM_OK;
-    m->cur = BM_SLOT_NEXT(m->cur);
+    if (!m->overlap || m->nq == 0) return BM_OK;
+    const bm_mosaic_s::Staged e = m->q[0];
+    const int prev_cur = m->cur;
+    m->cur = e.slot;
+    q_pop_front(m);
     BM_CUDA_OK(cudaStreamWaitEvent(m->stream, m->ev_up[m->cur], 0));
     bm_status st = bm_pipeline_estimate_begin(m->pipe, m->d_gray[m->cur]);
-    if (st < 0) { m->cur = BM_SLOT_PREV(m->cur); return st; }
-    m->begun = m->prefetched;
-    m->prefetched = nullptr;
+    if (st < 0) { m->cur = prev_cur; return st; }
+    m->begun = e.ptr;
     return BM_OK;
 }
 
-// The next frame is staged and the current frame's detect / match / RANSAC are queued: queue the next frame's detectAndCompute behind
-// them NOW, before the host blocks on the RANSAC result -- the detect stream then runs straight on while the host takes the
-// skip / validate / smooth decision and issues the chain.  Without it the device idles for the wake-up + launch latency every frame.
+// The current frame's detect / match / RANSAC are queued: queue the detectAndCompute of every staged frame behind them NOW, before the
+// host blocks on the RANSAC result -- the detect streams then run straight on while the host takes the skip / validate / smooth
+// decision and issues the chain.  With two frames staged, three detects are in flight.
 static bm_status detect_ahead(bm_mosaic_s* m) {
-    if (!m->overlap || !m->prefetched || m->prefetched_slot != (BM_SLOT_NEXT(m->cur))) return BM_OK;
-    const int slot = BM_SLOT_NEXT(m->cur);
-    BM_CUDA_OK(cudaStreamWaitEvent(m->stream, m->ev_up[slot], 0));
-    BM_TRY(bm_pipeline_detect_ahead(m->pipe, m->d_gray[slot]));
-    m->ev_spec[slot] = bm_pipeline_last_detect_event(m->pipe);
+    if (!m->overlap) return BM_OK;
+    for (int i = 0; i < m->nq; ++i) {
+        if (m->q[i].detected) continue;
+        const int slot = m->q[i].slot;
+        BM_CUDA_OK(cudaStreamWaitEvent(m->stream, m->ev_up[slot], 0));
+        int done = 0;
+        BM_TRY(bm_pipeline_detect_ahead(m->pipe, m->d_gray[slot], &done));
+        if (!done) break;                                  // no free keypoint slot yet: try again at the next frame
+        m->ev_spec[slot] = bm_pipeline_last_detect_event(m->pipe);
+        m->q[i].detected = true;
+    }
     return BM_OK;
 }
 
@@ -586,7 +627,7 @@ static bm_status finish_frame(bm_mosaic_s* m, int slot, bm_frame_info* info_out)
     double H_rel[9]; int have_h = 0;
     BM_TRY(detect_ahead(m));
     bm_status st = bm_pipeline_estimate_end(m->pipe, &info, H_rel, &have_h);
-    if (st < 0) { m->cur = BM_SLOT_PREV(m->cur); return st; }
+    if (st < 0) return st;
     if (info.n_matches < 4) { info.status = BM_SKIP_FEW_MATCHES; BM_TRY(early_begin(m)); if (info_out) *info_out = info; return BM_SKIP_FEW_MATCHES; }
     if (!have_h) { info.status = BM_SKIP_NO_H; BM_TRY(early_begin(m)); if (info_out) *info_out = info; return BM_SKIP_NO_H; }
     memcpy(info.H_rel, H_rel, 72);
@@ -635,12 +676,9 @@ extern "C" bm_status bm_process_frame_begin(bm_handle m, const uint8_t* h_bgr, s
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
     if (m->begun == h_bgr) { m->begun = nullptr; return BM_OK; }      // already enqueued by the previous frame's _end
     cancel_early_begin(m);
-    m->cur = BM_SLOT_NEXT(m->cur);
-    BM_TRY(stage_frame(m, h_bgr, stride, m->cur, m->stream));
+    BM_TRY(take_frame(m, h_bgr, stride, false, m->stream));
     BM_TRY(order_after_chain(m));
-    bm_status st = bm_pipeline_estimate_begin(m->pipe, m->d_gray[m->cur]);
-    if (st < 0) m->cur = BM_SLOT_PREV(m->cur);
-    return st;
+    return bm_pipeline_estimate_begin(m->pipe, m->d_gray[m->cur]);
 }
 
 extern "C" bm_status bm_process_frame_begin_device(bm_handle m, const uint8_t* d_bgr) {
@@ -648,21 +686,9 @@ extern "C" bm_status bm_process_frame_begin_device(bm_handle m, const uint8_t* d
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
     if (m->begun == d_bgr) { m->begun = nullptr; return BM_OK; }      // already enqueued by the previous frame's _end
     cancel_early_begin(m);
-    m->cur = BM_SLOT_NEXT(m->cur);
-    if (m->prefetched == d_bgr && m->prefetched_slot == m->cur) {
-        BM_CUDA_OK(cudaStreamWaitEvent(m->stream, m->ev_up[m->cur], 0));
-    } else {
-        BM_CUDA_OK(cudaStreamWaitEvent(m->stream, m->ev_chain[m->cur], 0));      // the slot's previous chain still reads its BGRX copy
-        if (m->ev_spec[m->cur]) BM_CUDA_OK(cudaStreamWaitEvent(m->stream, m->ev_spec[m->cur], 0));   // ... or an abandoned detect-ahead its gray plane
-        bm_pipeline_drop_ahead(m->pipe, m->d_gray[m->cur]);
-        BM_CUDA_OK(bm_launch_ingest(d_bgr, m->cfg.frame_h, m->cfg.frame_w, m->d_gray[m->cur], m->d_bgrx[m->cur], m->stream));
-        BM_CUDA_OK(cudaEventRecord(m->ev_up[m->cur], m->stream));
-    }
-    m->prefetched = nullptr;
+    BM_TRY(take_frame(m, d_bgr, 0, true, m->stream));
     BM_TRY(order_after_chain(m));
-    bm_status st = bm_pipeline_estimate_begin(m->pipe, m->d_gray[m->cur]);
-    if (st < 0) m->cur = BM_SLOT_PREV(m->cur);
-    return st;
+    return bm_pipeline_estimate_begin(m->pipe, m->d_gray[m->cur]);
 }
 
 extern "C" bm_status bm_process_frame_end(bm_handle m, bm_frame_info* info_out) {
@@ -687,19 +713,17 @@ extern "C" bm_status bm_estimate_frame(bm_handle m, const uint8_t* h_bgr, size_t
     if (!m || !h_bgr) { bm_set_error("bm_estimate_frame: null"); return BM_ERR_ARG; }
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
     cancel_early_begin(m);
-    m->cur = BM_SLOT_NEXT(m->cur);
-    BM_TRY(stage_frame(m, h_bgr, stride, m->cur, m->stream));
+    BM_TRY(take_frame(m, h_bgr, stride, false, m->stream));
     bm_frame_info info; memset(&info, 0, sizeof(info));
     double H_rel[9]; int have_h = 0;
     bm_status st = bm_pipeline_estimate_begin(m->pipe, m->d_gray[m->cur]);
-    if (st < 0) { m->cur = BM_SLOT_PREV(m->cur); return st; }
+    if (st < 0) return st;
     if (h_next) {                                  // the next frame's H2D + ingest overlap this pair's estimation
-        BM_TRY(upload(m, h_next, stride, BM_SLOT_NEXT(m->cur)));
-        m->prefetched = h_next; m->prefetched_slot = BM_SLOT_NEXT(m->cur);
+        BM_TRY(prefetch(m, h_next, stride, false));
         BM_TRY(detect_ahead(m));                   // and its features are computed while the host waits for this pair
     }
     st = bm_pipeline_estimate_end(m->pipe, &info, H_rel, &have_h);
-    if (st < 0) { m->cur = BM_SLOT_PREV(m->cur); return st; }
+    if (st < 0) return st;
     bm_pipeline_advance(m->pipe);                  // pair (t-1, t): the frame always becomes "previous"
     bm_status ret = BM_OK;
     if (info.n_matches < 4) ret = BM_SKIP_FEW_MATCHES;

@@ -622,7 +622,7 @@ cudaError_t bm_orb_detect(BmOrb* o, const uint8_t* d_gray, BmKeypoints* out, boo
             BM_COUNT_LAUNCHES(o->graphs[i].launches);
             return cudaGraphLaunch(o->graphs[i].exec, o->stream);
         }
-    if (o->ngraphs >= 12) return orb_enqueue(o, d_gray, out);
+    if (o->ngraphs >= 20) return orb_enqueue(o, d_gray, out);
     const long long before = g_bm_launches;
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamBeginCapture(o->stream, cudaStreamCaptureModeRelaxed);

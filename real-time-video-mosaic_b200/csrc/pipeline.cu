@@ -27,15 +27,15 @@ struct BmPipeline {
     cudaEvent_t ev_fork = nullptr;
     int det_toggle = 0, last_det_slot = 0;
     bool is_orb = false;
-    BmKeypoints kp[3];       // previous / current / detected ahead (the next frame's features may be computed before the host
-    int prev = 0, cur = 1;   // knows whether the current frame becomes "previous")
-    const uint8_t* ahead_gray = nullptr;     // gray buffer whose features were enqueued into kp[ahead_slot] by bm_pipeline_detect_ahead
-    int ahead_slot = -1;
+    BmKeypoints kp[BM_KP_SLOTS];   // previous / current / up to two detected ahead (the next frames' features may be computed before
+    int prev = 0, cur = 1;         // the host knows whether the current frame becomes "previous")
+    const uint8_t* ahead_gray[2] = {nullptr, nullptr};   // gray buffers whose features were enqueued into kp[ahead_slot[i]] by bm_pipeline_detect_ahead
+    int ahead_slot[2] = {-1, -1};
     cudaEvent_t ev_done = nullptr;           // RANSAC result + counts of the current frame are in the pinned readback
     // match + RANSAC run on their own stream: a handful of small, latency-bound launches (one-CTA RANSAC stages, selection sort) that
     // would otherwise sit between two detects on the detect stream; with a detect-ahead queued they overlap the next frame's pyramid
     cudaStream_t s_est = nullptr;
-    cudaEvent_t ev_det[3] = {nullptr, nullptr, nullptr};   // features of the slot are complete (recorded on the detect stream)
+    cudaEvent_t ev_det[BM_KP_SLOTS] = {};    // features of the slot are complete (recorded on the detect stream)
     cudaEvent_t ev_est = nullptr;            // last match that read the keypoint slots finished (a detect may overwrite a slot)
     BmMatches m[2];          // double buffered: the next frame may be matched while the last one's matches are still readable
     int mcur = 0, mdone = 0;
@@ -56,12 +56,11 @@ bm_status bm_pipeline_create(BmPipeline** out, const bm_config& cfg, cudaStream_
     p->cfg = cfg; p->stream = stream;
     memset(p->kp, 0, sizeof(p->kp)); memset(p->m, 0, sizeof(p->m));
     const int desc_bytes = cfg.detector == BM_DET_ORB ? 32 : 128;
-    bool ok = bm_kp_alloc(&p->kp[0], desc_bytes) == 0 && bm_kp_alloc(&p->kp[1], desc_bytes) == 0 && bm_kp_alloc(&p->kp[2], desc_bytes) == 0 &&
-              cudaEventCreateWithFlags(&p->ev_done, cudaEventDisableTiming) == cudaSuccess &&
-              cudaEventCreateWithFlags(&p->ev_est, cudaEventDisableTiming) == cudaSuccess &&
-              cudaEventCreateWithFlags(&p->ev_det[0], cudaEventDisableTiming) == cudaSuccess &&
-              cudaEventCreateWithFlags(&p->ev_det[1], cudaEventDisableTiming) == cudaSuccess &&
-              cudaEventCreateWithFlags(&p->ev_det[2], cudaEventDisableTiming) == cudaSuccess &&
+    bool ok = cudaEventCreateWithFlags(&p->ev_done, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&p->ev_est, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < BM_KP_SLOTS && ok; ++i)
+        ok = bm_kp_alloc(&p->kp[i], desc_bytes) == 0 && cudaEventCreateWithFlags(&p->ev_det[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok &&
               bm_stream_create(&p->s_est, 2) == cudaSuccess && bm_matches_alloc(&p->m[0]) == 0 && bm_matches_alloc(&p->m[1]) == 0 &&
               cudaMalloc(&p->d_mask, BM_KP_CAP) == cudaSuccess && cudaMalloc(&p->d_res, sizeof(BmRansacResult)) == cudaSuccess &&
               cudaHostAlloc(&p->h_rb, sizeof(BmHostReadback), cudaHostAllocDefault) == cudaSuccess;
@@ -93,10 +92,10 @@ void bm_pipeline_destroy(BmPipeline* p) {
         if (p->s_det[i]) cudaStreamDestroy(p->s_det[i]);
     }
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
-    bm_kp_free(&p->kp[0]); bm_kp_free(&p->kp[1]); bm_kp_free(&p->kp[2]);
+    for (int i = 0; i < BM_KP_SLOTS; ++i) bm_kp_free(&p->kp[i]);
     if (p->ev_done) cudaEventDestroy(p->ev_done);
     if (p->ev_est) cudaEventDestroy(p->ev_est);
-    for (int i = 0; i < 3; ++i) if (p->ev_det[i]) cudaEventDestroy(p->ev_det[i]);
+    for (int i = 0; i < BM_KP_SLOTS; ++i) if (p->ev_det[i]) cudaEventDestroy(p->ev_det[i]);
     if (p->s_est) cudaStreamDestroy(p->s_est);
     bm_matches_free(&p->m[0]); bm_matches_free(&p->m[1]);
     cudaFree(p->d_mask); cudaFree(p->d_res); cudaFreeHost(p->h_rb);
@@ -122,24 +121,38 @@ static cudaError_t detect(BmPipeline* p, const uint8_t* d_gray, BmKeypoints* out
 }
 
 bm_status bm_pipeline_first_frame(BmPipeline* p, const uint8_t* d_gray) {
-    p->prev = 0; p->cur = 1; p->ahead_gray = nullptr;
+    p->prev = 0; p->cur = 1; p->ahead_gray[0] = p->ahead_gray[1] = nullptr;
     BM_CUDA_OK(detect(p, d_gray, &p->kp[0]));
     p->have_prev = true;
     return BM_OK;
 }
 
+// a keypoint slot that holds neither the previous frame's features, nor the current frame's (while `cur_active`), nor features detected ahead
+static int free_kp_slot(const BmPipeline* p, bool cur_active) {
+    for (int s = 0; s < BM_KP_SLOTS; ++s) {
+        if (s == p->prev || (cur_active && s == p->cur)) continue;
+        if ((p->ahead_gray[0] && p->ahead_slot[0] == s) || (p->ahead_gray[1] && p->ahead_slot[1] == s)) continue;
+        return s;
+    }
+    return -1;
+}
+
 bm_status bm_pipeline_estimate_begin(BmPipeline* p, const uint8_t* d_gray) {
     if (!p->have_prev) { bm_set_error("process_frame before first frame"); return BM_ERR_ARG; }
     cudaStream_t s = p->s_est;
-    if (p->ahead_gray == d_gray && p->ahead_slot != p->prev) p->cur = p->ahead_slot;      // features already enqueued (detect_ahead)
-    else {
-        p->cur = (p->prev + 1) % 3;
+    int hit = -1;
+    for (int i = 0; i < 2; ++i) if (p->ahead_gray[i] == d_gray && p->ahead_slot[i] != p->prev) hit = i;
+    if (hit >= 0) {                                        // features already enqueued (detect_ahead)
+        p->cur = p->ahead_slot[hit];
+        p->ahead_gray[hit] = nullptr;
+    } else {
+        p->cur = free_kp_slot(p, false);
+        if (p->cur < 0) { p->ahead_gray[0] = p->ahead_gray[1] = nullptr; p->cur = free_kp_slot(p, false); }
         // the slot may still be read by the match of a frame the caller abandoned (a detect-ahead never needs this: its slot is
         // neither operand of the match in flight, and everything older has been waited for by the host)
         BM_CUDA_OK(cudaStreamWaitEvent(p->stream, p->ev_est, 0));
         BM_CUDA_OK(detect(p, d_gray, &p->kp[p->cur]));
     }
-    p->ahead_gray = nullptr;
     BmKeypoints& cur = p->kp[p->cur];
     BmKeypoints& prev = p->kp[p->prev];
     BM_CUDA_OK(cudaStreamWaitEvent(s, p->ev_det[p->cur], 0));
@@ -169,16 +182,24 @@ bm_status bm_pipeline_estimate_begin(BmPipeline* p, const uint8_t* d_gray) {
 // detectAndCompute of the NEXT frame, enqueued behind the current frame's RANSAC before the host has read its result: whichever way
 // the skip / accept decision goes (main.py:722-731), the features of the next frame are needed and depend on nothing else.  They go
 // to the third keypoint slot; the following estimate_begin with the same gray buffer only adds match + RANSAC.
-bm_status bm_pipeline_detect_ahead(BmPipeline* p, const uint8_t* d_gray) {
+bm_status bm_pipeline_detect_ahead(BmPipeline* p, const uint8_t* d_gray, int* done) {
+    if (done) *done = 0;
     if (!p->have_prev) return BM_OK;
-    const int slot = 3 - p->prev - p->cur;
-    if (slot < 0 || slot > 2 || slot == p->prev || slot == p->cur) return BM_OK;
+    for (int i = 0; i < 2; ++i) if (p->ahead_gray[i] == d_gray) { if (done) *done = 1; return BM_OK; }
+    const int e = p->ahead_gray[0] == nullptr ? 0 : (p->ahead_gray[1] == nullptr ? 1 : -1);
+    const int slot = free_kp_slot(p, true);
+    if (e < 0 || slot < 0) return BM_OK;                   // two frames are already detected ahead
+    // (the free slot is neither operand of the match in flight, and every older match has been waited for by the host)
     BM_CUDA_OK(detect(p, d_gray, &p->kp[slot]));
-    p->ahead_gray = d_gray; p->ahead_slot = slot;
+    p->ahead_gray[e] = d_gray; p->ahead_slot[e] = slot;
+    if (done) *done = 1;
     return BM_OK;
 }
 // the buffer is about to be overwritten: features detected ahead from it no longer describe its contents
-void bm_pipeline_drop_ahead(BmPipeline* p, const uint8_t* d_gray) { if (p && p->ahead_gray == d_gray) p->ahead_gray = nullptr; }
+void bm_pipeline_drop_ahead(BmPipeline* p, const uint8_t* d_gray) {
+    if (!p) return;
+    for (int i = 0; i < 2; ++i) if (p->ahead_gray[i] == d_gray) p->ahead_gray[i] = nullptr;
+}
 
 bm_status bm_pipeline_estimate_end(BmPipeline* p, bm_frame_info* info, double H_rel[9], int* have_h) {
     BM_CUDA_OK(cudaEventSynchronize(p->ev_done));           // not the stream: a detect-ahead of the next frame may be queued behind
@@ -216,7 +237,7 @@ cudaEvent_t bm_pipeline_last_detect_event(BmPipeline* p) { return p->ev_det[p->l
 bm_status bm_pipeline_warm_up(BmPipeline* p, const uint8_t* const* d_gray, int n_gray) {
     for (int i = 0; i < 2; ++i)
         for (int g = 0; g < n_gray; ++g)
-            for (int k = 0; k < 3; ++k)
+            for (int k = 0; k < BM_KP_SLOTS; ++k)
                 BM_CUDA_OK(p->is_orb ? bm_orb_detect(p->orb[i], d_gray[g], &p->kp[k], false) : bm_sift_detect(p->sift[i], d_gray[g], &p->kp[k], false));
     return BM_OK;
 }

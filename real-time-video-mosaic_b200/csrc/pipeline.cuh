@@ -12,7 +12,8 @@ bm_status bm_pipeline_first_frame(BmPipeline* p, const uint8_t* d_gray);
 bm_status bm_pipeline_estimate(BmPipeline* p, const uint8_t* d_gray, bm_frame_info* info, double H_rel[9], int* have_h);
 // split form of bm_pipeline_estimate: enqueue (no wait) / wait + read back
 bm_status bm_pipeline_estimate_begin(BmPipeline* p, const uint8_t* d_gray);
-bm_status bm_pipeline_detect_ahead(BmPipeline* p, const uint8_t* d_gray);
+#define BM_KP_SLOTS 4            // previous, current and up to two frames detected ahead
+bm_status bm_pipeline_detect_ahead(BmPipeline* p, const uint8_t* d_gray, int* done);
 void bm_pipeline_drop_ahead(BmPipeline* p, const uint8_t* d_gray);
 bm_status bm_pipeline_estimate_end(BmPipeline* p, bm_frame_info* info, double H_rel[9], int* have_h);
 // cur -> prev (main.py:756-759)

@@ -63,7 +63,7 @@ struct BmSift {
     // fork / join streams + events of the captured detect graph, and the graph cache
     cudaStream_t s2, s3;
     cudaEvent_t ev_fork, ev_l3[SIFT_MAX_OCT], ev_l5[SIFT_MAX_OCT], ev_join2, ev_join3;
-    static const int kMaxGraphs = 12;
+    static const int kMaxGraphs = 20;   // 4 frame slots x 4 keypoint slots
     SiftGraph graphs[kMaxGraphs];
     int ngraphs;
     bool graphs_enabled;

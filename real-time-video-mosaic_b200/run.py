@@ -95,18 +95,18 @@ class LazyCanvas:
 class AheadCapture:
     """cv2.VideoCapture with a one-frame-ahead reader thread (the reference's loop is
     `ret, frame = cap.read(); video_mosaic.process_frame(frame, n)`, main.py:1597-1613).  Frames are decoded by the real
-    cv2.VideoCapture on a background thread into a ring of pinned host buffers; `read()` hands out frame t while frame t+1 is
-    already decoded, and `peek_next()` lets the swapped `process_frame` stage t+1 (H2D + detect-ahead) while t is processed --
+    cv2.VideoCapture on a background thread into a ring of pinned host buffers; `read()` hands out frame t while frames t+1, t+2 are
+    already decoded, and `peek_next(2)` lets the swapped `process_frame` stage them (H2D + detect-ahead) while t is processed --
     the unmodified driver loop gets the double-buffered ingest without passing `next_frame`."""
     current = None
-    RING = 6
+    RING = 9                    # pinned buffers: 3 queued + 2 peeked + the frames the pipeline still holds
 
     def __init__(self, *args, **kw):
         import queue
         import threading
         self._cap = AheadCapture.real(*args, **kw)
-        self._q = queue.Queue(maxsize=2)
-        self._next = None
+        self._q = queue.Queue(maxsize=3)
+        self._peeked = []
         self._ring, self._slot, self._lib = [], 0, None
         self._stop = False
         self._thread = threading.Thread(target=self._worker, daemon=True)
@@ -148,16 +148,15 @@ class AheadCapture:
         return self._q.get()
 
     def read(self):
-        item = self._next if self._next is not None else self._pull()
-        self._next = None
-        return item
+        return self._peeked.pop(0) if self._peeked else self._pull()
 
-    def peek_next(self):
-        """the frame the NEXT read() will return (blocks until it is decoded), or None at the end of the stream"""
-        if self._next is None:
-            self._next = self._pull()
-        ok, f = self._next
-        return f if ok else None
+    def peek_next(self, k=1):
+        """the frames the next k (<= 2) read() calls will return (blocks until they are decoded); None in place of frames past the
+        end of the stream"""
+        while len(self._peeked) < k and not (self._peeked and not self._peeked[-1][0]):
+            self._peeked.append(self._pull())
+        out = [f if ok else None for ok, f in self._peeked[:k]]
+        return out + [None] * (k - len(out))
 
     def release(self):
         self._stop = True
@@ -182,10 +181,10 @@ def make_swapped_class(det, ahead=True):
             kw.setdefault("visualize", False)
             super().__init__(first_image, *args, **kw)
 
-        def process_frame(self, frame_cur, frame_count=0, next_frame=None):
+        def process_frame(self, frame_cur, frame_count=0, next_frame=None, next2_frame=None):
             if next_frame is None and ahead and AheadCapture.current is not None:
-                next_frame = AheadCapture.current.peek_next()
-            return super().process_frame(frame_cur, frame_count, next_frame=next_frame)
+                next_frame, next2_frame = AheadCapture.current.peek_next(2)
+            return super().process_frame(frame_cur, frame_count, next_frame=next_frame, next2_frame=next2_frame)
 
         @property
         def output_img(self):
