@@ -69,7 +69,8 @@ struct bm_mosaic_s {
     cudaStream_t stream = nullptr, s_chain = nullptr, s_copy = nullptr;
     cudaEvent_t ev_up[BM_SLOTS] = {};          // upload + ingest of the slot finished
     cudaEvent_t ev_chain[BM_SLOTS] = {};       // last chain that read the slot's BGRX finished
-    cudaEvent_t ev_spec[BM_SLOTS] = {};        // last detect-ahead that read the slot's gray plane finished (owned by the pipeline)
+    cudaEvent_t ev_spec[BM_SLOTS] = {};        // last detect-ahead that read the slot's gray plane finished (recorded on that detect's stream)
+    bool spec_used[BM_SLOTS] = {};
     int overlap = 1;                                    // 0: detect waits for the previous chain (clean chain timing)
     // frames staged ahead by bm_prefetch_frame, in the order the caller will process them: q[0] is the next frame.  Their H2D copy +
     // ingest run on the copy stream, their detectAndCompute is queued at the start of the next _end ("detect-ahead"): with two frames
@@ -145,6 +146,7 @@ extern "C" bm_status bm_create(const bm_config* cfg, bm_handle* out) {
     for (int i = 0; i < BM_SLOTS; ++i) {
         BM_CREATE_OK(cudaEventCreateWithFlags(&m->ev_up[i], cudaEventDisableTiming));
         BM_CREATE_OK(cudaEventCreateWithFlags(&m->ev_chain[i], cudaEventDisableTiming));
+        BM_CREATE_OK(cudaEventCreateWithFlags(&m->ev_spec[i], cudaEventDisableTiming));
     }
     for (int k = 0; k < 2; ++k) {            // page-locking is slow (tens of ms): at creation, not in the first bm_get_canvas
         BM_CREATE_OK(cudaHostAlloc(&m->h_cstage[k], BM_CANVAS_STAGE_BYTES, cudaHostAllocDefault));
@@ -193,7 +195,7 @@ extern "C" bm_status bm_destroy(bm_handle m) {
     bm_preview_free(&m->preview);
     for (int k = 0; k < 2; ++k) { if (m->h_cstage[k]) cudaFreeHost(m->h_cstage[k]); if (m->ev_cstage[k]) cudaEventDestroy(m->ev_cstage[k]); }
     for (int i = 0; i < bm_mosaic_s::kEvRing; ++i) { if (m->ev0[i]) cudaEventDestroy(m->ev0[i]); if (m->ev1[i]) cudaEventDestroy(m->ev1[i]); }
-    for (int i = 0; i < BM_SLOTS; ++i) { if (m->ev_up[i]) cudaEventDestroy(m->ev_up[i]); if (m->ev_chain[i]) cudaEventDestroy(m->ev_chain[i]); }
+    for (int i = 0; i < BM_SLOTS; ++i) { if (m->ev_up[i]) cudaEventDestroy(m->ev_up[i]); if (m->ev_chain[i]) cudaEventDestroy(m->ev_chain[i]); if (m->ev_spec[i]) cudaEventDestroy(m->ev_spec[i]); }
     if (m->stream) cudaStreamDestroy(m->stream);
     if (m->s_chain) cudaStreamDestroy(m->s_chain);
     if (m->s_copy) cudaStreamDestroy(m->s_copy);
@@ -221,7 +223,7 @@ static bm_status upload(bm_mosaic_s* m, const uint8_t* h_bgr, size_t stride, int
     // the slot's previous tenant: its detect finished (the host waited for it), its chain may still be reading the BGRX copy
     // (a detect-ahead of a frame the caller did not continue with may also still be reading the gray plane)
     BM_CUDA_OK(cudaStreamWaitEvent(m->s_copy, m->ev_chain[slot], 0));
-    if (m->ev_spec[slot]) BM_CUDA_OK(cudaStreamWaitEvent(m->s_copy, m->ev_spec[slot], 0));
+    if (m->spec_used[slot]) BM_CUDA_OK(cudaStreamWaitEvent(m->s_copy, m->ev_spec[slot], 0));
     bm_pipeline_drop_ahead(m->pipe, m->d_gray[slot]);
     BM_CUDA_OK(cudaMemcpyAsync(m->d_bgr[slot], src, fb, cudaMemcpyHostToDevice, m->s_copy));
     BM_CUDA_OK(cudaEventRecord(m->ev_h2d[slot], m->s_copy));
@@ -246,7 +248,7 @@ static void q_pop_front(bm_mosaic_s* m) {
 // device frame (packed BGR) -> slot, ingest on the copy stream
 static bm_status ingest_device(bm_mosaic_s* m, const uint8_t* d_bgr, int slot, cudaStream_t s) {
     BM_CUDA_OK(cudaStreamWaitEvent(s, m->ev_chain[slot], 0));              // the slot's previous chain still reads its BGRX copy
-    if (m->ev_spec[slot]) BM_CUDA_OK(cudaStreamWaitEvent(s, m->ev_spec[slot], 0));   // ... or an abandoned detect-ahead its gray plane
+    if (m->spec_used[slot]) BM_CUDA_OK(cudaStreamWaitEvent(s, m->ev_spec[slot], 0));   // ... or an abandoned detect-ahead its gray plane
     bm_pipeline_drop_ahead(m->pipe, m->d_gray[slot]);
     BM_CUDA_OK(bm_launch_ingest(d_bgr, m->cfg.frame_h, m->cfg.frame_w, m->d_gray[slot], m->d_bgrx[slot], s));
     BM_CUDA_OK(cudaEventRecord(m->ev_up[slot], s));
@@ -610,7 +612,8 @@ static bm_status detect_ahead(bm_mosaic_s* m) {
         int done = 0;
         BM_TRY(bm_pipeline_detect_ahead(m->pipe, m->d_gray[slot], &done));
         if (!done) break;                                  // no free keypoint slot yet: try again at the next frame
-        m->ev_spec[slot] = bm_pipeline_last_detect_event(m->pipe);
+        BM_CUDA_OK(bm_pipeline_record_after_last_detect(m->pipe, m->ev_spec[slot]));
+        m->spec_used[slot] = true;
         m->q[i].detected = true;
     }
     return BM_OK;

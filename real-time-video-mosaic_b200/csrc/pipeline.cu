@@ -231,6 +231,9 @@ cudaError_t bm_pipeline_sync_est(BmPipeline* p) {       // everything the pipeli
     return e;
 }
 cudaEvent_t bm_pipeline_last_detect_event(BmPipeline* p) { return p->ev_det[p->last_det_slot]; }
+// record `ev` behind the most recently queued detect, on that detect's own stream (the caller owns the event: unlike ev_det[slot] it is
+// not re-recorded when the keypoint slot is reused, so waiting on it never picks up a LATER detect)
+cudaError_t bm_pipeline_record_after_last_detect(BmPipeline* p, cudaEvent_t ev) { return cudaEventRecord(ev, p->s_det[p->det_toggle ^ 1]); }
 
 // Capture the detector graph of every (detector instance, gray buffer, keypoint slot) combination now, so that no capture /
 // instantiation (milliseconds for the ~90-node SIFT graph) lands in the first frames of a stream.  Nothing is executed.

@@ -20,7 +20,8 @@ bm_status bm_pipeline_estimate_end(BmPipeline* p, bm_frame_info* info, double H_
 void bm_pipeline_advance(BmPipeline* p);
 cudaError_t bm_pipeline_sync_est(BmPipeline* p);      // detect (two alternating streams) and match + RANSAC run on the pipeline's own streams
 bm_status bm_pipeline_warm_up(BmPipeline* p, const uint8_t* const* d_gray, int n_gray);
-cudaEvent_t bm_pipeline_last_detect_event(BmPipeline* p);   // completion of the most recently queued detect (owned by the pipeline)
+cudaEvent_t bm_pipeline_last_detect_event(BmPipeline* p);
+cudaError_t bm_pipeline_record_after_last_detect(BmPipeline* p, cudaEvent_t ev);   // `ev` completes when the most recently queued detect has   // completion of the most recently queued detect (owned by the pipeline)
 struct BmKeypoints; struct BmMatches;
 BmKeypoints* bm_pipeline_keypoints(BmPipeline* p, int which /*0 prev, 1 cur*/);
 BmMatches* bm_pipeline_matches(BmPipeline* p);
