@@ -20,7 +20,8 @@ void bm_set_error(const char* fmt, ...) {
 extern "C" const char* bm_last_error(void) { return g_err; }
 extern "C" int bm_version(void) { return 100; }
 long long g_bm_launches = 0;
-extern "C" long long bm_kernel_launches(void) { return g_bm_launches; }
+thread_local long long* t_bm_launch_sink = nullptr;
+extern "C" long long bm_kernel_launches(void) { return __atomic_load_n(&g_bm_launches, __ATOMIC_RELAXED); }
 
 #define BM_TRY(expr) do { bm_status _s = (expr); if (_s < 0) return _s; } while (0)
 
@@ -205,6 +206,7 @@ extern "C" bm_status bm_destroy(bm_handle m) {
 
 // host frame -> device (BGR packed, BGRX, gray).  Pinned sources are copied directly; pageable ones are staged.
 static bm_status upload(bm_mosaic_s* m, const uint8_t* h_bgr, size_t stride, int slot) {
+    BM_NVTX("bm:upload+ingest");
     const int fh = m->cfg.frame_h, fw = m->cfg.frame_w;
     const size_t rowb = (size_t)fw * 3, fb = rowb * fh;
     if (stride == 0) stride = rowb;
@@ -349,6 +351,7 @@ extern "C" bm_status bm_timing_read(bm_handle m, double* ms, double* bytes, int*
 }
 
 static bm_status warp_device(bm_mosaic_s* m, const uchar4* d_bgrx, const double H[9], bm_frame_info* info, bool want_flag, int slot = -1) {
+    BM_NVTX("bm:warp+blend chain");
     BmFramePlan plan;
     bm_make_plan(H, m->cfg.frame_w, m->cfg.frame_h, m->cfg.canvas_w, m->cfg.canvas_h, &plan);
     const size_t need = (size_t)bm_win_w(plan.reg) * bm_win_h(plan.reg);
@@ -625,6 +628,7 @@ static void cancel_early_begin(bm_mosaic_s* m) {
 }
 
 static bm_status finish_frame(bm_mosaic_s* m, int slot, bm_frame_info* info_out) {
+    BM_NVTX("bm:process_frame_end");
     bm_frame_info info; memset(&info, 0, sizeof(info));
     // one small D2H read of (n_matches, H_rel): the reference's control flow (skip / reject prints) needs them on the host
     double H_rel[9]; int have_h = 0;

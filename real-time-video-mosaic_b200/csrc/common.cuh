@@ -44,8 +44,17 @@ void bm_set_error(const char* fmt, ...);
         }                                                                                  \
     } while (0)
 
-extern long long g_bm_launches;          // kernels launched by this library (bench.py reports it)
-#define BM_COUNT_LAUNCHES(n) (g_bm_launches += (n))
+extern long long g_bm_launches;          // kernels launched by this library (bench.py reports it); handles may be driven from several threads
+extern thread_local long long* t_bm_launch_sink;   // non-null while this thread captures a CUDA graph: the launches are counted per replay instead
+#define BM_COUNT_LAUNCHES(n) ((void)__atomic_fetch_add(t_bm_launch_sink ? t_bm_launch_sink : &g_bm_launches, (long long)(n), __ATOMIC_RELAXED))
+
+// NVTX ranges around the stages of the per-frame path (visible in Nsight Systems / ncu --nvtx; header-only, no library needed)
+#include <nvtx3/nvToolsExt.h>
+struct BmNvtxRange {
+    explicit BmNvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~BmNvtxRange() { nvtxRangePop(); }
+};
+#define BM_NVTX(name) BmNvtxRange bm_nvtx_range_##__LINE__(name)
 
 // Opt a kernel into more than 48 KB of dynamic shared memory, once per (call site, device): the attribute is per device, and one
 // process may drive handles on several devices (bm_config.device).  `err` receives the CUDA status.

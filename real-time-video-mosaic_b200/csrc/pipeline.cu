@@ -103,6 +103,7 @@ void bm_pipeline_destroy(BmPipeline* p) {
 }
 
 static cudaError_t detect(BmPipeline* p, const uint8_t* d_gray, BmKeypoints* out) {
+    BM_NVTX("bm:detectAndCompute");
     const int slot = (int)(out - p->kp);
     const int i = p->det_toggle;
     p->det_toggle ^= 1;
@@ -202,6 +203,7 @@ void bm_pipeline_drop_ahead(BmPipeline* p, const uint8_t* d_gray) {
 }
 
 bm_status bm_pipeline_estimate_end(BmPipeline* p, bm_frame_info* info, double H_rel[9], int* have_h) {
+    BM_NVTX("bm:wait match+RANSAC");
     BM_CUDA_OK(cudaEventSynchronize(p->ev_done));           // not the stream: a detect-ahead of the next frame may be queued behind
     p->mdone = p->mcur;
     BmHostReadback* rb = p->h_rb;

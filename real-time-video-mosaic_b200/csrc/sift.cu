@@ -1250,14 +1250,15 @@ cudaError_t bm_sift_detect(BmSift* o, const uint8_t* d_gray, BmKeypoints* out, b
             return cudaGraphLaunch(o->graphs[i].exec, o->stream);
         }
     if (o->ngraphs >= BmSift::kMaxGraphs) return sift_enqueue(o, d_gray, out, true);
-    const long long before = g_bm_launches;
+    long long captured = 0;
+    t_bm_launch_sink = &captured;                            // nothing runs during capture: count the nodes, not launches
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamBeginCapture(o->stream, cudaStreamCaptureModeRelaxed);
     if (e != cudaSuccess) return e;
     e = sift_enqueue(o, d_gray, out, true);
     const cudaError_t e2 = cudaStreamEndCapture(o->stream, &graph);
-    const int launches = (int)(g_bm_launches - before);
-    g_bm_launches = before;                                   // nothing ran during capture
+    t_bm_launch_sink = nullptr;
+    const int launches = (int)captured;
     cudaGraphExec_t exec = nullptr;
     if (e == cudaSuccess && e2 == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
     else if (e == cudaSuccess) e = e2;
