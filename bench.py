@@ -347,7 +347,7 @@ def main():
         res[det].pop("vm2").close()
 
     # SIFT pyramid alone (roofline_pyramid): its kernels back to back on one stream between two CUDA events
-    pyr = None
+    pyr = mt = None
     if rank == 0:
         import ctypes as C
         gray = torch.from_numpy(np.ascontiguousarray(frames[1][:, :, 1])).cuda(local_rank)
@@ -355,6 +355,9 @@ def main():
         torch.cuda.synchronize()
         if lib.bm_sift_pyramid_ms(C.c_void_p(gray.data_ptr()), h, w, 20, C.byref(ms), C.byref(by)) == 0:
             pyr = (ms.value, by.value)
+        mt = None
+        if lib.bm_match_l2_ms(700, 700, 50, C.byref(ms), C.byref(by)) == 0:
+            mt = (ms.value, by.value)
     del dev_frames
 
     # ---------------- max over ranks, per region ----------------
@@ -370,7 +373,7 @@ def main():
     if not args.no_modes:
         modes = []
         for fn, kw in ((bench_modes.run_streams, dict(streams=64, frames=8, warmup=2)),
-                       (bench_modes.run_pairs, dict(frames=40 + world)),
+                       (bench_modes.run_pairs, dict(frames=max(40, 16 * world) + world)),
                        (bench_modes.run_tiles, dict(frames=24, warmup=2, size="3840x2160", canvas="32768x32768"))):
             try:
                 torch.cuda.empty_cache()
@@ -469,6 +472,11 @@ def main():
                     "frac": (pyr[1] / 1e9) / (pyr[0] / 1e3) / peak, "algorithmic_bytes_per_frame": pyr[1], "ms_per_frame": pyr[0],
                     "kernel": "SIFT Gaussian + DoG pyramid (k_sift_upsample + k_sift_blur<0..5> over all octaves), 256 N bytes per frame "
                               "(SURVEY 8d); the kernels back to back on one stream between two CUDA events (bm_sift_pyramid_ms)"},
+                "roofline_matcher": None if mt is None else {
+                    "bound": "tensor", "achieved": mt[1] / 1e12 / (mt[0] / 1e3), "peak": float(peaks.get("bf16_tflops", 2250.0)), "unit": "TFLOP/s",
+                    "frac": mt[1] / 1e12 / (mt[0] / 1e3) / float(peaks.get("bf16_tflops", 2250.0)), "flops_per_pair": mt[1], "ms_per_pair": mt[0],
+                    "kernel": "SIFT matcher (k_l2_knn2_tc: tcgen05 bf16 x bf16 -> f32 in TMEM, + merge, ratio test, stable sort), 700 x 700 x 128: one "
+                              "frame pair is 0.125 GFLOP -- latency bound by construction, the tensor pipe idles (SURVEY 8d)"},
                 "cpu_baseline": rm["cpu_baseline"], "frames_ok": rm["frames_ok"], "event_ms_per_step": rm["event_ms_per_step"],
                 "regions": rm["regions"],
                 "finalize": {"what": "crop_black_areas(80, 30) + scale_to_screen of the final canvas (main.py:1647-1659) via bm_finalize, "

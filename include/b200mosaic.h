@@ -197,6 +197,9 @@ bm_status bm_get_matches(bm_handle h, int* h_q, int* h_t, float* h_dist, int cap
 int bm_keypoint_capacity(void);
 /* debug / parity: level `level` of the ORB pyramid (INTER_LINEAR_EXACT chain) and its FAST score map (either may be NULL) */
 bm_status bm_orb_debug_level(const uint8_t* d_gray, int h, int w, int level, uint8_t* h_img, uint8_t* h_score, int* lw, int* lh);
+/* measurement: the SIFT matcher of main.py:687-698 (tensor-core kNN + merge + ratio + sort) on nq x nt random descriptors, CUDA-event
+ * timed on its launching stream; *flops_per_pair = 2 * nq * nt * 128 (the dense contraction north_star asks the tensor-pipe figure for) */
+bm_status bm_match_l2_ms(int nq, int nt, int reps, double* ms_per_pair, double* flops_per_pair);
 /* measurement: the SIFT Gaussian + DoG pyramid kernels alone (inside detectAndCompute, main.py:718), `reps` times between two CUDA
  * events on their launching stream; *algorithmic_bytes = 256 * h * w (six f32 levels per octave written and read once) */
 bm_status bm_sift_pyramid_ms(const uint8_t* d_gray, int h, int w, int reps, double* ms_per_frame, double* algorithmic_bytes);

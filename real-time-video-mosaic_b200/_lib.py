@@ -110,6 +110,7 @@ def load():
     _sig(lib, "bm_keypoint_capacity", i)
     _sig(lib, "bm_orb_debug_level", i, vp, i, i, i, vp, vp, ip, ip)
     _sig(lib, "bm_sift_pyramid_ms", i, vp, i, i, i, dp, dp)
+    _sig(lib, "bm_match_l2_ms", i, i, i, i, dp, dp)
     _sig(lib, "bm_sift_debug_level", i, vp, i, i, i, i, i, vp, ip, ip, ip)
     _lib = lib
     return lib

@@ -98,6 +98,40 @@ static bm_status run_match(int mode, const uint8_t* h_q, int nq, const uint8_t* 
     return BM_OK;
 }
 
+// measurement: the SIFT matcher (tcgen05 kNN + merge + ratio + sort) on nq x nt random descriptors, `reps` times between two CUDA events
+// on its launching stream; *flops = 2 * nq * nt * 128 per pair (the dense contraction)
+extern "C" bm_status bm_match_l2_ms(int nq, int nt, int reps, double* ms_per_pair, double* flops_per_pair) {
+    if (nq < 2 || nt < 2 || nq > BM_KP_CAP || nt > BM_KP_CAP || reps < 1 || !ms_per_pair) return BM_ERR_ARG;
+    BmKeypoints a, b; BmMatches m;
+    if (bm_kp_alloc(&a, 128) != 0 || bm_kp_alloc(&b, 128) != 0 || bm_matches_alloc(&m) != 0) return BM_ERR_CUDA;
+    std::vector<uint8_t> ha((size_t)nq * 128), hb((size_t)nt * 128);
+    unsigned st = 12345u;
+    for (auto* v : {&ha, &hb}) for (auto& x : *v) { st = st * 1664525u + 1013904223u; x = (uint8_t)((st >> 24) & 0x7f); }
+    cudaMemcpy(a.desc, ha.data(), ha.size(), cudaMemcpyHostToDevice); cudaMemcpy(b.desc, hb.data(), hb.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(a.count, &nq, 4, cudaMemcpyHostToDevice); cudaMemcpy(b.count, &nt, 4, cudaMemcpyHostToDevice);
+    cudaMemset(a.pt, 0, BM_KP_CAP * sizeof(float2)); cudaMemset(b.pt, 0, BM_KP_CAP * sizeof(float2));
+    cudaStream_t s = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    for (int r = -2; r < reps && e == cudaSuccess; ++r) {
+        if (r == 0) e = cudaEventRecord(e0, s);
+        if (e == cudaSuccess) e = bm_match_l2_ratio(a, b, m, 0.7, s);
+    }
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventRecord(e1, s);
+    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (s) cudaStreamDestroy(s);
+    bm_kp_free(&a); bm_kp_free(&b); bm_matches_free(&m);
+    BM_CUDA_OK(e);
+    *ms_per_pair = (double)ms / reps;
+    if (flops_per_pair) *flops_per_pair = 2.0 * nq * nt * 128.0;
+    return BM_OK;
+}
+
 extern "C" bm_status bm_match_hamming_crosscheck(const uint8_t* q, int nq, const uint8_t* t, int nt, int* oq, int* ot, float* od, int* m_out) {
     return run_match(0, q, nq, t, nt, 32, 0.0, oq, ot, od, m_out);
 }
