@@ -15,6 +15,7 @@
 //  * retainBest(700): 3-pass radix select on the float response bits (ties kept), final order = cv2's
 //    KeyPoint_LessThan order (x, y, size desc, angle, response desc, octave desc) by rank counting.
 #include "sift.cuh"
+#include "cvorder.cuh"
 #include <cuda.h>          // CUtensorMap / cuTensorMapEncodeTiled (TMA descriptors of the pyramid levels)
 #include <stdlib.h>
 #include <float.h>
@@ -32,7 +33,7 @@
 // synthetic sweep: 55 k candidates) and an overflow is reported through BmKeypoints::flags -> BM_ERR_UNSUPPORTED, never silently.
 
 struct SiftOct { int w, h; long long g[6]; long long d[5]; long long claim; };   // float offsets; claim: bit offset / 32
-struct SiftLayout { int noct; int raw_cap, cand_cap, kp_cap; SiftOct o[SIFT_MAX_OCT]; };
+struct SiftLayout { int noct; int raw_cap, cand_cap, kp_cap, order_cand_cap; SiftOct o[SIFT_MAX_OCT]; };
 
 struct SiftCand {            // refined extremum (adjustLocalExtrema output)
     int o, layer, r, c;
@@ -51,6 +52,7 @@ struct BmSift {
     size_t claim_words;
     SiftCand* cand; int* ctr;            // ctr[0] = #cand, ctr[1] = #kp (pre-select), ctr[2] = overflow, ctr[3] = #selected, ctr[4] = #raw
     unsigned* raw;           // raw extrema before refinement: o<<28 | (layer-1)<<26 | r<<13 | c
+    int* order_idx;          // [SIFT_ORDER_MAX_KP] permutation scratch of k_sift_order
     float* cresp; int* csel; // candidate responses, candidates that can survive retainBest (ctr[5] = threshold bits, ctr[7] = count, ctr[6] = #kp after pass A)
     float2* kpt; float* ksize; float* kangle; float* kresp; int* koct;     // pre-select keypoint list (lay.kp_cap)
     int* sel;                // indices of the selected keypoints
@@ -633,9 +635,13 @@ __global__ void __launch_bounds__(32 * SIFT_ORI_WARPS) k_sift_orient(SiftLayout 
     __shared__ float sh_f[SIFT_ORI_WARPS][40];
     const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int ncand = ctr[0]; if (ncand > lay.cand_cap) ncand = lay.cand_cap;
-    if (rest && (ctr[6] >= nfeatures || ctr[7] >= ncand)) return;      // pass A was enough / had everything
+    // rest == 2: EVERY candidate, for frames whose keypoints are emitted in cv2's retainBest order (that order depends on the number
+    // of orientations of every candidate); taken iff the frame has at most order_cand_cap candidates.  Passes A / B otherwise.
+    const bool exact = ncand <= lay.order_cand_cap;
+    if ((rest == 2) != exact) return;
+    if (rest == 1 && (ctr[6] >= nfeatures || ctr[7] >= ncand)) return;      // pass A was enough / had everything
   for (int ci = blockIdx.x * SIFT_ORI_WARPS + wi; ci < (rest ? ncand : ctr[7]); ci += gridDim.x * SIFT_ORI_WARPS) {
-    if (rest && __float_as_uint(cand[ci].response) >= (unsigned)ctr[5]) continue;     // done in pass A
+    if (rest == 1 && __float_as_uint(cand[ci].response) >= (unsigned)ctr[5]) continue;     // done in pass A
     const SiftCand cd = cand[rest ? ci : csel[ci]];
     const SiftOct O = lay.o[cd.o];
     const float* img = pyr + O.g[cd.layer];
@@ -733,6 +739,7 @@ __global__ void __launch_bounds__(1024) k_sift_select(int nfeatures, const int* 
     __shared__ unsigned hist[2048];
     __shared__ unsigned s_prefix, s_mask, s_remaining, s_wsum[32];
     __shared__ int s_count;
+    if (out_thr == nullptr && ctr[8]) return;            // the keypoint list was already selected in cv2's order (k_sift_order)
     int n = *n_ptr; if (n > ncap) n = ncap;
     const int tid = threadIdx.x;
     unsigned thr_bits = 0;      // keep response bits >= thr_bits
@@ -829,6 +836,69 @@ __global__ void __launch_bounds__(1024) k_sift_select(int nfeatures, const int* 
     if (tid == 0) { int m = s_count; if (m > BM_KP_CAP) { m = BM_KP_CAP; ctr[2] = 1; } *out_count = m; if (out_thr) *out_thr = thr_bits; }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// cv2's SIFT output order (frames with <= order_cand_cap candidates, i.e. every real clip we have; richer frames keep the
+// KeyPoint_LessThan order below).  SIFT_Impl::detectAndCompute does, on ALL keypoints of the frame:
+//   KeyPointsFilter::removeDuplicatedSorted  -> std::sort by (x, y, size desc, angle, response desc, octave desc)
+//   KeyPointsFilter::retainBest(nfeatures)   -> std::nth_element + std::partition by response (cvorder.cuh)
+// One CTA: bitonic sort of (x, index) pairs in shared memory with the full comparator on ties, then the retainBest emulation on the
+// responses in that order.  Duplicates cannot occur here (the claim bitmap of k_sift_refine removed them), so the "remove" half of
+// removeDuplicatedSorted is a no-op.
+// ------------------------------------------------------------------------------------------------------------------
+#define SIFT_ORDER_MAX_KP 16384
+#define SIFT_ORDER_SMEM (SIFT_ORDER_MAX_KP * 8 + 64 * 1024)
+__device__ __forceinline__ bool sift_kp_before(const float2* __restrict__ kpt, const float* __restrict__ ksize, const float* __restrict__ kangle,
+                                               const float* __restrict__ kresp, const int* __restrict__ koct, float xa, int a, float xb, int b) {
+    if (xa != xb) return xa < xb;
+    if (a == b) return false;
+    if (a < 0 || b < 0) return b < 0 && a >= 0;                      // padding sorts last
+    const float ya = kpt[a].y, yb = kpt[b].y;
+    if (ya != yb) return ya < yb;
+    if (ksize[a] != ksize[b]) return ksize[a] > ksize[b];
+    if (kangle[a] != kangle[b]) return kangle[a] < kangle[b];
+    if (kresp[a] != kresp[b]) return kresp[a] > kresp[b];
+    if (koct[a] != koct[b]) return koct[a] > koct[b];
+    return a < b;
+}
+
+__global__ void __launch_bounds__(CVO_THREADS) k_sift_order(SiftLayout lay, int nfeatures, int* __restrict__ ctr, const float2* __restrict__ kpt,
+                                                            const float* __restrict__ ksize, const float* __restrict__ kangle,
+                                                            const float* __restrict__ kresp, const int* __restrict__ koct, int* __restrict__ sel,
+                                                            int* __restrict__ scratch_idx) {
+    extern __shared__ __align__(16) unsigned char ord_smem[];
+    __shared__ CvoShared sh;
+    int ncand = ctr[0]; if (ncand > lay.cand_cap) ncand = lay.cand_cap;
+    const int n = ctr[1];
+    if (ncand > lay.order_cand_cap || n > SIFT_ORDER_MAX_KP || n > lay.kp_cap) return;      // k_sift_select + the sorting emit take over
+    const int tid = threadIdx.x;
+    float* sx = reinterpret_cast<float*>(ord_smem);                      // [np]
+    int* si = reinterpret_cast<int*>(ord_smem) + SIFT_ORDER_MAX_KP;       // [np]
+    int np = 1; while (np < n) np <<= 1;
+    for (int i = tid; i < np; i += CVO_THREADS) { sx[i] = i < n ? kpt[i].x : __int_as_float(0x7f800000); si[i] = i < n ? i : -1; }
+    __syncthreads();
+    for (int k = 2; k <= np; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < np / 2; t += CVO_THREADS) {
+                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;
+                const bool up = (lo & k) == 0;
+                const float xa = sx[lo], xb = sx[hi]; const int a = si[lo], b = si[hi];
+                const bool swap = up ? sift_kp_before(kpt, ksize, kangle, kresp, koct, xb, b, xa, a) : sift_kp_before(kpt, ksize, kangle, kresp, koct, xa, a, xb, b);
+                if (swap) { sx[lo] = xb; sx[hi] = xa; si[lo] = b; si[hi] = a; }
+            }
+            __syncthreads();
+        }
+    // sorted order -> keys (responses) for retainBest; the selection permutes scratch_idx (positions in the sorted list)
+    float* keys = sx;                                                    // reuse: x is no longer needed
+    for (int i = tid; i < n; i += CVO_THREADS) { keys[i] = kresp[si[i]]; scratch_idx[i] = i; }
+    __syncthreads();
+    CvoRows rows;
+    rows.bind(ord_smem + (size_t)SIFT_ORDER_MAX_KP * 8, cvo_rows_needed(n));
+    const int m = cvo_retain_best<float>(keys, scratch_idx, n, nfeatures, sh, rows);
+    const int mm = m > BM_KP_CAP ? BM_KP_CAP : m;
+    for (int i = tid; i < mm; i += CVO_THREADS) sel[i] = si[scratch_idx[i]];
+    if (tid == 0) { ctr[3] = mm; ctr[8] = 1; if (m > BM_KP_CAP) ctr[2] = 1; }
+}
+
 __device__ __forceinline__ bool kp_less(float ax, float ay, float as, float aa, float ar, int ao, int ai,
                                         float bx, float by, float bs, float ba, float br, int bo, int bi) {
     if (ax != bx) return ax < bx;
@@ -845,6 +915,7 @@ __global__ void __launch_bounds__(256) k_sift_emit(const int* __restrict__ ctr, 
                                                     const float* __restrict__ ksize, const float* __restrict__ kangle, const float* __restrict__ kresp,
                                                     const int* __restrict__ koct, BmKeypoints out) {
     const int m = ctr[3];
+    const bool ordered = ctr[8] != 0;                          // sel[] is already in cv2's retainBest order (k_sift_order)
     __shared__ float s_x[1024], s_y[1024], s_s[1024], s_a[1024], s_r[1024];
     __shared__ int s_o[1024], s_i[1024];
     if ((int)(blockIdx.x * blockDim.x) >= m && blockIdx.x != 0) return;      // CTA b ranks keypoints [256 b, 256 b + 256)
@@ -853,8 +924,8 @@ __global__ void __launch_bounds__(256) k_sift_emit(const int* __restrict__ ctr, 
         const int i = a < m ? sel[a] : 0;
         float2 pi = make_float2(0.f, 0.f); float si = 0.f, ai = 0.f, ri = 0.f; int oi = 0;
         if (a < m) { pi = kpt[i]; si = ksize[i]; ai = kangle[i]; ri = kresp[i]; oi = koct[i]; }
-        int rank = 0;
-        for (int b0 = 0; b0 < m; b0 += 1024) {                 // rank = number of selected keypoints ordered before this one
+        int rank = ordered ? a : 0;
+        for (int b0 = 0; b0 < (ordered ? 0 : m); b0 += 1024) {  // rank = number of selected keypoints ordered before this one
             __syncthreads();
             for (int b = b0 + threadIdx.x; b < min(m, b0 + 1024); b += blockDim.x) {
                 const int j = sel[b], q = b - b0;
@@ -1012,6 +1083,10 @@ int bm_sift_create(BmSift** out, int h, int w, int nfeatures, cudaStream_t s) {
         const long long N = (long long)w * h;
         o->lay.raw_cap = (int)(4 * N < (1LL << 21) ? (1LL << 21) : 4 * N);
         o->lay.cand_cap = o->lay.kp_cap = (int)(N / 2 < (1LL << 17) ? (1LL << 17) : N / 2);
+        // frames with at most this many candidates get cv2's exact retainBest order (needs an orientation histogram for every
+        // candidate instead of the ~nfeatures best: ~3.5 us per thousand); BM_SIFT_ORDER_CAP overrides, 0 = never
+        o->lay.order_cand_cap = 12288;
+        if (const char* e = getenv("BM_SIFT_ORDER_CAP")) o->lay.order_cand_cap = atoi(e);
     }
     long long off = 0, cbits = 0;
     int ow = bw, oh = bh;
@@ -1046,7 +1121,7 @@ int bm_sift_create(BmSift** out, int h, int w, int nfeatures, cudaStream_t s) {
               cudaMalloc(&o->ksize, (size_t)o->lay.kp_cap * 4) == cudaSuccess && cudaMalloc(&o->kangle, (size_t)o->lay.kp_cap * 4) == cudaSuccess &&
               cudaMalloc(&o->kresp, (size_t)o->lay.kp_cap * 4) == cudaSuccess && cudaMalloc(&o->koct, (size_t)o->lay.kp_cap * 4) == cudaSuccess &&
               cudaMalloc(&o->sel, BM_KP_CAP * 4) == cudaSuccess && cudaMalloc(&o->raw, (size_t)o->lay.raw_cap * 4) == cudaSuccess &&
-              cudaMalloc(&o->cresp, (size_t)o->lay.cand_cap * 4) == cudaSuccess && cudaMalloc(&o->csel, BM_KP_CAP * 4) == cudaSuccess;
+              cudaMalloc(&o->order_idx, (size_t)SIFT_ORDER_MAX_KP * 4) == cudaSuccess && cudaMalloc(&o->cresp, (size_t)o->lay.cand_cap * 4) == cudaSuccess && cudaMalloc(&o->csel, BM_KP_CAP * 4) == cudaSuccess;
     if (ok) ok = cudaMemcpyToSymbol(c_sift_k, hk, sizeof(hk)) == cudaSuccess;
     if (ok) ok = bm_stream_create(&o->s2, 1) == cudaSuccess && bm_stream_create(&o->s3, 1) == cudaSuccess &&
                  cudaEventCreateWithFlags(&o->ev_fork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&o->ev_join2, cudaEventDisableTiming) == cudaSuccess &&
@@ -1055,6 +1130,7 @@ int bm_sift_create(BmSift** out, int h, int w, int nfeatures, cudaStream_t s) {
         ok = cudaEventCreateWithFlags(&o->ev_l3[i], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&o->ev_l5[i], cudaEventDisableTiming) == cudaSuccess;
     o->graphs_enabled = true;
     if (ok) sift_make_tensor_maps(o);
+    if (ok) { cudaError_t ea; BM_SMEM_OPTIN(k_sift_order, SIFT_ORDER_SMEM, ea); ok = ea == cudaSuccess; }
     if (!ok) { bm_set_error("bm_sift_create: %s", cudaGetErrorString(cudaGetLastError())); bm_sift_destroy(o); return -1; }
     *out = o;
     return 0;
@@ -1070,7 +1146,7 @@ void bm_sift_destroy(BmSift* o) {
     if (o->ev_join3) cudaEventDestroy(o->ev_join3);
     for (int i = 0; i < SIFT_MAX_OCT; ++i) { if (o->ev_l3[i]) cudaEventDestroy(o->ev_l3[i]); if (o->ev_l5[i]) cudaEventDestroy(o->ev_l5[i]); }
     cudaFree(o->pyr); cudaFree(o->up); cudaFree(o->claim); cudaFree(o->cand); cudaFree(o->ctr); cudaFree(o->kpt); cudaFree(o->ksize);
-    cudaFree(o->kangle); cudaFree(o->kresp); cudaFree(o->koct); cudaFree(o->sel); cudaFree(o->raw); cudaFree(o->cresp); cudaFree(o->csel);
+    cudaFree(o->kangle); cudaFree(o->kresp); cudaFree(o->koct); cudaFree(o->sel); cudaFree(o->raw); cudaFree(o->cresp); cudaFree(o->csel); cudaFree(o->order_idx);
     delete o;
 }
 
@@ -1203,6 +1279,8 @@ static cudaError_t sift_enqueue(BmSift* o, const uint8_t* d_gray, BmKeypoints* o
     BM_COUNT_LAUNCHES(1), k_sift_orient<<<512, 32 * SIFT_ORI_WARPS, 0, s>>>(L, o->pyr, o->cand, o->csel, 0, o->nfeatures, o->ctr, o->kpt, o->ksize, o->kangle, o->kresp, o->koct);
     SIFT_OK(cudaMemcpyAsync(o->ctr + 6, o->ctr + 1, sizeof(int), cudaMemcpyDeviceToDevice, s));
     BM_COUNT_LAUNCHES(1), k_sift_orient<<<1024, 32 * SIFT_ORI_WARPS, 0, s>>>(L, o->pyr, o->cand, o->csel, 1, o->nfeatures, o->ctr, o->kpt, o->ksize, o->kangle, o->kresp, o->koct);
+    BM_COUNT_LAUNCHES(1), k_sift_orient<<<1024, 32 * SIFT_ORI_WARPS, 0, s>>>(L, o->pyr, o->cand, o->csel, 2, o->nfeatures, o->ctr, o->kpt, o->ksize, o->kangle, o->kresp, o->koct);
+    BM_COUNT_LAUNCHES(1), k_sift_order<<<1, CVO_THREADS, SIFT_ORDER_SMEM, s>>>(L, o->nfeatures, o->ctr, o->kpt, o->ksize, o->kangle, o->kresp, o->koct, o->sel, o->order_idx);
     BM_COUNT_LAUNCHES(1), k_sift_select<<<1, 1024, 0, s>>>(o->nfeatures, o->ctr + 1, L.kp_cap, o->ctr, o->kresp, o->sel, o->ctr + 3, nullptr);
     BM_COUNT_LAUNCHES(1), k_sift_emit<<<BM_KP_CAP / 256, 256, 0, s>>>(o->ctr, o->sel, o->kpt, o->ksize, o->kangle, o->kresp, o->koct, *out);
     BM_COUNT_LAUNCHES(1), k_sift_describe<<<1024, 256, 0, s>>>(L, o->pyr, *out);

@@ -10,9 +10,10 @@ SIFT is tolerance-based by north_star (descriptors "within a stated L2 tolerance
 repeatable: a SECOND run of the unmodified reference over this clip differs from the goldens by up to 0.88 px in the relative
 homographies (33 of 591 frames above 1e-3 px, 4 above 0.5 px, 1.15 px absolute drift; tests/golden/clip01_sift_repeatability.json) --
 cv2's orientation angles jitter by an ulp between calls and a keypoint at the 0.8-of-maximum threshold comes or goes, which
-reshuffles retainBest's order and with it the cv::RNG subsets.  Our keypoints and descriptors reproduce cv2's (tests/test_sift_gpu.py:
-100 %, descriptors exact), in KeyPoint_LessThan order rather than retainBest's, so the trajectory is held to the same kind of bar:
-median identical (< 1e-5 px), 97 % of the frames within north_star's 0.5 px, none beyond 1 px, stated drift bound on the absolute pose.
+reshuffles retainBest's order and with it the cv::RNG subsets.  Our SIFT reproduces cv2's keypoints, descriptors (tests/test_sift_gpu.py)
+and, on frames of this size, cv2's retainBest ORDER (tests/test_order_gpu.py), so the trajectory is held to the reference's own noise
+floor: median identical (< 1e-5 px), at most 60 frames above 1e-3 px (measured 32), at most 6 above north_star's 0.5 px (measured 2),
+none beyond 1 px, absolute drift below 2 px (measured 0.66).
 """
 import zlib
 
@@ -106,15 +107,15 @@ def test_sift_full_clip_tracks_reference_run(golden_dir):
     vm, status, nkp, nm, H, Hrel, ckpt = _run(frames, "sift")
     assert np.array_equal(status, g["status"])
     # keypoint / match counts: cv2's own SIFT is not bit-repeatable, ours reproduces >= 99 % of its keypoints
-    assert np.abs(nkp[1:] - g["n_kp"][1:]).max() <= 8
-    assert np.median(np.abs(nm - g["n_matches"])) <= 6 and np.abs(nm - g["n_matches"]).max() <= 40
+    assert np.abs(nkp[1:] - g["n_kp"][1:]).max() <= 4
+    assert np.median(np.abs(nm - g["n_matches"])) <= 2 and np.abs(nm - g["n_matches"]).max() <= 12
     rel = np.array([_reproj(Hrel[t], g["H_rel"][t]) for t in range(1, len(frames)) if g["status"][t] == 0])
     err = np.array([_reproj(H[t], g["H"][t]) for t in range(len(frames))])
     print(f"SIFT full clip: relative H max {rel.max():.3f} px, median {np.median(rel):.2e} px, {(rel > 1e-3).sum()} frames above 1e-3, "
           f"{(rel > 0.5).sum()} above 0.5 px; absolute drift max {err.max():.3f} px; |n_kp diff| max {np.abs(nkp[1:] - g['n_kp'][1:]).max()}, "
           f"|n_matches diff| max {np.abs(nm - g['n_matches']).max()}")
-    assert np.percentile(rel, 97) < 0.5 and rel.max() < 1.0                 # north_star: homographies within 0.5 px reprojection
-    assert err.max() < 10.0                                                 # 591 composed steps: stated drift bound on the absolute pose
+    assert np.median(rel) < 1e-5 and (rel > 1e-3).sum() <= 60 and (rel > 0.5).sum() <= 6 and rel.max() < 1.0
+    assert err.max() < 2.0                                                  # 591 composed steps: stated drift bound on the absolute pose
     d = np.abs(vm.output_img.astype(np.int16) - g["canvas_final"].astype(np.int16))
     print(f"SIFT final canvas: mean |diff| {d.mean():.3f}, > 8 levels on {(d > 8).mean() * 100:.2f} %")
-    assert d.mean() < 4.0                                                   # a 7.6 px pose drift at the end of the clip shows as ~2.6 grey levels mean
+    assert d.mean() < 2.0                                                   # measured 1.08 grey levels mean at 0.66 px of pose drift

@@ -77,3 +77,40 @@ def test_orb_order_clip_frames_and_budgets(golden_dir):
             kp_cv, des_cv = oorb.cv_detect_and_compute(gray, nf)
             assert np.array_equal(kp.astype(np.float32), kp_cv.astype(np.float32)), (t, nf)
             assert np.array_equal(des, des_cv), (t, nf)
+
+
+def test_sift_order_equals_cv2_on_clip_frames(golden_dir):
+    """SIFT keypoints in cv2's own order (removeDuplicatedSorted's sort, then retainBest = nth_element + partition) on frames of the
+    reference's clip (~1500 keypoints before retainBest).  cv2's SIFT is not perfectly repeatable (a keypoint at the 0.8-of-maximum
+    orientation threshold comes or goes, which reshuffles the whole order), so a frame counts as reproduced when ours equals ONE of
+    three cv2 runs; at least 80 % of the frames must be, and every frame must hold the same keypoint set."""
+    import cv2
+    from b200mosaic import ops
+    from oracle import sift as osift
+    cap = cv2.VideoCapture(str(golden_dir / "clip01.mp4"))
+    frames, t = [], 0
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        if t % 53 == 0:
+            frames.append(cv2.cvtColor(f, cv2.COLOR_BGR2GRAY))
+        t += 1
+    assert len(frames) >= 10
+    same_order = 0
+    for g in frames:
+        kp, des = ops.sift_detect_and_compute(torch.from_numpy(g).cuda())
+        hit = False
+        for attempt in range(3):
+            kc, dc = osift.cv_detect_and_compute(g)
+            # row for row: same keypoint (position within 1e-3 px -- ~0.5 % of the refined positions differ from cv2's by a float32
+            # ulp --, same packed octave / layer field)
+            if len(kc) == len(kp) and np.array_equal(kp[:, 5], kc[:, 5]) and np.abs(kp[:, :2] - kc[:, :2]).max() < 1e-3:
+                hit = True
+                assert np.abs(((kp[:, 3] - kc[:, 3]) + 180.0) % 360.0 - 180.0).max() < 0.01
+                assert np.linalg.norm(des.astype(np.float64) - dc.astype(np.float64), axis=1).max() <= 16.0      # descriptors row for row
+                break
+        same_order += hit
+        pairs = osift.match_keypoints(kc, kp.astype(np.float64))
+        assert len(pairs) >= len(kc) - 2
+    assert same_order >= 0.8 * len(frames), (same_order, len(frames))
