@@ -338,6 +338,10 @@ def main():
     tf = time.perf_counter()
     final_img = vm2.finalize()
     finalize_ms = 1e3 * (time.perf_counter() - tf)
+    vm2.finalize_jpeg()
+    tf = time.perf_counter()
+    jpeg_bytes = vm2.finalize_jpeg()
+    finalize_jpeg_ms = 1e3 * (time.perf_counter() - tf)
     vm2.preview()
     tf = time.perf_counter()
     thumb = vm2.preview()
@@ -424,12 +428,16 @@ def main():
                 cpus[det] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                              "sample": f"first {nf - 1} frames of the same sweep ({dt:.1f} s), detector={det}, oracle.mosaic_ref.RefMosaic = the "
                                        f"reference's cv2 {cv2.__version__}/NumPy calls minus its display-only copies, cv2.setNumThreads({cores}), IPP on"}
-        finalize_cpu_ms = preview_cpu_ms = None
+        finalize_cpu_ms = preview_cpu_ms = jpeg_cpu_ms = jpeg_same = None
         if cpus:                                          # the reference's own functions on the same canvas, same host
             from oracle import finalize as ofin
             tc = time.perf_counter()
             ofin.scale_to_screen(ofin.crop_black_areas(canvas, threshold=80, margin=30))
             finalize_cpu_ms = 1e3 * (time.perf_counter() - tc)
+            tc = time.perf_counter()
+            enc = cv2.imencode(".jpg", final_img)[1]          # what cv2.imwrite('mosaic.jpg', scaled) encodes (main.py:1664-1665)
+            jpeg_cpu_ms = 1e3 * (time.perf_counter() - tc)
+            jpeg_same = bool(enc.tobytes() == jpeg_bytes)
             try:                                          # gui.py:143-158 on the copy main.py:1630-1632 hands over (host side only)
                 from oracle import preview as opv
                 tc = time.perf_counter()
@@ -481,7 +489,11 @@ def main():
                 "regions": rm["regions"],
                 "finalize": {"what": "crop_black_areas(80, 30) + scale_to_screen of the final canvas (main.py:1647-1659) via bm_finalize, "
                                      "result copied to the host", "device_ms": finalize_ms, "out_shape": list(final_img.shape),
-                             "cpu_ms": finalize_cpu_ms},
+                             "cpu_ms": finalize_cpu_ms,
+                             "mosaic_jpg": {"what": "the same plus the JPEG file of main.py:1664-1665 encoded on the device (bm_finalize_jpeg): only the "
+                                                    "compressed file is copied to the host; cpu_ms = cv2.imencode of the scaled image alone",
+                                            "device_ms": finalize_jpeg_ms, "bytes": len(jpeg_bytes), "cpu_ms": jpeg_cpu_ms,
+                                            "identical_to_cv2": jpeg_same}},
                 "preview": {"what": "400 x 300 RGB progress thumbnail of the live canvas (gui.py:143-158: cvtColor + Pillow bicubic resize) via "
                                     "bm_preview, result copied to the host; cpu_ms excludes the full-canvas D2H the reference path would need",
                             "device_ms": preview_ms, "out_shape": list(thumb.shape), "cpu_ms": preview_cpu_ms},

@@ -113,6 +113,15 @@ bm_status bm_get_canvas(bm_handle h, uint8_t* h_bgr_out);
  * crop.  h_out == NULL only computes the sizes; otherwise h_out receives height x width x 3 BGR bytes. */
 bm_status bm_finalize(bm_handle h, int threshold, int margin, int target_w, int target_h, uint8_t* h_bgr_out, size_t cap_bytes,
                       int out_wh[2], int rect[4]);
+/* the file cv2.imwrite(os.path.join(output_dir, 'mosaic.jpg'), scaled_mosaic) writes (main.py:1664-1665), encoded on the device:
+ * baseline JPEG, 4:2:0, Annex K Huffman tables, quality as cv2's IMWRITE_JPEG_QUALITY (the reference uses the default, 95); byte for
+ * byte the output of cv2 4.13's bundled libjpeg.  bm_finalize_jpeg = bm_finalize followed by that encoder without leaving the device:
+ * only the compressed file crosses PCIe.  *nbytes = size of the file; BM_ERR_ARG with *nbytes set when cap_bytes is too small
+ * (bm_jpeg_bound(w, h) is always enough).  bm_jpeg_encode is the stage entry point for a host BGR image. */
+size_t bm_jpeg_bound(int w, int h);
+bm_status bm_jpeg_encode(const uint8_t* h_bgr, int w, int h, int quality, int device, uint8_t* h_out, size_t cap_bytes, size_t* nbytes);
+bm_status bm_finalize_jpeg(bm_handle h, int threshold, int margin, int target_w, int target_h, int quality, uint8_t* h_jpeg_out,
+                           size_t cap_bytes, size_t* nbytes, int out_wh[2], int rect[4]);
 /* live-preview thumbnail made on the device: what the GUI's progress callback computes from a full-canvas copy --
  * cv2.cvtColor(BGR2RGB), Image.fromarray, Image.resize((out_w, out_h)) with Pillow's default bicubic filter (gui.py:143-158 on the
  * copy handed over at main.py:1630-1632).  h_out receives out_h x out_w x 3 bytes, RGB when rgb != 0 (the GUI's order) else BGR. */

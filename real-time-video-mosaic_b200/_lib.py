@@ -78,6 +78,9 @@ def load():
     _sig(lib, "bm_prefetch_frame_device", i, vp, vp)
     _sig(lib, "bm_finalize", i, vp, i, i, i, i, vp, sz, ip, ip)
     _sig(lib, "bm_preview", i, vp, i, i, i, vp, sz)
+    _sig(lib, "bm_jpeg_bound", sz, i, i)
+    _sig(lib, "bm_jpeg_encode", i, vp, i, i, i, i, vp, sz, C.POINTER(sz))
+    _sig(lib, "bm_finalize_jpeg", i, vp, i, i, i, i, i, vp, sz, C.POINTER(sz), ip, ip)
     _sig(lib, "bm_warm_up", i, vp)
     _sig(lib, "bm_warp_frame_async", i, vp, vp, sz, dp)
     _sig(lib, "bm_set_overlap", i, vp, i)

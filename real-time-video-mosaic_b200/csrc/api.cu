@@ -8,6 +8,7 @@
 #include "pipeline.cuh"
 #include "finalize.cuh"
 #include "preview.cuh"
+#include "jpeg.cuh"
 #include <stdarg.h>
 #include <string.h>
 #include <math.h>
@@ -95,6 +96,7 @@ struct bm_mosaic_s {
     uint8_t* h_cstage[2] = {nullptr, nullptr};              // pinned staging of bm_get_canvas for pageable destinations
     cudaEvent_t ev_cstage[2] = {nullptr, nullptr};
     BmPreviewPlan preview;                                  // thumbnail tables / buffers, built on first use
+    BmJpeg jpeg;                                            // scratch of the mosaic.jpg encoder, built on first use
     // stitcher state (main.py:92-102)
     double H_old[9];
     double history[5][9];
@@ -194,6 +196,7 @@ extern "C" bm_status bm_destroy(bm_handle m) {
     }
     cudaFree(m->d_canvas_bgr); cudaFree(m->d_final); cudaFree(m->d_bounds); cudaFree(m->d_ghost[0]); cudaFree(m->d_ghost[1]);
     bm_preview_free(&m->preview);
+    bm_jpeg_free(&m->jpeg);
     for (int k = 0; k < 2; ++k) { if (m->h_cstage[k]) cudaFreeHost(m->h_cstage[k]); if (m->ev_cstage[k]) cudaEventDestroy(m->ev_cstage[k]); }
     for (int i = 0; i < bm_mosaic_s::kEvRing; ++i) { if (m->ev0[i]) cudaEventDestroy(m->ev0[i]); if (m->ev1[i]) cudaEventDestroy(m->ev1[i]); }
     for (int i = 0; i < BM_SLOTS; ++i) { if (m->ev_up[i]) cudaEventDestroy(m->ev_up[i]); if (m->ev_chain[i]) cudaEventDestroy(m->ev_chain[i]); if (m->ev_spec[i]) cudaEventDestroy(m->ev_spec[i]); }
@@ -468,9 +471,8 @@ extern "C" bm_status bm_get_canvas(bm_handle m, uint8_t* h_out) {
 
 // crop_black_areas(output_img, threshold, margin) + scale_to_screen(cropped, target_w, target_h) (main.py:980-1038, as called
 // at :1647-1659) on the device canvas.  h_out == NULL: only the sizes are computed (out_wh, rect), so that the caller can allocate.
-extern "C" bm_status bm_finalize(bm_handle m, int threshold, int margin, int target_w, int target_h, uint8_t* h_out, size_t cap_bytes,
-                                 int out_wh[2], int rect[4]) {
-    if (!m || !out_wh) return BM_ERR_ARG;
+// crop_black_areas + scale_to_screen of the live canvas into m->d_final (packed BGR, out_wh[0] x out_wh[1]); run = false only sizes it
+static bm_status bm_finalize_device(bm_handle m, int threshold, int margin, int target_w, int target_h, bool run, int out_wh[2], int rect[4]) {
     BM_CUDA_OK(cudaSetDevice(m->cfg.device));
     const int cw = m->cfg.canvas_w, ch = m->cfg.canvas_h;
     if (!m->d_bounds) BM_CUDA_OK(cudaMalloc(&m->d_bounds, 4 * sizeof(int)));
@@ -495,18 +497,73 @@ extern "C" bm_status bm_finalize(bm_handle m, int threshold, int margin, int tar
     if (nw < 1) nw = 1;
     if (nh < 1) nh = 1;
     out_wh[0] = nw; out_wh[1] = nh;
-    if (!h_out) return BM_OK;
+    if (!run) return BM_OK;
     const size_t need = (size_t)nw * nh * 3;
-    if (cap_bytes < need) { bm_set_error("bm_finalize: output buffer too small (%zu < %zu)", cap_bytes, need); return BM_ERR_ARG; }
     if (m->final_cap < need) {
         cudaFree(m->d_final); m->d_final = nullptr; m->final_cap = 0;
         BM_CUDA_OK(cudaMalloc(&m->d_final, need + 16));
         m->final_cap = need;
     }
     BM_CUDA_OK(bm_launch_resize_linear(m->blend.canvas, cw, x, y, w, h, m->d_final, nw, nh, m->s_chain));
+    return BM_OK;
+}
+
+extern "C" bm_status bm_finalize(bm_handle m, int threshold, int margin, int target_w, int target_h, uint8_t* h_out, size_t cap_bytes,
+                                 int out_wh[2], int rect[4]) {
+    if (!m || !out_wh) return BM_ERR_ARG;
+    if (!h_out) return bm_finalize_device(m, threshold, margin, target_w, target_h, false, out_wh, rect);
+    bm_status st = bm_finalize_device(m, threshold, margin, target_w, target_h, false, out_wh, rect);
+    if (st != BM_OK) return st;
+    const size_t need = (size_t)out_wh[0] * out_wh[1] * 3;
+    if (cap_bytes < need) { bm_set_error("bm_finalize: output buffer too small (%zu < %zu)", cap_bytes, need); return BM_ERR_ARG; }
+    st = bm_finalize_device(m, threshold, margin, target_w, target_h, true, out_wh, rect);
+    if (st != BM_OK) return st;
     BM_CUDA_OK(cudaMemcpyAsync(h_out, m->d_final, need, cudaMemcpyDeviceToHost, m->s_chain));
     BM_CUDA_OK(cudaStreamSynchronize(m->s_chain));
     return BM_OK;
+}
+
+// header + stuffed scan (already in j->out) + EOI -> host
+static bm_status bm_jpeg_assemble(BmJpeg* j, int w, int h, int quality, size_t scan_bytes, uint8_t* h_out, size_t cap, size_t* nbytes, cudaStream_t s) {
+    uint8_t hdr[BM_JPEG_HEADER_MAX];
+    const size_t nh = bm_jpeg_write_header(hdr, w, h, quality), total = nh + scan_bytes + 2;
+    *nbytes = total;
+    if (cap < total) { bm_set_error("jpeg: output buffer too small (%zu < %zu)", cap, total); return BM_ERR_ARG; }
+    memcpy(h_out, hdr, nh);
+    if (scan_bytes) BM_CUDA_OK(cudaMemcpyAsync(h_out + nh, j->out, scan_bytes, cudaMemcpyDeviceToHost, s));
+    BM_CUDA_OK(cudaStreamSynchronize(s));
+    h_out[nh + scan_bytes] = 0xFF; h_out[nh + scan_bytes + 1] = 0xD9;
+    return BM_OK;
+}
+
+extern "C" size_t bm_jpeg_bound(int w, int h) { return BM_JPEG_HEADER_MAX + bm_jpeg_scan_bound(w, h) + 2; }
+
+// cv2.imwrite(path, img) / cv2.imencode('.jpg', img) of a host BGR image, encoded on `device` (stage entry point; main.py:1664-1665)
+extern "C" bm_status bm_jpeg_encode(const uint8_t* h_bgr, int w, int h, int quality, int device, uint8_t* h_out, size_t cap_bytes, size_t* nbytes) {
+    if (!h_bgr || !h_out || !nbytes || w < 1 || h < 1 || w > 65535 || h > 65535) { bm_set_error("bm_jpeg_encode: bad args"); return BM_ERR_ARG; }
+    BM_CUDA_OK(cudaSetDevice(device));
+    BmJpeg j; uint8_t* d_img = nullptr; cudaStream_t s = nullptr; size_t scan = 0;
+    bm_status st = BM_ERR_CUDA;
+    cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&d_img, (size_t)w * h * 3);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_img, h_bgr, (size_t)w * h * 3, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = bm_jpeg_encode_scan(&j, d_img, w, h, (size_t)w * 3, quality, &scan, s);
+    if (e == cudaSuccess) st = bm_jpeg_assemble(&j, w, h, quality, scan, h_out, cap_bytes, nbytes, s);
+    else bm_set_error("bm_jpeg_encode: %s", cudaGetErrorString(e));
+    bm_jpeg_free(&j); cudaFree(d_img);
+    if (s) cudaStreamDestroy(s);
+    return st;
+}
+
+// main.py:1647-1666 in one call: crop_black_areas + scale_to_screen + the bytes of cv2.imwrite('mosaic.jpg', scaled), all on the device
+extern "C" bm_status bm_finalize_jpeg(bm_handle m, int threshold, int margin, int target_w, int target_h, int quality, uint8_t* h_jpeg_out,
+                                      size_t cap_bytes, size_t* nbytes, int out_wh[2], int rect[4]) {
+    if (!m || !out_wh || !h_jpeg_out || !nbytes) return BM_ERR_ARG;
+    bm_status st = bm_finalize_device(m, threshold, margin, target_w, target_h, true, out_wh, rect);
+    if (st != BM_OK) return st;
+    size_t scan = 0;
+    BM_CUDA_OK(bm_jpeg_encode_scan(&m->jpeg, m->d_final, out_wh[0], out_wh[1], (size_t)out_wh[0] * 3, quality, &scan, m->s_chain));
+    return bm_jpeg_assemble(&m->jpeg, out_wh[0], out_wh[1], quality, scan, h_jpeg_out, cap_bytes, nbytes, m->s_chain);
 }
 
 // Thumbnail of the live canvas for progress callbacks: cv2.cvtColor(BGR2RGB) + PIL Image.resize((out_w, out_h)) of output_img

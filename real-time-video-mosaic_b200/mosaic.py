@@ -253,6 +253,20 @@ class VideMosaic:
         self.last_crop_rect = tuple(rect)
         return out
 
+    def finalize_jpeg(self, threshold=80, margin=30, target_w=None, target_h=None, quality=95):
+        """main.py:1647-1666 in one device pass: crop_black_areas + scale_to_screen + the bytes cv2.imwrite('mosaic.jpg', scaled) writes
+        (baseline JPEG, default quality 95; byte-identical to cv2's file).  Only the compressed file is copied to the host.
+        Returns `bytes`; `self.last_crop_rect`, `self.last_final_size` = (w, h) describe the image inside."""
+        wh = (C.c_int * 2)(); rect = (C.c_int * 4)(); n = C.c_size_t(0)
+        tw, th = (int(target_w), int(target_h)) if target_w and target_h else (0, 0)
+        _lib.check(self._lib.bm_finalize(self._h, int(threshold), int(margin), tw, th, None, 0, wh, rect), "bm_finalize")
+        out = np.empty(self._lib.bm_jpeg_bound(wh[0], wh[1]), dtype=np.uint8)
+        _lib.check(self._lib.bm_finalize_jpeg(self._h, int(threshold), int(margin), tw, th, int(quality), out.ctypes.data_as(C.c_void_p),
+                                              out.nbytes, C.byref(n), wh, rect), "bm_finalize_jpeg")
+        self.last_crop_rect = tuple(rect)
+        self.last_final_size = (wh[0], wh[1])
+        return out[:n.value].tobytes()
+
     def preview(self, size=(400, 300), rgb=True):
         """Thumbnail of the live canvas made on the device: bit-identical to what the GUI computes from `output_img.copy()`
         (main.py:1630-1632 -> gui.py:143-158: cv2.cvtColor(BGR2RGB), Image.fromarray(...).resize(size), Pillow's default bicubic),

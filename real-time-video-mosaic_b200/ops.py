@@ -110,6 +110,19 @@ def cv_retain_best(resp: np.ndarray, n_points: int, as_u8: bool = False) -> np.n
     return out[:m.value].astype(np.int64)
 
 
+def jpeg_encode(bgr: np.ndarray, quality: int = 95, device: int = 0) -> bytes:
+    """the bytes cv2.imwrite(path, bgr) / cv2.imencode('.jpg', bgr) produce (main.py:1664-1665 writes mosaic.jpg with the default
+    quality 95), encoded on the device: baseline JPEG, 4:2:0, Annex K tables, byte for byte cv2 4.13's libjpeg output."""
+    lib = _lib.load()
+    img = np.ascontiguousarray(bgr)
+    if img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] != 3:
+        raise ValueError("jpeg_encode: expected an (h, w, 3) uint8 BGR image")
+    h, w = img.shape[:2]
+    out = np.empty(lib.bm_jpeg_bound(w, h), np.uint8); n = C.c_size_t(0)
+    _lib.check(lib.bm_jpeg_encode(_np_ptr(img), w, h, int(quality), int(device), _np_ptr(out), out.nbytes, C.byref(n)), "bm_jpeg_encode")
+    return out[:n.value].tobytes()
+
+
 def match_hamming_crosscheck(des_q: np.ndarray, des_t: np.ndarray):
     """BFMatcher(NORM_HAMMING, crossCheck=True).match + sorted(key=distance) (main.py:694-698). -> (m,3) float64."""
     lib = _lib.load()

@@ -255,6 +255,38 @@ def install_device_finalize(ref):
         return ref_scale(image, target_w, target_h)
 
     ref.crop_black_areas, ref.scale_to_screen = crop_black_areas, scale_to_screen
+    install_device_imwrite(ref)
+
+
+def install_device_imwrite(ref):
+    """main() ends with cv2.imwrite(os.path.join(output_dir, 'mosaic.jpg'), scaled_mosaic) (main.py:1664-1665; navigation_map.jpg at
+    :1696-1697 likewise).  Inside the reference module only, `cv2` becomes a pass-through proxy whose imwrite encodes 3-channel 8-bit
+    images going to .jpg / .jpeg with default parameters on the device (`ops.jpeg_encode`: the same bytes libjpeg writes) and hands
+    everything else -- other formats, explicit parameters, any failure of the device path -- to the real cv2.imwrite."""
+    import numpy as np
+    from . import ops
+    real = ref.cv2
+
+    class _Cv2Proxy:
+        def __getattr__(self, name):
+            return getattr(real, name)
+
+        @staticmethod
+        def imwrite(path, img, params=None):
+            if (params is None and isinstance(img, np.ndarray) and img.dtype == np.uint8 and img.ndim == 3 and img.shape[2] == 3
+                    and img.size > 0 and str(path).lower().endswith((".jpg", ".jpeg"))):
+                try:
+                    data = ops.jpeg_encode(img)
+                    with open(path, "wb") as f:
+                        f.write(data)
+                    return True
+                except OSError:
+                    return False                         # cv2.imwrite reports an unwritable path the same way
+                except Exception:
+                    pass
+            return real.imwrite(path, img) if params is None else real.imwrite(path, img, params)
+
+    ref.cv2 = _Cv2Proxy()
 
 
 if __name__ == "__main__":

@@ -21,7 +21,7 @@ def _stand_in_main():
     ref.log = {}
 
     def main(video_path, show_intermediate=False, output_dir=None, max_frames=40):
-        cap = cv2.VideoCapture(video_path)                                   # main.py:1579 (looked up at call time)
+        cap = ref.cv2.VideoCapture(video_path)                               # main.py:1579 (the module global `cv2`, looked up at call time)
         ret, first = cap.read()
         vm = ref.VideMosaic(first, detector_type="sift", show_intermediate=show_intermediate, output_dir=output_dir)   # :1603
         n = 0
@@ -35,7 +35,7 @@ def _stand_in_main():
         cropped = ref.crop_black_areas(vm.output_img, threshold=80, margin=30)   # :1649
         ref.log["cropped_shape"] = cropped.shape
         scaled = ref.scale_to_screen(cropped)                                # :1656
-        cv2.imwrite(str(output_dir) + "/mosaic.jpg", scaled)                 # :1663
+        ref.cv2.imwrite(str(output_dir) + "/mosaic.jpg", scaled)             # :1663-1665
         ref.log["scaled"] = scaled
         ref.log["full"] = vm.output_img.astype(np.uint8)                     # :1670
         ref.log["vm"] = vm
@@ -70,7 +70,10 @@ def test_launcher_swap_with_read_ahead_and_device_finalize(golden_dir, tmp_path,
     want = ofin.scale_to_screen(ofin.crop_black_areas(full, threshold=80, margin=30))
     assert np.array_equal(ref.log["scaled"], want)
     assert ref.log["cropped_shape"] == ofin.crop_black_areas(full, threshold=80, margin=30).shape
-    assert (tmp_path / "mosaic.jpg").exists()
+    # mosaic.jpg was encoded on the device (the launcher's cv2.imwrite proxy): the file cv2 itself would have written, byte for byte
+    ok, enc = cv2.imencode(".jpg", ref.log["scaled"])
+    assert ok and (tmp_path / "mosaic.jpg").read_bytes() == enc.tobytes()
+    assert ref.cv2.imwrite(str(tmp_path / "other.png"), ref.log["scaled"]) and (tmp_path / "other.png").exists()   # everything else passes through
     # same mosaic with and without the reader thread, and equal to direct class use
     cap = real_cap(str(golden_dir / "clip01.mp4"))
     frames = [cap.read()[1] for _ in range(41)]
