@@ -20,7 +20,7 @@ LIBDIR = HERE / "lib"
 LIB = LIBDIR / "libb200mosaic.so"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-         "--expt-relaxed-constexpr", "-Xptxas", "-v", "--fmad=false"]
+         "--expt-relaxed-constexpr", "-Xptxas", "-v", "--fmad=false"] + os.environ.get("BM_EXTRA_NVCC_FLAGS", "").split()
 # --fmad=false: the parity-critical kernels spell every FMA explicitly (__fmaf_rn); the compiler must not contract the
 # rest (OpenCV's scalar code paths are not contracted either).
 

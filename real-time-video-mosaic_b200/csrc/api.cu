@@ -11,10 +11,16 @@
 #include "jpeg.cuh"
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 #include <math.h>
 #include <new>
 
 static thread_local char g_err[512] = "";
+bool bm_pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("BM_NO_PDL"); return !(e && e[0] == '1'); }();
+    return on;
+}
+
 void bm_set_error(const char* fmt, ...) {
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
 }
@@ -30,7 +36,7 @@ extern "C" long long bm_kernel_launches(void) { return __atomic_load_n(&g_bm_lau
 // handle
 // ------------------------------------------------------------------------------------------------------------------
 static void free_blend(BmBlendBufs& b) {
-    cudaFree(b.canvas); cudaFree(b.wbuf); cudaFree(b.wn); cudaFree(b.wo); cudaFree(b.flags);
+    cudaFree(b.canvas); cudaFree(b.wbuf); cudaFree(b.wno); cudaFree(b.flags);
     bm_dt_free_plane(&b.dt.p[0]); bm_dt_free_plane(&b.dt.p[1]);
     memset(&b, 0, sizeof(b));
 }
@@ -46,8 +52,7 @@ static bm_status alloc_blend(BmBlendBufs& b, int canvas_h, int canvas_w, size_t 
     BM_CUDA_OK(bm_dt_alloc_plane(&b.dt.p[0], canvas_w, canvas_h, n));
     BM_CUDA_OK(bm_dt_alloc_plane(&b.dt.p[1], canvas_w, canvas_h, scratch_px));
     BM_CUDA_OK(cudaMalloc(&b.wbuf, (scratch_px + pad) * sizeof(uchar4)));
-    BM_CUDA_OK(cudaMalloc(&b.wn, (scratch_px + pad) * sizeof(float)));
-    BM_CUDA_OK(cudaMalloc(&b.wo, (scratch_px + pad) * sizeof(float)));
+    BM_CUDA_OK(cudaMalloc(&b.wno, (scratch_px + pad) * sizeof(float2)));
     BM_CUDA_OK(cudaMalloc(&b.flags, 16 * sizeof(int)));
     BM_CUDA_OK(cudaMemset(b.canvas, 0, n * sizeof(uchar4)));
     BM_CUDA_OK(cudaMemset(b.flags, 0, 16 * sizeof(int)));

@@ -35,6 +35,7 @@ struct DtRange { int xa[2], xb[2]; };
 __global__ void __launch_bounds__(256) k_rowscan_bgrx(const uchar4* __restrict__ img, int img_stride, int img_col0, int img_row0,
                                                       uint32_t* __restrict__ g, int gs, int n, int row0, const int* __restrict__ flags,
                                                       int need_flag) {
+    BM_PDL_TRIGGER(); BM_PDL_WAIT();
     if (need_flag && flags[0] == 0) return;
     const int r = blockIdx.x, tid = threadIdx.x;
     const uchar4* row = img + (size_t)(img_row0 + r) * img_stride + img_col0;
@@ -157,6 +158,7 @@ struct DtNoRow { __device__ __forceinline__ void operator()(int, const u32 (&)[4
 // phase 1: block-local diagonal sweeps.  CTA = 2 tiles x {down, up}: one warp per (tile, direction)
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_dt_local(BmDtPlane p, int kb0, const int* __restrict__ flags, int need_flag) {
+    BM_PDL_TRIGGER(); BM_PDL_WAIT();
     if (need_flag && flags[0] == 0) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x * 2 + (warp >> 1), k = kb0 + blockIdx.y;
@@ -194,6 +196,7 @@ __device__ __forceinline__ u32 dt_ghost_vert(const BmDtPlane& p, bool down, int 
 // phase 2: diagonal carries.  type 0: down, from x-16; 1: down, from x+16; 2: up, from x-16; 3: up, from x+16
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_dt_diag_chain(BmDtPair pp, const int* __restrict__ flags, int need_flag) {
+    BM_PDL_TRIGGER(); BM_PDL_WAIT();
     if (need_flag && flags[0] == 0) return;
     const BmDtPlane& p = pp.p[blockIdx.z];
     const int type = blockIdx.y;
@@ -253,6 +256,7 @@ __device__ __forceinline__ void dt_chain_seg(const u32* __restrict__ L, u32* __r
 
 template <int DT_SEG>
 __global__ void __launch_bounds__(512) k_dt_diag_chain16(BmDtPair pp, const int* __restrict__ flags, int need_flag) {
+    BM_PDL_TRIGGER(); BM_PDL_WAIT();
     if (need_flag && flags[0] == 0) return;
     const BmDtPlane& p = pp.p[blockIdx.z];
     const int type = blockIdx.y;
@@ -270,6 +274,7 @@ __global__ void __launch_bounds__(512) k_dt_diag_chain16(BmDtPair pp, const int*
 
 template <int DT_SEG>
 __global__ void __launch_bounds__(512) k_dt_vert_chain16(BmDtPair pp, DtRange rg, const int* __restrict__ flags, int need_flag) {
+    BM_PDL_TRIGGER(); BM_PDL_WAIT();
     if (need_flag && flags[0] == 0) return;
     const int pl = blockIdx.z;
     const BmDtPlane& p = pp.p[pl];
@@ -285,6 +290,7 @@ __global__ void __launch_bounds__(512) k_dt_vert_chain16(BmDtPair pp, DtRange rg
 // phase 3: diagonal sweeps with carries -> block-local vertical sweep
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_dt_vert_local(BmDtPair pp, DtRange rg, const int* __restrict__ flags, int need_flag) {
+    BM_PDL_TRIGGER(); BM_PDL_WAIT();
     if (need_flag && flags[0] == 0) return;
     const int pl = blockIdx.z;
     const BmDtPlane& p = pp.p[pl];
@@ -308,6 +314,7 @@ __global__ void __launch_bounds__(128) k_dt_vert_local(BmDtPair pp, DtRange rg, 
 // phase 4: vertical carries, in place.  type 0: down, 1: up
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_dt_vert_chain(BmDtPair pp, DtRange rg, const int* __restrict__ flags, int need_flag) {
+    BM_PDL_TRIGGER(); BM_PDL_WAIT();
     if (need_flag && flags[0] == 0) return;
     const int pl = blockIdx.z;
     const BmDtPlane& p = pp.p[pl];
@@ -365,8 +372,9 @@ __global__ void __launch_bounds__(64) k_dt_map(BmDtPlane p, float* __restrict__ 
 }
 
 // (dn/s, do/s) in float32 exactly as NumPy does it (main.py:892-894): dist = uint * 2^-16, s = (dn + do) + 1e-6f
-__global__ void __launch_bounds__(128) k_dt_weights(BmDtPair pp, BmFramePlan plan, float* __restrict__ wn, float* __restrict__ wo,
+__global__ void __launch_bounds__(128) k_dt_weights(BmDtPair pp, BmFramePlan plan, float2* __restrict__ wno,
                                                     const int* __restrict__ flags) {
+    BM_PDL_TRIGGER(); BM_PDL_WAIT();
     if (flags[0] == 0) return;
     __shared__ __align__(16) u32 T[4][BM_BLK_ROWS][DT_TW];      // old down, old up, new down, new up
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -390,8 +398,7 @@ __global__ void __launch_bounds__(128) k_dt_weights(BmDtPair pp, BmFramePlan pla
         const float dold = __fmul_rn(__uint2float_rn(d_old), scale);
         const float s = __fadd_rn(__fadd_rn(dn, dold), 1e-6f);
         const size_t o = (size_t)(y - plan.reg.y0) * plan.rws + (x - plan.rx0);
-        wn[o] = __fdiv_rn(dn, s);
-        wo[o] = __fdiv_rn(dold, s);
+        wno[o] = make_float2(__fdiv_rn(dn, s), __fdiv_rn(dold, s));
     }
 }
 
@@ -429,8 +436,8 @@ cudaError_t bm_launch_rowscan_bgrx(const uchar4* img, int img_stride, int img_co
                                    const int* flags, int need_flag, cudaStream_t s) {
     if (nrows <= 0) return cudaSuccess;
     if (p.W > BM_ROWSCAN_CHUNK * BM_ROWSCAN_MAX_CHUNKS) return cudaErrorInvalidValue;
-    BM_COUNT_LAUNCHES(1), k_rowscan_bgrx<<<nrows, 256, 0, s>>>(img, img_stride, img_col0, img_row0, p.g, p.gs, p.W, row0, flags, need_flag);
-    return cudaGetLastError();
+    BM_COUNT_LAUNCHES(1);
+    return bm_launch_pdl(k_rowscan_bgrx, dim3(nrows), dim3(256), 0, s, img, img_stride, img_col0, img_row0, p.g, p.gs, p.W, row0, flags, need_flag);
 }
 
 cudaError_t bm_launch_rowscan_u8(const uint8_t* mask, int stride, const BmDtPlane& p, cudaStream_t s) {
@@ -443,8 +450,8 @@ static inline int dt_tiles(int width) { return bm_div_up(width, BM_DT_TILE_VALID
 
 cudaError_t bm_launch_dt_local(const BmDtPlane& p, int kb0, int kb1, const int* flags, int need_flag, cudaStream_t s) {
     if (kb1 <= kb0) return cudaSuccess;
-    BM_COUNT_LAUNCHES(1), k_dt_local<<<dim3(bm_div_up(dt_tiles(p.W), 2), kb1 - kb0), 128, 0, s>>>(p, kb0, flags, need_flag);
-    return cudaGetLastError();
+    BM_COUNT_LAUNCHES(1);
+    return bm_launch_pdl(k_dt_local, dim3(bm_div_up(dt_tiles(p.W), 2), kb1 - kb0), dim3(128), 0, s, p, kb0, flags, need_flag);
 }
 
 cudaError_t bm_launch_dt_carries(const BmDtPair& pp, int nplanes, const int xa[2], const int xb[2], const int* flags, int need_flag,
@@ -466,20 +473,24 @@ cudaError_t bm_launch_dt_carries(const BmDtPair& pp, int nplanes, const int xa[2
     const bool par = max_nb <= 1024 && pp.p[0].tsz < ((size_t)1 << 31) && pp.p[1].tsz < ((size_t)1 << 31);
     const int seg = max_nb <= 256 ? 8 : 32;
     const int chain_threads = 32 * bm_div_up(bm_div_up(max_nb, seg), 2);        // 16 lines x ceil(nb / seg) segments
-    if (par && seg == 8) BM_COUNT_LAUNCHES(1), k_dt_diag_chain16<8><<<dim3(bm_div_up(max_lines, 16), 4, nplanes), chain_threads, 0, s>>>(pp, flags, need_flag);
-    else if (par) BM_COUNT_LAUNCHES(1), k_dt_diag_chain16<32><<<dim3(bm_div_up(max_lines, 16), 4, nplanes), chain_threads, 0, s>>>(pp, flags, need_flag);
-    else BM_COUNT_LAUNCHES(1), k_dt_diag_chain<<<dim3(bm_div_up(max_lines, 128), 4, nplanes), 128, 0, s>>>(pp, flags, need_flag);
-    BM_COUNT_LAUNCHES(1), k_dt_vert_local<<<dim3(bm_div_up(max_tiles, 2), max_nb, nplanes), 128, 0, s>>>(pp, rg, flags, need_flag);
-    if (par && seg == 8) BM_COUNT_LAUNCHES(1), k_dt_vert_chain16<8><<<dim3(bm_div_up(max_cols, 16), 2, nplanes), chain_threads, 0, s>>>(pp, rg, flags, need_flag);
-    else if (par) BM_COUNT_LAUNCHES(1), k_dt_vert_chain16<32><<<dim3(bm_div_up(max_cols, 16), 2, nplanes), chain_threads, 0, s>>>(pp, rg, flags, need_flag);
-    else BM_COUNT_LAUNCHES(1), k_dt_vert_chain<<<dim3(bm_div_up(max_cols, 128), 2, nplanes), 128, 0, s>>>(pp, rg, flags, need_flag);
-    return cudaGetLastError();
+    BM_COUNT_LAUNCHES(3);
+    cudaError_t e;
+    const dim3 gd(bm_div_up(max_lines, 16), 4, nplanes), gv(bm_div_up(max_cols, 16), 2, nplanes);
+    if (par && seg == 8) e = bm_launch_pdl(k_dt_diag_chain16<8>, gd, dim3(chain_threads), 0, s, pp, flags, need_flag);
+    else if (par) e = bm_launch_pdl(k_dt_diag_chain16<32>, gd, dim3(chain_threads), 0, s, pp, flags, need_flag);
+    else e = bm_launch_pdl(k_dt_diag_chain, dim3(bm_div_up(max_lines, 128), 4, nplanes), dim3(128), 0, s, pp, flags, need_flag);
+    if (e != cudaSuccess) return e;
+    if ((e = bm_launch_pdl(k_dt_vert_local, dim3(bm_div_up(max_tiles, 2), max_nb, nplanes), dim3(128), 0, s, pp, rg, flags, need_flag)) != cudaSuccess) return e;
+    if (par && seg == 8) e = bm_launch_pdl(k_dt_vert_chain16<8>, gv, dim3(chain_threads), 0, s, pp, rg, flags, need_flag);
+    else if (par) e = bm_launch_pdl(k_dt_vert_chain16<32>, gv, dim3(chain_threads), 0, s, pp, rg, flags, need_flag);
+    else e = bm_launch_pdl(k_dt_vert_chain, dim3(bm_div_up(max_cols, 128), 2, nplanes), dim3(128), 0, s, pp, rg, flags, need_flag);
+    return e;
 }
 
-cudaError_t bm_launch_dt_weights(const BmDtPair& pp, const BmFramePlan& plan, float* wn, float* wo, const int* flags, cudaStream_t s) {
+cudaError_t bm_launch_dt_weights(const BmDtPair& pp, const BmFramePlan& plan, float2* wno, const int* flags, cudaStream_t s) {
     const int nyb = (plan.reg.y1 - 1) / BM_BLK_ROWS - plan.reg.y0 / BM_BLK_ROWS + 1;
-    BM_COUNT_LAUNCHES(1), k_dt_weights<<<dim3(dt_tiles(plan.reg.x1 - plan.rx0), nyb), 128, 0, s>>>(pp, plan, wn, wo, flags);
-    return cudaGetLastError();
+    BM_COUNT_LAUNCHES(1);
+    return bm_launch_pdl(k_dt_weights, dim3(dt_tiles(plan.reg.x1 - plan.rx0), nyb), dim3(128), 0, s, pp, plan, wno, flags);
 }
 
 cudaError_t bm_launch_dt_export_carries(const BmDtPlane& p, int up, int block, uint32_t* d_out, cudaStream_t s) {

@@ -50,8 +50,8 @@ cudaError_t bm_launch_dt_local(const BmDtPlane& p, int kb0, int kb1, const int* 
 // diagonal carries + local vertical sweeps + vertical carries; column range [xa, xb) per plane (xa multiple of 4)
 cudaError_t bm_launch_dt_carries(const BmDtPair& pp, int nplanes, const int xa[2], const int xb[2], const int* flags, int need_flag,
                                  cudaStream_t s);
-// (dn/s, do/s) over R (main.py:888-894) -> two float planes with origin (plan.rx0, plan.reg.y0) and row stride plan.rws
-cudaError_t bm_launch_dt_weights(const BmDtPair& pp, const BmFramePlan& plan, float* wn, float* wo, const int* flags, cudaStream_t s);
+// (dn/s, do/s) over R (main.py:888-894) -> one plane of (w_new, w_old) pairs with origin (plan.rx0, plan.reg.y0) and row stride plan.rws
+cudaError_t bm_launch_dt_weights(const BmDtPair& pp, const BmFramePlan& plan, float2* wno, const int* flags, cudaStream_t s);
 // canvas-plane carries over the full width, then the three carry rows (E1, E2, V) a neighbouring tile needs: downward sweeps at the
 // last row of block `block` (up == 0) or upward sweeps at the first row of block `block` (up == 1) -> d_out [3][p.W]
 cudaError_t bm_launch_dt_export_carries(const BmDtPlane& p, int up, int block, uint32_t* d_out, cudaStream_t s);

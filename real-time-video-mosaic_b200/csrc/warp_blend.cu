@@ -195,6 +195,7 @@ __device__ __forceinline__ uchar4 warp_sample_bgrx(const uchar4* __restrict__ sr
 // of mask_new from the mask bits still in registers.
 __global__ void __launch_bounds__(256) k_warp_rows(const uchar4* __restrict__ src, BmFramePlan plan, const uchar4* __restrict__ canvas,
                                                    uchar4* __restrict__ wbuf, uint32_t* __restrict__ g_new, int gs, int* __restrict__ flags) {
+    BM_PDL_TRIGGER();                                           // first kernel of the chain (follows a memset): nothing to wait for
     const int ly = blockIdx.x, tid = threadIdx.x;
     const int ww = bm_win_w(plan.win), y = plan.win.y0 + ly;
     const int nch = (ww + BM_ROWSCAN_CHUNK - 1) / BM_ROWSCAN_CHUNK;
@@ -265,30 +266,55 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 }
 
 // K4: GaussianBlur(31) of both weight planes + blend + canvas update, one kernel.  CTA = 64 x 64 output pixels of W (512 threads).
-// Per weight plane: tile with a 15 px halo (reflect-101 at the canvas border) -> shared memory; row pass, 8 consecutive
-// outputs per thread from a 38-value register window (cv2 order: tap 0 product, then FMAs left to right); column pass,
-// 8 consecutive outputs per thread from a 38-value window (cv2's symmetric FMA form).  Then the blend of main.py:905-927.
-// Shared-memory strides are odd and lanes walk rows (row pass) / columns (column pass): no bank conflicts.
+// The two planes are blurred TOGETHER with Blackwell's packed fp32 instructions (FFMA2 / FADD2 / FMUL2, PTX fma.rn.f32x2): the tile
+// holds (w_new, w_old) pairs, one LDS.64 fetches both and one FFMA2 applies the tap to both -- per lane the IEEE-rn result of the
+// scalar instruction, so the arithmetic is unchanged, at half the FP and shared-memory instructions.  Tile with a 15 px halo
+// (reflect-101 at the canvas border) -> shared memory, one 8-byte cp.async per pair (k_dt_weights writes the pairs interleaved); row pass, 16 consecutive outputs per thread from a 46-pair register
+// window (cv2 order: tap 0 product, then FMAs left to right), written back IN PLACE over the tile (one extra barrier; 71 KB per CTA);
+// column pass, 8 consecutive outputs per thread (cv2's symmetric FMA form).  Then the blend of main.py:905-927.
+// Rows are 95 pairs apart: lanes walking rows hit distinct banks within each half warp of a 64-bit access; lanes walking columns are
+// contiguous.
 #define FB_TW 64
 #define FB_TH 64
 #define FB_NT 512                         // threads: 64 columns x 8 groups of 8 rows in the column pass
 #define FB_SW (FB_TW + 2 * BM_BLUR_R)      // 94
-#define FB_SH (FB_TH + 2 * BM_BLUR_R)      // 62
+#define FB_SH (FB_TH + 2 * BM_BLUR_R)      // 94
 struct FbSmem {
-    float tile[2][FB_SH][FB_SW + 1];     // both weight planes with halo, filled by cp.async while the CTA starts computing
-    float hrow[FB_SH][FB_TW + 1];        // row-filtered plane
+    float2 tile[FB_SH][FB_SW + 1];       // (w_new, w_old) with halo; columns [0, 64) are overwritten by the row-filtered pairs
 };
-__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src, bool valid) {
+typedef unsigned long long fb_u64;
+__constant__ float2 c_gk2[16] = {          // (k, k) pairs of c_gk: the multiplier operand of the packed instructions
+    {8.880585083e-04f, 8.880585083e-04f}, {1.586106606e-03f, 1.586106606e-03f}, {2.721769968e-03f, 2.721769968e-03f}, {4.487439990e-03f, 4.487439990e-03f},
+    {7.108436897e-03f, 7.108436897e-03f}, {1.081876736e-02f, 1.081876736e-02f}, {1.582011767e-02f, 1.582011767e-02f}, {2.222643606e-02f, 2.222643606e-02f},
+    {3.000254929e-02f, 3.000254929e-02f}, {3.891120851e-02f, 3.891120851e-02f}, {4.848635197e-02f, 4.848635197e-02f}, {5.804870278e-02f, 5.804870278e-02f},
+    {6.677190214e-02f, 6.677190214e-02f}, {7.379436493e-02f, 7.379436493e-02f}, {7.835755497e-02f, 7.835755497e-02f}, {7.994048297e-02f, 7.994048297e-02f}};
+__device__ __forceinline__ fb_u64 fb_fma2(fb_u64 a, fb_u64 b, fb_u64 c) { fb_u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ fb_u64 fb_mul2(fb_u64 a, fb_u64 b) { fb_u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ fb_u64 fb_add2(fb_u64 a, fb_u64 b) { fb_u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ fb_u64 fb_gk2(int k) { return *reinterpret_cast<const fb_u64*>(&c_gk2[k]); }
+__device__ __forceinline__ void cp_async8(float2* smem_dst, const float2* gmem_src, bool valid) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    const int sz = valid ? 4 : 0;        // src-size 0: the 4 bytes are zero-filled, nothing is read
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sa), "l"(gmem_src), "r"(sz) : "memory");
+    const int sz = valid ? 8 : 0;        // src-size 0: the 8 bytes are zero-filled, nothing is read
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(gmem_src), "r"(sz) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(FB_NT, 2) k_blur_blend(BmFramePlan plan, const float* __restrict__ wnp, const float* __restrict__ wop,
+// One channel of the blend without the conversion unit (I2F.U8 / F2I.TRUNC run at a quarter of the FP rate and were the busiest
+// pipe of the kernel): byte -> float as the exact difference (2^23 + b) - 2^23 with the byte dropped into the mantissa by one PRMT,
+// float -> byte as the low mantissa bits of f + 2^23 rounded TOWARD ZERO (= 2^23 + floor(f) for 0 <= f < 2^23: the truncation of astype).
+template <int CH>
+__device__ __forceinline__ unsigned fb_blend_channel(unsigned cv, unsigned w, float wo, float wn) {
+    const float fc = __fsub_rn(__uint_as_float(__byte_perm(cv, 0x4B000000u, 0x7440 | CH)), 8388608.0f);
+    const float fw = __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440 | CH)), 8388608.0f);
+    const float f = __fadd_rn(__fmul_rn(fc, wo), __fmul_rn(fw, wn));
+    return __float_as_uint(__fadd_rz(f, 8388608.0f)) & 255u;
+}
+
+__global__ void __launch_bounds__(FB_NT, 2) k_blur_blend(BmFramePlan plan, const float2* __restrict__ wnop,
                                                        const uchar4* __restrict__ wbuf, uchar4* __restrict__ canvas,
                                                        const int* __restrict__ flags) {
+    BM_PDL_TRIGGER(); BM_PDL_WAIT();
     extern __shared__ __align__(16) unsigned char fb_smem_raw[];
     FbSmem& sm = *reinterpret_cast<FbSmem*>(fb_smem_raw);
     const int tid = threadIdx.x;
@@ -314,7 +340,6 @@ __global__ void __launch_bounds__(FB_NT, 2) k_blur_blend(BmFramePlan plan, const
         }
         return;
     }
-    float wgt[2][8];
     {
         const int warp = tid >> 5, lane = tid & 31;
         // both weight planes (tile + 15 px halo) are requested first: the copies fly while the overlap test below loads wbuf / canvas.
@@ -327,21 +352,17 @@ __global__ void __launch_bounds__(FB_NT, 2) k_blur_blend(BmFramePlan plan, const
             gxok[j] = gx >= plan.reg.x0 && gx < plan.reg.x1;     // beyond R only in partial edge tiles: never used
             gxo[j] = gxok[j] ? gx - plan.rx0 : 0;
         }
+        for (int ty = warp; ty < FB_SH; ty += FB_NT / 32) {
+            const int gy = reflect101(by + ty - BM_BLUR_R, plan.canvas_h);
+            const bool yok = gy >= plan.reg.y0 && gy < plan.reg.y1;
+            const size_t ro = yok ? (size_t)(gy - plan.reg.y0) * plan.rws : 0;
 #pragma unroll
-        for (int pl = 0; pl < 2; ++pl) {
-            const float* __restrict__ src = pl ? wop : wnp;
-            for (int ty = warp; ty < FB_SH; ty += FB_NT / 32) {
-                const int gy = reflect101(by + ty - BM_BLUR_R, plan.canvas_h);
-                const bool yok = gy >= plan.reg.y0 && gy < plan.reg.y1;
-                const float* __restrict__ rowp = src + (yok ? (size_t)(gy - plan.reg.y0) * plan.rws : 0);
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    const int tx = lane + 32 * j;
-                    if (tx < FB_SW) cp_async4(&sm.tile[pl][ty][tx], rowp + gxo[j], yok && gxok[j]);
-                }
+            for (int j = 0; j < 3; ++j) {
+                const int tx = lane + 32 * j;
+                if (tx < FB_SW) cp_async8(&sm.tile[ty][tx], wnop + ro + gxo[j], yok && gxok[j]);
             }
-            cp_async_commit();
         }
+        cp_async_commit();
     }
     // the thread's 8 warped and 8 canvas pixels: 16 independent loads issued together (a short-circuit test would chain them), kept
     // in registers for the blend at the end -- this CTA is the only writer of these canvas pixels
@@ -357,45 +378,45 @@ __global__ void __launch_bounds__(FB_NT, 2) k_blur_blend(BmFramePlan plan, const
     bool need = false;
 #pragma unroll
     for (int o = 0; o < 8; ++o) need |= (wv[o] >> 24) && (cv8[o] >> 24);
-    if (__syncthreads_or(need)) {                          // tiles without a single overlap pixel need no weights
+    fb_u64 wgt[8];                                         // (w_new, w_old) of the thread's 8 pixels
+    cp_async_wait<0>();                                    // nothing may be in flight into shared memory when the CTA exits
+    if (__syncthreads_or(need)) {                          // tiles without a single overlap pixel need no weights; the tile is complete
+        const bool rowt = tid < FB_SH * (FB_TW / 16);      // 94 rows x 4 segments of 16 outputs; lanes walk rows
+        const int seg = tid / FB_SH, r = tid - seg * FB_SH, c0 = seg * 16;
+        fb_u64 acc[16];
+        if (rowt) {
+            const fb_u64* __restrict__ trow = reinterpret_cast<const fb_u64*>(&sm.tile[r][c0]);
 #pragma unroll
-        for (int pl = 0; pl < 2; ++pl) {
-            if (pl == 0) cp_async_wait<1>(); else cp_async_wait<0>();
-            __syncthreads();                               // tile[pl] complete for all threads; previous column pass done with hrow
-            float (*tile)[FB_SW + 1] = sm.tile[pl];
-            float (*hrow)[FB_TW + 1] = sm.hrow;
-            if (tid < FB_SH * (FB_TW / 16)) {              // 62 rows x 4 segments of 16 outputs; lanes walk rows
-                const int seg = tid / FB_SH, r = tid - seg * FB_SH, c0 = seg * 16;
-                float acc[16];
+            for (int t = 0; t < 46; ++t) {
+                const fb_u64 v = trow[t];
 #pragma unroll
-                for (int t = 0; t < 46; ++t) {
-                    const float v = tile[r][c0 + t];
-#pragma unroll
-                    for (int o = 0; o < 16; ++o) {
-                        const int k = t - o;
-                        if (k == 0) acc[o] = __fmul_rn(v, c_gk[0]);
-                        else if (k > 0 && k < 31) acc[o] = __fmaf_rn(v, c_gk[k < 16 ? k : 30 - k], acc[o]);
-                    }
+                for (int o = 0; o < 16; ++o) {
+                    const int k = t - o;
+                    if (k == 0) acc[o] = fb_mul2(v, fb_gk2(0));
+                    else if (k > 0 && k < 31) acc[o] = fb_fma2(v, fb_gk2(k < 16 ? k : 30 - k), acc[o]);
                 }
-#pragma unroll
-                for (int o = 0; o < 16; ++o) hrow[r][c0 + o] = acc[o];
-            }
-            __syncthreads();
-            float h[38];
-#pragma unroll
-            for (int t = 0; t < 38; ++t) h[t] = hrow[r0 + t][c];
-#pragma unroll
-            for (int o = 0; o < 8; ++o) {
-                float a = __fmul_rn(h[o + 15], c_gk[15]);
-#pragma unroll
-                for (int t = 1; t <= BM_BLUR_R; ++t) a = __fmaf_rn(__fadd_rn(h[o + 15 + t], h[o + 15 - t]), c_gk[15 - t], a);
-                wgt[pl][o] = a;
             }
         }
-    } else {
-        cp_async_wait<0>();                                // nothing may be in flight into shared memory when the CTA exits
+        __syncthreads();                                   // every window has been read: the row-filtered pairs go back in place
+        if (rowt) {
+            fb_u64* __restrict__ hrow = reinterpret_cast<fb_u64*>(&sm.tile[r][c0]);
 #pragma unroll
-        for (int o = 0; o < 8; ++o) { wgt[0][o] = 0.f; wgt[1][o] = 0.f; }
+            for (int o = 0; o < 16; ++o) hrow[o] = acc[o];
+        }
+        __syncthreads();
+        fb_u64 h[38];
+#pragma unroll
+        for (int t = 0; t < 38; ++t) h[t] = *reinterpret_cast<const fb_u64*>(&sm.tile[r0 + t][c]);
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+            fb_u64 a = fb_mul2(h[o + 15], fb_gk2(15));
+#pragma unroll
+            for (int t = 1; t <= BM_BLUR_R; ++t) a = fb_fma2(fb_add2(h[o + 15 + t], h[o + 15 - t]), fb_gk2(15 - t), a);
+            wgt[o] = a;
+        }
+    } else {
+#pragma unroll
+        for (int o = 0; o < 8; ++o) wgt[o] = 0ull;
     }
 #pragma unroll
     for (int o = 0; o < 8; ++o) {
@@ -404,11 +425,9 @@ __global__ void __launch_bounds__(FB_NT, 2) k_blur_blend(BmFramePlan plan, const
         if (!(w >> 24)) continue;                          // canvas keeps its value where mask_new == 0 (nrow rows only: wv = 0 beyond)
         unsigned* cp = reinterpret_cast<unsigned*>(ccol + (size_t)o * plan.canvas_w);
         if (!(cv >> 24)) { *cp = w; continue; }            // non-overlap new: pixel copy (main.py:922-924)
-        const float wn = wgt[0][o], wo = wgt[1][o];
+        const float wn = __uint_as_float((unsigned)wgt[o]), wo = __uint_as_float((unsigned)(wgt[o] >> 32));
         // float32(canvas)*w_old + float32(warped)*w_new, then astype(uint8) = truncation (main.py:905-910)
-        const unsigned ox = (unsigned)__float2int_rz(__fadd_rn(__fmul_rn((float)(cv & 255u), wo), __fmul_rn((float)(w & 255u), wn))) & 255u;
-        const unsigned oy = (unsigned)__float2int_rz(__fadd_rn(__fmul_rn((float)((cv >> 8) & 255u), wo), __fmul_rn((float)((w >> 8) & 255u), wn))) & 255u;
-        const unsigned oz = (unsigned)__float2int_rz(__fadd_rn(__fmul_rn((float)((cv >> 16) & 255u), wo), __fmul_rn((float)((w >> 16) & 255u), wn))) & 255u;
+        const unsigned ox = fb_blend_channel<0>(cv, w, wo, wn), oy = fb_blend_channel<1>(cv, w, wo, wn), oz = fb_blend_channel<2>(cv, w, wo, wn);
         *cp = ox | (oy << 8) | (oz << 16) | ((ox | oy | oz) ? 0xff000000u : 0u);
     }
 }
@@ -508,8 +527,10 @@ static cudaError_t blend_tail(const BmBlendBufs& b, const BmFramePlan& plan, cud
     if ((e = bm_launch_dt_local(pn, 0, pn.nb, b.flags, 1, s)) != cudaSuccess) return e;
     const int xa[2] = {plan.rx0, 0}, xb[2] = {plan.reg.x1, ww};
     if ((e = bm_launch_dt_carries(b.dt, 2, xa, xb, b.flags, 1, s)) != cudaSuccess) return e;
-    if ((e = bm_launch_dt_weights(b.dt, plan, b.wn, b.wo, b.flags, s)) != cudaSuccess) return e;
-    BM_COUNT_LAUNCHES(1), k_blur_blend<<<dim3(bm_div_up(ww, FB_TW), bm_div_up(wh, FB_TH)), FB_NT, sizeof(FbSmem), s>>>(plan, b.wn, b.wo, b.wbuf, b.canvas, b.flags);
+    if ((e = bm_launch_dt_weights(b.dt, plan, b.wno, b.flags, s)) != cudaSuccess) return e;
+    BM_COUNT_LAUNCHES(1);
+    if ((e = bm_launch_pdl(k_blur_blend, dim3(bm_div_up(ww, FB_TW), bm_div_up(wh, FB_TH)), dim3(FB_NT), sizeof(FbSmem), s, plan, (const float2*)b.wno,
+                           (const uchar4*)b.wbuf, b.canvas, (const int*)b.flags)) != cudaSuccess) return e;
     // refresh the persistent tables of the canvas plane for the rows the frame touched
     if ((e = bm_launch_rowscan_bgrx(b.canvas, b.canvas_w, 0, plan.win.y0, po, plan.win.y0, wh, b.flags, 0, s)) != cudaSuccess) return e;
     return bm_launch_dt_local(po, plan.win.y0 / BM_BLK_ROWS, bm_div_up(plan.win.y1, BM_BLK_ROWS), b.flags, 0, s);

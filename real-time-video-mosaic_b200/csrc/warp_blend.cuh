@@ -9,8 +9,7 @@ struct BmBlendBufs {
     BmDtPair dt;           // sweep tables: [0] canvas plane (mask_old, persistent), [1] window plane (mask_new, per frame)
     // per-frame scratch, sized for the largest window
     uchar4* wbuf;          // warped frame over W, .w = mask_new               [win_h][plan.ws]
-    float* wn;             // dn/s over R                                       [reg_h][plan.rws]
-    float* wo;             // do/s over R
+    float2* wno;           // (dn/s, do/s) over R                               [reg_h][plan.rws]
     int* flags;            // [0] any_overlap
     size_t scratch_px;     // capacity of the scratch buffers in pixels (reg_h*reg_w <= scratch_px)
     int canvas_w, canvas_h;
