@@ -194,6 +194,14 @@ def regions_max_over_ranks(torch, dist, times):
     return [float(v) for v in allr.max(dim=0).values], [[float(v) for v in r] for r in allr]
 
 
+LOOKAHEAD = int(os.environ.get("BM_AHEAD", "3"))      # frames handed over ahead of the current one (the library stages up to 3)
+
+
+def ahead_ptrs(base, i, fb, n):
+    """pointers of the frames i+1 .. i+LOOKAHEAD of a contiguous frame array (None past its end)"""
+    return [base + (i + k) * fb if (k <= LOOKAHEAD and i + k < n) else None for k in (1, 2, 3)]
+
+
 def headline(args, det, frames, dev_frames, pinned, ctx, lib, want_chain, sample_clocks):
     """legs 1 (frames resident in HBM), 1b (chain alone, roofline) and 2 (end to end from pinned host frames) for one detector;
     every leg is R regions of exactly K steps, each region bracketed by barrier + synchronize, timed per rank, max over ranks"""
@@ -210,7 +218,7 @@ def headline(args, det, frames, dev_frames, pinned, ctx, lib, want_chain, sample
     vm.warm_up()                                   # setup: CUDA graphs of the detector captured up front (executes nothing)
     ramp_clocks(torch)
     for i in range(1, W + 1):
-        vm.process_frame_device(base + i * fb, base + (i + 1) * fb, base + (i + 2) * fb)
+        vm.process_frame_device(base + i * fb, *ahead_ptrs(base, i, fb, n))
     vm.sync()
     statuses, t_dev, ev_ms = [], [], []
     launches0 = lib.bm_kernel_launches()
@@ -222,7 +230,7 @@ def headline(args, det, frames, dev_frames, pinned, ctx, lib, want_chain, sample
         e0.record()
         t0 = time.perf_counter()
         for _ in range(K):
-            statuses.append(vm.process_frame_device(base + i * fb, base + (i + 1) * fb if i + 1 < n else None, base + (i + 2) * fb if i + 2 < n else None))
+            statuses.append(vm.process_frame_device(base + i * fb, *ahead_ptrs(base, i, fb, n)))
             i += 1
         vm.sync()
         e1.record()
@@ -260,7 +268,7 @@ def headline(args, det, frames, dev_frames, pinned, ctx, lib, want_chain, sample
     vm2.warm_up()
     ramp_clocks(torch)
     for i in range(1, W + 1):
-        vm2.process_frame_ptr(pbase + i * fb, pbase + (i + 1) * fb, pbase + (i + 2) * fb)
+        vm2.process_frame_ptr(pbase + i * fb, *ahead_ptrs(pbase, i, fb, n))
     vm2.sync()
     t_e2e = []
     i = W + 1
@@ -269,9 +277,9 @@ def headline(args, det, frames, dev_frames, pinned, ctx, lib, want_chain, sample
         ctx.barrier()
         t0 = time.perf_counter()
         for _ in range(K):
-            # H2D (the copies of frames i+1, i+2 are started while frame i is processed: what a reader thread two frames ahead of the
-            # stitcher provides, run.AheadCapture) + all kernels + D2H of (counts, H)
-            vm2.process_frame_ptr(pbase + i * fb, pbase + (i + 1) * fb if i + 1 < n else None, pbase + (i + 2) * fb if i + 2 < n else None)
+            # H2D (the copies of frames i+1 .. i+3 are started while frame i is processed: what a reader thread three frames ahead of
+            # the stitcher provides, run.AheadCapture) + all kernels + D2H of (counts, H)
+            vm2.process_frame_ptr(pbase + i * fb, *ahead_ptrs(pbase, i, fb, n))
             i += 1
         canvas = vm2.read_canvas(canvas_host)          # the canvas (what becomes mosaic.jpg) D2H into the caller's pinned buffer, every region
         torch.cuda.synchronize()
@@ -319,7 +327,7 @@ def main():
     if args.regions <= 0:
         args.regions = max(1, min(5, 360 // max(K, 1)))
     R = args.regions
-    n = R * K + W + 3
+    n = R * K + W + 4
     frames, sweep = make_frames(w, h, n, 1234 + 1000 * rank)
     fb = h * w * 3
     dev_frames = torch.from_numpy(np.stack(frames)).cuda(local_rank)          # (n, h, w, 3) u8

@@ -66,8 +66,8 @@ static bm_status alloc_blend(BmBlendBufs& b, int canvas_h, int canvas_w, size_t 
 // Frame slots rotate over three buffers; events order  upload(slot) -> detect / chain(slot) -> next upload(slot).  Three, not two:
 // the upload of frame t+1 must not wait for the chain of frame t-1, which is still reading that frame's BGRX copy when the caller
 // stages t+1 (with two slots the H2D copy of every frame started a whole chain late and sat on the critical path of the e2e rate).
-#define BM_SLOTS 4
-#define BM_LOOKAHEAD 2                  // frames that may be staged (and detected) ahead of the current one
+#define BM_LOOKAHEAD BM_AHEAD_MAX       // frames that may be staged (and detected) ahead of the current one
+#define BM_SLOTS (BM_LOOKAHEAD + 2)
 #define BM_CANVAS_STAGE_BYTES ((size_t)4 << 20)
 #define BM_SLOT_NEXT(c) (((c) + 1) % BM_SLOTS)
 #define BM_SLOT_PREV(c) (((c) + BM_SLOTS - 1) % BM_SLOTS)

@@ -70,6 +70,7 @@ struct BmNvtxRange {
     } while (0)
 
 static inline int bm_div_up(int a, int b) { return (a + b - 1) / b; }
+#define BM_DET_MAX_GRAPHS 32     // detector graph cache per instance: (frame slot, keypoint slot) pairs, 5 x 5 with three frames of look-ahead
 
 // Programmatic dependent launch for back-to-back kernels of one stream (the warp / blend chain): a kernel launched through
 // bm_launch_pdl is set up (launch processing, CTA scheduling) while its predecessor drains instead of after it; it starts with

@@ -72,6 +72,7 @@ __device__ __forceinline__ int block_prefix(bool flag, int* total, int* warp_sum
 // select (mode 0: mutual NN; mode 1: Lowe ratio), keep query order, then stable sort by distance and gather the points
 __global__ void __launch_bounds__(1024) k_select_sort(int mode, double ratio, const int* __restrict__ nqp, const int* __restrict__ ntp,
                                                       BmMatches m, const float2* __restrict__ pt_cur, const float2* __restrict__ pt_prev) {
+    BM_PDL_WAIT();
     __shared__ int warp_sums[32];
     __shared__ int s_count;
     const int nq = *nqp, nt = *ntp;
@@ -109,13 +110,13 @@ __global__ void __launch_bounds__(1024) k_select_sort(int mode, double ratio, co
 cudaError_t bm_match_hamming(const BmKeypoints& cur, const BmKeypoints& prev, BmMatches& m, cudaStream_t s) {
     const int blocks = (BM_KP_CAP * 32) / 256;
     BM_COUNT_LAUNCHES(1), k_hamming_nn<<<dim3(blocks, 2), 256, 0, s>>>(cur.desc, cur.count, prev.desc, prev.count, m.nn_q2t, m.d_q2t, m.nn_t2q, m.d_t2q);
-    BM_COUNT_LAUNCHES(1), k_select_sort<<<1, 1024, 0, s>>>(0, 0.0, cur.count, prev.count, m, cur.pt, prev.pt);
-    return cudaGetLastError();
+    BM_COUNT_LAUNCHES(1);
+    return bm_launch_pdl(k_select_sort, dim3(1), dim3(1024), 0, s, 0, 0.0, (const int*)cur.count, (const int*)prev.count, m, (const float2*)cur.pt, (const float2*)prev.pt);
 }
 
 cudaError_t bm_match_l2_ratio(const BmKeypoints& cur, const BmKeypoints& prev, BmMatches& m, double ratio, cudaStream_t s) {
     cudaError_t e = bm_launch_l2_knn2_tc(cur.desc, cur.count, prev.desc, prev.count, m.l2_part, m.nn_q2t, m.d_q2t, m.nn2_q2t, m.d2_q2t, s);
     if (e != cudaSuccess) return e;
-    BM_COUNT_LAUNCHES(1), k_select_sort<<<1, 1024, 0, s>>>(1, ratio, cur.count, prev.count, m, cur.pt, prev.pt);
-    return cudaGetLastError();
+    BM_COUNT_LAUNCHES(1);
+    return bm_launch_pdl(k_select_sort, dim3(1), dim3(1024), 0, s, 1, ratio, (const int*)cur.count, (const int*)prev.count, m, (const float2*)cur.pt, (const float2*)prev.pt);
 }

@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(128, 1) k_l2_knn2_tc(const uint8_t* __restrict
 // merge the (best, second) pairs of the splits: candidates ordered by (squared distance, train index)
 __global__ void __launch_bounds__(256) k_l2_knn2_merge(const int4* __restrict__ part, const int* __restrict__ nAp, const int* __restrict__ nBp,
                                                        int* __restrict__ nn1, float* __restrict__ d1o, int* __restrict__ nn2, float* __restrict__ d2o) {
+    BM_PDL_WAIT();
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     const int nA = *nAp, nB = *nBp;
     if (q >= nA) return;
@@ -181,6 +182,6 @@ cudaError_t bm_launch_l2_knn2_tc(const uint8_t* A, const int* nA, const uint8_t*
     BM_SMEM_OPTIN(k_l2_knn2_tc, sizeof(TcSmem) + 1024, attr);
     if (attr != cudaSuccess) return attr;
     BM_COUNT_LAUNCHES(1), k_l2_knn2_tc<<<dim3(BM_KP_CAP / TC_M, TC_SPLIT), 128, sizeof(TcSmem) + 1024, s>>>(A, nA, B, nB, part);
-    BM_COUNT_LAUNCHES(1), k_l2_knn2_merge<<<BM_KP_CAP / 256, 256, 0, s>>>(part, nA, nB, nn1, d1, nn2, d2);
-    return cudaGetLastError();
+    BM_COUNT_LAUNCHES(1);
+    return bm_launch_pdl(k_l2_knn2_merge, dim3(BM_KP_CAP / 256), dim3(256), 0, s, (const int4*)part, nA, nB, nn1, d1, nn2, d2);
 }

@@ -622,7 +622,7 @@ cudaError_t bm_orb_detect(BmOrb* o, const uint8_t* d_gray, BmKeypoints* out, boo
             BM_COUNT_LAUNCHES(o->graphs[i].launches);
             return cudaGraphLaunch(o->graphs[i].exec, o->stream);
         }
-    if (o->ngraphs >= 20) return orb_enqueue(o, d_gray, out);
+    if (o->ngraphs >= BM_DET_MAX_GRAPHS) return orb_enqueue(o, d_gray, out);
     long long captured = 0;
     t_bm_launch_sink = &captured;                            // nothing runs during capture: count the nodes, not launches
     cudaGraph_t graph = nullptr;

@@ -50,7 +50,7 @@ struct BmOrb {
     float* resp2;       // [total_cand] Harris responses when they do not fit in shared memory
     uint2* cand2;       // [total_cand] per level: the final keypoints (xy, response bits) in cv2's order
     cudaStream_t stream;
-    BmOrbGraph graphs[20];   // captured detect sequences, one per (input buffer, output buffer): 4 frame slots x 4 keypoint slots
+    BmOrbGraph graphs[BM_DET_MAX_GRAPHS];   // captured detect sequences, one per (input buffer, output buffer): 5 frame slots x 5 keypoint slots
     int ngraphs, graphs_disabled;
 };
 

@@ -190,6 +190,7 @@ __device__ __forceinline__ void block_sum(RsShared& sh, const double (&v)[NV]) {
 __global__ void __launch_bounds__(RS_THREADS, 1) k_ransac_homography(const float2* __restrict__ gsrc, const float2* __restrict__ gdst,
                                                                      const int* __restrict__ countp, double thresh, int max_iters, double confidence,
                                                                      uint8_t* __restrict__ mask, BmRansacResult* __restrict__ out) {
+    BM_PDL_WAIT();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RsShared& sh = *reinterpret_cast<RsShared*>(smem_raw);
     float2* spts = reinterpret_cast<float2*>(smem_raw + ((sizeof(RsShared) + 15) & ~(size_t)15));
@@ -506,6 +507,7 @@ __device__ __noinline__ void rf_accumulate(RfShared& sh, const float2* src, cons
 
 __global__ void __launch_bounds__(32 * RF_WARPS, 1) k_ransac_refine(const float2* __restrict__ gsrc, const float2* __restrict__ gdst, const int* __restrict__ countp,
                                                          const uint8_t* __restrict__ mask, BmRansacResult* __restrict__ out) {
+    BM_PDL_WAIT();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RfShared& sh = *reinterpret_cast<RfShared*>(smem_raw);
     float2* spts = reinterpret_cast<float2*>(smem_raw + ((sizeof(RfShared) + 15) & ~(size_t)15));
@@ -735,7 +737,7 @@ cudaError_t bm_launch_ransac(const float2* d_src, const float2* d_dst, const int
     if (e != cudaSuccess) return e;
     BM_SMEM_OPTIN(k_ransac_refine, smem2, e);
     if (e != cudaSuccess) return e;
-    BM_COUNT_LAUNCHES(1), k_ransac_homography<<<1, RS_THREADS, smem, s>>>(d_src, d_dst, d_count, thresh, max_iters, confidence, d_mask, d_out);
-    BM_COUNT_LAUNCHES(1), k_ransac_refine<<<1, 32 * RF_WARPS, smem2, s>>>(d_src, d_dst, d_count, d_mask, d_out);
-    return cudaGetLastError();
+    BM_COUNT_LAUNCHES(2);
+    if ((e = bm_launch_pdl(k_ransac_homography, dim3(1), dim3(RS_THREADS), smem, s, d_src, d_dst, d_count, thresh, max_iters, confidence, d_mask, d_out)) != cudaSuccess) return e;
+    return bm_launch_pdl(k_ransac_refine, dim3(1), dim3(32 * RF_WARPS), smem2, s, d_src, d_dst, d_count, (const uint8_t*)d_mask, d_out);
 }

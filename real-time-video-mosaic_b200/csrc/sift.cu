@@ -65,7 +65,7 @@ struct BmSift {
     // fork / join streams + events of the captured detect graph, and the graph cache
     cudaStream_t s2, s3;
     cudaEvent_t ev_fork, ev_l3[SIFT_MAX_OCT], ev_l5[SIFT_MAX_OCT], ev_join2, ev_join3;
-    static const int kMaxGraphs = 20;   // 4 frame slots x 4 keypoint slots
+    static const int kMaxGraphs = BM_DET_MAX_GRAPHS;   // 5 frame slots x 5 keypoint slots
     SiftGraph graphs[kMaxGraphs];
     int ngraphs;
     bool graphs_enabled;

@@ -129,10 +129,10 @@ class VideMosaic:
         return out
 
     # ---- main.py:710-759 -------------------------------------------------------------------------------------
-    def process_frame(self, frame_cur, frame_count=0, next_frame=None, next2_frame=None):
-        """main.py:710-759.  `next_frame` / `next2_frame` (optional, not in the reference): the frames of the NEXT two calls, if the
-        caller already has them -- their H2D copies and detectAndCompute then overlap this frame's processing (double-buffered ingest,
-        detect-ahead); pass the same array objects to the following process_frame calls."""
+    def process_frame(self, frame_cur, frame_count=0, next_frame=None, next2_frame=None, next3_frame=None):
+        """main.py:710-759.  `next_frame` / `next2_frame` / `next3_frame` (optional, not in the reference): the frames of the NEXT
+        calls, if the caller already has them (up to LOOKAHEAD = 3) -- their H2D copies and detectAndCompute then overlap this frame's
+        processing (multi-buffered ingest, detect-ahead); pass the same array objects to the following process_frame calls."""
         frame_cur = self._check_frame(frame_cur)
         if frame_cur.shape != self._frame_shape:
             raise ValueError(f"frame shape {frame_cur.shape} != first frame shape {self._frame_shape}")
@@ -147,10 +147,12 @@ class VideMosaic:
             _lib.check(self._lib.bm_process_frame_begin(self._h, frame_cur.ctypes.data_as(C.c_void_p), 0), "bm_process_frame_begin")
             _lib.check(self._lib.bm_prefetch_frame(self._h, next_frame.ctypes.data_as(C.c_void_p), 0), "bm_prefetch_frame")
             self._next_frame_ref = [next_frame]                    # keep the staged buffers alive / unchanged until they are consumed
-            if next2_frame is not None:
-                next2_frame = self._check_frame(next2_frame)
-                _lib.check(self._lib.bm_prefetch_frame(self._h, next2_frame.ctypes.data_as(C.c_void_p), 0), "bm_prefetch_frame")
-                self._next_frame_ref.append(next2_frame)
+            for more in (next2_frame, next3_frame):
+                if more is None:
+                    break
+                more = self._check_frame(more)
+                _lib.check(self._lib.bm_prefetch_frame(self._h, more.ctypes.data_as(C.c_void_p), 0), "bm_prefetch_frame")
+                self._next_frame_ref.append(more)
             st = _lib.check(self._lib.bm_process_frame_end(self._h, C.byref(info)), "bm_process_frame_end")
         self.last_info = info
         if st == _lib.BM_SKIP_FEW_MATCHES:
@@ -177,24 +179,26 @@ class VideMosaic:
         self._canvas_cache = None
 
     # ---- device-resident / raw-pointer variants used by bench.py ------------------------------------------------
-    def process_frame_ptr(self, host_ptr, next_ptr=None, next2_ptr=None):
+    def process_frame_ptr(self, host_ptr, next_ptr=None, next2_ptr=None, next3_ptr=None):
         """process_frame on a raw host pointer (e.g. pinned memory): no NumPy checks, no prints.  Returns the status.
-        next_ptr / next2_ptr: host pointers of the next two frames, staged (H2D + ingest on the copy stream, detect-ahead) while this
-        one is processed."""
+        next_ptr / next2_ptr / next3_ptr: host pointers of the next frames, staged (H2D + ingest on the copy stream, detect-ahead) while
+        this one is processed."""
         info = _lib.BmFrameInfo()
         if next_ptr is None:
             st = _lib.check(self._lib.bm_process_frame(self._h, C.c_void_p(host_ptr), 0, C.byref(info)), "bm_process_frame")
         else:
             _lib.check(self._lib.bm_process_frame_begin(self._h, C.c_void_p(host_ptr), 0), "bm_process_frame_begin")
             _lib.check(self._lib.bm_prefetch_frame(self._h, C.c_void_p(next_ptr), 0), "bm_prefetch_frame")
-            if next2_ptr is not None:
-                _lib.check(self._lib.bm_prefetch_frame(self._h, C.c_void_p(next2_ptr), 0), "bm_prefetch_frame")
+            for more in (next2_ptr, next3_ptr):
+                if more is None:
+                    break
+                _lib.check(self._lib.bm_prefetch_frame(self._h, C.c_void_p(more), 0), "bm_prefetch_frame")
             st = _lib.check(self._lib.bm_process_frame_end(self._h, C.byref(info)), "bm_process_frame_end")
         self.last_info = info
         self._canvas_cache = None
         return st
 
-    def process_frame_device(self, dev_ptr, next_ptr=None, next2_ptr=None):
+    def process_frame_device(self, dev_ptr, next_ptr=None, next2_ptr=None, next3_ptr=None):
         """process_frame on a frame already in device memory (packed BGR).  Returns the status.  next_ptr: device pointer of the
         next frame (ingested and started while this one is finished, like process_frame_ptr's next_ptr)."""
         info = _lib.BmFrameInfo()
@@ -203,8 +207,10 @@ class VideMosaic:
         else:
             _lib.check(self._lib.bm_process_frame_begin_device(self._h, C.c_void_p(dev_ptr)), "bm_process_frame_begin_device")
             _lib.check(self._lib.bm_prefetch_frame_device(self._h, C.c_void_p(next_ptr)), "bm_prefetch_frame_device")
-            if next2_ptr is not None:
-                _lib.check(self._lib.bm_prefetch_frame_device(self._h, C.c_void_p(next2_ptr)), "bm_prefetch_frame_device")
+            for more in (next2_ptr, next3_ptr):
+                if more is None:
+                    break
+                _lib.check(self._lib.bm_prefetch_frame_device(self._h, C.c_void_p(more)), "bm_prefetch_frame_device")
             st = _lib.check(self._lib.bm_process_frame_end(self._h, C.byref(info)), "bm_process_frame_end")
         self.last_info = info
         self._canvas_cache = None

@@ -95,11 +95,11 @@ class LazyCanvas:
 class AheadCapture:
     """cv2.VideoCapture with a one-frame-ahead reader thread (the reference's loop is
     `ret, frame = cap.read(); video_mosaic.process_frame(frame, n)`, main.py:1597-1613).  Frames are decoded by the real
-    cv2.VideoCapture on a background thread into a ring of pinned host buffers; `read()` hands out frame t while frames t+1, t+2 are
-    already decoded, and `peek_next(2)` lets the swapped `process_frame` stage them (H2D + detect-ahead) while t is processed --
+    cv2.VideoCapture on a background thread into a ring of pinned host buffers; `read()` hands out frame t while frames t+1 .. t+3 are
+    already decoded, and `peek_next(3)` lets the swapped `process_frame` stage them (H2D + detect-ahead) while t is processed --
     the unmodified driver loop gets the double-buffered ingest without passing `next_frame`."""
     current = None
-    RING = 9                    # pinned buffers: 3 queued + 2 peeked + the frames the pipeline still holds
+    RING = 12                   # pinned buffers: 3 queued + 1 being decoded + 3 peeked + the frames the pipeline still holds
 
     def __init__(self, *args, **kw):
         import queue
@@ -151,7 +151,7 @@ class AheadCapture:
         return self._peeked.pop(0) if self._peeked else self._pull()
 
     def peek_next(self, k=1):
-        """the frames the next k (<= 2) read() calls will return (blocks until they are decoded); None in place of frames past the
+        """the frames the next k (<= 3) read() calls will return (blocks until they are decoded); None in place of frames past the
         end of the stream"""
         while len(self._peeked) < k and not (self._peeked and not self._peeked[-1][0]):
             self._peeked.append(self._pull())
@@ -181,10 +181,10 @@ def make_swapped_class(det, ahead=True):
             kw.setdefault("visualize", False)
             super().__init__(first_image, *args, **kw)
 
-        def process_frame(self, frame_cur, frame_count=0, next_frame=None, next2_frame=None):
+        def process_frame(self, frame_cur, frame_count=0, next_frame=None, next2_frame=None, next3_frame=None):
             if next_frame is None and ahead and AheadCapture.current is not None:
-                next_frame, next2_frame = AheadCapture.current.peek_next(2)
-            return super().process_frame(frame_cur, frame_count, next_frame=next_frame, next2_frame=next2_frame)
+                next_frame, next2_frame, next3_frame = AheadCapture.current.peek_next(3)
+            return super().process_frame(frame_cur, frame_count, next_frame=next_frame, next2_frame=next2_frame, next3_frame=next3_frame)
 
         @property
         def output_img(self):

@@ -317,10 +317,10 @@ def test_row_tiles_with_boundary_exchange_equal_untiled_canvas():
 
 
 @pytest.mark.parametrize("det", ["orb", "sift"])
-def test_two_frame_lookahead_does_not_change_results(det):
-    """next_frame= and next2_frame= (two frames staged and detected ahead, three detects in flight) are scheduling only: statuses,
-    trajectory, canvas and final features equal strictly serial calls -- also across a skipped (featureless) frame, a stale staged
-    frame and a caller that stops passing look-ahead frames in the middle of the run"""
+def test_multi_frame_lookahead_does_not_change_results(det):
+    """next_frame= / next2_frame= / next3_frame= (up to three frames staged and detected ahead on the three detector instances) are
+    scheduling only: statuses, trajectory, canvas and final features equal strictly serial calls -- also across a skipped (featureless)
+    frame, stale staged frames and a caller that stops passing look-ahead frames in the middle of the run"""
     import b200mosaic
     from b200mosaic.synth import DroneSweep
     frames = DroneSweep(640, 360, seed=33, ground_size=2048, max_step=7.0).frames(26)
@@ -334,22 +334,31 @@ def test_two_frame_lookahead_does_not_change_results(det):
         for t in range(1, n):
             n1 = seq[t + 1] if t + 1 < n else None
             n2 = seq[t + 2] if t + 2 < n else None
+            n3 = seq[t + 3] if t + 3 < n else None
             if mode == "serial" or (mode == "mixed" and 14 <= t < 17):
-                n1 = n2 = None                                                         # no look-ahead for a while
+                n1 = n2 = n3 = None                                                    # no look-ahead for a while
             elif mode == "mixed" and t == 5:
                 n2 = seq[2]                                                            # a stale second look-ahead frame
             elif mode == "mixed" and t == 19:
                 n1, n2 = seq[3], seq[t + 1]                                            # a stale first one
+            elif mode == "mixed" and t == 11:
+                n3 = seq[4]                                                            # a stale third one
             elif mode == "one":
+                n2 = n3 = None
+            elif mode == "two":
+                n3 = None
+            if n1 is None:
                 n2 = None
-            vm.process_frame(seq[t], t, next_frame=n1, next2_frame=n2 if n1 is not None else None)
+            if n2 is None:
+                n3 = None
+            vm.process_frame(seq[t], t, next_frame=n1, next2_frame=n2, next3_frame=n3)
             st.append(vm.last_info.status)
             Hs.append(None if vm.H is None else vm.H.copy())
         kp = np.array([[k.pt[0], k.pt[1], k.size, k.angle, k.response] for k in vm.kp_prev])
         return st, Hs, vm.output_img.copy(), kp, np.asarray(vm.des_prev).copy(), [(m.queryIdx, m.trainIdx) for m in vm.matches]
     want = run("serial")
     assert want[0][8] != 0 and want[0].count(0) == n - 2                               # exactly the blank frame is skipped
-    for mode in ("two", "one", "mixed"):
+    for mode in ("three", "two", "one", "mixed"):
         got = run(mode)
         assert got[0] == want[0], mode
         assert all((a is None) == (b is None) and (a is None or np.array_equal(a, b)) for a, b in zip(got[1], want[1])), mode
