@@ -8,6 +8,7 @@
 #include <new>
 #include <string.h>
 #include <stdlib.h>
+#include <time.h>
 
 struct BmHostReadback {      // pinned + mapped: written by k_publish_readback straight from the device, polled by the host
     BmRansacResult r;
@@ -66,6 +67,7 @@ struct BmPipeline {
     cudaEvent_t pd0[BM_NDET] = {}, pd1[BM_NDET] = {}, pe0 = nullptr, pe1 = nullptr;
     bool pd_pending[BM_NDET] = {}, pe_pending = false;
     double pd_ms = 0.0, pe_ms = 0.0; long pd_n = 0, pe_n = 0;
+    double wait_us = 0.0; long wait_n = 0;    // host time spent waiting for the result in estimate_end
 };
 
 bm_status bm_pipeline_create(BmPipeline** out, const bm_config& cfg, cudaStream_t stream) {
@@ -84,7 +86,7 @@ bm_status bm_pipeline_create(BmPipeline** out, const bm_config& cfg, cudaStream_
               cudaHostAlloc(&p->h_rb, sizeof(BmHostReadback), cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess;
     if (ok) memset(p->h_rb, 0, sizeof(BmHostReadback));
     p->is_orb = cfg.detector == BM_DET_ORB;
-    p->prof = getenv("BM_PROFILE") != nullptr;
+    { const char* e = getenv("BM_PROFILE"); p->prof = e && e[0] != '0'; }
     if (p->prof) { for (int i = 0; i < BM_NDET; ++i) { cudaEventCreate(&p->pd0[i]); cudaEventCreate(&p->pd1[i]); } cudaEventCreate(&p->pe0); cudaEventCreate(&p->pe1); }
     ok = ok && cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < BM_NDET && ok; ++i) {
@@ -103,8 +105,8 @@ void bm_pipeline_destroy(BmPipeline* p) {
     if (p->s_est) cudaStreamSynchronize(p->s_est);
     if (p->stream) cudaStreamSynchronize(p->stream);
     if (p->prof && p->pd_n > 0)
-        fprintf(stderr, "[bm profile] detect graph: %.1f us avg over %ld (in pipeline), match + RANSAC: %.1f us avg over %ld\n",
-                1e3 * p->pd_ms / p->pd_n, p->pd_n, p->pe_n ? 1e3 * p->pe_ms / p->pe_n : 0.0, p->pe_n);
+        fprintf(stderr, "[bm profile] detect graph: %.1f us avg over %ld (in pipeline), match + RANSAC: %.1f us avg over %ld; host waited %.1f us per frame for the result\n",
+                1e3 * p->pd_ms / p->pd_n, p->pd_n, p->pe_n ? 1e3 * p->pe_ms / p->pe_n : 0.0, p->pe_n, p->wait_n ? p->wait_us / p->wait_n : 0.0);
     for (int i = 0; i < BM_NDET; ++i) {
         if (p->s_det[i]) cudaStreamSynchronize(p->s_det[i]);
         bm_orb_destroy(p->orb[i]); bm_sift_destroy(p->sift[i]);
@@ -225,6 +227,7 @@ void bm_pipeline_drop_ahead(BmPipeline* p, const uint8_t* d_gray) {
 bm_status bm_pipeline_estimate_end(BmPipeline* p, bm_frame_info* info, double H_rel[9], int* have_h) {
     BM_NVTX("bm:wait match+RANSAC");
     BmHostReadback* rb = p->h_rb;
+    timespec tw0; if (p->prof) clock_gettime(CLOCK_MONOTONIC, &tw0);
     {   // spin on the flag k_publish_readback stores last; the event is only consulted now and then, to surface a device error
         const volatile unsigned* flag = &rb->seq;
         for (unsigned spins = 1; *flag != p->seq; ++spins) {
@@ -239,6 +242,7 @@ bm_status bm_pipeline_estimate_end(BmPipeline* p, bm_frame_info* info, double H_
         }
         __atomic_thread_fence(__ATOMIC_ACQUIRE);
     }
+    if (p->prof) { timespec tw1; clock_gettime(CLOCK_MONOTONIC, &tw1); p->wait_us += 1e6 * (tw1.tv_sec - tw0.tv_sec) + 1e-3 * (tw1.tv_nsec - tw0.tv_nsec); p->wait_n++; }
     p->mdone = p->mcur;
     if (rb->overflow_cur || rb->overflow_prev) {
         // a detector list ran out of capacity: which candidates were kept depends on atomic order, the features are not cv2's
