@@ -80,7 +80,8 @@ bm_status bm_process_frame_end(bm_handle h, bm_frame_info* info);
 /* double-buffered ingest (north_star: "pinned, double-buffered H2D copies"): start the H2D + BGR->gray/BGRX of the NEXT frame on
  * the copy stream while the current one is processed; the following bm_process_frame / _begin / bm_warp_frame / bm_estimate_frame
  * call with the same host pointer consumes the staged copy instead of uploading again.  The buffer must stay unchanged in
- * between (pageable buffers are copied to pinned staging memory immediately). */
+ * between (pageable buffers are copied to pinned staging memory immediately).  May be called for up to THREE frames ahead, in the order
+ * they will be processed: each staged frame's detectAndCompute is queued while the current frame is still in flight. */
 bm_status bm_prefetch_frame(bm_handle h, const uint8_t* h_bgr, size_t stride_bytes);
 bm_status bm_prefetch_frame_device(bm_handle h, const uint8_t* d_bgr);     /* frame already in device memory (packed BGR) */
 /* 1 (default): the warp/blend chain of frame t runs concurrently with detect/match/RANSAC of frame t+1 (separate streams);
