@@ -384,7 +384,7 @@ def main():
     modes = None
     if not args.no_modes:
         modes = []
-        for fn, kw in ((bench_modes.run_streams, dict(streams=64, frames=8, warmup=2)),
+        for fn, kw in ((bench_modes.run_streams, dict(streams=64, frames=16, warmup=3)),
                        (bench_modes.run_pairs, dict(frames=max(40, 16 * world) + world)),
                        (bench_modes.run_tiles, dict(frames=24, warmup=2, size="3840x2160", canvas="32768x32768"))):
             try:

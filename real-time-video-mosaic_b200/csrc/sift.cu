@@ -61,6 +61,7 @@ struct BmSift {
     CUtensorMap tmap[SIFT_MAX_OCT][6];   // TMA descriptor of the SOURCE image of blur level l in octave o (box 32 x 64|128 floats, SWIZZLE_128B)
     bool tma_ok[SIFT_MAX_OCT][6];
     bool use_tma;
+    bool separate_upsample;  // BM_SIFT_SEPARATE_UPSAMPLE=1: keep k_sift_upsample + the float plane (A/B of the fused base level)
     cudaStream_t stream;
     // fork / join streams + events of the captured detect graph, and the graph cache
     cudaStream_t s2, s3;
@@ -133,9 +134,13 @@ __host__ __device__ constexpr int sift_tile_h(int level, int sh) {
 #define SIFT_BLUR_TSTRIDE (64 + 2 * 13 + 1)
 __host__ __device__ constexpr size_t sift_blur_smem(int sh) { return (size_t)sh * (SIFT_BLUR_TSTRIDE + 65) * sizeof(float); }
 
-template <int LEVEL, int SHT>
+// UP (level 0 of octave 0 only): the source is the 8-bit gray frame and the tile fill evaluates cv2.resize(2x, INTER_LINEAR) on the fly
+// instead of reading a float plane a separate kernel wrote (k_sift_upsample: 21 us and 66 MB of traffic per 1080p frame).  The
+// interpolation weights are 1/4 and 3/4 on both axes, so every intermediate of the float evaluation is an exact multiple of 1/16
+// below 256: the integer form  (wy0 (wx0 g00 + wx1 g01) + wy1 (wx0 g10 + wx1 g11)) / 16  is the same float, bit for bit.
+template <int LEVEL, int SHT, bool UP = false>
 __global__ void __launch_bounds__(sift_blur_nt(SHT), 2) k_sift_blur(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ dog,
-                                                               float* __restrict__ dec, int w, int h) {
+                                                               float* __restrict__ dec, int w, int h, const uint8_t* __restrict__ gray = nullptr) {
     constexpr int R = sift_level_radius(LEVEL), K = 2 * R + 1, TW = 64, TH = sift_tile_h(LEVEL, SHT), SW = TW + 2 * R, SH = TH + 2 * R,
                   NO = TH / sift_blur_ng(SHT), NT = sift_blur_nt(SHT);
     extern __shared__ __align__(16) unsigned char sift_blur_smem_raw[];
@@ -143,7 +148,49 @@ __global__ void __launch_bounds__(sift_blur_nt(SHT), 2) k_sift_blur(const float*
     float (*rowf)[64 + 1] = reinterpret_cast<float (*)[64 + 1]>(sift_blur_smem_raw + (size_t)SHT * SIFT_BLUR_TSTRIDE * sizeof(float));
     const int bx = blockIdx.x * TW, by = blockIdx.y * TH;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    {
+    if (UP) {
+        // 1. the gray pixels the tile needs -- rows [r_lo, r_hi] x columns [c_lo, c_hi], at most 34 x 39 -- go to shared memory (the row-pass
+        //    buffer is still free); the bounds are the min / max of the (reflected) source coordinates, the same in every warp
+        // 2. every tile element is interpolated from four shared-memory bytes
+        const int gw = w >> 1, gh = h >> 1;
+        uint8_t* gt = reinterpret_cast<uint8_t*>(&rowf[0][0]);
+        constexpr int GTS = 48;                            // row stride of the staged gray tile
+        int x0[3], x1[3], wx0[3];                          // per lane column: the two source columns and the weight (in quarters) of the first
+        int c_lo = gw, c_hi = 0, r_lo = gh, r_hi = 0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int X = refl101(bx + min(lane + 32 * j, SW - 1) - R, w), kx = X >> 1;
+            if (X & 1) { x0[j] = kx; x1[j] = min(kx + 1, gw - 1); wx0[j] = 3; } else { x0[j] = max(kx - 1, 0); x1[j] = kx; wx0[j] = 1; }
+            c_lo = min(c_lo, x0[j]); c_hi = max(c_hi, x1[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < (SH + 31) / 32; ++j) {
+            const int Y = refl101(by + min(lane + 32 * j, SH - 1) - R, h), ky = Y >> 1;
+            r_lo = min(r_lo, (Y & 1) ? ky : max(ky - 1, 0)); r_hi = max(r_hi, (Y & 1) ? min(ky + 1, gh - 1) : ky);
+        }
+        c_lo = __reduce_min_sync(0xffffffffu, c_lo); c_hi = __reduce_max_sync(0xffffffffu, c_hi);
+        r_lo = __reduce_min_sync(0xffffffffu, r_lo); r_hi = __reduce_max_sync(0xffffffffu, r_hi);
+        const int nc = c_hi - c_lo + 1, nr = r_hi - r_lo + 1;
+        for (int i = tid; i < nr * nc; i += NT) {
+            const int r = i / nc, c = i - r * nc;
+            gt[r * GTS + c] = __ldg(gray + (size_t)(r_lo + r) * gw + c_lo + c);
+        }
+        __syncthreads();
+        for (int ty = warp; ty < SH; ty += NT / 32) {
+            const int Y = refl101(by + ty - R, h), ky = Y >> 1;
+            int y0, y1, wy0;
+            if (Y & 1) { y0 = ky; y1 = min(ky + 1, gh - 1); wy0 = 3; } else { y0 = max(ky - 1, 0); y1 = ky; wy0 = 1; }
+            const uint8_t* r0 = gt + (y0 - r_lo) * GTS - c_lo;
+            const uint8_t* r1 = gt + (y1 - r_lo) * GTS - c_lo;
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                if (lane + 32 * j < SW) {
+                    const int a = wx0[j], b = 4 - a;
+                    const int v = wy0 * (a * r0[x0[j]] + b * r0[x1[j]]) + (4 - wy0) * (a * r1[x0[j]] + b * r1[x1[j]]);
+                    tile[ty][lane + 32 * j] = __fmul_rn((float)v, 0.0625f);
+                }
+        }
+    } else {
         int gx[3];
 #pragma unroll
         for (int j = 0; j < 3; ++j) gx[j] = refl101(bx + lane + 32 * j - R, w);
@@ -1173,6 +1220,15 @@ static void launch_blur(const CUtensorMap* tm, const float* in, float* out, floa
     else launch_blur_sh<LEVEL, 64>(tm, in, out, dog, dec, w, h, s);
 }
 
+// level 0 of octave 0 straight from the gray frame (k_sift_blur<0, 64, true>)
+static void blur_base_from_gray(const uint8_t* d_gray, float* out, int w, int h, cudaStream_t s) {
+    cudaError_t attr;
+    constexpr int TH = sift_tile_h(0, 64);
+    BM_SMEM_OPTIN((k_sift_blur<0, 64, true>), sift_blur_smem(64), attr);
+    (void)attr;
+    BM_COUNT_LAUNCHES(1), k_sift_blur<0, 64, true><<<dim3((w + 63) / 64, (h + TH - 1) / TH), sift_blur_nt(64), sift_blur_smem(64), s>>>(nullptr, out, nullptr, nullptr, w, h, d_gray);
+}
+
 static void blur_level(const BmSift* o, int oc, int level, const float* in, float* out, float* dog, float* dec, int w, int h, cudaStream_t s) {
     const CUtensorMap* tm = (o->use_tma && o->tma_ok[oc][level]) ? &o->tmap[oc][level] : nullptr;
     switch (level) {
@@ -1202,6 +1258,7 @@ static void sift_make_tensor_maps(BmSift* o) {
     // A/B (profiles/r02_pyramid_tma_ab.md): the TMA form is not faster than the cp.async form at 1080p (the kernel is bound by the
     // FMA / LDS issue of its two passes, not by the tile fill), so it is opt-in: BM_SIFT_TMA=1
     o->use_tma = getenv("BM_SIFT_TMA") != nullptr && getenv("BM_SIFT_NO_TMA") == nullptr;
+    { const char* e = getenv("BM_SIFT_SEPARATE_UPSAMPLE"); o->separate_upsample = e && e[0] == '1'; }
     const bm_encode_tiled_fn encode = o->use_tma ? sift_encode_tiled() : nullptr;
     if (!encode) o->use_tma = false;
     for (int oc = 0; oc < o->lay.noct; ++oc) {
@@ -1250,10 +1307,12 @@ static cudaError_t sift_enqueue(BmSift* o, const uint8_t* d_gray, BmKeypoints* o
     SIFT_OK(cudaMemsetAsync(o->claim, 0, o->claim_words * 4, s3));
     const dim3 blk(32, 8);
     const int bw = 2 * o->w, bh = 2 * o->h;
-    BM_COUNT_LAUNCHES(1), k_sift_upsample<<<dim3((bw + 31) / 32, (bh + 31) / 32), blk, 0, s>>>(d_gray, o->w, o->h, o->up);
+    const bool fuse_up = !(o->use_tma && o->tma_ok[0][0]) && !o->separate_upsample;
+    if (!fuse_up) BM_COUNT_LAUNCHES(1), k_sift_upsample<<<dim3((bw + 31) / 32, (bh + 31) / 32), blk, 0, s>>>(d_gray, o->w, o->h, o->up);
     for (int oc = 0; oc < L.noct; ++oc) {
         const SiftOct& O = L.o[oc];
-        if (oc == 0) blur_level(o, oc, 0, o->up, o->pyr + O.g[0], nullptr, nullptr, O.w, O.h, s);
+        if (oc == 0 && fuse_up) blur_base_from_gray(d_gray, o->pyr + O.g[0], O.w, O.h, s);
+        else if (oc == 0) blur_level(o, oc, 0, o->up, o->pyr + O.g[0], nullptr, nullptr, O.w, O.h, s);
         // level 3 also writes the next octave's base (its 2x decimation)
         for (int l = 1; l <= 3; ++l)
             blur_level(o, oc, l, o->pyr + O.g[l - 1], o->pyr + O.g[l], o->pyr + O.d[l - 1], (l == 3 && oc + 1 < L.noct) ? o->pyr + L.o[oc + 1].g[0] : nullptr, O.w, O.h, s);
@@ -1301,10 +1360,12 @@ cudaError_t bm_sift_time_pyramid(BmSift* o, const uint8_t* d_gray, int reps, flo
     const int bw = 2 * o->w, bh = 2 * o->h;
     for (int r = -1; r < reps; ++r) {                      // r == -1: warm-up
         if (r == 0) cudaEventRecord(e0, s);
-        BM_COUNT_LAUNCHES(1), k_sift_upsample<<<dim3((bw + 31) / 32, (bh + 31) / 32), blk, 0, s>>>(d_gray, o->w, o->h, o->up);
+        const bool fuse_up = !(o->use_tma && o->tma_ok[0][0]) && !o->separate_upsample;
+        if (!fuse_up) BM_COUNT_LAUNCHES(1), k_sift_upsample<<<dim3((bw + 31) / 32, (bh + 31) / 32), blk, 0, s>>>(d_gray, o->w, o->h, o->up);
         for (int oc = 0; oc < L.noct; ++oc) {
             const SiftOct& O = L.o[oc];
-            if (oc == 0) blur_level(o, oc, 0, o->up, o->pyr + O.g[0], nullptr, nullptr, O.w, O.h, s);
+            if (oc == 0 && fuse_up) blur_base_from_gray(d_gray, o->pyr + O.g[0], O.w, O.h, s);
+            else if (oc == 0) blur_level(o, oc, 0, o->up, o->pyr + O.g[0], nullptr, nullptr, O.w, O.h, s);
             for (int l = 1; l <= 5; ++l)
                 blur_level(o, oc, l, o->pyr + O.g[l - 1], o->pyr + O.g[l], o->pyr + O.d[l - 1], (l == 3 && oc + 1 < L.noct) ? o->pyr + L.o[oc + 1].g[0] : nullptr, O.w, O.h, s);
         }
