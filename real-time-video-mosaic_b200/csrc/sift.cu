@@ -491,9 +491,10 @@ __global__ void __launch_bounds__(256) k_sift_extrema(SiftLayout lay, int o, con
 // Tiled form of phase 1 for octaves whose rows are 16-byte aligned (w % 4 == 0, w >= 64): 12 % of the samples pass the cheap
 // centre-column test, but 82 % of all warps hold at least one of them, so in the per-pixel kernel nearly every warp pays for the
 // (serialised, short-circuit) 26-neighbour test of every layer.  Here a CTA stages a 64 x 16 tile (+1 halo) of the 5 DoG planes in
-// shared memory with whole-row float4 loads, compacts the samples that pass the centre-column test into a CTA list and runs the
-// neighbour test densely over that list (24 independent shared loads + a max / min tree).  Found extrema are collected per CTA:
-// one atomic on the global list counter per CTA instead of one per warp.  Same conjunction as cv2's test, evaluated in another order.
+// shared memory with whole-row float4 loads; every WARP compacts the samples of its two tile rows that pass the centre-column test into
+// its own list and runs the neighbour test densely over it (24 independent shared loads + a max / min tree) -- two barriers per tile
+// (tile staged / tile free again), no CTA-wide list.  Found extrema are collected per CTA over all its tiles: one atomic on the global
+// list counter per CTA.  Same conjunction as cv2's test, evaluated in another order.
 #define EX_TW 64
 #define EX_TH 14                       // interior rows; 16 rows are staged (one float4 per thread and plane)
 #define EX_STRIDE 72                   // floats per tile row: [3] left halo, [4, 68) interior (16-byte aligned), [68] right halo
@@ -501,9 +502,9 @@ __global__ void __launch_bounds__(256) k_sift_extrema(SiftLayout lay, int o, con
 __global__ void __launch_bounds__(256) k_sift_extrema_tile(SiftLayout lay, int o, int kt, const float* __restrict__ pyr,
                                                            unsigned* __restrict__ raw, int* __restrict__ ctr) {
     __shared__ __align__(16) float sm[5][EX_TH + 2][EX_STRIDE];
-    __shared__ unsigned short s_list[EX_TW * EX_TH * 3];
+    __shared__ unsigned short s_list[8 * 2 * EX_TW * 3];           // per warp: its two tile rows x 64 columns x 3 layers
     __shared__ unsigned s_found[EX_FOUND_CAP];
-    __shared__ int s_n, s_nf, s_base;
+    __shared__ int s_nf, s_base;
     const SiftOct& O = lay.o[o];                                     // stays in the parameter bank
     const int w = O.w, h = O.h;
     const size_t pn = (size_t)w * h;                                 // the 5 DoG planes of an octave are consecutive (checked by the launcher)
@@ -515,7 +516,7 @@ __global__ void __launch_bounds__(256) k_sift_extrema_tile(SiftLayout lay, int o
     float* const my_sm = &sm[0][rr][4 + 4 * q];
     float* const my_halo = &sm[tid < 160 ? hl : 0][hr][side ? 4 + EX_TW : 3];
     const unsigned ebase = ((unsigned)rr << 8) | ((unsigned)(4 * q) << 2);
-    if (tid == 0) { s_n = 0; s_nf = 0; }
+    if (tid == 0) s_nf = 0;
     // a CTA walks kt vertically adjacent tiles: the per-thread address set-up is paid once
     for (int it = 0; it < kt; ++it) {
         const int y0 = (blockIdx.y * kt + it) * EX_TH - 1;           // tile row rr <-> image row y0 + rr
@@ -549,32 +550,32 @@ __global__ void __launch_bounds__(256) k_sift_extrema_tile(SiftLayout lay, int o
                 for (int l = 0; l < 5; ++l) d[l] = j == 0 ? d4[l].x : j == 1 ? d4[l].y : j == 2 ? d4[l].z : d4[l].w;
 #pragma unroll
                 for (int l0 = 1; l0 <= SIFT_LAYERS; ++l0) {
-                    const float v = d[l0], hi = fmaxf(d[l0 - 1], d[l0 + 1]), lo = fminf(d[l0 - 1], d[l0 + 1]);
-                    const bool pre = inside & ((v > 1.0f & v >= hi) | (v < -1.0f & v <= lo));
-                    mask |= (pre ? 1u : 0u) << (3 * j + l0 - 1);
+                    // v > 1 && v >= both neighbours  <=>  v >= max3(below, above, nextafter(1));  likewise for minima: 5 instructions
+                    const float v = d[l0];
+                    const float hi = fmaxf(fmaxf(d[l0 - 1], d[l0 + 1]), __int_as_float(0x3F800001));
+                    const float lo = fminf(fminf(d[l0 - 1], d[l0 + 1]), __int_as_float(0xBF800001));
+                    if (inside && (v >= hi || v <= lo)) mask |= 1u << (3 * j + l0 - 1);
                 }
             }
         }
-        {   // CTA list of the survivors: warp scan of the counts, one shared atomic per warp
-            const int cnt = __popc(mask);
-            int inc = cnt;
+        // warp list of the survivors (a warp owns two tile rows = 384 samples): warp scan of the counts, no CTA-wide step
+        unsigned short* const wl = s_list + (tid >> 5) * (2 * EX_TW * 3);
+        const int cnt = __popc(mask);
+        int inc = cnt;
 #pragma unroll
-            for (int dlt = 1; dlt < 32; dlt <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, dlt); if (lane >= dlt) inc += u; }
-            __syncthreads();                                           // counters are zero; the tile is complete
-            int base = 0;
-            if (lane == 31 && inc) base = atomicAdd(&s_n, inc);
-            base = __shfl_sync(0xffffffffu, base, 31);
-            int at = base + inc - cnt;
+        for (int dlt = 1; dlt < 32; dlt <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, dlt); if (lane >= dlt) inc += u; }
+        const int n = __shfl_sync(0xffffffffu, inc, 31);
+        {
+            int at = inc - cnt;
             while (mask) {
                 const unsigned b = __ffs(mask) - 1; mask &= mask - 1;
                 const unsigned j = (b * 11u) >> 5;                     // b / 3 for b < 12
-                s_list[at++] = (unsigned short)(ebase + (j << 2) + (b - 3u * j));
+                wl[at++] = (unsigned short)(ebase + (j << 2) + (b - 3u * j));
             }
         }
-        __syncthreads();
-        const int n = s_n;
-        for (int i = tid; i < n; i += 256) {
-            const unsigned e = s_list[i];
+        __syncthreads();                                               // the tile is complete (and this warp's list)
+        for (int i = lane; i < n; i += 32) {
+            const unsigned e = wl[i];
             const int l0 = (e & 3) + 1, col = (e >> 2) & 63, row = e >> 8;
             const float* __restrict__ ctrp = &sm[l0][row][4 + col];
             const float v = *ctrp;
@@ -599,19 +600,17 @@ __global__ void __launch_bounds__(256) k_sift_extrema_tile(SiftLayout lay, int o
                 }
             }
         }
-        __syncthreads();                                            // the tile and the list are free again; s_nf is final
-        const int nf = min(s_nf, EX_FOUND_CAP);
-        if (nf) {                                                   // (uniform) one atomic on the global list counter per CTA and tile
-            if (tid == 0) s_base = atomicAdd(&ctr[4], nf);
-            __syncthreads();
-            if (tid < nf) {
-                const int idx = s_base + tid;
-                if (idx < lay.raw_cap) raw[idx] = s_found[tid]; else ctr[2] = 1;
-            }
-        }
-        if (it + 1 < kt) {
-            __syncthreads();                                        // everybody has read s_n / s_nf / s_found
-            if (tid == 0) { s_n = 0; s_nf = 0; }
+        if (it + 1 < kt) __syncthreads();                           // the tile may be overwritten
+    }
+    // the extrema of all kt tiles leave the CTA together: one atomic on the global list counter per CTA
+    __syncthreads();
+    const int nf = min(s_nf, EX_FOUND_CAP);
+    if (nf) {
+        if (tid == 0) s_base = atomicAdd(&ctr[4], nf);
+        __syncthreads();
+        for (int i = tid; i < nf; i += 256) {
+            const int idx = s_base + i;
+            if (idx < lay.raw_cap) raw[idx] = s_found[i]; else ctr[2] = 1;
         }
     }
 }
