@@ -231,17 +231,25 @@ class VideMosaic:
         self._canvas_cache = None
         return st
 
-    def estimate_frame(self, frame, next_frame=None):
+    def estimate_frame(self, frame, next_frame=None, later_frames=()):
         """offline pair mode: features + matches + RANSAC against the previous frame, no validation / warp; the frame
         becomes the new previous.  Returns (status, H_rel or None, n_matches).  next_frame: the frame of the next call (its
-        upload overlaps this pair's estimation; pass the same array object next time)."""
+        upload overlaps this pair's estimation; pass the same array object next time).  later_frames: up to two frames after that one,
+        staged as well (their uploads start now, their features are computed during the next call)."""
         frame = self._check_frame(frame)
         nxt = None
+        keep = []
         if next_frame is not None:
-            self._next_frame_ref = self._check_frame(next_frame)
-            nxt = self._next_frame_ref.ctypes.data_as(C.c_void_p)
+            keep.append(self._check_frame(next_frame))
+            nxt = keep[0].ctypes.data_as(C.c_void_p)
         info = _lib.BmFrameInfo()
         st = _lib.check(self._lib.bm_estimate_frame(self._h, frame.ctypes.data_as(C.c_void_p), 0, nxt, C.byref(info)), "bm_estimate_frame")
+        if nxt is not None:
+            for f in later_frames:
+                f = self._check_frame(f)
+                _lib.check(self._lib.bm_prefetch_frame(self._h, f.ctypes.data_as(C.c_void_p), 0), "bm_prefetch_frame")
+                keep.append(f)
+        self._next_frame_ref = keep                                # the staged buffers stay alive / unchanged until they are consumed
         self.last_info = info
         H = np.array(info.H_rel, dtype=np.float64).reshape(3, 3) if st == _lib.BM_OK else None
         return st, H, info.n_matches

@@ -172,7 +172,8 @@ def estimate_pairs(frames, t_start, t_end, detector_type="sift", device=0, vm=No
         vm = VideMosaic(frames[t_start - 1], detector_type=detector_type, show_intermediate=False, visualize=False, device=device)
     st, Hs = [], []
     for t in range(t_start, t_end):
-        s, H, _ = vm.estimate_frame(frames[t], frames[t + 1] if t + 1 < t_end else None)      # next frame's upload overlaps
+        s, H, _ = vm.estimate_frame(frames[t], frames[t + 1] if t + 1 < t_end else None,            # the next frames' uploads and detects overlap
+                                    [frames[u] for u in (t + 2, t + 3) if u < t_end])
         st.append(s)
         Hs.append(H)
     if own:
