@@ -142,12 +142,20 @@ def touches_tile(H, frame_w, frame_h, y0, y1):
     return hi >= y0 and lo < y1
 
 
-def gather_tiles(tile, canvas_h, rank, world, dist=None):
+def gather_tiles(tile, canvas_h, rank, world, dist=None, out=None):
     """tile: torch uint8 (rows_r, Wc, 3) on this rank's device; returns the full canvas on every rank (all_gather; NCCL over
-    NVLink on the GPU box, gloo in the CPU tests).  Tiles are padded to the common size for the collective."""
+    NVLink on the GPU box, gloo in the CPU tests).  `out`: a preallocated (canvas_h, Wc, 3) tensor to gather into -- with equal tiles
+    the collective then writes the canvas in place (no padded staging copy, no concatenation, no allocation inside the call).
+    Otherwise tiles are padded to the common size for the collective."""
     import torch
     spans = [tile_rows(canvas_h, r, world) for r in range(world)]
     per = max(e - s for s, e in spans)
+    if out is not None and all(e - s == per for s, e in spans) and tile.is_contiguous() and out.is_contiguous():
+        if dist is None or world == 1:
+            out.copy_(tile)
+        else:
+            dist.all_gather_into_tensor(out.view(-1), tile.view(-1))
+        return out
     pad = torch.zeros((per,) + tuple(tile.shape[1:]), dtype=tile.dtype, device=tile.device)
     pad[:tile.shape[0]] = tile
     if dist is None or world == 1:
@@ -155,7 +163,11 @@ def gather_tiles(tile, canvas_h, rank, world, dist=None):
     else:
         parts = [torch.empty_like(pad) for _ in range(world)]
         dist.all_gather(parts, pad)
-    return torch.cat([parts[r][:spans[r][1] - spans[r][0]] for r in range(world)], dim=0)
+    full = torch.cat([parts[r][:spans[r][1] - spans[r][0]] for r in range(world)], dim=0)
+    if out is not None:
+        out.copy_(full)
+        return out
+    return full
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -150,7 +150,8 @@ def run_tiles(ctx, frames=48, warmup=3, size="3840x2160", canvas="16384x16384"):
     nseq = min(n, 12)                                        # frame CONTENT is recycled (irrelevant for throughput); poses are not
     base = DroneSweep(w, h, seed=77, ground=cv2.resize(ground, (2 * 4096, 2 * 4096)) if max(w, h) > 3000 else ground, max_step=40.0,
                       noise_sigma=2.0).frames(nseq)
-    fr = [base[t % nseq] for t in range(n)]
+    pinned = torch.from_numpy(np.stack(base)).pin_memory()   # host frames in pinned memory (DMA'd directly, like the other modes)
+    fr = [pinned[t % nseq].numpy() for t in range(n)]
     y0, y1 = sh.tile_rows(Hc, ctx.rank, ctx.world)
     # the camera climbs the whole canvas in n frames (so every row tile gets work), with a slow sideways weave and rotation
     Hs = []
@@ -165,13 +166,16 @@ def run_tiles(ctx, frames=48, warmup=3, size="3840x2160", canvas="16384x16384"):
     for t in range(0, warmup + 1):
         tiler.put(fr[t], Hs[t])
     tiler.sync()
+    full = torch.zeros((Hc, Wc, 3), dtype=torch.uint8, device=f"cuda:{ctx.local}")       # setup: the gather's destination, allocated and touched up front
+    _ = tiler.tile_tensor(); del _                           # setup: the export buffer of the tile comes out of torch's caching allocator afterwards
+    torch.cuda.synchronize()
     ctx.barrier()
     t0 = time.perf_counter()
     mine = sum(tiler.put(fr[t], Hs[t]) for t in range(warmup + 1, n))
     tile = tiler.tile_tensor()
     torch.cuda.synchronize()
     t_warp = ctx.max_over_ranks(time.perf_counter() - t0)
-    full = sh.gather_tiles(tile, Hc, ctx.rank, ctx.world, ctx.dist)
+    full = sh.gather_tiles(tile, Hc, ctx.rank, ctx.world, ctx.dist, out=full)
     torch.cuda.synchronize()
     dt = ctx.max_over_ranks(time.perf_counter() - t0)
     nbytes = int(full.numel())
