@@ -247,7 +247,9 @@ def headline(args, det, frames, dev_frames, pinned, ctx, lib, want_chain, sample
     # ---------------- leg 1b: the warp/blend chain alone (roofline) ----------------
     # same frames and pipeline, but detect of frame t+1 is ordered after the chain of frame t (no overlap), so the CUDA events
     # around the chain on its launching stream measure the chain and nothing else
-    if want_chain:
+    # (rank 0 only, the others wait at the barrier below: with 8 ranks launching at once on 4 host cores each, the host could not keep
+    # the idle GPU fed and the event interval measured launch gaps -- 0.32 ms instead of 0.126)
+    if want_chain and rank == 0:
         vmr = b200mosaic.VideMosaic(frames[0], detector_type=det, show_intermediate=False, visualize=False, device=local_rank)
         vmr.set_overlap(False)
         Kr = min(n - W - 2, 60)
@@ -260,6 +262,8 @@ def headline(args, det, frames, dev_frames, pinned, ctx, lib, want_chain, sample
         vmr.sync()
         out["chain"] = vmr.timing(reset=True)
         del vmr
+    if want_chain:
+        ctx.barrier()
 
     # ---------------- leg 2: end to end through the host-facing call ----------------
     vm2 = b200mosaic.VideMosaic(frames[0], detector_type=det, show_intermediate=False, visualize=False, device=local_rank)
