@@ -220,6 +220,11 @@ class VideMosaic:
         """enqueue half of process_frame (H2D + detect + match + RANSAC), no wait -- see bm_process_frame_begin"""
         _lib.check(self._lib.bm_process_frame_begin(self._h, C.c_void_p(host_ptr), 0), "bm_process_frame_begin")
 
+    def prefetch_ptr(self, host_ptr):
+        """stage a frame the caller will process soon (H2D + ingest now, detect-ahead during the next end_frame) -- bm_prefetch_frame;
+        up to three frames ahead, in processing order"""
+        _lib.check(self._lib.bm_prefetch_frame(self._h, C.c_void_p(host_ptr), 0), "bm_prefetch_frame")
+
     def begin_frame_device(self, dev_ptr):
         _lib.check(self._lib.bm_process_frame_begin_device(self._h, C.c_void_p(dev_ptr)), "bm_process_frame_begin_device")
 
