@@ -15,6 +15,8 @@ One "step" = one `process_frame` of the stitching hot path on the next synthetic
                 value / e2e are the MEDIAN region, min / max and the per-rank times are reported next to them.
  * <other detector>: the same legs for the detector that is not the headline (the metric names SIFT & ORB).
  * roofline_pyramid: the SIFT Gaussian + DoG pyramid alone (256 N algorithmic bytes per frame).
+ * clip       : BASELINE configs 1 / 2 -- the reference's own 592-frame clip through main.main()'s loop with the launcher's swaps, H.264
+                decode, finalisation and mosaic.jpg inside the wall-clock time; decode alone and the CPU port beside it (tools/bench_clip.py).
  * modes      : the sharded modes of SURVEY 8e over the N ranks of this launch -- 64 x 720p ORB streams (config 4), offline frame-pair
                 sharding with its all_gather (config 3 at N GPUs), 4K frames into a 32768^2 canvas in N row tiles + NCCL gather (config 5).
 N > 1: one process per GPU, each rank stitches its own independent sweep (streams sharded one per GPU, SURVEY.md 8e);
@@ -52,6 +54,7 @@ def parse_args():
     ap.add_argument("--regions", type=int, default=0, help="timed regions of exactly --steps steps each (0: min(5, 360 // steps))")
     ap.add_argument("--single-detector", action="store_true", help="skip the sub-record of the other detector")
     ap.add_argument("--no-modes", action="store_true", help="skip the sharded-mode records (configs 3 offline / 4 / 5)")
+    ap.add_argument("--no-clip", action="store_true", help="skip the real-clip record (configs 1 / 2 end to end with decode)")
     return ap.parse_args()
 
 
@@ -440,6 +443,14 @@ def main():
                 cpus[det] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                              "sample": f"first {nf - 1} frames of the same sweep ({dt:.1f} s), detector={det}, oracle.mosaic_ref.RefMosaic = the "
                                        f"reference's cv2 {cv2.__version__}/NumPy calls minus its display-only copies, cv2.setNumThreads({cores}), IPP on"}
+        # configs 1 / 2: the reference's own clip through main.main()'s loop with decode inside (tools/bench_clip.py), rank 0 only
+        clip = None
+        if not args.no_clip:
+            try:
+                import bench_clip
+                clip = bench_clip.clip_record(cpu_frames=0 if args.no_cpu_baseline else 30, repeat=3)
+            except Exception as ex:                     # reported, never silently dropped
+                clip = {"error": f"{type(ex).__name__}: {ex}"[:300]}
         finalize_cpu_ms = preview_cpu_ms = jpeg_cpu_ms = jpeg_same = None
         if cpus:                                          # the reference's own functions on the same canvas, same host
             from oracle import finalize as ofin
@@ -515,6 +526,8 @@ def main():
             line[det] = {"metric": f"mosaic frames/sec at {w}x{h}, detector={det} (same sweep, same legs as the headline)", "unit": "frames/s", **r}
         if modes is not None:
             line["modes"] = modes
+        if clip is not None:
+            line["clip"] = clip
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
