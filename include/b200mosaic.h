@@ -198,9 +198,14 @@ bm_status bm_match_l2_knn2_ratio(const float* h_des_q, int nq, const float* h_de
  * h_src/h_dst: n x 2 float32.  *ok = 0 means the reference would get None. */
 bm_status bm_ransac_homography(const float* h_src, const float* h_dst, int n, double thresh, int max_iters,
                                double confidence, double H[9], int* ok, int* iters, int* n_inliers);
-/* profiling variant: also returns SM cycle counts per phase (subsets, hypotheses, selection, refit sums, Jacobi, LM, total, -) */
+/* profiling variant: also returns SM cycle counts per phase (subsets, hypotheses, selection, refit sums, DLT, LM, total, -), the number of
+ * LM iterations and, in *jacobi_sweeps, bits 8-15: how many of them solved their system by eigen-decomposition (see below) */
 bm_status bm_ransac_profile(const float* h_src, const float* h_dst, int n, double thresh, int max_iters, double confidence,
                             double H[9], long long cycles[8], int* lm_iters, int* jacobi_sweeps);
+/* debug / parity tests: cv2 4.13's LM polish (nine parameters, cv::solve / cv::invert with DECOMP_EIG = eigen-decomposition + truncated
+ * back substitution) is evaluated through one SPD elimination per iteration whenever a bound proves that only the scale gauge is
+ * truncated, and through the literal eigen-decomposition otherwise; on != 0 forces the literal route for every iteration */
+bm_status bm_debug_lm_force_eig(int on);
 /* features / matches of the handle's last frame: which = 0 -> prev, 1 -> cur.  h_desc: uint8 n x 32 (ORB) or n x 128 (SIFT) */
 bm_status bm_get_keypoints(bm_handle h, int which, float* h_kp, uint8_t* h_desc, int cap, int* n_out);
 bm_status bm_get_matches(bm_handle h, int* h_q, int* h_t, float* h_dist, int cap, int* m_out);

@@ -110,25 +110,48 @@ def update_num_iters(p, ep, model_points, max_iters):
     return int(np.rint(num / denom))
 
 
+def _eig_pinv(A):
+    """What cv::solve / cv::invert do with DECOMP_EIG: symmetric eigen-decomposition (cv2 runs a Jacobi), then SVBkSb's back substitution,
+    which DROPS every eigenvalue with |w_i| <= 2 * DBL_EPSILON * sum(w) -- a truncated pseudo-inverse.  Returns (w, V, keep)."""
+    w, V = np.linalg.eigh(A)
+    keep = np.abs(w) > 2.0 * DBL_EPSILON * w.sum()
+    return w, V, keep
+
+
+def _solve_eig(A, b):
+    w, V, keep = _eig_pinv(A)
+    return V[:, keep] @ ((V[:, keep].T @ b) / w[keep])
+
+
+def _invert_eig_diag(A):
+    w, V, keep = _eig_pinv(A)
+    return (V[:, keep] ** 2) @ (1.0 / w[keep])
+
+
 def lm_refine(H, M, m, max_iters=10):
-    """LMSolver (calib3d levmarq.cpp) on the 8 free parameters with HomographyRefineCallback residuals."""
+    """LMSolver (calib3d levmarq.cpp: the lambda / lc schedule) with cv2 4.13's HomographyRefineCallback, which refines ALL NINE
+    elements of H (fundam.cpp asserts `J.cols == 9`; the classic callback fixed h33 = 1 and had 8 columns) and scales by 1 / h33
+    afterwards.  J^T J is therefore singular along the scale gauge h -> (1 + e) h, and what keeps the iteration defined is that
+    `solve(Ap, v, d, DECOMP_EIG)` / `invert(A, Ap, DECOMP_EIG)` are truncated pseudo-inverses (_eig_pinv).  On well-conditioned
+    consensus sets this converges to the same homography as the 8-parameter form; on ill-conditioned ones (inliers in a corner of the
+    frame) the two walk different paths in ten iterations -- pinned by tests/golden/ransac_illcond.npz (frame 359 of clip 01)."""
     M = M.astype(np.float64); m = m.astype(np.float64)
 
     def compute(h, want_j):
-        ww = 1.0 / (h[6] * M[:, 0] + h[7] * M[:, 1] + 1.0)
+        ww = 1.0 / (h[6] * M[:, 0] + h[7] * M[:, 1] + h[8])
         xi = (h[0] * M[:, 0] + h[1] * M[:, 1] + h[2]) * ww
         yi = (h[3] * M[:, 0] + h[4] * M[:, 1] + h[5]) * ww
         r = np.empty(2 * len(M)); r[0::2] = xi - m[:, 0]; r[1::2] = yi - m[:, 1]
         if not want_j:
             return r, None
-        J = np.zeros((2 * len(M), 8))
+        J = np.zeros((2 * len(M), 9))
         J[0::2, 0] = M[:, 0] * ww; J[0::2, 1] = M[:, 1] * ww; J[0::2, 2] = ww
-        J[0::2, 6] = -M[:, 0] * ww * xi; J[0::2, 7] = -M[:, 1] * ww * xi
+        J[0::2, 6] = -M[:, 0] * ww * xi; J[0::2, 7] = -M[:, 1] * ww * xi; J[0::2, 8] = -ww * xi
         J[1::2, 3] = M[:, 0] * ww; J[1::2, 4] = M[:, 1] * ww; J[1::2, 5] = ww
-        J[1::2, 6] = -M[:, 0] * ww * yi; J[1::2, 7] = -M[:, 1] * ww * yi
+        J[1::2, 6] = -M[:, 0] * ww * yi; J[1::2, 7] = -M[:, 1] * ww * yi; J[1::2, 8] = -ww * yi
         return r, J
 
-    x = H.ravel()[:8].copy()
+    x = H.ravel().copy()
     r, J = compute(x, True)
     S = float(r @ r)
     A = J.T @ J; v = J.T @ r
@@ -138,7 +161,7 @@ def lm_refine(H, M, m, max_iters=10):
     it = 0
     while True:
         Ap = A + np.diag(lam * D)
-        d = np.linalg.solve(Ap, v)
+        d = _solve_eig(Ap, v)
         xd = x - d
         rd, _ = compute(xd, False)
         Sd = float(rd @ rd)
@@ -154,8 +177,7 @@ def lm_refine(H, M, m, max_iters=10):
             nu = (Sd - S) / (t if abs(t) > DBL_EPSILON else 1.0) + 2.0
             nu = min(max(nu, 2.0), 10.0)
             if lam == 0.0:
-                Ai = np.linalg.inv(A)
-                maxval = max(DBL_EPSILON, float(np.abs(np.diag(Ai)).max()))
+                maxval = max(DBL_EPSILON, float(np.abs(_invert_eig_diag(A)).max()))
                 lam = lc = 1.0 / maxval
                 nu *= 0.5
             lam *= nu
@@ -167,8 +189,7 @@ def lm_refine(H, M, m, max_iters=10):
         it += 1
         if not (it < max_iters and np.abs(d).max() >= FLT_EPSILON and np.abs(r).max() >= FLT_EPSILON):
             break
-    out = np.ones(9); out[:8] = x
-    return out.reshape(3, 3)
+    return (x / x[8]).reshape(3, 3)
 
 
 def find_homography_ransac(src, dst, thresh=2.0, max_iters=2000, confidence=0.995, return_trace=False):

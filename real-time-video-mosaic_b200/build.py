@@ -48,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     OBJ.mkdir(exist_ok=True)
     LIBDIR.mkdir(exist_ok=True)
     srcs = sorted(CSRC.glob("*.cu"))
-    hdrs = sorted(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "b200mosaic.h"]
+    hdrs = sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [HERE.parent / "include" / "b200mosaic.h"]
     stamp = OBJ / "stamp.txt"
     dig = _digest(srcs + hdrs)
     if not force and LIB.exists() and stamp.exists() and stamp.read_text() == dig:

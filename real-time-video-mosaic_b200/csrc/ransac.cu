@@ -12,6 +12,7 @@
 // instructions (550 KB) and ran at ~80 cycles per instruction.  All small dense algebra therefore goes through ONE
 // non-inlined, non-unrolled routine (warp_solve) on a per-warp matrix in shared memory, and helpers are __noinline__.
 #include "ransac.cuh"
+#include "eig9.h"
 #include <float.h>
 #include <math.h>
 
@@ -334,50 +335,21 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_ransac_homography(const float
 #define RF_WARPS 4            // warp 0 runs the serial algebra; all four warps share the sums over the points (8 warps measured no faster)
 struct RfShared {
     double A[9][9], V[9];
-    double lmA[8][8], lmv[8], lmd[8], lmx[8], lmxd[8], lmD[8];
-    double M[9][10], X[9], P[9];
-    double G[9 * 18], Ainv[9][9];   // [A | I] elimination workspace, explicit inverse of the shifted LtL
-    double sums[46];
-    double wsum[RF_WARPS][46];      // per-warp partial sums of rf_accumulate
+    double lmA[9][9], lmv[9], lmd[9], lmx[9], lmxd[9], lmD[9], lmW[9];
+    double X[9], P[9];              // LM: unit gauge vector h / |h|, diagonal of the pseudo-inverse
+    double G[9 * 18], Ainv[9][9];   // [A | I] elimination workspace, explicit inverse (shifted LtL of the DLT; damped / deflated JtJ of the LM)
+    double sums[56];                // 0..44 upper triangle of a 9x9, 45..53 J^T r, 54 |r|^2, 55 max |r|
+    double wsum[RF_WARPS][56];      // per-warp partial sums of rf_accumulate
     const double* cmd_h;            // command block for the helper warps: parameter vector, Jacobian wanted, 0 = exit
     int cmd, cmd_want_j;
 };
 
-// Gauss-Jordan elimination WITHOUT pivoting of a symmetric positive definite NxN system M[r][0..N) | M[r][N] by one warp: every
-// lane owns up to three of the N*(N+1) augmented entries and all rows are eliminated at once, so a pivot step costs one
-// round of shared-memory reads instead of a serial loop over the rows (the stage-2 systems -- LtL + shift*I of the inverse
-// iteration, JtJ + lambda*diag of Levenberg-Marquardt -- are SPD, for which elimination without pivoting is as stable as
-// Cholesky).  Solution in X[0..N).  Returns false on a non-positive / non-finite pivot.
-__device__ __noinline__ bool warp_solve_spd(double (*M)[10], double* X, int N) {
-    const int lane = threadIdx.x & 31;
-    const int ne = N * (N + 1);
-    int er[3], ek[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) { const int e = lane + 32 * j; er[j] = e < ne ? e / (N + 1) : -1; ek[j] = e < ne ? e - er[j] * (N + 1) : 0; }
-    bool ok = true;
-    for (int c = 0; c < N; ++c) {
-        const double piv = M[c][c];
-        if (!(piv > 0.0) || !isfinite(piv)) ok = false;
-        const double inv = __drcp_rn(piv);
-        double nv[3];
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            nv[j] = 0.0;
-            if (er[j] >= 0 && er[j] != c && ek[j] > c) nv[j] = M[er[j]][ek[j]] - (M[er[j]][c] * inv) * M[c][ek[j]];
-        }
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 3; ++j) if (er[j] >= 0 && er[j] != c && ek[j] > c) M[er[j]][ek[j]] = nv[j];
-        __syncwarp();
-    }
-    if (lane < N) X[lane] = M[lane][N] / M[lane][lane];
-    __syncwarp();
-    return ok;
-}
-
-// The same elimination on an N x NC augmented matrix (row-major, NC > N): with [A | I] the right half becomes inv(A) once every
-// row is divided by its pivot.  Columns evolve independently, so column N + c equals the right-hand side of a separate solve of
-// A x = e_c bit for bit -- eight 8x8 solves or six 9x9 factorizations collapse into one pass.
+// Gauss-Jordan elimination WITHOUT pivoting of a symmetric positive definite N x N matrix by one warp: every lane owns a few entries
+// of the N x NC augmented matrix (row-major, NC > N) and all rows are eliminated at once, so a pivot step costs one round of
+// shared-memory reads instead of a serial loop over the rows (the stage-2 systems -- LtL + shift*I of the inverse iteration, the damped /
+// deflated JtJ of Levenberg-Marquardt -- are SPD, for which elimination without pivoting is as stable as Cholesky).  With [A | I] the
+// right half becomes inv(A) once every row is divided by its pivot.  Columns evolve independently, so column N + c equals the
+// right-hand side of a separate solve of A x = e_c bit for bit.  Returns false on a non-positive / non-finite pivot.
 template <int N, int NC>
 __device__ __noinline__ bool warp_gj_spd(double* M) {
     constexpr int EPL = (N * NC + 31) / 32;
@@ -427,33 +399,34 @@ __device__ __forceinline__ void rf_halve(double (&v)[64], int hi, int xor_mask) 
     }
 }
 
-// HomographyRefineCallback sums over this warp's share of the points (i = tid, tid + 128, ...): JtJ (36), JtR (8), |r|^2, max |r|.
-// The Jacobian rows are j0 = (Mx*ww, My*ww, ww, 0, 0, 0, -Mx*ww*xi, -My*ww*xi), j1 = (0, 0, 0, Mx*ww, My*ww, ww, -Mx*ww*yi, -My*ww*yi):
-// products with a structural zero are skipped; the sums use fused multiply-adds (cv2's own gemm order is not reproducible either --
-// the refined H is compared within 0.5 px, tests/test_features_gpu.py).
+// HomographyRefineCallback sums over this warp's share of the points (i = tid, tid + 128, ...): JtJ (45), JtR (9), |r|^2, max |r|.
+// cv2 4.13 refines ALL NINE elements of H (fundam.cpp: `J.cols == 9`; the classic callback fixed h33 = 1): with ww = 1 / (h6 Mx + h7 My + h8)
+// the Jacobian rows are j0 = (Mx*ww, My*ww, ww, 0, 0, 0, -Mx*ww*xi, -My*ww*xi, -ww*xi), j1 = (0, 0, 0, Mx*ww, My*ww, ww, -Mx*ww*yi,
+// -My*ww*yi, -ww*yi): products with a structural zero are skipped; the sums use fused multiply-adds (cv2's own gemm order is not
+// reproducible either -- the refined H is compared within 0.5 px, tests/test_features_gpu.py).
 __device__ __noinline__ void rf_partial(RfShared& sh, const float2* src, const float2* dst, const uint8_t* mask, int n, const double* h, bool want_j) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr bool nz0[8] = {true, true, true, false, false, false, true, true}, nz1[8] = {false, false, false, true, true, true, true, true};
-    double acc[45];
+    constexpr bool nz0[9] = {true, true, true, false, false, false, true, true, true}, nz1[9] = {false, false, false, true, true, true, true, true, true};
+    double acc[55];
 #pragma unroll
-    for (int k = 0; k < 45; ++k) acc[k] = 0.0;
+    for (int k = 0; k < 55; ++k) acc[k] = 0.0;
     double rmax = 0.0;
     for (int i = threadIdx.x; i < n; i += 32 * RF_WARPS) {
         if (!mask[i]) continue;
         const double Mx = src[i].x, My = src[i].y;
-        const double ww = __drcp_rn(h[6] * Mx + h[7] * My + 1.0);
+        const double ww = __drcp_rn(h[6] * Mx + h[7] * My + h[8]);
         const double xi = (h[0] * Mx + h[1] * My + h[2]) * ww, yi = (h[3] * Mx + h[4] * My + h[5]) * ww;
         const double rx = xi - (double)dst[i].x, ry = yi - (double)dst[i].y;
-        acc[44] += rx * rx + ry * ry;
+        acc[54] += rx * rx + ry * ry;
         rmax = fmax(rmax, fmax(fabs(rx), fabs(ry)));
         if (want_j) {
-            const double j0[8] = {Mx * ww, My * ww, ww, 0, 0, 0, -Mx * ww * xi, -My * ww * xi};
-            const double j1[8] = {0, 0, 0, Mx * ww, My * ww, ww, -Mx * ww * yi, -My * ww * yi};
+            const double j0[9] = {Mx * ww, My * ww, ww, 0, 0, 0, -Mx * ww * xi, -My * ww * xi, -ww * xi};
+            const double j1[9] = {0, 0, 0, Mx * ww, My * ww, ww, -Mx * ww * yi, -My * ww * yi, -ww * yi};
             int k = 0;
 #pragma unroll
-            for (int a = 0; a < 8; ++a) {
+            for (int a = 0; a < 9; ++a) {
 #pragma unroll
-                for (int b = a; b < 8; ++b) {
+                for (int b = a; b < 9; ++b) {
                     if (nz0[a] && nz0[b] && nz1[a] && nz1[b]) acc[k] = __fma_rn(j1[a], j1[b], __fma_rn(j0[a], j0[b], acc[k]));
                     else if (nz0[a] && nz0[b]) acc[k] = __fma_rn(j0[a], j0[b], acc[k]);
                     else if (nz1[a] && nz1[b]) acc[k] = __fma_rn(j1[a], j1[b], acc[k]);
@@ -461,31 +434,31 @@ __device__ __noinline__ void rf_partial(RfShared& sh, const float2* src, const f
                 }
             }
 #pragma unroll
-            for (int a = 0; a < 8; ++a) {
-                if (nz0[a] && nz1[a]) acc[36 + a] = __fma_rn(j1[a], ry, __fma_rn(j0[a], rx, acc[36 + a]));
-                else if (nz0[a]) acc[36 + a] = __fma_rn(j0[a], rx, acc[36 + a]);
-                else acc[36 + a] = __fma_rn(j1[a], ry, acc[36 + a]);
+            for (int a = 0; a < 9; ++a) {
+                if (nz0[a] && nz1[a]) acc[45 + a] = __fma_rn(j1[a], ry, __fma_rn(j0[a], rx, acc[45 + a]));
+                else if (nz0[a]) acc[45 + a] = __fma_rn(j0[a], rx, acc[45 + a]);
+                else acc[45 + a] = __fma_rn(j1[a], ry, acc[45 + a]);
             }
         }
     }
     for (int o = 16; o > 0; o >>= 1) rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
     if (want_j) {
-        // 45 sums over 32 lanes by recursive halving: at every step a lane hands one half of its values to its partner and adds
-        // the partner's copy of the other half -- 62 exchanges instead of 45 x 5 (the shuffle unit is the bottleneck of this kernel)
+        // 55 sums over 32 lanes by recursive halving: at every step a lane hands one half of its values to its partner and adds
+        // the partner's copy of the other half -- 62 exchanges instead of 55 x 5 (the shuffle unit is the bottleneck of this kernel)
         double v[64];
 #pragma unroll
-        for (int k = 0; k < 64; ++k) v[k] = k < 45 ? acc[k] : 0.0;
+        for (int k = 0; k < 64; ++k) v[k] = k < 55 ? acc[k] : 0.0;
         rf_halve<32>(v, lane & 16, 16); rf_halve<16>(v, lane & 8, 8); rf_halve<8>(v, lane & 4, 4); rf_halve<4>(v, lane & 2, 2);
         rf_halve<2>(v, lane & 1, 1);
-        if (2 * lane < 45) sh.wsum[warp][2 * lane] = v[0];            // lane L ends up with the totals of values 2L and 2L + 1
-        if (2 * lane + 1 < 45) sh.wsum[warp][2 * lane + 1] = v[1];
+        if (2 * lane < 55) sh.wsum[warp][2 * lane] = v[0];            // lane L ends up with the totals of values 2L and 2L + 1
+        if (2 * lane + 1 < 55) sh.wsum[warp][2 * lane + 1] = v[1];
     } else {
-        double x = acc[44];
+        double x = acc[54];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if (lane == 0) sh.wsum[warp][44] = x;
+        if (lane == 0) sh.wsum[warp][54] = x;
     }
-    if (lane == 0) sh.wsum[warp][45] = rmax;
+    if (lane == 0) sh.wsum[warp][55] = rmax;
 }
 
 // called by warp 0: wake the helper warps, take a share, combine the per-warp partials (fixed order: deterministic)
@@ -495,15 +468,30 @@ __device__ __noinline__ void rf_accumulate(RfShared& sh, const float2* src, cons
     __syncthreads();
     rf_partial(sh, src, dst, mask, n, h, want_j);
     __syncthreads();
-    for (int k = lane; k < 46; k += 32) {
-        if (!want_j && k < 44) continue;
+    for (int k = lane; k < 56; k += 32) {
+        if (!want_j && k < 54) continue;
         double t = sh.wsum[0][k];
 #pragma unroll
-        for (int w = 1; w < RF_WARPS; ++w) t = (k == 45) ? fmax(t, sh.wsum[w][k]) : t + sh.wsum[w][k];
+        for (int w = 1; w < RF_WARPS; ++w) t = (k == 55) ? fmax(t, sh.wsum[w][k]) : t + sh.wsum[w][k];
         sh.sums[k] = t;
     }
     __syncwarp();
 }
+
+// warp 0: the sums of the last rf_accumulate become the LM's normal matrix and gradient
+__device__ __forceinline__ void lm_adopt(RfShared& sh) {
+    const int lane = threadIdx.x & 31;
+    for (int t = lane; t < 45; t += 32) {          // unpack the upper triangle of JtJ
+        int a = 0, k = t;
+        while (k >= 9 - a) { k -= 9 - a; ++a; }
+        const int b = a + k;
+        sh.lmA[a][b] = sh.sums[t]; sh.lmA[b][a] = sh.sums[t];
+    }
+    if (lane < 9) sh.lmv[lane] = sh.sums[45 + lane];
+    __syncwarp();
+}
+
+__device__ int g_lm_force_eig = 0;              // debug / tests (bm_debug_lm_force_eig): always take the eigen-decomposition route below
 
 __global__ void __launch_bounds__(32 * RF_WARPS, 1) k_ransac_refine(const float2* __restrict__ gsrc, const float2* __restrict__ gdst, const int* __restrict__ countp,
                                                          const uint8_t* __restrict__ mask, BmRansacResult* __restrict__ out) {
@@ -634,63 +622,110 @@ __global__ void __launch_bounds__(32 * RF_WARPS, 1) k_ransac_refine(const float2
         }
     }
     const long long t_eig = clock64();
-    // ---- LMSolver(HomographyRefineCallback, maxIters = 10) on the 8 free parameters ----
+    // ---- LMSolver(HomographyRefineCallback, maxIters = 10) over all nine elements of H, scaled by 1 / h33 afterwards (cv2 4.13) ----
+    // J^T J is singular along the scale gauge h -> (1 + e) h.  cv2 solves (A + lambda diag(D)) d = v with cv::solve(DECOMP_EIG) and takes
+    // max |diag| of cv::invert(A, DECOMP_EIG): eigen-decomposition + a back substitution that drops every eigenvalue
+    // |w| <= 2 eps sum(w) = 2 eps trace -- a truncated pseudo-inverse.  Here: ONE elimination of [B | I] per iteration, B = the damped
+    // matrix (lambda > 0) or A + mu h^ h^T (lambda == 0: the gauge direction h^ = h / |h| is the exact null vector of J, deflated with
+    // mu = trace / 9 and projected out of the step again, which IS the pseudo-inverse with only the gauge dropped).  1 / |inv(B)|_F is a
+    // lower bound of B's smallest eigenvalue: above twice cv2's threshold nothing else can have been dropped and the step is exact;
+    // otherwise (ill-conditioned consensus sets: inliers in a corner of the frame) lane 0 runs the eigen-decomposition and applies
+    // cv2's rule literally (eig9.h).  No frame of the reference clip takes the second route; tests force it.
     __syncwarp();
     if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) sh.lmx[i] = bestH[i];
+        for (int i = 0; i < 9; ++i) sh.lmx[i] = bestH[i];
     }
     __syncwarp();
     rf_accumulate(sh, src, dst, mask, n, sh.lmx, true);
-    if (lane == 0) {
-        int k = 0;
-        for (int a = 0; a < 8; ++a) for (int b = a; b < 8; ++b) { sh.lmA[a][b] = sh.sums[k]; sh.lmA[b][a] = sh.sums[k]; ++k; }
-        for (int a = 0; a < 8; ++a) { sh.lmv[a] = sh.sums[36 + a]; sh.lmD[a] = sh.lmA[a][a]; }
-    }
+    lm_adopt(sh);
+    if (lane < 9) sh.lmD[lane] = sh.lmA[lane][lane];
     __syncwarp();
-    double S = sh.sums[44], rinf = sh.sums[45];
+    double sumD = 0;
+    for (int k = 0; k < 9; ++k) sumD += sh.lmD[k];
+    double S = sh.sums[54], rinf = sh.sums[55];
     double lambda = 1.0, lc = 0.75;
-    int it = 0;
+    const bool force_eig = g_lm_force_eig != 0;
+    int it = 0, n_eig = 0, last_sweeps = 0;
     while (true) {
-        if (lane < 8) {
-            for (int k = 0; k < 8; ++k) sh.M[lane][k] = sh.lmA[lane][k] + (k == lane ? lambda * sh.lmD[k] : 0.0);
-            sh.M[lane][8] = sh.lmv[lane];
+        double tr = 0;
+        for (int k = 0; k < 9; ++k) tr += sh.lmA[k][k];
+        const double thr = (tr + lambda * sumD) * (2.0 * DBL_EPSILON);      // cv2's truncation threshold for this system
+        const bool gauge = lambda == 0.0;
+        const double mu = tr / 9.0;
+        if (gauge) {
+            double nrm2 = 0;
+            for (int k = 0; k < 9; ++k) nrm2 += sh.lmx[k] * sh.lmx[k];
+            if (lane < 9) sh.X[lane] = sh.lmx[lane] / sqrt(nrm2);
         }
         __syncwarp();
-        const bool ok = warp_solve_spd(sh.M, sh.X, 8);
-        if (lane < 8) { const double d = ok ? sh.X[lane] : 0.0; sh.lmd[lane] = d; sh.lmxd[lane] = sh.lmx[lane] - d; }
+        for (int e = lane; e < 9 * 18; e += 32) {
+            const int r = e / 18, k = e - r * 18;
+            double val;
+            if (k < 9) {
+                val = sh.lmA[r][k];
+                if (k == r) val += lambda * sh.lmD[k];
+                if (gauge) val += mu * sh.X[r] * sh.X[k];
+            } else val = (k - 9 == r) ? 1.0 : 0.0;
+            sh.G[e] = val;
+        }
+        __syncwarp();
+        bool fast = warp_gj_spd<9, 18>(sh.G);
+        double fro2 = 0;
+        for (int e = lane; e < 81; e += 32) {
+            const int r = e / 9, k = e - r * 9;
+            const double bi = sh.G[r * 18 + 9 + k] / sh.G[r * 18 + r];
+            sh.Ainv[r][k] = bi; fro2 += bi * bi;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) fro2 += __shfl_xor_sync(0xffffffffu, fro2, o);
+        __syncwarp();
+        fast = fast && !force_eig && isfinite(fro2) && fro2 > 0.0 && (1.0 / sqrt(fro2) > 2.0 * thr);
+        if (fast) {
+            double d = 0;
+            if (lane < 9) for (int k = 0; k < 9; ++k) d = __fma_rn(sh.Ainv[lane][k], sh.lmv[k], d);
+            if (gauge) {
+                const double t = lane < 9 ? sh.X[lane] * d : 0.0;
+                double dot = 0;
+#pragma unroll
+                for (int a = 0; a < 9; ++a) dot += __shfl_sync(0xffffffffu, t, a);
+                if (lane < 9) { d -= sh.X[lane] * dot; sh.P[lane] = sh.Ainv[lane][lane] - sh.X[lane] * sh.X[lane] / mu; }
+            } else if (lane < 9) sh.P[lane] = sh.Ainv[lane][lane];
+            if (lane < 9) sh.lmd[lane] = d;
+        } else {
+            if (lane == 0) {
+                for (int r = 0; r < 9; ++r) for (int k = 0; k < 9; ++k) sh.G[r * 9 + k] = sh.lmA[r][k] + (k == r ? lambda * sh.lmD[k] : 0.0);
+                last_sweeps = bm_jacobi9(sh.G, sh.lmW, &sh.A[0][0]);
+                bm_eig_pinv9(sh.lmW, &sh.A[0][0], sh.lmv, sh.lmd, sh.P);
+            }
+            ++n_eig;
+        }
+        __syncwarp();
+        if (lane < 9) sh.lmxd[lane] = sh.lmx[lane] - sh.lmd[lane];
         __syncwarp();
         // error AND normal equations at the trial point in one pass over the points: when the step is accepted (the usual case) the
         // sums are simply adopted below instead of being recomputed (same code, same order: bit-identical to a second pass)
         rf_accumulate(sh, src, dst, mask, n, sh.lmxd, true);
-        const double Sd = sh.sums[44];
-        // dS = d . (-A d + 2 v), tdv = d . v: lane a forms row a, the eight terms are added in index order (as a serial loop would)
+        const double Sd = sh.sums[54];
+        // dS = d . (-A d + 2 v), tdv = d . v: lane a forms row a, the nine terms are added in index order (as a serial loop would)
         double ta = 0, ua = 0;
-        if (lane < 8) {
+        if (lane < 9) {
             double Ad = 0;
-            for (int b = 0; b < 8; ++b) Ad += sh.lmA[lane][b] * sh.lmd[b];
+            for (int b = 0; b < 9; ++b) Ad += sh.lmA[lane][b] * sh.lmd[b];
             ta = sh.lmd[lane] * (-Ad + 2.0 * sh.lmv[lane]);
             ua = sh.lmd[lane] * sh.lmv[lane];
         }
         double dS = 0, tdv = 0;
 #pragma unroll
-        for (int a = 0; a < 8; ++a) { dS += __shfl_sync(0xffffffffu, ta, a); tdv += __shfl_sync(0xffffffffu, ua, a); }
+        for (int a = 0; a < 9; ++a) { dS += __shfl_sync(0xffffffffu, ta, a); tdv += __shfl_sync(0xffffffffu, ua, a); }
         const double R = (S - Sd) / (fabs(dS) > DBL_EPSILON ? dS : 1.0);
         if (R > 0.75) { lambda *= 0.5; if (lambda < lc) lambda = 0.0; }
         else if (R < 0.25) {
             double nu = (Sd - S) / (fabs(tdv) > DBL_EPSILON ? tdv : 1.0) + 2.0;
             nu = fmin(fmax(nu, 2.0), 10.0);
             if (lambda == 0.0) {
-                double maxval = DBL_EPSILON;       // max |diag(inv(A))|: one elimination of [A | I]
-                for (int e = lane; e < 8 * 16; e += 32) {
-                    const int r = e >> 4, k = e & 15;
-                    sh.G[e] = k < 8 ? sh.lmA[r][k] : (k - 8 == r ? 1.0 : 0.0);
-                }
-                __syncwarp();
-                if (warp_gj_spd<8, 16>(sh.G)) {
-                    for (int c = 0; c < 8; ++c) maxval = fmax(maxval, fabs(sh.G[c * 16 + 8 + c] / sh.G[c * 16 + c]));
-                }
-                __syncwarp();
+                double maxval = DBL_EPSILON;       // max |diag(pinv(A))|: lambda == 0, so this iteration's decomposition is A's
+                for (int c = 0; c < 9; ++c) maxval = fmax(maxval, fabs(sh.P[c]));
                 lambda = lc = 1.0 / maxval;
                 nu *= 0.5;
             }
@@ -700,33 +735,29 @@ __global__ void __launch_bounds__(32 * RF_WARPS, 1) k_ransac_refine(const float2
         __syncwarp();
         if (accept) {
             S = Sd;
-            if (lane < 8) { sh.lmx[lane] = sh.lmxd[lane]; sh.lmv[lane] = sh.sums[36 + lane]; }
-            for (int t = lane; t < 36; t += 32) {          // unpack the upper triangle of JtJ
-                int a = 0, k = t;
-                while (k >= 8 - a) { k -= 8 - a; ++a; }
-                const int b = a + k;
-                sh.lmA[a][b] = sh.sums[t]; sh.lmA[b][a] = sh.sums[t];
-            }
-            __syncwarp();
-            rinf = sh.sums[45];
+            if (lane < 9) sh.lmx[lane] = sh.lmxd[lane];
+            lm_adopt(sh);
+            rinf = sh.sums[55];
         }
         ++it;
-        double dinf = lane < 8 ? fabs(sh.lmd[lane]) : 0.0;
+        double dinf = lane < 9 ? fabs(sh.lmd[lane]) : 0.0;
 #pragma unroll
-        for (int o = 4; o > 0; o >>= 1) dinf = fmax(dinf, __shfl_xor_sync(0xffffffffu, dinf, o));
+        for (int o = 8; o > 0; o >>= 1) dinf = fmax(dinf, __shfl_xor_sync(0xffffffffu, dinf, o));
         dinf = __shfl_sync(0xffffffffu, dinf, 0);
         if (!(it < 10 && dinf >= (double)FLT_EPSILON && rinf >= (double)FLT_EPSILON)) break;
     }
     if (lane == 0) {
-        for (int i = 0; i < 8; ++i) out->H[i] = sh.lmx[i];
+        for (int i = 0; i < 8; ++i) out->H[i] = sh.lmx[i] / sh.lmx[8];
         out->H[8] = 1.0;
-        out->ok = 1; out->lm_iters = it; out->jacobi_sweeps = eig_iters;
+        out->ok = 1; out->lm_iters = it; out->jacobi_sweeps = eig_iters | (n_eig << 8) | (last_sweeps << 16);
         out->cyc[4] = t_eig - t_start; out->cyc[5] = clock64() - t_eig; out->cyc[7] = clock64() - t_start;
         sh.cmd = 0;
     }
     __syncwarp();
     __syncthreads();                            // releases the helper warps (cmd == 0)
 }
+
+cudaError_t bm_lm_force_eig(int on) { return cudaMemcpyToSymbol(g_lm_force_eig, &on, sizeof(int)); }
 
 cudaError_t bm_launch_ransac(const float2* d_src, const float2* d_dst, const int* d_count, double thresh, int max_iters, double confidence,
                              uint8_t* d_mask, BmRansacResult* d_out, cudaStream_t s) {

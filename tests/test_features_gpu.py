@@ -221,27 +221,81 @@ def test_orb_process_frame_end_to_end(frames, golden_dir, capsys):
     assert capsys.readouterr().out == ""    # no warnings were printed on this clip (as in the reference run)
 
 
+def _lm_routes(lib):
+    """(lm_iters, iterations solved by eigen-decomposition) of the last profile call"""
+    import ctypes as C
+
+    def run(src, dst):
+        H = np.zeros(9); cyc = np.zeros(8, np.int64); lm = C.c_int(0); js = C.c_int(0)
+        rc = lib.bm_ransac_profile(src.ctypes.data_as(C.c_void_p), dst.ctypes.data_as(C.c_void_p), len(src), 2.0, 2000, 0.995,
+                                   H.ctypes.data_as(C.POINTER(C.c_double)), cyc.ctypes.data_as(C.c_void_p), C.byref(lm), C.byref(js))
+        assert rc == 0
+        return H.reshape(3, 3), lm.value, (js.value >> 8) & 0xFF
+    return run
+
+
 def test_ransac_ill_conditioned_polish(golden_dir):
-    """Frame 359 of clip 01 (ORB): the one frame of the 591 where the full-clip run leaves the reference's trajectory
-    (tests/test_clip_gpu.py).  The RANSAC stage is identical (same cv::RNG subsets, same 398-point consensus set after 16
-    iterations); the inliers cover only the right half of the frame, the 8x8 normal matrix of the LM polish has condition ~1e15
-    and cv2's LMSolver stops part-way down a flat valley while ours reaches its floor.  Pinned here: same consensus set, our
-    polished homography fits that set at least as well as cv2's, and the two agree to < 1 px ON the consensus points (they
-    differ by ~10 px when extrapolated to the far frame corners)."""
-    from b200mosaic import ops
+    """Frame 359 of clip 01 (ORB): the inliers (398 of 549) cover only the right half of the frame and the normal matrix of the LM polish
+    has condition ~1e15.  cv2 4.13 polishes ALL NINE elements of H (its callback asserts `J.cols == 9`) and solves the singular normal
+    equations with a truncated eigen pseudo-inverse; on this set ten iterations end part-way down a flat valley (residual 197.14 against a
+    floor of 193.45), 10 px away -- at the far frame corners -- from where an 8-parameter polish ends.  Pinned: the restatement and the
+    device (both of its solve routes) follow cv2 to that point."""
+    from b200mosaic import ops, _lib
     from oracle import ransac as orc
+    lib = _lib.load()
     g = np.load(golden_dir / "ransac_illcond.npz")
     src, dst, Hcv = g["src"], g["dst"], g["H_cv"]
-    H, iters, ninl = ops.ransac_homography(src, dst, 2.0)
     Ho, tr = orc.find_homography_ransac(src, dst, 2.0, return_trace=True)
-    assert iters == tr["iters"] == 16 and ninl == int(tr["mask"].sum()) == 398
-    assert np.abs(H - Ho).max() < 1e-6                                        # device == restatement
-    m = tr["mask"]
+    assert _reproj(Ho, Hcv, 854, 480) < 5e-3                                  # restatement == cv2 (measured 9e-4 px)
+    prof = _lm_routes(lib)
+    try:
+        for force in (0, 1):
+            assert lib.bm_debug_lm_force_eig(force) == 0
+            H, iters, ninl = ops.ransac_homography(src, dst, 2.0)
+            assert iters == tr["iters"] == 16 and ninl == int(tr["mask"].sum()) == 398
+            err = _reproj(H, Hcv, 854, 480)
+            Hp, lm_iters, n_eig = prof(src, dst)
+            print(f"ill-conditioned polish, force_eig={force}: {err:.2e} px from cv2 at the frame corners, {lm_iters} LM iterations, {n_eig} by eigen-decomposition")
+            assert err < 5e-3
+            assert np.array_equal(Hp, H) and lm_iters == 10 and (n_eig == lm_iters if force else n_eig <= lm_iters)
+    finally:
+        lib.bm_debug_lm_force_eig(0)
 
-    def proj(Hm, p):
-        q = np.c_[p, np.ones(len(p))] @ Hm.T
-        return q[:, :2] / q[:, 2:]
-    res_ours = np.sum((proj(H, src[m]) - dst[m]) ** 2)
-    res_cv = np.sum((proj(Hcv, src[m]) - dst[m]) ** 2)
-    assert res_ours <= res_cv
-    assert np.linalg.norm(proj(H, src[m]) - proj(Hcv, src[m]), axis=1).max() < 1.0
+
+@pytest.mark.parametrize("force", [0, 1])
+def test_ransac_polish_on_partial_coverage(force):
+    """consensus sets that cover the whole frame, a part of it, or one corner (ill-conditioned): the device polish (elimination route and
+    forced eigen-decomposition route) against cv2.findHomography, compared where the points are (inside their bounding box +- 25 %)"""
+    from b200mosaic import ops, _lib
+    lib = _lib.load()
+    prof = _lm_routes(lib)
+    rng = np.random.default_rng(11)
+    worst = 0.0
+    n_eig_total = 0
+    try:
+        assert lib.bm_debug_lm_force_eig(force) == 0
+        for case in range(36):
+            n = int(rng.integers(20, 500))
+            lo, hi = [((0, 0), (854, 480)), ((500, 100), (854, 300)), ((700, 0), (854, 60)), ((0, 0), (1920, 1080)), ((1500, 800), (1920, 1080)),
+                      ((0, 0), (3840, 2160))][case % 6]
+            P = rng.uniform(lo, hi, (n, 2))
+            Ht = np.array([[1 + rng.normal(0, .01), rng.normal(0, .01), rng.normal(0, 8)], [rng.normal(0, .01), 1 + rng.normal(0, .01), rng.normal(0, 8)],
+                           [rng.normal(0, 1e-6), rng.normal(0, 1e-6), 1]])
+            q = np.c_[P, np.ones(n)] @ Ht.T
+            Q = q[:, :2] / q[:, 2:] + rng.normal(0, 0.4, (n, 2))
+            src = P.astype(np.float32); dst = Q.astype(np.float32)
+            Hc, _ = cv2.findHomography(src.reshape(-1, 1, 2), dst.reshape(-1, 1, 2), cv2.RANSAC, 2.0)
+            H, lm_iters, n_eig = prof(src, dst)
+            assert Hc is not None and 1 <= lm_iters <= 10
+            n_eig_total += n_eig
+            assert n_eig == lm_iters if force else True
+            ext = 0.25 * (np.array(hi) - np.array(lo))
+            b0 = np.array(lo) - ext; b1 = np.array(hi) + ext
+            box = np.array([[b0[0], b0[1], 1], [b1[0], b0[1], 1], [b1[0], b1[1], 1], [b0[0], b1[1], 1.0]]).T
+            a = H @ box; b = Hc @ box
+            e = float(np.abs(a[:2] / a[2] - b[:2] / b[2]).max())
+            worst = max(worst, e)
+            assert e < 0.02, (case, n, e)
+    finally:
+        lib.bm_debug_lm_force_eig(0)
+    print(f"polish on partial coverage, force_eig={force}: worst {worst:.2e} px from cv2, {n_eig_total} eigen-decomposition iterations")
