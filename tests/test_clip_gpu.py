@@ -4,8 +4,9 @@ trajectory".
 
 ORB is bit-exact stage by stage INCLUDING keypoint order, so the trajectory must be the reference's: same status, same number of
 keypoints and matches on every frame, every absolute homography within 0.5 px corner reprojection (north_star's bar; measured
-here: < 1e-3 px -- RANSAC draws the same cv::RNG subsets from the same point order, the LM refit agrees to ~1e-9), and the canvas
-within a few grey levels (the blend itself is +-1 LSB per step against cv2, and the canvas is fed back 591 times).
+here: < 6e-5 px over the whole clip -- RANSAC draws the same cv::RNG subsets from the same point order, the nine-parameter LM polish
+follows cv2's to ~1e-9), and the final canvas within 1 grey level of the reference's (the blend itself is +-1 LSB per step against cv2,
+and the canvas is fed back 591 times).
 SIFT is tolerance-based by north_star (descriptors "within a stated L2 tolerance"), and the reference's own SIFT run is not
 repeatable: a SECOND run of the unmodified reference over this clip differs from the goldens by up to 0.88 px in the relative
 homographies (33 of 591 frames above 1e-3 px, 4 above 0.5 px, 1.15 px absolute drift; tests/golden/clip01_sift_repeatability.json) --
@@ -81,24 +82,20 @@ def test_orb_full_clip_equals_reference_run(golden_dir):
     print(f"ORB full clip: relative H: median {np.median(rel[1:]):.2e} px, {len(bad)} of {len(frames) - 1} frames above 1e-3 px {bad.tolist()} "
           f"(max {rel.max():.3f}); absolute H: max {err[:first_bad].max():.2e} px up to the first of them, {err.max():.3f} px after")
     # Same keypoints in the same order => same matches => same cv::RNG subsets => same consensus set on EVERY frame (asserted above
-    # through n_matches and below through the relative homographies).  The final LM polish (calib3d LMSolver) is the one step that
-    # cannot be pinned bit for bit: on frames whose inliers cover only part of the image the 8x8 normal matrix has condition ~1e15
-    # (frame 359 of this clip: smallest eigenvalue 0.045 against 6e13) and cv2's own result is decided by the rounding of its J^T J
-    # accumulation -- both polished homographies fit the consensus set equally well (tests/test_features_gpu.py::
-    # test_ransac_ill_conditioned_polish), but differ by pixels when extrapolated to the frame corners.  Stated bar: all but <= 1 %
-    # of the frames within 1e-3 px of the reference run (north_star: 0.5 px), none off by more than 16 px at the corners.
-    assert len(bad) <= 5 and rel.max() < 16.0
-    assert np.median(rel[1:]) < 1e-5 and err[:first_bad].max() < 1e-3
-    assert err.max() < 16.0
-    # canvas: identical up to the blend's +-1 LSB per step (fed back 591 times) as long as the trajectory is identical
+    # through n_matches), and the same LM polish: cv2 4.13 refines all nine elements of H with truncated eigen pseudo-inverses, which
+    # the device follows (ransac.cu; frame 359 of this clip, whose inliers cover half the frame, is where an 8-parameter polish ends
+    # 10 px away -- tests/test_features_gpu.py::test_ransac_ill_conditioned_polish).  Bar: EVERY frame within 1e-3 px of the reference
+    # run, relative and absolute (north_star: 0.5 px; measured: median 1e-9 px, max 5.6e-5 px absolute over the 591 composed steps).
+    assert len(bad) == 0 and np.median(rel[1:]) < 1e-5
+    assert err.max() < 1e-3
+    # canvas: identical up to the blend's +-1 LSB per step (fed back 591 times) -- measured: max 1 grey level at every checkpoint
     for i, t in enumerate(g["ckpt_idx"]):
         d = np.abs(ckpt[int(t)].astype(np.int16) - g["ckpt"][i].astype(np.int16))
         print(f"  canvas @ frame {int(t)}: max |diff| {d.max()}, > 1 level on {(d > 1).mean() * 100:.3f} % (2x downscaled)")
-        if t < first_bad:
-            assert d.max() <= 6 and (d > 1).mean() < 0.01, (int(t), int(d.max()), float((d > 1).mean()))
+        assert d.max() <= 3 and (d > 1).mean() < 1e-3, (int(t), int(d.max()), float((d > 1).mean()))
     d = np.abs(vm.output_img.astype(np.int16) - g["canvas_final"].astype(np.int16))
-    print(f"ORB final canvas: max |diff| {d.max()}, > 1 LSB on {(d > 1).mean() * 100:.3f} % of the samples, mean {d.mean():.4f}")
-    assert d.mean() < 1.0
+    print(f"ORB final canvas: max |diff| {d.max()}, > 1 LSB on {(d > 1).mean() * 100:.3f} % of the samples, differing {(d > 0).mean() * 100:.3f} %, mean {d.mean():.4f}")
+    assert d.max() <= 3 and (d > 1).mean() < 1e-3 and d.mean() < 0.02        # the reference's final mosaic, within the blend's own +-1 LSB
 
 
 def test_sift_full_clip_tracks_reference_run(golden_dir):

@@ -14,3 +14,7 @@ rng=np.random.default_rng(3); n=500
 s2=(rng.random((n,2))*[1920,1080]).astype(np.float32); Ht=np.array([[1.0,0.002,3],[-0.002,1.0,-11],[1e-7,2e-7,1]])
 p=np.c_[s2,np.ones(n)]@Ht.T; d2=(p[:,:2]/p[:,2:]+rng.normal(0,0.3,(n,2))).astype(np.float32)
 run(s2,d2)
+# a consensus set in one corner of the frame (ill-conditioned): some LM iterations take the eigen-decomposition route (bits 8-15 of "jacobi sweeps")
+s3=(rng.random((300,2))*[154,60]+[700,0]).astype(np.float32); p=np.c_[s3,np.ones(300)]@Ht.T; d3=(p[:,:2]/p[:,2:]+rng.normal(0,0.3,(300,2))).astype(np.float32)
+run(s3,d3)
+lib.bm_debug_lm_force_eig(1); run(s2,d2); lib.bm_debug_lm_force_eig(0)
