@@ -104,17 +104,43 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons)}
 
 
-def cpu_reference_fps(frames, detector, nthreads):
-    """The reference's CPU path (cv2 + NumPy, same calls as main.py's VideMosaic) on the given frames; frames/s."""
+def cpu_reference_fps(frames, detector, nthreads, stages=None):
+    """The reference's CPU path (cv2 + NumPy, same calls as main.py's VideMosaic) on the given frames; frames/s.
+    `stages` (a dict) receives the per-stage split SURVEY.md 8d asks for: seconds inside detectAndCompute, match, findHomography and
+    warp() (warpPerspective + blend) summed over the frames -- measured by timing wrappers around the port's own calls."""
     import cv2
     from oracle.mosaic_ref import RefMosaic
     cv2.setNumThreads(nthreads)
     cv2.ipp.setUseIPP(True)                       # timing runs keep IPP on (SURVEY.md 8d); parity runs switch it off
     m = RefMosaic(frames[0], detector_type=detector)
+    if stages is not None:
+        acc = {"detectAndCompute": 0.0, "match": 0.0, "findHomography": 0.0, "warp": 0.0}
+
+        def timed(name, fn):
+            def w(*a, **k):
+                t = time.perf_counter()
+                try:
+                    return fn(*a, **k)
+                finally:
+                    acc[name] += time.perf_counter() - t
+            return w
+
+        class Det:                                # cv2 feature objects do not take attributes: a pass-through with one timed method
+            def __init__(self, d):
+                self.detectAndCompute = timed("detectAndCompute", d.detectAndCompute)
+        m.detector = Det(m.detector)
+        m.match = timed("match", m.match)
+        m.findHomography = timed("findHomography", m.findHomography)
+        m.warp = timed("warp", m.warp)
     t0 = time.perf_counter()
     for i, f in enumerate(frames[1:], 1):
         m.process_frame(f, i)
     dt = time.perf_counter() - t0
+    if stages is not None:
+        nfr = max(len(frames) - 1, 1)
+        stages.update({k: 1e3 * v / nfr for k, v in acc.items()})
+        stages["other"] = 1e3 * (dt - sum(acc.values())) / nfr
+        stages["unit"] = "ms per frame"
     return (len(frames) - 1) / dt, dt
 
 
@@ -438,9 +464,10 @@ def main():
             cores = os.cpu_count() or 1
             nf = min(args.cpu_frames + 1, len(frames))
             for det in dets:
+                st = {}
                 with contextlib.redirect_stdout(io.StringIO()):
-                    fps, dt = cpu_reference_fps(frames[:nf], det, cores)
-                cpus[det] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                    fps, dt = cpu_reference_fps(frames[:nf], det, cores, st)
+                cpus[det] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "stages": st,
                              "sample": f"first {nf - 1} frames of the same sweep ({dt:.1f} s), detector={det}, oracle.mosaic_ref.RefMosaic = the "
                                        f"reference's cv2 {cv2.__version__}/NumPy calls minus its display-only copies, cv2.setNumThreads({cores}), IPP on"}
         # configs 1 / 2: the reference's own clip through main.main()'s loop with decode inside (tools/bench_clip.py), rank 0 only

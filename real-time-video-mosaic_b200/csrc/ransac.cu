@@ -491,6 +491,56 @@ __device__ __forceinline__ void lm_adopt(RfShared& sh) {
     __syncwarp();
 }
 
+// bm_jacobi9 (eig9.h) with the two 9-element loops of every rotation spread over nine lanes: lane k rotates row / column k of the matrix and
+// row k of the eigenvector matrix.  An element (k, p) or (k, q) is read and written by lane k only, so the values are those of the serial
+// loop bit for bit (--fmad=false: no contraction on either side); the rotation parameters are derived by every lane from the same three
+// shared-memory words.  a, v: shared memory, row-major 9x9.  ~3x faster than the serial form on one lane (-DBM_JACOBI_SERIAL).
+__device__ __noinline__ int jacobi9_warp(double* a, double* w, double* v) {
+    const int lane = threadIdx.x & 31;
+    constexpr int n = 9;
+    for (int i = lane; i < n * n; i += 32) v[i] = (i / n == i % n) ? 1.0 : 0.0;
+    __syncwarp();
+    int sweep = 0;
+    for (; sweep < 40; ++sweep) {
+        bool rotated = false;
+        for (int p = 0; p < n - 1; ++p) {
+            for (int q = p + 1; q < n; ++q) {
+                const double apq = a[p * n + q];
+                if (apq == 0.0) continue;
+                const double app = a[p * n + p], aqq = a[q * n + q];
+                __syncwarp();                       // every lane has read the three words before anybody writes them
+                if (fabs(apq) <= 1e-300 + 2.220446049250313e-19 * sqrt(fabs(app) * fabs(aqq))) {
+                    if (lane == 0) { a[p * n + q] = 0.0; a[q * n + p] = 0.0; }
+                    __syncwarp();
+                    continue;
+                }
+                rotated = true;
+                const double theta = (aqq - app) / (2.0 * apq);
+                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+                double np_ = 0, nq_ = 0, vp_ = 0, vq_ = 0;
+                if (lane < n) {
+                    const double akp = a[lane * n + p], akq = a[lane * n + q];
+                    np_ = c * akp - sn * akq; nq_ = sn * akp + c * akq;
+                    const double vp = v[lane * n + p], vq = v[lane * n + q];
+                    vp_ = c * vp - sn * vq; vq_ = sn * vp + c * vq;
+                }
+                __syncwarp();
+                if (lane < n) {
+                    if (lane != p && lane != q) { a[lane * n + p] = np_; a[p * n + lane] = np_; a[lane * n + q] = nq_; a[q * n + lane] = nq_; }
+                    v[lane * n + p] = vp_; v[lane * n + q] = vq_;
+                }
+                if (lane == 0) { a[p * n + p] = app - t * apq; a[q * n + q] = aqq + t * apq; a[p * n + q] = 0.0; a[q * n + p] = 0.0; }
+                __syncwarp();
+            }
+        }
+        if (!rotated) break;
+    }
+    if (lane < n) w[lane] = a[lane * n + lane];
+    __syncwarp();
+    return sweep;
+}
+
 __device__ int g_lm_force_eig = 0;              // debug / tests (bm_debug_lm_force_eig): always take the eigen-decomposition route below
 
 __global__ void __launch_bounds__(32 * RF_WARPS, 1) k_ransac_refine(const float2* __restrict__ gsrc, const float2* __restrict__ gdst, const int* __restrict__ countp,
@@ -693,11 +743,18 @@ __global__ void __launch_bounds__(32 * RF_WARPS, 1) k_ransac_refine(const float2
             } else if (lane < 9) sh.P[lane] = sh.Ainv[lane][lane];
             if (lane < 9) sh.lmd[lane] = d;
         } else {
+#ifdef BM_JACOBI_SERIAL
             if (lane == 0) {
                 for (int r = 0; r < 9; ++r) for (int k = 0; k < 9; ++k) sh.G[r * 9 + k] = sh.lmA[r][k] + (k == r ? lambda * sh.lmD[k] : 0.0);
                 last_sweeps = bm_jacobi9(sh.G, sh.lmW, &sh.A[0][0]);
                 bm_eig_pinv9(sh.lmW, &sh.A[0][0], sh.lmv, sh.lmd, sh.P);
             }
+#else
+            for (int e = lane; e < 81; e += 32) { const int r = e / 9, k = e - r * 9; sh.G[e] = sh.lmA[r][k] + (k == r ? lambda * sh.lmD[k] : 0.0); }
+            __syncwarp();
+            last_sweeps = jacobi9_warp(sh.G, sh.lmW, &sh.A[0][0]);
+            if (lane == 0) bm_eig_pinv9(sh.lmW, &sh.A[0][0], sh.lmv, sh.lmd, sh.P);
+#endif
             ++n_eig;
         }
         __syncwarp();
