@@ -15,6 +15,7 @@ One "step" = one `process_frame` of the stitching hot path on the next synthetic
                 value / e2e are the MEDIAN region, min / max and the per-rank times are reported next to them.
  * <other detector>: the same legs for the detector that is not the headline (the metric names SIFT & ORB).
  * roofline_pyramid: the SIFT Gaussian + DoG pyramid alone (256 N algorithmic bytes per frame).
+ * long_run   : configs[2] at its named length (2000 frames) end to end, one region on rank 0.
  * clip       : BASELINE configs 1 / 2 -- the reference's own 592-frame clip through main.main()'s loop with the launcher's swaps, H.264
                 decode, finalisation and mosaic.jpg inside the wall-clock time; decode alone and the CPU port beside it (tools/bench_clip.py).
  * modes      : the sharded modes of SURVEY 8e over the N ranks of this launch -- 64 x 720p ORB streams (config 4), offline frame-pair
@@ -54,6 +55,7 @@ def parse_args():
     ap.add_argument("--regions", type=int, default=0, help="timed regions of exactly --steps steps each (0: min(5, 360 // steps))")
     ap.add_argument("--single-detector", action="store_true", help="skip the sub-record of the other detector")
     ap.add_argument("--no-modes", action="store_true", help="skip the sharded-mode records (configs 3 offline / 4 / 5)")
+    ap.add_argument("--no-long-run", action="store_true", help="skip the 2000-frame run of configs[2] at its named length")
     ap.add_argument("--no-clip", action="store_true", help="skip the real-clip record (configs 1 / 2 end to end with decode)")
     return ap.parse_args()
 
@@ -323,6 +325,43 @@ def headline(args, det, frames, dev_frames, pinned, ctx, lib, want_chain, sample
     return out
 
 
+def long_run(det, frames, pinned, ctx, total=2000):
+    """BASELINE configs[2] at its NAMED length: 2000 frames through the host-facing call (pinned host frames, H2D + per-frame read-back
+    inside the timed region), one region, rank 0.  The frames are the sweep's resident ones walked forwards and backwards (a camera that
+    flies the same serpentine to and fro: consecutive frames stay <= 24 px apart, so every frame validates); a turn skips one frame so
+    that no frame appears twice among the current frame and the two staged right behind it (a third-ahead frame that equals the current
+    one is simply staged one call later)."""
+    import b200mosaic
+    torch = ctx.torch
+    h, w = frames[0].shape[:2]
+    fb = h * w * 3
+    n = len(frames)
+    seq, i, d = [], 1, 1
+    while len(seq) < total + 3:
+        seq.append(i)
+        if not 0 <= i + d < n:
+            d = -d
+            i += 2 * d
+        else:
+            i += d
+    vm = b200mosaic.VideMosaic(frames[0], detector_type=det, show_intermediate=False, visualize=False, device=ctx.local)
+    pbase = pinned.data_ptr()
+    vm.warm_up()
+    ramp_clocks(torch)
+    ok = 0
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for t in range(total):
+        ptrs = [pbase + seq[t + k] * fb if k <= LOOKAHEAD else None for k in (1, 2, 3)]
+        ok += vm.process_frame_ptr(pbase + seq[t] * fb, *ptrs) == 0
+    vm.sync()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    vm.close()
+    return {"what": f"configs[2] at its named length: {total} frames, detector={det}, end to end from pinned host frames (the resident sweep walked "
+                    f"to and fro), one timed region on rank 0", "frames": total, "frames_ok": int(ok), "seconds": dt, "e2e_frames_per_s": total / dt}
+
+
 def stats(xs):
     xs = sorted(xs)
     return {"min": xs[0], "median": xs[len(xs) // 2] if len(xs) % 2 else 0.5 * (xs[len(xs) // 2 - 1] + xs[len(xs) // 2]), "max": xs[-1]}
@@ -372,6 +411,14 @@ def main():
         res[det] = headline(args, det, frames, dev_frames, pinned, ctx, lib, want_chain=(di == 0), sample_clocks=(di == 0))
     main_det = dets[0]
     hm = res[main_det]
+    longrec = None
+    if not args.no_long_run:
+        if rank == 0:
+            try:
+                longrec = long_run(main_det, frames, pinned, ctx)
+            except Exception as ex:                     # reported, never silently dropped
+                longrec = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+        ctx.barrier()
 
     # SURVEY 8f rank 1 / 3 (outside the timed regions): finalisation and preview thumbnail of the final canvas on the device
     vm2 = hm["vm2"]
@@ -555,6 +602,8 @@ def main():
             line["modes"] = modes
         if clip is not None:
             line["clip"] = clip
+        if longrec is not None:
+            line["long_run"] = longrec
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
