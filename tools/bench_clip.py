@@ -116,14 +116,19 @@ def run_cpu(det, max_frames, cores):
     import cv2
     from oracle import finalize as ofin
     from oracle.mosaic_ref import RefMosaic
+    ipp0, thr0 = cv2.ipp.useIPP(), cv2.getNumThreads()
     cv2.setNumThreads(cores)
-    cv2.ipp.setUseIPP(True)
+    cv2.ipp.setUseIPP(True)                       # timing runs keep IPP on; the caller's setting is restored below
     ref = driver_module(cv2, ofin.crop_black_areas, ofin.scale_to_screen)
     ref.VideMosaic = lambda first, detector_type, **kw: RefMosaic(first, detector_type=detector_type)
-    with tempfile.TemporaryDirectory() as td, contextlib.redirect_stdout(io.StringIO()):
-        t0 = time.perf_counter()
-        ref.main(str(CLIP), det, td, max_frames=max_frames)
-        dt = time.perf_counter() - t0
+    try:
+        with tempfile.TemporaryDirectory() as td, contextlib.redirect_stdout(io.StringIO()):
+            t0 = time.perf_counter()
+            ref.main(str(CLIP), det, td, max_frames=max_frames)
+            dt = time.perf_counter() - t0
+    finally:
+        cv2.ipp.setUseIPP(ipp0)
+        cv2.setNumThreads(thr0)
     return {"frames": ref.log["frames"], "seconds": dt, "fps": ref.log["frames"] / dt, "cores": cores, "kind": "port",
             "sample": f"first {ref.log['frames']} frames of the clip through the same loop (decode, finalisation and mosaic.jpg inside), "
                       f"oracle.mosaic_ref.RefMosaic, cv2 {cv2.__version__}, cv2.setNumThreads({cores}), IPP on"}
