@@ -206,6 +206,9 @@ bm_status bm_ransac_profile(const float* h_src, const float* h_dst, int n, doubl
  * back substitution) is evaluated through one SPD elimination per iteration whenever a bound proves that only the scale gauge is
  * truncated, and through the literal eigen-decomposition otherwise; on != 0 forces the literal route for every iteration */
 bm_status bm_debug_lm_force_eig(int on);
+/* counters of the current CUDA device since the last reset (synchronises the device): out[0] polishes run, out[1] their LM iterations,
+ * out[2] the iterations among them that were solved by eigen-decomposition */
+bm_status bm_debug_lm_stats(unsigned long long out[3], int reset);
 /* features / matches of the handle's last frame: which = 0 -> prev, 1 -> cur.  h_desc: uint8 n x 32 (ORB) or n x 128 (SIFT) */
 bm_status bm_get_keypoints(bm_handle h, int which, float* h_kp, uint8_t* h_desc, int cap, int* n_out);
 bm_status bm_get_matches(bm_handle h, int* h_q, int* h_t, float* h_dist, int cap, int* m_out);

@@ -109,6 +109,7 @@ def load():
     _sig(lib, "bm_ransac_homography", i, vp, vp, i, C.c_double, i, C.c_double, dp, ip, ip, ip)
     _sig(lib, "bm_ransac_profile", i, vp, vp, i, C.c_double, i, C.c_double, dp, vp, ip, ip)
     _sig(lib, "bm_debug_lm_force_eig", i, i)
+    _sig(lib, "bm_debug_lm_stats", i, vp, i)
     _sig(lib, "bm_get_keypoints", i, vp, i, vp, vp, i, ip)
     _sig(lib, "bm_get_matches", i, vp, vp, vp, vp, i, ip)
     _sig(lib, "bm_keypoint_capacity", i)

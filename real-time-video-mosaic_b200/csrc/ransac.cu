@@ -541,6 +541,7 @@ __device__ __noinline__ int jacobi9_warp(double* a, double* w, double* v) {
     return sweep;
 }
 
+__device__ unsigned long long g_lm_stats[3];   // polishes run, LM iterations, iterations solved by eigen-decomposition (bm_debug_lm_stats)
 __device__ int g_lm_force_eig = 0;              // debug / tests (bm_debug_lm_force_eig): always take the eigen-decomposition route below
 
 __global__ void __launch_bounds__(32 * RF_WARPS, 1) k_ransac_refine(const float2* __restrict__ gsrc, const float2* __restrict__ gdst, const int* __restrict__ countp,
@@ -808,6 +809,7 @@ __global__ void __launch_bounds__(32 * RF_WARPS, 1) k_ransac_refine(const float2
         out->H[8] = 1.0;
         out->ok = 1; out->lm_iters = it; out->jacobi_sweeps = eig_iters | (n_eig << 8) | (last_sweeps << 16);
         out->cyc[4] = t_eig - t_start; out->cyc[5] = clock64() - t_eig; out->cyc[7] = clock64() - t_start;
+        atomicAdd(&g_lm_stats[0], 1ull); atomicAdd(&g_lm_stats[1], (unsigned long long)it); atomicAdd(&g_lm_stats[2], (unsigned long long)n_eig);
         sh.cmd = 0;
     }
     __syncwarp();
@@ -815,6 +817,13 @@ __global__ void __launch_bounds__(32 * RF_WARPS, 1) k_ransac_refine(const float2
 }
 
 cudaError_t bm_lm_force_eig(int on) { return cudaMemcpyToSymbol(g_lm_force_eig, &on, sizeof(int)); }
+
+cudaError_t bm_lm_stats(unsigned long long out[3], int reset) {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpyFromSymbol(out, g_lm_stats, 3 * sizeof(unsigned long long));
+    if (e == cudaSuccess && reset) { const unsigned long long z[3] = {0, 0, 0}; e = cudaMemcpyToSymbol(g_lm_stats, z, sizeof(z)); }
+    return e;
+}
 
 cudaError_t bm_launch_ransac(const float2* d_src, const float2* d_dst, const int* d_count, double thresh, int max_iters, double confidence,
                              uint8_t* d_mask, BmRansacResult* d_out, cudaStream_t s) {

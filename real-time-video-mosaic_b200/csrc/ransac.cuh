@@ -18,3 +18,5 @@ cudaError_t bm_launch_ransac(const float2* d_src, const float2* d_dst, const int
                              double confidence, uint8_t* d_mask, BmRansacResult* d_out, cudaStream_t s);
 // debug / tests: make every LM iteration of k_ransac_refine take the eigen-decomposition route (eig9.h)
 cudaError_t bm_lm_force_eig(int on);
+// counters of the current device since the last reset: polishes run, LM iterations, iterations that took the eigen-decomposition route
+cudaError_t bm_lm_stats(unsigned long long out[3], int reset);

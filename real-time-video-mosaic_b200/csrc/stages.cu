@@ -163,6 +163,13 @@ extern "C" bm_status bm_debug_lm_force_eig(int on) {
     return BM_OK;
 }
 
+extern "C" bm_status bm_debug_lm_stats(unsigned long long out[3], int reset) {
+    if (!out) return BM_ERR_ARG;
+    const cudaError_t e = bm_lm_stats(out, reset);
+    if (e != cudaSuccess) { bm_set_error("bm_debug_lm_stats: %s", cudaGetErrorString(e)); return BM_ERR_CUDA; }
+    return BM_OK;
+}
+
 extern "C" bm_status bm_ransac_homography(const float* h_src, const float* h_dst, int n, double thresh, int max_iters, double confidence,
                                           double H[9], int* ok, int* iters, int* n_inliers) {
     if (!H) return BM_ERR_ARG;

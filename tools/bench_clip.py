@@ -43,21 +43,31 @@ def driver_module(cv2, crop, scale):
     ref.log = {}
 
     def main(video_path, detector, output_dir, max_frames=None):
+        tm = time.perf_counter
+        t_a = tm()
         cap = ref.cv2.VideoCapture(video_path)                                   # main.py:1579
         ret, first = cap.read()
         vm = ref.VideMosaic(first, detector_type=detector, show_intermediate=False, output_dir=output_dir, visualize=False)   # :1603
         n = 0
+        t_b = tm()
+        t_read = t_proc = 0.0
         while cap.isOpened() and (max_frames is None or n < max_frames):
+            t0 = tm()
             ret, frame = cap.read()                                              # :1597
+            t1 = tm()
+            t_read += t1 - t0
             if not ret:
                 break
             n += 1
             vm.process_frame(frame, n)                                           # :1613
+            t_proc += tm() - t1
         cap.release()
+        t_c = tm()
         cropped = ref.crop_black_areas(vm.output_img, threshold=80, margin=30)   # :1649
         scaled = ref.scale_to_screen(cropped)                                    # :1656
         ref.cv2.imwrite(os.path.join(output_dir, "mosaic.jpg"), scaled)          # :1663-1665
-        ref.log.update(frames=n, vm=vm, scaled=scaled)
+        ref.log.update(frames=n, vm=vm, scaled=scaled,
+                       split={"setup_s": t_b - t_a, "read_s": t_read, "process_frame_s": t_proc, "finalize_and_write_s": tm() - t_c})
     ref.main = main
     return ref
 
@@ -77,8 +87,10 @@ def decode_only(cv2, max_frames=None):
 
 def run_b200(det, repeat, ahead=True):
     """the launcher's configuration (b200mosaic.run.main) around the stand-in driver; returns the per-run records"""
+    import ctypes as C
     import cv2
-    from b200mosaic import run as brun
+    from b200mosaic import run as brun, _lib
+    lib = _lib.load()
 
     def not_on_device(*a, **k):                   # the driver's own host crop / scale: reaching them means the device path was not taken
         raise RuntimeError("finalisation fell back to the host functions")
@@ -95,6 +107,8 @@ def run_b200(det, repeat, ahead=True):
                 ref.VideMosaic = brun.make_swapped_class(det, ahead=ahead)
                 brun.install_device_finalize(ref)
                 brun.LazyCanvas.materialized = 0
+                lm = np.zeros(3, np.uint64)
+                lib.bm_debug_lm_stats(lm.ctypes.data_as(C.c_void_p), 1)
                 t0 = time.perf_counter()
                 with contextlib.redirect_stdout(io.StringIO()) as warn:
                     ref.main(str(CLIP), det, td)
@@ -103,10 +117,12 @@ def run_b200(det, repeat, ahead=True):
                 cv2.VideoCapture = real_cap
             jpg = (Path(td) / "mosaic.jpg").read_bytes()
         vm = ref.log.pop("vm")
+        lib.bm_debug_lm_stats(lm.ctypes.data_as(C.c_void_p), 0)
         ok, enc = cv2.imencode(".jpg", ref.log["scaled"])
         runs.append({"frames": ref.log["frames"], "seconds": dt, "fps": ref.log["frames"] / dt, "mosaic_jpg_bytes": len(jpg),
                      "mosaic_jpg_identical_to_cv2_imencode": bool(ok and enc.tobytes() == jpg),
-                     "full_canvas_d2h": brun.LazyCanvas.materialized, "warnings_printed": warn.getvalue().count("\n")})
+                     "full_canvas_d2h": brun.LazyCanvas.materialized, "warnings_printed": warn.getvalue().count("\n"),
+                     "split": ref.log["split"], "polish": {"runs": int(lm[0]), "lm_iterations": int(lm[1]), "by_eigen_decomposition": int(lm[2])}})
         vm.close()
     return runs
 
@@ -151,7 +167,9 @@ def clip_record(cpu_frames=40, repeat=3, detectors=("sift", "orb")):
         rec[det] = {"fps": med["fps"], "seconds": med["seconds"], "frames": med["frames"], "fps_min_max": [runs[0]["fps"], runs[-1]["fps"]],
                     "mosaic_jpg_bytes": med["mosaic_jpg_bytes"],
                     "mosaic_jpg_identical_to_cv2_imencode": all(r["mosaic_jpg_identical_to_cv2_imencode"] for r in runs),
-                    "full_canvas_d2h": med["full_canvas_d2h"], "fraction_of_decode_rate": med["fps"] / (nd / td)}
+                    "full_canvas_d2h": med["full_canvas_d2h"], "fraction_of_decode_rate": med["fps"] / (nd / td),
+                    "polish": med["polish"], "split": med["split"],
+                    "runs": [{"fps": r["fps"], "seconds": r["seconds"]} for r in runs]}
         if cpu_frames > 0:
             rec[det]["cpu_baseline"] = run_cpu(det, cpu_frames, cores)
     return rec
