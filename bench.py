@@ -505,6 +505,15 @@ def main():
                 os.sched_setaffinity(0, all_cores)     # the CPU baseline may use every host core
             except OSError:
                 pass
+        # configs 1 / 2: the reference's own clip through main.main()'s loop with decode inside (tools/bench_clip.py), rank 0 only; before the CPU
+        # baselines below, whose 16 cv2 worker threads keep spinning for a while and would compete with the decode and launch threads
+        clip = None
+        if not args.no_clip:
+            try:
+                import bench_clip
+                clip = bench_clip.clip_record(cpu_frames=0 if args.no_cpu_baseline else 30, repeat=3)
+            except Exception as ex:                     # reported, never silently dropped
+                clip = {"error": f"{type(ex).__name__}: {ex}"[:300]}
         cpus = {}
         if not args.no_cpu_baseline:
             import cv2
@@ -517,14 +526,6 @@ def main():
                 cpus[det] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "stages": st,
                              "sample": f"first {nf - 1} frames of the same sweep ({dt:.1f} s), detector={det}, oracle.mosaic_ref.RefMosaic = the "
                                        f"reference's cv2 {cv2.__version__}/NumPy calls minus its display-only copies, cv2.setNumThreads({cores}), IPP on"}
-        # configs 1 / 2: the reference's own clip through main.main()'s loop with decode inside (tools/bench_clip.py), rank 0 only
-        clip = None
-        if not args.no_clip:
-            try:
-                import bench_clip
-                clip = bench_clip.clip_record(cpu_frames=0 if args.no_cpu_baseline else 30, repeat=3)
-            except Exception as ex:                     # reported, never silently dropped
-                clip = {"error": f"{type(ex).__name__}: {ex}"[:300]}
         finalize_cpu_ms = preview_cpu_ms = jpeg_cpu_ms = jpeg_same = None
         if cpus:                                          # the reference's own functions on the same canvas, same host
             from oracle import finalize as ofin
