@@ -29,14 +29,10 @@ struct RsShared {
     double bestH[9];
     double red[RS_WARPS][46];    // cross-warp reduction scratch
     double sums[46];
-    double A[9][9], V[9];        // DLT normal matrix, its smallest eigenvector
-    double lmA[8][8], lmv[8], lmd[8], lmx[8], lmxd[8], lmD[8];
     double M[RS_WARPS][9][10];   // per-warp augmented matrices for warp_solve
     double X[RS_WARPS][9];       // per-warp solutions
     double P[RS_WARPS][9];       // per-warp reciprocal pivots
     int niters, iter, best_good, stop, batch, fail_at;
-    int eig_iters;
-    double S;
 };
 
 __device__ __forceinline__ unsigned rng_next(unsigned long long& st) {
