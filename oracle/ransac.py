@@ -1,7 +1,8 @@
 """Restatement of cv2.findHomography(p_cur, p_prev, cv2.RANSAC, 2.0) as the reference calls it (main.py:856-857)
 (TEST INFRASTRUCTURE, see oracle/__init__.py).  OpenCV 4.x calib3d: RANSACPointSetRegistrator::run +
-HomographyEstimatorCallback + LMSolver refinement, from the published sources as pinned in SURVEY.md A.7; checked
-against live cv2 4.13 in tests/test_oracle_ransac_cpu.py."""
+HomographyEstimatorCallback + LMSolver refinement, from the published sources as pinned in SURVEY.md A.7 -- except the LM polish, which
+in cv2 4.13 runs over all nine elements of H with truncated eigen pseudo-inverses (established from the installed binary and by probing
+cv2.findHomography(method=0); see lm_refine and DESIGN.md section 2.1); checked against live cv2 4.13 in tests/test_oracle_features_cpu.py."""
 from __future__ import annotations
 
 import math
