@@ -2,7 +2,7 @@
 
     python real-time-video-mosaic_b200/build.py [--force] [--verbose]
 
-Objects go to csrc/_obj/, the library to lib/libb200mosaic.so (git-ignored, but it travels with gpurun).
+Objects go to csrc/_obj/, the library and its source-digest stamp to lib/ (git-ignored, but the directory travels with gpurun).
 """
 from __future__ import annotations
 
@@ -18,6 +18,7 @@ CSRC = HERE / "csrc"
 OBJ = CSRC / "_obj"
 LIBDIR = HERE / "lib"
 LIB = LIBDIR / "libb200mosaic.so"
+STAMP = LIBDIR / "stamp.txt"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v", "--fmad=false"] + os.environ.get("BM_EXTRA_NVCC_FLAGS", "").split()
@@ -44,29 +45,49 @@ def _compile(src: Path, verbose: bool) -> tuple[Path, str]:
     return obj, log
 
 
+def _up_to_date(dig: str) -> bool:
+    return LIB.exists() and STAMP.exists() and STAMP.read_text() == dig
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile csrc/*.cu and link lib/libb200mosaic.so unless lib/stamp.txt already carries the digest of the sources + flags.
+    The stamp lives NEXT TO the library (lib/ travels to the GPU box with the tree, csrc/_obj/ does not): a box that received an
+    up-to-date library loads it as is instead of recompiling in every process.  Builders are serialised by a file lock, so the N ranks of
+    a torchrun launch that all find a stale library compile once, not N times into the same object files."""
+    import fcntl
     OBJ.mkdir(exist_ok=True)
     LIBDIR.mkdir(exist_ok=True)
     srcs = sorted(CSRC.glob("*.cu"))
     hdrs = sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [HERE.parent / "include" / "b200mosaic.h"]
-    stamp = OBJ / "stamp.txt"
     dig = _digest(srcs + hdrs)
-    if not force and LIB.exists() and stamp.exists() and stamp.read_text() == dig:
+    if not force and _up_to_date(dig):
         return LIB
-    logs = []
-    with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
-        objs = []
-        for obj, log in ex.map(lambda s: _compile(s, verbose), srcs):
-            objs.append(obj)
-            logs.append(log)
-    (OBJ / "ptxas.log").write_text("\n".join(logs))
-    cmd = [NVCC, "-shared", "-o", str(LIB), *map(str, objs), "-cudart", "static", "-lcuda"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
-    stamp.write_text(dig)
-    if verbose:
-        print("\n".join(logs))
+    with open(LIBDIR / ".build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and _up_to_date(dig):          # another process built it while this one waited for the lock
+                return LIB
+            logs = []
+            with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+                objs = []
+                for obj, log in ex.map(lambda s: _compile(s, verbose), srcs):
+                    objs.append(obj)
+                    logs.append(log)
+            (OBJ / "ptxas.log").write_text("\n".join(logs))
+            tmp = LIBDIR / (LIB.name + f".tmp{os.getpid()}")
+            cmd = [NVCC, "-shared", "-o", str(tmp), *map(str, objs), "-cudart", "static", "-lcuda"]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                tmp.unlink(missing_ok=True)
+                raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+            if STAMP.exists():
+                STAMP.unlink()                          # never a stamp that vouches for a library it does not describe
+            os.replace(tmp, LIB)                        # atomic: a process that already mapped the old file keeps its inode
+            STAMP.write_text(dig)
+            if verbose:
+                print("\n".join(logs))
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 
