@@ -91,3 +91,18 @@ def test_validate_homography_single_native_implementation():
     assert reasons == {_lib.BM_VAL_OK, _lib.BM_VAL_NAN, _lib.BM_VAL_TRANSLATION, _lib.BM_VAL_SCALE, _lib.BM_VAL_PERSPECTIVE}
     assert _lib.validate_homography(neg)[0] == _lib.BM_VAL_OK
     assert _lib.validate_homography(None)[0] == _lib.BM_VAL_NAN
+
+
+def test_library_carries_its_source_digest():
+    """lib/stamp.txt (next to the library: lib/ travels to the GPU box, csrc/_obj/ does not) vouches for the binary: after load() the
+    stamp equals the digest of csrc + the public header + the nvcc flags, so a box that received the tree loads the library as is and a
+    stale binary is rebuilt (once: builders hold lib/.build.lock)"""
+    import importlib
+    import b200mosaic
+    b200mosaic.load()
+    bld = importlib.import_module("real-time-video-mosaic_b200.build")
+    srcs = sorted(bld.CSRC.glob("*.cu"))
+    hdrs = sorted(bld.CSRC.glob("*.cuh")) + sorted(bld.CSRC.glob("*.h")) + [bld.HERE.parent / "include" / "b200mosaic.h"]
+    assert bld.STAMP.parent == bld.LIB.parent
+    assert bld._up_to_date(bld._digest(srcs + hdrs))
+    assert not bld._up_to_date("something else")

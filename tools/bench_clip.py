@@ -169,7 +169,7 @@ def clip_record(cpu_frames=40, repeat=3, detectors=("sift", "orb")):
                     "mosaic_jpg_identical_to_cv2_imencode": all(r["mosaic_jpg_identical_to_cv2_imencode"] for r in runs),
                     "full_canvas_d2h": med["full_canvas_d2h"], "fraction_of_decode_rate": med["fps"] / (nd / td),
                     "polish": med["polish"], "split": med["split"],
-                    "runs": [{"fps": r["fps"], "seconds": r["seconds"]} for r in runs]}
+                    "runs": [{"fps": r["fps"], "seconds": r["seconds"], **r["split"]} for r in runs]}
     for det in detectors:                        # after every device run: cv2's 16-thread pool keeps spinning for a while and would steal the
         if cpu_frames > 0:                       # cores the decode thread and the launch thread of the next device run need
             rec[det]["cpu_baseline"] = run_cpu(det, cpu_frames, cores)

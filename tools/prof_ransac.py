@@ -8,7 +8,7 @@ def run(src,dst):
     H=np.zeros(9); cyc=np.zeros(8,np.int64); lm=C.c_int(0); js=C.c_int(0)
     for _ in range(2):
         _lib.check(lib.bm_ransac_profile(src.ctypes.data_as(C.c_void_p),dst.ctypes.data_as(C.c_void_p),len(src),2.0,2000,0.995,H.ctypes.data_as(C.POINTER(C.c_double)),cyc.ctypes.data_as(C.c_void_p),C.byref(lm),C.byref(js)))
-    print('n',len(src),'cycles: subsets %d hyp %d sel %d refit-sums %d jacobi %d LM %d total %d param %d'%tuple(cyc[:8]),'lm_iters',lm.value,'jacobi sweeps',js.value)
+    print('n',len(src),'cycles: subsets %d hyp %d sel %d refit-sums %d DLT %d LM %d total %d param %d'%tuple(cyc[:8]),'lm_iters',lm.value,'of which by eigen-decomposition',(js.value>>8)&255,'(sweeps of the last one %d)'%(js.value>>16),'DLT inverse-iteration steps',js.value&255)
 run(src,dst)
 rng=np.random.default_rng(3); n=500
 s2=(rng.random((n,2))*[1920,1080]).astype(np.float32); Ht=np.array([[1.0,0.002,3],[-0.002,1.0,-11],[1e-7,2e-7,1]])
