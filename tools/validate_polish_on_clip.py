@@ -6,7 +6,7 @@ sets are intercepted at findHomography and solved both ways.  Prints the corner 
     python tools/validate_polish_on_clip.py            (about 4 minutes on 8 cores)
 
 Result of the run behind DESIGN.md section 2.1: ORB 591 frames, max 8.9e-4 px (frame 359, the ill-conditioned one), median 1.7e-9 px;
-SIFT 591 frames, max 4.2e-7 px, median 4.1e-10 px."""
+SIFT 591 frames, max 4e-7 ... 5e-7 px (cv2's SIFT differs slightly from run to run), median 4e-10 px."""
 import contextlib
 import io
 import sys
