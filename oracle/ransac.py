@@ -111,12 +111,91 @@ def update_num_iters(p, ep, model_points, max_iters):
     return int(np.rint(num / denom))
 
 
+def cv_jacobi(A):
+    """cv::eigen of a symmetric matrix (OpenCV core/src/lapack.cpp, JacobiImpl_): classical Jacobi -- the pivot is the largest off-diagonal
+    element, found through per-row / per-column maxima that are refreshed for the two rotated indices only; rotation from
+    hypot(p, y) with y = (w_l - w_k) / 2; at most 30 n^2 rotations, stop at |pivot| <= DBL_EPSILON; eigenvalues sorted descending by
+    selection sort, eigenvectors in ROWS.  Matches cv2.eigen to an ulp (tests/test_oracle_features_cpu.py) and -- what matters here --
+    keeps the RELATIVE accuracy of the small eigenvalues, which LAPACK's tridiagonal QR (np.linalg.eigh) loses at condition 1e15."""
+    A = np.array(A, dtype=np.float64)
+    n = len(A)
+    V = np.eye(n)
+    W = np.diag(A).copy()
+    ind_r = [0] * n
+    ind_c = [0] * n
+
+    def row_max(k):
+        m = k + 1; mv = abs(A[k, m])
+        for i in range(k + 2, n):
+            v = abs(A[k, i])
+            if mv < v:
+                mv = v; m = i
+        return m
+
+    def col_max(k):
+        m = 0; mv = abs(A[0, k])
+        for i in range(1, k):
+            v = abs(A[i, k])
+            if mv < v:
+                mv = v; m = i
+        return m
+
+    for k in range(n):
+        if k < n - 1:
+            ind_r[k] = row_max(k)
+        if k > 0:
+            ind_c[k] = col_max(k)
+    for _ in range(n * n * 30 if n > 1 else 0):
+        k = 0; mv = abs(A[0, ind_r[0]])
+        for i in range(1, n - 1):
+            v = abs(A[i, ind_r[i]])
+            if mv < v:
+                mv = v; k = i
+        l = ind_r[k]
+        for i in range(1, n):
+            v = abs(A[ind_c[i], i])
+            if mv < v:
+                mv = v; k = ind_c[i]; l = i
+        p = A[k, l]
+        if abs(p) <= DBL_EPSILON:
+            break
+        y = (W[l] - W[k]) * 0.5
+        t = abs(y) + math.hypot(p, y)
+        s = math.hypot(p, t)
+        c = t / s
+        s = p / s; t = (p / t) * p
+        if y < 0:
+            s = -s; t = -t
+        A[k, l] = 0.0
+        W[k] -= t; W[l] += t
+        for (i0, j0, i1, j1) in ([(i, k, i, l) for i in range(0, k)] + [(k, i, i, l) for i in range(k + 1, l)]
+                                 + [(k, i, l, i) for i in range(l + 1, n)]):
+            a0 = A[i0, j0]; b0 = A[i1, j1]
+            A[i0, j0] = a0 * c - b0 * s; A[i1, j1] = a0 * s + b0 * c
+        vk = V[k].copy(); vl = V[l].copy()
+        V[k] = vk * c - vl * s; V[l] = vk * s + vl * c
+        for idx in (k, l):
+            if idx < n - 1:
+                ind_r[idx] = row_max(idx)
+            if idx > 0:
+                ind_c[idx] = col_max(idx)
+    for k in range(n - 1):
+        m = k
+        for i in range(k + 1, n):
+            if W[m] < W[i]:
+                m = i
+        if k != m:
+            W[[m, k]] = W[[k, m]]; V[[m, k]] = V[[k, m]]
+    return W, V
+
+
 def _eig_pinv(A):
-    """What cv::solve / cv::invert do with DECOMP_EIG: symmetric eigen-decomposition (cv2 runs a Jacobi), then SVBkSb's back substitution,
-    which DROPS every eigenvalue with |w_i| <= 2 * DBL_EPSILON * sum(w) -- a truncated pseudo-inverse.  Returns (w, V, keep)."""
-    w, V = np.linalg.eigh(A)
+    """What cv::solve / cv::invert do with DECOMP_EIG: symmetric eigen-decomposition (cv_jacobi), then SVBkSb's back substitution,
+    which DROPS every eigenvalue with |w_i| <= 2 * DBL_EPSILON * sum(w) -- a truncated pseudo-inverse.  Returns (w, V, keep), eigenvectors
+    in the columns of V."""
+    w, Vr = cv_jacobi(A)
     keep = np.abs(w) > 2.0 * DBL_EPSILON * w.sum()
-    return w, V, keep
+    return w, Vr.T, keep
 
 
 def _solve_eig(A, b):

@@ -87,7 +87,7 @@ def test_lm_polish_is_cv2s_nine_parameter_form(golden_dir):
     H, tr = rs.find_homography_ransac(src, dst, 2.0, return_trace=True)
     m = tr["mask"]
     assert tr["iters"] == 16 and int(m.sum()) == 398
-    assert _reproj(H, Hcv, 854, 480) < 5e-3                     # measured 9e-4 px (LAPACK's eigenvalues against cv2's Jacobi at cond 1e15)
+    assert _reproj(H, Hcv, 854, 480) < 1e-5                     # measured 1.4e-8 px (9e-4 with LAPACK's eigh in place of cv2's Jacobi: cond 1e15)
     q = np.c_[src[m].astype(np.float64), np.ones(int(m.sum()))] @ H.T
     res = float(np.sum((q[:, :2] / q[:, 2:] - dst[m]) ** 2))
     assert abs(res - 197.136) < 0.01
@@ -106,7 +106,22 @@ def test_lm_polish_is_cv2s_nine_parameter_form(golden_dir):
         Hm = rs.lm_refine(rs.run_kernel(P32, Q32), P32, Q32)
         box = np.array([[lo[0], lo[1], 1], [hi[0], lo[1], 1], [hi[0], hi[1], 1], [lo[0], hi[1], 1.0]]).T
         a = Hm @ box; b = Hc @ box
-        assert np.abs(a[:2] / a[2] - b[:2] / b[2]).max() < 1e-2, case
+        assert np.abs(a[:2] / a[2] - b[:2] / b[2]).max() < 1e-3, case
+
+
+def test_cv_jacobi_is_cv2_eigen():
+    """oracle.ransac.cv_jacobi restates the Jacobi inside cv::eigen / cv::solve(DECOMP_EIG): same eigenvalues and row eigenvectors as
+    cv2.eigen to a few ulps, including the tiny eigenvalues of badly scaled matrices (where the pseudo-inverse's truncation rule looks)"""
+    rng = np.random.default_rng(0)
+    for case in range(8):
+        n = [2, 3, 5, 9, 9, 9, 9, 9][case]
+        B = rng.normal(size=(n, n)); A = B @ B.T
+        if case >= 4:
+            d = np.diag(10.0 ** rng.uniform(-3, 6, n)); A = d @ A @ d
+        ok, w, v = cv2.eigen(A)
+        W, V = rs.cv_jacobi(A)
+        assert np.all(np.abs(W - w.ravel()) <= 1e-11 * np.abs(w.ravel()) + 1e-300)     # RELATIVE, eigenvalue by eigenvalue (measured <= 4e-13)
+        assert np.abs(V - v).max() < 1e-12
 
 
 def test_rng_first_draws():
