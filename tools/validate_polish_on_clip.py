@@ -5,8 +5,8 @@ sets are intercepted at findHomography and solved both ways.  Prints the corner 
 
     python tools/validate_polish_on_clip.py            (about 4 minutes on 8 cores)
 
-Result of the run behind DESIGN.md section 2.1: ORB 591 frames, max 8.9e-4 px (frame 359, the ill-conditioned one), median 1.7e-9 px;
-SIFT 591 frames, max 4e-7 ... 5e-7 px (cv2's SIFT differs slightly from run to run), median 4e-10 px."""
+Result of the run behind DESIGN.md section 2.1: ORB 591 frames, max 3.4e-6 px, median 9.5e-10 px (frame 359, the ill-conditioned one: 1.4e-8 px);
+SIFT 591 frames, max 3.5e-7 px, median 3e-13 px.  (With np.linalg.eigh in place of the restated cv2 Jacobi: ORB max 8.9e-4 px at frame 359.)"""
 import contextlib
 import io
 import sys
