@@ -246,7 +246,7 @@ def test_ransac_ill_conditioned_polish(golden_dir):
     g = np.load(golden_dir / "ransac_illcond.npz")
     src, dst, Hcv = g["src"], g["dst"], g["H_cv"]
     Ho, tr = orc.find_homography_ransac(src, dst, 2.0, return_trace=True)
-    assert _reproj(Ho, Hcv, 854, 480) < 5e-3                                  # restatement == cv2 (measured 9e-4 px)
+    assert _reproj(Ho, Hcv, 854, 480) < 5e-3                                  # restatement == cv2 (measured 1.4e-8 px with the restated cv2 Jacobi)
     prof = _lm_routes(lib)
     try:
         for force in (0, 1):
