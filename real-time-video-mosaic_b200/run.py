@@ -228,7 +228,8 @@ def install_device_finalize(ref):
     scaled = scale_to_screen(cropped)  (main.py:1647-1659).  Under this launcher `video_mosaic.output_img` is a LazyCanvas:
     crop_black_areas recognises it and runs bm_finalize on the device WITHOUT fetching the canvas; it returns a zero-copy
     placeholder of the cropped SHAPE (main() only prints it) that carries the device result, scale_to_screen returns that result.
-    Any other use of the two functions (or a failure of the device path) falls through to the reference's implementation."""
+    Any other use of the two functions (plain ndarrays, explicit target sizes) goes to the reference's implementation; a FAILURE of the
+    device path raises -- there is no silent host fallback."""
     import numpy as np
     ref_crop, ref_scale = ref.crop_black_areas, ref.scale_to_screen
 
@@ -237,14 +238,11 @@ def install_device_finalize(ref):
 
     def crop_black_areas(image, threshold=15, margin=5):
         if isinstance(image, LazyCanvas):
-            try:
-                out = image._vm.finalize(threshold, margin)
-                x, y, w, h = image._vm.last_crop_rect
-                ph = np.lib.stride_tricks.as_strided(np.zeros(1, np.uint8), shape=(h, w, 3), strides=(0, 0, 0)).view(_Placeholder)
-                ph._b200_result = out
-                return ph
-            except Exception:
-                image = np.asarray(image)
+            out = image._vm.finalize(threshold, margin)
+            x, y, w, h = image._vm.last_crop_rect
+            ph = np.lib.stride_tricks.as_strided(np.zeros(1, np.uint8), shape=(h, w, 3), strides=(0, 0, 0)).view(_Placeholder)
+            ph._b200_result = out
+            return ph
         return ref_crop(image, threshold, margin)
 
     def scale_to_screen(image, target_w=None, target_h=None):
@@ -262,7 +260,8 @@ def install_device_imwrite(ref):
     """main() ends with cv2.imwrite(os.path.join(output_dir, 'mosaic.jpg'), scaled_mosaic) (main.py:1664-1665; navigation_map.jpg at
     :1696-1697 likewise).  Inside the reference module only, `cv2` becomes a pass-through proxy whose imwrite encodes 3-channel 8-bit
     images going to .jpg / .jpeg with default parameters on the device (`ops.jpeg_encode`: the same bytes libjpeg writes) and hands
-    everything else -- other formats, explicit parameters, any failure of the device path -- to the real cv2.imwrite."""
+    everything else -- other formats, explicit parameters -- to the real cv2.imwrite.  A failure of the device encoder raises (no
+    silent host fallback); an unwritable path returns False like cv2.imwrite does."""
     import numpy as np
     from . import ops
     real = ref.cv2
@@ -275,15 +274,13 @@ def install_device_imwrite(ref):
         def imwrite(path, img, params=None):
             if (params is None and isinstance(img, np.ndarray) and img.dtype == np.uint8 and img.ndim == 3 and img.shape[2] == 3
                     and img.size > 0 and str(path).lower().endswith((".jpg", ".jpeg"))):
+                data = ops.jpeg_encode(img)
                 try:
-                    data = ops.jpeg_encode(img)
                     with open(path, "wb") as f:
                         f.write(data)
                     return True
                 except OSError:
                     return False                         # cv2.imwrite reports an unwritable path the same way
-                except Exception:
-                    pass
             return real.imwrite(path, img) if params is None else real.imwrite(path, img, params)
 
     ref.cv2 = _Cv2Proxy()
