@@ -5,7 +5,7 @@
 // Sequential semantics kept on a parallel evaluator: the cv::RNG stream, the subset rejection rules, "first strictly
 // better hypothesis wins" and the adaptive iteration cap are evaluated in iteration order by one thread, while the
 // expensive parts -- 4-point solves and inlier counting of a batch of hypotheses (one per warp), the 45-term normal
-// equation sums of the refit and of each LM step -- run across the CTA.
+// equation sums of the refit and the 55 sums of each (nine-parameter, cv2 4.13) LM step -- run across the CTA.
 //
 // Code-size note (measured, see profiles/): the kernel is executed by 16 warps once per frame, so every instruction is
 // fetched cold.  A first version with fully unrolled register-resident 8x8 / 9x9 algebra compiled to 34k SASS
